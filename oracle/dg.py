@@ -308,31 +308,64 @@ class Geometry:
                     fC[indf] = cC[index0] if fm <= 1 else cC[index1]
                     fN[indf] = fN[indf] * wgt
 
-        # ---- Jinv (dg.cpp:413-476) ----
+        # ---- Jinv (dg.cpp:413-476), same accumulation and product order as the reference ----
         D = [b.D(0), b.D(1), b.D(2)]
         X = cC[: self.gBCSfield].reshape(nB, NPX, NPY, NPZ, 3)
-        # J[a, d] = sum_m x_m[a] * dpsi_d(q <- m)   (mul(cC[index1], dpsi_ij) = outer(x, dpsi))
-        J = np.zeros((nB, NPX, NPY, NPZ, 3, 3))
-        J[..., 0] = np.einsum("si,cijka->csjka", D[0], X)
-        J[..., 1] = np.einsum("sj,cijka->ciska", D[1], X)
-        J[..., 2] = np.einsum("sk,cijka->cijsa", D[2], X)
+        J = np.zeros((nB, NPX, NPY, NPZ, 3, 3))          # J[a,d] = sum_m x_m[a]*dpsi_d ; mul(cC[index1], dpsi_ij)
+        for ii in range(NPX):
+            for jj in range(NPY):
+                for kk in range(NPZ):
+                    Jq = J[:, ii, jj, kk]
+                    for i in range(NPX):
+                        Jq[:, :, 0] += X[:, i, jj, kk] * D[0][ii, i]
+                        if i == ii:
+                            Jq[:, :, 1] += X[:, i, jj, kk] * D[1][jj, jj]
+                            Jq[:, :, 2] += X[:, i, jj, kk] * D[2][kk, kk]
+                    for j in range(NPY):
+                        if j != jj:
+                            Jq[:, :, 1] += X[:, ii, j, kk] * D[1][jj, j]
+                    for k in range(NPZ):
+                        if k != kk:
+                            Jq[:, :, 2] += X[:, ii, jj, k] * D[2][kk, k]
         J = J.reshape(-1, 3, 3)
-        JT = np.swapaxes(J, 1, 2)
-        A = JT @ J
+
+        def mul33(p, q):       # mul(Tensor,Tensor), tensor.cpp:42-58
+            r = np.empty_like(p)
+            for a in range(3):
+                for c in range(3):
+                    r[:, a, c] = (p[:, a, 0] * q[:, 0, c] + p[:, a, 1] * q[:, 1, c]) + p[:, a, 2] * q[:, 2, c]
+            return r
+
+        def inv33(p):          # inv(Tensor), tensor.cpp:152-168
+            r = np.empty_like(p)
+            r[:, 0, 0] = p[:, 1, 1] * p[:, 2, 2] - p[:, 1, 2] * p[:, 2, 1]
+            r[:, 1, 1] = p[:, 0, 0] * p[:, 2, 2] - p[:, 0, 2] * p[:, 2, 0]
+            r[:, 2, 2] = p[:, 0, 0] * p[:, 1, 1] - p[:, 0, 1] * p[:, 1, 0]
+            r[:, 0, 1] = p[:, 0, 2] * p[:, 2, 1] - p[:, 0, 1] * p[:, 2, 2]
+            r[:, 0, 2] = p[:, 0, 1] * p[:, 1, 2] - p[:, 0, 2] * p[:, 1, 1]
+            r[:, 1, 0] = p[:, 1, 2] * p[:, 2, 0] - p[:, 1, 0] * p[:, 2, 2]
+            r[:, 1, 2] = p[:, 0, 2] * p[:, 1, 0] - p[:, 0, 0] * p[:, 1, 2]
+            r[:, 2, 0] = p[:, 1, 0] * p[:, 2, 1] - p[:, 1, 1] * p[:, 2, 0]
+            r[:, 2, 1] = p[:, 0, 1] * p[:, 2, 0] - p[:, 0, 0] * p[:, 2, 1]
+            d = (p[:, 0, 0] * r[:, 0, 0] + p[:, 0, 1] * r[:, 1, 0]) + p[:, 0, 2] * r[:, 2, 0]
+            return r / d[:, None, None]
+
+        JT = np.swapaxes(J, 1, 2).copy()
+        A = mul33(JT, J)
         if NPX == 1:
             A[:, 0, 0] = 1
         if NPY == 1:
             A[:, 1, 1] = 1
         if NPZ == 1:
             A[:, 2, 2] = 1
-        A = np.linalg.inv(A)
+        A = inv33(A)
         if NPX == 1:
             A[:, 0, 0] = 0
         if NPY == 1:
             A[:, 1, 1] = 0
         if NPZ == 1:
             A[:, 2, 2] = 0
-        Ji = np.swapaxes(A @ JT, 1, 2)
+        Ji = np.swapaxes(mul33(A, JT), 1, 2).copy()
         self.Jinv33 = Ji                                           # (gBCSfield,3,3) row-major [a,d]
         self.Jinv = Ji.reshape(-1, 9)[:, T9_FLAT]                  # reference AoS component order
 
