@@ -1,0 +1,144 @@
+/* nsem_c.h -- C ABI of libnsem_cuda.so: the B200 (sm_100a) replacement for the compute bodies of
+ * NebulaSEM's explicit dGSEM Euler path.
+ *
+ * The reference has no plugin/FFI boundary (its operator API is C++ templates in src/field/field.h used
+ * directly by apps/euler/euler.cpp).  This header IS the boundary the drop-in introduces: the host side
+ * (nebulasem_b200/csrc/host, the `euler` app mirror) keeps the reference's surface and calls these entry
+ * points instead of running the OpenMP/OpenACC loops.  Each entry cites the reference code it replaces
+ * (file:line relative to the NebulaSEM tree).
+ *
+ * Conventions: every function returns 0 on success, non-zero on error (message via nsem_last_error);
+ * host arrays are borrowed for the duration of the call; device memory is owned by the context; one host
+ * thread per context; array layouts are the reference's (AoS Vector = 3, Tensor = 9 doubles per node in
+ * XX,YY,ZZ,XY,YZ,XZ,YX,ZY,ZX order, node index = cell*NP + i*NPY*NPZ + j*NPZ + k, src/field/dg.h:43-44;
+ * all indices uint32 like `Int`, src/tensor/types.h:9).
+ */
+#ifndef NSEM_C_H
+#define NSEM_C_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nsem_ctx nsem_ctx;
+
+/* Boundary-condition kinds that reach the explicit path (src/field/field.h:129-141, 2674-2719). */
+enum nsem_bc_kind {
+    NSEM_BC_NONE = 0,
+    NSEM_BC_NEUMANN = 1,      /* ghost = owner + value*|dx|, |dx| = 0 for DG ghost nodes (field.h:2674-2676) */
+    NSEM_BC_DIRICHLET = 2,    /* ghost = value (field.h:2688-2689) */
+    NSEM_BC_SYMMETRY = 3,     /* ghost = sym(owner, fN) (field.h:2681-2682, tensor.h:483-494) */
+    NSEM_BC_CYCLIC = 4,       /* ghost = owner value on the paired patch face (field.h:2683-2687) */
+    NSEM_BC_GHOST = 5,        /* inter-partition face: filled by the halo exchange (field.h:2605-2606, 2255-2324) */
+    NSEM_BC_FIXED = 6,        /* frozen per-node values: CALC_DIRICHLET/POWER/LOG/PARABOLIC/INVERSE after their
+                                 first evaluation (field.h:2691-2718) */
+    NSEM_BC_ROBIN = 7         /* ghost = shape*value + (1-shape)*(owner + tvalue*|dx|) (field.h:2677-2680) */
+};
+
+/* Field ids for BC tables and op-level calls. */
+enum nsem_field { NSEM_F_RHO = 0, NSEM_F_P = 1, NSEM_F_U = 2, NSEM_F_T = 3, NSEM_F_COUNT = 4 };
+
+/* Geometry + connectivity exactly as Mesh::initGeomMeshFields / DG::init_geom leave them
+ * (src/field/field.cpp:171-280, src/field/dg.cpp:167-477). */
+typedef struct {
+    uint32_t n_cells_real;        /* gBCS */
+    uint32_t n_cells_all;         /* gNCells = real + boundary ("ghost") cells */
+    uint32_t n_faces;             /* gNFacets */
+    const double* cV;             /* [n_cells_all*NP] nodal mass (dg.cpp:315-318) */
+    const double* Jinv;           /* [n_cells_real*NP*9] (dg.cpp:413-476) */
+    const double* fN;             /* [n_faces*NPF*3] weighted area vectors (dg.cpp:359) */
+    const double* fI;             /* [n_faces*NPF] owner weight: 0.5 interior/inter-rank, 0 physical boundary
+                                     (field.cpp:257-270) */
+    const double* face_normal;    /* [n_faces*3] un-weighted gFN (mesh.cpp:476-502); fN = face_normal * w_a*w_b/4 */
+    const uint32_t* FO;           /* [n_faces*NPF] owner node of each face node, sentinel n_cells_all*NP */
+    const uint32_t* FN;           /* [n_faces*NPF] neighbour node */
+    const uint32_t* face_begin;   /* [n_cells_all] faceIndices[0] (field.cpp:178-193) */
+    const uint32_t* face_end;     /* [n_cells_all] faceIndices[1] */
+    const uint32_t* all_faces;    /* [face_end[n_cells_all-1]] */
+    const uint32_t* face_id;      /* [same] gFaceID flattened: local face id 0..5 (mesh.cpp:161-446) */
+    const uint32_t* face_owner;   /* [n_faces] gFOC */
+    const uint32_t* face_neigh;   /* [n_faces] gFNC */
+    const uint32_t* face_mortar;  /* [n_faces] gFMC (0 = conforming) */
+} nsem_mesh;
+
+/* One boundary patch's condition for one field (BCondition<T>, field.h:144-173). */
+typedef struct {
+    int32_t field;                /* enum nsem_field */
+    int32_t kind;                 /* enum nsem_bc_kind */
+    uint32_t n_faces;
+    const uint32_t* faces;        /* patch face list (gBoundaries[name]) */
+    const uint32_t* peer_faces;   /* CYCLIC: faces of the `neighbor` patch, same length (field.h:2662-2664) */
+    double value[3];              /* value (scalar in [0]) */
+    double shape;
+    double tvalue[3];
+    double tshape;
+    double zMin;
+    const double* fixed;          /* NSEM_BC_FIXED: [n_faces*NPF*comps] */
+} nsem_bc;
+
+/* Scalars of general{} / euler{} that the step needs (apps/utils/properties.cpp:14-34, euler.cpp:19-48,
+ * src/field/field.cpp:496-552). */
+typedef struct {
+    double P0, T0, cp, cv, viscosity, Pr;
+    double gravity[3];
+    double dt;
+    int32_t buoyancy;             /* euler{buoyancy} */
+    int32_t diffusion;            /* euler{diffusion} */
+} nsem_params;
+
+/* Inter-partition neighbour (Mesh::interBoundary, src/mesh/mesh.h:32-37). */
+typedef struct {
+    int32_t peer_rank;
+    uint32_t n_faces;
+    const uint32_t* faces;        /* faces of patch interMesh_<me>_<peer>, ascending global order */
+} nsem_halo_peer;
+
+/* ---- life cycle ------------------------------------------------------------------------------------ */
+/* MP::MP / MP::~MP (src/mp/mp.cpp:17-35): one context per rank/GPU. nccl_unique_id is the 128-byte
+ * ncclUniqueId shared by all ranks (NULL when nranks == 1). */
+int nsem_create(int device, int rank, int nranks, const void* nccl_unique_id, nsem_ctx** out);
+void nsem_destroy(nsem_ctx* ctx);
+const char* nsem_last_error(const nsem_ctx* ctx);          /* ctx may be NULL: error of the last failed create */
+int nsem_get_unique_id(void* out128);                      /* ncclGetUniqueId for rank 0 to broadcast */
+
+/* ---- set-up ---------------------------------------------------------------------------------------- */
+/* DG::init_poly (dg.cpp:147-163): points per direction = order+1 (npx+1, npy+1, npz+1). */
+int nsem_set_order(nsem_ctx* ctx, int NPX, int NPY, int NPZ);
+/* DG::init_basis tables (dg.cpp:481-547): dpsi[d][s*n+i] = l_i'(x_s), wgl[d][n]. */
+int nsem_set_basis(nsem_ctx* ctx, const double* const dpsi[3], const double* const wgl[3]);
+int nsem_upload_mesh(nsem_ctx* ctx, const nsem_mesh* mesh);
+int nsem_set_bcs(nsem_ctx* ctx, const nsem_bc* bcs, uint32_t n_bcs);           /* AllBConditions of rho,p,U,T */
+int nsem_set_halo(nsem_ctx* ctx, const nsem_halo_peer* peers, uint32_t n_peers); /* gInterMesh */
+int nsem_set_params(nsem_ctx* ctx, const nsem_params* p);
+/* Process elements in this order (cache blocking); NULL = mesh order. Results do not depend on it. */
+int nsem_set_schedule(nsem_ctx* ctx, const uint32_t* order, uint32_t n);
+
+/* ---- state ------------------------------------------------------------------------------------------ */
+/* Fields over ALL nodes (n_cells_all*NP), ghost nodes included, as euler.cpp holds them between steps:
+ * rho, U (AoS 3), T (perturbation theta - T0, euler.cpp:181,286), p (perturbation p - p_ref). */
+int nsem_upload_state(nsem_ctx* ctx, const double* rho, const double* U, const double* T, const double* p);
+int nsem_download_state(nsem_ctx* ctx, double* rho, double* U, double* T, double* p);
+/* Hydrostatic reference state and gravity (euler.cpp:105-131); g may be NULL for uniform params.gravity. */
+int nsem_upload_ref(nsem_ctx* ctx, const double* rho_ref, const double* p_ref, const double* g);
+
+/* ---- the hot path ------------------------------------------------------------------------------------ */
+/* nsteps iterations of the time-loop body apps/euler/euler.cpp:179-287 (steps 1-8 and 10 of SURVEY 3.2):
+ * rho-, U- and T-equations with divf<weak>/gradf<strong>/rusanov/addTemporal<1>/Solve + BCs + halo. */
+int nsem_euler_step(nsem_ctx* ctx, int nsteps);
+/* euler.cpp:261-283 + Mesh::calc_courant (field.cpp:440-448): out = {courant max, min, avg, mass, energy,
+ * volume}, all-reduced over ranks. */
+int nsem_diagnostics(nsem_ctx* ctx, double out[6]);
+/* cudaDeviceSynchronize on the context's streams. */
+int nsem_sync(nsem_ctx* ctx);
+/* Time `nsteps` steps with CUDA events on the launching stream; returns milliseconds in *ms and, when
+ * per_kernel_ms != NULL, the accumulated event time of {sweepA, bcA, sweepB, bcB} (4 doubles). */
+int nsem_time_steps(nsem_ctx* ctx, int nsteps, double* ms, double* per_kernel_ms);
+/* Number of kernels of this library launched since the context was created. */
+uint64_t nsem_launch_count(const nsem_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,798 @@
+// nsem_cuda.cu -- C ABI (include/nsem_c.h) over the sm_100a kernels in nsem_kernels.cuh.
+//
+// Owns all device memory.  Translates the reference's mesh/field layout (Mesh::initGeomMeshFields,
+// src/field/field.cpp:171-280) into the device layout: SoA node arrays with element stride NPS, compact
+// ghost cells (NPF slots per boundary face, stride GPS) and per-(element, local face) tables derived
+// from gFaceID/gFOC/gFNC.  The derived face-node pairing is verified against the reference's FO/FN maps
+// (dg.cpp:328-410) at upload time, so an orientation the kernels do not reproduce is rejected loudly.
+#include "../../include/nsem_c.h"
+#include "nsem_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#ifdef NSEM_WITH_NCCL
+#include <nccl.h>
+#endif
+
+using namespace nsem;
+
+namespace {
+std::string g_create_error;
+
+#define CUDA_TRY(ctx, expr)                                                                       \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(e_);                      \
+            return 1;                                                                             \
+        }                                                                                         \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc(&p, count * sizeof(T));
+    }
+    cudaError_t upload(const std::vector<T>& h, cudaStream_t s) {
+        cudaError_t e = alloc(h.size());
+        if (e != cudaSuccess || h.empty()) return e;
+        return cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+};
+}  // namespace
+
+struct nsem_ctx {
+    int device = 0, rank = 0, nranks = 1;
+    cudaStream_t stream = nullptr, comm = nullptr;
+    mutable std::string err;
+    uint64_t launches = 0;
+
+    int NX = 0, NY = 0, NZ = 0, NP = 0, NPF = 0, NPS = 0, GPS = 0;
+    bool have_basis = false, have_mesh = false, have_params = false, have_state = false, have_ref = false, have_bcs = false;
+    double D[3][MAXN * MAXN], W[3][MAXN];
+    nsem_params prm{};
+
+    uint32_t nB = 0, nG = 0, nF = 0, nAll = 0;
+    size_t nNodes = 0;        // device nodes: nB*NPS + nG*GPS
+    uint64_t ghostBase = 0;
+    uint64_t nRefNodes = 0;   // n_cells_all * NP
+
+    // host copies needed after upload_mesh
+    std::vector<uint32_t> h_face_owner, h_face_neigh, h_bOwner;
+    std::vector<uint8_t> h_bFid;
+
+    // node arrays
+    DevBuf<double> rho[2], U[2][3], T[2], p, GU[9], GT[3], Jinv[9], cV, rho_ref, p_ref, gfield[3];
+    int cur = 0;
+    bool has_gfield = false;
+    // element-face tables
+    DevBuf<uint32_t> faceOther, faceMeta, sched;
+    DevBuf<double> faceVec, faceUnit;
+    bool has_sched = false;
+    // ghost tables
+    DevBuf<uint32_t> ghostRef, bOwner;
+    DevBuf<uint8_t> bFid;
+    DevBuf<double> bUnit;
+    DevBuf<uint8_t> bcKind[4];
+    DevBuf<uint32_t> bcRec[4], bcPeer[4];
+    DevBuf<double> bcFixed[4];
+    DevBuf<BCRec> bcRecs;
+    // staging for layout conversion
+    DevBuf<double> stage;
+    DevBuf<double*> ptrTab;
+    DevBuf<int> compMap;
+
+    // timing
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+
+#ifdef NSEM_WITH_NCCL
+    ncclComm_t nccl = nullptr;
+#endif
+    struct Peer { int rank; std::vector<uint32_t> ghosts; };   // ghost cells (indices) filled by this peer, in face order
+    std::vector<Peer> peers;
+    DevBuf<double> sendBuf;
+    DevBuf<uint32_t> sendNodes;      // owner node (device index) per send slot
+    std::vector<size_t> peerOff;     // slot offsets per peer (in face nodes)
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// dispatch over the compiled (NX,NY,NZ) instantiations
+// ---------------------------------------------------------------------------------------------------------
+#define NSEM_ORDERS(X)                                                                            \
+    X(2, 2, 2) X(3, 3, 3) X(4, 4, 4) X(5, 5, 5) X(6, 6, 6) X(7, 7, 7) X(8, 8, 8)                  \
+    X(2, 1, 2) X(3, 1, 3) X(4, 1, 4) X(5, 1, 5) X(6, 1, 6) X(7, 1, 7) X(8, 1, 8)                  \
+    X(2, 2, 1) X(3, 3, 1) X(4, 4, 1) X(5, 5, 1) X(6, 6, 1) X(7, 7, 1) X(8, 8, 1)
+
+template <int NX, int NY, int NZ>
+struct Launch {
+    using Dm = Dims<NX, NY, NZ>;
+    // elements per block: aim at ~256 threads
+    static constexpr int EPB = (Dm::TPE >= 256) ? 1 : (256 / Dm::TPE);
+
+    static constexpr size_t smemA(bool visc) { return (size_t)EPB * (visc ? 7 : 3) * Dm::NP * sizeof(double); }
+    static constexpr size_t smemB = (size_t)EPB * 12 * Dm::NP * sizeof(double);
+
+    template <class K>
+    static cudaError_t go(K kernel, size_t smem, const KParams& P, cudaStream_t s) {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        const unsigned grid = (P.nB + EPB - 1) / EPB;
+        kernel<<<grid, EPB * Dm::TPE, smem, s>>>(P);
+        return cudaGetLastError();
+    }
+    static cudaError_t sweepA(const KParams& P, cudaStream_t s) {
+        if (P.visc) return go(sweepA_kernel<NX, NY, NZ, EPB, true>, smemA(true), P, s);
+        return go(sweepA_kernel<NX, NY, NZ, EPB, false>, smemA(false), P, s);
+    }
+    static cudaError_t sweepB(const KParams& P, cudaStream_t s) {
+        if (P.visc) return go(sweepB_kernel<NX, NY, NZ, EPB, true>, smemB, P, s);
+        return go(sweepB_kernel<NX, NY, NZ, EPB, false>, smemB, P, s);
+    }
+    static cudaError_t bc(const BCParams& B, cudaStream_t s) {
+        const uint64_t n = (uint64_t)B.nG * Dm::NPF;
+        if (n == 0) return cudaSuccess;
+        bc_kernel<NX, NY, NZ><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(B);
+        return cudaGetLastError();
+    }
+};
+
+static bool order_supported(int nx, int ny, int nz) {
+#define X(a, b, c) if (nx == a && ny == b && nz == c) return true;
+    NSEM_ORDERS(X)
+#undef X
+    return false;
+}
+
+static cudaError_t launch_sweepA(const nsem_ctx* c, const KParams& P) {
+#define X(a, b, cc) if (c->NX == a && c->NY == b && c->NZ == cc) return Launch<a, b, cc>::sweepA(P, c->stream);
+    NSEM_ORDERS(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+static cudaError_t launch_sweepB(const nsem_ctx* c, const KParams& P) {
+#define X(a, b, cc) if (c->NX == a && c->NY == b && c->NZ == cc) return Launch<a, b, cc>::sweepB(P, c->stream);
+    NSEM_ORDERS(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+static cudaError_t launch_bc(const nsem_ctx* c, const BCParams& B) {
+#define X(a, b, cc) if (c->NX == a && c->NY == b && c->NZ == cc) return Launch<a, b, cc>::bc(B, c->stream);
+    NSEM_ORDERS(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// life cycle
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int nsem_create(int device, int rank, int nranks, const void* nccl_unique_id, nsem_ctx** out) {
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("nsem_create: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback";
+        return 1;
+    }
+    if (device < 0 || device >= ndev) {
+        g_create_error = "nsem_create: device index out of range";
+        return 1;
+    }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        return 1;
+    }
+    nsem_ctx* c = new nsem_ctx();
+    c->device = device;
+    c->rank = rank;
+    c->nranks = nranks;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->comm, cudaStreamNonBlocking) != cudaSuccess) {
+        g_create_error = "nsem_create: cudaStreamCreate failed";
+        delete c;
+        return 1;
+    }
+    for (auto& ev : c->ev) cudaEventCreate(&ev);
+    if (nranks > 1) {
+#ifdef NSEM_WITH_NCCL
+        if (!nccl_unique_id) {
+            g_create_error = "nsem_create: nranks > 1 needs an ncclUniqueId";
+            delete c;
+            return 1;
+        }
+        ncclUniqueId id;
+        std::memcpy(&id, nccl_unique_id, sizeof(id));
+        ncclResult_t r = ncclCommInitRank(&c->nccl, nranks, id, rank);
+        if (r != ncclSuccess) {
+            g_create_error = std::string("ncclCommInitRank: ") + ncclGetErrorString(r);
+            delete c;
+            return 1;
+        }
+#else
+        (void)nccl_unique_id;
+        g_create_error = "nsem_create: library built without NCCL";
+        delete c;
+        return 1;
+#endif
+    }
+    *out = c;
+    return 0;
+}
+
+extern "C" void nsem_destroy(nsem_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+#ifdef NSEM_WITH_NCCL
+    if (c->nccl) ncclCommDestroy(c->nccl);
+#endif
+    for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->comm) cudaStreamDestroy(c->comm);
+    delete c;
+}
+
+extern "C" const char* nsem_last_error(const nsem_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int nsem_get_unique_id(void* out128) {
+#ifdef NSEM_WITH_NCCL
+    ncclUniqueId id;
+    if (ncclGetUniqueId(&id) != ncclSuccess) return 1;
+    std::memcpy(out128, &id, sizeof(id));
+    return 0;
+#else
+    (void)out128;
+    return 1;
+#endif
+}
+
+extern "C" uint64_t nsem_launch_count(const nsem_ctx* c) { return c->launches; }
+
+extern "C" int nsem_sync(nsem_ctx* c) {
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->comm));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// set-up
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int nsem_set_order(nsem_ctx* c, int NPX, int NPY, int NPZ) {
+    if (!order_supported(NPX, NPY, NPZ)) {
+        char b[160];
+        snprintf(b, sizeof b, "nsem_set_order: (%d,%d,%d) points per direction has no compiled kernel "
+                 "(3-D n^3, 2-D n x 1 x n and n x n x 1 for n = 2..8)", NPX, NPY, NPZ);
+        c->err = b;
+        return 1;
+    }
+    c->NX = NPX; c->NY = NPY; c->NZ = NPZ;
+    c->NP = NPX * NPY * NPZ;
+    c->NPF = (NPX <= NPY && NPX <= NPZ) ? NPY * NPZ : ((NPY <= NPX && NPY <= NPZ) ? NPX * NPZ : NPX * NPY);
+    c->NPS = pad_to(c->NP, 16);
+    c->GPS = pad_to(c->NPF, 4);
+    c->have_basis = c->have_mesh = c->have_state = c->have_ref = c->have_bcs = false;
+    return 0;
+}
+
+extern "C" int nsem_set_basis(nsem_ctx* c, const double* const dpsi[3], const double* const wgl[3]) {
+    if (!c->NP) { c->err = "nsem_set_basis: call nsem_set_order first"; return 1; }
+    const int n[3] = {c->NX, c->NY, c->NZ};
+    std::memset(c->D, 0, sizeof c->D);
+    std::memset(c->W, 0, sizeof c->W);
+    for (int d = 0; d < 3; d++) {
+        for (int q = 0; q < n[d] * n[d]; q++) c->D[d][q] = dpsi[d][q];
+        for (int q = 0; q < n[d]; q++) c->W[d][q] = wgl[d][q];
+    }
+    c->have_basis = true;
+    return 0;
+}
+
+extern "C" int nsem_set_params(nsem_ctx* c, const nsem_params* p) {
+    if (!(p->dt > 0) || !(p->cv > 0) || !(p->cp > p->cv) || !(p->P0 > 0) || !(p->Pr > 0)) {
+        c->err = "nsem_set_params: need dt > 0, cp > cv > 0, P0 > 0, Pr > 0";
+        return 1;
+    }
+    c->prm = *p;
+    c->have_params = true;
+    return 0;
+}
+
+// local node of face `fid` at face coordinates (a,b)
+static inline int h_face_node(const nsem_ctx* c, int fid, int a, int b) {
+    const int NX = c->NX, NY = c->NY, NZ = c->NZ;
+    if (fid < 2) return a * NY * NZ + b * NZ + (fid == 0 ? 0 : NZ - 1);
+    if (fid < 4) return a * NY * NZ + (fid == 2 ? 0 : NY - 1) * NZ + b;
+    return (fid == 4 ? 0 : NX - 1) * NY * NZ + a * NZ + b;
+}
+
+extern "C" int nsem_upload_mesh(nsem_ctx* c, const nsem_mesh* m) {
+    if (!c->have_basis) { c->err = "nsem_upload_mesh: call nsem_set_order and nsem_set_basis first"; return 1; }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const int NX = c->NX, NY = c->NY, NZ = c->NZ, NP = c->NP, NPF = c->NPF, NPS = c->NPS, GPS = c->GPS;
+    const uint32_t nB = m->n_cells_real, nAll = m->n_cells_all, nF = m->n_faces, nG = nAll - nB;
+    if ((uint64_t)nB * NPS + (uint64_t)nG * GPS >= 0xffffffffull) {
+        c->err = "nsem_upload_mesh: more than 2^32 device nodes on one GPU";
+        return 1;
+    }
+    c->nB = nB; c->nG = nG; c->nF = nF; c->nAll = nAll;
+    c->ghostBase = (uint64_t)nB * NPS;
+    c->nNodes = (size_t)nB * NPS + (size_t)nG * GPS;
+    c->nRefNodes = (uint64_t)nAll * NP;
+    const uint32_t sentinel = (uint32_t)c->nRefNodes;
+
+    // ---- per (element, local face id) tables ----
+    std::vector<uint32_t> fOther((size_t)nB * 6, 0), fMeta((size_t)nB * 6, FM_ABSENT);
+    std::vector<double> fVec((size_t)nB * 18, 0.0), fUnit((size_t)nB * 18, 0.0);
+    std::vector<uint32_t> ghostRef((size_t)nG * NPF, 0xffffffffu), bOwner(nG, 0);
+    std::vector<uint8_t> bFid(nG, 0);
+    std::vector<double> bUnit((size_t)nG * 3, 0.0);
+    // face id of a face as seen from a real cell
+    auto local_id = [&](uint32_t cell, uint32_t face) -> int {
+        for (uint32_t f = m->face_begin[cell]; f < m->face_end[cell]; f++)
+            if (m->all_faces[f] == face) return (int)m->face_id[f];
+        return -1;
+    };
+    for (uint32_t ci = 0; ci < nB; ci++) {
+        for (uint32_t f = m->face_begin[ci]; f < m->face_end[ci]; f++) {
+            const uint32_t face = m->all_faces[f];
+            const int sid = (int)m->face_id[f];
+            if (sid < 0 || sid > 5) { c->err = "nsem_upload_mesh: face id outside 0..5"; return 1; }
+            if (m->face_mortar && m->face_mortar[face] != 0) {
+                c->err = "nsem_upload_mesh: non-conforming (mortar) faces are not supported by this build";
+                return 1;
+            }
+            const size_t e6 = (size_t)ci * 6 + sid;
+            if ((fMeta[e6] & FM_FID_MASK) != FM_ABSENT) {
+                c->err = "nsem_upload_mesh: two faces with the same local id on one element (non-conforming mesh)";
+                return 1;
+            }
+            const bool own = (m->face_owner[face] == ci);
+            const uint32_t other = own ? m->face_neigh[face] : m->face_owner[face];
+            uint32_t meta = own ? FM_OWNER : 0u;
+            // fI at the first used slot of the face
+            double alpha = -1;
+            for (int n = 0; n < NPF; n++)
+                if (m->FO[(size_t)face * NPF + n] != sentinel) { alpha = m->fI[(size_t)face * NPF + n]; break; }
+            if (alpha == 0.5) meta |= FM_HALF;
+            else if (alpha != 0.0) { c->err = "nsem_upload_mesh: fI must be 0.5 or 0 on a DG mesh"; return 1; }
+            if (other < nB) {
+                const int oid = local_id(other, face);
+                if (oid < 0) { c->err = "nsem_upload_mesh: face not found in its neighbour cell"; return 1; }
+                meta |= (uint32_t)oid;
+                fOther[e6] = other * (uint32_t)NPS;
+            } else {
+                if (!own) { c->err = "nsem_upload_mesh: boundary cell owns a face"; return 1; }
+                const uint32_t g = other - nB;
+                meta |= FM_GHOST;
+                fOther[e6] = (uint32_t)(c->ghostBase + (uint64_t)g * GPS);
+                bOwner[g] = ci;
+                bFid[g] = (uint8_t)sid;
+            }
+            fMeta[e6] = meta;
+            const double* N = m->face_normal + (size_t)face * 3;
+            const double mg = std::sqrt(N[0] * N[0] + (N[1] * N[1] + N[2] * N[2]));
+            for (int d = 0; d < 3; d++) {
+                fVec[e6 * 3 + d] = N[d];
+                fUnit[e6 * 3 + d] = N[d] / mg;
+            }
+            if (other >= nB)
+                for (int d = 0; d < 3; d++) bUnit[(size_t)(other - nB) * 3 + d] = N[d] / mg;
+
+            // ---- verify the derived node pairing + weights against the reference maps ----
+            const int na = (sid < 2) ? NX : (sid < 4 ? NX : NY);
+            const int nb = (sid < 2) ? NY : NZ;
+            for (int a = 0; a < na; a++)
+                for (int b = 0; b < nb; b++) {
+                    const int n = (sid < 2) ? a * NY + b : a * NZ + b;
+                    const size_t k = (size_t)face * NPF + n;
+                    const uint32_t mine = ci * (uint32_t)NP + (uint32_t)h_face_node(c, sid, a, b);
+                    const uint32_t refMine = own ? m->FO[k] : m->FN[k];
+                    const uint32_t refOther = own ? m->FN[k] : m->FO[k];
+                    bool ok = (refMine == mine);
+                    if (other < nB) {
+                        const uint32_t theirs = other * (uint32_t)NP + (uint32_t)h_face_node(c, (int)(meta & FM_FID_MASK), a, b);
+                        ok = ok && (refOther == theirs);
+                    } else if (ok) {
+                        ghostRef[(size_t)(other - nB) * NPF + n] = refOther;
+                    }
+                    if (!ok) {
+                        char bmsg[200];
+                        snprintf(bmsg, sizeof bmsg, "nsem_upload_mesh: face %u (cell %u, local id %d) does not follow the "
+                                 "tensor-product node pairing of dg.cpp:372-404", face, ci, sid);
+                        c->err = bmsg;
+                        return 1;
+                    }
+                    const double w = (sid < 2) ? c->W[0][a] * c->W[1][b] / 4 : (sid < 4 ? c->W[0][a] * c->W[2][b] / 4 : c->W[1][a] * c->W[2][b] / 4);
+                    for (int d = 0; d < 3; d++) {
+                        const double want = m->fN[k * 3 + d], got = N[d] * w;
+                        if (std::fabs(want - got) > 1e-12 * (std::fabs(want) + mg * w)) {
+                            c->err = "nsem_upload_mesh: fN != face_normal * w_a*w_b/4";
+                            return 1;
+                        }
+                    }
+                }
+        }
+    }
+    c->h_face_owner.assign(m->face_owner, m->face_owner + nF);
+    c->h_face_neigh.assign(m->face_neigh, m->face_neigh + nF);
+    c->h_bOwner = bOwner;
+    c->h_bFid = bFid;
+
+    cudaStream_t s = c->stream;
+    CUDA_TRY(c, c->faceOther.upload(fOther, s));
+    CUDA_TRY(c, c->faceMeta.upload(fMeta, s));
+    CUDA_TRY(c, c->faceVec.upload(fVec, s));
+    CUDA_TRY(c, c->faceUnit.upload(fUnit, s));
+    CUDA_TRY(c, c->ghostRef.upload(ghostRef, s));
+    CUDA_TRY(c, c->bOwner.upload(bOwner, s));
+    CUDA_TRY(c, c->bFid.upload(bFid, s));
+    CUDA_TRY(c, c->bUnit.upload(bUnit, s));
+
+    // ---- node arrays ----
+    const size_t nN = c->nNodes;
+    for (int b = 0; b < 2; b++) {
+        CUDA_TRY(c, c->rho[b].alloc(nN));
+        CUDA_TRY(c, c->T[b].alloc(nN));
+        for (int d = 0; d < 3; d++) CUDA_TRY(c, c->U[b][d].alloc(nN));
+        CUDA_TRY(c, cudaMemsetAsync(c->rho[b].p, 0, nN * 8, s));
+        CUDA_TRY(c, cudaMemsetAsync(c->T[b].p, 0, nN * 8, s));
+        for (int d = 0; d < 3; d++) CUDA_TRY(c, cudaMemsetAsync(c->U[b][d].p, 0, nN * 8, s));
+    }
+    CUDA_TRY(c, c->p.alloc(nN));
+    CUDA_TRY(c, cudaMemsetAsync(c->p.p, 0, nN * 8, s));
+    for (int q = 0; q < 9; q++) { CUDA_TRY(c, c->GU[q].alloc(nN)); CUDA_TRY(c, cudaMemsetAsync(c->GU[q].p, 0, nN * 8, s)); }
+    for (int q = 0; q < 3; q++) { CUDA_TRY(c, c->GT[q].alloc(nN)); CUDA_TRY(c, cudaMemsetAsync(c->GT[q].p, 0, nN * 8, s)); }
+    CUDA_TRY(c, c->rho_ref.alloc(nN));
+    CUDA_TRY(c, c->p_ref.alloc(nN));
+    CUDA_TRY(c, cudaMemsetAsync(c->rho_ref.p, 0, nN * 8, s));
+    CUDA_TRY(c, cudaMemsetAsync(c->p_ref.p, 0, nN * 8, s));
+
+    // metrics: cV for all nodes, Jinv (AoS XX,YY,ZZ,XY,YZ,XZ,YX,ZY,ZX -> row-major arrays) for real nodes
+    {
+        std::vector<double> h(nN, 1.0);
+        for (uint32_t ci = 0; ci < nB; ci++)
+            for (int t = 0; t < NP; t++) h[(size_t)ci * NPS + t] = m->cV[(size_t)ci * NP + t];
+        for (uint32_t g = 0; g < nG; g++)
+            for (int n = 0; n < NPF; n++) {
+                const uint32_t ref = ghostRef[(size_t)g * NPF + n];
+                if (ref != 0xffffffffu) h[c->ghostBase + (size_t)g * GPS + n] = m->cV[ref];
+            }
+        CUDA_TRY(c, c->cV.upload(h, s));
+        CUDA_TRY(c, cudaStreamSynchronize(s));
+        static const int rm[9] = {0, 4, 8, 1, 5, 2, 3, 7, 6};      // AoS component -> row-major a*3+d
+        std::vector<double> hj((size_t)nB * NPS);
+        for (int comp = 0; comp < 9; comp++) {
+            std::fill(hj.begin(), hj.end(), 0.0);
+            for (uint32_t ci = 0; ci < nB; ci++)
+                for (int t = 0; t < NP; t++) hj[(size_t)ci * NPS + t] = m->Jinv[((size_t)ci * NP + t) * 9 + comp];
+            CUDA_TRY(c, c->Jinv[rm[comp]].upload(hj, s));
+            CUDA_TRY(c, cudaStreamSynchronize(s));
+        }
+    }
+    // BC tables default to NONE
+    for (int f = 0; f < 4; f++) {
+        std::vector<uint8_t> k0(nG, 0);
+        std::vector<uint32_t> z(nG, 0);
+        CUDA_TRY(c, c->bcKind[f].upload(k0, s));
+        CUDA_TRY(c, c->bcRec[f].upload(z, s));
+        CUDA_TRY(c, c->bcPeer[f].upload(z, s));
+    }
+    CUDA_TRY(c, cudaStreamSynchronize(s));
+    c->has_sched = false;
+    c->have_mesh = true;
+    c->have_state = c->have_ref = c->have_bcs = false;
+    c->cur = 0;
+    return 0;
+}
+
+extern "C" int nsem_set_schedule(nsem_ctx* c, const uint32_t* order, uint32_t n) {
+    if (!c->have_mesh) { c->err = "nsem_set_schedule: no mesh"; return 1; }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (!order) { c->has_sched = false; return 0; }
+    if (n != c->nB) { c->err = "nsem_set_schedule: order must list every real element once"; return 1; }
+    std::vector<uint8_t> seen(n, 0);
+    for (uint32_t q = 0; q < n; q++) {
+        if (order[q] >= n || seen[order[q]]) { c->err = "nsem_set_schedule: not a permutation"; return 1; }
+        seen[order[q]] = 1;
+    }
+    std::vector<uint32_t> h(order, order + n);
+    CUDA_TRY(c, c->sched.upload(h, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->has_sched = true;
+    return 0;
+}
+
+extern "C" int nsem_set_bcs(nsem_ctx* c, const nsem_bc* bcs, uint32_t nb) {
+    if (!c->have_mesh) { c->err = "nsem_set_bcs: no mesh"; return 1; }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const uint32_t nG = c->nG, nB = c->nB;
+    const int NPF = c->NPF;
+    std::vector<uint8_t> kind[4];
+    std::vector<uint32_t> rec[4], peer[4];
+    std::vector<double> fixedv[4];
+    std::vector<BCRec> recs;
+    for (int f = 0; f < 4; f++) { kind[f].assign(nG, 0); rec[f].assign(nG, 0); peer[f].assign(nG, 0); }
+    recs.push_back(BCRec{});
+    for (uint32_t q = 0; q < nb; q++) {
+        const nsem_bc& b = bcs[q];
+        if (b.field < 0 || b.field >= 4) { c->err = "nsem_set_bcs: bad field id"; return 1; }
+        if (b.kind < NSEM_BC_NEUMANN || b.kind > NSEM_BC_ROBIN) { c->err = "nsem_set_bcs: unsupported BC kind"; return 1; }
+        const int comps = (b.field == NSEM_F_U) ? 3 : 1;
+        BCRec r{};
+        for (int d = 0; d < 3; d++) { r.value[d] = b.value[d]; r.tvalue[d] = b.tvalue[d]; }
+        r.shape = b.shape; r.tshape = b.tshape; r.zMin = b.zMin;
+        recs.push_back(r);
+        const uint32_t ri = (uint32_t)recs.size() - 1;
+        if (b.kind == NSEM_BC_FIXED && fixedv[b.field].empty()) fixedv[b.field].assign((size_t)nG * NPF * comps, 0.0);
+        for (uint32_t j = 0; j < b.n_faces; j++) {
+            const uint32_t face = b.faces[j];
+            if (face >= c->nF || c->h_face_neigh[face] < nB) {
+                c->err = "nsem_set_bcs: patch face is not a boundary face of this partition";
+                return 1;
+            }
+            const uint32_t g = c->h_face_neigh[face] - nB;
+            kind[b.field][g] = (uint8_t)b.kind;
+            rec[b.field][g] = ri;
+            if (b.kind == NSEM_BC_CYCLIC) {
+                if (!b.peer_faces) { c->err = "nsem_set_bcs: CYCLIC needs peer_faces"; return 1; }
+                const uint32_t pf = b.peer_faces[j];
+                if (pf >= c->nF || c->h_face_neigh[pf] < nB) { c->err = "nsem_set_bcs: CYCLIC peer is not a boundary face"; return 1; }
+                peer[b.field][g] = c->h_face_neigh[pf] - nB;
+            }
+            if (b.kind == NSEM_BC_FIXED) {
+                if (!b.fixed) { c->err = "nsem_set_bcs: FIXED needs values"; return 1; }
+                for (int n = 0; n < NPF * comps; n++)
+                    fixedv[b.field][((size_t)g * NPF) * comps + n] = b.fixed[((size_t)j * NPF) * comps + n];
+            }
+        }
+    }
+    // every ghost cell needs a condition for every field (a patch without one keeps stale ghost values in the
+    // reference, field.h:2602-2611; the shipped euler cases always define all four)
+    for (int f = 0; f < 4; f++)
+        for (uint32_t g = 0; g < nG; g++)
+            if (kind[f][g] == 0) {
+                char bmsg[160];
+                snprintf(bmsg, sizeof bmsg, "nsem_set_bcs: boundary face of element %u has no condition for field %d", c->h_bOwner[g], f);
+                c->err = bmsg;
+                return 1;
+            }
+    cudaStream_t s = c->stream;
+    for (int f = 0; f < 4; f++) {
+        CUDA_TRY(c, c->bcKind[f].upload(kind[f], s));
+        CUDA_TRY(c, c->bcRec[f].upload(rec[f], s));
+        CUDA_TRY(c, c->bcPeer[f].upload(peer[f], s));
+        CUDA_TRY(c, c->bcFixed[f].upload(fixedv[f], s));
+    }
+    CUDA_TRY(c, c->bcRecs.upload(recs, s));
+    CUDA_TRY(c, cudaStreamSynchronize(s));
+    c->have_bcs = true;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// state transfer (reference AoS <-> device SoA)
+// ---------------------------------------------------------------------------------------------------------
+static int to_device(nsem_ctx* c, const double* host, int comps, double* const dst[3]) {
+    const size_t bytes = (size_t)c->nRefNodes * comps * sizeof(double);
+    if (c->stage.n < (size_t)c->nRefNodes * 3) CUDA_TRY(c, c->stage.alloc((size_t)c->nRefNodes * 3));
+    if (!c->ptrTab.p) { CUDA_TRY(c, c->ptrTab.alloc(3)); CUDA_TRY(c, c->compMap.alloc(3)); }
+    const int cm[3] = {0, 1, 2};
+    CUDA_TRY(c, cudaMemcpyAsync(c->stage.p, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->ptrTab.p, dst, comps * sizeof(double*), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->compMap.p, cm, comps * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    const uint64_t n = (uint64_t)c->nB * c->NP + (uint64_t)c->nG * c->NPF;
+    scatter_to_device<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->stage.p, comps, c->ptrTab.p, c->compMap.p, c->nB, c->NP,
+                                                                         c->NPS, c->nG, c->NPF, c->GPS, c->ghostRef.p, c->ghostBase);
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+static int from_device(nsem_ctx* c, double* host, int comps, const double* const src[3]) {
+    const size_t bytes = (size_t)c->nRefNodes * comps * sizeof(double);
+    if (c->stage.n < (size_t)c->nRefNodes * 3) CUDA_TRY(c, c->stage.alloc((size_t)c->nRefNodes * 3));
+    if (!c->ptrTab.p) { CUDA_TRY(c, c->ptrTab.alloc(3)); CUDA_TRY(c, c->compMap.alloc(3)); }
+    const int cm[3] = {0, 1, 2};
+    // nodes of ghost cells that no face touches keep the caller's values
+    CUDA_TRY(c, cudaMemcpyAsync(c->stage.p, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->ptrTab.p, src, comps * sizeof(double*), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->compMap.p, cm, comps * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    const uint64_t n = (uint64_t)c->nB * c->NP + (uint64_t)c->nG * c->NPF;
+    gather_from_device<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->stage.p, comps, (const double* const*)c->ptrTab.p, c->compMap.p,
+                                                                          c->nB, c->NP, c->NPS, c->nG, c->NPF, c->GPS, c->ghostRef.p, c->ghostBase);
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaMemcpyAsync(host, c->stage.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int nsem_upload_state(nsem_ctx* c, const double* rho, const double* U, const double* T, const double* p) {
+    if (!c->have_mesh) { c->err = "nsem_upload_state: no mesh"; return 1; }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const int k = c->cur;
+    double* d1[3] = {c->rho[k].p, nullptr, nullptr};
+    if (to_device(c, rho, 1, d1)) return 1;
+    double* d3[3] = {c->U[k][0].p, c->U[k][1].p, c->U[k][2].p};
+    if (to_device(c, U, 3, d3)) return 1;
+    d1[0] = c->T[k].p;
+    if (to_device(c, T, 1, d1)) return 1;
+    if (p) { d1[0] = c->p.p; if (to_device(c, p, 1, d1)) return 1; }
+    c->have_state = true;
+    return 0;
+}
+
+extern "C" int nsem_download_state(nsem_ctx* c, double* rho, double* U, double* T, double* p) {
+    if (!c->have_state) { c->err = "nsem_download_state: no state"; return 1; }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const int k = c->cur;
+    const double* s1[3] = {c->rho[k].p, nullptr, nullptr};
+    if (rho && from_device(c, rho, 1, s1)) return 1;
+    const double* s3[3] = {c->U[k][0].p, c->U[k][1].p, c->U[k][2].p};
+    if (U && from_device(c, U, 3, s3)) return 1;
+    s1[0] = c->T[k].p;
+    if (T && from_device(c, T, 1, s1)) return 1;
+    s1[0] = c->p.p;
+    if (p && from_device(c, p, 1, s1)) return 1;
+    return 0;
+}
+
+extern "C" int nsem_upload_ref(nsem_ctx* c, const double* rho_ref, const double* p_ref, const double* g) {
+    if (!c->have_mesh) { c->err = "nsem_upload_ref: no mesh"; return 1; }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    double* d1[3] = {c->rho_ref.p, nullptr, nullptr};
+    if (to_device(c, rho_ref, 1, d1)) return 1;
+    d1[0] = c->p_ref.p;
+    if (to_device(c, p_ref, 1, d1)) return 1;
+    c->has_gfield = false;
+    if (g) {
+        for (int d = 0; d < 3; d++) CUDA_TRY(c, c->gfield[d].alloc(c->nNodes));
+        double* d3[3] = {c->gfield[0].p, c->gfield[1].p, c->gfield[2].p};
+        if (to_device(c, g, 3, d3)) return 1;
+        c->has_gfield = true;
+    }
+    c->have_ref = true;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the step
+// ---------------------------------------------------------------------------------------------------------
+static void fill_kparams(const nsem_ctx* c, KParams& P) {
+    std::memset(&P, 0, sizeof P);
+    const int k = c->cur, o = 1 - c->cur;
+    P.nB = c->nB; P.nG = c->nG; P.ghostBase = c->ghostBase;
+    const nsem_params& q = c->prm;
+    P.P0 = q.P0; P.T0 = q.T0; P.R = q.cp - q.cv; P.gamma = q.cp / q.cv; P.nu = q.viscosity; P.iPr = 1 / q.Pr; P.dt = q.dt;
+    for (int d = 0; d < 3; d++) P.g[d] = q.gravity[d];
+    P.buoyancy = q.buoyancy;
+    // mu = rho*viscosity when diffusion is on (euler.cpp:189-190); viscosity == 0 gives the same fluxes
+    P.visc = (q.diffusion && q.viscosity != 0.0) ? 1 : 0;
+    P.has_gfield = c->has_gfield ? 1 : 0;
+    std::memcpy(P.D, c->D, sizeof P.D);
+    std::memcpy(P.W, c->W, sizeof P.W);
+    P.rho_old = c->rho[k].p; P.rho_new = c->rho[o].p;
+    P.T_old = c->T[k].p; P.T_new = c->T[o].p;
+    for (int d = 0; d < 3; d++) { P.U_old[d] = c->U[k][d].p; P.U_new[d] = c->U[o][d].p; P.gfield[d] = c->gfield[d].p; }
+    P.p = c->p.p;
+    for (int d = 0; d < 9; d++) { P.GU[d] = c->GU[d].p; P.Jinv[d] = c->Jinv[d].p; }
+    for (int d = 0; d < 3; d++) P.GT[d] = c->GT[d].p;
+    P.cV = c->cV.p; P.rho_ref = c->rho_ref.p; P.p_ref = c->p_ref.p;
+    P.faceOther = c->faceOther.p; P.faceMeta = c->faceMeta.p; P.faceVec = c->faceVec.p; P.faceUnit = c->faceUnit.p;
+    P.sched = c->has_sched ? c->sched.p : nullptr;
+}
+static void fill_bcparams(const nsem_ctx* c, const KParams& P, BCParams& B, int phase) {
+    std::memset(&B, 0, sizeof B);
+    B.nB = c->nB; B.nG = c->nG; B.ghostBase = c->ghostBase;
+    B.P0 = P.P0; B.T0 = P.T0; B.R = P.R; B.gamma = P.gamma; B.visc = P.visc; B.phase = phase;
+    B.bOwner = c->bOwner.p; B.bFid = c->bFid.p; B.bUnit = c->bUnit.p;
+    for (int f = 0; f < 4; f++) { B.kind[f] = c->bcKind[f].p; B.rec[f] = c->bcRec[f].p; B.peer[f] = c->bcPeer[f].p; B.fixedv[f] = c->bcFixed[f].p; }
+    B.recs = c->bcRecs.p;
+    B.rho_new = P.rho_new; B.p = P.p; B.T_old = P.T_old; B.p_ref = P.p_ref;
+    for (int d = 0; d < 9; d++) B.GU[d] = P.GU[d];
+    for (int d = 0; d < 3; d++) { B.GT[d] = P.GT[d]; B.U_new[d] = P.U_new[d]; }
+    B.T_new = P.T_new;
+}
+
+static int one_step(nsem_ctx* c, bool timed, double* acc) {
+    KParams P;
+    BCParams B;
+    fill_kparams(c, P);
+    if (timed) cudaEventRecord(c->ev[0], c->stream);
+    CUDA_TRY(c, launch_sweepA(c, P));
+    if (timed) cudaEventRecord(c->ev[1], c->stream);
+    fill_bcparams(c, P, B, 0);
+    CUDA_TRY(c, launch_bc(c, B));
+    if (timed) cudaEventRecord(c->ev[2], c->stream);
+    CUDA_TRY(c, launch_sweepB(c, P));
+    if (timed) cudaEventRecord(c->ev[3], c->stream);
+    B.phase = 1;
+    CUDA_TRY(c, launch_bc(c, B));
+    if (timed) cudaEventRecord(c->ev[4], c->stream);
+    c->launches += 2 + (c->nG ? 2 : 0);
+    c->cur ^= 1;
+    if (timed) {
+        CUDA_TRY(c, cudaEventSynchronize(c->ev[4]));
+        for (int q = 0; q < 4; q++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, c->ev[q], c->ev[q + 1]);
+            acc[q] += ms;
+        }
+    }
+    return 0;
+}
+
+static int check_ready(nsem_ctx* c, const char* who) {
+    if (!(c->have_mesh && c->have_params && c->have_state && c->have_ref && (c->have_bcs || c->nG == 0))) {
+        c->err = std::string(who) + ": mesh, params, BCs, reference state and state must all be set first";
+        return 1;
+    }
+    return 0;
+}
+
+extern "C" int nsem_euler_step(nsem_ctx* c, int nsteps) {
+    if (check_ready(c, "nsem_euler_step")) return 1;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    for (int s = 0; s < nsteps; s++)
+        if (one_step(c, false, nullptr)) return 1;
+    return 0;
+}
+
+extern "C" int nsem_time_steps(nsem_ctx* c, int nsteps, double* ms, double* per_kernel_ms) {
+    if (check_ready(c, "nsem_time_steps")) return 1;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    double acc[4] = {0, 0, 0, 0};
+    cudaEvent_t t0, t1;
+    CUDA_TRY(c, cudaEventCreate(&t0));
+    CUDA_TRY(c, cudaEventCreate(&t1));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (per_kernel_ms) {
+        // per-kernel events serialise host and device; the total below is taken in a second, untimed-inside pass
+        for (int s = 0; s < nsteps; s++)
+            if (one_step(c, true, acc)) return 1;
+        for (int q = 0; q < 4; q++) per_kernel_ms[q] = acc[q];
+    }
+    CUDA_TRY(c, cudaEventRecord(t0, c->stream));
+    for (int s = 0; s < nsteps; s++)
+        if (one_step(c, false, nullptr)) return 1;
+    CUDA_TRY(c, cudaEventRecord(t1, c->stream));
+    CUDA_TRY(c, cudaEventSynchronize(t1));
+    float tot = 0;
+    CUDA_TRY(c, cudaEventElapsedTime(&tot, t0, t1));
+    *ms = tot;
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    return 0;
+}
+
+extern "C" int nsem_set_halo(nsem_ctx* c, const nsem_halo_peer* peers, uint32_t n_peers) {
+    if (n_peers == 0) { c->peers.clear(); return 0; }
+    (void)peers;
+    c->err = "nsem_set_halo: multi-partition halo not built yet";
+    return 1;
+}
+
+extern "C" int nsem_diagnostics(nsem_ctx* c, double out[6]) {
+    (void)out;
+    c->err = "nsem_diagnostics: not built yet";
+    return 1;
+}

@@ -1,0 +1,647 @@
+// nsem_kernels.cuh -- sm_100a kernels of the explicit dGSEM Euler step (FP64, HBM-bound).
+//
+// One reference time step (apps/euler/euler.cpp:179-287) = two grid-wide element sweeps with a boundary
+// (ghost) update after each:
+//   sweep A : old (rho,U,theta)           -> rho_new, p' = P0 (rho_new theta R/P0)^gamma - p_ref, grad U, grad theta
+//   bc    A : ghosts of rho_new, p', grad U, grad theta   (applyExplicitBCs field.h:2586-2727, fillBCs :2731-2769)
+//   sweep B : + neighbours' rho_new, p', gradients        -> U_new, theta_new
+//   bc    B : ghosts of U_new, T_new
+// The split is forced by the sequential coupling rho -> p -> U -> theta of the reference: the
+// U/theta fluxes need the NEIGHBOURS' new density and gradients.
+//
+// Element-centric evaluation: one thread per LGL node, each element recomputes the Rusanov flux on its own
+// faces in the owner's frame (div_flux/grad_flux, field.h:3051-3117, are per-cell loops too), so there are no
+// atomics and the summation order is fixed.  Node data is structure-of-arrays with element stride NPS
+// (NP rounded up to 16 doubles = 128 B) so a warp reads 256 contiguous bytes per array.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace nsem {
+
+constexpr int MAXN = 8;   // points per direction (orders 1..7)
+
+__host__ __device__ constexpr int pad_to(int n, int m) { return ((n + m - 1) / m) * m; }
+
+template <int NX, int NY, int NZ>
+struct Dims {
+    static constexpr int NP = NX * NY * NZ;
+    // DG::init_poly (dg.cpp:147-163): the face slot count is the product of the two larger extents
+    static constexpr int NPF = (NX <= NY && NX <= NZ) ? NY * NZ : ((NY <= NX && NY <= NZ) ? NX * NZ : NX * NY);
+    static constexpr int NPS = pad_to(NP, 16);
+    static constexpr int GPS = pad_to(NPF, 4);
+    static constexpr int TPE = pad_to(NP, 32);   // threads per element
+};
+
+// faceMeta bits
+constexpr uint32_t FM_FID_MASK = 7u;      // 0..5 neighbour's local face id, 6 = ghost cell (compact), 7 = absent
+constexpr uint32_t FM_GHOST = 6u;
+constexpr uint32_t FM_ABSENT = 7u;
+constexpr uint32_t FM_OWNER = 8u;         // this element is the face's owner (gFOC)
+constexpr uint32_t FM_HALF = 16u;         // fI = 0.5 (interior / inter-rank); else fI = 0 (physical boundary)
+
+struct KParams {
+    // sizes
+    uint32_t nB;                 // real elements
+    uint32_t nG;                 // ghost (boundary) cells
+    uint64_t ghostBase;          // nB * NPS
+    // physics
+    double P0, T0, R, gamma, nu, iPr, dt, g[3];
+    int buoyancy, visc, has_gfield;
+    // basis
+    double D[3][MAXN * MAXN];    // D[d][s*n+i] = l_i'(x_s)
+    double W[3][MAXN];
+    // state in
+    const double* rho_old;
+    const double* U_old[3];
+    const double* T_old;
+    // sweep A out / sweep B in
+    double* rho_new;
+    double* p;                   // p' = p - p_ref
+    double* GU[9];               // GU[a*3+b] = d_a U_b  (row-major of the reference Tensor G[ab])
+    double* GT[3];
+    // sweep B out
+    double* U_new[3];
+    double* T_new;
+    // geometry
+    const double* Jinv[9];       // row-major [a*3+d] = d xi_d / d x_a
+    const double* cV;
+    const double* rho_ref;
+    const double* p_ref;
+    const double* gfield[3];     // optional per-node gravity
+    // element-face tables [nB*6]
+    const uint32_t* faceOther;   // first device node of the other cell
+    const uint32_t* faceMeta;
+    const double* faceVec;       // [nB*6*3] un-weighted area vector gFN (outward from the OWNER)
+    const double* faceUnit;      // [nB*6*3] unit(gFN)
+    const uint32_t* sched;       // optional processing order
+};
+
+// ---------------------------------------------------------------------------------------------------
+// index helpers (dg.h:43-44 INDEX4; dg.cpp:372-404 face node maps)
+// ---------------------------------------------------------------------------------------------------
+template <int NX, int NY, int NZ>
+__device__ __forceinline__ int face_slot(int s, int i, int j, int k, int& a, int& b) {
+    if (s < 2) { a = i; b = j; return a * NY + b; }
+    if (s < 4) { a = i; b = k; return a * NZ + b; }
+    a = j; b = k; return a * NZ + b;
+}
+template <int NX, int NY, int NZ>
+__device__ __forceinline__ int face_node(int fid, int a, int b) {
+    if (fid < 2) return a * NY * NZ + b * NZ + (fid == 0 ? 0 : NZ - 1);
+    if (fid < 4) return a * NY * NZ + (fid == 2 ? 0 : NY - 1) * NZ + b;
+    return (fid == 4 ? 0 : NX - 1) * NY * NZ + a * NZ + b;
+}
+// slot n of a face with local id fid -> local node of the cell that owns that slot numbering
+template <int NX, int NY, int NZ>
+__device__ __forceinline__ int face_node_from_slot(int fid, int n, bool& valid) {
+    int a, b;
+    if (fid < 2) { a = n / NY; b = n % NY; valid = n < NX * NY; }
+    else if (fid < 4) { a = n / NZ; b = n % NZ; valid = n < NX * NZ; }
+    else { a = n / NZ; b = n % NZ; valid = n < NY * NZ; }
+    return face_node<NX, NY, NZ>(fid, a, b);
+}
+template <int NX, int NY, int NZ>
+__device__ __forceinline__ double face_weight(const KParams& P, int s, int a, int b) {
+    // wgl[.][a] * wgl[.][b] / 4   (dg.cpp:374,387,400)
+    if (s < 2) return P.W[0][a] * P.W[1][b] / 4;
+    if (s < 4) return P.W[0][a] * P.W[2][b] / 4;
+    return P.W[1][a] * P.W[2][b] / 4;
+}
+__device__ __forceinline__ bool on_face(int s, int i, int j, int k, int NX, int NY, int NZ) {
+    switch (s) {
+        case 0: return k == 0;
+        case 1: return k == NZ - 1;
+        case 2: return j == 0;
+        case 3: return j == NY - 1;
+        case 4: return i == 0;
+        default: return i == NX - 1;
+    }
+}
+
+// p = P0 * pow(rho*theta*R/P0, gamma)   (euler.cpp:211); explicit rounding so every call site agrees bitwise
+__device__ __forceinline__ double eos_pressure(double P0, double R, double gamma, double rho, double theta) {
+    double x = __ddiv_rn(__dmul_rn(__dmul_rn(rho, theta), R), P0);
+    return __dmul_rn(P0, pow(x, gamma));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// sweep A
+// ---------------------------------------------------------------------------------------------------
+template <int NX, int NY, int NZ, int EPB, bool VISC>
+__global__ void __launch_bounds__(EPB * Dims<NX, NY, NZ>::TPE)
+sweepA_kernel(const __grid_constant__ KParams P) {
+    using Dm = Dims<NX, NY, NZ>;
+    constexpr int NP = Dm::NP, NPS = Dm::NPS, TPE = Dm::TPE;
+    __shared__ double sD[3][MAXN * MAXN];
+    extern __shared__ double dyn_smem[];
+    double (*sR)[3][NP] = reinterpret_cast<double (*)[3][NP]>(dyn_smem);                      // [EPB] contravariant mass flux F.Jin[:,d]
+    double (*sQ)[4][NP] = reinterpret_cast<double (*)[4][NP]>(dyn_smem + EPB * 3 * NP);       // [EPB] Ux,Uy,Uz,theta (VISC only)
+
+    const int tid = threadIdx.x;
+    for (int q = tid; q < 3 * MAXN * MAXN; q += EPB * TPE) sD[q / (MAXN * MAXN)][q % (MAXN * MAXN)] = P.D[q / (MAXN * MAXN)][q % (MAXN * MAXN)];
+    const int el = tid / TPE, t = tid % TPE;
+    const uint32_t eseq = blockIdx.x * EPB + el;
+    const bool active = (eseq < P.nB) && (t < NP);
+    const uint32_t elem = (eseq < P.nB) ? (P.sched ? P.sched[eseq] : eseq) : 0u;
+    const int i = t / (NY * NZ), j = (t / NZ) % NY, k = t % NZ;
+    const size_t idx = (size_t)elem * NPS + t;
+
+    double rho = 0, u[3] = {0, 0, 0}, th = 0, cV = 1, Jin[9];
+#pragma unroll
+    for (int c = 0; c < 9; c++) Jin[c] = 0;
+    if (active) {
+        rho = P.rho_old[idx];
+        u[0] = P.U_old[0][idx]; u[1] = P.U_old[1][idx]; u[2] = P.U_old[2][idx];
+        th = P.T_old[idx] + P.T0;                                   // euler.cpp:181
+        cV = P.cV[idx];
+#pragma unroll
+        for (int c = 0; c < 9; c++) Jin[c] = P.Jinv[c][idx] * cV;   // Jin = Jinv*cV (field.h:3341,3448)
+        const double F0 = u[0] * rho, F1 = u[1] * rho, F2 = u[2] * rho;    // fq = U*rho (euler.cpp:200)
+#pragma unroll
+        for (int d = 0; d < 3; d++) sR[el][d][t] = F0 * Jin[0 * 3 + d] + F1 * Jin[1 * 3 + d] + F2 * Jin[2 * 3 + d];
+        if (VISC) { sQ[el][0][t] = u[0]; sQ[el][1][t] = u[1]; sQ[el][2][t] = u[2]; sQ[el][3][t] = th; }
+    }
+    __syncthreads();
+    if (!active) return;
+
+    // ---- volume terms --------------------------------------------------------------------------
+    // weak divergence (field.h:3443-3464): r[m] -= sum_q (F_q . Jin_q . dpsi(q->m))
+    double r_rho = 0;
+    {
+        double acc = 0;
+#pragma unroll
+        for (int ii = 0; ii < NX; ii++) acc += sR[el][0][ii * NY * NZ + j * NZ + k] * sD[0][ii * NX + i];
+#pragma unroll
+        for (int jj = 0; jj < NY; jj++) acc += sR[el][1][i * NY * NZ + jj * NZ + k] * sD[1][jj * NY + j];
+#pragma unroll
+        for (int kk = 0; kk < NZ; kk++) acc += sR[el][2][i * NY * NZ + j * NZ + kk] * sD[2][kk * NZ + k];
+        r_rho = -acc;
+    }
+    // strong gradients (field.h:3336-3357): G[a][b] = sum_d Jin[a][d] * d(U_b)/d(xi_d)
+    double gU[9], gT[3];
+    if (VISC) {
+#pragma unroll
+        for (int f = 0; f < 4; f++) {
+            double d0 = 0, d1 = 0, d2 = 0;
+#pragma unroll
+            for (int m = 0; m < NX; m++) d0 += sD[0][i * NX + m] * sQ[el][f][m * NY * NZ + j * NZ + k];
+#pragma unroll
+            for (int m = 0; m < NY; m++) d1 += sD[1][j * NY + m] * sQ[el][f][i * NY * NZ + m * NZ + k];
+#pragma unroll
+            for (int m = 0; m < NZ; m++) d2 += sD[2][k * NZ + m] * sQ[el][f][i * NY * NZ + j * NZ + m];
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                const double v = Jin[a * 3 + 0] * d0 + Jin[a * 3 + 1] * d1 + Jin[a * 3 + 2] * d2;
+                if (f < 3) gU[a * 3 + f] = v; else gT[a] = v;
+            }
+        }
+    }
+
+    // ---- surface terms (rusanov field.h:2928-2943, div_flux/grad_flux :3051-3117), face-ID order ----
+#pragma unroll
+    for (int s = 0; s < 6; s++) {
+        if (!on_face(s, i, j, k, NX, NY, NZ)) continue;
+        const uint32_t meta = P.faceMeta[elem * 6 + s];
+        const uint32_t fid = meta & FM_FID_MASK;
+        if (fid == FM_ABSENT) continue;
+        int a, b;
+        const int n = face_slot<NX, NY, NZ>(s, i, j, k, a, b);
+        const size_t oidx = (size_t)P.faceOther[elem * 6 + s] + (fid == FM_GHOST ? n : face_node<NX, NY, NZ>(fid, a, b));
+        const double w = face_weight<NX, NY, NZ>(P, s, a, b);
+        const double* fv = P.faceVec + (size_t)(elem * 6 + s) * 3;
+        const double* fu = P.faceUnit + (size_t)(elem * 6 + s) * 3;
+        const double N0 = fv[0] * w, N1 = fv[1] * w, N2 = fv[2] * w;          // fN[k] (dg.cpp:359)
+        const double nN = fu[0] * N0 + fu[1] * N1 + fu[2] * N2;               // unit(fN).fN
+        const double rho_x = P.rho_old[oidx];
+        const double ux = P.U_old[0][oidx], uy = P.U_old[1][oidx], uz = P.U_old[2][oidx];
+        const double th_x = P.T_old[oidx] + P.T0;
+        const bool own = meta & FM_OWNER;
+        const double al = (meta & FM_HALF) ? 0.5 : 0.0;                       // fI (field.cpp:257-270)
+        // owner / neighbour roles
+        const double rho_o = own ? rho : rho_x, rho_n = own ? rho_x : rho;
+        const double uo0 = own ? u[0] : ux, uo1 = own ? u[1] : uy, uo2 = own ? u[2] : uz;
+        const double un0 = own ? ux : u[0], un1 = own ? uy : u[1], un2 = own ? uz : u[2];
+        const double th_o = own ? th : th_x, th_n = own ? th_x : th;
+        // lambdaMax = (cds(mag(U)) + cds(sqrt(gamma R T)))/2   (euler.cpp:186)
+        const double mo = sqrt(uo0 * uo0 + (uo1 * uo1 + uo2 * uo2)), mn = sqrt(un0 * un0 + (un1 * un1 + un2 * un2));
+        const double co = sqrt(P.gamma * P.R * th_o), cn = sqrt(P.gamma * P.R * th_n);
+        const double lam = ((mo * al + mn * (1 - al)) + (co * al + cn * (1 - al))) / 2;
+        // mass flux
+        const double fo = rho_o * (uo0 * N0 + uo1 * N1 + uo2 * N2), fn = rho_n * (un0 * N0 + un1 * N1 + un2 * N2);
+        const double flux = (fo * al + fn * (1 - al)) - lam * (rho_n - rho_o) * nN;
+        r_rho += own ? flux : -flux;
+        if (VISC) {
+            // grad_flux<strong>: r[c1] += fN (x) (cds(P) - P_o) ; r[c2] -= fN (x) (cds(P) - P_n)
+            const double sgn = own ? 1.0 : -1.0;
+            const double dq[4] = {(uo0 * al + un0 * (1 - al)) - u[0], (uo1 * al + un1 * (1 - al)) - u[1],
+                                  (uo2 * al + un2 * (1 - al)) - u[2], (th_o * al + th_n * (1 - al)) - th};
+            const double Ns[3] = {sgn * N0, sgn * N1, sgn * N2};
+#pragma unroll
+            for (int aa = 0; aa < 3; aa++) {
+                gU[aa * 3 + 0] += Ns[aa] * dq[0];
+                gU[aa * 3 + 1] += Ns[aa] * dq[1];
+                gU[aa * 3 + 2] += Ns[aa] * dq[2];
+                gT[aa] += Ns[aa] * dq[3];
+            }
+        }
+    }
+
+    // ---- rho update (addTemporal<1> field.h:3875-3920, SolveTexplicit solve.cpp:563-570) ----
+    const double ap0 = (-1.0 / P.dt) * cV;
+    const double rho_new = (r_rho + rho * ap0) / ap0;
+    P.rho_new[idx] = rho_new;
+    // p = P0 (rho T R / P0)^gamma ; p -= p_ref   (euler.cpp:211-213)
+    P.p[idx] = __dsub_rn(eos_pressure(P.P0, P.R, P.gamma, rho_new, th), P.p_ref[idx]);
+    if (VISC) {
+#pragma unroll
+        for (int c = 0; c < 9; c++) P.GU[c][idx] = gU[c] / cV;      // per-unit-volume (field.h:3359)
+#pragma unroll
+        for (int c = 0; c < 3; c++) P.GT[c][idx] = gT[c] / cV;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// sweep B
+// ---------------------------------------------------------------------------------------------------
+template <int NX, int NY, int NZ, int EPB, bool VISC>
+__global__ void __launch_bounds__(EPB * Dims<NX, NY, NZ>::TPE)
+sweepB_kernel(const __grid_constant__ KParams P) {
+    using Dm = Dims<NX, NY, NZ>;
+    constexpr int NP = Dm::NP, NPS = Dm::NPS, TPE = Dm::TPE;
+    __shared__ double sD[3][MAXN * MAXN];
+    extern __shared__ double dyn_smem[];
+    double (*sH)[12][NP] = reinterpret_cast<double (*)[12][NP]>(dyn_smem);   // [EPB] contravariant fluxes: [a*3+d] momentum a, [9+d] theta
+
+    const int tid = threadIdx.x;
+    for (int q = tid; q < 3 * MAXN * MAXN; q += EPB * TPE) sD[q / (MAXN * MAXN)][q % (MAXN * MAXN)] = P.D[q / (MAXN * MAXN)][q % (MAXN * MAXN)];
+    const int el = tid / TPE, t = tid % TPE;
+    const uint32_t eseq = blockIdx.x * EPB + el;
+    const bool active = (eseq < P.nB) && (t < NP);
+    const uint32_t elem = (eseq < P.nB) ? (P.sched ? P.sched[eseq] : eseq) : 0u;
+    const int i = t / (NY * NZ), j = (t / NZ) % NY, k = t % NZ;
+    const size_t idx = (size_t)elem * NPS + t;
+
+    double rho_o = 0, rho_nw = 1, u[3] = {0, 0, 0}, th = 0, pp = 0, cV = 1, mu = 0;
+    double gU[9], gT[3];
+    if (active) {
+        rho_o = P.rho_old[idx];
+        rho_nw = P.rho_new[idx];
+        u[0] = P.U_old[0][idx]; u[1] = P.U_old[1][idx]; u[2] = P.U_old[2][idx];
+        th = P.T_old[idx] + P.T0;
+        pp = P.p[idx];
+        cV = P.cV[idx];
+        mu = VISC ? rho_o * P.nu : 0.0;                                   // mu = rho*viscosity, OLD rho (euler.cpp:189)
+        double Jin[9];
+#pragma unroll
+        for (int c = 0; c < 9; c++) Jin[c] = P.Jinv[c][idx] * cV;
+        if (VISC) {
+#pragma unroll
+            for (int c = 0; c < 9; c++) gU[c] = P.GU[c][idx];
+#pragma unroll
+            for (int c = 0; c < 3; c++) gT[c] = P.GT[c][idx];
+        }
+        // fq = mul(Fc,U) + I p - mu grad U (euler.cpp:232) ; Fc = rho_old U (:184)
+        const double Fc[3] = {rho_o * u[0], rho_o * u[1], rho_o * u[2]};
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            double fq[3];
+#pragma unroll
+            for (int b = 0; b < 3; b++) {
+                fq[b] = Fc[a] * u[b] + (a == b ? pp : 0.0);
+                if (VISC) fq[b] -= mu * gU[a * 3 + b];
+            }
+#pragma unroll
+            for (int d = 0; d < 3; d++) sH[el][a * 3 + d][t] = fq[0] * Jin[0 * 3 + d] + fq[1] * Jin[1 * 3 + d] + fq[2] * Jin[2 * 3 + d];
+        }
+        {
+            // fq = Fc*T - (mu/Pr) grad T (euler.cpp:249-250)
+            double fq[3];
+#pragma unroll
+            for (int b = 0; b < 3; b++) {
+                fq[b] = Fc[b] * th;
+                if (VISC) fq[b] -= (mu * P.iPr) * gT[b];
+            }
+#pragma unroll
+            for (int d = 0; d < 3; d++) sH[el][9 + d][t] = fq[0] * Jin[0 * 3 + d] + fq[1] * Jin[1 * 3 + d] + fq[2] * Jin[2 * 3 + d];
+        }
+    }
+    __syncthreads();
+    if (!active) return;
+
+    double r[4];
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        double acc = 0;
+#pragma unroll
+        for (int ii = 0; ii < NX; ii++) acc += sH[el][a * 3 + 0][ii * NY * NZ + j * NZ + k] * sD[0][ii * NX + i];
+#pragma unroll
+        for (int jj = 0; jj < NY; jj++) acc += sH[el][a * 3 + 1][i * NY * NZ + jj * NZ + k] * sD[1][jj * NY + j];
+#pragma unroll
+        for (int kk = 0; kk < NZ; kk++) acc += sH[el][a * 3 + 2][i * NY * NZ + j * NZ + kk] * sD[2][kk * NZ + k];
+        r[a] = -acc;
+    }
+
+#pragma unroll
+    for (int s = 0; s < 6; s++) {
+        if (!on_face(s, i, j, k, NX, NY, NZ)) continue;
+        const uint32_t meta = P.faceMeta[elem * 6 + s];
+        const uint32_t fid = meta & FM_FID_MASK;
+        if (fid == FM_ABSENT) continue;
+        int a, b;
+        const int n = face_slot<NX, NY, NZ>(s, i, j, k, a, b);
+        const size_t oidx = (size_t)P.faceOther[elem * 6 + s] + (fid == FM_GHOST ? n : face_node<NX, NY, NZ>(fid, a, b));
+        const double w = face_weight<NX, NY, NZ>(P, s, a, b);
+        const double* fv = P.faceVec + (size_t)(elem * 6 + s) * 3;
+        const double* fu = P.faceUnit + (size_t)(elem * 6 + s) * 3;
+        const double N[3] = {fv[0] * w, fv[1] * w, fv[2] * w};
+        const double nN = fu[0] * N[0] + fu[1] * N[1] + fu[2] * N[2];
+        const bool own = meta & FM_OWNER;
+        const double al = (meta & FM_HALF) ? 0.5 : 0.0;
+        // the other side
+        const double xrho_o = P.rho_old[oidx], xrho_nw = P.rho_new[oidx];
+        const double xu[3] = {P.U_old[0][oidx], P.U_old[1][oidx], P.U_old[2][oidx]};
+        const double xth = P.T_old[oidx] + P.T0;
+        const double xpp = P.p[oidx];
+        // per-side normal fluxes  (fq.N)_a = Fc_a (U.N) + p N_a - mu (G.N)_a ;  (fT.N) = theta (Fc.N) - mu/Pr (gT.N)
+        double me[4], xe[4];
+        {
+            const double un = u[0] * N[0] + u[1] * N[1] + u[2] * N[2];
+            const double xun = xu[0] * N[0] + xu[1] * N[1] + xu[2] * N[2];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                me[c] = (rho_o * u[c]) * un + pp * N[c];
+                xe[c] = (xrho_o * xu[c]) * xun + xpp * N[c];
+            }
+            me[3] = th * (rho_o * un);
+            xe[3] = xth * (xrho_o * xun);
+            if (VISC) {
+                const double xmu = xrho_o * P.nu;
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    me[c] -= mu * (gU[c * 3 + 0] * N[0] + gU[c * 3 + 1] * N[1] + gU[c * 3 + 2] * N[2]);
+                    xe[c] -= xmu * (P.GU[c * 3 + 0][oidx] * N[0] + P.GU[c * 3 + 1][oidx] * N[1] + P.GU[c * 3 + 2][oidx] * N[2]);
+                }
+                me[3] -= (mu * P.iPr) * (gT[0] * N[0] + gT[1] * N[1] + gT[2] * N[2]);
+                xe[3] -= (xmu * P.iPr) * (P.GT[0][oidx] * N[0] + P.GT[1][oidx] * N[1] + P.GT[2][oidx] * N[2]);
+            }
+        }
+        // lambdaMax from the OLD state on both sides (euler.cpp:186); symmetric in owner/neighbour when fI = 0.5
+        const double mm = sqrt(u[0] * u[0] + (u[1] * u[1] + u[2] * u[2])), xm = sqrt(xu[0] * xu[0] + (xu[1] * xu[1] + xu[2] * xu[2]));
+        const double mc = sqrt(P.gamma * P.R * th), xc = sqrt(P.gamma * P.R * xth);
+        const double wo = own ? al : 1 - al, wx = own ? 1 - al : al;       // weight of my side / the other side
+        const double lam = ((mm * wo + xm * wx) + (mc * wo + xc * wx)) / 2;
+        // dissipation: - unit(fN)_a lam ((q_n - q_o).fN) for q = rho_new U ; - lam (q_n - q_o) unit(fN).fN for q = rho_new theta
+        const double sg = own ? 1.0 : -1.0;                                 // (q_n - q_o) = sg * (q_other - q_mine)
+        double dqN = 0;
+#pragma unroll
+        for (int c = 0; c < 3; c++) dqN += (xrho_nw * xu[c] - rho_nw * u[c]) * N[c];
+        const double dqT = xrho_nw * xth - rho_nw * th;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const double flux = (me[c] * wo + xe[c] * wx) - fu[c] * (lam * (sg * dqN));
+            r[c] += sg * flux;
+        }
+        {
+            const double flux = (me[3] * wo + xe[3] * wx) - lam * (sg * dqT) * nN;
+            r[3] += sg * flux;
+        }
+    }
+
+    // ---- updates (src field.h:3712-3723, addTemporal<1> :3875-3920 with rho/rho0, SolveTexplicit) ----
+    const double ap0 = (-1.0 / P.dt) * cV;
+    const double ap = ap0 * rho_nw;
+    double g[3] = {P.g[0], P.g[1], P.g[2]};
+    if (P.has_gfield) { g[0] = P.gfield[0][idx]; g[1] = P.gfield[1][idx]; g[2] = P.gfield[2][idx]; }
+    const double drho = P.buoyancy ? (rho_nw - P.rho_ref[idx]) : 0.0;      // Sc = (rho - rho_ref) g (euler.cpp:224-225)
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const double Su = (r[c] - (drho * g[c]) * cV) + (u[c] * rho_o) * ap0;
+        P.U_new[c][idx] = Su / ap;
+    }
+    {
+        const double Su = r[3] + (th * rho_o) * ap0;
+        P.T_new[idx] = Su / ap - P.T0;                                      // euler.cpp:286
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// boundary (ghost) updates: applyExplicitBCs (field.h:2586-2727) and fillBCs(r, fIndex) (:2731-2769)
+// ---------------------------------------------------------------------------------------------------
+struct BCRec {            // BCondition<T> payload (field.h:146-150), in the reference's member order
+    double value[3];
+    double shape;
+    double tvalue[3];
+    double tshape;
+    double zMin;
+};
+
+struct BCParams {
+    uint32_t nB, nG;
+    uint64_t ghostBase;
+    double P0, T0, R, gamma;
+    int visc;
+    int phase;                       // 0 = after sweep A, 1 = after sweep B
+    // ghost-cell tables [nG]
+    const uint32_t* bOwner;          // owner element
+    const uint8_t* bFid;             // owner's local face id
+    const double* bUnit;             // [nG*3] unit(gFN)
+    const uint8_t* kind[4];          // per field (enum nsem_field order): bc kind per ghost cell
+    const uint32_t* rec[4];          // per field: index into recs
+    const uint32_t* peer[4];         // per field: CYCLIC partner ghost cell
+    const double* fixedv[4];         // per field: FIXED values [nG*NPF*comps] (may be null)
+    const BCRec* recs;
+    // fields
+    double* rho_new;
+    double* p;
+    const double* T_old;
+    const double* p_ref;
+    double* GU[9];
+    double* GT[3];
+    double* U_new[3];
+    double* T_new;
+};
+
+__device__ __forceinline__ double bc_scalar(int kind, double owner, const BCRec& rc, double peer, double fixedv) {
+    switch (kind) {
+        case 1: return owner;                                            // NEUMANN: owner + value*|dx|, |dx| == 0
+        case 2: return rc.value[0];                                      // DIRICHLET
+        case 3: return owner;                                            // SYMMETRY of a scalar (tensor.h:483-485)
+        case 4: return peer;                                             // CYCLIC
+        case 6: return fixedv;                                           // FIXED
+        case 7: return rc.shape * rc.value[0] + (1 - rc.shape) * owner;  // ROBIN
+        default: return owner;
+    }
+}
+
+// sym(Vector p, Vector n) (tensor.h:486-494): tangential projection rescaled to |p|
+__device__ __forceinline__ void sym_vector(const double p[3], const double en[3], double out[3]) {
+    const double Axx = 1.0 - en[0] * en[0], Ayy = 1.0 - en[1] * en[1], Azz = 1.0 - en[2] * en[2];
+    const double Axy = -(en[0] * en[1]), Ayz = -(en[1] * en[2]), Axz = -(en[0] * en[2]);
+    const double r0 = Axx * p[0] + Axy * p[1] + Axz * p[2];
+    const double r1 = Axy * p[0] + Ayy * p[1] + Ayz * p[2];
+    const double r2 = Axz * p[0] + Ayz * p[1] + Azz * p[2];
+    const double magR = sqrt(r0 * r0 + (r1 * r1 + r2 * r2));
+    // equal(magR, 0) with EqualEpsilon = 1e-7 (tensor.h:462,469-474)
+    if (magR <= 1e-7) { out[0] = r0; out[1] = r1; out[2] = r2; return; }
+    const double f = sqrt(p[0] * p[0] + (p[1] * p[1] + p[2] * p[2])) / magR;
+    out[0] = r0 * f; out[1] = r1 * f; out[2] = r2 * f;
+}
+
+template <int NX, int NY, int NZ>
+__global__ void __launch_bounds__(256) bc_kernel(const __grid_constant__ BCParams B) {
+    using Dm = Dims<NX, NY, NZ>;
+    constexpr int NPF = Dm::NPF, NPS = Dm::NPS, GPS = Dm::GPS;
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (uint64_t)B.nG * NPF) return;
+    const uint32_t g = (uint32_t)(gid / NPF);
+    const int n = (int)(gid % NPF);
+    bool valid;
+    const int ln = face_node_from_slot<NX, NY, NZ>(B.bFid[g], n, valid);
+    if (!valid) return;
+    const size_t oi = (size_t)B.bOwner[g] * NPS + ln;              // owner node
+    const size_t gi = B.ghostBase + (size_t)g * GPS + n;           // ghost node
+
+    auto peer_node = [&](int f) -> size_t {
+        const uint32_t pg = B.peer[f][g];
+        bool v2;
+        const int pl = face_node_from_slot<NX, NY, NZ>(B.bFid[pg], n, v2);
+        return (size_t)B.bOwner[pg] * NPS + pl;
+    };
+
+    if (B.phase == 0) {
+        // rho (after Solve of the rho-equation, solve.cpp:574-581)
+        {
+            const int kd = B.kind[0][g];
+            if (kd != 5) {
+                const double peer = (kd == 4) ? B.rho_new[peer_node(0)] : 0.0;
+                const double fx = (kd == 6) ? B.fixedv[0][(size_t)g * NPF + n] : 0.0;
+                B.rho_new[gi] = bc_scalar(kd, B.rho_new[oi], B.recs[B.rec[0][g]], peer, fx);
+            }
+        }
+        // p: the BC acts on the full pressure, then p -= p_ref (euler.cpp:211-213)
+        {
+            const int kd = B.kind[1][g];
+            if (kd != 5) {
+                const double po = eos_pressure(B.P0, B.R, B.gamma, B.rho_new[oi], B.T_old[oi] + B.T0);
+                double peer = 0.0;
+                if (kd == 4) {
+                    const size_t pn = peer_node(1);
+                    peer = eos_pressure(B.P0, B.R, B.gamma, B.rho_new[pn], B.T_old[pn] + B.T0);
+                }
+                const double fx = (kd == 6) ? B.fixedv[1][(size_t)g * NPF + n] : 0.0;
+                const double pg = bc_scalar(kd, po, B.recs[B.rec[1][g]], peer, fx);
+                B.p[gi] = __dsub_rn(pg, B.p_ref[gi]);
+            }
+        }
+        // gradients: ghost = owner copy, then NEUMANN -> value (type-punned), SYMMETRY -> 0 (field.h:2735-2766)
+        if (B.visc) {
+            {
+                const int kd = B.kind[2][g];
+                if (kd != 5) {
+                    const BCRec& rc = B.recs[B.rec[2][g]];
+                    // BCondition<Vector> read as BCondition<Tensor>: 9 consecutive doubles from &value,
+                    // in Tensor AoS order XX,YY,ZZ,XY,YZ,XZ,YX,ZY,ZX (tensor.h:452-454)
+                    const double raw[9] = {rc.value[0], rc.value[1], rc.value[2], rc.shape, rc.tvalue[0],
+                                           rc.tvalue[1], rc.tvalue[2], rc.tshape, rc.zMin};
+                    const int rm[9] = {0, 4, 8, 1, 5, 2, 3, 7, 6};       // AoS component -> row-major a*3+b
+#pragma unroll
+                    for (int c = 0; c < 9; c++) {
+                        double v = B.GU[rm[c]][oi];
+                        if (kd == 1) v = raw[c];
+                        else if (kd == 3) v = 0.0;
+                        B.GU[rm[c]][gi] = v;
+                    }
+                }
+            }
+            {
+                const int kd = B.kind[3][g];
+                if (kd != 5) {
+                    const BCRec& rc = B.recs[B.rec[3][g]];
+                    const double raw[3] = {rc.value[0], rc.shape, rc.tvalue[0]};   // BCondition<Scalar> read as <Vector>
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        double v = B.GT[c][oi];
+                        if (kd == 1) v = raw[c];
+                        else if (kd == 3) v = 0.0;
+                        B.GT[c][gi] = v;
+                    }
+                }
+            }
+        }
+    } else {
+        // U (Solve of the U-equation)
+        {
+            const int kd = B.kind[2][g];
+            if (kd != 5) {
+                const BCRec& rc = B.recs[B.rec[2][g]];
+                const double o[3] = {B.U_new[0][oi], B.U_new[1][oi], B.U_new[2][oi]};
+                double out[3] = {o[0], o[1], o[2]};
+                if (kd == 2) { out[0] = rc.value[0]; out[1] = rc.value[1]; out[2] = rc.value[2]; }
+                else if (kd == 3) { const double en[3] = {B.bUnit[g * 3], B.bUnit[g * 3 + 1], B.bUnit[g * 3 + 2]}; sym_vector(o, en, out); }
+                else if (kd == 4) { const size_t pn = peer_node(2); out[0] = B.U_new[0][pn]; out[1] = B.U_new[1][pn]; out[2] = B.U_new[2][pn]; }
+                else if (kd == 6) { const double* fx = B.fixedv[2] + ((size_t)g * NPF + n) * 3; out[0] = fx[0]; out[1] = fx[1]; out[2] = fx[2]; }
+                else if (kd == 7) {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) out[c] = rc.shape * rc.value[c] + (1 - rc.shape) * o[c];
+                }
+                B.U_new[0][gi] = out[0]; B.U_new[1][gi] = out[1]; B.U_new[2][gi] = out[2];
+            }
+        }
+        // T: the BC is applied while the field holds theta = T + T0; T -= T0 follows (euler.cpp:258,286)
+        {
+            const int kd = B.kind[3][g];
+            if (kd != 5) {
+                const BCRec& rc = B.recs[B.rec[3][g]];
+                double v = B.T_new[oi];
+                if (kd == 2) v = rc.value[0] - B.T0;
+                else if (kd == 4) v = B.T_new[peer_node(3)];
+                else if (kd == 6) v = B.fixedv[3][(size_t)g * NPF + n] - B.T0;
+                else if (kd == 7) v = (rc.shape * rc.value[0] + (1 - rc.shape) * (v + B.T0)) - B.T0;
+                B.T_new[gi] = v;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// layout conversion: reference AoS node arrays <-> device SoA (element stride NPS, compact ghost cells)
+// ---------------------------------------------------------------------------------------------------
+// src: [nRef*comps] AoS in reference node order; dst[c]: device arrays. ghostRef[g*NPF+n] = reference node of
+// ghost slot (or 0xffffffff).
+__global__ void scatter_to_device(const double* __restrict__ src, int comps, double* const* dst, const int* compMap,
+                                  uint32_t nB, int NP, int NPS, uint32_t nG, int NPF, int GPS,
+                                  const uint32_t* __restrict__ ghostRef, uint64_t ghostBase) {
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t nReal = (uint64_t)nB * NP;
+    if (gid < nReal) {
+        const uint64_t c = gid / NP, t = gid % NP;
+        for (int k = 0; k < comps; k++) dst[k][c * NPS + t] = src[gid * comps + compMap[k]];
+    } else if (gid < nReal + (uint64_t)nG * NPF) {
+        const uint64_t q = gid - nReal;
+        const uint32_t ref = ghostRef[q];
+        if (ref != 0xffffffffu) {
+            const uint64_t g = q / NPF, n = q % NPF;
+            for (int k = 0; k < comps; k++) dst[k][ghostBase + g * GPS + n] = src[(uint64_t)ref * comps + compMap[k]];
+        }
+    }
+}
+__global__ void gather_from_device(double* __restrict__ dstRef, int comps, const double* const* src, const int* compMap,
+                                   uint32_t nB, int NP, int NPS, uint32_t nG, int NPF, int GPS,
+                                   const uint32_t* __restrict__ ghostRef, uint64_t ghostBase) {
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t nReal = (uint64_t)nB * NP;
+    if (gid < nReal) {
+        const uint64_t c = gid / NP, t = gid % NP;
+        for (int k = 0; k < comps; k++) dstRef[gid * comps + compMap[k]] = src[k][c * NPS + t];
+    } else if (gid < nReal + (uint64_t)nG * NPF) {
+        const uint64_t q = gid - nReal;
+        const uint32_t ref = ghostRef[q];
+        if (ref != 0xffffffffu) {
+            const uint64_t g = q / NPF, n = q % NPF;
+            for (int k = 0; k < comps; k++) dstRef[(uint64_t)ref * comps + compMap[k]] = src[k][ghostBase + g * GPS + n];
+        }
+    }
+}
+
+}  // namespace nsem

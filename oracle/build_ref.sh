@@ -52,6 +52,7 @@ build_variant() {
     g++ -std=c++17 $flags -DUSE_DOUBLE -DUSE_EXPR_TMPL -w $INC "$R/apps/prepare/prepareApp.cpp" "$dir/libnebulasem.a" -o "$dir/prepare" &
     g++ -std=c++17 $flags -DUSE_DOUBLE -DUSE_EXPR_TMPL -w $INC "$HERE/tools/geomdump.cpp" "$dir/libnebulasem.a" -o "$dir/geomdump" &
     wait
+    rm -rf "$dir/obj" "$dir/libnebulasem.a"      # keep oracle/_ref small: it travels to the GPU box with every gpurun
     echo "$flags" > "$stamp"
 }
 

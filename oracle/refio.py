@@ -160,7 +160,7 @@ def write_grid_text(path: str, g: Grid) -> None:
     out = []
     out.append(f"{len(g.vertices)}\n{{")
     for v in g.vertices:
-        out.append(f"{v[0]!r} {v[1]!r} {v[2]!r}")
+        out.append(f"{float(v[0])!r} {float(v[1])!r} {float(v[2])!r}")
     out.append("}")
     out.append(f"{len(g.facets)}\n{{")
     for f in g.facets:
