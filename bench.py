@@ -1,0 +1,259 @@
+#!/usr/bin/env python
+"""bench.py -- dGSEM Euler DOF-updates/s per stage (BASELINE.json metric) on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n CELLS_PER_SIDE]
+
+Workload (BASELINE.json configs[1]): rising thermal bubble, 3-D synthetic hex mesh of n^3 elements (default
+100^3 = 1.0e6 elements, order 4, 1.25e8 LGL nodes), FP64, diffusion + buoyancy on, one reference time step =
+one explicit stage (SURVEY finding 1).  One step = one pass of the hot path (sweep A, ghost update, sweep B,
+ghost update) over the whole mesh.  DOF-updates/s = 5 * nodes * steps / time.
+
+One JSON line on stdout (rank 0).  `value` = device-resident throughput timed with CUDA events on the launching
+stream; `e2e` = the same step driven through the C ABI with HOST buffers (pinned upload of rho,U,T + step +
+download inside the timed region); `roofline` = algorithmic bytes of the two sweeps / event time against the
+measured HBM copy bandwidth; `cpu_baseline` = the reference's own CPU code (oracle/_ref/fast/euler, OpenMP on
+all host cores) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ORDER = 4
+NP = (ORDER + 1) ** 3
+
+
+# ------------------------------------------------------------------------------------------------------
+def algorithmic_bytes_per_node(visc: bool = True) -> dict:
+    """Bytes each sweep must move per LGL node for the data flow that is implemented.
+    Every node array is counted once per sweep that touches it; neighbour-trace re-reads are assumed to hit L2."""
+    n1 = ORDER + 1
+    face_tab = 6 * (4 + 4 + 24 + 24) / NP                     # faceOther, faceMeta, faceVec, faceUnit per element
+    a_read = 5 + 10 + 1                                       # rho,U(3),T ; Jinv(9),cV ; p_ref
+    a_write = 1 + 1 + (12 if visc else 0)                     # rho_new, p', gradU(9)+gradT(3)
+    b_read = 2 + 4 + 1 + (12 if visc else 0) + 10 + 1         # rho_old,rho_new ; U,T ; p' ; gradients ; Jinv,cV ; rho_ref
+    b_write = 4                                               # U_new(3), T_new
+    pad = 128.0 / NP                                          # element stride padded from 125 to 128 doubles
+    A = 8 * (a_read + a_write) * pad + face_tab
+    B = 8 * (b_read + b_write) * pad + face_tab
+    return dict(A=A, B=B, total=A + B, survey_B_alg=8 * (62 + 24 / n1))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(smax), "power_w_max": max(power), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the UNMODIFIED reference solver on the host cores, bounded sample
+# ------------------------------------------------------------------------------------------------------
+def run_reference_sample(n_side: int, steps: int, warmup: int, threads: int | None = None) -> dict:
+    from oracle import cases, run_ref          # test infrastructure, allowed here (cpu_baseline / reference arm only)
+    variant = "fast" if run_ref.have_ref("fast") else "parity"
+    if not run_ref.have_ref(variant):
+        return {"unavailable": "oracle/_ref has no compiled reference (run oracle/build_ref.sh where /root/reference exists)"}
+    threads = threads or os.cpu_count() or 1
+    d = tempfile.mkdtemp(prefix="nsem_ref_")
+    try:
+        total = warmup + steps
+        c = cases.bubble3d(n=n_side, order=ORDER, scheme="AB1")
+        c.write(d, end_step=total, write_interval=10 * total + 7)       # no field dump inside the timed run
+        wall, out = run_ref.run_euler(d, variant=variant, threads=threads, timeout=3000)
+        stamps = [int(m.group(1)) for m in re.finditer(r"^(\d+) \[0\] Time ", out, flags=re.M)]
+        end = re.search(r"^(\d+) \[0\] Exiting", out, flags=re.M)
+        if len(stamps) < total or not end:
+            return {"unavailable": "could not parse the reference log"}
+        stamps.append(int(end.group(1)))
+        t_ms = stamps[total] - stamps[warmup]
+        nodes = n_side ** 3 * NP
+        val = 5.0 * nodes * steps / (t_ms * 1e-3)
+        return {"value": val, "unit": "DOF-updates/s", "cores": threads, "kind": "reference",
+                "sample": f"bubble3d {n_side}^3 elements order {ORDER} ({nodes} nodes), {steps} steps after {warmup} warm-up, "
+                          f"oracle/_ref/{variant}/euler (unmodified reference, 1 rank x {threads} OpenMP threads; no MPI in the image)",
+                "ms_per_step": t_ms / steps}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=100, help="elements per side of the cubic mesh")
+    ap.add_argument("--ref-n", type=int, default=16, help="elements per side of the CPU reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    steps, warmup = args.steps, max(3, args.warmup)
+    config = {"workload": f"rising thermal bubble 3-D synthetic hex mesh, order {ORDER}, {args.n}^3 = {args.n ** 3} elements per GPU "
+                          f"({args.n ** 3 * NP} LGL nodes), diffusion+buoyancy on, dt 0.00125, one forward-Euler stage per step",
+              "elements_per_gpu": args.n ** 3, "order": ORDER, "l2": "state and metrics (tens of GB) far exceed the 126 MB L2; no flush needed"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        r = run_reference_sample(args.ref_n, steps, warmup)
+        line = {"impl": "reference", "metric": "dGSEM Euler DOF-updates/s per stage", "unit": "DOF-updates/s", "n_gpus": args.gpus,
+                "steps": steps, "warmup": warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": config}
+        if "unavailable" in r:
+            line["unavailable"] = r["unavailable"]
+        else:
+            line.update({"value": r["value"], "ms_per_step": r["ms_per_step"], "cpu_baseline": r,
+                         "e2e": {"value": r["value"], "unit": "DOF-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        print(json.dumps(line), flush=True)
+        return 0
+
+    import numpy as np
+    import torch
+    from nebulasem_b200 import host
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    if world > 1:
+        raise SystemExit("bench.py: multi-partition halo is not wired into the bench yet")
+    device = local_rank
+    torch.cuda.set_device(device)
+
+    t0 = time.time()
+    s = host.Solver.synthetic("bubble3d", args.n, args.n, args.n, ORDER)
+    t_setup = time.time() - t0
+    s.attach(device)
+    nodes = s.gBCSfield
+    launches0 = s.launch_count
+
+    s.step(warmup)
+    s.sync()
+    sampler = ClockSampler(device)
+    sampler.start()
+    ms, _ = s.time_steps(steps, per_kernel=False)
+    clocks = sampler.stop()
+    launches = s.launch_count - launches0 - 4 * warmup     # kernels inside the timed region
+    ms_pk_total, pk = s.time_steps(max(2, steps // 2), per_kernel=True)
+    pk_steps = max(2, steps // 2)
+    value = 5.0 * nodes * steps / (ms * 1e-3)
+
+    # finite-state sanity after all those steps (a diverged run would be a meaningless number)
+    s.download()
+    rho, U, T, p = s.state()
+    if not (np.isfinite(rho).all() and np.isfinite(U).all() and np.isfinite(T).all()):
+        raise SystemExit("bench.py: state is not finite after the timed steps")
+
+    # roofline of the dominant kernel (sweep B) and of the pair
+    bpn = algorithmic_bytes_per_node(visc=True)
+    peak, peak_src = measured_peak_gbs()
+    tA, tB = pk[0] / pk_steps * 1e-3, pk[2] / pk_steps * 1e-3
+    achieved_B = bpn["B"] * nodes / tB / 1e9
+    achieved_A = bpn["A"] * nodes / tA / 1e9
+    roofline = {"bound": "hbm", "kernel": "sweepB_kernel<5,5,5,2,true>", "achieved": achieved_B, "peak": peak, "unit": "GB/s",
+                "frac": achieved_B / peak, "traffic": None, "peak_source": peak_src,
+                "bytes_per_node": {"sweepA": bpn["A"], "sweepB": bpn["B"], "step": bpn["total"], "survey_B_alg": bpn["survey_B_alg"]},
+                "sweepA": {"achieved": achieved_A, "frac": achieved_A / peak, "ms": tA * 1e3},
+                "sweepB": {"achieved": achieved_B, "frac": achieved_B / peak, "ms": tB * 1e3},
+                "bc_ms": [pk[1] / pk_steps, pk[3] / pk_steps],
+                "step": {"achieved": bpn["total"] * nodes / (ms / steps * 1e-3) / 1e9, "frac": bpn["total"] * nodes / (ms / steps * 1e-3) / 1e9 / peak}}
+
+    # e2e: host buffers in, host buffers out, every step
+    e2e = None
+    if not args.no_e2e:
+        e_steps = max(1, min(steps, 3))
+        s.upload(); s.step(1); s.download()                # warm the transfer path
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        for _ in range(e_steps):
+            s.upload()
+            s.step(1)
+            s.download()
+        torch.cuda.synchronize()
+        dt_e = time.perf_counter() - t1
+        gall = s.gALL
+        e2e = {"value": 5.0 * nodes * e_steps / dt_e, "unit": "DOF-updates/s", "h2d_bytes_per_step": 6 * gall * 8,
+               "d2h_bytes_per_step": 6 * gall * 8, "steps": e_steps, "ms_per_step": dt_e / e_steps * 1e3,
+               "what": "nsem_upload_state(rho,U,T,p host arrays) + nsem_euler_step(1) + nsem_download_state, wall clock"}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = run_reference_sample(args.ref_n, 5, 1)
+
+    line = {"metric": "dGSEM Euler DOF-updates/s per stage", "value": value, "unit": "DOF-updates/s", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config, "node_updates_per_s": value / 5.0, "roofline": roofline,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "setup_s": t_setup}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -36,5 +36,33 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+HOST_LIB = os.path.join(LIBDIR, "libnsem_host.so")
+EULER_BIN = os.path.join(LIBDIR, "euler")
+CXX = os.environ.get("NSEM_CXX", "g++")   # the image's $CXX wrapper (/opt/gcc) lacks libgomp.spec
+# -ffp-contract=off: geometry and reference-state arithmetic must round like the reference's own -O2 build
+HOST_FLAGS = ["-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-fopenmp", "-Wall", "-Wno-unknown-pragmas"]
+
+
+def build_host(force: bool = False) -> str:
+    hdir = os.path.join(CSRC, "host")
+    srcs = [os.path.join(hdir, f) for f in ("io.cpp", "mesh.cpp", "dg.cpp", "euler_app.cpp", "capi_host.cpp")]
+    deps = srcs + [os.path.join(hdir, "nsem_host.h"), os.path.join(ROOT, "include", "nsem_c.h"), LIB]
+    if force or not _newer(HOST_LIB, deps):
+        cmd = [CXX, *HOST_FLAGS, "-shared", *srcs, "-o", HOST_LIB, "-L" + LIBDIR, "-lnsem_cuda", "-Wl,-rpath,$ORIGIN"]
+        print("[nebulasem_b200.build]", " ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+    main = os.path.join(hdir, "euler_main.cpp")
+    if force or not _newer(EULER_BIN, [main, HOST_LIB]):
+        cmd = [CXX, *HOST_FLAGS, main, "-o", EULER_BIN, "-L" + LIBDIR, "-lnsem_host", "-lnsem_cuda", "-Wl,-rpath,$ORIGIN"]
+        print("[nebulasem_b200.build]", " ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+    return HOST_LIB
+
+
+def build_all(force: bool = False, verbose: bool = False) -> None:
+    build_cuda(force, verbose)
+    build_host(force)
+
+
 if __name__ == "__main__":
-    build_cuda(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)

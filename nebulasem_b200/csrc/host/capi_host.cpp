@@ -1,0 +1,202 @@
+// capi_host.cpp -- C entry points of libnsem_host.so for the Python test/bench harness and other FFI users.
+// Wraps nsemh::EulerSolver (euler_app.cpp); every call returns 0 on success, the message is in nsemh_error().
+#include <cmath>
+#include <cstring>
+
+#include "nsem_host.h"
+
+using namespace nsemh;
+
+struct nsemh_solver {
+    EulerSolver s;
+    std::string err;
+};
+static std::string g_err;
+
+namespace {
+struct HillArg { double H, xc, hw, Lz; };
+void hill_map(Vec3& v, const void* a) {
+    const HillArg* h = (const HillArg*)a;
+    const double PI = 3.14159265358979323846264;
+    const double x = v[0];
+    double ht = 0;
+    if (std::fabs(x - h->xc) < h->hw) {
+        const double c = std::cos(0.5 * PI * (x - h->xc) / h->hw);
+        ht = h->H * (c * c);
+    }
+    v[2] = ht + v[2] * (h->Lz - ht) / h->Lz;
+}
+FieldFile mkfield(int comps, const std::string& kind, std::vector<double> a, const std::vector<BCond>& bcs) {
+    FieldFile f;
+    f.comps = comps;
+    f.inits.push_back({kind, std::move(a)});
+    f.bcs = bcs;
+    return f;
+}
+std::vector<BCond> all(const std::vector<std::string>& patches, const std::string& type) {
+    std::vector<BCond> v;
+    for (auto& p : patches) { BCond b; b.patch = p; b.type = type; v.push_back(b); }
+    return v;
+}
+}  // namespace
+
+extern "C" {
+
+const char* nsemh_error(const nsemh_solver* h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+void nsemh_close(nsemh_solver* h) { delete h; }
+
+// Full pre-loop sequence of the euler app on a case directory (controls, <mesh>_<step>, rho/U/T/p<step>).
+nsemh_solver* nsemh_open_case(const char* dir, int step) {
+    nsemh_solver* h = new nsemh_solver();
+    try {
+        h->s.read_controls(dir);
+        h->s.load_mesh(step);
+        h->s.read_fields(step);
+        h->s.setup();
+        return h;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        delete h;
+        return nullptr;
+    }
+}
+
+// In-memory synthetic cases (same definitions as oracle/cases.py): kind in {bubble2d, bubble3d, vortex, hill3d}.
+nsemh_solver* nsemh_synthetic(const char* kind_, int nx, int ny, int nz, int order) {
+    nsemh_solver* h = new nsemh_solver();
+    EulerSolver& s = h->s;
+    const std::string kind = kind_;
+    try {
+        s.time_scheme = "BDF1";
+        s.viscosity = 1.5;
+        if (kind == "bubble2d") {
+            const int n[3] = {nx, 1, nz};
+            const double lo[3] = {0, 0, 0}, hi[3] = {1000, 100, 1000};
+            s.nop[0] = order; s.nop[1] = 0; s.nop[2] = order;
+            s.dt = 0.005; s.gravity = Vec3{0, 0, -9.80606};
+            s.set_mesh(box_grid(n, lo, hi, {"sides", "sides", "delete", "delete", "bottom", "top"}));
+            const std::vector<std::string> pt = {"top", "bottom", "sides"};
+            s.set_fields(mkfield(1, "uniform", {0}, all(pt, "NEUMANN")), mkfield(3, "uniform", {0, 0, 0}, all(pt, "SYMMETRY")),
+                         mkfield(1, "cosine", {0, 0.5, 500, 50, 350, 250, 1000, 250}, all(pt, "NEUMANN")),
+                         mkfield(1, "uniform", {0}, all(pt, "NEUMANN")));
+        } else if (kind == "bubble3d") {
+            const int n[3] = {nx, ny, nz};
+            const double lo[3] = {0, 0, 0}, hi[3] = {1000, 1000, 1000};
+            s.nop[0] = s.nop[1] = s.nop[2] = order;
+            s.dt = 0.00125; s.gravity = Vec3{0, -9.80606, 0}; s.time_scheme = "AB1";
+            s.set_mesh(box_grid(n, lo, hi, {"sides", "sides", "bottom", "top", "sides", "sides"}));
+            const std::vector<std::string> pt = {"top", "bottom", "sides"};
+            s.set_fields(mkfield(1, "uniform", {0}, all(pt, "NEUMANN")), mkfield(3, "uniform", {0, 0, 0}, all(pt, "SYMMETRY")),
+                         mkfield(1, "cosine", {0, 0.5, 500, 350, 500, 250, 250, 250}, all(pt, "NEUMANN")),
+                         mkfield(1, "uniform", {0}, all(pt, "NEUMANN")));
+        } else if (kind == "vortex") {
+            const int n[3] = {nx, ny, 1};
+            const double lo[3] = {-5, -5, -0.5}, hi[3] = {5, 5, 0.5};
+            s.nop[0] = s.nop[1] = order; s.nop[2] = 0;
+            s.T0 = 1; s.P0 = 1; s.cp = 3.5; s.cv = 2.5; s.viscosity = 0; s.dt = 0.0005;
+            s.gravity = Vec3{0, -9.80606, 0}; s.diffusion = false; s.buoyancy = false; s.problem_init = "ISENTROPIC_VORTEX";
+            s.set_mesh(box_grid(n, lo, hi, {"inx", "outx", "iny", "outy", "delete", "delete"}));
+            std::vector<BCond> cyc;
+            const char* pr[4][2] = {{"inx", "outx"}, {"outx", "inx"}, {"iny", "outy"}, {"outy", "iny"}};
+            for (auto& q : pr) { BCond b; b.patch = q[0]; b.type = "CYCLIC"; b.neighbor = q[1]; cyc.push_back(b); }
+            s.set_fields(mkfield(1, "uniform", {0}, cyc), mkfield(3, "uniform", {1, 1, 0}, cyc), mkfield(1, "uniform", {0}, cyc),
+                         mkfield(1, "uniform", {0}, cyc));
+        } else if (kind == "hill3d") {
+            const int n[3] = {nx, ny, nz};
+            static HillArg ha{200.0, 1000.0, 400.0, 1400.0};
+            const double lo[3] = {0, 0, 0}, hi[3] = {3400, 100.0 * ny, ha.Lz};
+            s.nop[0] = s.nop[1] = s.nop[2] = order;
+            s.dt = 0.001; s.gravity = Vec3{0, 0, -9.80606};
+            s.set_mesh(box_grid(n, lo, hi, {"inlet", "outlet", "sides", "sides", "WALLS", "top"}, hill_map, &ha));
+            const std::vector<std::string> pt = {"inlet", "outlet", "WALLS", "top", "sides"};
+            std::vector<BCond> ub = all(pt, "SYMMETRY");
+            ub[0].type = "DIRICHLET"; ub[0].value[0] = 10;
+            ub[1].type = "NEUMANN";
+            s.set_fields(mkfield(1, "uniform", {0}, all(pt, "NEUMANN")), mkfield(3, "uniform", {10, 0, 0}, ub),
+                         mkfield(1, "cosine", {0, 0.5, 1700, 100, 700, 400, 1000, 300}, all(pt, "NEUMANN")),
+                         mkfield(1, "uniform", {0}, all(pt, "NEUMANN")));
+        } else {
+            throw Error("unknown synthetic case " + kind);
+        }
+        s.setup();
+        return h;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        delete h;
+        return nullptr;
+    }
+}
+
+#define GUARD(body)                         \
+    try { body; return 0; }                 \
+    catch (const std::exception& e) { h->err = e.what(); return 1; }
+
+int nsemh_attach(nsemh_solver* h, int device, int rank, int nranks, const void* uid) { GUARD(h->s.attach_device(device, rank, nranks, uid)) }
+int nsemh_step(nsemh_solver* h, int n) { GUARD(h->s.step(n)) }
+int nsemh_upload(nsemh_solver* h) { GUARD(h->s.upload_state()) }
+int nsemh_download(nsemh_solver* h) { GUARD(h->s.download()) }
+int nsemh_write(nsemh_solver* h, int index) { GUARD(h->s.write_fields(index)) }
+int nsemh_run(nsemh_solver* h) { GUARD(h->s.run()) }
+int nsemh_sync(nsemh_solver* h) { GUARD(if (nsem_sync(h->s.ctx)) throw Error(nsem_last_error(h->s.ctx))) }
+int nsemh_time(nsemh_solver* h, int nsteps, double* ms, double* per_kernel) {
+    GUARD(if (!h->s.ctx) throw Error("no device attached"); if (nsem_time_steps(h->s.ctx, nsteps, ms, per_kernel)) throw Error(nsem_last_error(h->s.ctx)))
+}
+uint64_t nsemh_launch_count(nsemh_solver* h) { return h->s.ctx ? nsem_launch_count(h->s.ctx) : 0; }
+int nsemh_set_schedule(nsemh_solver* h, const uint32_t* order, uint32_t n) {
+    GUARD(if (nsem_set_schedule(h->s.ctx, order, n)) throw Error(nsem_last_error(h->s.ctx)))
+}
+
+// out = {NPX, NPY, NPZ, NP, NPF, nBCS, nCells, nFacets, gBCSfield, gALL}
+int nsemh_dims(nsemh_solver* h, uint64_t out[10]) {
+    Basis b(h->s.nop);
+    const Geometry& g = h->s.geo;
+    const uint64_t v[10] = {(uint64_t)b.NPX, (uint64_t)b.NPY, (uint64_t)b.NPZ, (uint64_t)b.NP, (uint64_t)b.NPF,
+                            g.nBCS, g.nCells, g.nFacets, g.gBCSfield, g.gALL};
+    std::memcpy(out, v, sizeof v);
+    return 0;
+}
+int nsemh_params(nsemh_solver* h, double out[12]) {
+    const EulerSolver& s = h->s;
+    const double v[12] = {s.P0, s.T0, s.cp, s.cv, s.viscosity, s.Pr, s.gravity[0], s.gravity[1], s.gravity[2], s.dt,
+                          (double)s.buoyancy, (double)s.diffusion};
+    std::memcpy(out, v, sizeof v);
+    return 0;
+}
+
+const double* nsemh_f64(nsemh_solver* h, const char* name, uint64_t* n) {
+    EulerSolver& s = h->s;
+    const std::string k = name;
+    const std::vector<double>* v = nullptr;
+    if (k == "cC") v = &s.geo.cC; else if (k == "cV") v = &s.geo.cV; else if (k == "Jinv") v = &s.geo.Jinv;
+    else if (k == "fN") v = &s.geo.fN; else if (k == "fC") v = &s.geo.fC; else if (k == "fI") v = &s.geo.fI;
+    else if (k == "faceNormal") v = &s.geo.faceNormal;
+    else if (k == "rho") v = &s.rho; else if (k == "U") v = &s.U; else if (k == "T") v = &s.T; else if (k == "p") v = &s.p;
+    else if (k == "rho_ref") v = &s.rho_ref; else if (k == "p_ref") v = &s.p_ref; else if (k == "g") v = &s.gvec;
+    if (!v) { *n = 0; return nullptr; }
+    *n = v->size();
+    return v->data();
+}
+const uint32_t* nsemh_u32(nsemh_solver* h, const char* name, uint64_t* n) {
+    EulerSolver& s = h->s;
+    const std::string k = name;
+    const std::vector<u32>* v = nullptr;
+    if (k == "FO") v = &s.geo.FO; else if (k == "FN") v = &s.geo.FN; else if (k == "faceBegin") v = &s.geo.faceBegin;
+    else if (k == "faceEnd") v = &s.geo.faceEnd; else if (k == "allFaces") v = &s.geo.allFaces; else if (k == "faceID") v = &s.geo.faceID;
+    else if (k == "faceOwner") v = &s.geo.faceOwner; else if (k == "faceNeigh") v = &s.geo.faceNeigh; else if (k == "faceMortar") v = &s.geo.faceMortar;
+    if (!v) { *n = 0; return nullptr; }
+    *n = v->size();
+    return v->data();
+}
+double* nsemh_state_ptr(nsemh_solver* h, const char* name) {
+    EulerSolver& s = h->s;
+    const std::string k = name;
+    if (k == "rho") return s.rho.data();
+    if (k == "U") return s.U.data();
+    if (k == "T") return s.T.data();
+    if (k == "p") return s.p.data();
+    return nullptr;
+}
+void nsemh_totals(nsemh_solver* h, double out[3]) { out[0] = h->s.mass0; out[1] = h->s.energy0; out[2] = h->s.volume0; }
+
+}  // extern "C"

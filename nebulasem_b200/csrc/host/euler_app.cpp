@@ -1,0 +1,402 @@
+// euler_app.cpp -- host mirror of apps/euler/euler.cpp around the GPU time loop.
+//
+//   parameters          apps/euler/euler.cpp:17-51, apps/utils/properties.cpp:14-34, src/field/field.cpp:496-552
+//   field read + ICs    src/field/field.h:1412-1586 (analytic initialisers run over ALL nodes, ghosts included)
+//   applyExplicitBCs    src/field/field.h:2586-2727 (host version, used during set-up only)
+//   set-up              apps/euler/euler.cpp:58-176 (isentropic vortex, gravity, hydrostatic reference state,
+//                       rho from p, scaleBCs/fixedBCs)
+//   time loop           apps/euler/euler.cpp:179-287 -> nsem_euler_step (CUDA)
+//   Iteration::next     src/solvers/iteration.h:62-84 (dump every write_interval steps)
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "nsem_host.h"
+
+namespace nsemh {
+
+namespace {
+constexpr double PI = 3.14159265358979323846264;
+inline double dot3(const double* a, const double* b) { return a[0] * b[0] + (a[1] * b[1] + a[2] * b[2]); }
+inline double mag3(const double* a) { return std::sqrt(dot3(a, a)); }
+// equal(p,q) with EqualEpsilon (tensor.h:469-474)
+inline bool equal(double p, double q, double tol = 1e-7) {
+    const double d = std::fabs(p - q);
+    return d <= tol || d <= tol * std::fabs(p) || d <= tol * std::fabs(q);
+}
+}  // namespace
+
+EulerSolver::~EulerSolver() {
+    if (ctx) nsem_destroy(ctx);
+}
+
+void EulerSolver::read_controls(const std::string& case_dir) {
+    dir = case_dir;
+    ctl = Controls::read(dir + "/controls");
+    const std::string solver = ctl.str("general", "solver", "euler");
+    if (solver != "euler") throw Error("Incorrect solver euler used instead of " + solver + ".");   // wrapper.cpp:32-38
+    meshName = ctl.str("general", "mesh", "grid");
+    nop[0] = (int)ctl.integer("general", "npx", 0);
+    nop[1] = (int)ctl.integer("general", "npy", 0);
+    nop[2] = (int)ctl.integer("general", "npz", 0);
+    viscosity = ctl.num("general", "viscosity", viscosity);
+    Pr = ctl.num("general", "Pr", Pr);
+    T0 = ctl.num("general", "T0", T0);
+    P0 = ctl.num("general", "P0", P0);
+    cp = ctl.num("general", "cp", cp);
+    cv = ctl.num("general", "cv", cv);
+    dt = ctl.num("general", "dt", dt);
+    gravity = ctl.vec("general", "gravity", gravity);
+    time_scheme = ctl.str("general", "time_scheme", time_scheme);
+    start_step = ctl.integer("general", "start_step", start_step);
+    end_step = ctl.integer("general", "end_step", end_step);
+    write_interval = ctl.integer("general", "write_interval", write_interval);
+    binary_out = ctl.str("general", "write_format", "BINARY") != "TEXT";
+    buoyancy = ctl.yes("euler", "buoyancy", buoyancy);
+    diffusion = ctl.yes("euler", "diffusion", diffusion);
+    problem_init = ctl.str("euler", "problem_init", problem_init);
+    if (ctl.str("general", "convection_scheme", "RUSANOV") != "RUSANOV")
+        throw Error("only convection_scheme RUSANOV is implemented on the GPU path");
+    // BDF1, AB1 and RK1..RK4 are the same single forward-Euler stage on this path (SURVEY finding 1)
+    const std::string& ts = time_scheme;
+    if (!(ts == "BDF1" || ts == "AB1" || ts == "RK1" || ts == "RK2" || ts == "RK3" || ts == "RK4"))
+        throw Error("time_scheme " + ts + " is not implemented on the GPU path (BDF1, AB1, RK1-RK4 are)");
+    if (ctl.yes("general", "is_spherical", false)) throw Error("spherical meshes are not implemented on the GPU path");
+    if (ctl.str("general", "state", "STEADY") != "TRANSIENT") throw Error("state must be TRANSIENT");
+}
+
+void EulerSolver::set_mesh(const Grid& g) {
+    topo.load(g);
+    Basis b(nop);
+    geo.build(topo, b);
+}
+
+void EulerSolver::load_mesh(int step) { set_mesh(read_grid(dir + "/" + meshName + "_" + std::to_string(step))); }
+
+// ---------------------------------------------------------------------------------------------------------
+std::vector<double> init_field(const FieldFile& ff, const Geometry& g, const Vec3& gravity) {
+    const int c = ff.comps;
+    const uint64_t gA = g.gALL;
+    std::vector<double> out(gA * c, 0.0);
+    if (!ff.values.empty()) {
+        std::copy(ff.values.begin(), ff.values.begin() + std::min(ff.values.size(), out.size()), out.begin());
+        return out;
+    }
+    for (const auto& in : ff.inits) {
+        const double* a = in.a.data();
+        if (in.kind == "uniform") {
+#pragma omp parallel for schedule(static)
+            for (uint64_t i = 0; i < gA; i++) for (int d = 0; d < c; d++) out[i * c + d] += a[d];
+        } else if (in.kind == "cosine" || in.kind == "cosine2" || in.kind == "linear" || in.kind == "gaussian") {
+            const double *value = a, *pert = a + c, *center = a + 2 * c, *radius = a + 2 * c + 3;
+            const double pw = (in.kind == "cosine2") ? 2.0 : 1.0;
+#pragma omp parallel for schedule(static)
+            for (uint64_t i = 0; i < gA; i++) {
+                double q[3];
+                for (int d = 0; d < 3; d++) q[d] = (g.cC[i * 3 + d] - center[d]) / radius[d];
+                double R = mag3(q);
+                for (int d = 0; d < c; d++) {
+                    double val = value[d];
+                    if (in.kind == "gaussian") {
+                        double v = std::exp(-R * R);
+                        if (equal(v, 0.0)) v = 0;
+                        val += pert[d] * v;
+                    } else {
+                        const double Rc = (1.0 <= R) ? 1.0 : R;
+                        if (in.kind == "linear") val += pert[d] * (1.0 - Rc);
+                        else val += (pert[d] / 2) * std::pow(1.0 + std::cos(Rc * PI), pw);
+                    }
+                    out[i * c + d] += val;
+                }
+            }
+        } else if (in.kind == "gaussian-outside") {
+            const double *value = a, *pert = a + c, *center = a + 2 * c;
+            const double radius = a[2 * c + 3], radius2 = a[2 * c + 4];
+            for (uint64_t i = 0; i < gA; i++) {
+                double q[3];
+                for (int d = 0; d < 3; d++) q[d] = g.cC[i * 3 + d] - center[d];
+                const double R = (mag3(q) - radius) / radius2;
+                for (int d = 0; d < c; d++) {
+                    double val = value[d];
+                    if (R <= 0) val += pert[d];
+                    else {
+                        double v = std::exp(-R * R);
+                        if (equal(v, 0.0)) v = 0;
+                        val += pert[d] * v;
+                    }
+                    out[i * c + d] += val;
+                }
+            }
+        } else if (in.kind == "hydrostatic") {
+            const double *p0 = a, scale = a[c], expon = a[c + 1];
+            for (uint64_t i = 0; i < gA; i++) {
+                const double gh = dot3(&g.cC[i * 3], gravity.data());
+                for (int d = 0; d < c; d++) out[i * c + d] += p0[d] * std::pow(1.0 + scale * gh, expon);
+            }
+        }
+    }
+    return out;
+}
+
+// applyExplicitBCs on host arrays (set-up only; in the time loop the CUDA bc_kernel does this)
+void EulerSolver::apply_bcs(std::vector<double>& F, int comps, std::vector<BCond>& bcs) {
+    const int NPF = Basis(nop).NPF;
+    const uint64_t gA = geo.gALL;
+    for (auto& bc : bcs) {
+        if (bc.type == "GHOST") continue;
+        auto it = topo.boundaries.find(bc.patch);
+        if (it == topo.boundaries.end() || it->second.empty()) continue;
+        const std::vector<u32>& faces = it->second;
+        const std::vector<u32>* nb = nullptr;
+        if (!bc.neighbor.empty()) {
+            auto jt = topo.boundaries.find(bc.neighbor);
+            if (jt == topo.boundaries.end()) throw Error("CYCLIC neighbor patch " + bc.neighbor + " not found");
+            nb = &jt->second;
+        }
+        const bool fresh_fixed = (bc.type == "CALC_DIRICHLET" && bc.fixed.empty());
+        if (fresh_fixed) bc.fixed.assign(faces.size() * (size_t)NPF * comps, 0.0);
+        for (size_t j = 0; j < faces.size(); j++)
+            for (int n = 0; n < NPF; n++) {
+                const size_t k = (size_t)faces[j] * NPF + n;
+                const u32 c1 = geo.FO[k], c2 = geo.FN[k];
+                if (c2 >= gA) continue;
+                double* gph = &F[(size_t)c2 * comps];
+                const double* own = &F[(size_t)c1 * comps];
+                if (bc.type == "NEUMANN") {
+                    double dv[3];
+                    for (int d = 0; d < 3; d++) dv[d] = geo.cC[(size_t)c2 * 3 + d] - geo.cC[(size_t)c1 * 3 + d];
+                    const double m = mag3(dv);
+                    for (int d = 0; d < comps; d++) gph[d] = own[d] + bc.value[d] * m;
+                } else if (bc.type == "ROBIN") {
+                    for (int d = 0; d < comps; d++) gph[d] = bc.shape * bc.value[d] + (1 - bc.shape) * own[d];
+                } else if (bc.type == "SYMMETRY") {
+                    if (comps == 1) gph[0] = own[0];
+                    else {
+                        // sym(Vector,Vector), tensor.h:486-494
+                        const double* N = &geo.fN[k * 3];
+                        const double mg = mag3(N);
+                        const double en[3] = {N[0] / mg, N[1] / mg, N[2] / mg};
+                        const double Axx = 1.0 - en[0] * en[0], Ayy = 1.0 - en[1] * en[1], Azz = 1.0 - en[2] * en[2];
+                        const double Axy = 0.0 - en[0] * en[1], Ayz = 0.0 - en[1] * en[2], Axz = 0.0 - en[0] * en[2];
+                        const double r[3] = {Axx * own[0] + Axy * own[1] + Axz * own[2], Axy * own[0] + Ayy * own[1] + Ayz * own[2],
+                                             Axz * own[0] + Ayz * own[1] + Azz * own[2]};
+                        const double magR = mag3(r);
+                        if (equal(magR, 0.0)) { gph[0] = r[0]; gph[1] = r[1]; gph[2] = r[2]; }
+                        else {
+                            const double f = mag3(own) / magR;
+                            gph[0] = r[0] * f; gph[1] = r[1] * f; gph[2] = r[2] * f;
+                        }
+                    }
+                } else if (bc.type == "CYCLIC") {
+                    if (!nb || nb->size() != faces.size()) throw Error("CYCLIC patches " + bc.patch + "/" + bc.neighbor + " differ in size");
+                    const u32 c11 = geo.FO[(size_t)(*nb)[j] * NPF + n];
+                    for (int d = 0; d < comps; d++) gph[d] = F[(size_t)c11 * comps + d];
+                } else if (bc.type == "DIRICHLET") {
+                    for (int d = 0; d < comps; d++) gph[d] = bc.value[d];
+                } else if (bc.type == "CALC_DIRICHLET") {
+                    double* fx = &bc.fixed[(j * NPF + n) * comps];
+                    if (fresh_fixed) for (int d = 0; d < comps; d++) fx[d] = own[d];
+                    for (int d = 0; d < comps; d++) gph[d] = fx[d];
+                } else {
+                    throw Error("boundary condition type " + bc.type + " is not implemented on the GPU path");
+                }
+            }
+    }
+}
+
+void EulerSolver::set_fields(const FieldFile& frho, const FieldFile& fU, const FieldFile& fT, const FieldFile& fp) {
+    p = init_field(fp, geo, gravity);
+    U = init_field(fU, geo, gravity);
+    T = init_field(fT, geo, gravity);
+    rho = init_field(frho, geo, gravity);
+    bc_p = fp.bcs; bc_U = fU.bcs; bc_T = fT.bcs; bc_rho = frho.bcs;
+    // MeshField::read_ applies the BCs right after reading (field.h:1562-1565)
+    apply_bcs(p, 1, bc_p);
+    apply_bcs(U, 3, bc_U);
+    apply_bcs(T, 1, bc_T);
+    apply_bcs(rho, 1, bc_rho);
+}
+
+void EulerSolver::read_fields(int step) {
+    const std::string s = std::to_string(step);
+    set_fields(read_field(dir + "/rho" + s, 1), read_field(dir + "/U" + s, 3), read_field(dir + "/T" + s, 1),
+               read_field(dir + "/p" + s, 1));
+}
+
+static std::vector<BCond> scale_bcs(const std::vector<BCond>& src) {
+    // Mesh::scaleBCs with psi = 1 (field.h:2797-2826): NEUMANN/ROBIN/SYMMETRY/CYCLIC stay, the rest freeze
+    std::vector<BCond> out = src;
+    for (auto& b : out)
+        if (!(b.type == "NEUMANN" || b.type == "ROBIN" || b.type == "SYMMETRY" || b.type == "CYCLIC")) {
+            b.type = "CALC_DIRICHLET";
+            b.fixed.clear();
+        }
+    return out;
+}
+
+void EulerSolver::setup() {
+    const uint64_t gA = geo.gALL, gB = geo.gBCSfield;
+    const double R = cp - cv, gamma = cp / cv;
+    if (problem_init == "ISENTROPIC_VORTEX") {        // euler.cpp:80-95
+        const double beta = 5;
+        for (uint64_t i = 0; i < gA; i++) {
+            const double r = mag3(&geo.cC[i * 3]);
+            T[i] = (-((gamma - 1) * beta * beta) / (8 * gamma * PI * PI)) * std::exp(1 - r * r);
+        }
+        for (uint64_t i = 0; i < gB; i++) {
+            const double r = mag3(&geo.cC[i * 3]);
+            U[i * 3 + 0] += (beta / (2 * PI)) * std::exp((1 - r * r) / 2.0) * -geo.cC[i * 3 + 1];
+            U[i * 3 + 1] += (beta / (2 * PI)) * std::exp((1 - r * r) / 2.0) * geo.cC[i * 3 + 0];
+        }
+        for (uint64_t i = 0; i < gA; i++) {
+            p[i] = std::pow(T[i] + T0, gamma / (gamma - 1)) - P0;
+            rho[i] = (P0 / (R * (T[i] + T0))) * std::pow((p[i] + P0) / P0, 1 / gamma) - (P0 / (R * T0));
+        }
+    } else if (problem_init != "NONE") {
+        throw Error("unknown problem_init " + problem_init);
+    }
+    gvec.assign(gA * 3, 0.0);
+    gh.assign(gA, 0.0);
+    p_ref.assign(gA, P0);
+    rho_ref.assign(gA, P0 / (R * T0));
+    if (buoyancy) {                                    // euler.cpp:105-123
+#pragma omp parallel for schedule(static)
+        for (uint64_t i = 0; i < gA; i++) {
+            for (int d = 0; d < 3; d++) gvec[i * 3 + d] = gravity[d];
+            gh[i] = dot3(&gvec[i * 3], &geo.cC[i * 3]);
+        }
+        bc_g = bc_U;                                   // Mesh::fixedBCs<Vector>(U,g), field.h:2779-2795
+        for (auto& b : bc_g) { b.type = "CALC_DIRICHLET"; b.fixed.clear(); }
+        apply_bcs(gvec, 3, bc_g);
+#pragma omp parallel for schedule(static)
+        for (uint64_t i = 0; i < gA; i++) {
+            p_ref[i] = P0 * std::pow(1.0 + gh[i] / (cp * T0), cp / R);
+            rho_ref[i] = (P0 / (R * T0)) * std::pow(p_ref[i] / P0, 1 / gamma);
+        }
+    }
+    // ait.start() branch, euler.cpp:133-146
+    for (uint64_t i = 0; i < gA; i++) p[i] += p_ref[i];
+    bc_p_ref = scale_bcs(bc_p);
+    apply_bcs(p_ref, 1, bc_p_ref);
+    apply_bcs(p, 1, bc_p);
+#pragma omp parallel for schedule(static)
+    for (uint64_t i = 0; i < gA; i++) rho[i] = (P0 / (R * (T[i] + T0))) * std::pow(p[i] / P0, 1 / gamma);
+    apply_bcs(rho, 1, bc_rho);
+    bc_rho_ref = scale_bcs(bc_rho);
+    apply_bcs(rho_ref, 1, bc_rho_ref);
+    for (uint64_t i = 0; i < gA; i++) p[i] -= p_ref[i];
+    // totals (euler.cpp:164-176)
+    mass0 = energy0 = volume0 = 0;
+    for (uint64_t i = 0; i < gB; i++) {
+        const double sf = rho[i] * geo.cV[i];
+        mass0 += sf;
+        const double e = gh[i] + 0.5 * dot3(&U[i * 3], &U[i * 3]) + std::pow((p[i] + p_ref[i]) / P0, R / cp) * (T[i] + T0) * cv;
+        energy0 += rho[i] * geo.cV[i] * e;
+        volume0 += geo.cV[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+static int kind_of(const std::string& t) {
+    if (t == "NEUMANN") return NSEM_BC_NEUMANN;
+    if (t == "DIRICHLET") return NSEM_BC_DIRICHLET;
+    if (t == "SYMMETRY") return NSEM_BC_SYMMETRY;
+    if (t == "CYCLIC") return NSEM_BC_CYCLIC;
+    if (t == "GHOST") return NSEM_BC_GHOST;
+    if (t == "CALC_DIRICHLET") return NSEM_BC_FIXED;
+    if (t == "ROBIN") return NSEM_BC_ROBIN;
+    throw Error("boundary condition type " + t + " is not implemented on the GPU path");
+}
+
+void EulerSolver::build_c_bcs() {
+    c_bcs_.clear();
+    keep_faces_.clear();
+    struct Src { int field; std::vector<BCond>* list; };
+    Src srcs[4] = {{NSEM_F_RHO, &bc_rho}, {NSEM_F_P, &bc_p}, {NSEM_F_U, &bc_U}, {NSEM_F_T, &bc_T}};
+    for (auto& s : srcs)
+        for (auto& b : *s.list) {
+            auto it = topo.boundaries.find(b.patch);
+            if (it == topo.boundaries.end() || it->second.empty()) continue;
+            nsem_bc c;
+            std::memset(&c, 0, sizeof c);
+            c.field = s.field;
+            c.kind = kind_of(b.type);
+            c.n_faces = (u32)it->second.size();
+            c.faces = it->second.data();
+            if (c.kind == NSEM_BC_CYCLIC) {
+                auto jt = topo.boundaries.find(b.neighbor);
+                if (jt == topo.boundaries.end() || jt->second.size() != it->second.size())
+                    throw Error("CYCLIC neighbor patch of " + b.patch + " missing or of different size");
+                c.peer_faces = jt->second.data();
+            }
+            for (int d = 0; d < 3; d++) { c.value[d] = b.value[d]; c.tvalue[d] = b.tvalue[d]; }
+            c.shape = b.shape; c.tshape = b.tshape; c.zMin = b.zMin;
+            if (c.kind == NSEM_BC_FIXED) {
+                if (b.fixed.empty()) throw Error("CALC_DIRICHLET on " + b.patch + " has no frozen values yet");
+                c.fixed = b.fixed.data();
+            }
+            c_bcs_.push_back(c);
+        }
+}
+
+void EulerSolver::attach_device(int device, int rank, int nranks, const void* uid) {
+    if (ctx) { nsem_destroy(ctx); ctx = nullptr; }
+    if (nsem_create(device, rank, nranks, uid, &ctx)) throw Error(nsem_last_error(nullptr));
+    auto ck = [&](int rc) { if (rc) throw Error(nsem_last_error(ctx)); };
+    Basis b(nop);
+    ck(nsem_set_order(ctx, b.NPX, b.NPY, b.NPZ));
+    const double* dp[3] = {b.dpsi[0].data(), b.dpsi[1].data(), b.dpsi[2].data()};
+    const double* wp[3] = {b.wgl[0].data(), b.wgl[1].data(), b.wgl[2].data()};
+    ck(nsem_set_basis(ctx, dp, wp));
+    nsem_mesh m = geo.as_c();
+    ck(nsem_upload_mesh(ctx, &m));
+    build_c_bcs();
+    ck(nsem_set_bcs(ctx, c_bcs_.data(), (u32)c_bcs_.size()));
+    nsem_params q;
+    std::memset(&q, 0, sizeof q);
+    q.P0 = P0; q.T0 = T0; q.cp = cp; q.cv = cv; q.viscosity = viscosity; q.Pr = Pr; q.dt = dt;
+    for (int d = 0; d < 3; d++) q.gravity[d] = gravity[d];
+    q.buoyancy = buoyancy; q.diffusion = diffusion;
+    ck(nsem_set_params(ctx, &q));
+    ck(nsem_upload_ref(ctx, rho_ref.data(), p_ref.data(), nullptr));
+    upload_state();
+}
+
+void EulerSolver::upload_state() {
+    if (nsem_upload_state(ctx, rho.data(), U.data(), T.data(), p.data())) throw Error(nsem_last_error(ctx));
+}
+void EulerSolver::step(int n) {
+    if (!ctx) throw Error("EulerSolver::step: no device attached (there is no CPU fallback)");
+    if (nsem_euler_step(ctx, n)) throw Error(nsem_last_error(ctx));
+}
+void EulerSolver::download() {
+    if (nsem_download_state(ctx, rho.data(), U.data(), T.data(), p.data())) throw Error(nsem_last_error(ctx));
+}
+
+void EulerSolver::write_fields(int index) {
+    const std::string s = std::to_string(index);
+    const uint64_t n = geo.gBCSfield;
+    write_field(dir + "/rho" + s, binary_out, 1, rho.data(), n, bc_rho);
+    write_field(dir + "/U" + s, binary_out, 3, U.data(), n, bc_U);
+    write_field(dir + "/T" + s, binary_out, 1, T.data(), n, bc_T);
+    write_field(dir + "/p" + s, binary_out, 1, p.data(), n, bc_p);
+}
+
+void EulerSolver::run() {
+    // Iteration (iteration.h:18-84): steps start_step*write_interval+1 .. end_step, dump when i % write_interval == 0
+    long i = write_interval * start_step + 1;
+    while (i <= end_step) {
+        long next_dump = ((i + write_interval - 1) / write_interval) * write_interval;
+        long upto = std::min(next_dump, end_step);
+        step((int)(upto - i + 1));
+        i = upto + 1;
+        if (upto % write_interval == 0) {
+            download();
+            write_fields((int)(upto / write_interval));
+            std::printf("Time %f : wrote fields %ld\n", upto * dt, upto / write_interval);
+        }
+    }
+    if (nsem_sync(ctx)) throw Error(nsem_last_error(ctx));
+}
+
+}  // namespace nsemh

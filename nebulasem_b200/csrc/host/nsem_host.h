@@ -1,0 +1,182 @@
+// nsem_host.h -- host side of the drop-in: what NebulaSEM's `euler` app does around its time loop.
+//
+// Mirrors the reference's host surface for the explicit Euler path (names follow the reference):
+//   Util::read_params / ParamList      src/util/util.cpp:32-79, util.h:343-393   -> Controls
+//   MeshObject::readTextMesh           src/mesh/mesh.h:158-200                   -> Grid, read_grid
+//   Mesh::LoadMesh                     src/field/field.cpp:95-167                -> MeshTopo::load
+//   DG::init_poly/init_basis/init_geom src/field/dg.cpp:147-590                  -> Basis, Geometry
+//   MeshField::read/write, BCondition  src/field/field.h:144-267,1412-1677       -> FieldFile, read_field, write_field
+//   euler() set-up + time loop         apps/euler/euler.cpp:17-293               -> EulerSolver
+//   Iteration / AmrIteration           src/solvers/iteration.h                   -> EulerSolver::run
+// The compute bodies are NOT here: the time-loop body is nsem_euler_step() of include/nsem_c.h (CUDA).
+#pragma once
+#include <array>
+#include <cstdint>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../../include/nsem_c.h"
+
+namespace nsemh {
+
+using u32 = uint32_t;
+using Vec3 = std::array<double, 3>;
+constexpr u32 MAX_INT = 1u << 31;        // Constants::MAX_INT (tensor.h:455)
+
+struct Error : std::exception {
+    std::string msg;
+    explicit Error(std::string m) : msg(std::move(m)) {}
+    const char* what() const noexcept override { return msg.c_str(); }
+};
+
+// ---- token streams (text and binary share one grammar, util.h:191-256) --------------------------------
+class Tokens {
+public:
+    static Tokens open(const std::string& path_noext);            // .txt first, then .bin (field.cpp:108-117)
+    static Tokens from_text(const std::string& text);
+    static Tokens from_binary(std::vector<unsigned char> bytes);
+    std::string word();
+    u32 uint();
+    double real();
+    void sym() { word(); }
+    bool eof() const;
+    bool binary = false;
+
+private:
+    std::vector<std::string> tok_;
+    size_t pos_ = 0;
+    std::vector<unsigned char> bin_;
+};
+
+// ---- controls -------------------------------------------------------------------------------------------
+struct Controls {
+    std::map<std::string, std::map<std::string, std::vector<std::string>>> blocks;
+    static Controls read(const std::string& path);
+    bool has(const std::string& blk, const std::string& key) const;
+    std::string str(const std::string& blk, const std::string& key, const std::string& def) const;
+    double num(const std::string& blk, const std::string& key, double def) const;
+    long integer(const std::string& blk, const std::string& key, long def) const;
+    bool yes(const std::string& blk, const std::string& key, bool def) const;
+    Vec3 vec(const std::string& blk, const std::string& key, Vec3 def) const;
+};
+
+// ---- grid -------------------------------------------------------------------------------------------------
+struct Grid {
+    std::vector<Vec3> V;
+    std::vector<u32> facetStart{0}, facetVerts;      // CSR
+    std::vector<u32> cellStart{0}, cellFaces;        // CSR, real cells
+    std::map<std::string, std::vector<u32>> boundaries;   // std::map: iteration in name order like the reference
+    u32 nFacets() const { return (u32)facetStart.size() - 1; }
+    u32 nCells() const { return (u32)cellStart.size() - 1; }
+};
+Grid read_grid(const std::string& path_noext);
+void write_grid_text(const std::string& path, const Grid& g);
+// structured box of n cells on [lo,hi]; sides x-,x+,y-,y+,z-,z+ -> patch names; optional terrain map
+Grid box_grid(const int n[3], const double lo[3], const double hi[3], const std::array<std::string, 6>& patches,
+              void (*vertex_map)(Vec3&, const void*) = nullptr, const void* map_arg = nullptr);
+
+// ---- topology + element geometry (mesh.cpp:55-109, 113-157, 161-446, 450-577, 581-669) ------------------
+struct MeshTopo {
+    std::vector<Vec3> V;
+    std::vector<u32> facetStart, facetVerts;
+    std::vector<u32> cellStart, cellFaces, cellFaceID;   // all cells (real + boundary); faceID aligned with cellFaces
+    std::map<std::string, std::vector<u32>> boundaries;
+    u32 nBCS = 0;
+    std::vector<u32> FOC, FNC, FMC;
+    std::vector<Vec3> FC, FN, CC;
+    std::vector<double> CV;
+    u32 nFacets() const { return (u32)facetStart.size() - 1; }
+    u32 nCells() const { return (u32)cellStart.size() - 1; }
+    void load(const Grid& g);            // Mesh::LoadMesh
+    void hex_corners(const u32* f1, const u32* f2, u32 out[8]) const;   // quads only
+
+private:
+    void add_boundary_cells();
+    void fix_hex_cells();
+    void calc_geometry();
+    void remove_boundary(const std::vector<u32>& faces);
+};
+
+// ---- DG basis + node geometry ---------------------------------------------------------------------------------
+struct Basis {
+    int NPX = 1, NPY = 1, NPZ = 1, NP = 1, NPF = 1;
+    std::vector<double> xgl[3], wgl[3], psi[3], dpsi[3];
+    explicit Basis(const int nop[3]);     // DG::Nop = polynomial degree per direction
+    int n(int d) const { return d == 0 ? NPX : (d == 1 ? NPY : NPZ); }
+};
+void legendre_gauss_lobatto(int N, double* xgl, double* wgl);                               // dg.cpp:53-99
+void lagrange_basis(int N, const double* xgl, int Ns, const double* xs, double* psi);      // dg.cpp:103-118
+void lagrange_basis_derivative(int N, const double* xgl, int Ns, const double* xs, double* dpsi);   // dg.cpp:122-143
+
+struct Geometry {
+    u32 nBCS = 0, nCells = 0, nFacets = 0;
+    uint64_t gBCSfield = 0, gALL = 0;
+    std::vector<double> cC, cV, Jinv, fN, fC, fI, faceNormal;   // AoS like the reference
+    std::vector<u32> FO, FN, faceBegin, faceEnd, allFaces, faceID, faceOwner, faceNeigh, faceMortar;
+    void build(const MeshTopo& t, const Basis& b);   // initGeomMeshFields + init_geom
+    nsem_mesh as_c() const;
+};
+
+// ---- field files -------------------------------------------------------------------------------------------------
+struct BCond {                       // BCondition<T>, field.h:144-173
+    std::string patch, type, neighbor;
+    double value[3] = {0, 0, 0}, tvalue[3] = {0, 0, 0};
+    double shape = 0, tshape = 0, zMin = 0, zMax = 0;
+    Vec3 dir{0, 0, 1};
+    std::vector<double> fixed;       // frozen CALC_DIRICHLET values [nfaces*NPF*comps]
+};
+struct FieldFile {
+    int comps = 1;
+    struct Init { std::string kind; std::vector<double> a; };
+    std::vector<Init> inits;          // `internal N<=4` analytic initialisers (field.h:1424-1521)
+    std::vector<double> values;       // otherwise raw node values
+    std::vector<BCond> bcs;
+};
+FieldFile read_field(const std::string& path_noext, int comps_expected);
+std::vector<double> init_field(const FieldFile& ff, const Geometry& g, const Vec3& gravity);
+void write_field(const std::string& path_noext, bool binary, int comps, const double* v, uint64_t n_nodes,
+                 const std::vector<BCond>& bcs);
+
+// ---- the solver app ------------------------------------------------------------------------------------------------
+struct EulerSolver {
+    Controls ctl;
+    std::string dir, meshName = "grid";
+    int nop[3] = {0, 0, 0};
+    // general{} / euler{} (properties.cpp:14-34, euler.cpp:19-48, field.cpp:56-74)
+    double viscosity = 1.568e-5, Pr = 0.9, T0 = 300, P0 = 101325, cp = 1004.67, cv = 715.5, dt = 0.1;
+    Vec3 gravity{0, 0, -9.860616};
+    bool buoyancy = true, diffusion = true, binary_out = true;
+    std::string time_scheme = "BDF1", problem_init = "NONE";
+    long start_step = 0, end_step = 2, write_interval = 20;
+
+    MeshTopo topo;
+    Geometry geo;
+    std::vector<double> rho, U, T, p, rho_ref, p_ref, gvec, gh;
+    std::vector<BCond> bc_rho, bc_U, bc_T, bc_p, bc_rho_ref, bc_p_ref, bc_g;
+    double mass0 = 0, energy0 = 0, volume0 = 0;
+
+    nsem_ctx* ctx = nullptr;
+    ~EulerSolver();
+
+    void read_controls(const std::string& case_dir);      // Solver::Initialize + euler{} params
+    void load_mesh(int step);                             // Mesh::LoadMesh from <mesh>_<step>.{txt,bin}
+    void set_mesh(const Grid& g);                         // same, from memory
+    void read_fields(int step);                           // Mesh::read_fields
+    void set_fields(const FieldFile& frho, const FieldFile& fU, const FieldFile& fT, const FieldFile& fp);
+    void setup();                                         // euler.cpp:58-176 (reference state, rho from p, BCs)
+    void attach_device(int device, int rank = 0, int nranks = 1, const void* uid = nullptr);   // C-ABI uploads
+    void upload_state();
+    void step(int n);                                     // time-loop body on the GPU
+    void download();
+    void write_fields(int index);                         // Mesh::write_fields
+    void run();                                           // Iteration loop: steps + dumps every write_interval
+
+    void apply_bcs(std::vector<double>& f, int comps, std::vector<BCond>& bcs);   // applyExplicitBCs on the host
+private:
+    std::vector<nsem_bc> c_bcs_;
+    std::vector<std::vector<u32>> keep_faces_;
+    void build_c_bcs();
+};
+
+}  // namespace nsemh

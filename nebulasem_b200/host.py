@@ -1,0 +1,175 @@
+"""ctypes binding of libnsem_host.so: the C++ host side of the drop-in (mesh + DG geometry + euler set-up + I/O).
+
+`Solver.open_case(dir)` performs what the reference's `euler ./controls` does before its time loop;
+`Solver.synthetic(kind, ...)` builds the same cases in memory (benchmarks).  `attach()` uploads everything to the
+GPU through the C ABI of include/nsem_c.h; `step()` runs the CUDA time loop.  No CPU fallback exists.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import capi
+
+HOST_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libnsem_host.so")
+HOST_EXPORTS = ["nsemh_error", "nsemh_close", "nsemh_open_case", "nsemh_synthetic", "nsemh_attach", "nsemh_step",
+                "nsemh_upload", "nsemh_download", "nsemh_write", "nsemh_run", "nsemh_sync", "nsemh_time",
+                "nsemh_launch_count", "nsemh_set_schedule", "nsemh_dims", "nsemh_params", "nsemh_f64", "nsemh_u32",
+                "nsemh_state_ptr", "nsemh_totals"]
+_lib = None
+
+
+def load_host_library() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(HOST_LIB_PATH):
+        raise RuntimeError(f"{HOST_LIB_PATH} is missing: run `python -m nebulasem_b200.build`")
+    capi.load_library()          # libnsem_cuda.so first (rpath $ORIGIN also finds it)
+    lib = C.CDLL(HOST_LIB_PATH)
+    vp = C.c_void_p
+    lib.nsemh_error.argtypes = [vp]
+    lib.nsemh_error.restype = C.c_char_p
+    lib.nsemh_close.argtypes = [vp]
+    lib.nsemh_close.restype = None
+    lib.nsemh_open_case.argtypes = [C.c_char_p, C.c_int]
+    lib.nsemh_open_case.restype = vp
+    lib.nsemh_synthetic.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.nsemh_synthetic.restype = vp
+    lib.nsemh_attach.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
+    for n in ("nsemh_upload", "nsemh_download", "nsemh_run", "nsemh_sync"):
+        getattr(lib, n).argtypes = [vp]
+    lib.nsemh_step.argtypes = [vp, C.c_int]
+    lib.nsemh_write.argtypes = [vp, C.c_int]
+    lib.nsemh_time.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.nsemh_launch_count.argtypes = [vp]
+    lib.nsemh_launch_count.restype = C.c_uint64
+    lib.nsemh_set_schedule.argtypes = [vp, C.POINTER(C.c_uint32), C.c_uint32]
+    lib.nsemh_dims.argtypes = [vp, C.POINTER(C.c_uint64)]
+    lib.nsemh_params.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.nsemh_f64.argtypes = [vp, C.c_char_p, C.POINTER(C.c_uint64)]
+    lib.nsemh_f64.restype = C.POINTER(C.c_double)
+    lib.nsemh_u32.argtypes = [vp, C.c_char_p, C.POINTER(C.c_uint64)]
+    lib.nsemh_u32.restype = C.POINTER(C.c_uint32)
+    lib.nsemh_state_ptr.argtypes = [vp, C.c_char_p]
+    lib.nsemh_state_ptr.restype = C.POINTER(C.c_double)
+    lib.nsemh_totals.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.nsemh_totals.restype = None
+    _lib = lib
+    return lib
+
+
+class Solver:
+    """Host-side euler solver (nsemh::EulerSolver)."""
+
+    def __init__(self, handle):
+        self.lib = load_host_library()
+        if not handle:
+            raise capi.NsemError(self.lib.nsemh_error(None).decode())
+        self.h = C.c_void_p(handle)
+        d = (C.c_uint64 * 10)()
+        self.lib.nsemh_dims(self.h, d)
+        (self.NPX, self.NPY, self.NPZ, self.NP, self.NPF, self.nBCS, self.nCells, self.nFacets, self.gBCSfield,
+         self.gALL) = [int(x) for x in d]
+        p = (C.c_double * 12)()
+        self.lib.nsemh_params(self.h, p)
+        self.params = dict(P0=p[0], T0=p[1], cp=p[2], cv=p[3], viscosity=p[4], Pr=p[5], gravity=(p[6], p[7], p[8]),
+                           dt=p[9], buoyancy=bool(p[10]), diffusion=bool(p[11]))
+
+    @classmethod
+    def open_case(cls, case_dir: str, step: int = 0) -> "Solver":
+        lib = load_host_library()
+        return cls(lib.nsemh_open_case(os.fspath(case_dir).encode(), step))
+
+    @classmethod
+    def synthetic(cls, kind: str, nx: int, ny: int, nz: int, order: int) -> "Solver":
+        lib = load_host_library()
+        return cls(lib.nsemh_synthetic(kind.encode(), nx, ny, nz, order))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.nsemh_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise capi.NsemError(self.lib.nsemh_error(self.h).decode())
+
+    def f64(self, name: str) -> np.ndarray:
+        n = C.c_uint64()
+        p = self.lib.nsemh_f64(self.h, name.encode(), C.byref(n))
+        if not p:
+            raise KeyError(name)
+        return np.ctypeslib.as_array(p, shape=(n.value,)).copy()
+
+    def u32(self, name: str) -> np.ndarray:
+        n = C.c_uint64()
+        p = self.lib.nsemh_u32(self.h, name.encode(), C.byref(n))
+        if not p:
+            raise KeyError(name)
+        return np.ctypeslib.as_array(p, shape=(n.value,)).copy()
+
+    def state(self):
+        """(rho, U, T, p) host copies over all nodes (reference layout)."""
+        return self.f64("rho"), self.f64("U").reshape(-1, 3), self.f64("T"), self.f64("p")
+
+    def set_state(self, rho=None, U=None, T=None, p=None):
+        for name, a, comps in (("rho", rho, 1), ("U", U, 3), ("T", T, 1), ("p", p, 1)):
+            if a is None:
+                continue
+            a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
+            assert a.size == self.gALL * comps
+            C.memmove(self.lib.nsemh_state_ptr(self.h, name.encode()), a.ctypes.data, a.nbytes)
+
+    def totals(self):
+        t = (C.c_double * 3)()
+        self.lib.nsemh_totals(self.h, t)
+        return tuple(t)
+
+    # ---- device --------------------------------------------------------------------------------------
+    def attach(self, device: int = 0, rank: int = 0, nranks: int = 1, unique_id: bytes | None = None):
+        uid = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
+        self._ck(self.lib.nsemh_attach(self.h, device, rank, nranks, uid))
+
+    def upload(self):
+        self._ck(self.lib.nsemh_upload(self.h))
+
+    def step(self, n: int = 1):
+        self._ck(self.lib.nsemh_step(self.h, int(n)))
+
+    def download(self):
+        self._ck(self.lib.nsemh_download(self.h))
+
+    def sync(self):
+        self._ck(self.lib.nsemh_sync(self.h))
+
+    def write(self, index: int):
+        self._ck(self.lib.nsemh_write(self.h, int(index)))
+
+    def run(self):
+        self._ck(self.lib.nsemh_run(self.h))
+
+    def time_steps(self, nsteps: int, per_kernel: bool = False):
+        ms = C.c_double()
+        pk = (C.c_double * 4)()
+        self._ck(self.lib.nsemh_time(self.h, int(nsteps), C.byref(ms), pk if per_kernel else None))
+        return ms.value, list(pk)
+
+    def set_schedule(self, order):
+        if order is None:
+            self._ck(self.lib.nsemh_set_schedule(self.h, None, 0))
+        else:
+            o = np.ascontiguousarray(order, dtype=np.uint32)
+            self._ck(self.lib.nsemh_set_schedule(self.h, o.ctypes.data_as(C.POINTER(C.c_uint32)), len(o)))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.nsemh_launch_count(self.h))

@@ -33,3 +33,24 @@ def test_steps_match_oracle(tmp_cases, name, kw, nsteps):
     assert err["rhoTheta"] <= TOL
     assert err["rhoU_scaled"] <= TOL
     ctx.close()
+
+
+@pytest.mark.parametrize("name,kw,syn,nsteps", [
+    ("bubble3d", dict(n=3, order=4), ("bubble3d", 3, 3, 3, 4), 10),
+    ("bubble2d", dict(n=6, order=4), ("bubble2d", 6, 1, 6, 4), 10),
+    ("vortex", dict(n=6, order=3), ("vortex", 6, 6, 1, 3), 10),
+])
+def test_host_solver_path_matches_oracle(tmp_cases, name, kw, syn, nsteps):
+    """C++ host (mesh + geometry + set-up) -> C ABI -> CUDA, from a case directory and from the in-memory generator."""
+    from nebulasem_b200 import host
+    orc = make_oracle(tmp_cases, name, nsteps, exact=False, **kw)
+    orc.run(nsteps)
+    for s in (host.Solver.open_case(orc.case_dir), host.Solver.synthetic(*syn)):
+        s.attach(0)
+        s.step(nsteps)
+        s.download()
+        rho, U, T, p = s.state()
+        err = conserved_errors(orc, rho, U, T)
+        print(name, err)
+        assert err["rho"] <= TOL and err["rhoTheta"] <= TOL and err["rhoU_scaled"] <= TOL
+        s.close()
