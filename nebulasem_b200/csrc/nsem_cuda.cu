@@ -7,10 +7,12 @@
 // (dg.cpp:328-410) at upload time, so an orientation the kernels do not reproduce is rejected loudly.
 #include "../../include/nsem_c.h"
 #include "nsem_kernels.cuh"
+#include "nsem_kernels_v2.cuh"
 
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -62,6 +64,7 @@ struct nsem_ctx {
     cudaStream_t stream = nullptr, comm = nullptr;
     mutable std::string err;
     uint64_t launches = 0;
+    bool use_v2 = false;      // bulk-async staged kernels (3-D); NSEM_KERNELS=v1 forces the plain-load kernels
 
     int NX = 0, NY = 0, NZ = 0, NP = 0, NPF = 0, NPS = 0, GPS = 0;
     bool have_basis = false, have_mesh = false, have_params = false, have_state = false, have_ref = false, have_bcs = false;
@@ -146,6 +149,32 @@ struct Launch {
         if (P.visc) return go(sweepB_kernel<NX, NY, NZ, EPB, true>, smemB, P, s);
         return go(sweepB_kernel<NX, NY, NZ, EPB, false>, smemB, P, s);
     }
+    // ---- v2: bulk-async staged, dense face tasks (3-D only) ----
+    static constexpr int EPB2 = (Dm::NP >= 100) ? 1 : (Dm::NP >= 48 ? 2 : 4);
+    using C2 = v2::Cfg<NX, NY, NZ, EPB2>;
+    static constexpr bool has_v2 = (NX > 1 && NY > 1 && NZ > 1) && C2::smemB(true) <= 227 * 1024;
+    template <class K>
+    static cudaError_t go2(K kernel, size_t smem, const KParams& P, cudaStream_t s) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        const unsigned grid = (P.nB + EPB2 - 1) / EPB2;
+        kernel<<<grid, C2::NT, smem, s>>>(P);
+        return cudaGetLastError();
+    }
+    static cudaError_t sweepA2(const KParams& P, cudaStream_t s) {
+        if constexpr (has_v2) {
+            if (P.visc) return go2(v2::sweepA_v2<NX, NY, NZ, EPB2, true, C2::minb(C2::smemA(true))>, C2::smemA(true), P, s);
+            return go2(v2::sweepA_v2<NX, NY, NZ, EPB2, false, C2::minb(C2::smemA(false))>, C2::smemA(false), P, s);
+        } else return cudaErrorInvalidValue;
+    }
+    static cudaError_t sweepB2(const KParams& P, cudaStream_t s) {
+        if constexpr (has_v2) {
+            if (P.visc) return go2(v2::sweepB_v2<NX, NY, NZ, EPB2, true, C2::minb(C2::smemB(true))>, C2::smemB(true), P, s);
+            return go2(v2::sweepB_v2<NX, NY, NZ, EPB2, false, C2::minb(C2::smemB(false))>, C2::smemB(false), P, s);
+        } else return cudaErrorInvalidValue;
+    }
     static cudaError_t bc(const BCParams& B, cudaStream_t s) {
         const uint64_t n = (uint64_t)B.nG * Dm::NPF;
         if (n == 0) return cudaSuccess;
@@ -161,14 +190,21 @@ static bool order_supported(int nx, int ny, int nz) {
     return false;
 }
 
+static bool has_v2(int nx, int ny, int nz) {
+#define X(a, b, c) if (nx == a && ny == b && nz == c) return Launch<a, b, c>::has_v2;
+    NSEM_ORDERS(X)
+#undef X
+    return false;
+}
+
 static cudaError_t launch_sweepA(const nsem_ctx* c, const KParams& P) {
-#define X(a, b, cc) if (c->NX == a && c->NY == b && c->NZ == cc) return Launch<a, b, cc>::sweepA(P, c->stream);
+#define X(a, b, cc) if (c->NX == a && c->NY == b && c->NZ == cc) return c->use_v2 ? Launch<a, b, cc>::sweepA2(P, c->stream) : Launch<a, b, cc>::sweepA(P, c->stream);
     NSEM_ORDERS(X)
 #undef X
     return cudaErrorInvalidValue;
 }
 static cudaError_t launch_sweepB(const nsem_ctx* c, const KParams& P) {
-#define X(a, b, cc) if (c->NX == a && c->NY == b && c->NZ == cc) return Launch<a, b, cc>::sweepB(P, c->stream);
+#define X(a, b, cc) if (c->NX == a && c->NY == b && c->NZ == cc) return c->use_v2 ? Launch<a, b, cc>::sweepB2(P, c->stream) : Launch<a, b, cc>::sweepB(P, c->stream);
     NSEM_ORDERS(X)
 #undef X
     return cudaErrorInvalidValue;
@@ -290,6 +326,8 @@ extern "C" int nsem_set_order(nsem_ctx* c, int NPX, int NPY, int NPZ) {
     c->NPS = pad_to(c->NP, 16);
     c->GPS = pad_to(c->NPF, 4);
     c->have_basis = c->have_mesh = c->have_state = c->have_ref = c->have_bcs = false;
+    const char* kv = std::getenv("NSEM_KERNELS");
+    c->use_v2 = has_v2(NPX, NPY, NPZ) && !(kv && std::strcmp(kv, "v1") == 0);
     return 0;
 }
 
