@@ -87,6 +87,7 @@ struct nsem_ctx {
     // element-face tables
     DevBuf<uint32_t> faceOther, faceMeta, sched;
     DevBuf<double> faceVec, faceUnit;
+    DevBuf<FaceRec> faceRec;
     bool has_sched = false;
     // ghost tables
     DevBuf<uint32_t> ghostRef, bOwner;
@@ -171,8 +172,8 @@ struct Launch {
     }
     static cudaError_t sweepB2(const KParams& P, cudaStream_t s) {
         if constexpr (has_v2) {
-            if (P.visc) return go2(v2::sweepB_v2<NX, NY, NZ, EPB2, true, C2::minb(C2::smemB(true))>, C2::smemB(true), P, s);
-            return go2(v2::sweepB_v2<NX, NY, NZ, EPB2, false, C2::minb(C2::smemB(false))>, C2::smemB(false), P, s);
+            if (P.visc) return go2(v2::sweepB_v2<NX, NY, NZ, EPB2, true, C2::minb(C2::smemB(true), 128)>, C2::smemB(true), P, s);
+            return go2(v2::sweepB_v2<NX, NY, NZ, EPB2, false, C2::minb(C2::smemB(false), 128)>, C2::smemB(false), P, s);
         } else return cudaErrorInvalidValue;
     }
     static cudaError_t bc(const BCParams& B, cudaStream_t s) {
@@ -480,6 +481,17 @@ extern "C" int nsem_upload_mesh(nsem_ctx* c, const nsem_mesh* m) {
     CUDA_TRY(c, c->faceMeta.upload(fMeta, s));
     CUDA_TRY(c, c->faceVec.upload(fVec, s));
     CUDA_TRY(c, c->faceUnit.upload(fUnit, s));
+    {
+        std::vector<FaceRec> rec((size_t)nB * 6);
+        for (size_t q = 0; q < rec.size(); q++) {
+            rec[q].other = fOther[q];
+            rec[q].meta = fMeta[q];
+            for (int d = 0; d < 3; d++) { rec[q].vec[d] = fVec[q * 3 + d]; rec[q].unit[d] = fUnit[q * 3 + d]; }
+            rec[q].pad = 0;
+        }
+        CUDA_TRY(c, c->faceRec.upload(rec, s));
+        CUDA_TRY(c, cudaStreamSynchronize(s));
+    }
     CUDA_TRY(c, c->ghostRef.upload(ghostRef, s));
     CUDA_TRY(c, c->bOwner.upload(bOwner, s));
     CUDA_TRY(c, c->bFid.upload(bFid, s));
@@ -737,6 +749,7 @@ static void fill_kparams(const nsem_ctx* c, KParams& P) {
     P.cV = c->cV.p; P.rho_ref = c->rho_ref.p; P.p_ref = c->p_ref.p;
     P.faceOther = c->faceOther.p; P.faceMeta = c->faceMeta.p; P.faceVec = c->faceVec.p; P.faceUnit = c->faceUnit.p;
     P.sched = c->has_sched ? c->sched.p : nullptr;
+    P.faceRec = c->faceRec.p;
 }
 static void fill_bcparams(const nsem_ctx* c, const KParams& P, BCParams& B, int phase) {
     std::memset(&B, 0, sizeof B);

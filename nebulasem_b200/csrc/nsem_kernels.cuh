@@ -40,6 +40,7 @@ constexpr uint32_t FM_ABSENT = 7u;
 constexpr uint32_t FM_OWNER = 8u;         // this element is the face's owner (gFOC)
 constexpr uint32_t FM_HALF = 16u;         // fI = 0.5 (interior / inter-rank); else fI = 0 (physical boundary)
 
+struct FaceRec;
 struct KParams {
     // sizes
     uint32_t nB;                 // real elements
@@ -75,7 +76,16 @@ struct KParams {
     const double* faceVec;       // [nB*6*3] un-weighted area vector gFN (outward from the OWNER)
     const double* faceUnit;      // [nB*6*3] unit(gFN)
     const uint32_t* sched;       // optional processing order
+    const struct FaceRec* faceRec;   // [nB*6] the four tables above packed in one 64-byte record (v2 kernels)
 };
+
+struct alignas(16) FaceRec {
+    uint32_t other, meta;
+    double vec[3];
+    double unit[3];
+    double pad;
+};
+static_assert(sizeof(FaceRec) == 64, "FaceRec must be 64 bytes");
 
 // ---------------------------------------------------------------------------------------------------
 // index helpers (dg.h:43-44 INDEX4; dg.cpp:372-404 face node maps)

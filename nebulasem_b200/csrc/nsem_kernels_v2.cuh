@@ -78,9 +78,9 @@ struct Cfg {
         return sizeof(double) * ((size_t)NIN_A * EPB * NPS + 3 * EPB * NP + (size_t)EPB * NFT * (visc ? 8 : 1) + 3 * MAXN * MAXN) + 16;
     }
     // resident CTAs per SM aimed at: limited by 227 KB of shared memory and by >= 96 registers per thread
-    static constexpr int minb(size_t smem) {
+    static constexpr int minb(size_t smem, int regs = 96) {
         int bs = (int)((227 * 1024) / (smem + 1024));
-        int br = 65536 / (NT * 96);
+        int br = 65536 / (NT * regs);
         int b = bs < br ? bs : br;
         return b < 1 ? 1 : (b > 4 ? 4 : b);
     }
@@ -131,34 +131,25 @@ __global__ void __launch_bounds__(Cfg<NX, NY, NZ, EPB>::NT, MINB) sweepA_v2(cons
     const int i = nt / (NY * NZ), j = (nt / NZ) % NY, k = nt % NZ;
     const size_t idx = (size_t)nelem * NPS + nt;
 
-    // ---- face task: decode, tables and neighbour gathers before the element data has landed ----
+    // ---- face task: decode, one 64-byte table record and the neighbour gathers are ISSUED before the element
+    //      data has landed; nothing loaded here is consumed until after the wait ----
     const int fe = tid / NFT, ff = tid % NFT;
-    bool faceOn = tid < EPB * NFT && fe < nvalid;
-    int fs = 0, fa = 0, fb = 0, fln = 0;
-    double N0 = 0, N1 = 0, N2 = 0, nN = 0, al = 0;
-    bool own = false;
-    double xr = 0, xu0 = 0, xu1 = 0, xu2 = 0, xth = 0;
+    const bool faceOn = tid < EPB * NFT && fe < nvalid;
+    int fs = 0, fa = 0, fb = 0;
+    double2 q0 = {0, 0}, q1 = {0, 0}, q2 = {0, 0}, q3 = {0, 0};
+    double xr = 0, xu0 = 0, xu1 = 0, xu2 = 0, xT = 0;
     if (faceOn) {
         Tk::decode(ff, fs, fa, fb);
         const uint32_t felem = P.sched ? P.sched[first + fe] : first + fe;
-        const uint32_t meta = P.faceMeta[felem * 6 + fs];
-        const uint32_t fid = meta & FM_FID_MASK;
-        if (fid == FM_ABSENT) faceOn = false;
-        else {
-            fln = face_node<NX, NY, NZ>(fs, fa, fb);
-            const int n = (fs < 2) ? fa * NY + fb : fa * NZ + fb;
-            const size_t oidx = (size_t)P.faceOther[felem * 6 + fs] + (fid == FM_GHOST ? n : face_node<NX, NY, NZ>(fid, fa, fb));
-            xr = P.rho_old[oidx];
-            xu0 = P.U_old[0][oidx]; xu1 = P.U_old[1][oidx]; xu2 = P.U_old[2][oidx];
-            xth = P.T_old[oidx] + P.T0;
-            const double w = face_weight<NX, NY, NZ>(P, fs, fa, fb);
-            const double* fv = P.faceVec + (size_t)(felem * 6 + fs) * 3;
-            const double* fu = P.faceUnit + (size_t)(felem * 6 + fs) * 3;
-            N0 = fv[0] * w; N1 = fv[1] * w; N2 = fv[2] * w;
-            nN = fu[0] * N0 + fu[1] * N1 + fu[2] * N2;
-            own = meta & FM_OWNER;
-            al = (meta & FM_HALF) ? 0.5 : 0.0;
-        }
+        const double2* rp = reinterpret_cast<const double2*>(P.faceRec + ((size_t)felem * 6 + fs));
+        q0 = rp[0]; q1 = rp[1]; q2 = rp[2]; q3 = rp[3];
+        const unsigned long long om = (unsigned long long)__double_as_longlong(q0.x);
+        const uint32_t fid = (uint32_t)(om >> 32) & FM_FID_MASK;
+        const int n = (fs < 2) ? fa * NY + fb : fa * NZ + fb;
+        const size_t oidx = (size_t)(uint32_t)om + (fid == FM_GHOST ? n : face_node<NX, NY, NZ>(fid, fa, fb));
+        xr = P.rho_old[oidx];
+        xu0 = P.U_old[0][oidx]; xu1 = P.U_old[1][oidx]; xu2 = P.U_old[2][oidx];
+        xT = P.T_old[oidx];
     }
 
     mbar_wait(bar, 0);
@@ -211,6 +202,14 @@ __global__ void __launch_bounds__(Cfg<NX, NY, NZ, EPB>::NT, MINB) sweepA_v2(cons
 
     // ---- face tasks ----
     if (faceOn) {
+        const uint32_t meta = (uint32_t)((unsigned long long)__double_as_longlong(q0.x) >> 32);
+        const bool own = meta & FM_OWNER;
+        const double al = (meta & FM_HALF) ? 0.5 : 0.0;
+        const double w = face_weight<NX, NY, NZ>(P, fs, fa, fb);
+        const double N0 = q0.y * w, N1 = q1.x * w, N2 = q1.y * w;          // fN[k] = gFN * w_a w_b / 4
+        const double nN = q2.x * N0 + q2.y * N1 + q3.x * N2;               // unit(fN).fN
+        const double xth = xT + P.T0;
+        const int fln = face_node<NX, NY, NZ>(fs, fa, fb);
         const double mr = IN(0, fe, fln), m0 = IN(1, fe, fln), m1 = IN(2, fe, fln), m2 = IN(3, fe, fln), mth = IN(4, fe, fln);
         const double rho_o = own ? mr : xr, rho_n = own ? xr : mr;
         const double uo0 = own ? m0 : xu0, uo1 = own ? m1 : xu1, uo2 = own ? m2 : xu2;
@@ -239,7 +238,6 @@ __global__ void __launch_bounds__(Cfg<NX, NY, NZ, EPB>::NT, MINB) sweepA_v2(cons
 #pragma unroll
     for (int s = 0; s < 6; s++) {
         if (!on_face(s, i, j, k, NX, NY, NZ)) continue;
-        if ((P.faceMeta[nelem * 6 + s] & FM_FID_MASK) == FM_ABSENT) continue;
         int a, b;
         face_slot<NX, NY, NZ>(s, i, j, k, a, b);
         const double* in = &sF[(size_t)ne * NFT + Tk::index(s, a, b)];
@@ -262,10 +260,11 @@ __global__ void __launch_bounds__(Cfg<NX, NY, NZ, EPB>::NT, MINB) sweepA_v2(cons
     P.rho_new[idx] = rho_new;
     P.p[idx] = __dsub_rn(eos_pressure(P.P0, P.R, P.gamma, rho_new, th), IN(15, ne, nt));
     if (VISC) {
+        const double rcV = 1.0 / cV;            // r / cV (field.h:3359) as one reciprocal and 12 products
 #pragma unroll
-        for (int c = 0; c < 9; c++) P.GU[c][idx] = gU[c] / cV;
+        for (int c = 0; c < 9; c++) P.GU[c][idx] = gU[c] * rcV;
 #pragma unroll
-        for (int c = 0; c < 3; c++) P.GT[c][idx] = gT[c] / cV;
+        for (int c = 0; c < 3; c++) P.GT[c][idx] = gT[c] * rcV;
     }
 }
 
@@ -323,40 +322,28 @@ __global__ void __launch_bounds__(Cfg<NX, NY, NZ, EPB>::NT, MINB) sweepB_v2(cons
     const size_t idx = (size_t)nelem * NPS + nt;
 
     const int fe = tid / NFT, ff = tid % NFT;
-    bool faceOn = tid < EPB * NFT && fe < nvalid;
-    int fs = 0, fa = 0, fb = 0, fln = 0;
-    double N[3] = {0, 0, 0}, fu[3] = {0, 0, 0}, nN = 0, al = 0;
-    bool own = false;
-    double xro = 0, xrn = 0, xu[3] = {0, 0, 0}, xth = 0, xpp = 0, xgN[4] = {0, 0, 0, 0};
+    const bool faceOn = tid < EPB * NFT && fe < nvalid;
+    int fs = 0, fa = 0, fb = 0;
+    double2 q0 = {0, 0}, q1 = {0, 0}, q2 = {0, 0}, q3 = {0, 0};
+    double xro = 0, xrn = 0, xu[3] = {0, 0, 0}, xT = 0, xpp = 0, xG[VISC ? 12 : 1];
     if (faceOn) {
         Tk::decode(ff, fs, fa, fb);
         const uint32_t felem = P.sched ? P.sched[first + fe] : first + fe;
-        const uint32_t meta = P.faceMeta[felem * 6 + fs];
-        const uint32_t fid = meta & FM_FID_MASK;
-        if (fid == FM_ABSENT) faceOn = false;
-        else {
-            fln = face_node<NX, NY, NZ>(fs, fa, fb);
-            const int n = (fs < 2) ? fa * NY + fb : fa * NZ + fb;
-            const size_t oidx = (size_t)P.faceOther[felem * 6 + fs] + (fid == FM_GHOST ? n : face_node<NX, NY, NZ>(fid, fa, fb));
-            xro = P.rho_old[oidx]; xrn = P.rho_new[oidx];
-            xu[0] = P.U_old[0][oidx]; xu[1] = P.U_old[1][oidx]; xu[2] = P.U_old[2][oidx];
-            xth = P.T_old[oidx] + P.T0;
-            xpp = P.p[oidx];
-            const double w = face_weight<NX, NY, NZ>(P, fs, fa, fb);
-            const double* fv = P.faceVec + (size_t)(felem * 6 + fs) * 3;
-            const double* fup = P.faceUnit + (size_t)(felem * 6 + fs) * 3;
+        const double2* rp = reinterpret_cast<const double2*>(P.faceRec + ((size_t)felem * 6 + fs));
+        q0 = rp[0]; q1 = rp[1]; q2 = rp[2]; q3 = rp[3];
+        const unsigned long long om = (unsigned long long)__double_as_longlong(q0.x);
+        const uint32_t fid = (uint32_t)(om >> 32) & FM_FID_MASK;
+        const int n = (fs < 2) ? fa * NY + fb : fa * NZ + fb;
+        const size_t oidx = (size_t)(uint32_t)om + (fid == FM_GHOST ? n : face_node<NX, NY, NZ>(fid, fa, fb));
+        xro = P.rho_old[oidx]; xrn = P.rho_new[oidx];
+        xu[0] = P.U_old[0][oidx]; xu[1] = P.U_old[1][oidx]; xu[2] = P.U_old[2][oidx];
+        xT = P.T_old[oidx];
+        xpp = P.p[oidx];
+        if (VISC) {
 #pragma unroll
-            for (int c = 0; c < 3; c++) { N[c] = fv[c] * w; fu[c] = fup[c]; }
-            nN = fu[0] * N[0] + fu[1] * N[1] + fu[2] * N[2];
-            own = meta & FM_OWNER;
-            al = (meta & FM_HALF) ? 0.5 : 0.0;
-            if (VISC) {
-                // the neighbour's viscous normal fluxes (G.N)_a and gT.N only need 4 numbers
+            for (int c = 0; c < 9; c++) xG[c] = P.GU[c][oidx];
 #pragma unroll
-                for (int c = 0; c < 3; c++)
-                    xgN[c] = P.GU[c * 3 + 0][oidx] * N[0] + P.GU[c * 3 + 1][oidx] * N[1] + P.GU[c * 3 + 2][oidx] * N[2];
-                xgN[3] = P.GT[0][oidx] * N[0] + P.GT[1][oidx] * N[1] + P.GT[2][oidx] * N[2];
-            }
+            for (int c = 0; c < 3; c++) xG[9 + c] = P.GT[c][oidx];
         }
     }
 
@@ -416,6 +403,21 @@ __global__ void __launch_bounds__(Cfg<NX, NY, NZ, EPB>::NT, MINB) sweepB_v2(cons
     }
 
     if (faceOn) {
+        const uint32_t meta = (uint32_t)((unsigned long long)__double_as_longlong(q0.x) >> 32);
+        const bool own = meta & FM_OWNER;
+        const double al = (meta & FM_HALF) ? 0.5 : 0.0;
+        const double w = face_weight<NX, NY, NZ>(P, fs, fa, fb);
+        const double N[3] = {q0.y * w, q1.x * w, q1.y * w};
+        const double fu[3] = {q2.x, q2.y, q3.x};
+        const double nN = fu[0] * N[0] + fu[1] * N[1] + fu[2] * N[2];
+        const double xth = xT + P.T0;
+        double xgN[4] = {0, 0, 0, 0};
+        if (VISC) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) xgN[c] = xG[c * 3 + 0] * N[0] + xG[c * 3 + 1] * N[1] + xG[c * 3 + 2] * N[2];
+            xgN[3] = xG[9] * N[0] + xG[10] * N[1] + xG[11] * N[2];
+        }
+        const int fln = face_node<NX, NY, NZ>(fs, fa, fb);
         const double mro = IN(A_RO, fe, fln), mrn = IN(A_RN, fe, fln);
         const double mu3[3] = {IN(A_U, fe, fln), IN(A_U + 1, fe, fln), IN(A_U + 2, fe, fln)};
         const double mth = IN(A_T, fe, fln) + P.T0;
@@ -461,7 +463,6 @@ __global__ void __launch_bounds__(Cfg<NX, NY, NZ, EPB>::NT, MINB) sweepB_v2(cons
 #pragma unroll
     for (int s = 0; s < 6; s++) {
         if (!on_face(s, i, j, k, NX, NY, NZ)) continue;
-        if ((P.faceMeta[nelem * 6 + s] & FM_FID_MASK) == FM_ABSENT) continue;
         int a, b;
         face_slot<NX, NY, NZ>(s, i, j, k, a, b);
         const double* in = &sF[(size_t)ne * NFT + Tk::index(s, a, b)];
@@ -473,14 +474,15 @@ __global__ void __launch_bounds__(Cfg<NX, NY, NZ, EPB>::NT, MINB) sweepB_v2(cons
     double g[3] = {P.g[0], P.g[1], P.g[2]};
     if (P.has_gfield) { g[0] = P.gfield[0][idx]; g[1] = P.gfield[1][idx]; g[2] = P.gfield[2][idx]; }
     const double drho = P.buoyancy ? (rho_nw - rref) : 0.0;
+    const double rap = 1.0 / ap;                 // x = Su / ap (solve.cpp:563-570) as one reciprocal and 4 products
 #pragma unroll
     for (int c = 0; c < 3; c++) {
         const double Su = (r[c] - (drho * g[c]) * cV) + (u[c] * rho_o) * ap0;
-        P.U_new[c][idx] = Su / ap;
+        P.U_new[c][idx] = Su * rap;
     }
     {
         const double Su = r[3] + (th * rho_o) * ap0;
-        P.T_new[idx] = Su / ap - P.T0;
+        P.T_new[idx] = Su * rap - P.T0;
     }
 }
 
