@@ -28,7 +28,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     if not force and _newer(LIB, deps):
         return LIB
     cmd = [NVCC, "-O3", "-std=c++17", *ARCH, "-lineinfo", "-Xcompiler", "-fPIC", "-shared", "-DNSEM_WITH_NCCL",
-           *srcs, "-o", LIB, "-lnccl"]
+           *srcs, "-o", LIB, "-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     print("[nebulasem_b200.build]", " ".join(cmd), flush=True)

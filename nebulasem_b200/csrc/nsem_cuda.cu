@@ -18,13 +18,54 @@
 #include <vector>
 
 #ifdef NSEM_WITH_NCCL
-#include <nccl.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the library is resolved at run time (see NcclApi) so that this .so carries no
+                    // link-time NCCL dependency and shares whichever libnccl.so.2 the process already loaded
+                    // (torch bundles its own; two different NCCL builds in one process do not mix)
 #endif
 
 using namespace nsem;
 
 namespace {
 std::string g_create_error;
+
+#ifdef NSEM_WITH_NCCL
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string err;
+    bool load() {
+        if (handle) return true;
+        handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);      // already in the process (torch)?
+        if (!handle) handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!handle) handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!handle) { err = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }
+#define NSEM_SYM(field, name)                                                         \
+    field = reinterpret_cast<decltype(field)>(dlsym(handle, name));                     \
+    if (!field) { err = std::string("libnccl is missing ") + name; handle = nullptr; return false; }
+        NSEM_SYM(GetUniqueId, "ncclGetUniqueId")
+        NSEM_SYM(CommInitRank, "ncclCommInitRank")
+        NSEM_SYM(CommDestroy, "ncclCommDestroy")
+        NSEM_SYM(GroupStart, "ncclGroupStart")
+        NSEM_SYM(GroupEnd, "ncclGroupEnd")
+        NSEM_SYM(Send, "ncclSend")
+        NSEM_SYM(Recv, "ncclRecv")
+        NSEM_SYM(AllReduce, "ncclAllReduce")
+        NSEM_SYM(GetErrorString, "ncclGetErrorString")
+#undef NSEM_SYM
+        return true;
+    }
+};
+NcclApi g_nccl;
+#endif
 
 #define CUDA_TRY(ctx, expr)                                                                       \
     do {                                                                                          \
@@ -255,11 +296,16 @@ extern "C" int nsem_create(int device, int rank, int nranks, const void* nccl_un
             delete c;
             return 1;
         }
+        if (!g_nccl.load()) {
+            g_create_error = "nsem_create: " + g_nccl.err;
+            delete c;
+            return 1;
+        }
         ncclUniqueId id;
         std::memcpy(&id, nccl_unique_id, sizeof(id));
-        ncclResult_t r = ncclCommInitRank(&c->nccl, nranks, id, rank);
+        ncclResult_t r = g_nccl.CommInitRank(&c->nccl, nranks, id, rank);
         if (r != ncclSuccess) {
-            g_create_error = std::string("ncclCommInitRank: ") + ncclGetErrorString(r);
+            g_create_error = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r);
             delete c;
             return 1;
         }
@@ -279,7 +325,7 @@ extern "C" void nsem_destroy(nsem_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
 #ifdef NSEM_WITH_NCCL
-    if (c->nccl) ncclCommDestroy(c->nccl);
+    if (c->nccl) g_nccl.CommDestroy(c->nccl);
 #endif
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -292,7 +338,8 @@ extern "C" const char* nsem_last_error(const nsem_ctx* c) { return c ? c->err.c_
 extern "C" int nsem_get_unique_id(void* out128) {
 #ifdef NSEM_WITH_NCCL
     ncclUniqueId id;
-    if (ncclGetUniqueId(&id) != ncclSuccess) return 1;
+    if (!g_nccl.load()) { g_create_error = g_nccl.err; return 1; }
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) return 1;
     std::memcpy(out128, &id, sizeof(id));
     return 0;
 #else

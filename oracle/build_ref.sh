@@ -31,13 +31,13 @@ build_variant() {
     local name="$1"; shift
     local flags="$*"
     local dir="$OUT/$name"
-    mkdir -p "$dir/obj"
     local stamp="$dir/.flags"
     if [ -f "$stamp" ] && [ "$(cat "$stamp")" = "$flags" ] && [ -x "$dir/euler" ] && [ -x "$dir/mesh" ] \
        && [ "$HERE/tools/geomdump.cpp" -ot "$dir/euler" ]; then
         echo "build_ref: $name up to date"; return
     fi
     echo "build_ref: compiling $name ($flags)"
+    mkdir -p "$dir/obj"
     local pids=() n=0
     for s in $LIBSRC; do
         local o="$dir/obj/$(echo "$s" | sed "s#$R/##; s#/#_#g; s#\.cpp\$#.o#")"

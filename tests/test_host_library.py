@@ -1,0 +1,92 @@
+"""C++ host side (libnsem_host.so) against the oracle: file readers, topology, DG geometry, euler set-up, dump writer.
+CPU only: nothing here touches the GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from nebulasem_b200 import capi, host
+from oracle import refio
+from tests.helpers import make_oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("bubble2d", dict(n=4, order=4)),
+    ("bubble3d", dict(n=3, order=3)),
+    ("vortex", dict(n=4, order=5)),
+    ("hill3d", dict(nx=5, ny=2, nz=3, order=2)),
+])
+def test_host_geometry_and_setup_bit_equal_to_oracle(tmp_cases, name, kw):
+    orc = make_oracle(tmp_cases, name, 1, exact=False, **kw)
+    s = host.Solver.open_case(orc.case_dir)
+    g = orc.g
+    assert (s.NPX, s.NPY, s.NPZ, s.NP, s.NPF) == (g.basis.NPX, g.basis.NPY, g.basis.NPZ, g.basis.NP, g.basis.NPF)
+    assert (s.nBCS, s.nCells, s.nFacets) == (g.nBCS, g.nCells, g.nFacets)
+    for nm, ref in (("cC", g.cC), ("cV", g.cV), ("Jinv", g.Jinv), ("fN", g.fN), ("fC", g.fC), ("fI", g.fI), ("faceNormal", g.topo.FNv)):
+        assert np.array_equal(s.f64(nm), np.asarray(ref).ravel()), nm
+    for nm, ref in (("FO", g.FO), ("FN", g.FN), ("allFaces", g.allFaces), ("faceBegin", g.faceIndices[0]), ("faceEnd", g.faceIndices[1]),
+                    ("faceOwner", g.topo.FOC), ("faceNeigh", g.topo.FNC), ("faceID", np.concatenate(g.topo.faceID))):
+        assert np.array_equal(s.u32(nm), np.asarray(ref, dtype=np.uint32).ravel()), nm
+    rho, U, T, p = s.state()
+    assert np.array_equal(rho, orc.rho) and np.array_equal(U, orc.U) and np.array_equal(T, orc.T) and np.array_equal(p, orc.pp)
+    assert np.array_equal(s.f64("rho_ref"), orc.rho_ref) and np.array_equal(s.f64("p_ref"), orc.p_ref)
+    m0, e0, v0 = s.totals()
+    assert abs(m0 - orc.mass0) <= 1e-12 * abs(orc.mass0) and abs(v0 - orc.volume0) <= 1e-12 * abs(orc.volume0)
+    s.close()
+
+
+def test_field_dump_written_in_the_reference_format(tmp_cases):
+    orc = make_oracle(tmp_cases, "bubble3d", 1, exact=False, n=2, order=2)
+    s = host.Solver.open_case(orc.case_dir)
+    s.write(7)            # rho7.bin, U7.bin, T7.bin, p7.bin (write_format defaults to BINARY, field.cpp:74)
+    nb = orc.gB
+    for nm, ref in (("rho", orc.rho), ("U", orc.U), ("T", orc.T), ("p", orc.pp)):
+        ff = refio.read_field(os.path.join(orc.case_dir, f"{nm}7"))
+        vals = ff.values[:, 0] if ff.comps == 1 else ff.values
+        assert np.array_equal(vals, ref[:nb])
+        assert [b.kind for b in ff.bcs] == [b.kind for b in orc.bcs[nm]]
+    s.close()
+
+
+def test_synthetic_generator_matches_case_files(tmp_cases):
+    orc = make_oracle(tmp_cases, "bubble3d", 1, exact=False, n=3, order=4)
+    a = host.Solver.open_case(orc.case_dir)
+    b = host.Solver.synthetic("bubble3d", 3, 3, 3, 4)
+    for nm in ("cC", "cV", "Jinv", "fN", "rho", "U", "T", "p", "rho_ref", "p_ref"):
+        assert np.array_equal(a.f64(nm), b.f64(nm)), nm
+    for nm in ("FO", "FN", "allFaces", "faceID"):
+        assert np.array_equal(a.u32(nm), b.u32(nm)), nm
+
+
+def test_errors_are_reported_not_swallowed(tmp_cases):
+    with pytest.raises(capi.NsemError):
+        host.Solver.open_case(os.path.join(str(tmp_cases), "does_not_exist"))
+    with pytest.raises(capi.NsemError, match="unknown synthetic case"):
+        host.Solver.synthetic("nonsense", 2, 2, 2, 2)
+    orc = make_oracle(tmp_cases, "bubble2d", 1, exact=False, n=3, order=2)
+    s = host.Solver.open_case(orc.case_dir)
+    with pytest.raises(capi.NsemError, match="no device attached|no CPU fallback"):
+        s.step(1)        # the hot path has no CPU fallback
+
+
+def test_c_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "nsem_c.h")).read()
+    declared = sorted(set(re.findall(r"\b(nsem_[a-z_0-9]+)\s*\(", hdr)))
+    assert set(declared) == set(capi.EXPORTS), (declared, capi.EXPORTS)
+    lib = capi.load_library()
+    for name in declared:
+        assert hasattr(lib, name), name
+    hl = host.load_host_library()
+    for name in host.HOST_EXPORTS:
+        assert hasattr(hl, name), name
+
+
+def test_create_fails_loudly_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(capi.NsemError, match="no CUDA device"):
+        capi.Context(0)

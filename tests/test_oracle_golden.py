@@ -1,0 +1,43 @@
+"""The numpy oracle against the golden fixtures produced by the unmodified reference binary (CPU, no GPU)."""
+import ast
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from tests.helpers import make_oracle, rel_l2
+
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_oracle_reproduces_reference_dump(tmp_cases, path):
+    g = np.load(path)
+    case, kw, nsteps = str(g["case"]), ast.literal_eval(str(g["kwargs"])), int(g["nsteps"])
+    orc = make_oracle(tmp_cases, case, nsteps, exact=True, **kw)
+    orc.run(nsteps)
+    nb = orc.gB
+    # the exact-order oracle is bit-identical to the reference where libm is the same; 1e-13 allows another libm
+    for name, mine in (("rho", orc.rho), ("U", orc.U), ("T", orc.T), ("p", orc.pp)):
+        ref = g[name]
+        scale = max(1.0, float(np.abs(ref).max()))
+        assert np.abs(mine[:nb] - ref).max() <= 1e-12 * scale, name
+    assert rel_l2(orc.rho[:nb], g["rho"]) <= 1e-14
+
+
+@pytest.mark.parametrize("path", GOLD[:3], ids=[os.path.basename(p)[:-4] for p in GOLD[:3]])
+def test_fast_order_oracle_within_tolerance(tmp_cases, path):
+    """The einsum (fast) evaluation order used for the larger GPU comparisons stays within 1e-12 of the reference."""
+    g = np.load(path)
+    case, kw, nsteps = str(g["case"]), ast.literal_eval(str(g["kwargs"])), int(g["nsteps"])
+    orc = make_oracle(tmp_cases, case, nsteps, exact=False, **kw)
+    orc.run(nsteps)
+    nb = orc.gB
+    assert rel_l2(orc.rho[:nb], g["rho"]) <= 1e-13
+    c0 = np.sqrt(orc.gamma * orc.R * orc.p.T0)
+    mom_ref = g["rho"][:, None] * g["U"]
+    mom = orc.rho[:nb, None] * orc.U[:nb]
+    assert np.linalg.norm(mom - mom_ref) / (np.linalg.norm(g["rho"]) * c0) <= 1e-13
+    th_ref = g["rho"] * (g["T"] + orc.p.T0)
+    assert rel_l2(orc.rho[:nb] * (orc.T[:nb] + orc.p.T0), th_ref) <= 1e-13
