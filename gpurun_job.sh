@@ -1,1 +1,3 @@
-for n in 64 100; do timeout 600 python bench.py --n $n --steps 5 --warmup 3 --no-cpu-baseline --no-e2e 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); r=d['roofline']; print(d['ms_per_step'], '%.3e'%d['value'], 'A %.2f ms %.3f'%(r['sweepA']['ms'], r['sweepA']['frac']), 'B %.2f ms %.3f'%(r['sweepB']['ms'], r['sweepB']['frac']), 'step %.3f'%r['step']['frac'], r['bc_ms'])"; done
+nvidia-smi -L
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/mp_gpu_check.py XYZ 2>&1 | tail -15
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tests/mp_gpu_check.py METIS 2>&1 | tail -8

@@ -127,6 +127,9 @@ int nsem_upload_ref(nsem_ctx* ctx, const double* rho_ref, const double* p_ref, c
 /* nsteps iterations of the time-loop body apps/euler/euler.cpp:179-287 (steps 1-8 and 10 of SURVEY 3.2):
  * rho-, U- and T-equations with divf<weak>/gradf<strong>/rusanov/addTemporal<1>/Solve + BCs + halo. */
 int nsem_euler_step(nsem_ctx* ctx, int nsteps);
+/* applyExplicitBCs(field, true) halos of the set-up phase (euler.cpp:105-146, field.h:2596-2599,2726): fills the
+ * inter-partition ghost cells of rho, U, T, p, rho_ref and p_ref from the neighbouring ranks. Collective. */
+int nsem_exchange_state_halos(nsem_ctx* ctx);
 /* euler.cpp:261-283 + Mesh::calc_courant (field.cpp:440-448): out = {courant max, min, avg, mass, energy,
  * volume}, all-reduced over ranks. */
 int nsem_diagnostics(nsem_ctx* ctx, double out[6]);

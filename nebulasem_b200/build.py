@@ -45,10 +45,14 @@ HOST_FLAGS = ["-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-fopenmp", "-W
 
 def build_host(force: bool = False) -> str:
     hdir = os.path.join(CSRC, "host")
-    srcs = [os.path.join(hdir, f) for f in ("io.cpp", "mesh.cpp", "dg.cpp", "euler_app.cpp", "capi_host.cpp")]
+    srcs = [os.path.join(hdir, f) for f in ("io.cpp", "mesh.cpp", "dg.cpp", "partition.cpp", "euler_app.cpp", "capi_host.cpp")]
+    metis = os.path.join(os.path.dirname(os.path.dirname(NVCC)), "targets", "x86_64-linux", "lib", "libmetis_static.a")
+    metis_flags = ["-DNSEM_WITH_METIS"] if os.path.exists(metis) else []
+    metis_libs = [metis] if os.path.exists(metis) else []
     deps = srcs + [os.path.join(hdir, "nsem_host.h"), os.path.join(ROOT, "include", "nsem_c.h"), LIB]
     if force or not _newer(HOST_LIB, deps):
-        cmd = [CXX, *HOST_FLAGS, "-shared", *srcs, "-o", HOST_LIB, "-L" + LIBDIR, "-lnsem_cuda", "-Wl,-rpath,$ORIGIN"]
+        cmd = [CXX, *HOST_FLAGS, *metis_flags, "-shared", *srcs, *metis_libs, "-o", HOST_LIB, "-L" + LIBDIR, "-lnsem_cuda",
+               "-Wl,-rpath,$ORIGIN"]
         print("[nebulasem_b200.build]", " ".join(cmd), flush=True)
         subprocess.check_call(cmd)
     main = os.path.join(hdir, "euler_main.cpp")

@@ -63,10 +63,18 @@ nsemh_solver* nsemh_open_case(const char* dir, int step) {
 }
 
 // In-memory synthetic cases (same definitions as oracle/cases.py): kind in {bubble2d, bubble3d, vortex, hill3d}.
-nsemh_solver* nsemh_synthetic(const char* kind_, int nx, int ny, int nz, int order) {
+// nranks > 1: the global grid is decomposed (decomp = METIS | XYZ | CELLID; XYZ uses px*py*pz = nranks) and only
+// partition `rank` is kept (Prepare::decomposeMesh, field.cpp:1086-1257).
+nsemh_solver* nsemh_synthetic_part(const char* kind_, int nx, int ny, int nz, int order, int rank, int nranks,
+                                   const char* decomp, int px, int py, int pz) {
     nsemh_solver* h = new nsemh_solver();
     EulerSolver& s = h->s;
     const std::string kind = kind_;
+    const int pxyz[3] = {px, py, pz};
+    auto mesh = [&](const Grid& g) {
+        if (nranks > 1) s.set_mesh_partition(g, rank, nranks, decomp ? decomp : "METIS", pxyz);
+        else s.set_mesh(g);
+    };
     try {
         s.time_scheme = "BDF1";
         s.viscosity = 1.5;
@@ -75,7 +83,7 @@ nsemh_solver* nsemh_synthetic(const char* kind_, int nx, int ny, int nz, int ord
             const double lo[3] = {0, 0, 0}, hi[3] = {1000, 100, 1000};
             s.nop[0] = order; s.nop[1] = 0; s.nop[2] = order;
             s.dt = 0.005; s.gravity = Vec3{0, 0, -9.80606};
-            s.set_mesh(box_grid(n, lo, hi, {"sides", "sides", "delete", "delete", "bottom", "top"}));
+            mesh(box_grid(n, lo, hi, {"sides", "sides", "delete", "delete", "bottom", "top"}));
             const std::vector<std::string> pt = {"top", "bottom", "sides"};
             s.set_fields(mkfield(1, "uniform", {0}, all(pt, "NEUMANN")), mkfield(3, "uniform", {0, 0, 0}, all(pt, "SYMMETRY")),
                          mkfield(1, "cosine", {0, 0.5, 500, 50, 350, 250, 1000, 250}, all(pt, "NEUMANN")),
@@ -85,7 +93,7 @@ nsemh_solver* nsemh_synthetic(const char* kind_, int nx, int ny, int nz, int ord
             const double lo[3] = {0, 0, 0}, hi[3] = {1000, 1000, 1000};
             s.nop[0] = s.nop[1] = s.nop[2] = order;
             s.dt = 0.00125; s.gravity = Vec3{0, -9.80606, 0}; s.time_scheme = "AB1";
-            s.set_mesh(box_grid(n, lo, hi, {"sides", "sides", "bottom", "top", "sides", "sides"}));
+            mesh(box_grid(n, lo, hi, {"sides", "sides", "bottom", "top", "sides", "sides"}));
             const std::vector<std::string> pt = {"top", "bottom", "sides"};
             s.set_fields(mkfield(1, "uniform", {0}, all(pt, "NEUMANN")), mkfield(3, "uniform", {0, 0, 0}, all(pt, "SYMMETRY")),
                          mkfield(1, "cosine", {0, 0.5, 500, 350, 500, 250, 250, 250}, all(pt, "NEUMANN")),
@@ -96,7 +104,7 @@ nsemh_solver* nsemh_synthetic(const char* kind_, int nx, int ny, int nz, int ord
             s.nop[0] = s.nop[1] = order; s.nop[2] = 0;
             s.T0 = 1; s.P0 = 1; s.cp = 3.5; s.cv = 2.5; s.viscosity = 0; s.dt = 0.0005;
             s.gravity = Vec3{0, -9.80606, 0}; s.diffusion = false; s.buoyancy = false; s.problem_init = "ISENTROPIC_VORTEX";
-            s.set_mesh(box_grid(n, lo, hi, {"inx", "outx", "iny", "outy", "delete", "delete"}));
+            mesh(box_grid(n, lo, hi, {"inx", "outx", "iny", "outy", "delete", "delete"}));
             std::vector<BCond> cyc;
             const char* pr[4][2] = {{"inx", "outx"}, {"outx", "inx"}, {"iny", "outy"}, {"outy", "iny"}};
             for (auto& q : pr) { BCond b; b.patch = q[0]; b.type = "CYCLIC"; b.neighbor = q[1]; cyc.push_back(b); }
@@ -108,7 +116,7 @@ nsemh_solver* nsemh_synthetic(const char* kind_, int nx, int ny, int nz, int ord
             const double lo[3] = {0, 0, 0}, hi[3] = {3400, 100.0 * ny, ha.Lz};
             s.nop[0] = s.nop[1] = s.nop[2] = order;
             s.dt = 0.001; s.gravity = Vec3{0, 0, -9.80606};
-            s.set_mesh(box_grid(n, lo, hi, {"inlet", "outlet", "sides", "sides", "WALLS", "top"}, hill_map, &ha));
+            mesh(box_grid(n, lo, hi, {"inlet", "outlet", "sides", "sides", "WALLS", "top"}, hill_map, &ha));
             const std::vector<std::string> pt = {"inlet", "outlet", "WALLS", "top", "sides"};
             std::vector<BCond> ub = all(pt, "SYMMETRY");
             ub[0].type = "DIRICHLET"; ub[0].value[0] = 10;
@@ -126,6 +134,10 @@ nsemh_solver* nsemh_synthetic(const char* kind_, int nx, int ny, int nz, int ord
         delete h;
         return nullptr;
     }
+}
+
+nsemh_solver* nsemh_synthetic(const char* kind, int nx, int ny, int nz, int order) {
+    return nsemh_synthetic_part(kind, nx, ny, nz, order, 0, 1, "METIS", 1, 1, 1);
 }
 
 #define GUARD(body)                         \
@@ -183,6 +195,7 @@ const uint32_t* nsemh_u32(nsemh_solver* h, const char* name, uint64_t* n) {
     const std::vector<u32>* v = nullptr;
     if (k == "FO") v = &s.geo.FO; else if (k == "FN") v = &s.geo.FN; else if (k == "faceBegin") v = &s.geo.faceBegin;
     else if (k == "faceEnd") v = &s.geo.faceEnd; else if (k == "allFaces") v = &s.geo.allFaces; else if (k == "faceID") v = &s.geo.faceID;
+    else if (k == "cellGlobal") v = &s.cellGlobal;
     else if (k == "faceOwner") v = &s.geo.faceOwner; else if (k == "faceNeigh") v = &s.geo.faceNeigh; else if (k == "faceMortar") v = &s.geo.faceMortar;
     if (!v) { *n = 0; return nullptr; }
     *n = v->size();
@@ -196,6 +209,18 @@ double* nsemh_state_ptr(nsemh_solver* h, const char* name) {
     if (k == "T") return s.T.data();
     if (k == "p") return s.p.data();
     return nullptr;
+}
+// faces of boundary patch `name` (local ids); returns the count, copies at most cap entries
+uint64_t nsemh_patch_faces(nsemh_solver* h, const char* name, uint32_t* out, uint64_t cap) {
+    auto it = h->s.topo.boundaries.find(name);
+    if (it == h->s.topo.boundaries.end()) return 0;
+    for (uint64_t q = 0; q < it->second.size() && q < cap; q++) out[q] = it->second[q];
+    return it->second.size();
+}
+// number of neighbouring ranks; copies them to out (ascending)
+int nsemh_peers(nsemh_solver* h, int* out, int cap) {
+    for (int q = 0; q < (int)h->s.peers.size() && q < cap; q++) out[q] = h->s.peers[q];
+    return (int)h->s.peers.size();
 }
 void nsemh_totals(nsemh_solver* h, double out[3]) { out[0] = h->s.mass0; out[1] = h->s.energy0; out[2] = h->s.volume0; }
 

@@ -311,6 +311,11 @@ void Geometry::build(const MeshTopo& t, const Basis& b) {
 
     // ---- fI (field.cpp:257-270): 0 on physical boundary faces, 0.5 elsewhere (ghost faces of other ranks too) ----
     for (size_t k = 0; k < nfn; k++) fI[k] = (FN[k] >= gBCSfield) ? 0.0 : 0.5;
+    for (const auto& kv : t.boundaries)
+        if (kv.first.find("interMesh") != std::string::npos)
+            for (u32 f : kv.second)
+                for (int n = 0; n < NPF; n++)
+                    if (FO[(size_t)f * NPF + n] < gALL) fI[(size_t)f * NPF + n] = 0.5;   // isGhostFace
 }
 
 nsem_mesh Geometry::as_c() const {

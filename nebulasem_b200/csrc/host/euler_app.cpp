@@ -71,6 +71,16 @@ void EulerSolver::set_mesh(const Grid& g) {
     geo.build(topo, b);
 }
 
+void EulerSolver::set_mesh_partition(const Grid& global, int rank_, int nranks_, const std::string& type, const int nxyz[3]) {
+    rank = rank_; nranks = nranks_;
+    const std::vector<u32> part = partition_cells(global, nranks, type, nxyz);
+    Partition P = extract_partition(global, part, rank, nranks);
+    if (P.cellGlobal.empty()) throw Error("partition " + std::to_string(rank) + " is empty");
+    cellGlobal = P.cellGlobal;
+    peers = P.peers;
+    set_mesh(P.grid);
+}
+
 void EulerSolver::load_mesh(int step) { set_mesh(read_grid(dir + "/" + meshName + "_" + std::to_string(step))); }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -210,6 +220,14 @@ void EulerSolver::set_fields(const FieldFile& frho, const FieldFile& fU, const F
     T = init_field(fT, geo, gravity);
     rho = init_field(frho, geo, gravity);
     bc_p = fp.bcs; bc_U = fU.bcs; bc_T = fT.bcs; bc_rho = frho.bcs;
+    for (const auto& kv : topo.boundaries)
+        if (kv.first.find("interMesh") != std::string::npos)
+            for (auto* list : {&bc_p, &bc_U, &bc_T, &bc_rho}) {
+                BCond b;
+                b.patch = kv.first;
+                b.type = "GHOST";
+                list->insert(list->begin(), b);
+            }
     // MeshField::read_ applies the BCs right after reading (field.h:1562-1565)
     apply_bcs(p, 1, bc_p);
     apply_bcs(U, 3, bc_U);
@@ -360,6 +378,25 @@ void EulerSolver::attach_device(int device, int rank, int nranks, const void* ui
     ck(nsem_set_params(ctx, &q));
     ck(nsem_upload_ref(ctx, rho_ref.data(), p_ref.data(), nullptr));
     upload_state();
+    if (nranks > 1) {
+        // gInterMesh (mesh.h:180-196): one entry per interMesh_<me>_<peer> patch
+        std::vector<nsem_halo_peer> hp;
+        for (const auto& kv : topo.boundaries) {
+            if (kv.first.find("interMesh") == std::string::npos) continue;
+            const size_t us = kv.first.rfind('_');
+            nsem_halo_peer h;
+            h.peer_rank = std::stoi(kv.first.substr(us + 1));
+            h.n_faces = (u32)kv.second.size();
+            h.faces = kv.second.data();
+            hp.push_back(h);
+        }
+        ck(nsem_set_halo(ctx, hp.data(), (u32)hp.size()));
+        exchange_setup_halos();
+    }
+}
+
+void EulerSolver::exchange_setup_halos() {
+    if (nsem_exchange_state_halos(ctx)) throw Error(nsem_last_error(ctx));
 }
 
 void EulerSolver::upload_state() {

@@ -76,6 +76,15 @@ void write_grid_text(const std::string& path, const Grid& g);
 Grid box_grid(const int n[3], const double lo[3], const double hi[3], const std::array<std::string, 6>& patches,
               void (*vertex_map)(Vec3&, const void*) = nullptr, const void* map_arg = nullptr);
 
+// ---- domain decomposition (Prepare::decomposeMesh, field.cpp:1086-1257) --------------------------------------
+std::vector<u32> partition_cells(const Grid& g, int nparts, const std::string& method, const int nxyz[3]);
+struct Partition {
+    Grid grid;                      // local grid with interMesh_<me>_<peer> patches
+    std::vector<u32> cellGlobal;    // local real cell -> global cell
+    std::vector<int> peers;         // neighbouring ranks, ascending
+};
+Partition extract_partition(const Grid& g, const std::vector<u32>& part, int rank, int nparts);
+
 // ---- topology + element geometry (mesh.cpp:55-109, 113-157, 161-446, 450-577, 581-669) ------------------
 struct MeshTopo {
     std::vector<Vec3> V;
@@ -114,7 +123,7 @@ struct Geometry {
     uint64_t gBCSfield = 0, gALL = 0;
     std::vector<double> cC, cV, Jinv, fN, fC, fI, faceNormal;   // AoS like the reference
     std::vector<u32> FO, FN, faceBegin, faceEnd, allFaces, faceID, faceOwner, faceNeigh, faceMortar;
-    void build(const MeshTopo& t, const Basis& b);   // initGeomMeshFields + init_geom
+    void build(const MeshTopo& t, const Basis& b);   // initGeomMeshFields + init_geom (fI = 0.5 on interMesh_* faces)
     nsem_mesh as_c() const;
 };
 
@@ -162,6 +171,12 @@ struct EulerSolver {
     void read_controls(const std::string& case_dir);      // Solver::Initialize + euler{} params
     void load_mesh(int step);                             // Mesh::LoadMesh from <mesh>_<step>.{txt,bin}
     void set_mesh(const Grid& g);                         // same, from memory
+    // decompose `global` into nranks parts (type METIS | XYZ | CELLID) and keep part `rank` (decomposeMesh)
+    void set_mesh_partition(const Grid& global, int rank, int nranks, const std::string& type, const int nxyz[3]);
+    int rank = 0, nranks = 1;
+    std::vector<u32> cellGlobal;                          // local real cell -> global cell (identity on 1 rank)
+    std::vector<int> peers;
+    void exchange_setup_halos();                          // the applyExplicitBCs(...,true) halos of euler.cpp:105-146
     void read_fields(int step);                           // Mesh::read_fields
     void set_fields(const FieldFile& frho, const FieldFile& fU, const FieldFile& fT, const FieldFile& fp);
     void setup();                                         // euler.cpp:58-176 (reference state, rho from p, BCs)

@@ -149,11 +149,12 @@ struct nsem_ctx {
 #ifdef NSEM_WITH_NCCL
     ncclComm_t nccl = nullptr;
 #endif
-    struct Peer { int rank; std::vector<uint32_t> ghosts; };   // ghost cells (indices) filled by this peer, in face order
+    struct Peer { int rank; uint32_t g0, nf; uint64_t off; };   // ghost cells [g0, g0+nf) are filled by this peer; off = slot offset
     std::vector<Peer> peers;
-    DevBuf<double> sendBuf;
+    uint64_t nSendSlots = 0;
+    DevBuf<double> sendBuf;          // [16][nSendSlots]
     DevBuf<uint32_t> sendNodes;      // owner node (device index) per send slot
-    std::vector<size_t> peerOff;     // slot offsets per peer (in face nodes)
+    cudaEvent_t evCompute = nullptr, evComm = nullptr;
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -811,6 +812,8 @@ static void fill_bcparams(const nsem_ctx* c, const KParams& P, BCParams& B, int 
     B.T_new = P.T_new;
 }
 
+static int halo_exchange(nsem_ctx* c, double* const* arrays, int nf, cudaStream_t s);
+
 static int one_step(nsem_ctx* c, bool timed, double* acc) {
     KParams P;
     BCParams B;
@@ -820,11 +823,21 @@ static int one_step(nsem_ctx* c, bool timed, double* acc) {
     if (timed) cudaEventRecord(c->ev[1], c->stream);
     fill_bcparams(c, P, B, 0);
     CUDA_TRY(c, launch_bc(c, B));
+    if (!c->peers.empty()) {
+        double* arr[14] = {P.rho_new, P.p};
+        int nf = 2;
+        if (P.visc) { for (int q = 0; q < 9; q++) arr[nf++] = P.GU[q]; for (int q = 0; q < 3; q++) arr[nf++] = P.GT[q]; }
+        if (halo_exchange(c, arr, nf, c->stream)) return 1;
+    }
     if (timed) cudaEventRecord(c->ev[2], c->stream);
     CUDA_TRY(c, launch_sweepB(c, P));
     if (timed) cudaEventRecord(c->ev[3], c->stream);
     B.phase = 1;
     CUDA_TRY(c, launch_bc(c, B));
+    if (!c->peers.empty()) {
+        double* arr[4] = {P.U_new[0], P.U_new[1], P.U_new[2], P.T_new};
+        if (halo_exchange(c, arr, 4, c->stream)) return 1;
+    }
     if (timed) cudaEventRecord(c->ev[4], c->stream);
     c->launches += 2 + (c->nG ? 2 : 0);
     c->cur ^= 1;
@@ -883,10 +896,94 @@ extern "C" int nsem_time_steps(nsem_ctx* c, int nsteps, double* ms, double* per_
 }
 
 extern "C" int nsem_set_halo(nsem_ctx* c, const nsem_halo_peer* peers, uint32_t n_peers) {
-    if (n_peers == 0) { c->peers.clear(); return 0; }
-    (void)peers;
-    c->err = "nsem_set_halo: multi-partition halo not built yet";
+    if (!c->have_mesh) { c->err = "nsem_set_halo: no mesh"; return 1; }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    c->peers.clear();
+    c->nSendSlots = 0;
+    if (n_peers == 0) return 0;
+    if (c->nranks <= 1) { c->err = "nsem_set_halo: context was created for a single rank"; return 1; }
+    const int NPF = c->NPF, GPS = c->GPS, NPS = c->NPS;
+    std::vector<uint32_t> nodes;
+    for (uint32_t q = 0; q < n_peers; q++) {
+        const nsem_halo_peer& hp = peers[q];
+        if (hp.peer_rank < 0 || hp.peer_rank >= c->nranks || hp.peer_rank == c->rank || hp.n_faces == 0) {
+            c->err = "nsem_set_halo: bad peer entry";
+            return 1;
+        }
+        nsem_ctx::Peer P{hp.peer_rank, 0, hp.n_faces, (uint64_t)nodes.size()};
+        for (uint32_t j = 0; j < hp.n_faces; j++) {
+            const uint32_t face = hp.faces[j];
+            if (face >= c->nF || c->h_face_neigh[face] < c->nB) { c->err = "nsem_set_halo: face is not a boundary face"; return 1; }
+            const uint32_t g = c->h_face_neigh[face] - c->nB;
+            if (j == 0) P.g0 = g;
+            else if (g != P.g0 + j) {
+                c->err = "nsem_set_halo: ghost cells of an interMesh patch are not contiguous (addBoundaryCells creates them patch by patch)";
+                return 1;
+            }
+            const int fid = c->h_bFid[g];
+            const int NX = c->NX, NY = c->NY, NZ = c->NZ;
+            for (int n = 0; n < GPS; n++) {
+                uint32_t nd = 0xffffffffu;
+                int a, b, cnt;
+                if (fid < 2) { a = n / NY; b = n % NY; cnt = NX * NY; }
+                else if (fid < 4) { a = n / NZ; b = n % NZ; cnt = NX * NZ; }
+                else { a = n / NZ; b = n % NZ; cnt = NY * NZ; }
+                if (n < NPF && n < cnt) nd = c->h_bOwner[g] * (uint32_t)NPS + (uint32_t)h_face_node(c, fid, a, b);
+                nodes.push_back(nd);
+            }
+        }
+        c->peers.push_back(P);
+    }
+    c->nSendSlots = nodes.size();
+    CUDA_TRY(c, c->sendNodes.upload(nodes, c->stream));
+    CUDA_TRY(c, c->sendBuf.alloc((size_t)16 * nodes.size()));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (!c->evCompute) { CUDA_TRY(c, cudaEventCreateWithFlags(&c->evCompute, cudaEventDisableTiming)); CUDA_TRY(c, cudaEventCreateWithFlags(&c->evComm, cudaEventDisableTiming)); }
+    return 0;
+}
+
+// pack the owner-side face values of `nf` arrays and exchange them with every peer on stream `s`:
+// send from the packed buffer, receive straight into the ghost region [ghostBase + g0*GPS, +nf*GPS) of each array
+static int halo_exchange(nsem_ctx* c, double* const* arrays, int nf, cudaStream_t s) {
+    if (c->peers.empty()) return 0;
+#ifdef NSEM_WITH_NCCL
+    if (nf > 16) { c->err = "halo_exchange: too many fields"; return 1; }
+    PackParams H;
+    std::memset(&H, 0, sizeof H);
+    H.nfields = nf; H.nslots = c->nSendSlots; H.node = c->sendNodes.p; H.dst = c->sendBuf.p;
+    for (int f = 0; f < nf; f++) H.src[f] = arrays[f];
+    halo_pack_kernel<<<(unsigned)((H.nslots + 255) / 256), 256, 0, s>>>(H);
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    ncclResult_t r = g_nccl.GroupStart();
+    for (const auto& P : c->peers) {
+        const size_t cnt = (size_t)P.nf * c->GPS;
+        for (int f = 0; f < nf && r == ncclSuccess; f++) {
+            r = g_nccl.Send(c->sendBuf.p + (size_t)f * c->nSendSlots + P.off, cnt, ncclDouble, P.rank, c->nccl, s);
+            if (r == ncclSuccess) r = g_nccl.Recv(arrays[f] + c->ghostBase + (size_t)P.g0 * c->GPS, cnt, ncclDouble, P.rank, c->nccl, s);
+        }
+    }
+    ncclResult_t r2 = g_nccl.GroupEnd();
+    if (r != ncclSuccess || r2 != ncclSuccess) {
+        c->err = std::string("NCCL halo exchange: ") + g_nccl.GetErrorString(r != ncclSuccess ? r : r2);
+        return 1;
+    }
+    return 0;
+#else
+    (void)arrays; (void)nf; (void)s;
+    c->err = "library built without NCCL";
     return 1;
+#endif
+}
+
+extern "C" int nsem_exchange_state_halos(nsem_ctx* c) {
+    if (!(c->have_mesh && c->have_state && c->have_ref)) { c->err = "nsem_exchange_state_halos: upload state and reference first"; return 1; }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const int k = c->cur;
+    double* arr[8] = {c->rho[k].p, c->U[k][0].p, c->U[k][1].p, c->U[k][2].p, c->T[k].p, c->p.p, c->rho_ref.p, c->p_ref.p};
+    if (halo_exchange(c, arr, 8, c->stream)) return 1;
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return 0;
 }
 
 extern "C" int nsem_diagnostics(nsem_ctx* c, double out[6]) {

@@ -615,6 +615,25 @@ __global__ void __launch_bounds__(256) bc_kernel(const __grid_constant__ BCParam
 }
 
 // ---------------------------------------------------------------------------------------------------
+// halo pack (ASYNC_COMM::send, field.h:2283-2290): sendBuf[f][slot] = P[FO[k]] for every slot of every
+// inter-partition face, laid out exactly like the receiver's ghost cells (stride GPS per face) so that the
+// receive lands directly in the ghost region of each array (no unpack pass, cf. field.h:2314-2321).
+// ---------------------------------------------------------------------------------------------------
+struct PackParams {
+    int nfields;
+    uint64_t nslots;                 // total send slots (faces * GPS over all peers)
+    const uint32_t* node;            // [nslots] owner node (device index) or 0xffffffff for padding slots
+    const double* src[16];
+    double* dst;                     // [nfields][nslots]
+};
+__global__ void __launch_bounds__(256) halo_pack_kernel(const __grid_constant__ PackParams H) {
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= H.nslots) return;
+    const uint32_t nd = H.node[q];
+    for (int f = 0; f < H.nfields; f++) H.dst[(uint64_t)f * H.nslots + q] = (nd != 0xffffffffu) ? H.src[f][nd] : 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // layout conversion: reference AoS node arrays <-> device SoA (element stride NPS, compact ghost cells)
 // ---------------------------------------------------------------------------------------------------
 // src: [nRef*comps] AoS in reference node order; dst[c]: device arrays. ghostRef[g*NPF+n] = reference node of

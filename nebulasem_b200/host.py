@@ -14,7 +14,8 @@ import numpy as np
 from . import capi
 
 HOST_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libnsem_host.so")
-HOST_EXPORTS = ["nsemh_error", "nsemh_close", "nsemh_open_case", "nsemh_synthetic", "nsemh_attach", "nsemh_step",
+HOST_EXPORTS = ["nsemh_error", "nsemh_close", "nsemh_open_case", "nsemh_synthetic", "nsemh_synthetic_part", "nsemh_patch_faces",
+                "nsemh_peers", "nsemh_attach", "nsemh_step",
                 "nsemh_upload", "nsemh_download", "nsemh_write", "nsemh_run", "nsemh_sync", "nsemh_time",
                 "nsemh_launch_count", "nsemh_set_schedule", "nsemh_dims", "nsemh_params", "nsemh_f64", "nsemh_u32",
                 "nsemh_state_ptr", "nsemh_totals"]
@@ -38,6 +39,12 @@ def load_host_library() -> C.CDLL:
     lib.nsemh_open_case.restype = vp
     lib.nsemh_synthetic.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.nsemh_synthetic.restype = vp
+    lib.nsemh_synthetic_part.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int,
+                                         C.c_int, C.c_int]
+    lib.nsemh_synthetic_part.restype = vp
+    lib.nsemh_patch_faces.argtypes = [vp, C.c_char_p, C.POINTER(C.c_uint32), C.c_uint64]
+    lib.nsemh_patch_faces.restype = C.c_uint64
+    lib.nsemh_peers.argtypes = [vp, C.POINTER(C.c_int), C.c_int]
     lib.nsemh_attach.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
     for n in ("nsemh_upload", "nsemh_download", "nsemh_run", "nsemh_sync"):
         getattr(lib, n).argtypes = [vp]
@@ -87,6 +94,27 @@ class Solver:
     def synthetic(cls, kind: str, nx: int, ny: int, nz: int, order: int) -> "Solver":
         lib = load_host_library()
         return cls(lib.nsemh_synthetic(kind.encode(), nx, ny, nz, order))
+
+    @classmethod
+    def synthetic_part(cls, kind: str, nx: int, ny: int, nz: int, order: int, rank: int, nranks: int, decomp: str = "METIS",
+                       pxyz=(1, 1, 1)) -> "Solver":
+        """Partition `rank` of `nranks` of the synthetic case (decomp: METIS | XYZ with pxyz | CELLID)."""
+        lib = load_host_library()
+        s = cls(lib.nsemh_synthetic_part(kind.encode(), nx, ny, nz, order, rank, nranks, decomp.encode(), *[int(x) for x in pxyz]))
+        s.rank, s.nranks = rank, nranks
+        return s
+
+    def patch_faces(self, name: str) -> np.ndarray:
+        n = self.lib.nsemh_patch_faces(self.h, name.encode(), None, 0)
+        out = np.zeros(int(n), dtype=np.uint32)
+        if n:
+            self.lib.nsemh_patch_faces(self.h, name.encode(), out.ctypes.data_as(C.POINTER(C.c_uint32)), n)
+        return out
+
+    def peers(self):
+        buf = (C.c_int * 64)()
+        n = self.lib.nsemh_peers(self.h, buf, 64)
+        return [int(buf[i]) for i in range(n)]
 
     def close(self):
         if getattr(self, "h", None):

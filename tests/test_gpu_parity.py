@@ -1,4 +1,6 @@
 """GPU parity: CUDA path (through the C ABI) vs the numpy oracle on the same seeded cases.  -m gpu"""
+import os
+
 import numpy as np
 import pytest
 
@@ -54,3 +56,20 @@ def test_host_solver_path_matches_oracle(tmp_cases, name, kw, syn, nsteps):
         print(name, err)
         assert err["rho"] <= TOL and err["rhoTheta"] <= TOL and err["rhoU_scaled"] <= TOL
         s.close()
+
+
+@pytest.mark.parametrize("decomp", ["METIS", "XYZ"])
+def test_two_partitions_equal_one_partition(decomp):
+    """One METIS/XYZ partition per GPU with the NCCL face-trace halo == the single-partition run."""
+    import subprocess
+    import sys
+
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(root, "tests", "mp_gpu_check.py"), decomp]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    print(out.stdout[-3000:], out.stderr[-3000:])
+    assert out.returncode == 0 and "MP_CHECK_OK" in out.stdout
