@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- dGSEM Euler DOF-updates/s per stage (BASELINE.json metric) on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n CELLS_PER_SIDE]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--cells CELLS_PER_SIDE]
 
 Workload (BASELINE.json configs[1]): rising thermal bubble, 3-D synthetic hex mesh of n^3 elements (default
 100^3 = 1.0e6 elements, order 4, 1.25e8 LGL nodes), FP64, diffusion + buoyancy on, one reference time step =
@@ -147,10 +147,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=100, help="elements per side of the cubic mesh")
-    ap.add_argument("--ref-n", type=int, default=16, help="elements per side of the CPU reference sample")
+    ap.add_argument("--cells", dest="n", type=int, default=100, help="elements per side of the cubic mesh")
+    ap.add_argument("--ref-cells", dest="ref_n", type=int, default=16, help="elements per side of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--decomp", default="METIS", choices=["METIS", "XYZ", "CELLID"], help="domain decomposition for --gpus > 1")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -176,33 +177,75 @@ def main():
         print(json.dumps(line), flush=True)
         return 0
 
+    # torchrun exports OMP_NUM_THREADS=1; the host-side mesh/geometry set-up (not timed) is OpenMP-parallel
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(1, world)))
     import numpy as np
     import torch
     from nebulasem_b200 import host
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
-    if world > 1:
-        raise SystemExit("bench.py: multi-partition halo is not wired into the bench yet")
     device = local_rank
     torch.cuda.set_device(device)
+    import torch.distributed as dist
+    pgrid = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(world, (world, 1, 1))
+    uid_bytes = None
+    if world > 1:
+        # one process per GPU; torch.distributed is plumbing (rendezvous, barrier, max-over-ranks), the halo is NCCL
+        dist.init_process_group("nccl", device_id=torch.device("cuda", device))
+        import ctypes
+        from nebulasem_b200 import capi
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf = ctypes.create_string_buffer(128)
+            if capi.load_library().nsem_get_unique_id(buf) != 0:
+                raise SystemExit("bench.py: ncclGetUniqueId failed")
+            uid = torch.tensor(list(buf.raw), dtype=torch.uint8, device="cuda")
+        dist.broadcast(uid, 0)
+        uid_bytes = bytes(uid.cpu().tolist())
+        config["parallelism"] = (f"{world} partitions ({args.decomp}), one per GPU, global mesh {args.n * pgrid[0]}x{args.n * pgrid[1]}x"
+                                 f"{args.n * pgrid[2]} elements, NCCL face-trace halo")
 
     t0 = time.time()
-    s = host.Solver.synthetic("bubble3d", args.n, args.n, args.n, ORDER)
+    if world == 1:
+        s = host.Solver.synthetic("bubble3d", args.n, args.n, args.n, ORDER)
+        s.attach(device)
+    else:
+        s = host.Solver.synthetic_part("bubble3d", args.n * pgrid[0], args.n * pgrid[1], args.n * pgrid[2], ORDER, rank, world,
+                                       args.decomp, pgrid)
+        s.attach(device, rank, world, uid_bytes)
     t_setup = time.time() - t0
-    s.attach(device)
-    nodes = s.gBCSfield
+    nodes_local = s.gBCSfield
     launches0 = s.launch_count
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
     s.step(warmup)
     s.sync()
+    barrier()
     sampler = ClockSampler(device)
     sampler.start()
     ms, _ = s.time_steps(steps, per_kernel=False)
+    barrier()
     clocks = sampler.stop()
-    launches = s.launch_count - launches0 - 4 * warmup     # kernels inside the timed region
-    ms_pk_total, pk = s.time_steps(max(2, steps // 2), per_kernel=True)
+    launches = s.launch_count - launches0
+    nodes = nodes_local
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)            # device time, max over ranks
+        ms = float(t.item())
+        nn = torch.tensor([nodes_local], dtype=torch.float64, device="cuda")
+        dist.all_reduce(nn)
+        nodes = int(nn.item())
+    steps_per_launchcount = launches / max(1, warmup + steps)
+    launches = int(round(steps_per_launchcount * steps))   # kernels inside the timed region
     pk_steps = max(2, steps // 2)
+    ms_pk_total, pk = s.time_steps(pk_steps, per_kernel=True)
+    barrier()
     value = 5.0 * nodes * steps / (ms * 1e-3)
 
     # finite-state sanity after all those steps (a diverged run would be a meaningless number)
@@ -215,19 +258,20 @@ def main():
     bpn = algorithmic_bytes_per_node(visc=True)
     peak, peak_src = measured_peak_gbs()
     tA, tB = pk[0] / pk_steps * 1e-3, pk[2] / pk_steps * 1e-3
-    achieved_B = bpn["B"] * nodes / tB / 1e9
-    achieved_A = bpn["A"] * nodes / tA / 1e9
+    achieved_B = bpn["B"] * nodes_local / tB / 1e9
+    achieved_A = bpn["A"] * nodes_local / tA / 1e9
     roofline = {"bound": "hbm", "kernel": "sweepB_kernel<5,5,5,2,true>", "achieved": achieved_B, "peak": peak, "unit": "GB/s",
                 "frac": achieved_B / peak, "traffic": None, "peak_source": peak_src,
                 "bytes_per_node": {"sweepA": bpn["A"], "sweepB": bpn["B"], "step": bpn["total"], "survey_B_alg": bpn["survey_B_alg"]},
                 "sweepA": {"achieved": achieved_A, "frac": achieved_A / peak, "ms": tA * 1e3},
                 "sweepB": {"achieved": achieved_B, "frac": achieved_B / peak, "ms": tB * 1e3},
                 "bc_ms": [pk[1] / pk_steps, pk[3] / pk_steps],
-                "step": {"achieved": bpn["total"] * nodes / (ms / steps * 1e-3) / 1e9, "frac": bpn["total"] * nodes / (ms / steps * 1e-3) / 1e9 / peak}}
+                "step": {"achieved": bpn["total"] * nodes / world / (ms / steps * 1e-3) / 1e9,
+                         "frac": bpn["total"] * nodes / world / (ms / steps * 1e-3) / 1e9 / peak, "note": "per GPU"}}
 
     # e2e: host buffers in, host buffers out, every step
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and world == 1:
         e_steps = max(1, min(steps, 3))
         s.upload(); s.step(1); s.download()                # warm the transfer path
         torch.cuda.synchronize()
@@ -243,15 +287,43 @@ def main():
                "d2h_bytes_per_step": 6 * gall * 8, "steps": e_steps, "ms_per_step": dt_e / e_steps * 1e3,
                "what": "nsem_upload_state(rho,U,T,p host arrays) + nsem_euler_step(1) + nsem_download_state, wall clock"}
 
+    if not args.no_e2e and world > 1:
+        # every rank moves its own partition through the C ABI with host buffers; aggregate = all nodes / max wall time
+        e_steps = max(1, min(steps, 3))
+        s.upload(); s.step(1); s.download()
+        barrier()
+        t1 = time.perf_counter()
+        for _ in range(e_steps):
+            s.upload()
+            s.step(1)
+            s.download()
+        torch.cuda.synchronize()
+        dt_e = torch.tensor([time.perf_counter() - t1], dtype=torch.float64, device="cuda")
+        dist.all_reduce(dt_e, op=dist.ReduceOp.MAX)
+        dt_e = float(dt_e.item())
+        e2e = {"value": 5.0 * nodes * e_steps / dt_e, "unit": "DOF-updates/s", "h2d_bytes_per_step": 6 * s.gALL * 8 * world,
+               "d2h_bytes_per_step": 6 * s.gALL * 8 * world, "steps": e_steps, "ms_per_step": dt_e / e_steps * 1e3,
+               "what": "per rank: nsem_upload_state + nsem_euler_step(1) + nsem_download_state, max wall clock over ranks"}
+
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and rank == 0 and world == 1:
         cpu = run_reference_sample(args.ref_n, 5, 1)
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        s.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
 
     line = {"metric": "dGSEM Euler DOF-updates/s per stage", "value": value, "unit": "DOF-updates/s", "n_gpus": world, "steps": steps,
             "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config, "node_updates_per_s": value / 5.0, "roofline": roofline,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "setup_s": t_setup}
     print(json.dumps(line), flush=True)
+    s.close()
+    if world > 1:
+        dist.destroy_process_group()
     return 0
 
 

@@ -154,7 +154,12 @@ struct nsem_ctx {
     uint64_t nSendSlots = 0;
     DevBuf<double> sendBuf;          // [16][nSendSlots]
     DevBuf<uint32_t> sendNodes;      // owner node (device index) per send slot
-    cudaEvent_t evCompute = nullptr, evComm = nullptr;
+    // overlap of the halo exchange with the interior elements (mul(), field.h:2381-2415 does interior cells first too)
+    DevBuf<uint32_t> schedInt, schedHalo;     // elements without / with an inter-partition face
+    uint32_t nInt = 0, nHalo = 0;
+    cudaEvent_t evA = nullptr, evCA = nullptr, evB = nullptr, evCB = nullptr;
+    bool cbPending = false;                   // an exchange of U_new/T_new is in flight on the comm stream
+    bool overlap = false;                     // NSEM_OVERLAP=1: halo elements first, exchange overlapped with the interior (measured slower)
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -814,7 +819,62 @@ static void fill_bcparams(const nsem_ctx* c, const KParams& P, BCParams& B, int 
 
 static int halo_exchange(nsem_ctx* c, double* const* arrays, int nf, cudaStream_t s);
 
+// One step with the halo exchanges on the comm stream overlapped with the interior elements (the reference's mul()
+// also does interior cells while the halo is in flight, field.h:2381-2415).  Elements that touch an
+// inter-partition face go first in each sweep, their traces are packed and exchanged while the interior runs:
+//   compute: wait exch(U,T) of the previous step | A(halo) -> evA | A(interior) | bcA | wait exch(A fields) | B(halo) -> evB | B(interior) | bcB
+//   comm   :                     wait evA: pack + exchange(rho_new,p,grads) -> evCA      wait evB: pack + exchange(U_new,T_new) -> evCB
+static int one_step_overlapped(nsem_ctx* c) {
+    KParams P;
+    BCParams B;
+    fill_kparams(c, P);
+    KParams PI = P, PH = P;
+    PI.sched = c->schedInt.p; PI.nB = c->nInt;
+    PH.sched = c->schedHalo.p; PH.nB = c->nHalo;
+    cudaStream_t s = c->stream, cs = c->comm;
+    if (c->cbPending) CUDA_TRY(c, cudaStreamWaitEvent(s, c->evCB, 0));
+    if (c->nHalo) CUDA_TRY(c, launch_sweepA(c, PH));
+    CUDA_TRY(c, cudaEventRecord(c->evA, s));
+    CUDA_TRY(c, cudaStreamWaitEvent(cs, c->evA, 0));
+    {
+        double* arr[14] = {P.rho_new, P.p};
+        int nf = 2;
+        if (P.visc) { for (int q = 0; q < 9; q++) arr[nf++] = P.GU[q]; for (int q = 0; q < 3; q++) arr[nf++] = P.GT[q]; }
+        if (halo_exchange(c, arr, nf, cs)) return 1;
+    }
+    CUDA_TRY(c, cudaEventRecord(c->evCA, cs));
+    if (c->nInt) CUDA_TRY(c, launch_sweepA(c, PI));
+    fill_bcparams(c, P, B, 0);
+    CUDA_TRY(c, launch_bc(c, B));
+    CUDA_TRY(c, cudaStreamWaitEvent(s, c->evCA, 0));
+    if (c->nHalo) CUDA_TRY(c, launch_sweepB(c, PH));
+    CUDA_TRY(c, cudaEventRecord(c->evB, s));
+    CUDA_TRY(c, cudaStreamWaitEvent(cs, c->evB, 0));
+    {
+        double* arr[4] = {P.U_new[0], P.U_new[1], P.U_new[2], P.T_new};
+        if (halo_exchange(c, arr, 4, cs)) return 1;
+    }
+    CUDA_TRY(c, cudaEventRecord(c->evCB, cs));
+    c->cbPending = true;
+    if (c->nInt) CUDA_TRY(c, launch_sweepB(c, PI));
+    B.phase = 1;
+    CUDA_TRY(c, launch_bc(c, B));
+    c->launches += (c->nInt ? 2 : 0) + (c->nHalo ? 2 : 0) + (c->nG ? 2 : 0);
+    c->cur ^= 1;
+    return 0;
+}
+// make the compute stream see the last in-flight halo exchange (before downloads, timing stops, serial steps)
+static int join_comm(nsem_ctx* c) {
+    if (c->cbPending) {
+        CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->evCB, 0));
+        c->cbPending = false;
+    }
+    return 0;
+}
+
 static int one_step(nsem_ctx* c, bool timed, double* acc) {
+    if (!timed && !c->peers.empty() && c->overlap) return one_step_overlapped(c);
+    if (join_comm(c)) return 1;
     KParams P;
     BCParams B;
     fill_kparams(c, P);
@@ -865,7 +925,7 @@ extern "C" int nsem_euler_step(nsem_ctx* c, int nsteps) {
     CUDA_TRY(c, cudaSetDevice(c->device));
     for (int s = 0; s < nsteps; s++)
         if (one_step(c, false, nullptr)) return 1;
-    return 0;
+    return join_comm(c);
 }
 
 extern "C" int nsem_time_steps(nsem_ctx* c, int nsteps, double* ms, double* per_kernel_ms) {
@@ -885,6 +945,7 @@ extern "C" int nsem_time_steps(nsem_ctx* c, int nsteps, double* ms, double* per_
     CUDA_TRY(c, cudaEventRecord(t0, c->stream));
     for (int s = 0; s < nsteps; s++)
         if (one_step(c, false, nullptr)) return 1;
+    if (join_comm(c)) return 1;
     CUDA_TRY(c, cudaEventRecord(t1, c->stream));
     CUDA_TRY(c, cudaEventSynchronize(t1));
     float tot = 0;
@@ -938,7 +999,23 @@ extern "C" int nsem_set_halo(nsem_ctx* c, const nsem_halo_peer* peers, uint32_t 
     CUDA_TRY(c, c->sendNodes.upload(nodes, c->stream));
     CUDA_TRY(c, c->sendBuf.alloc((size_t)16 * nodes.size()));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    if (!c->evCompute) { CUDA_TRY(c, cudaEventCreateWithFlags(&c->evCompute, cudaEventDisableTiming)); CUDA_TRY(c, cudaEventCreateWithFlags(&c->evComm, cudaEventDisableTiming)); }
+    if (!c->evA)
+        for (cudaEvent_t* e : {&c->evA, &c->evCA, &c->evB, &c->evCB}) CUDA_TRY(c, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    {
+        std::vector<uint8_t> isHalo(c->nB, 0);
+        for (const auto& P : c->peers)
+            for (uint32_t j = 0; j < P.nf; j++) isHalo[c->h_bOwner[P.g0 + j]] = 1;
+        std::vector<uint32_t> li, lh;
+        for (uint32_t e = 0; e < c->nB; e++) (isHalo[e] ? lh : li).push_back(e);
+        c->nInt = (uint32_t)li.size();
+        c->nHalo = (uint32_t)lh.size();
+        CUDA_TRY(c, c->schedInt.upload(li, c->stream));
+        CUDA_TRY(c, c->schedHalo.upload(lh, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
+    const char* ov = std::getenv("NSEM_OVERLAP");
+    c->overlap = (ov && std::strcmp(ov, "1") == 0);
+    c->cbPending = false;
     return 0;
 }
 
