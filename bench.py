@@ -273,7 +273,7 @@ def main():
     e2e = None
     if not args.no_e2e and world == 1:
         e_steps = max(1, min(steps, 3))
-        s.upload(); s.step(1); s.download()                # warm the transfer path
+        s.upload(); s.step(1); s.download()                # warm the transfer path (first call page-locks the host arrays)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         for _ in range(e_steps):

@@ -122,6 +122,8 @@ int nsem_upload_state(nsem_ctx* ctx, const double* rho, const double* U, const d
 int nsem_download_state(nsem_ctx* ctx, double* rho, double* U, double* T, double* p);
 /* Hydrostatic reference state and gravity (euler.cpp:105-131); g may be NULL for uniform params.gravity. */
 int nsem_upload_ref(nsem_ctx* ctx, const double* rho_ref, const double* p_ref, const double* g);
+/* Geopotential gh = dot(g, cC) per node (euler.cpp:113), only needed by the energy diagnostic; optional. */
+int nsem_upload_geopotential(nsem_ctx* ctx, const double* gh);
 
 /* ---- the hot path ------------------------------------------------------------------------------------ */
 /* nsteps iterations of the time-loop body apps/euler/euler.cpp:179-287 (steps 1-8 and 10 of SURVEY 3.2):
@@ -131,7 +133,7 @@ int nsem_euler_step(nsem_ctx* ctx, int nsteps);
  * inter-partition ghost cells of rho, U, T, p, rho_ref and p_ref from the neighbouring ranks. Collective. */
 int nsem_exchange_state_halos(nsem_ctx* ctx);
 /* euler.cpp:261-283 + Mesh::calc_courant (field.cpp:440-448): out = {courant max, min, avg, mass, energy,
- * volume}, all-reduced over ranks. */
+ * volume} over the real nodes, all-reduced over ranks (reduce_max/min/avg/sum, field.h:953-1006). Collective. */
 int nsem_diagnostics(nsem_ctx* ctx, double out[6]);
 /* cudaDeviceSynchronize on the context's streams. */
 int nsem_sync(nsem_ctx* ctx);

@@ -46,7 +46,7 @@ class NsemHaloPeer(C.Structure):
 
 EXPORTS = ["nsem_create", "nsem_destroy", "nsem_last_error", "nsem_get_unique_id", "nsem_set_order", "nsem_set_basis",
            "nsem_upload_mesh", "nsem_set_bcs", "nsem_set_halo", "nsem_set_params", "nsem_set_schedule",
-           "nsem_upload_state", "nsem_download_state", "nsem_upload_ref", "nsem_euler_step", "nsem_exchange_state_halos", "nsem_diagnostics",
+           "nsem_upload_state", "nsem_download_state", "nsem_upload_ref", "nsem_upload_geopotential", "nsem_euler_step", "nsem_exchange_state_halos", "nsem_diagnostics",
            "nsem_sync", "nsem_time_steps", "nsem_launch_count"]
 
 _lib = None
@@ -78,6 +78,7 @@ def load_library() -> C.CDLL:
     lib.nsem_upload_state.argtypes = [vp, _dp, _dp, _dp, _dp]
     lib.nsem_download_state.argtypes = [vp, _dp, _dp, _dp, _dp]
     lib.nsem_upload_ref.argtypes = [vp, _dp, _dp, _dp]
+    lib.nsem_upload_geopotential.argtypes = [vp, _dp]
     lib.nsem_euler_step.argtypes = [vp, C.c_int]
     lib.nsem_exchange_state_halos.argtypes = [vp]
     lib.nsem_diagnostics.argtypes = [vp, _dp]
@@ -219,10 +220,13 @@ class Context:
         self._ck(self.lib.nsem_download_state(self.h, _pd(rho), _pd(U), _pd(T), _pd(p)))
         return rho, U, T, p
 
-    def upload_ref(self, rho_ref, p_ref, g=None):
+    def upload_ref(self, rho_ref, p_ref, g=None, gh=None):
         a, b = _f64(rho_ref), _f64(p_ref)
         gg = _f64(g) if g is not None else None
         self._ck(self.lib.nsem_upload_ref(self.h, _pd(a), _pd(b), _pd(gg)))
+        if gh is not None:
+            hh = _f64(gh)
+            self._ck(self.lib.nsem_upload_geopotential(self.h, _pd(hh)))
 
     # ---- hot path ----------------------------------------------------------------------------------
     def step(self, nsteps=1):

@@ -154,6 +154,11 @@ int nsemh_sync(nsemh_solver* h) { GUARD(if (nsem_sync(h->s.ctx)) throw Error(nse
 int nsemh_time(nsemh_solver* h, int nsteps, double* ms, double* per_kernel) {
     GUARD(if (!h->s.ctx) throw Error("no device attached"); if (nsem_time_steps(h->s.ctx, nsteps, ms, per_kernel)) throw Error(nsem_last_error(h->s.ctx)))
 }
+// {courant max, min, avg, mass, energy, volume} of the CURRENT device state + the initial totals mass0/energy0/volume0
+int nsemh_diagnostics(nsemh_solver* h, double out[9]) {
+    GUARD(if (!h->s.ctx) throw Error("no device attached"); if (nsem_diagnostics(h->s.ctx, out)) throw Error(nsem_last_error(h->s.ctx));
+          out[6] = h->s.mass0; out[7] = h->s.energy0; out[8] = h->s.volume0)
+}
 uint64_t nsemh_launch_count(nsemh_solver* h) { return h->s.ctx ? nsem_launch_count(h->s.ctx) : 0; }
 int nsemh_set_schedule(nsemh_solver* h, const uint32_t* order, uint32_t n) {
     GUARD(if (nsem_set_schedule(h->s.ctx, order, n)) throw Error(nsem_last_error(h->s.ctx)))

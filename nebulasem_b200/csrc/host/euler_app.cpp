@@ -377,6 +377,7 @@ void EulerSolver::attach_device(int device, int rank, int nranks, const void* ui
     q.buoyancy = buoyancy; q.diffusion = diffusion;
     ck(nsem_set_params(ctx, &q));
     ck(nsem_upload_ref(ctx, rho_ref.data(), p_ref.data(), nullptr));
+    ck(nsem_upload_geopotential(ctx, gh.data()));
     upload_state();
     if (nranks > 1) {
         // gInterMesh (mesh.h:180-196): one entry per interMesh_<me>_<peer> patch

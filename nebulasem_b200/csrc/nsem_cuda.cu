@@ -122,7 +122,8 @@ struct nsem_ctx {
     std::vector<uint8_t> h_bFid;
 
     // node arrays
-    DevBuf<double> rho[2], U[2][3], T[2], p, GU[9], GT[3], Jinv[9], cV, rho_ref, p_ref, gfield[3];
+    DevBuf<double> rho[2], U[2][3], T[2], p, GU[9], GT[3], Jinv[9], cV, rho_ref, p_ref, gfield[3], gh, diagPartial;
+    bool has_gh = false;
     int cur = 0;
     bool has_gfield = false;
     // element-face tables
@@ -142,6 +143,19 @@ struct nsem_ctx {
     DevBuf<double> stage;
     DevBuf<double*> ptrTab;
     DevBuf<int> compMap;
+
+    // host arrays handed to upload/download are page-locked once (cudaHostRegister) so the PCIe copies run at full rate
+    std::vector<std::pair<const void*, size_t>> pinned;
+    bool pin(const void* p, size_t bytes) {
+        for (auto& r : pinned)
+            if (r.first == p && r.second >= bytes) return true;
+        if (cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault) != cudaSuccess) {
+            cudaGetLastError();     // pageable copies still work
+            return false;
+        }
+        pinned.emplace_back(p, bytes);
+        return true;
+    }
 
     // timing
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -334,6 +348,7 @@ extern "C" void nsem_destroy(nsem_ctx* c) {
     if (c->nccl) g_nccl.CommDestroy(c->nccl);
 #endif
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& r : c->pinned) cudaHostUnregister(const_cast<void*>(r.first));
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->comm) cudaStreamDestroy(c->comm);
     delete c;
@@ -699,6 +714,7 @@ static int to_device(nsem_ctx* c, const double* host, int comps, double* const d
     if (c->stage.n < (size_t)c->nRefNodes * 3) CUDA_TRY(c, c->stage.alloc((size_t)c->nRefNodes * 3));
     if (!c->ptrTab.p) { CUDA_TRY(c, c->ptrTab.alloc(3)); CUDA_TRY(c, c->compMap.alloc(3)); }
     const int cm[3] = {0, 1, 2};
+    c->pin(host, bytes);
     CUDA_TRY(c, cudaMemcpyAsync(c->stage.p, host, bytes, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(c->ptrTab.p, dst, comps * sizeof(double*), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(c->compMap.p, cm, comps * sizeof(int), cudaMemcpyHostToDevice, c->stream));
@@ -710,13 +726,16 @@ static int to_device(nsem_ctx* c, const double* host, int comps, double* const d
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
+// Writes the real nodes and every ghost node that a boundary face touches; the remaining nodes of the ghost cells
+// (never read by any operator) are returned as 0.
 static int from_device(nsem_ctx* c, double* host, int comps, const double* const src[3]) {
     const size_t bytes = (size_t)c->nRefNodes * comps * sizeof(double);
+    const size_t realBytes = (size_t)c->nB * c->NP * comps * sizeof(double);
     if (c->stage.n < (size_t)c->nRefNodes * 3) CUDA_TRY(c, c->stage.alloc((size_t)c->nRefNodes * 3));
     if (!c->ptrTab.p) { CUDA_TRY(c, c->ptrTab.alloc(3)); CUDA_TRY(c, c->compMap.alloc(3)); }
     const int cm[3] = {0, 1, 2};
-    // nodes of ghost cells that no face touches keep the caller's values
-    CUDA_TRY(c, cudaMemcpyAsync(c->stage.p, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    c->pin(host, bytes);
+    CUDA_TRY(c, cudaMemsetAsync(reinterpret_cast<char*>(c->stage.p) + realBytes, 0, bytes - realBytes, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(c->ptrTab.p, src, comps * sizeof(double*), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(c->compMap.p, cm, comps * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     const uint64_t n = (uint64_t)c->nB * c->NP + (uint64_t)c->nG * c->NPF;
@@ -1063,8 +1082,55 @@ extern "C" int nsem_exchange_state_halos(nsem_ctx* c) {
     return 0;
 }
 
+extern "C" int nsem_upload_geopotential(nsem_ctx* c, const double* gh) {
+    if (!c->have_mesh) { c->err = "nsem_upload_geopotential: no mesh"; return 1; }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, c->gh.alloc(c->nNodes));
+    double* d1[3] = {c->gh.p, nullptr, nullptr};
+    if (to_device(c, gh, 1, d1)) return 1;
+    c->has_gh = true;
+    return 0;
+}
+
 extern "C" int nsem_diagnostics(nsem_ctx* c, double out[6]) {
-    (void)out;
-    c->err = "nsem_diagnostics: not built yet";
-    return 1;
+    if (check_ready(c, "nsem_diagnostics")) return 1;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (join_comm(c)) return 1;
+    const int nblk = 148 * 4;
+    if (c->diagPartial.n < (size_t)(nblk + 1) * 6) CUDA_TRY(c, c->diagPartial.alloc((size_t)(nblk + 1) * 6));
+    DiagParams D;
+    std::memset(&D, 0, sizeof D);
+    const int k = c->cur;
+    D.nB = c->nB; D.NP = c->NP; D.NPS = c->NPS;
+    D.P0 = c->prm.P0; D.T0 = c->prm.T0; D.R = c->prm.cp - c->prm.cv; D.cp = c->prm.cp; D.cv = c->prm.cv; D.dt = c->prm.dt;
+    D.rho = c->rho[k].p; D.T = c->T[k].p; D.p = c->p.p; D.p_ref = c->p_ref.p; D.cV = c->cV.p;
+    for (int d = 0; d < 3; d++) D.U[d] = c->U[k][d].p;
+    D.gh = c->has_gh ? c->gh.p : nullptr;
+    D.partial = c->diagPartial.p; D.nparts = nblk;
+    diag_kernel<<<nblk, 256, 0, c->stream>>>(D);
+    diag_fold_kernel<<<1, 256, 0, c->stream>>>(D);
+    c->launches += 2;
+    CUDA_TRY(c, cudaGetLastError());
+    double* res = c->diagPartial.p + (size_t)nblk * 6;      // {max, min, sum courant, mass, energy, volume}
+    double count = (double)c->nB * c->NP;
+#ifdef NSEM_WITH_NCCL
+    if (c->nranks > 1) {
+        // reduce_max / reduce_min / reduce_sum over ranks (MP::allreduce, mp.h:93-104)
+        if (c->stage.n < 8) CUDA_TRY(c, c->stage.alloc(8));
+        CUDA_TRY(c, cudaMemcpyAsync(c->stage.p, &count, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        ncclResult_t r = g_nccl.GroupStart();
+        if (r == ncclSuccess) r = g_nccl.AllReduce(res + 0, res + 0, 1, ncclDouble, ncclMax, c->nccl, c->stream);
+        if (r == ncclSuccess) r = g_nccl.AllReduce(res + 1, res + 1, 1, ncclDouble, ncclMin, c->nccl, c->stream);
+        if (r == ncclSuccess) r = g_nccl.AllReduce(res + 2, res + 2, 4, ncclDouble, ncclSum, c->nccl, c->stream);
+        if (r == ncclSuccess) r = g_nccl.AllReduce(c->stage.p, c->stage.p, 1, ncclDouble, ncclSum, c->nccl, c->stream);
+        ncclResult_t r2 = g_nccl.GroupEnd();
+        if (r != ncclSuccess || r2 != ncclSuccess) { c->err = std::string("nsem_diagnostics: ") + g_nccl.GetErrorString(r != ncclSuccess ? r : r2); return 1; }
+        CUDA_TRY(c, cudaMemcpyAsync(&count, c->stage.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
+#endif
+    double h[6];
+    CUDA_TRY(c, cudaMemcpyAsync(h, res, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    out[0] = h[0]; out[1] = h[1]; out[2] = h[2] / count; out[3] = h[3]; out[4] = h[4]; out[5] = h[5];
+    return 0;
 }

@@ -615,6 +615,71 @@ __global__ void __launch_bounds__(256) bc_kernel(const __grid_constant__ BCParam
 }
 
 // ---------------------------------------------------------------------------------------------------
+// diagnostics (euler.cpp:261-283, Mesh::calc_courant field.cpp:440-448, reduce_* field.h:953-1006):
+// per block partials of {courant max, courant min, courant sum, mass, energy, volume}; a second launch with one
+// block folds the partials in index order (deterministic, no atomics).
+// ---------------------------------------------------------------------------------------------------
+struct DiagParams {
+    uint32_t nB;
+    int NP, NPS;
+    double P0, T0, R, cp, cv, dt;
+    const double *rho, *U[3], *T, *p, *p_ref, *cV, *gh;
+    double* partial;     // [nblocks][6]
+    int nparts;          // second pass: number of partials to fold
+};
+__device__ __forceinline__ void diag_block_fold(double v[6], double* sh) {
+    // sh: [6][blockDim.x/32]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        v[0] = fmax(v[0], __shfl_down_sync(0xffffffffu, v[0], o));
+        v[1] = fmin(v[1], __shfl_down_sync(0xffffffffu, v[1], o));
+#pragma unroll
+        for (int c = 2; c < 6; c++) v[c] += __shfl_down_sync(0xffffffffu, v[c], o);
+    }
+    if (lane == 0)
+        for (int c = 0; c < 6; c++) sh[c * nw + w] = v[c];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 1; q < nw; q++) {
+            v[0] = fmax(v[0], sh[0 * nw + q]);
+            v[1] = fmin(v[1], sh[1 * nw + q]);
+            for (int c = 2; c < 6; c++) v[c] += sh[c * nw + q];
+        }
+    }
+}
+__global__ void __launch_bounds__(256) diag_kernel(const __grid_constant__ DiagParams D) {
+    __shared__ double sh[6 * 8];
+    double v[6] = {-1e300, 1e300, 0, 0, 0, 0};
+    const uint64_t n = (uint64_t)D.nB * D.NP;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = (q / D.NP) * D.NPS + (q % D.NP);
+        const double u0 = D.U[0][i], u1 = D.U[1][i], u2 = D.U[2][i], cv_ = D.cV[i], rho = D.rho[i];
+        const double m2 = u0 * u0 + (u1 * u1 + u2 * u2);
+        const double co = sqrt(m2) * D.dt / pow(cv_, 1.0 / 3);
+        const double th = D.T[i] + D.T0;
+        const double e = (D.gh ? D.gh[i] : 0.0) + 0.5 * m2 + pow((D.p[i] + D.p_ref[i]) / D.P0, D.R / D.cp) * th * D.cv;
+        v[0] = fmax(v[0], co); v[1] = fmin(v[1], co); v[2] += co;
+        v[3] += rho * cv_; v[4] += rho * cv_ * e; v[5] += cv_;
+    }
+    diag_block_fold(v, sh);
+    if (threadIdx.x == 0)
+        for (int c = 0; c < 6; c++) D.partial[(size_t)blockIdx.x * 6 + c] = v[c];
+}
+__global__ void __launch_bounds__(256) diag_fold_kernel(const __grid_constant__ DiagParams D) {
+    __shared__ double sh[6 * 8];
+    double v[6] = {-1e300, 1e300, 0, 0, 0, 0};
+    for (int q = threadIdx.x; q < D.nparts; q += blockDim.x) {
+        const double* p = D.partial + (size_t)q * 6;
+        v[0] = fmax(v[0], p[0]); v[1] = fmin(v[1], p[1]);
+        for (int c = 2; c < 6; c++) v[c] += p[c];
+    }
+    diag_block_fold(v, sh);
+    if (threadIdx.x == 0)
+        for (int c = 0; c < 6; c++) D.partial[(size_t)D.nparts * 6 + c] = v[c];
+}
+
+// ---------------------------------------------------------------------------------------------------
 // halo pack (ASYNC_COMM::send, field.h:2283-2290): sendBuf[f][slot] = P[FO[k]] for every slot of every
 // inter-partition face, laid out exactly like the receiver's ghost cells (stride GPS per face) so that the
 // receive lands directly in the ghost region of each array (no unpack pass, cf. field.h:2314-2321).

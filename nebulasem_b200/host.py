@@ -15,7 +15,7 @@ from . import capi
 
 HOST_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libnsem_host.so")
 HOST_EXPORTS = ["nsemh_error", "nsemh_close", "nsemh_open_case", "nsemh_synthetic", "nsemh_synthetic_part", "nsemh_patch_faces",
-                "nsemh_peers", "nsemh_attach", "nsemh_step",
+                "nsemh_peers", "nsemh_diagnostics", "nsemh_attach", "nsemh_step",
                 "nsemh_upload", "nsemh_download", "nsemh_write", "nsemh_run", "nsemh_sync", "nsemh_time",
                 "nsemh_launch_count", "nsemh_set_schedule", "nsemh_dims", "nsemh_params", "nsemh_f64", "nsemh_u32",
                 "nsemh_state_ptr", "nsemh_totals"]
@@ -51,6 +51,7 @@ def load_host_library() -> C.CDLL:
     lib.nsemh_step.argtypes = [vp, C.c_int]
     lib.nsemh_write.argtypes = [vp, C.c_int]
     lib.nsemh_time.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.nsemh_diagnostics.argtypes = [vp, C.POINTER(C.c_double)]
     lib.nsemh_launch_count.argtypes = [vp]
     lib.nsemh_launch_count.restype = C.c_uint64
     lib.nsemh_set_schedule.argtypes = [vp, C.POINTER(C.c_uint32), C.c_uint32]
@@ -190,6 +191,13 @@ class Solver:
         pk = (C.c_double * 4)()
         self._ck(self.lib.nsemh_time(self.h, int(nsteps), C.byref(ms), pk if per_kernel else None))
         return ms.value, list(pk)
+
+    def diagnostics(self) -> dict:
+        """Courant max/min/avg, mass, energy, volume of the device state and the relative losses euler.cpp:278-281 prints."""
+        o = (C.c_double * 9)()
+        self._ck(self.lib.nsemh_diagnostics(self.h, o))
+        return dict(courant_max=o[0], courant_min=o[1], courant_avg=o[2], mass=o[3], energy=o[4], volume=o[5],
+                    mass_loss=(o[6] - o[3]) / o[6], energy_loss=(o[7] - o[4]) / o[7], volume_loss=(o[8] - o[5]) / o[8])
 
     def set_schedule(self, order):
         if order is None:

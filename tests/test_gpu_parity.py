@@ -73,3 +73,25 @@ def test_two_partitions_equal_one_partition(decomp):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     print(out.stdout[-3000:], out.stderr[-3000:])
     assert out.returncode == 0 and "MP_CHECK_OK" in out.stdout
+
+
+def test_diagnostics_match_oracle(tmp_cases):
+    """nsem_diagnostics (Courant, mass, energy, volume; euler.cpp:261-283) against the oracle's sums."""
+    from nebulasem_b200 import host
+    nsteps = 8
+    orc = make_oracle(tmp_cases, "hill3d", nsteps, exact=False, nx=6, ny=2, nz=4, order=3)
+    orc.run(nsteps)
+    s = host.Solver.open_case(orc.case_dir)
+    s.attach(0)
+    s.step(nsteps)
+    d = s.diagnostics()
+    mass, energy, volume = orc.diagnostics_sums(orc.T + orc.p.T0)
+    nb = orc.gB
+    co = np.sqrt((orc.U[:nb] ** 2).sum(axis=1)) * orc.p.dt / orc.g.cV[:nb] ** (1.0 / 3)
+    assert abs(d["mass"] - mass) <= 1e-12 * abs(mass)
+    assert abs(d["energy"] - energy) <= 1e-12 * abs(energy)
+    assert abs(d["volume"] - volume) <= 1e-12 * abs(volume)
+    assert abs(d["courant_max"] - co.max()) <= 1e-12 * co.max()
+    assert abs(d["courant_avg"] - co.mean()) <= 1e-12 * co.mean()
+    assert abs(d["mass_loss"]) < 1e-12          # the scheme conserves mass to rounding (reference prints ~1e-15)
+    s.close()
