@@ -120,6 +120,9 @@ int nsem_set_schedule(nsem_ctx* ctx, const uint32_t* order, uint32_t n);
  * rho, U (AoS 3), T (perturbation theta - T0, euler.cpp:181,286), p (perturbation p - p_ref). */
 int nsem_upload_state(nsem_ctx* ctx, const double* rho, const double* U, const double* T, const double* p);
 int nsem_download_state(nsem_ctx* ctx, double* rho, double* U, double* T, double* p);
+/* Page-lock a host array that will be passed to upload/download repeatedly and outlives the context (the solver's
+ * field storage); optional, transfers from pageable memory work too. Unregistered by nsem_destroy. */
+int nsem_pin_host(nsem_ctx* ctx, const void* ptr, uint64_t bytes);
 /* Hydrostatic reference state and gravity (euler.cpp:105-131); g may be NULL for uniform params.gravity. */
 int nsem_upload_ref(nsem_ctx* ctx, const double* rho_ref, const double* p_ref, const double* g);
 /* Geopotential gh = dot(g, cC) per node (euler.cpp:113), only needed by the energy diagnostic; optional. */

@@ -8,6 +8,7 @@
 #include "../../include/nsem_c.h"
 #include "nsem_kernels.cuh"
 #include "nsem_kernels_v2.cuh"
+#include "nsem_kernels_v3.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -22,6 +23,13 @@
 #include <nccl.h>   // types only: the library is resolved at run time (see NcclApi) so that this .so carries no
                     // link-time NCCL dependency and shares whichever libnccl.so.2 the process already loaded
                     // (torch bundles its own; two different NCCL builds in one process do not mix)
+#endif
+
+#ifndef NSEM_V3_MINB_A
+#define NSEM_V3_MINB_A 4
+#endif
+#ifndef NSEM_V3_MINB_B
+#define NSEM_V3_MINB_B 4
 #endif
 
 using namespace nsem;
@@ -105,6 +113,7 @@ struct nsem_ctx {
     cudaStream_t stream = nullptr, comm = nullptr;
     mutable std::string err;
     uint64_t launches = 0;
+    bool use_v3 = false;      // warp-per-element pencil kernels (NSEM_KERNELS=v3)
     bool use_v2 = false;      // bulk-async staged kernels (3-D); NSEM_KERNELS=v1 forces the plain-load kernels
 
     int NX = 0, NY = 0, NZ = 0, NP = 0, NPF = 0, NPS = 0, GPS = 0;
@@ -144,7 +153,7 @@ struct nsem_ctx {
     DevBuf<double*> ptrTab;
     DevBuf<int> compMap;
 
-    // host arrays handed to upload/download are page-locked once (cudaHostRegister) so the PCIe copies run at full rate
+    // host arrays the caller declares long-lived (nsem_pin_host) are page-locked so the PCIe copies run at full rate
     std::vector<std::pair<const void*, size_t>> pinned;
     bool pin(const void* p, size_t bytes) {
         for (auto& r : pinned)
@@ -237,6 +246,35 @@ struct Launch {
             return go2(v2::sweepB_v2<NX, NY, NZ, EPB2, false, C2::minb(C2::smemB(false), 128)>, C2::smemB(false), P, s);
         } else return cudaErrorInvalidValue;
     }
+    // ---- v3: one warp per element, one thread per k-pencil (isotropic 3-D orders with N*N <= 32) ----
+    static constexpr bool has_v3 = (NX == NY && NY == NZ && NX > 1 && NX * NX <= 32);
+    static constexpr int N3 = has_v3 ? NX : 2;
+    static constexpr int WPB3 = 2;
+    using C3 = v3::Cfg3<N3>;
+    template <class K>
+    static cudaError_t go3(K kernel, size_t smem, const KParams& P, cudaStream_t s) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        const unsigned grid = (P.nB + WPB3 - 1) / WPB3;
+        kernel<<<grid, WPB3 * 32, smem, s>>>(P);
+        return cudaGetLastError();
+    }
+    static cudaError_t sweepA3(const KParams& P, cudaStream_t s) {
+        if constexpr (has_v3) {
+            const size_t smem = (size_t)WPB3 * C3::smemA_w * sizeof(double);
+            if (P.visc) return go3(v3::sweepA_v3<N3, WPB3, true, NSEM_V3_MINB_A>, smem, P, s);
+            return go3(v3::sweepA_v3<N3, WPB3, false, NSEM_V3_MINB_A>, smem, P, s);
+        } else return cudaErrorInvalidValue;
+    }
+    static cudaError_t sweepB3(const KParams& P, cudaStream_t s) {
+        if constexpr (has_v3) {
+            const size_t smem = (size_t)WPB3 * C3::smemB_w * sizeof(double);
+            if (P.visc) return go3(v3::sweepB_v3<N3, WPB3, true, NSEM_V3_MINB_B>, smem, P, s);
+            return go3(v3::sweepB_v3<N3, WPB3, false, NSEM_V3_MINB_B>, smem, P, s);
+        } else return cudaErrorInvalidValue;
+    }
     static cudaError_t bc(const BCParams& B, cudaStream_t s) {
         const uint64_t n = (uint64_t)B.nG * Dm::NPF;
         if (n == 0) return cudaSuccess;
@@ -259,14 +297,21 @@ static bool has_v2(int nx, int ny, int nz) {
     return false;
 }
 
+static bool has_v3(int nx, int ny, int nz) {
+#define X(a, b, c) if (nx == a && ny == b && nz == c) return Launch<a, b, c>::has_v3;
+    NSEM_ORDERS(X)
+#undef X
+    return false;
+}
+
 static cudaError_t launch_sweepA(const nsem_ctx* c, const KParams& P) {
-#define X(a, b, cc) if (c->NX == a && c->NY == b && c->NZ == cc) return c->use_v2 ? Launch<a, b, cc>::sweepA2(P, c->stream) : Launch<a, b, cc>::sweepA(P, c->stream);
+#define X(a, b, cc) if (c->NX == a && c->NY == b && c->NZ == cc) return c->use_v3 ? Launch<a, b, cc>::sweepA3(P, c->stream) : c->use_v2 ? Launch<a, b, cc>::sweepA2(P, c->stream) : Launch<a, b, cc>::sweepA(P, c->stream);
     NSEM_ORDERS(X)
 #undef X
     return cudaErrorInvalidValue;
 }
 static cudaError_t launch_sweepB(const nsem_ctx* c, const KParams& P) {
-#define X(a, b, cc) if (c->NX == a && c->NY == b && c->NZ == cc) return c->use_v2 ? Launch<a, b, cc>::sweepB2(P, c->stream) : Launch<a, b, cc>::sweepB(P, c->stream);
+#define X(a, b, cc) if (c->NX == a && c->NY == b && c->NZ == cc) return c->use_v3 ? Launch<a, b, cc>::sweepB3(P, c->stream) : c->use_v2 ? Launch<a, b, cc>::sweepB2(P, c->stream) : Launch<a, b, cc>::sweepB(P, c->stream);
     NSEM_ORDERS(X)
 #undef X
     return cudaErrorInvalidValue;
@@ -397,6 +442,7 @@ extern "C" int nsem_set_order(nsem_ctx* c, int NPX, int NPY, int NPZ) {
     c->have_basis = c->have_mesh = c->have_state = c->have_ref = c->have_bcs = false;
     const char* kv = std::getenv("NSEM_KERNELS");
     c->use_v2 = has_v2(NPX, NPY, NPZ) && !(kv && std::strcmp(kv, "v1") == 0);
+    c->use_v3 = has_v3(NPX, NPY, NPZ) && (kv && std::strcmp(kv, "v3") == 0);
     return 0;
 }
 
@@ -714,7 +760,6 @@ static int to_device(nsem_ctx* c, const double* host, int comps, double* const d
     if (c->stage.n < (size_t)c->nRefNodes * 3) CUDA_TRY(c, c->stage.alloc((size_t)c->nRefNodes * 3));
     if (!c->ptrTab.p) { CUDA_TRY(c, c->ptrTab.alloc(3)); CUDA_TRY(c, c->compMap.alloc(3)); }
     const int cm[3] = {0, 1, 2};
-    c->pin(host, bytes);
     CUDA_TRY(c, cudaMemcpyAsync(c->stage.p, host, bytes, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(c->ptrTab.p, dst, comps * sizeof(double*), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(c->compMap.p, cm, comps * sizeof(int), cudaMemcpyHostToDevice, c->stream));
@@ -734,7 +779,6 @@ static int from_device(nsem_ctx* c, double* host, int comps, const double* const
     if (c->stage.n < (size_t)c->nRefNodes * 3) CUDA_TRY(c, c->stage.alloc((size_t)c->nRefNodes * 3));
     if (!c->ptrTab.p) { CUDA_TRY(c, c->ptrTab.alloc(3)); CUDA_TRY(c, c->compMap.alloc(3)); }
     const int cm[3] = {0, 1, 2};
-    c->pin(host, bytes);
     CUDA_TRY(c, cudaMemsetAsync(reinterpret_cast<char*>(c->stage.p) + realBytes, 0, bytes - realBytes, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(c->ptrTab.p, src, comps * sizeof(double*), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(c->compMap.p, cm, comps * sizeof(int), cudaMemcpyHostToDevice, c->stream));
@@ -745,6 +789,12 @@ static int from_device(nsem_ctx* c, double* host, int comps, const double* const
     CUDA_TRY(c, cudaGetLastError());
     CUDA_TRY(c, cudaMemcpyAsync(host, c->stage.p, bytes, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int nsem_pin_host(nsem_ctx* c, const void* p, uint64_t bytes) {
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (!c->pin(p, (size_t)bytes)) { c->err = "nsem_pin_host: cudaHostRegister failed"; return 1; }
     return 0;
 }
 
