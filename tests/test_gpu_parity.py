@@ -95,3 +95,77 @@ def test_diagnostics_match_oracle(tmp_cases):
     assert abs(d["courant_avg"] - co.mean()) <= 1e-12 * co.mean()
     assert abs(d["mass_loss"]) < 1e-12          # the scheme conserves mass to rounding (reference prints ~1e-15)
     s.close()
+
+
+@pytest.mark.parametrize("order", [2, 3, 4, 5, 6, 7])
+def test_isentropic_vortex_orders_2_to_7(tmp_cases, order):
+    """BASELINE configs[2]: examples/isentropic (CYCLIC, no viscosity, no buoyancy), orders 2-7, 15 steps vs the oracle.
+    Velocities are O(1) here, so rho*U is held to 1e-11 SELF-relative as well."""
+    nsteps = 15
+    orc = make_oracle(tmp_cases, "vortex", nsteps, exact=False, n=5, order=order)
+    ctx = device_from_oracle(orc)
+    ctx.step(nsteps)
+    orc.run(nsteps)
+    rho, U, T, p = ctx.download_state()
+    err = conserved_errors(orc, rho, U, T)
+    print(order, err)
+    assert err["rho"] <= TOL and err["rhoTheta"] <= TOL and err["rhoU_self"] <= TOL
+    ctx.close()
+
+
+@pytest.mark.parametrize("order", [1, 2, 3, 5, 6, 7])
+def test_bubble3d_other_orders(tmp_cases, order):
+    """3-D orders other than 4 (v2 kernels with their per-order EPB/shared-memory configuration)."""
+    nsteps = 6
+    orc = make_oracle(tmp_cases, "bubble3d", nsteps, exact=False, n=2, order=order)
+    ctx = device_from_oracle(orc)
+    ctx.step(nsteps)
+    orc.run(nsteps)
+    rho, U, T, p = ctx.download_state()
+    err = conserved_errors(orc, rho, U, T)
+    print(order, err)
+    assert err["rho"] <= TOL and err["rhoTheta"] <= TOL and err["rhoU_scaled"] <= TOL
+    ctx.close()
+
+
+def test_kernel_generations_agree_and_conserve_mass_at_scale():
+    """Size-independent properties on a mesh far beyond what the oracle can run (48^3 order 4 = 13.8 M nodes):
+    the three kernel generations (plain loads / bulk-async staged / warp-per-element) agree to rounding, the result does
+    not depend on the element schedule, and mass is conserved to 1e-13 (the reference prints ~1e-15 losses)."""
+    import subprocess
+    import sys
+    code = r'''
+import os, sys, numpy as np
+sys.path.insert(0, %r)
+from nebulasem_b200 import host
+s = host.Solver.synthetic("bubble3d", 48, 48, 48, 4)
+s.attach(0)
+d0 = s.diagnostics()
+s.step(10)
+d = s.diagnostics()
+d["mass_loss"] = (d0["mass"] - d["mass"]) / d0["mass"]      # same device reduction order before and after
+d["volume_loss"] = (d0["volume"] - d["volume"]) / d0["volume"]
+s.download()
+rho, U, T, p = s.state()
+nb = s.gBCSfield
+np.save(sys.argv[1], np.concatenate([rho[:nb, None], U[:nb], T[:nb, None]], axis=1))
+print("MASS_LOSS", d["mass_loss"], "VOLUME_LOSS", d["volume_loss"])
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import tempfile
+    outs = {}
+    with tempfile.TemporaryDirectory() as td:
+        for tag, env in (("v1", {"NSEM_KERNELS": "v1"}), ("v2", {}), ("v3", {"NSEM_KERNELS": "v3"}), ("v2m", {"NSEM_SCHEDULE": "morton"})):
+            f = os.path.join(td, tag + ".npy")
+            r = subprocess.run([sys.executable, "-c", code, f], env={**os.environ, **env}, capture_output=True, text=True, timeout=900)
+            assert r.returncode == 0, r.stderr[-2000:]
+            loss = float(r.stdout.split("MASS_LOSS")[1].split()[0])
+            assert abs(loss) <= 1e-13, (tag, loss)
+            outs[tag] = np.load(f)
+    ref = outs["v1"]
+    assert np.isfinite(ref).all()
+    assert np.array_equal(outs["v2"], outs["v2m"])            # the schedule never changes the result
+    for tag in ("v2", "v3"):
+        a = outs[tag]
+        assert np.linalg.norm(a[:, 0] - ref[:, 0]) / np.linalg.norm(ref[:, 0]) <= 1e-13
+        assert np.linalg.norm(a[:, 0] * (a[:, 4] + 300) - ref[:, 0] * (ref[:, 4] + 300)) / np.linalg.norm(ref[:, 0] * (ref[:, 4] + 300)) <= 1e-13
+        assert np.linalg.norm(a[:, 0:1] * a[:, 1:4] - ref[:, 0:1] * ref[:, 1:4]) / (np.linalg.norm(ref[:, 0]) * 347.0) <= 1e-13
