@@ -260,8 +260,16 @@ def main():
     tA, tB = pk[0] / pk_steps * 1e-3, pk[2] / pk_steps * 1e-3
     achieved_B = bpn["B"] * nodes_local / tB / 1e9
     achieved_A = bpn["A"] * nodes_local / tA / 1e9
-    roofline = {"bound": "hbm", "kernel": "sweepB_kernel<5,5,5,2,true>", "achieved": achieved_B, "peak": peak, "unit": "GB/s",
-                "frac": achieved_B / peak, "traffic": None, "peak_source": peak_src,
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath) and os.environ.get("NSEM_KERNELS", "v2") == "v2":
+        with open(tpath) as f:
+            tj = json.load(f)
+        if tj.get("cells") == args.n:
+            traffic = tj["sweepB_bytes_per_launch"]       # ncu dram__bytes_read+write of the dominant kernel, per launch
+    roofline = {"bound": "hbm", "kernel": "v2::sweepB_v2<5,5,5,1,true,3>", "achieved": achieved_B, "peak": peak, "unit": "GB/s",
+                "frac": achieved_B / peak, "traffic": traffic, "algorithmic_bytes_per_launch": bpn["B"] * nodes_local,
+                "peak_source": peak_src,
                 "bytes_per_node": {"sweepA": bpn["A"], "sweepB": bpn["B"], "step": bpn["total"], "survey_B_alg": bpn["survey_B_alg"]},
                 "sweepA": {"achieved": achieved_A, "frac": achieved_A / peak, "ms": tA * 1e3},
                 "sweepB": {"achieved": achieved_B, "frac": achieved_B / peak, "ms": tB * 1e3},

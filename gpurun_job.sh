@@ -1,1 +1,4 @@
-timeout 1200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "generations" 2>&1 | grep -E "Error|error|assert|passed|failed" | head -20
+mkdir -p gpurun_out
+timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r1_launches_n100.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_launch_bench.log 2>&1
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:sweep -s 6 -c 2 -o gpurun_out/prof_r1_n100 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full_bench.log 2>&1
+ls -la gpurun_out | tail -5
