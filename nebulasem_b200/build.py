@@ -24,7 +24,7 @@ def _newer(target: str, sources: list[str]) -> bool:
 def build_cuda(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     srcs = [os.path.join(CSRC, "nsem_cuda.cu")]
-    deps = srcs + [os.path.join(CSRC, "nsem_kernels.cuh"), os.path.join(ROOT, "include", "nsem_c.h")]
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] + [os.path.join(ROOT, "include", "nsem_c.h")]
     if not force and _newer(LIB, deps):
         return LIB
     cmd = [NVCC, "-O3", "-std=c++17", *ARCH, "-lineinfo", "-Xcompiler", "-fPIC", "-shared", "-DNSEM_WITH_NCCL",

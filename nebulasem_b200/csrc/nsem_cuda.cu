@@ -139,6 +139,7 @@ struct nsem_ctx {
     DevBuf<uint32_t> faceOther, faceMeta, sched;
     DevBuf<double> faceVec, faceUnit;
     DevBuf<FaceRec> faceRec;
+    DevBuf<double> traceA, bVec;     // face traces of sweep A (v2), area vectors of the boundary faces
     bool has_sched = false;
     // ghost tables
     DevBuf<uint32_t> ghostRef, bOwner;
@@ -275,6 +276,12 @@ struct Launch {
             return go3(v3::sweepB_v3<N3, WPB3, false, NSEM_V3_MINB_B>, smem, P, s);
         } else return cudaErrorInvalidValue;
     }
+    static cudaError_t ghost_trace(const GhostTraceParams& G, cudaStream_t s) {
+        const uint64_t n = (uint64_t)G.nG * Dm::NPF;
+        if (n == 0) return cudaSuccess;
+        ghost_trace_kernel<NX, NY, NZ><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(G);
+        return cudaGetLastError();
+    }
     static cudaError_t bc(const BCParams& B, cudaStream_t s) {
         const uint64_t n = (uint64_t)B.nG * Dm::NPF;
         if (n == 0) return cudaSuccess;
@@ -312,6 +319,23 @@ static cudaError_t launch_sweepA(const nsem_ctx* c, const KParams& P) {
 }
 static cudaError_t launch_sweepB(const nsem_ctx* c, const KParams& P) {
 #define X(a, b, cc) if (c->NX == a && c->NY == b && c->NZ == cc) return c->use_v3 ? Launch<a, b, cc>::sweepB3(P, c->stream) : c->use_v2 ? Launch<a, b, cc>::sweepB2(P, c->stream) : Launch<a, b, cc>::sweepB(P, c->stream);
+    NSEM_ORDERS(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+static cudaError_t launch_ghost_trace(const nsem_ctx* c, const KParams& P) {
+    if (!c->use_v2 || c->use_v3) return cudaSuccess;       // only the v2 sweep B consumes face traces
+    GhostTraceParams G;
+    std::memset(&G, 0, sizeof G);
+    G.nB = c->nB; G.nG = c->nG; G.ghostBase = c->ghostBase;
+    G.T0 = P.T0; G.nu = P.nu; G.iPr = P.iPr; G.gammaR = P.gamma * P.R; G.visc = P.visc;
+    std::memcpy(G.W, c->W, sizeof G.W);
+    G.bFid = c->bFid.p; G.bVec = c->bVec.p;
+    G.rho_old = P.rho_old; G.rho_new = P.rho_new; G.T_old = P.T_old; G.p = P.p;
+    for (int d = 0; d < 3; d++) { G.U_old[d] = P.U_old[d]; G.GT[d] = P.GT[d]; }
+    for (int d = 0; d < 9; d++) G.GU[d] = P.GU[d];
+    G.traceA = c->traceA.p;
+#define X(a, b, cc) if (c->NX == a && c->NY == b && c->NZ == cc) return Launch<a, b, cc>::ghost_trace(G, c->stream);
     NSEM_ORDERS(X)
 #undef X
     return cudaErrorInvalidValue;
@@ -601,8 +625,24 @@ extern "C" int nsem_upload_mesh(nsem_ctx* c, const nsem_mesh* m) {
             rec[q].other = fOther[q];
             rec[q].meta = fMeta[q];
             for (int d = 0; d < 3; d++) { rec[q].vec[d] = fVec[q * 3 + d]; rec[q].unit[d] = fUnit[q * 3 + d]; }
-            rec[q].pad = 0;
+            const uint32_t fid = fMeta[q] & FM_FID_MASK;
+            if (fid == FM_GHOST) rec[q].otherBlock = (uint64_t)nB * 6 + (fOther[q] - (uint32_t)c->ghostBase) / (uint32_t)GPS;
+            else if (fid == FM_ABSENT) rec[q].otherBlock = 0;
+            else rec[q].otherBlock = (uint64_t)(fOther[q] / (uint32_t)NPS) * 6 + fid;
         }
+        const size_t FS = (size_t)trace_stride(NPF);
+        CUDA_TRY(c, c->traceA.alloc(((size_t)nB * 6 + nG) * 7 * FS));
+        CUDA_TRY(c, cudaMemsetAsync(c->traceA.p, 0, ((size_t)nB * 6 + nG) * 7 * FS * sizeof(double), s));
+        std::vector<double> bv((size_t)nG * 3, 0.0);
+        for (uint32_t ci2 = 0; ci2 < nB; ci2++)
+            for (int sid = 0; sid < 6; sid++) {
+                const size_t e6 = (size_t)ci2 * 6 + sid;
+                if ((fMeta[e6] & FM_FID_MASK) == FM_GHOST) {
+                    const uint32_t g = (fOther[e6] - (uint32_t)c->ghostBase) / (uint32_t)GPS;
+                    for (int d = 0; d < 3; d++) bv[(size_t)g * 3 + d] = fVec[e6 * 3 + d];
+                }
+            }
+        CUDA_TRY(c, c->bVec.upload(bv, s));
         CUDA_TRY(c, c->faceRec.upload(rec, s));
         CUDA_TRY(c, cudaStreamSynchronize(s));
     }
@@ -860,6 +900,7 @@ static void fill_kparams(const nsem_ctx* c, KParams& P) {
     // mu = rho*viscosity when diffusion is on (euler.cpp:189-190); viscosity == 0 gives the same fluxes
     P.visc = (q.diffusion && q.viscosity != 0.0) ? 1 : 0;
     P.has_gfield = c->has_gfield ? 1 : 0;
+    { const char* pr = std::getenv("NSEM_PROBE"); P.probe = pr ? std::atoi(pr) : 0; }
     std::memcpy(P.D, c->D, sizeof P.D);
     std::memcpy(P.W, c->W, sizeof P.W);
     P.rho_old = c->rho[k].p; P.rho_new = c->rho[o].p;
@@ -872,6 +913,7 @@ static void fill_kparams(const nsem_ctx* c, KParams& P) {
     P.faceOther = c->faceOther.p; P.faceMeta = c->faceMeta.p; P.faceVec = c->faceVec.p; P.faceUnit = c->faceUnit.p;
     P.sched = c->has_sched ? c->sched.p : nullptr;
     P.faceRec = c->faceRec.p;
+    P.traceA = c->traceA.p;
 }
 static void fill_bcparams(const nsem_ctx* c, const KParams& P, BCParams& B, int phase) {
     std::memset(&B, 0, sizeof B);
@@ -916,6 +958,7 @@ static int one_step_overlapped(nsem_ctx* c) {
     fill_bcparams(c, P, B, 0);
     CUDA_TRY(c, launch_bc(c, B));
     CUDA_TRY(c, cudaStreamWaitEvent(s, c->evCA, 0));
+    CUDA_TRY(c, launch_ghost_trace(c, P));
     if (c->nHalo) CUDA_TRY(c, launch_sweepB(c, PH));
     CUDA_TRY(c, cudaEventRecord(c->evB, s));
     CUDA_TRY(c, cudaStreamWaitEvent(cs, c->evB, 0));
@@ -958,6 +1001,7 @@ static int one_step(nsem_ctx* c, bool timed, double* acc) {
         if (P.visc) { for (int q = 0; q < 9; q++) arr[nf++] = P.GU[q]; for (int q = 0; q < 3; q++) arr[nf++] = P.GT[q]; }
         if (halo_exchange(c, arr, nf, c->stream)) return 1;
     }
+    CUDA_TRY(c, launch_ghost_trace(c, P));
     if (timed) cudaEventRecord(c->ev[2], c->stream);
     CUDA_TRY(c, launch_sweepB(c, P));
     if (timed) cudaEventRecord(c->ev[3], c->stream);
@@ -968,7 +1012,7 @@ static int one_step(nsem_ctx* c, bool timed, double* acc) {
         if (halo_exchange(c, arr, 4, c->stream)) return 1;
     }
     if (timed) cudaEventRecord(c->ev[4], c->stream);
-    c->launches += 2 + (c->nG ? 2 : 0);
+    c->launches += 2 + (c->nG ? 2 : 0) + ((c->nG && c->use_v2 && !c->use_v3) ? 1 : 0);
     c->cur ^= 1;
     if (timed) {
         CUDA_TRY(c, cudaEventSynchronize(c->ev[4]));

@@ -49,6 +49,7 @@ struct KParams {
     // physics
     double P0, T0, R, gamma, nu, iPr, dt, g[3];
     int buoyancy, visc, has_gfield;
+    int probe;                   // diagnostics only (NSEM_PROBE): 1 = stream the inputs and skip the arithmetic, 2 = also skip the gathers
     // basis
     double D[3][MAXN * MAXN];    // D[d][s*n+i] = l_i'(x_s)
     double W[3][MAXN];
@@ -77,13 +78,16 @@ struct KParams {
     const double* faceUnit;      // [nB*6*3] unit(gFN)
     const uint32_t* sched;       // optional processing order
     const struct FaceRec* faceRec;   // [nB*6] the four tables above packed in one 64-byte record (v2 kernels)
+    // face traces (v2): per face block 7 x FS doubles {normal fluxes of the 3 momentum eqs and theta, rho_new U.N,
+    // rho_new theta, |U| + c} of the side that OWNS the block; block id = elem*6 + local face, ghost cells nB*6 + g
+    double* traceA;
 };
 
 struct alignas(16) FaceRec {
     uint32_t other, meta;
     double vec[3];
     double unit[3];
-    double pad;
+    uint64_t otherBlock;     // face-trace block of the other side (see KParams::traceA)
 };
 static_assert(sizeof(FaceRec) == 64, "FaceRec must be 64 bytes");
 
@@ -612,6 +616,80 @@ __global__ void __launch_bounds__(256) bc_kernel(const __grid_constant__ BCParam
             }
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// face traces: what a neighbour needs from this side of a face node to evaluate the Rusanov fluxes of the U- and
+// theta-equations (euler.cpp:232-233,249-251 with rusanov field.h:2928-2943), reduced with the face's weighted
+// area vector N (identical on both sides): the side's central normal fluxes, its conserved q contracted with N,
+// and its |U| + c for lambdaMax (euler.cpp:186).
+// ---------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int trace_stride(int npf) { return pad_to(npf, 2); }
+struct SideState {
+    double rho_o, rho_n, u[3], th, pp, gU[9], gT[3];
+};
+__device__ __forceinline__ void side_trace(const SideState& q, const double N[3], double nu, double iPr, double gammaR, bool visc,
+                                           double out[7]) {
+    const double un = q.u[0] * N[0] + q.u[1] * N[1] + q.u[2] * N[2];
+#pragma unroll
+    for (int c = 0; c < 3; c++) out[c] = (q.rho_o * q.u[c]) * un + q.pp * N[c];
+    out[3] = q.th * (q.rho_o * un);
+    if (visc) {
+        const double mu = q.rho_o * nu;
+#pragma unroll
+        for (int c = 0; c < 3; c++) out[c] -= mu * (q.gU[c * 3 + 0] * N[0] + q.gU[c * 3 + 1] * N[1] + q.gU[c * 3 + 2] * N[2]);
+        out[3] -= (mu * iPr) * (q.gT[0] * N[0] + q.gT[1] * N[1] + q.gT[2] * N[2]);
+    }
+    out[4] = q.rho_n * un;
+    out[5] = q.rho_n * q.th;
+    out[6] = sqrt(q.u[0] * q.u[0] + (q.u[1] * q.u[1] + q.u[2] * q.u[2])) + sqrt(gammaR * q.th);
+}
+
+struct GhostTraceParams {
+    uint32_t nB, nG;
+    uint64_t ghostBase;
+    double T0, nu, iPr, gammaR;
+    int visc;
+    double W[3][MAXN];
+    const uint8_t* bFid;
+    const double* bVec;              // [nG*3] area vector gFN of the boundary face
+    const double *rho_old, *rho_new, *U_old[3], *T_old, *p, *GU[9], *GT[3];
+    double* traceA;
+};
+template <int NX, int NY, int NZ>
+__global__ void __launch_bounds__(256) ghost_trace_kernel(const __grid_constant__ GhostTraceParams G) {
+    using Dm = Dims<NX, NY, NZ>;
+    constexpr int NPF = Dm::NPF, GPS = Dm::GPS, FS = trace_stride(NPF);
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (uint64_t)G.nG * NPF) return;
+    const uint32_t g = (uint32_t)(gid / NPF);
+    const int n = (int)(gid % NPF);
+    const int fid = G.bFid[g];
+    int a, b;
+    bool valid;
+    double w;
+    if (fid < 2) { a = n / NY; b = n % NY; valid = n < NX * NY; w = G.W[0][a % MAXN] * G.W[1][b % MAXN] / 4; }
+    else if (fid < 4) { a = n / NZ; b = n % NZ; valid = n < NX * NZ; w = G.W[0][a % MAXN] * G.W[2][b % MAXN] / 4; }
+    else { a = n / NZ; b = n % NZ; valid = n < NY * NZ; w = G.W[1][a % MAXN] * G.W[2][b % MAXN] / 4; }
+    if (!valid) return;
+    const size_t gi = G.ghostBase + (size_t)g * GPS + n;
+    SideState q;
+    q.rho_o = G.rho_old[gi]; q.rho_n = G.rho_new[gi];
+    q.u[0] = G.U_old[0][gi]; q.u[1] = G.U_old[1][gi]; q.u[2] = G.U_old[2][gi];
+    q.th = G.T_old[gi] + G.T0;
+    q.pp = G.p[gi];
+    if (G.visc) {
+#pragma unroll
+        for (int c = 0; c < 9; c++) q.gU[c] = G.GU[c][gi];
+#pragma unroll
+        for (int c = 0; c < 3; c++) q.gT[c] = G.GT[c][gi];
+    }
+    const double N[3] = {G.bVec[g * 3] * w, G.bVec[g * 3 + 1] * w, G.bVec[g * 3 + 2] * w};
+    double out[7];
+    side_trace(q, N, G.nu, G.iPr, G.gammaR, G.visc != 0, out);
+    double* dst = G.traceA + ((size_t)G.nB * 6 + g) * 7 * FS + n;
+#pragma unroll
+    for (int c = 0; c < 7; c++) dst[c * FS] = out[c];
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -84,8 +84,10 @@ struct Cfg {
         int b = bs < br ? bs : br;
         return b < 1 ? 1 : (b > 4 ? 4 : b);
     }
+    static constexpr int FS = trace_stride(Dm::NPF);
     static constexpr size_t smemB(bool visc) {
-        return sizeof(double) * ((size_t)nin_b(visc) * EPB * NPS + 12 * EPB * NP + (size_t)EPB * NFT * 4 + 3 * MAXN * MAXN) + 16;
+        return sizeof(double) * ((size_t)nin_b(visc) * EPB * NPS + 12 * EPB * NP + (size_t)EPB * NFT * 4 + (size_t)EPB * 6 * 7 * FS +
+                                 3 * MAXN * MAXN) + 16;
     }
 };
 
@@ -234,37 +236,69 @@ __global__ void __launch_bounds__(Cfg<NX, NY, NZ, EPB>::NT, MINB) sweepA_v2(cons
     }
     __syncthreads();
 
-    if (!nodeOn) return;
+    if (nodeOn) {
 #pragma unroll
-    for (int s = 0; s < 6; s++) {
-        if (!on_face(s, i, j, k, NX, NY, NZ)) continue;
-        int a, b;
-        face_slot<NX, NY, NZ>(s, i, j, k, a, b);
-        const double* in = &sF[(size_t)ne * NFT + Tk::index(s, a, b)];
-        constexpr int CS = EPB * NFT;
-        r_rho += in[0];
-        if (VISC) {
-            const double q0 = in[1 * CS], q1 = in[2 * CS], q2 = in[3 * CS], q3 = in[4 * CS];
+        for (int s = 0; s < 6; s++) {
+            if (!on_face(s, i, j, k, NX, NY, NZ)) continue;
+            int a, b;
+            face_slot<NX, NY, NZ>(s, i, j, k, a, b);
+            const double* in = &sF[(size_t)ne * NFT + Tk::index(s, a, b)];
+            constexpr int CS = EPB * NFT;
+            r_rho += in[0];
+            if (VISC) {
+                const double q0_ = in[1 * CS], q1_ = in[2 * CS], q2_ = in[3 * CS], q3_ = in[4 * CS];
 #pragma unroll
-            for (int aa = 0; aa < 3; aa++) {
-                const double sn = in[(5 + aa) * CS];
-                gU[aa * 3 + 0] += sn * q0;
-                gU[aa * 3 + 1] += sn * q1;
-                gU[aa * 3 + 2] += sn * q2;
-                gT[aa] += sn * q3;
+                for (int aa = 0; aa < 3; aa++) {
+                    const double sn = in[(5 + aa) * CS];
+                    gU[aa * 3 + 0] += sn * q0_;
+                    gU[aa * 3 + 1] += sn * q1_;
+                    gU[aa * 3 + 2] += sn * q2_;
+                    gT[aa] += sn * q3_;
+                }
             }
         }
+        const double ap0 = (-1.0 / P.dt) * cV;
+        const double rho_new = (r_rho + rho * ap0) / ap0;
+        P.rho_new[idx] = rho_new;
+        const double ppn = __dsub_rn(eos_pressure(P.P0, P.R, P.gamma, rho_new, th), IN(15, ne, nt));
+        P.p[idx] = ppn;
+        // the new values also go to shared memory (over the metric slots, which only this thread read) for the trace pass
+        IN(14, ne, nt) = rho_new;
+        IN(15, ne, nt) = ppn;
+        if (VISC) {
+            const double rcV = 1.0 / cV;            // r / cV (field.h:3359) as one reciprocal and 12 products
+#pragma unroll
+            for (int c = 0; c < 9; c++) { const double v = gU[c] * rcV; P.GU[c][idx] = v; IN(5 + c, ne, nt) = v; }
+#pragma unroll
+            for (int c = 0; c < 3; c++) { const double v = gT[c] * rcV; P.GT[c][idx] = v; sR[(c * EPB + ne) * NP + nt] = v; }
+        }
     }
-    const double ap0 = (-1.0 / P.dt) * cV;
-    const double rho_new = (r_rho + rho * ap0) / ap0;
-    P.rho_new[idx] = rho_new;
-    P.p[idx] = __dsub_rn(eos_pressure(P.P0, P.R, P.gamma, rho_new, th), IN(15, ne, nt));
-    if (VISC) {
-        const double rcV = 1.0 / cV;            // r / cV (field.h:3359) as one reciprocal and 12 products
+    __syncthreads();
+    // this side's face traces for sweep B of the neighbours (and of the peers behind a partition boundary): dense face
+    // tasks again, so every face block is written as contiguous runs
+    if (faceOn) {
+        const double w = face_weight<NX, NY, NZ>(P, fs, fa, fb);
+        const double Nv[3] = {q0.y * w, q1.x * w, q1.y * w};
+        const int fln = face_node<NX, NY, NZ>(fs, fa, fb);
+        SideState q;
+        q.rho_o = IN(0, fe, fln); q.rho_n = IN(14, fe, fln);
+        q.u[0] = IN(1, fe, fln); q.u[1] = IN(2, fe, fln); q.u[2] = IN(3, fe, fln);
+        q.th = IN(4, fe, fln);
+        q.pp = IN(15, fe, fln);
+        if (VISC) {
 #pragma unroll
-        for (int c = 0; c < 9; c++) P.GU[c][idx] = gU[c] * rcV;
+            for (int c = 0; c < 9; c++) q.gU[c] = IN(5 + c, fe, fln);
 #pragma unroll
-        for (int c = 0; c < 3; c++) P.GT[c][idx] = gT[c] * rcV;
+            for (int c = 0; c < 3; c++) q.gT[c] = sR[(c * EPB + fe) * NP + fln];
+        }
+        double out[7];
+        side_trace(q, Nv, P.nu, P.iPr, P.gamma * P.R, VISC, out);
+        constexpr int TS = C::FS;
+        const uint32_t felem = P.sched ? P.sched[first + fe] : first + fe;
+        const int n = (fs < 2) ? fa * NY + fb : fa * NZ + fb;
+        double* dst = P.traceA + ((size_t)felem * 6 + fs) * 7 * TS + n;
+#pragma unroll
+        for (int c = 0; c < 7; c++) dst[c * TS] = out[c];
     }
 }
 
@@ -284,7 +318,7 @@ __global__ void __launch_bounds__(Cfg<NX, NY, NZ, EPB>::NT, MINB) sweepB_v2(cons
     double* sIn = reinterpret_cast<double*>(smem_raw);             // [NIN][EPB][NPS]
     double* sH = sIn + (size_t)NIN * EPB * NPS;                    // [12][EPB][NP]
     double* sF = sH + 12 * EPB * NP;                               // [4][EPB][NFT]
-    double* sD = sF + (size_t)EPB * NFT * 4;                       // [3][MAXN*MAXN]
+    double* sD = sF + (size_t)EPB * NFT * 4 + (size_t)EPB * 6 * 7 * C::FS;   // [3][MAXN*MAXN]
     uint64_t* bar = reinterpret_cast<uint64_t*>(sD + 3 * MAXN * MAXN);
     auto IN = [&](int arr, int e, int t) -> double& { return sIn[((size_t)arr * EPB + e) * NPS + t]; };
 
@@ -293,9 +327,18 @@ __global__ void __launch_bounds__(Cfg<NX, NY, NZ, EPB>::NT, MINB) sweepB_v2(cons
     const int nvalid = (int)min((uint32_t)EPB, P.nB - first);
     if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
     __syncthreads();
+    constexpr int FS = C::FS;
+    double* sT = sF + (size_t)EPB * NFT * 4;                       // [EPB][6][7][FS] neighbour-side face traces
     if (tid < 32) {
-        if (tid == 0) mbar_expect_tx(bar, (uint32_t)(nvalid * NIN * NPS * sizeof(double)));
+        if (tid == 0) mbar_expect_tx(bar, (uint32_t)(nvalid * (NIN * NPS + 6 * 7 * FS) * sizeof(double)));
         __syncwarp();
+        // neighbour traces: one bulk copy per face (the block id sits in the face record)
+        for (int q = tid; q < nvalid * 6; q += 32) {
+            const int e = q / 6, f = q % 6;
+            const uint32_t elem = P.sched ? P.sched[first + e] : first + e;
+            const uint64_t blk = P.faceRec[(size_t)elem * 6 + f].otherBlock;
+            bulk_g2s(sT + ((size_t)e * 6 + f) * 7 * FS, P.traceA + (size_t)blk * 7 * FS, 7 * FS * sizeof(double), bar);
+        }
         for (int q = tid; q < nvalid * NIN; q += 32) {
             const int e = q / NIN, arr = q % NIN;
             const uint32_t elem = P.sched ? P.sched[first + e] : first + e;
@@ -325,30 +368,25 @@ __global__ void __launch_bounds__(Cfg<NX, NY, NZ, EPB>::NT, MINB) sweepB_v2(cons
     const bool faceOn = tid < EPB * NFT && fe < nvalid;
     int fs = 0, fa = 0, fb = 0;
     double2 q0 = {0, 0}, q1 = {0, 0}, q2 = {0, 0}, q3 = {0, 0};
-    double xro = 0, xrn = 0, xu[3] = {0, 0, 0}, xT = 0, xpp = 0, xG[VISC ? 12 : 1];
     if (faceOn) {
         Tk::decode(ff, fs, fa, fb);
         const uint32_t felem = P.sched ? P.sched[first + fe] : first + fe;
         const double2* rp = reinterpret_cast<const double2*>(P.faceRec + ((size_t)felem * 6 + fs));
         q0 = rp[0]; q1 = rp[1]; q2 = rp[2]; q3 = rp[3];
-        const unsigned long long om = (unsigned long long)__double_as_longlong(q0.x);
-        const uint32_t fid = (uint32_t)(om >> 32) & FM_FID_MASK;
-        const int n = (fs < 2) ? fa * NY + fb : fa * NZ + fb;
-        const size_t oidx = (size_t)(uint32_t)om + (fid == FM_GHOST ? n : face_node<NX, NY, NZ>(fid, fa, fb));
-        xro = P.rho_old[oidx]; xrn = P.rho_new[oidx];
-        xu[0] = P.U_old[0][oidx]; xu[1] = P.U_old[1][oidx]; xu[2] = P.U_old[2][oidx];
-        xT = P.T_old[oidx];
-        xpp = P.p[oidx];
-        if (VISC) {
-#pragma unroll
-            for (int c = 0; c < 9; c++) xG[c] = P.GU[c][oidx];
-#pragma unroll
-            for (int c = 0; c < 3; c++) xG[9 + c] = P.GT[c][oidx];
-        }
     }
 
     mbar_wait(bar, 0);
     __syncthreads();
+    if (P.probe) {
+        // bandwidth probe (not a product path): touch every staged value and every gathered value, write the 4 outputs
+        double acc = 0;
+        if (faceOn) for (int c = 0; c < 7; c++) acc += sT[((size_t)fe * 6 + fs) * 7 * FS + c * FS + ((fs < 2) ? fa * NY + fb : fa * NZ + fb)];
+        if (nodeOn) {
+            for (int a = 0; a < NIN; a++) acc += IN(a, ne, nt);
+            P.U_new[0][idx] = acc; P.U_new[1][idx] = acc; P.U_new[2][idx] = acc; P.T_new[idx] = acc;
+        } else if (acc == 1.2345e300) P.T_new[0] = acc;
+        return;
+    }
 
     double rho_o = 0, rho_nw = 1, u[3] = {0, 0, 0}, th = 0, cV = 1, rref = 0;
     if (nodeOn) {
@@ -404,58 +442,41 @@ __global__ void __launch_bounds__(Cfg<NX, NY, NZ, EPB>::NT, MINB) sweepB_v2(cons
 
     if (faceOn) {
         const uint32_t meta = (uint32_t)((unsigned long long)__double_as_longlong(q0.x) >> 32);
+        const uint32_t fid = meta & FM_FID_MASK;
         const bool own = meta & FM_OWNER;
         const double al = (meta & FM_HALF) ? 0.5 : 0.0;
         const double w = face_weight<NX, NY, NZ>(P, fs, fa, fb);
         const double N[3] = {q0.y * w, q1.x * w, q1.y * w};
         const double fu[3] = {q2.x, q2.y, q3.x};
         const double nN = fu[0] * N[0] + fu[1] * N[1] + fu[2] * N[2];
-        const double xth = xT + P.T0;
-        double xgN[4] = {0, 0, 0, 0};
-        if (VISC) {
-#pragma unroll
-            for (int c = 0; c < 3; c++) xgN[c] = xG[c * 3 + 0] * N[0] + xG[c * 3 + 1] * N[1] + xG[c * 3 + 2] * N[2];
-            xgN[3] = xG[9] * N[0] + xG[10] * N[1] + xG[11] * N[2];
-        }
+        // my side, from the staged element data
         const int fln = face_node<NX, NY, NZ>(fs, fa, fb);
-        const double mro = IN(A_RO, fe, fln), mrn = IN(A_RN, fe, fln);
-        const double mu3[3] = {IN(A_U, fe, fln), IN(A_U + 1, fe, fln), IN(A_U + 2, fe, fln)};
-        const double mth = IN(A_T, fe, fln) + P.T0;
-        const double mpp = IN(A_P, fe, fln);
-        double me[4], xe[4];
-        const double un = mu3[0] * N[0] + mu3[1] * N[1] + mu3[2] * N[2];
-        const double xun = xu[0] * N[0] + xu[1] * N[1] + xu[2] * N[2];
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            me[c] = (mro * mu3[c]) * un + mpp * N[c];
-            xe[c] = (xro * xu[c]) * xun + xpp * N[c];
-        }
-        me[3] = mth * (mro * un);
-        xe[3] = xth * (xro * xun);
+        SideState me;
+        me.rho_o = IN(A_RO, fe, fln); me.rho_n = IN(A_RN, fe, fln);
+        me.u[0] = IN(A_U, fe, fln); me.u[1] = IN(A_U + 1, fe, fln); me.u[2] = IN(A_U + 2, fe, fln);
+        me.th = IN(A_T, fe, fln) + P.T0;
+        me.pp = IN(A_P, fe, fln);
         if (VISC) {
-            const double mmu = mro * P.nu, xmu = xro * P.nu;
 #pragma unroll
-            for (int c = 0; c < 3; c++) {
-                me[c] -= mmu * (IN(A_GU + c * 3 + 0, fe, fln) * N[0] + IN(A_GU + c * 3 + 1, fe, fln) * N[1] + IN(A_GU + c * 3 + 2, fe, fln) * N[2]);
-                xe[c] -= xmu * xgN[c];
-            }
-            me[3] -= (mmu * P.iPr) * (IN(A_GT, fe, fln) * N[0] + IN(A_GT + 1, fe, fln) * N[1] + IN(A_GT + 2, fe, fln) * N[2]);
-            xe[3] -= (xmu * P.iPr) * xgN[3];
+            for (int c = 0; c < 9; c++) me.gU[c] = IN(A_GU + c, fe, fln);
+#pragma unroll
+            for (int c = 0; c < 3; c++) me.gT[c] = IN(A_GT + c, fe, fln);
         }
-        const double mm = sqrt(mu3[0] * mu3[0] + (mu3[1] * mu3[1] + mu3[2] * mu3[2])), xm = sqrt(xu[0] * xu[0] + (xu[1] * xu[1] + xu[2] * xu[2]));
-        const double mc = sqrt(P.gamma * P.R * mth), xc = sqrt(P.gamma * P.R * xth);
+        double mt[7];
+        side_trace(me, N, P.nu, P.iPr, P.gamma * P.R, VISC, mt);
+        // the other side: its face trace, slot = the same (a,b) in ITS face numbering (ghost blocks use mine)
+        const int oslot = (fid == FM_GHOST) ? ((fs < 2) ? fa * NY + fb : fa * NZ + fb) : ((fid < 2) ? fa * NY + fb : fa * NZ + fb);
+        const double* xt = sT + ((size_t)fe * 6 + fs) * 7 * FS + oslot;
         const double wo = own ? al : 1 - al, wx = own ? 1 - al : al;
-        const double lam = ((mm * wo + xm * wx) + (mc * wo + xc * wx)) / 2;
+        const double lam = (mt[6] * wo + xt[6 * FS] * wx) / 2;
         const double sg = own ? 1.0 : -1.0;
-        double dqN = 0;
-#pragma unroll
-        for (int c = 0; c < 3; c++) dqN += (xrn * xu[c] - mrn * mu3[c]) * N[c];
-        const double dqT = xrn * xth - mrn * mth;
+        const double dqN = xt[4 * FS] - mt[4];
+        const double dqT = xt[5 * FS] - mt[5];
         double* out = &sF[(size_t)fe * NFT + ff];
         constexpr int CS = EPB * NFT;
 #pragma unroll
-        for (int c = 0; c < 3; c++) out[c * CS] = sg * ((me[c] * wo + xe[c] * wx) - fu[c] * (lam * (sg * dqN)));
-        out[3 * CS] = sg * ((me[3] * wo + xe[3] * wx) - lam * (sg * dqT) * nN);
+        for (int c = 0; c < 3; c++) out[c * CS] = sg * ((mt[c] * wo + xt[c * FS] * wx) - fu[c] * (lam * (sg * dqN)));
+        out[3 * CS] = sg * ((mt[3] * wo + xt[3 * FS] * wx) - lam * (sg * dqT) * nN);
     }
     __syncthreads();
 
