@@ -315,10 +315,12 @@ __global__ void __launch_bounds__(Cfg<NX, NY, NZ, EPB>::NT, MINB) sweepB_v2(cons
     constexpr int A_RO = 0, A_RN = 1, A_U = 2, A_T = 5, A_P = 6, A_GU = 7, A_GT = 16;
     constexpr int A_J = VISC ? 19 : 7, A_CV = A_J + 9, A_RR = A_CV + 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    // bulk-copy destinations first: sIn is a multiple of 128 bytes, every trace block a multiple of 16 (FS is even)
     double* sIn = reinterpret_cast<double*>(smem_raw);             // [NIN][EPB][NPS]
-    double* sH = sIn + (size_t)NIN * EPB * NPS;                    // [12][EPB][NP]
+    double* sT = sIn + (size_t)NIN * EPB * NPS;                    // [EPB][6][7][FS] neighbour-side face traces
+    double* sH = sT + (size_t)EPB * 6 * 7 * C::FS;                 // [12][EPB][NP]
     double* sF = sH + 12 * EPB * NP;                               // [4][EPB][NFT]
-    double* sD = sF + (size_t)EPB * NFT * 4 + (size_t)EPB * 6 * 7 * C::FS;   // [3][MAXN*MAXN]
+    double* sD = sF + (size_t)EPB * NFT * 4;                       // [3][MAXN*MAXN]
     uint64_t* bar = reinterpret_cast<uint64_t*>(sD + 3 * MAXN * MAXN);
     auto IN = [&](int arr, int e, int t) -> double& { return sIn[((size_t)arr * EPB + e) * NPS + t]; };
 
@@ -328,7 +330,6 @@ __global__ void __launch_bounds__(Cfg<NX, NY, NZ, EPB>::NT, MINB) sweepB_v2(cons
     if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
     __syncthreads();
     constexpr int FS = C::FS;
-    double* sT = sF + (size_t)EPB * NFT * 4;                       // [EPB][6][7][FS] neighbour-side face traces
     if (tid < 32) {
         if (tid == 0) mbar_expect_tx(bar, (uint32_t)(nvalid * (NIN * NPS + 6 * 7 * FS) * sizeof(double)));
         __syncwarp();
