@@ -1,2 +1,1 @@
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "not generations" 2>&1 | tail -2
-timeout 900 python bench.py --cells 100 --steps 5 --warmup 3 --no-cpu-baseline --no-e2e 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); r=d['roofline']; print('traceA only', d['ms_per_step'], '%.3e'%d['value'], 'A %.2f ms %.3f'%(r['sweepA']['ms'], r['sweepA']['frac']), 'B %.2f ms %.3f'%(r['sweepB']['ms'], r['sweepB']['frac']), 'step %.3f'%r['step']['frac'], r['bc_ms'])"
+for p in 0 1 2 3; do NSEM_PROBE=$p timeout 600 python probe_tmp.py 2>&1 | tail -1; done

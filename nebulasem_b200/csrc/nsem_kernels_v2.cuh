@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(Cfg<NX, NY, NZ, EPB>::NT, MINB) sweepA_v2(cons
     int fs = 0, fa = 0, fb = 0;
     double2 q0 = {0, 0}, q1 = {0, 0}, q2 = {0, 0}, q3 = {0, 0};
     double xr = 0, xu0 = 0, xu1 = 0, xu2 = 0, xT = 0;
-    if (faceOn) {
+    if (faceOn && P.probe != 2) {
         Tk::decode(ff, fs, fa, fb);
         const uint32_t felem = P.sched ? P.sched[first + fe] : first + fe;
         const double2* rp = reinterpret_cast<const double2*>(P.faceRec + ((size_t)felem * 6 + fs));
@@ -156,6 +156,22 @@ __global__ void __launch_bounds__(Cfg<NX, NY, NZ, EPB>::NT, MINB) sweepA_v2(cons
 
     mbar_wait(bar, 0);
     __syncthreads();            // sD visible
+    if (P.probe) {
+        // bandwidth probe (not a product path): touch every staged and gathered value, write the 14 outputs (+ traces if probe == 3)
+        double acc = xr + xu0 + xu1 + xu2 + xT;
+        if (tid < EPB * NP && tid / NP < nvalid) {
+            for (int a = 0; a < NIN; a++) acc += IN(a, tid / NP, tid % NP);
+            const size_t id2 = (size_t)(P.sched ? P.sched[first + tid / NP] : first + tid / NP) * NPS + tid % NP;
+            P.rho_new[id2] = acc; P.p[id2] = acc;
+            if (VISC) { for (int c = 0; c < 9; c++) P.GU[c][id2] = acc; for (int c = 0; c < 3; c++) P.GT[c][id2] = acc; }
+        }
+        if (P.probe == 3 && faceOn) {
+            const uint32_t felem = P.sched ? P.sched[first + fe] : first + fe;
+            double* dst = P.traceA + ((size_t)felem * 6 + fs) * 7 * C::FS + ((fs < 2) ? fa * NY + fb : fa * NZ + fb);
+            for (int c = 0; c < 7; c++) dst[c * C::FS] = acc;
+        }
+        return;
+    }
 
     // ---- node: contravariant mass flux, theta ----
     double rho = 0, u0 = 0, u1 = 0, u2 = 0, th = 0, cV = 1, Jin[9];
