@@ -145,6 +145,9 @@ int nsem_sync(nsem_ctx* ctx);
 int nsem_time_steps(nsem_ctx* ctx, int nsteps, double* ms, double* per_kernel_ms);
 /* Number of kernels of this library launched since the context was created. */
 uint64_t nsem_launch_count(const nsem_ctx* ctx);
+/* Which kernel generation and metric path the context runs after nsem_upload_mesh, e.g. "v4 persistent pipelined,
+ * metrics on the fly (trilinear map verified)", "v4 persistent pipelined, stored metrics", "v2", "v1". */
+const char* nsem_kernel_info(const nsem_ctx* ctx);
 
 #ifdef __cplusplus
 }

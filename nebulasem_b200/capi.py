@@ -47,7 +47,7 @@ class NsemHaloPeer(C.Structure):
 EXPORTS = ["nsem_create", "nsem_destroy", "nsem_last_error", "nsem_get_unique_id", "nsem_set_order", "nsem_set_basis",
            "nsem_upload_mesh", "nsem_set_bcs", "nsem_set_halo", "nsem_set_params", "nsem_set_schedule",
            "nsem_pin_host", "nsem_upload_state", "nsem_download_state", "nsem_upload_ref", "nsem_upload_geopotential", "nsem_euler_step", "nsem_exchange_state_halos", "nsem_diagnostics",
-           "nsem_sync", "nsem_time_steps", "nsem_launch_count"]
+           "nsem_sync", "nsem_time_steps", "nsem_launch_count", "nsem_kernel_info"]
 
 _lib = None
 
@@ -87,6 +87,8 @@ def load_library() -> C.CDLL:
     lib.nsem_time_steps.argtypes = [vp, C.c_int, _dp, _dp]
     lib.nsem_launch_count.argtypes = [vp]
     lib.nsem_launch_count.restype = C.c_uint64
+    lib.nsem_kernel_info.argtypes = [vp]
+    lib.nsem_kernel_info.restype = C.c_char_p
     _lib = lib
     return lib
 
@@ -250,3 +252,7 @@ class Context:
     @property
     def launch_count(self):
         return int(self.lib.nsem_launch_count(self.h))
+
+    @property
+    def kernel_info(self) -> str:
+        return self.lib.nsem_kernel_info(self.h).decode()

@@ -160,6 +160,7 @@ int nsemh_diagnostics(nsemh_solver* h, double out[9]) {
           out[6] = h->s.mass0; out[7] = h->s.energy0; out[8] = h->s.volume0)
 }
 uint64_t nsemh_launch_count(nsemh_solver* h) { return h->s.ctx ? nsem_launch_count(h->s.ctx) : 0; }
+const char* nsemh_kernel_info(nsemh_solver* h) { return h->s.ctx ? nsem_kernel_info(h->s.ctx) : ""; }
 int nsemh_set_schedule(nsemh_solver* h, const uint32_t* order, uint32_t n) {
     GUARD(if (nsem_set_schedule(h->s.ctx, order, n)) throw Error(nsem_last_error(h->s.ctx)))
 }

@@ -9,6 +9,7 @@
 #include "nsem_kernels.cuh"
 #include "nsem_kernels_v2.cuh"
 #include "nsem_kernels_v3.cuh"
+#include "nsem_kernels_v4.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -16,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #ifdef NSEM_WITH_NCCL
@@ -25,6 +27,12 @@
                     // (torch bundles its own; two different NCCL builds in one process do not mix)
 #endif
 
+#ifndef NSEM_V4_REGS_A
+#define NSEM_V4_REGS_A 128
+#endif
+#ifndef NSEM_V4_REGS_B
+#define NSEM_V4_REGS_B 128
+#endif
 #ifndef NSEM_V3_MINB_A
 #define NSEM_V3_MINB_A 4
 #endif
@@ -115,6 +123,10 @@ struct nsem_ctx {
     uint64_t launches = 0;
     bool use_v3 = false;      // warp-per-element pencil kernels (NSEM_KERNELS=v3)
     bool use_v2 = false;      // bulk-async staged kernels (3-D); NSEM_KERNELS=v1 forces the plain-load kernels
+    bool use_v4 = false;      // persistent software-pipelined kernels (3-D, default); NSEM_KERNELS=v2|v1|v3 select the older generations
+    bool tri = false;         // v4: metrics evaluated on the fly from the element's trilinear map (verified at upload)
+    int numSMs = 148;
+    double X[3][MAXN];        // LGL nodes
 
     int NX = 0, NY = 0, NZ = 0, NP = 0, NPF = 0, NPS = 0, GPS = 0;
     bool have_basis = false, have_mesh = false, have_params = false, have_state = false, have_ref = false, have_bcs = false;
@@ -139,6 +151,7 @@ struct nsem_ctx {
     DevBuf<uint32_t> faceOther, faceMeta, sched;
     DevBuf<double> faceVec, faceUnit;
     DevBuf<FaceRec> faceRec;
+    DevBuf<ElemRec> elemRec;
     DevBuf<double> traceA, bVec;     // face traces of sweep A (v2), area vectors of the boundary faces
     bool has_sched = false;
     // ghost tables
@@ -276,6 +289,45 @@ struct Launch {
             return go3(v3::sweepB_v3<N3, WPB3, false, NSEM_V3_MINB_B>, smem, P, s);
         } else return cudaErrorInvalidValue;
     }
+    // ---- v4: persistent, software-pipelined (cubic 3-D orders) ----
+    static constexpr bool has_v4 = (NX == NY && NY == NZ && NX > 1) && v4::Cfg<NX, NY, NZ, true, false>::smemB <= 227 * 1024 &&
+                                   v4::CfgA<NX, NY, NZ, true, false>::smem <= 227 * 1024 && v4::CfgA<NX, NY, NZ, true, false>::ok;
+    template <class K>
+    static cudaError_t go4(K kernel, size_t smem, int nt, int minb, const KParams& P, int sms, cudaStream_t s) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        const uint64_t want = (uint64_t)sms * (uint64_t)minb;
+        const unsigned grid = (unsigned)std::min<uint64_t>(P.nB, want);
+        if (grid == 0) return cudaSuccess;
+        kernel<<<grid, nt, smem, s>>>(P);
+        return cudaGetLastError();
+    }
+    template <bool VISC, bool TRI>
+    static cudaError_t sweepA4t(const KParams& P, int sms, cudaStream_t s) {
+        using C4 = v4::CfgA<NX, NY, NZ, VISC, TRI>;
+        constexpr int MB = C4::minb(NSEM_V4_REGS_A);
+        return go4(v4::sweepA_v4<NX, NY, NZ, VISC, TRI, MB>, C4::smem, C4::NT, MB, P, sms, s);
+    }
+    template <bool VISC, bool TRI>
+    static cudaError_t sweepB4t(const KParams& P, int sms, cudaStream_t s) {
+        using C4 = v4::Cfg<NX, NY, NZ, VISC, TRI>;
+        constexpr int MB = C4::minb(C4::smemB, NSEM_V4_REGS_B);
+        return go4(v4::sweepB_v4<NX, NY, NZ, VISC, TRI, MB>, C4::smemB, C4::NT, MB, P, sms, s);
+    }
+    static cudaError_t sweepA4(const KParams& P, bool tri, int sms, cudaStream_t s) {
+        if constexpr (has_v4) {
+            if (P.visc) return tri ? sweepA4t<true, true>(P, sms, s) : sweepA4t<true, false>(P, sms, s);
+            return tri ? sweepA4t<false, true>(P, sms, s) : sweepA4t<false, false>(P, sms, s);
+        } else return cudaErrorInvalidValue;
+    }
+    static cudaError_t sweepB4(const KParams& P, bool tri, int sms, cudaStream_t s) {
+        if constexpr (has_v4) {
+            if (P.visc) return tri ? sweepB4t<true, true>(P, sms, s) : sweepB4t<true, false>(P, sms, s);
+            return tri ? sweepB4t<false, true>(P, sms, s) : sweepB4t<false, false>(P, sms, s);
+        } else return cudaErrorInvalidValue;
+    }
     static cudaError_t ghost_trace(const GhostTraceParams& G, cudaStream_t s) {
         const uint64_t n = (uint64_t)G.nG * Dm::NPF;
         if (n == 0) return cudaSuccess;
@@ -304,6 +356,13 @@ static bool has_v2(int nx, int ny, int nz) {
     return false;
 }
 
+static bool has_v4(int nx, int ny, int nz) {
+#define X(a, b, c) if (nx == a && ny == b && nz == c) return Launch<a, b, c>::has_v4;
+    NSEM_ORDERS(X)
+#undef X
+    return false;
+}
+
 static bool has_v3(int nx, int ny, int nz) {
 #define X(a, b, c) if (nx == a && ny == b && nz == c) return Launch<a, b, c>::has_v3;
     NSEM_ORDERS(X)
@@ -312,19 +371,19 @@ static bool has_v3(int nx, int ny, int nz) {
 }
 
 static cudaError_t launch_sweepA(const nsem_ctx* c, const KParams& P) {
-#define X(a, b, cc) if (c->NX == a && c->NY == b && c->NZ == cc) return c->use_v3 ? Launch<a, b, cc>::sweepA3(P, c->stream) : c->use_v2 ? Launch<a, b, cc>::sweepA2(P, c->stream) : Launch<a, b, cc>::sweepA(P, c->stream);
+#define X(a, b, cc) if (c->NX == a && c->NY == b && c->NZ == cc) return c->use_v4 ? Launch<a, b, cc>::sweepA4(P, c->tri, c->numSMs, c->stream) : c->use_v3 ? Launch<a, b, cc>::sweepA3(P, c->stream) : c->use_v2 ? Launch<a, b, cc>::sweepA2(P, c->stream) : Launch<a, b, cc>::sweepA(P, c->stream);
     NSEM_ORDERS(X)
 #undef X
     return cudaErrorInvalidValue;
 }
 static cudaError_t launch_sweepB(const nsem_ctx* c, const KParams& P) {
-#define X(a, b, cc) if (c->NX == a && c->NY == b && c->NZ == cc) return c->use_v3 ? Launch<a, b, cc>::sweepB3(P, c->stream) : c->use_v2 ? Launch<a, b, cc>::sweepB2(P, c->stream) : Launch<a, b, cc>::sweepB(P, c->stream);
+#define X(a, b, cc) if (c->NX == a && c->NY == b && c->NZ == cc) return c->use_v4 ? Launch<a, b, cc>::sweepB4(P, c->tri, c->numSMs, c->stream) : c->use_v3 ? Launch<a, b, cc>::sweepB3(P, c->stream) : c->use_v2 ? Launch<a, b, cc>::sweepB2(P, c->stream) : Launch<a, b, cc>::sweepB(P, c->stream);
     NSEM_ORDERS(X)
 #undef X
     return cudaErrorInvalidValue;
 }
 static cudaError_t launch_ghost_trace(const nsem_ctx* c, const KParams& P) {
-    if (!c->use_v2 || c->use_v3) return cudaSuccess;       // only the v2 sweep B consumes face traces
+    if (!(c->use_v4 || (c->use_v2 && !c->use_v3))) return cudaSuccess;       // only the v2/v4 sweep B consumes face traces
     GhostTraceParams G;
     std::memset(&G, 0, sizeof G);
     G.nB = c->nB; G.nG = c->nG; G.ghostBase = c->ghostBase;
@@ -371,6 +430,10 @@ extern "C" int nsem_create(int device, int rank, int nranks, const void* nccl_un
     c->device = device;
     c->rank = rank;
     c->nranks = nranks;
+    {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) c->numSMs = sms;
+    }
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->comm, cudaStreamNonBlocking) != cudaSuccess) {
         g_create_error = "nsem_create: cudaStreamCreate failed";
@@ -440,6 +503,13 @@ extern "C" int nsem_get_unique_id(void* out128) {
 
 extern "C" uint64_t nsem_launch_count(const nsem_ctx* c) { return c->launches; }
 
+extern "C" const char* nsem_kernel_info(const nsem_ctx* c) {
+    if (c->use_v4) return c->tri ? "v4 persistent pipelined, metrics on the fly (trilinear map verified)" : "v4 persistent pipelined, stored metrics";
+    if (c->use_v3) return "v3 warp per element";
+    if (c->use_v2) return "v2 bulk-async staged";
+    return "v1 plain loads";
+}
+
 extern "C" int nsem_sync(nsem_ctx* c) {
     CUDA_TRY(c, cudaSetDevice(c->device));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -467,6 +537,8 @@ extern "C" int nsem_set_order(nsem_ctx* c, int NPX, int NPY, int NPZ) {
     const char* kv = std::getenv("NSEM_KERNELS");
     c->use_v2 = has_v2(NPX, NPY, NPZ) && !(kv && std::strcmp(kv, "v1") == 0);
     c->use_v3 = has_v3(NPX, NPY, NPZ) && (kv && std::strcmp(kv, "v3") == 0);
+    c->use_v4 = has_v4(NPX, NPY, NPZ) && !(kv && (std::strcmp(kv, "v1") == 0 || std::strcmp(kv, "v2") == 0 || std::strcmp(kv, "v3") == 0));
+    c->tri = false;
     return 0;
 }
 
@@ -478,6 +550,29 @@ extern "C" int nsem_set_basis(nsem_ctx* c, const double* const dpsi[3], const do
     for (int d = 0; d < 3; d++) {
         for (int q = 0; q < n[d] * n[d]; q++) c->D[d][q] = dpsi[d][q];
         for (int q = 0; q < n[d]; q++) c->W[d][q] = wgl[d][q];
+    }
+    // Legendre-Gauss-Lobatto nodes (dg.cpp:53-99 computes the same points; here they are only used to evaluate the
+    // trilinear map of straight-edged elements, and that evaluation is verified against the uploaded Jinv)
+    std::memset(c->X, 0, sizeof c->X);
+    for (int d = 0; d < 3; d++) {
+        const int N = n[d] - 1;
+        if (N < 1) continue;
+        for (int q = 0; q <= N; q++) {
+            double x = -std::cos(M_PI * q / N);
+            for (int it = 0; it < 100; it++) {
+                double p0 = 1, p1 = x;
+                for (int m = 2; m <= N; m++) { const double p2 = ((2 * m - 1) * x * p1 - (m - 1) * p0) / m; p0 = p1; p1 = p2; }
+                const double dx = (N == 1) ? 0.0 : (x * p1 - p0) / ((N + 1) * p1);
+                x -= dx;
+                if (std::fabs(dx) < 1e-16) break;
+            }
+            c->X[d][q] = x;
+        }
+        c->X[d][0] = -1.0; c->X[d][N] = 1.0;
+        for (int q = 0; q <= N / 2; q++) {          // symmetrise
+            const double v = 0.5 * (c->X[d][N - q] - c->X[d][q]);
+            c->X[d][q] = -v; c->X[d][N - q] = v;
+        }
     }
     c->have_basis = true;
     return 0;
@@ -630,9 +725,9 @@ extern "C" int nsem_upload_mesh(nsem_ctx* c, const nsem_mesh* m) {
             else if (fid == FM_ABSENT) rec[q].otherBlock = 0;
             else rec[q].otherBlock = (uint64_t)(fOther[q] / (uint32_t)NPS) * 6 + fid;
         }
-        const size_t FS = (size_t)trace_stride(NPF);
-        CUDA_TRY(c, c->traceA.alloc(((size_t)nB * 6 + nG) * 7 * FS));
-        CUDA_TRY(c, cudaMemsetAsync(c->traceA.p, 0, ((size_t)nB * 6 + nG) * 7 * FS * sizeof(double), s));
+        const size_t TBS = (size_t)trace_bs(NPF);
+        CUDA_TRY(c, c->traceA.alloc(((size_t)nB * 6 + nG) * TBS));
+        CUDA_TRY(c, cudaMemsetAsync(c->traceA.p, 0, ((size_t)nB * 6 + nG) * TBS * sizeof(double), s));
         std::vector<double> bv((size_t)nG * 3, 0.0);
         for (uint32_t ci2 = 0; ci2 < nB; ci2++)
             for (int sid = 0; sid < 6; sid++) {
@@ -645,6 +740,97 @@ extern "C" int nsem_upload_mesh(nsem_ctx* c, const nsem_mesh* m) {
         CUDA_TRY(c, c->bVec.upload(bv, s));
         CUDA_TRY(c, c->faceRec.upload(rec, s));
         CUDA_TRY(c, cudaStreamSynchronize(s));
+
+        // ---- v4: element records = the six face records + the element's trilinear map ----
+        // dg.cpp:176-325 places the nodes of a straight-edged hexahedron by trilinear interpolation of its corners, so
+        // J = dx/dxi is a closed form of 7 coefficient vectors.  They are recovered from the uploaded Jinv at the 8 corner
+        // nodes and the closed form is then checked against the uploaded Jinv and cV at EVERY node; a mesh that fails
+        // (curved edges, spherical shells) runs the stored-metric instantiation instead.
+        c->tri = false;
+        if (c->use_v4) {
+            std::vector<ElemRec> er(nB);
+            static const int rm9[9] = {0, 4, 8, 1, 5, 2, 3, 7, 6};      // AoS component -> row-major a*3+d
+            const char* mv = std::getenv("NSEM_METRICS");
+            const bool want_tri = !(mv && std::strcmp(mv, "stored") == 0);
+            const unsigned nth = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+            std::vector<int> bad(nth, 0);
+            auto work = [&](unsigned t) {
+                const uint32_t e0 = (uint32_t)((uint64_t)nB * t / nth), e1 = (uint32_t)((uint64_t)nB * (t + 1) / nth);
+                for (uint32_t e = e0; e < e1; e++) {
+                    ElemRec& R = er[e];
+                    for (int f = 0; f < 6; f++) R.face[f] = rec[(size_t)e * 6 + f];
+                    for (int q = 0; q < 7; q++) for (int a = 0; a < 3; a++) R.c[q][a] = 0.0;
+                    R.vol = 0.0;
+                    if (!want_tri || bad[t]) continue;
+                    auto loadM = [&](int node, double M[9]) {
+                        const double* src = m->Jinv + ((size_t)e * NP + node) * 9;
+                        for (int comp = 0; comp < 9; comp++) M[rm9[comp]] = src[comp];
+                    };
+                    double acc[7][3] = {};
+                    bool ok = true;
+                    for (int v = 0; v < 8 && ok; v++) {
+                        const int sx = (v & 1) ? 1 : -1, sy = (v & 2) ? 1 : -1, sz = (v & 4) ? 1 : -1;
+                        const int node = ((sx > 0) ? NX - 1 : 0) * NY * NZ + ((sy > 0) ? NY - 1 : 0) * NZ + ((sz > 0) ? NZ - 1 : 0);
+                        double M[9], Ci[9];
+                        loadM(node, M);
+                        for (int a = 0; a < 3; a++)
+                            for (int d = 0; d < 3; d++) {
+                                const int a1 = (a + 1) % 3, a2 = (a + 2) % 3, d1 = (d + 1) % 3, d2 = (d + 2) % 3;
+                                Ci[a * 3 + d] = M[a1 * 3 + d1] * M[a2 * 3 + d2] - M[a1 * 3 + d2] * M[a2 * 3 + d1];
+                            }
+                        const double det = M[0] * Ci[0] + M[1] * Ci[1] + M[2] * Ci[2];
+                        if (!(std::fabs(det) > 0)) { ok = false; break; }
+                        // J = (M^-1)^T = cofactor(M) / det(M)
+                        double J[9];
+                        for (int q = 0; q < 9; q++) J[q] = Ci[q] / det;
+                        for (int a = 0; a < 3; a++) {
+                            const double j0 = J[a * 3 + 0], j1 = J[a * 3 + 1], j2 = J[a * 3 + 2];
+                            acc[0][a] += j0 / 8;                                   // c100
+                            acc[1][a] += j1 / 8;                                   // c010
+                            acc[2][a] += j2 / 8;                                   // c001
+                            acc[3][a] += (sy * j0 + sx * j1) / 16;                 // c110
+                            acc[4][a] += (sz * j0 + sx * j2) / 16;                 // c101
+                            acc[5][a] += (sz * j1 + sy * j2) / 16;                 // c011
+                            acc[6][a] += (sy * sz * j0 + sx * sz * j1 + sx * sy * j2) / 24;   // c111
+                        }
+                    }
+                    if (!ok) { bad[t] = 1; continue; }
+                    for (int q = 0; q < 7; q++) for (int a = 0; a < 3; a++) R.c[q][a] = acc[q][a];
+                    R.vol = m->cV[(size_t)e * NP] / (((c->W[0][0] * c->W[1][0]) * c->W[2][0]) / 8);
+                    for (int node = 0; node < NP && ok; node++) {
+                        const int i = node / (NY * NZ), j = (node / NZ) % NY, k = node % NZ;
+                        const double x0 = c->X[0][i], x1 = c->X[1][j], x2 = c->X[2][k];
+                        double M[9], J[9];
+                        loadM(node, M);
+                        for (int a = 0; a < 3; a++) {
+                            J[a * 3 + 0] = R.c[0][a] + R.c[3][a] * x1 + R.c[4][a] * x2 + R.c[6][a] * (x1 * x2);
+                            J[a * 3 + 1] = R.c[1][a] + R.c[3][a] * x0 + R.c[5][a] * x2 + R.c[6][a] * (x0 * x2);
+                            J[a * 3 + 2] = R.c[2][a] + R.c[4][a] * x0 + R.c[5][a] * x1 + R.c[6][a] * (x0 * x1);
+                        }
+                        for (int a = 0; a < 3; a++)
+                            for (int b = 0; b < 3; b++) {
+                                const double v = J[a * 3] * M[b * 3] + J[a * 3 + 1] * M[b * 3 + 1] + J[a * 3 + 2] * M[b * 3 + 2];
+                                if (!(std::fabs(v - (a == b ? 1.0 : 0.0)) <= 1e-11)) ok = false;
+                            }
+                        const double cv = R.vol * (((c->W[0][i] * c->W[1][j]) * c->W[2][k]) / 8);
+                        const double want = m->cV[(size_t)e * NP + node];
+                        if (!(std::fabs(cv - want) <= 1e-13 * std::fabs(want))) ok = false;
+                    }
+                    if (!ok) bad[t] = 1;
+                }
+            };
+            {
+                std::vector<std::thread> th;
+                for (unsigned t = 1; t < nth; t++) th.emplace_back(work, t);
+                work(0);
+                for (auto& x : th) x.join();
+            }
+            bool all_ok = want_tri;
+            for (unsigned t = 0; t < nth; t++) if (bad[t]) all_ok = false;
+            c->tri = all_ok;
+            CUDA_TRY(c, c->elemRec.upload(er, s));
+            CUDA_TRY(c, cudaStreamSynchronize(s));
+        }
     }
     CUDA_TRY(c, c->ghostRef.upload(ghostRef, s));
     CUDA_TRY(c, c->bOwner.upload(bOwner, s));
@@ -683,8 +869,9 @@ extern "C" int nsem_upload_mesh(nsem_ctx* c, const nsem_mesh* m) {
         CUDA_TRY(c, c->cV.upload(h, s));
         CUDA_TRY(c, cudaStreamSynchronize(s));
         static const int rm[9] = {0, 4, 8, 1, 5, 2, 3, 7, 6};      // AoS component -> row-major a*3+d
-        std::vector<double> hj((size_t)nB * NPS);
+        std::vector<double> hj(c->tri ? 0 : (size_t)nB * NPS);
         for (int comp = 0; comp < 9; comp++) {
+            if (c->tri) { c->Jinv[rm[comp]].release(); continue; }      // metrics on the fly: Jinv is never streamed
             std::fill(hj.begin(), hj.end(), 0.0);
             for (uint32_t ci = 0; ci < nB; ci++)
                 for (int t = 0; t < NP; t++) hj[(size_t)ci * NPS + t] = m->Jinv[((size_t)ci * NP + t) * 9 + comp];
@@ -903,6 +1090,8 @@ static void fill_kparams(const nsem_ctx* c, KParams& P) {
     { const char* pr = std::getenv("NSEM_PROBE"); P.probe = pr ? std::atoi(pr) : 0; }
     std::memcpy(P.D, c->D, sizeof P.D);
     std::memcpy(P.W, c->W, sizeof P.W);
+    std::memcpy(P.X, c->X, sizeof P.X);
+    P.elemRec = c->elemRec.p;
     P.rho_old = c->rho[k].p; P.rho_new = c->rho[o].p;
     P.T_old = c->T[k].p; P.T_new = c->T[o].p;
     for (int d = 0; d < 3; d++) { P.U_old[d] = c->U[k][d].p; P.U_new[d] = c->U[o][d].p; P.gfield[d] = c->gfield[d].p; }
@@ -1012,7 +1201,7 @@ static int one_step(nsem_ctx* c, bool timed, double* acc) {
         if (halo_exchange(c, arr, 4, c->stream)) return 1;
     }
     if (timed) cudaEventRecord(c->ev[4], c->stream);
-    c->launches += 2 + (c->nG ? 2 : 0) + ((c->nG && c->use_v2 && !c->use_v3) ? 1 : 0);
+    c->launches += 2 + (c->nG ? 2 : 0) + ((c->nG && (c->use_v4 || (c->use_v2 && !c->use_v3))) ? 1 : 0);
     c->cur ^= 1;
     if (timed) {
         CUDA_TRY(c, cudaEventSynchronize(c->ev[4]));

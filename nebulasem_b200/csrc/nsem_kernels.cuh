@@ -41,6 +41,7 @@ constexpr uint32_t FM_OWNER = 8u;         // this element is the face's owner (g
 constexpr uint32_t FM_HALF = 16u;         // fI = 0.5 (interior / inter-rank); else fI = 0 (physical boundary)
 
 struct FaceRec;
+struct ElemRec;
 struct KParams {
     // sizes
     uint32_t nB;                 // real elements
@@ -53,6 +54,7 @@ struct KParams {
     // basis
     double D[3][MAXN * MAXN];    // D[d][s*n+i] = l_i'(x_s)
     double W[3][MAXN];
+    double X[3][MAXN];           // LGL nodes in [-1,1] (v4 kernels: metrics on the fly)
     // state in
     const double* rho_old;
     const double* U_old[3];
@@ -81,6 +83,7 @@ struct KParams {
     // face traces (v2): per face block 7 x FS doubles {normal fluxes of the 3 momentum eqs and theta, rho_new U.N,
     // rho_new theta, |U| + c} of the side that OWNS the block; block id = elem*6 + local face, ghost cells nB*6 + g
     double* traceA;
+    const struct ElemRec* elemRec;   // [nB] v4 kernels: the six face records and the trilinear map of the element
 };
 
 struct alignas(16) FaceRec {
@@ -90,6 +93,13 @@ struct alignas(16) FaceRec {
     uint64_t otherBlock;     // face-trace block of the other side (see KParams::traceA)
 };
 static_assert(sizeof(FaceRec) == 64, "FaceRec must be 64 bytes");
+// x(xi) = c000 + c100 xi + c010 eta + c001 zeta + c110 xi eta + c101 xi zeta + c011 eta zeta + c111 xi eta zeta, xi in [-1,1]^3
+struct alignas(16) ElemRec {
+    FaceRec face[6];
+    double c[7][3];          // c100, c010, c001, c110, c101, c011, c111
+    double vol;              // element volume: cV[node] = vol * w_i w_j w_k / 8 (dg.cpp:315-318)
+};
+static_assert(sizeof(ElemRec) == 560, "ElemRec must be 560 bytes");
 
 // ---------------------------------------------------------------------------------------------------
 // index helpers (dg.h:43-44 INDEX4; dg.cpp:372-404 face node maps)
@@ -624,7 +634,9 @@ __global__ void __launch_bounds__(256) bc_kernel(const __grid_constant__ BCParam
 // area vector N (identical on both sides): the side's central normal fluxes, its conserved q contracted with N,
 // and its |U| + c for lambdaMax (euler.cpp:186).
 // ---------------------------------------------------------------------------------------------------
-__host__ __device__ constexpr int trace_stride(int npf) { return pad_to(npf, 2); }
+// layout of a face-trace block: 7 components of NPF doubles each, dense; blocks padded to whole 128-byte lines
+__host__ __device__ constexpr int trace_cs(int npf) { return npf; }
+__host__ __device__ constexpr int trace_bs(int npf) { return pad_to(7 * npf, 16); }
 struct SideState {
     double rho_o, rho_n, u[3], th, pp, gU[9], gT[3];
 };
@@ -659,7 +671,7 @@ struct GhostTraceParams {
 template <int NX, int NY, int NZ>
 __global__ void __launch_bounds__(256) ghost_trace_kernel(const __grid_constant__ GhostTraceParams G) {
     using Dm = Dims<NX, NY, NZ>;
-    constexpr int NPF = Dm::NPF, GPS = Dm::GPS, FS = trace_stride(NPF);
+    constexpr int NPF = Dm::NPF, GPS = Dm::GPS, FS = trace_cs(NPF), TBS = trace_bs(NPF);
     const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (uint64_t)G.nG * NPF) return;
     const uint32_t g = (uint32_t)(gid / NPF);
@@ -687,7 +699,7 @@ __global__ void __launch_bounds__(256) ghost_trace_kernel(const __grid_constant_
     const double N[3] = {G.bVec[g * 3] * w, G.bVec[g * 3 + 1] * w, G.bVec[g * 3 + 2] * w};
     double out[7];
     side_trace(q, N, G.nu, G.iPr, G.gammaR, G.visc != 0, out);
-    double* dst = G.traceA + ((size_t)G.nB * 6 + g) * 7 * FS + n;
+    double* dst = G.traceA + ((size_t)G.nB * 6 + g) * TBS + n;
 #pragma unroll
     for (int c = 0; c < 7; c++) dst[c * FS] = out[c];
 }

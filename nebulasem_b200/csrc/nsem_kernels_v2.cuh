@@ -84,9 +84,9 @@ struct Cfg {
         int b = bs < br ? bs : br;
         return b < 1 ? 1 : (b > 4 ? 4 : b);
     }
-    static constexpr int FS = trace_stride(Dm::NPF);
+    static constexpr int FS = trace_cs(Dm::NPF), TBS = trace_bs(Dm::NPF);
     static constexpr size_t smemB(bool visc) {
-        return sizeof(double) * ((size_t)nin_b(visc) * EPB * NPS + 12 * EPB * NP + (size_t)EPB * NFT * 4 + (size_t)EPB * 6 * 7 * FS +
+        return sizeof(double) * ((size_t)nin_b(visc) * EPB * NPS + 12 * EPB * NP + (size_t)EPB * NFT * 4 + (size_t)EPB * 6 * TBS +
                                  3 * MAXN * MAXN) + 16;
     }
 };
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(Cfg<NX, NY, NZ, EPB>::NT, MINB) sweepA_v2(cons
         }
         if (P.probe == 3 && faceOn) {
             const uint32_t felem = P.sched ? P.sched[first + fe] : first + fe;
-            double* dst = P.traceA + ((size_t)felem * 6 + fs) * 7 * C::FS + ((fs < 2) ? fa * NY + fb : fa * NZ + fb);
+            double* dst = P.traceA + ((size_t)felem * 6 + fs) * C::TBS + ((fs < 2) ? fa * NY + fb : fa * NZ + fb);
             for (int c = 0; c < 7; c++) dst[c * C::FS] = acc;
         }
         return;
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(Cfg<NX, NY, NZ, EPB>::NT, MINB) sweepA_v2(cons
         constexpr int TS = C::FS;
         const uint32_t felem = P.sched ? P.sched[first + fe] : first + fe;
         const int n = (fs < 2) ? fa * NY + fb : fa * NZ + fb;
-        double* dst = P.traceA + ((size_t)felem * 6 + fs) * 7 * TS + n;
+        double* dst = P.traceA + ((size_t)felem * 6 + fs) * C::TBS + n;
 #pragma unroll
         for (int c = 0; c < 7; c++) dst[c * TS] = out[c];
     }
@@ -331,10 +331,10 @@ __global__ void __launch_bounds__(Cfg<NX, NY, NZ, EPB>::NT, MINB) sweepB_v2(cons
     constexpr int A_RO = 0, A_RN = 1, A_U = 2, A_T = 5, A_P = 6, A_GU = 7, A_GT = 16;
     constexpr int A_J = VISC ? 19 : 7, A_CV = A_J + 9, A_RR = A_CV + 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // bulk-copy destinations first: sIn is a multiple of 128 bytes, every trace block a multiple of 16 (FS is even)
+    // bulk-copy destinations first: sIn and every trace block are multiples of 128 bytes
     double* sIn = reinterpret_cast<double*>(smem_raw);             // [NIN][EPB][NPS]
     double* sT = sIn + (size_t)NIN * EPB * NPS;                    // [EPB][6][7][FS] neighbour-side face traces
-    double* sH = sT + (size_t)EPB * 6 * 7 * C::FS;                 // [12][EPB][NP]
+    double* sH = sT + (size_t)EPB * 6 * C::TBS;                    // [12][EPB][NP]
     double* sF = sH + 12 * EPB * NP;                               // [4][EPB][NFT]
     double* sD = sF + (size_t)EPB * NFT * 4;                       // [3][MAXN*MAXN]
     uint64_t* bar = reinterpret_cast<uint64_t*>(sD + 3 * MAXN * MAXN);
@@ -345,16 +345,16 @@ __global__ void __launch_bounds__(Cfg<NX, NY, NZ, EPB>::NT, MINB) sweepB_v2(cons
     const int nvalid = (int)min((uint32_t)EPB, P.nB - first);
     if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
     __syncthreads();
-    constexpr int FS = C::FS;
+    constexpr int FS = C::FS, TBS = C::TBS;
     if (tid < 32) {
-        if (tid == 0) mbar_expect_tx(bar, (uint32_t)(nvalid * (NIN * NPS + 6 * 7 * FS) * sizeof(double)));
+        if (tid == 0) mbar_expect_tx(bar, (uint32_t)(nvalid * (NIN * NPS + 6 * TBS) * sizeof(double)));
         __syncwarp();
         // neighbour traces: one bulk copy per face (the block id sits in the face record)
         for (int q = tid; q < nvalid * 6; q += 32) {
             const int e = q / 6, f = q % 6;
             const uint32_t elem = P.sched ? P.sched[first + e] : first + e;
             const uint64_t blk = P.faceRec[(size_t)elem * 6 + f].otherBlock;
-            bulk_g2s(sT + ((size_t)e * 6 + f) * 7 * FS, P.traceA + (size_t)blk * 7 * FS, 7 * FS * sizeof(double), bar);
+            bulk_g2s(sT + ((size_t)e * 6 + f) * TBS, P.traceA + (size_t)blk * TBS, TBS * sizeof(double), bar);
         }
         for (int q = tid; q < nvalid * NIN; q += 32) {
             const int e = q / NIN, arr = q % NIN;
@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(Cfg<NX, NY, NZ, EPB>::NT, MINB) sweepB_v2(cons
     if (P.probe) {
         // bandwidth probe (not a product path): touch every staged value and every gathered value, write the 4 outputs
         double acc = 0;
-        if (faceOn) for (int c = 0; c < 7; c++) acc += sT[((size_t)fe * 6 + fs) * 7 * FS + c * FS + ((fs < 2) ? fa * NY + fb : fa * NZ + fb)];
+        if (faceOn) for (int c = 0; c < 7; c++) acc += sT[((size_t)fe * 6 + fs) * TBS + c * FS + ((fs < 2) ? fa * NY + fb : fa * NZ + fb)];
         if (nodeOn) {
             for (int a = 0; a < NIN; a++) acc += IN(a, ne, nt);
             P.U_new[0][idx] = acc; P.U_new[1][idx] = acc; P.U_new[2][idx] = acc; P.T_new[idx] = acc;
@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(Cfg<NX, NY, NZ, EPB>::NT, MINB) sweepB_v2(cons
         side_trace(me, N, P.nu, P.iPr, P.gamma * P.R, VISC, mt);
         // the other side: its face trace, slot = the same (a,b) in ITS face numbering (ghost blocks use mine)
         const int oslot = (fid == FM_GHOST) ? ((fs < 2) ? fa * NY + fb : fa * NZ + fb) : ((fid < 2) ? fa * NY + fb : fa * NZ + fb);
-        const double* xt = sT + ((size_t)fe * 6 + fs) * 7 * FS + oslot;
+        const double* xt = sT + ((size_t)fe * 6 + fs) * TBS + oslot;
         const double wo = own ? al : 1 - al, wx = own ? 1 - al : al;
         const double lam = (mt[6] * wo + xt[6 * FS] * wx) / 2;
         const double sg = own ? 1.0 : -1.0;

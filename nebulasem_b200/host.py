@@ -17,7 +17,7 @@ HOST_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", 
 HOST_EXPORTS = ["nsemh_error", "nsemh_close", "nsemh_open_case", "nsemh_synthetic", "nsemh_synthetic_part", "nsemh_patch_faces",
                 "nsemh_peers", "nsemh_diagnostics", "nsemh_attach", "nsemh_step",
                 "nsemh_upload", "nsemh_download", "nsemh_write", "nsemh_run", "nsemh_sync", "nsemh_time",
-                "nsemh_launch_count", "nsemh_set_schedule", "nsemh_dims", "nsemh_params", "nsemh_f64", "nsemh_u32",
+                "nsemh_launch_count", "nsemh_kernel_info", "nsemh_set_schedule", "nsemh_dims", "nsemh_params", "nsemh_f64", "nsemh_u32",
                 "nsemh_state_ptr", "nsemh_totals"]
 _lib = None
 
@@ -54,6 +54,8 @@ def load_host_library() -> C.CDLL:
     lib.nsemh_diagnostics.argtypes = [vp, C.POINTER(C.c_double)]
     lib.nsemh_launch_count.argtypes = [vp]
     lib.nsemh_launch_count.restype = C.c_uint64
+    lib.nsemh_kernel_info.argtypes = [vp]
+    lib.nsemh_kernel_info.restype = C.c_char_p
     lib.nsemh_set_schedule.argtypes = [vp, C.POINTER(C.c_uint32), C.c_uint32]
     lib.nsemh_dims.argtypes = [vp, C.POINTER(C.c_uint64)]
     lib.nsemh_params.argtypes = [vp, C.POINTER(C.c_double)]
@@ -209,3 +211,7 @@ class Solver:
     @property
     def launch_count(self) -> int:
         return int(self.lib.nsemh_launch_count(self.h))
+
+    @property
+    def kernel_info(self) -> str:
+        return self.lib.nsemh_kernel_info(self.h).decode()

@@ -115,7 +115,7 @@ def test_isentropic_vortex_orders_2_to_7(tmp_cases, order):
 
 @pytest.mark.parametrize("order", [1, 2, 3, 5, 6, 7])
 def test_bubble3d_other_orders(tmp_cases, order):
-    """3-D orders other than 4 (v2 kernels with their per-order EPB/shared-memory configuration)."""
+    """3-D orders other than 4 (v4 kernels with their per-order thread/shared-memory configuration)."""
     nsteps = 6
     orc = make_oracle(tmp_cases, "bubble3d", nsteps, exact=False, n=2, order=order)
     ctx = device_from_oracle(orc)
@@ -130,7 +130,8 @@ def test_bubble3d_other_orders(tmp_cases, order):
 
 def test_kernel_generations_agree_and_conserve_mass_at_scale():
     """Size-independent properties on a mesh far beyond what the oracle can run (48^3 order 4 = 13.8 M nodes):
-    the three kernel generations (plain loads / bulk-async staged / warp-per-element) agree to rounding, the result does
+    the kernel generations (plain loads / bulk-async staged / warp-per-element / persistent pipelined with metrics on the
+    fly or stored) agree to rounding, the result does
     not depend on the element schedule, and mass is conserved to 1e-13 (the reference prints ~1e-15 losses)."""
     import subprocess
     import sys
@@ -149,22 +150,28 @@ s.download()
 rho, U, T, p = s.state()
 nb = s.gBCSfield
 np.save(sys.argv[1], np.concatenate([rho[:nb, None], U[:nb], T[:nb, None]], axis=1))
+print("KERNELS", s.kernel_info)
 print("MASS_LOSS", d["mass_loss"], "VOLUME_LOSS", d["volume_loss"])
 ''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     import tempfile
     outs = {}
     with tempfile.TemporaryDirectory() as td:
-        for tag, env in (("v1", {"NSEM_KERNELS": "v1"}), ("v2", {}), ("v3", {"NSEM_KERNELS": "v3"}), ("v2m", {"NSEM_SCHEDULE": "morton"})):
+        for tag, env in (("v1", {"NSEM_KERNELS": "v1"}), ("v2", {"NSEM_KERNELS": "v2"}), ("v3", {"NSEM_KERNELS": "v3"}),
+                         ("v2m", {"NSEM_KERNELS": "v2", "NSEM_SCHEDULE": "morton"}), ("v4", {}), ("v4m", {"NSEM_SCHEDULE": "morton"}),
+                         ("v4s", {"NSEM_METRICS": "stored"})):
             f = os.path.join(td, tag + ".npy")
             r = subprocess.run([sys.executable, "-c", code, f], env={**os.environ, **env}, capture_output=True, text=True, timeout=900)
             assert r.returncode == 0, r.stderr[-2000:]
+            want = {"v1": "v1", "v2": "v2", "v3": "v3", "v2m": "v2", "v4": "on the fly", "v4m": "on the fly", "v4s": "stored metrics"}[tag]
+            assert want in r.stdout.split("KERNELS")[1].splitlines()[0], (tag, r.stdout)
             loss = float(r.stdout.split("MASS_LOSS")[1].split()[0])
             assert abs(loss) <= 1e-13, (tag, loss)
             outs[tag] = np.load(f)
     ref = outs["v1"]
     assert np.isfinite(ref).all()
     assert np.array_equal(outs["v2"], outs["v2m"])            # the schedule never changes the result
-    for tag in ("v2", "v3"):
+    assert np.array_equal(outs["v4"], outs["v4m"])
+    for tag in ("v2", "v3", "v4", "v4s"):
         a = outs[tag]
         assert np.linalg.norm(a[:, 0] - ref[:, 0]) / np.linalg.norm(ref[:, 0]) <= 1e-13
         assert np.linalg.norm(a[:, 0] * (a[:, 4] + 300) - ref[:, 0] * (ref[:, 4] + 300)) / np.linalg.norm(ref[:, 0] * (ref[:, 4] + 300)) <= 1e-13
