@@ -1083,6 +1083,7 @@ static void fill_kparams(const nsem_ctx* c, KParams& P) {
     const nsem_params& q = c->prm;
     P.P0 = q.P0; P.T0 = q.T0; P.R = q.cp - q.cv; P.gamma = q.cp / q.cv; P.nu = q.viscosity; P.iPr = 1 / q.Pr; P.dt = q.dt;
     for (int d = 0; d < 3; d++) P.g[d] = q.gravity[d];
+    P.mrdt = -1.0 / q.dt; P.mdt = -q.dt;
     P.buoyancy = q.buoyancy;
     // mu = rho*viscosity when diffusion is on (euler.cpp:189-190); viscosity == 0 gives the same fluxes
     P.visc = (q.diffusion && q.viscosity != 0.0) ? 1 : 0;
@@ -1091,6 +1092,7 @@ static void fill_kparams(const nsem_ctx* c, KParams& P) {
     std::memcpy(P.D, c->D, sizeof P.D);
     std::memcpy(P.W, c->W, sizeof P.W);
     std::memcpy(P.X, c->X, sizeof P.X);
+    P.sms = c->numSMs;
     P.elemRec = c->elemRec.p;
     P.rho_old = c->rho[k].p; P.rho_new = c->rho[o].p;
     P.T_old = c->T[k].p; P.T_new = c->T[o].p;

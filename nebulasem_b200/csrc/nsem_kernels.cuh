@@ -49,7 +49,9 @@ struct KParams {
     uint64_t ghostBase;          // nB * NPS
     // physics
     double P0, T0, R, gamma, nu, iPr, dt, g[3];
+    double mrdt, mdt;            // -1/dt, -dt
     int buoyancy, visc, has_gfield;
+    int sms;                     // SM count (v4: rotates the heavy warp roles between the CTAs that share an SM)
     int probe;                   // diagnostics only (NSEM_PROBE): 1 = stream the inputs and skip the arithmetic, 2 = also skip the gathers
     // basis
     double D[3][MAXN * MAXN];    // D[d][s*n+i] = l_i'(x_s)
@@ -640,21 +642,57 @@ __host__ __device__ constexpr int trace_bs(int npf) { return pad_to(7 * npf, 16)
 struct SideState {
     double rho_o, rho_n, u[3], th, pp, gU[9], gT[3];
 };
+// |U| + c of one side (lambdaMax, euler.cpp:186)
+__device__ __forceinline__ double side_speed(const double u[3], double th, double gammaR) {
+    return sqrt(u[0] * u[0] + (u[1] * u[1] + u[2] * u[2])) + sqrt(gammaR * th);
+}
+// The five N-dependent trace components are linear in N: out[c] = sum_b K[c][b] N_b.  The coefficients depend on the node
+// only, so a node that lies on several faces evaluates them once.  Every producer of a trace (sweep A, the "my side" of
+// sweep B, the ghost-cell kernel) goes through these two functions, with the operation order pinned by explicit
+// fma/mul, so that the two sides of a face and the two sides of a partition boundary see bitwise identical values.
+struct TraceCoef {
+    double M[9];     // (rho_o u_c) u_b + p' delta_cb - mu gU[c][b]
+    double V3[3];    // theta rho_o u_b - mu/Pr gT[b]
+    double V4[3];    // rho_n u_b
+    double q5, S;    // rho_n theta, |U| + c
+};
+__device__ __forceinline__ void trace_coef(const SideState& q, double S, double nu, double iPr, bool visc, TraceCoef& K) {
+    const double mu = __dmul_rn(q.rho_o, nu);
+    const double mup = __dmul_rn(mu, iPr);
+    const double rth = __dmul_rn(q.th, q.rho_o);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const double ruc = __dmul_rn(q.rho_o, q.u[c]);
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+            double m = (c == b) ? __fma_rn(ruc, q.u[b], q.pp) : __dmul_rn(ruc, q.u[b]);
+            if (visc) m = __fma_rn(-mu, q.gU[c * 3 + b], m);
+            K.M[c * 3 + b] = m;
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+        double v = __dmul_rn(rth, q.u[b]);
+        if (visc) v = __fma_rn(-mup, q.gT[b], v);
+        K.V3[b] = v;
+        K.V4[b] = __dmul_rn(q.rho_n, q.u[b]);
+    }
+    K.q5 = __dmul_rn(q.rho_n, q.th);
+    K.S = S;
+}
+__device__ __forceinline__ void trace_apply(const TraceCoef& K, const double N[3], double out[7]) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) out[c] = __fma_rn(K.M[c * 3 + 2], N[2], __fma_rn(K.M[c * 3 + 1], N[1], __dmul_rn(K.M[c * 3], N[0])));
+    out[3] = __fma_rn(K.V3[2], N[2], __fma_rn(K.V3[1], N[1], __dmul_rn(K.V3[0], N[0])));
+    out[4] = __fma_rn(K.V4[2], N[2], __fma_rn(K.V4[1], N[1], __dmul_rn(K.V4[0], N[0])));
+    out[5] = K.q5;
+    out[6] = K.S;
+}
 __device__ __forceinline__ void side_trace(const SideState& q, const double N[3], double nu, double iPr, double gammaR, bool visc,
                                            double out[7]) {
-    const double un = q.u[0] * N[0] + q.u[1] * N[1] + q.u[2] * N[2];
-#pragma unroll
-    for (int c = 0; c < 3; c++) out[c] = (q.rho_o * q.u[c]) * un + q.pp * N[c];
-    out[3] = q.th * (q.rho_o * un);
-    if (visc) {
-        const double mu = q.rho_o * nu;
-#pragma unroll
-        for (int c = 0; c < 3; c++) out[c] -= mu * (q.gU[c * 3 + 0] * N[0] + q.gU[c * 3 + 1] * N[1] + q.gU[c * 3 + 2] * N[2]);
-        out[3] -= (mu * iPr) * (q.gT[0] * N[0] + q.gT[1] * N[1] + q.gT[2] * N[2]);
-    }
-    out[4] = q.rho_n * un;
-    out[5] = q.rho_n * q.th;
-    out[6] = sqrt(q.u[0] * q.u[0] + (q.u[1] * q.u[1] + q.u[2] * q.u[2])) + sqrt(gammaR * q.th);
+    TraceCoef K;
+    trace_coef(q, side_speed(q.u, q.th, gammaR), nu, iPr, visc, K);
+    trace_apply(K, N, out);
 }
 
 struct GhostTraceParams {

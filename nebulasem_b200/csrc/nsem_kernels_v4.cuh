@@ -137,9 +137,9 @@ struct CfgA {
     static constexpr int NP = Dm::NP, NPS = Dm::NPS, NPF = Dm::NPF, NFT = Tk::NFT;
     static constexpr int NT = pad_to(NP, 32);
     static constexpr int EXTRA = NFT > NT ? NFT - NT : 0;               // face tasks of the second pass
-    static constexpr int EX0 = NT - pad_to(EXTRA, 32);                  // first thread of the second pass
-    static constexpr bool ok = EXTRA <= NT && EX0 >= 0;                 // at most two face passes
-    static constexpr int ISSUER = (NT - 1 >= NP) ? NT - 1 : 0;          // an idle node lane when there is one
+    static constexpr int EXW = pad_to(EXTRA, 32);                       // threads (whole warps) of the second pass
+    static constexpr bool ok = EXTRA <= NT;                             // at most two face passes
+    static constexpr int NGRP = EXW > 0 ? NT / EXW : 1;                 // positions the second pass can rotate through
     static constexpr int TBS = trace_bs(NPF);
     static constexpr int NFTP = pad_to(NFT, 2);
     static constexpr int NIN = TRI ? 6 : 16;                            // rho, U(3), T, p_ref, [Jinv(9), cV]
@@ -148,8 +148,8 @@ struct CfgA {
     static constexpr int oIn = 0;
     static constexpr int oRec = oIn + 2 * NIN * NPS;
     static constexpr int oG = oRec + 3 * RECD;
-    static constexpr int oR = oG + 5 * NFTP;                            // [4][NP]: contravariant mass flux (3), theta
-    static constexpr int oF = oR + pad_to(4 * NP, 2);
+    static constexpr int oR = oG + 5 * NFTP;                            // [5][NP]: contravariant mass flux (3), theta, |U| + c
+    static constexpr int oF = oR + pad_to(5 * NP, 2);
     static constexpr int oTr = oF + pad_to(FS * NFT, 2);                // [6][TBS]
     static constexpr int oD = oTr + 6 * TBS;
     static constexpr int oBar = oD + 3 * MAXN * MAXN;
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
     double* const sIn = sm + C::oIn;         // [2][NIN][NPS]
     double* const sRec = sm + C::oRec;       // [3][RECD]
     double* const sG = sm + C::oG;           // [5][NFTP]  neighbour values of the face tasks (cp.async)
-    double* const sR = sm + C::oR;           // [4][NP]
+    double* const sR = sm + C::oR;           // [5][NP]
     double* const sF = sm + C::oF;           // [FS][NFT]
     double* const sTr = sm + C::oTr;         // [6][TBS]
     double* const sD = sm + C::oD;           // [3][MAXN*MAXN]
@@ -215,8 +215,14 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
             bulk_g2s(dst + C::A_CV * NPS, P.cV + off, B, bar);
         }
     };
+    // The warps that run the second face pass and the warp that hosts the issuing thread rotate with the CTA's
+    // residency round (CTAs sharing an SM differ by multiples of the SM count), so the heavier warps of the resident CTAs
+    // do not all sit on the same SM sub-partition.
+    const int round = (int)(blockIdx.x / (unsigned)P.sms);
+    const int ex0 = (C::EXW > 0) ? (round % C::NGRP) * C::EXW : 0;
+    const int issuer = (((round + 2) * 32) % NT) + 31;
     // second face task of thread t (or -1)
-    auto task2_of = [&](int t) -> int { return (C::EXTRA > 0 && t >= C::EX0 && t - C::EX0 < C::EXTRA) ? NT + (t - C::EX0) : -1; };
+    auto task2_of = [&](int t) -> int { return (C::EXTRA > 0 && t >= ex0 && t - ex0 < C::EXTRA) ? NT + (t - ex0) : -1; };
     // neighbour values of face task `task` for the element whose record sits in `slot`
     auto gather_task = [&](int task, int slot) {
         int fs, fa, fb;
@@ -245,7 +251,7 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
         mbar_fence_init();
     }
     __syncthreads();
-    if (tid == C::ISSUER) {
+    if (tid == issuer) {
         issue_rec(0, elem_of(seq));
         if (seq + stride < P.nB) issue_rec(1, elem_of(seq + stride));
         issue_arrays(0, elem_of(seq));
@@ -261,7 +267,7 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
         const uint32_t nxt = seq + stride, nxt2 = nxt + stride;
         const bool hasNext = nxt < P.nB;
         const int rs1 = (rs == 2) ? 0 : rs + 1, rs2 = (rs1 == 2) ? 0 : rs1 + 1;
-        if (tid == C::ISSUER) {
+        if (tid == issuer) {
             if (hasNext) issue_arrays(st ^ 1, elem_of(nxt));
             if (nxt2 < P.nB) issue_rec(rs2, elem_of(nxt2));
         }
@@ -291,6 +297,8 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
 #pragma unroll
             for (int d = 0; d < 3; d++) sR[d * NP + nt] = F0 * Jin[d] + F1 * Jin[3 + d] + F2 * Jin[6 + d];
             sR[3 * NP + nt] = th;
+            const double uu[3] = {u0, u1, u2};
+            sR[4 * NP + nt] = side_speed(uu, th, P.gamma * P.R);       // used by this node's face tasks and by its traces
         }
         __syncthreads();                                                                   // (1)
 
@@ -335,30 +343,28 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
             const uint32_t meta = fr->meta;
             const double xr = sG[0 * NFTP + task], xu0 = sG[1 * NFTP + task], xu1 = sG[2 * NFTP + task], xu2 = sG[3 * NFTP + task];
             const double xth = sG[4 * NFTP + task] + P.T0;
+            // written for "my side" / "other side": with fI in {0, 1/2} this is bitwise cds() = fI*owner + (1-fI)*neighbour
             const bool own = meta & FM_OWNER;
             const double al = (meta & FM_HALF) ? 0.5 : 0.0;
+            const double wo = own ? al : 1 - al, wx = own ? 1 - al : al;       // weight of my side / the other side
+            const double sg = own ? 1.0 : -1.0;                                // (q_n - q_o) = sg * (q_other - q_mine)
             const double N0 = fr->vec[0] * fw, N1 = fr->vec[1] * fw, N2 = fr->vec[2] * fw;      // fN[k] = gFN * w_a w_b / 4
             const double nN = fr->unit[0] * N0 + fr->unit[1] * N1 + fr->unit[2] * N2;           // unit(fN).fN
             const double mr = in[0 * NPS + fln], m0 = in[1 * NPS + fln], m1 = in[2 * NPS + fln], m2 = in[3 * NPS + fln];
             const double mth = in[4 * NPS + fln] + P.T0;
-            const double rho_o = own ? mr : xr, rho_n = own ? xr : mr;
-            const double uo0 = own ? m0 : xu0, uo1 = own ? m1 : xu1, uo2 = own ? m2 : xu2;
-            const double un0 = own ? xu0 : m0, un1 = own ? xu1 : m1, un2 = own ? xu2 : m2;
-            const double th_o = own ? mth : xth, th_n = own ? xth : mth;
-            const double mo = sqrt(uo0 * uo0 + (uo1 * uo1 + uo2 * uo2)), mn = sqrt(un0 * un0 + (un1 * un1 + un2 * un2));
-            const double co = sqrt(P.gamma * P.R * th_o), cn = sqrt(P.gamma * P.R * th_n);
-            const double lam = ((mo * al + mn * (1 - al)) + (co * al + cn * (1 - al))) / 2;
-            const double fo = rho_o * (uo0 * N0 + uo1 * N1 + uo2 * N2), fn = rho_n * (un0 * N0 + un1 * N1 + un2 * N2);
-            const double flux = (fo * al + fn * (1 - al)) - lam * (rho_n - rho_o) * nN;
+            // lambdaMax = cds(|U| + c) / 2: my side's |U| + c comes from the node pass, the other side's is evaluated here
+            const double xu[3] = {xu0, xu1, xu2};
+            const double lam = (sR[4 * NP + fln] * wo + side_speed(xu, xth, P.gamma * P.R) * wx) / 2;
+            const double fm = mr * (m0 * N0 + m1 * N1 + m2 * N2), fx = xr * (xu0 * N0 + xu1 * N1 + xu2 * N2);
+            const double flux = (fm * wo + fx * wx) - lam * (sg * (xr - mr)) * nN;
             double* out = &sF[task];
-            out[0] = own ? flux : -flux;
+            out[0] = sg * flux;
             if (VISC) {
-                const double sgn = own ? 1.0 : -1.0;
-                out[1 * NFT] = (uo0 * al + un0 * (1 - al)) - m0;
-                out[2 * NFT] = (uo1 * al + un1 * (1 - al)) - m1;
-                out[3 * NFT] = (uo2 * al + un2 * (1 - al)) - m2;
-                out[4 * NFT] = (th_o * al + th_n * (1 - al)) - mth;
-                out[5 * NFT] = sgn * N0; out[6 * NFT] = sgn * N1; out[7 * NFT] = sgn * N2;
+                out[1 * NFT] = (m0 * wo + xu0 * wx) - m0;
+                out[2 * NFT] = (m1 * wo + xu1 * wx) - m1;
+                out[3 * NFT] = (m2 * wo + xu2 * wx) - m2;
+                out[4 * NFT] = (mth * wo + xth * wx) - mth;
+                out[5 * NFT] = sg * N0; out[6 * NFT] = sg * N1; out[7 * NFT] = sg * N2;
             }
         };
         {
@@ -373,7 +379,7 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
             phase ^= 1u << (2 + rs1);
             issue_gathers(rs1);
         }
-        if (tid == C::ISSUER) bulk_wait_read0();     // the previous element's trace block has left sTr
+        if (tid == issuer) bulk_wait_read0();     // the previous element's trace block has left sTr
         __syncthreads();                                                                   // (2)
 
         if (nodeT) {
@@ -400,13 +406,15 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
                 }
             }
             const size_t idx = (size_t)elem * NPS + nt;
-            const double ap0 = (-1.0 / P.dt) * cV;
-            const double rho_new = (r_rho + rho * ap0) / ap0;
+            // (Su + rho*ap0) / ap0 with ap0 = (-1/dt) cV (addTemporal<1>, SolveTexplicit) as ONE reciprocal of cV
+            const double rcV = 1.0 / cV;
+            const double ap0 = P.mrdt * cV;
+            const double rho_new = (r_rho + rho * ap0) * (rcV * P.mdt);
             const double ppn = __dsub_rn(eos_pressure(P.P0, P.R, P.gamma, rho_new, th), in[C::A_PREF * NPS + nt]);
             P.rho_new[idx] = rho_new;
             P.p[idx] = ppn;
             if (VISC) {
-                const double rcV = 1.0 / cV;            // r / cV (field.h:3359) as one reciprocal and 12 products
+                // r / cV (field.h:3359) as 12 products with the reciprocal
 #pragma unroll
                 for (int c = 0; c < 9; c++) { gU[c] *= rcV; P.GU[c][idx] = gU[c]; }
 #pragma unroll
@@ -425,6 +433,8 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
 #pragma unroll
                     for (int c = 0; c < 3; c++) q.gT[c] = gT[c];
                 }
+                TraceCoef K;
+                trace_coef(q, sR[4 * NP + nt], P.nu, P.iPr, VISC, K);
                 const double wi = P.W[0][i], wj = P.W[1][j], wk = P.W[2][k];
 #pragma unroll
                 for (int ax = 0; ax < 3; ax++) {
@@ -437,7 +447,7 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
                     const FaceRec* fr = reinterpret_cast<const FaceRec*>(rec) + s;
                     const double Nv[3] = {fr->vec[0] * fw, fr->vec[1] * fw, fr->vec[2] * fw};
                     double out[7];
-                    side_trace(q, Nv, P.nu, P.iPr, P.gamma * P.R, VISC, out);
+                    trace_apply(K, Nv, out);
                     double* dst = sTr + s * TBS + slot;
 #pragma unroll
                     for (int c = 0; c < 7; c++) dst[c * TCS] = out[c];
@@ -446,7 +456,7 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
         }
         fence_async_smem();
         __syncthreads();                                                                   // (3)
-        if (tid == C::ISSUER) {
+        if (tid == issuer) {
             bulk_s2g(P.traceA + (size_t)elem * 6 * TBS, sTr, (uint32_t)(6 * TBS * sizeof(double)));
             bulk_commit();
         }
@@ -455,7 +465,7 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
         st ^= 1;
         rs = rs1;
     }
-    if (tid == C::ISSUER) bulk_wait0();
+    if (tid == issuer) bulk_wait0();
 }
 
 // ---------------------------------------------------------------------------------------------------
