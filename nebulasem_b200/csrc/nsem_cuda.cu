@@ -290,7 +290,7 @@ struct Launch {
         } else return cudaErrorInvalidValue;
     }
     // ---- v4: persistent, software-pipelined (cubic 3-D orders) ----
-    static constexpr bool has_v4 = (NX == NY && NY == NZ && NX > 1) && v4::Cfg<NX, NY, NZ, true, false>::smemB <= 227 * 1024 &&
+    static constexpr bool has_v4 = (NX == NY && NY == NZ && NX > 1) && v4::CfgB<NX, NY, NZ, true, false>::smem <= 227 * 1024 &&
                                    v4::CfgA<NX, NY, NZ, true, false>::smem <= 227 * 1024 && v4::CfgA<NX, NY, NZ, true, false>::ok;
     template <class K>
     static cudaError_t go4(K kernel, size_t smem, int nt, int minb, const KParams& P, int sms, cudaStream_t s) {
@@ -312,9 +312,9 @@ struct Launch {
     }
     template <bool VISC, bool TRI>
     static cudaError_t sweepB4t(const KParams& P, int sms, cudaStream_t s) {
-        using C4 = v4::Cfg<NX, NY, NZ, VISC, TRI>;
-        constexpr int MB = C4::minb(C4::smemB, NSEM_V4_REGS_B);
-        return go4(v4::sweepB_v4<NX, NY, NZ, VISC, TRI, MB>, C4::smemB, C4::NT, MB, P, sms, s);
+        using C4 = v4::CfgB<NX, NY, NZ, VISC, TRI>;
+        constexpr int MB = C4::minb(NSEM_V4_REGS_B);
+        return go4(v4::sweepB_v4<NX, NY, NZ, VISC, TRI, MB>, C4::smem, C4::NT, MB, P, sms, s);
     }
     static cudaError_t sweepA4(const KParams& P, bool tri, int sms, cudaStream_t s) {
         if constexpr (has_v4) {
