@@ -35,19 +35,28 @@ NP = (ORDER + 1) ** 3
 
 
 # ------------------------------------------------------------------------------------------------------
-def algorithmic_bytes_per_node(visc: bool = True) -> dict:
+def algorithmic_bytes_per_node(kernel_info: str, visc: bool = True) -> dict:
     """Bytes each sweep must move per LGL node for the data flow that is implemented.
-    Every node array is counted once per sweep that touches it; neighbour-trace re-reads are assumed to hit L2."""
+    Every node array is counted once per sweep that touches it (element stride padded 125 -> 128 doubles); the face
+    traces sweep A publishes and sweep B consumes are counted as DRAM traffic on both sides (they are written long
+    before they are read); the neighbour values sweep A gathers (5 per face node) are counted as L2 hits (0 B)."""
     n1 = ORDER + 1
-    face_tab = 6 * (4 + 4 + 24 + 24) / NP                     # faceOther, faceMeta, faceVec, faceUnit per element
-    a_read = 5 + 10 + 1                                       # rho,U(3),T ; Jinv(9),cV ; p_ref
-    a_write = 1 + 1 + (12 if visc else 0)                     # rho_new, p', gradU(9)+gradT(3)
-    b_read = 2 + 4 + 1 + (12 if visc else 0) + 10 + 1         # rho_old,rho_new ; U,T ; p' ; gradients ; Jinv,cV ; rho_ref
-    b_write = 4                                               # U_new(3), T_new
     pad = 128.0 / NP                                          # element stride padded from 125 to 128 doubles
-    A = 8 * (a_read + a_write) * pad + face_tab
-    B = 8 * (b_read + b_write) * pad + face_tab
-    return dict(A=A, B=B, total=A + B, survey_B_alg=8 * (62 + 24 / n1))
+    g = 12 if visc else 0                                     # gradU(9) + gradT(3)
+    if kernel_info.startswith("v4"):
+        metrics = 0 if "on the fly" in kernel_info else 10    # Jinv(9), cV streamed only for curved meshes
+        npf = n1 * n1
+        tbs = ((7 * npf + 15) // 16) * 16                     # doubles per face-trace block (trace_bs)
+        per_elem = 560 + 6 * tbs * 8                          # element record + six trace blocks
+        A = 8 * ((5 + 1 + metrics) + (2 + g)) * pad + per_elem / NP      # rho,U,T,p_ref [,Jinv,cV] -> rho_new,p',grads + traces
+        B = 8 * ((7 + g + 1 + metrics) + 4) * pad + per_elem / NP        # rho_o,rho_n,U,T,p',grads,rho_ref [,Jinv,cV] + traces -> U,T
+        flow = "v4: " + ("metrics on the fly" if metrics == 0 else "stored metrics") + ", dense face traces through DRAM"
+    else:
+        face_tab = 6 * (4 + 4 + 24 + 24) / NP                 # faceOther, faceMeta, faceVec, faceUnit per element
+        A = 8 * ((5 + 10 + 1) + (2 + g)) * pad + face_tab
+        B = 8 * ((2 + 4 + 1 + g + 10 + 1) + 4) * pad + face_tab
+        flow = "v1/v2: stored metrics, neighbour data counted as L2 hits"
+    return dict(A=A, B=B, total=A + B, survey_B_alg=8 * (62 + 24 / n1), flow=flow)
 
 
 class ClockSampler:
@@ -64,7 +73,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -254,28 +263,32 @@ def main():
     if not (np.isfinite(rho).all() and np.isfinite(U).all() and np.isfinite(T).all()):
         raise SystemExit("bench.py: state is not finite after the timed steps")
 
-    # roofline of the dominant kernel (sweep B) and of the pair
-    bpn = algorithmic_bytes_per_node(visc=True)
+    # roofline of the dominant kernel (the sweep with the larger share of the step) and of the pair
+    kinfo = s.kernel_info
+    bpn = algorithmic_bytes_per_node(kinfo, visc=True)
     peak, peak_src = measured_peak_gbs()
     tA, tB = pk[0] / pk_steps * 1e-3, pk[2] / pk_steps * 1e-3
     achieved_B = bpn["B"] * nodes_local / tB / 1e9
     achieved_A = bpn["A"] * nodes_local / tA / 1e9
+    dom = "A" if tA >= tB else "B"
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(tpath) and os.environ.get("NSEM_KERNELS", "v2") == "v2":
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)
-        if tj.get("cells") == args.n:
-            traffic = tj["sweepB_bytes_per_launch"]       # ncu dram__bytes_read+write of the dominant kernel, per launch
-    roofline = {"bound": "hbm", "kernel": "v2::sweepB_v2<5,5,5,1,true,3>", "achieved": achieved_B, "peak": peak, "unit": "GB/s",
-                "frac": achieved_B / peak, "traffic": traffic, "algorithmic_bytes_per_launch": bpn["B"] * nodes_local,
-                "peak_source": peak_src,
+        if tj.get("cells") == args.n and tj.get("kernels", "") == kinfo.split()[0]:
+            traffic = tj[f"sweep{dom}_bytes_per_launch"]   # ncu dram__bytes_read+write of the dominant kernel, per launch
+    kname = {"A": "v4::sweepA_v4<5,5,5,visc,tri>", "B": "v4::sweepB_v4<5,5,5,visc,tri>"}[dom] if kinfo.startswith("v4") else f"sweep{dom} ({kinfo})"
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved_A if dom == "A" else achieved_B, "peak": peak, "unit": "GB/s",
+                "frac": (achieved_A if dom == "A" else achieved_B) / peak, "traffic": traffic,
+                "algorithmic_bytes_per_launch": bpn[dom] * nodes_local, "peak_source": peak_src, "kernels": kinfo, "data_flow": bpn["flow"],
                 "bytes_per_node": {"sweepA": bpn["A"], "sweepB": bpn["B"], "step": bpn["total"], "survey_B_alg": bpn["survey_B_alg"]},
                 "sweepA": {"achieved": achieved_A, "frac": achieved_A / peak, "ms": tA * 1e3},
                 "sweepB": {"achieved": achieved_B, "frac": achieved_B / peak, "ms": tB * 1e3},
                 "bc_ms": [pk[1] / pk_steps, pk[3] / pk_steps],
                 "step": {"achieved": bpn["total"] * nodes / world / (ms / steps * 1e-3) / 1e9,
-                         "frac": bpn["total"] * nodes / world / (ms / steps * 1e-3) / 1e9 / peak, "note": "per GPU"}}
+                         "frac": bpn["total"] * nodes / world / (ms / steps * 1e-3) / 1e9 / peak,
+                         "frac_at_survey_B_alg": bpn["survey_B_alg"] * nodes / world / (ms / steps * 1e-3) / 1e9 / peak, "note": "per GPU"}}
 
     # e2e: host buffers in, host buffers out, every step
     e2e = None

@@ -1105,6 +1105,20 @@ static void fill_kparams(const nsem_ctx* c, KParams& P) {
     P.sched = c->has_sched ? c->sched.p : nullptr;
     P.faceRec = c->faceRec.p;
     P.traceA = c->traceA.p;
+    // stage-slot order of the v4 sweeps (CfgA / CfgB)
+    {
+        int q = 0;
+        P.srcA[q++] = P.rho_old; for (int d = 0; d < 3; d++) P.srcA[q++] = P.U_old[d];
+        P.srcA[q++] = P.T_old; P.srcA[q++] = P.p_ref;
+        for (int d = 0; d < 9; d++) P.srcA[q++] = P.Jinv[d];
+        P.srcA[q++] = P.cV;
+        q = 0;
+        P.srcB[q++] = P.rho_old; P.srcB[q++] = P.rho_new; for (int d = 0; d < 3; d++) P.srcB[q++] = P.U_old[d];
+        P.srcB[q++] = P.T_old; P.srcB[q++] = P.p;
+        if (P.visc) { for (int d = 0; d < 9; d++) P.srcB[q++] = P.GU[d]; for (int d = 0; d < 3; d++) P.srcB[q++] = P.GT[d]; }
+        for (int d = 0; d < 9; d++) P.srcB[q++] = P.Jinv[d];
+        P.srcB[q++] = P.cV;
+    }
 }
 static void fill_bcparams(const nsem_ctx* c, const KParams& P, BCParams& B, int phase) {
     std::memset(&B, 0, sizeof B);

@@ -86,7 +86,11 @@ struct KParams {
     // rho_new theta, |U| + c} of the side that OWNS the block; block id = elem*6 + local face, ghost cells nB*6 + g
     double* traceA;
     const struct ElemRec* elemRec;   // [nB] v4 kernels: the six face records and the trilinear map of the element
+    // v4 kernels: the arrays each sweep stages, in stage-slot order (so the issuing lanes index them instead of branching)
+    const double* srcA[16];
+    const double* srcB[32];
 };
+static_assert(sizeof(KParams) <= 4000, "KParams must fit the kernel parameter space");
 
 struct alignas(16) FaceRec {
     uint32_t other, meta;

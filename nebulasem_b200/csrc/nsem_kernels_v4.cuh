@@ -1,20 +1,24 @@
-// nsem_kernels_v4.cuh -- persistent, software-pipelined sm_100a sweeps (3-D orders).
+// nsem_kernels_v4.cuh -- persistent, software-pipelined sm_100a sweeps (cubic 3-D orders).
 //
 // Same mathematics as nsem_kernels.cuh (v1) / nsem_kernels_v2.cuh; what changes is how the SM is kept busy:
 //   * PERSISTENT CTAs (grid = SMs x resident CTAs) loop over elements; while element e is being computed the
 //     bulk-async copies (cp.async.bulk, SASS UBLKCP, completion on an mbarrier) of element e+1 are already in
-//     flight into the other half of a two-stage shared-memory ring, so no warp ever waits for HBM latency;
+//     flight into the other half of a two-stage shared-memory ring, so no warp waits for HBM latency;
 //   * the 560-byte element record (six face records + the element's trilinear map) runs two elements ahead in a
-//     three-slot ring, so the neighbour gathers of sweep A (cp.async 8-byte, LDGSTS) and the six neighbour face
-//     traces of sweep B can be requested a full element early;
+//     three-slot ring, so the neighbour values of sweep A (8-byte cp.async, LDGSTS) and the six neighbour face
+//     traces of sweep B (bulk copies) are requested a full element early;
+//   * ONE THREAD PER NODE and nothing else: NT = NP rounded up to whole warps, every warp does the same work.  A node
+//     that lies on a face evaluates the Rusanov flux there itself (its side from registers, the other side from the
+//     gathered values / the neighbour's trace), so there are no face tasks, no face-result round trip through
+//     shared memory and only two CTA barriers per element;
 //   * METRICS ON THE FLY (TRI = true): for straight-edged hexahedra (every non-curved mesh: dg.cpp:257-263
 //     interpolates the nodes trilinearly) Jinv*cV at a node is a closed form of the element's 7 trilinear
 //     coefficient vectors and its volume, so the 10 per-node metric arrays (Jinv, cV) are neither stored nor
 //     streamed; nsem_upload_mesh verifies the closed form against the uploaded Jinv/cV at every node and keeps
 //     the stored-metric instantiation (TRI = false) for curved meshes;
-//   * results leave through shared memory and bulk-async stores (full 128-byte lines, element padding included),
-//     the face traces as one dense [6][7][NPF] block per element;
-//   * the issuing thread lives in the warp that has no node work.
+//   * node results leave from registers with coalesced stores; the element's six face-trace blocks are collected in
+//     shared memory and leave as one dense bulk-async store (full 128-byte lines);
+//   * the bulk copies of a stage are issued by lane 31 of up to four warps, each owning every fourth copy.
 #pragma once
 #include "nsem_kernels_v2.cuh"
 
@@ -46,55 +50,6 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 constexpr int RECD = (int)(sizeof(ElemRec) / sizeof(double));      // 70 doubles
 static_assert(sizeof(ElemRec) % 16 == 0, "ElemRec must be a multiple of 16 bytes (bulk copy)");
-
-template <int NX, int NY, int NZ, bool VISC, bool TRI>
-struct Cfg {
-    using Dm = Dims<NX, NY, NZ>;
-    using Tk = Tasks<NX, NY, NZ>;
-    static constexpr int NP = Dm::NP, NPS = Dm::NPS, NPF = Dm::NPF, NFT = Tk::NFT;
-    static constexpr int WORK = NP > NFT ? NP : NFT;
-    static constexpr int NT = pad_to(WORK, 32);
-    static constexpr int ISSUER = (NT - 1 >= WORK) ? NT - 1 : 0;       // an idle lane of the last warp when there is one
-    static constexpr int TBS = trace_bs(NPF);                          // doubles per face-trace block
-    static constexpr int NFTP = pad_to(NFT, 2);
-    // ---- sweep A ----
-    // staged arrays: rho, U(3), T, p_ref, [Jinv(9), cV]
-    static constexpr int NIN_A = TRI ? 6 : 16;
-    static constexpr int A_PREF = 5, A_J = 6, A_CV = 15;
-    static constexpr int NOUT_A = VISC ? 14 : 2;                       // rho_new, p, [GU(9), GT(3)]
-    static constexpr int FSA = VISC ? 8 : 1;                           // doubles per face task of sweep A
-    static constexpr int SF_A = (FSA * NFT > 6 * TBS) ? FSA * NFT : 6 * TBS;
-    static constexpr int oInA = 0;
-    static constexpr int oRecA = oInA + 2 * NIN_A * NPS;
-    static constexpr int oGA = oRecA + 3 * RECD;
-    static constexpr int oOutA = oGA + 5 * NFTP;
-    static constexpr int oRA = oOutA + NOUT_A * NPS;
-    static constexpr int oFA = oRA + pad_to(3 * NP, 2);
-    static constexpr int oDA = oFA + pad_to(SF_A, 2);
-    static constexpr int oKA = oDA + 3 * MAXN * MAXN;
-    static constexpr int oBarA = oKA + 5 * NT;
-    static constexpr size_t smemA = sizeof(double) * (size_t)(oBarA + 6);
-    // ---- sweep B ----
-    // staged arrays: rho_old, rho_new, U(3), T, p, [GU(9), GT(3)], rho_ref, [Jinv(9), cV]
-    static constexpr int B_RO = 0, B_RN = 1, B_U = 2, B_T = 5, B_P = 6, B_GU = 7, B_GT = 16;
-    static constexpr int B_RR = VISC ? 19 : 7, B_J = B_RR + 1, B_CV = B_J + 9;
-    static constexpr int NIN_B = B_RR + 1 + (TRI ? 0 : 10);
-    static constexpr int STG_B = NIN_B * NPS + 6 * TBS;               // doubles per stage: arrays, then the six neighbour traces
-    static constexpr int oInB = 0;
-    static constexpr int oRecB = oInB + 2 * STG_B;
-    static constexpr int oHB = oRecB + 3 * RECD;                       // contravariant fluxes [12][NPS] (inviscid runs only; else in place over GU/GT)
-    static constexpr int oFB = oHB + (VISC ? 0 : 12 * NPS);
-    static constexpr int oDB = oFB + pad_to(4 * NFT, 2);
-    static constexpr int oBarB = oDB + 3 * MAXN * MAXN;
-    static constexpr size_t smemB = sizeof(double) * (size_t)(oBarB + 6);
-    static_assert(4 * NPS <= 6 * TBS, "sweep B stages its four outputs in the consumed trace block");
-    static constexpr int minb(size_t smem, int regs) {
-        int bs = (int)((227 * 1024) / (smem + 1024));
-        int br = 65536 / (NT * regs);
-        int b = bs < br ? bs : br;
-        return b < 1 ? 1 : (b > 6 ? 6 : b);
-    }
-};
 
 // Jin = Jinv * cV at reference coordinates (x0,x1,x2) of a straight-edged hexahedron:  x(xi) = sum c_abc xi^a eta^b zeta^c,
 // J[a][d] = d x_a / d xi_d,  Jinv[a][d] = d xi_d / d x_a = cofactor(J)[a][d] / det J  (dg.cpp:413-476 evaluates the
@@ -201,17 +156,9 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
         double* dst = sIn + (size_t)st * NIN * NPS;
         const size_t off = (size_t)elem * NPS;
         constexpr uint32_t B = NPS * sizeof(double);
-        const int mine = (NIN - iss + NISS - 1) / NISS;
+        const int mine = (NIN - iss + NISS - 1) / NISS;          // copies q = iss, iss + NISS, ... < NIN
         mbar_expect_tx(bar, (uint32_t)(mine * B));
-#define NSEM_ARR(q, ptr) if ((q) % NISS == iss) bulk_g2s(dst + (q) * NPS, (ptr) + off, B, bar);
-        NSEM_ARR(0, P.rho_old) NSEM_ARR(1, P.U_old[0]) NSEM_ARR(2, P.U_old[1]) NSEM_ARR(3, P.U_old[2]) NSEM_ARR(4, P.T_old)
-        NSEM_ARR(C::A_PREF, P.p_ref)
-        if (!TRI) {
-#pragma unroll
-            for (int q = 0; q < 9; q++) { NSEM_ARR(C::A_J + q, P.Jinv[q]) }
-            NSEM_ARR(C::A_CV, P.cV)
-        }
-#undef NSEM_ARR
+        for (int q = iss; q < NIN; q += NISS) bulk_g2s(dst + q * NPS, P.srcA[q] + off, B, bar);
     };
     // request the neighbour values of every face node of the element whose record sits in `slot` into table `buf`
     auto issue_gathers = [&](int slot, int buf) {
@@ -342,6 +289,17 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
             if (onAny) {
                 const double uu[3] = {u0, u1, u2};
                 S = side_speed(uu, th, P.gamma * P.R);                  // |U| + c of this node: lambdaMax here, trace below
+                // |U| + c of the other side of the (up to) three faces, evaluated together so that the square roots overlap
+                double Sx[3];
+#pragma unroll
+                for (int ax = 0; ax < 3; ax++) {
+                    const bool on = (ax == 0) ? onK : (ax == 1 ? onJ : onI);
+                    const int cx = (ax == 0) ? k : (ax == 1 ? j : i);
+                    const int s = 2 * ax + (cx != 0 ? 1 : 0);
+                    const int ti = on ? ((ax == 0) ? Tk::index(s, i, j) : (ax == 1 ? Tk::index(s, i, k) : Tk::index(s, j, k))) : 0;
+                    const double xu[3] = {gx[1 * NFTP + ti], gx[2 * NFTP + ti], gx[3 * NFTP + ti]};
+                    Sx[ax] = side_speed(xu, gx[4 * NFTP + ti] + P.T0, P.gamma * P.R);
+                }
 #pragma unroll
                 for (int ax = 0; ax < 3; ax++) {
                     const bool on = (ax == 0) ? onK : (ax == 1 ? onJ : onI);
@@ -361,8 +319,7 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
                     const double sg = own ? 1.0 : -1.0;                                // (q_n - q_o) = sg * (q_other - q_mine)
                     const double N0 = fr->vec[0] * fw, N1 = fr->vec[1] * fw, N2 = fr->vec[2] * fw;      // fN[k] = gFN * w_a w_b / 4
                     const double nN = fr->unit[0] * N0 + fr->unit[1] * N1 + fr->unit[2] * N2;           // unit(fN).fN
-                    const double xu[3] = {xu0, xu1, xu2};
-                    const double lam = (S * wo + side_speed(xu, xth, P.gamma * P.R) * wx) / 2;          // cds(|U| + c) / 2
+                    const double lam = (S * wo + Sx[ax] * wx) / 2;                                      // cds(|U| + c) / 2
                     const double fm = rho * (u0 * N0 + u1 * N1 + u2 * N2), fx = xr * (xu0 * N0 + xu1 * N1 + xu2 * N2);
                     const double flux = (fm * wo + fx * wx) - lam * (sg * (xr - rho)) * nN;
                     r_rho += sg * flux;
@@ -511,21 +468,7 @@ __global__ void __launch_bounds__((CfgB<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
         constexpr uint32_t B = NPS * sizeof(double);
         const int mine = (NIN - iss + NISS - 1) / NISS;          // copies q = iss, iss + NISS, ... < NIN
         mbar_expect_tx(bar, (uint32_t)(mine * B));
-#define NSEM_ARR(q, ptr) if ((q) % NISS == iss) bulk_g2s(dst + (q) * NPS, (ptr) + off, B, bar);
-        NSEM_ARR(A_RO, P.rho_old) NSEM_ARR(A_RN, P.rho_new) NSEM_ARR(A_U + 0, P.U_old[0]) NSEM_ARR(A_U + 1, P.U_old[1])
-        NSEM_ARR(A_U + 2, P.U_old[2]) NSEM_ARR(A_T, P.T_old) NSEM_ARR(A_P, P.p)
-        if (VISC) {
-#pragma unroll
-            for (int q = 0; q < 9; q++) { NSEM_ARR(A_GU + q, P.GU[q]) }
-#pragma unroll
-            for (int q = 0; q < 3; q++) { NSEM_ARR(A_GT + q, P.GT[q]) }
-        }
-        if (!TRI) {
-#pragma unroll
-            for (int q = 0; q < 9; q++) { NSEM_ARR(A_J + q, P.Jinv[q]) }
-            NSEM_ARR(A_CV, P.cV)
-        }
-#undef NSEM_ARR
+        for (int q = iss; q < NIN; q += NISS) bulk_g2s(dst + q * NPS, P.srcB[q] + off, B, bar);
     };
     // the six neighbour traces named by the record in `slot` (which has landed)
     auto issue_traces = [&](int slot) {
