@@ -168,7 +168,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     steps, warmup = args.steps, max(3, args.warmup)
     config = {"workload": f"rising thermal bubble 3-D synthetic hex mesh, order {ORDER}, {args.n}^3 = {args.n ** 3} elements per GPU "
-                          f"({args.n ** 3 * NP} LGL nodes), diffusion+buoyancy on, dt 0.00125, one forward-Euler stage per step",
+                          f"({args.n ** 3 * NP} LGL nodes), diffusion+buoyancy on, one forward-Euler stage per step",
               "elements_per_gpu": args.n ** 3, "order": ORDER, "l2": "state and metrics (tens of GB) far exceed the 126 MB L2; no flush needed"}
 
     if args.impl == "reference":
@@ -213,15 +213,21 @@ def main():
         dist.broadcast(uid, 0)
         uid_bytes = bytes(uid.cpu().tolist())
         config["parallelism"] = (f"{world} partitions ({args.decomp}), one per GPU, global mesh {args.n * pgrid[0]}x{args.n * pgrid[1]}x"
-                                 f"{args.n * pgrid[2]} elements, NCCL face-trace halo")
+                                 f"{args.n * pgrid[2]} elements on a {1000 * pgrid[0]}x{1000 * pgrid[1]}x{1000 * pgrid[2]} m domain (element size as at N=1), NCCL face-trace halo")
 
     t0 = time.time()
+    # The example's dt = 0.00125 belongs to its 6^3 (+2 AMR levels, ~42 m) mesh; one step is ONE forward-Euler stage, so the
+    # finer benchmark mesh keeps the example's acoustic Courant number instead of its dt (at dt = 0.00125 the 100^3 mesh
+    # diverges after ~30 steps, in the reference's scheme as in this one).  The throughput does not depend on dt.
+    dt = min(0.00125, 0.00125 * 24.0 / args.n)
+    config["dt"] = dt
     if world == 1:
-        s = host.Solver.synthetic("bubble3d", args.n, args.n, args.n, ORDER)
+        s = host.Solver.synthetic(f"bubble3d:1,1,1,{dt!r}", args.n, args.n, args.n, ORDER)
         s.attach(device)
     else:
-        s = host.Solver.synthetic_part("bubble3d", args.n * pgrid[0], args.n * pgrid[1], args.n * pgrid[2], ORDER, rank, world,
-                                       args.decomp, pgrid)
+        # weak scaling: the domain grows with the process grid, the element size (and the Courant number) stays
+        s = host.Solver.synthetic_part(f"bubble3d:{pgrid[0]},{pgrid[1]},{pgrid[2]},{dt!r}", args.n * pgrid[0], args.n * pgrid[1],
+                                       args.n * pgrid[2], ORDER, rank, world, args.decomp, pgrid)
         s.attach(device, rank, world, uid_bytes)
     t_setup = time.time() - t0
     nodes_local = s.gBCSfield

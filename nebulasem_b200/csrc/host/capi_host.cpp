@@ -1,5 +1,7 @@
 // capi_host.cpp -- C entry points of libnsem_host.so for the Python test/bench harness and other FFI users.
 // Wraps nsemh::EulerSolver (euler_app.cpp); every call returns 0 on success, the message is in nsemh_error().
+#include <stdexcept>
+#include <cstdio>
 #include <cmath>
 #include <cstring>
 
@@ -88,15 +90,25 @@ nsemh_solver* nsemh_synthetic_part(const char* kind_, int nx, int ny, int nz, in
             s.set_fields(mkfield(1, "uniform", {0}, all(pt, "NEUMANN")), mkfield(3, "uniform", {0, 0, 0}, all(pt, "SYMMETRY")),
                          mkfield(1, "cosine", {0, 0.5, 500, 50, 350, 250, 1000, 250}, all(pt, "NEUMANN")),
                          mkfield(1, "uniform", {0}, all(pt, "NEUMANN")));
-        } else if (kind == "bubble3d") {
+        } else if (kind.rfind("bubble3d", 0) == 0) {
+            // "bubble3d" = the 1000 m cube of examples/atmo/srtb-3d; "bubble3d:sx,sy,sz" stretches the domain (not the
+            // elements) by integer factors, so that a weak-scaling run keeps the element size -- and with it the acoustic
+            // Courant number of the explicit step -- of the one-partition case.
+            // An optional fourth number replaces the example's dt = 0.00125, which belongs to ITS 6^3 (+AMR) mesh: the step is
+            // one forward-Euler stage, so a finer mesh needs a proportionally smaller dt to stay at the example's Courant number.
+            double sc[3] = {1, 1, 1}, dt_case = 0.00125;
+            if (kind.size() > 8) {
+                const int got = (kind[8] == ':') ? std::sscanf(kind.c_str() + 9, "%lf,%lf,%lf,%lf", &sc[0], &sc[1], &sc[2], &dt_case) : 0;
+                if (got < 3 || !(dt_case > 0)) throw std::runtime_error("synthetic: expected bubble3d or bubble3d:sx,sy,sz[,dt]");
+            }
             const int n[3] = {nx, ny, nz};
-            const double lo[3] = {0, 0, 0}, hi[3] = {1000, 1000, 1000};
+            const double lo[3] = {0, 0, 0}, hi[3] = {1000 * sc[0], 1000 * sc[1], 1000 * sc[2]};
             s.nop[0] = s.nop[1] = s.nop[2] = order;
-            s.dt = 0.00125; s.gravity = Vec3{0, -9.80606, 0}; s.time_scheme = "AB1";
+            s.dt = dt_case; s.gravity = Vec3{0, -9.80606, 0}; s.time_scheme = "AB1";
             mesh(box_grid(n, lo, hi, {"sides", "sides", "bottom", "top", "sides", "sides"}));
             const std::vector<std::string> pt = {"top", "bottom", "sides"};
             s.set_fields(mkfield(1, "uniform", {0}, all(pt, "NEUMANN")), mkfield(3, "uniform", {0, 0, 0}, all(pt, "SYMMETRY")),
-                         mkfield(1, "cosine", {0, 0.5, 500, 350, 500, 250, 250, 250}, all(pt, "NEUMANN")),
+                         mkfield(1, "cosine", {0, 0.5, 500 * sc[0], 350, 500 * sc[2], 250, 250, 250}, all(pt, "NEUMANN")),
                          mkfield(1, "uniform", {0}, all(pt, "NEUMANN")));
         } else if (kind == "vortex") {
             const int n[3] = {nx, ny, 1};

@@ -30,6 +30,9 @@ def main():
     dist.broadcast(uid, 0)
     uid_bytes = bytes(uid.cpu().tolist())
     kind, n, order, nsteps = "bubble3d", (4, 4, 4), 3, 12
+    if os.environ.get("MP_CHECK_MESH"):        # e.g. "16,8,8,4,20": elements per direction, order, steps
+        v = [int(x) for x in os.environ["MP_CHECK_MESH"].split(",")]
+        n, order, nsteps = tuple(v[:3]), v[3], v[4]
     pxyz = {2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(world, (world, 1, 1))
     s = host.Solver.synthetic_part(kind, *n, order, rank, world, decomp, pxyz)
     s.attach(local, rank, world, uid_bytes)
