@@ -160,6 +160,9 @@ def main():
     ap.add_argument("--ref-cells", dest="ref_n", type=int, default=16, help="elements per side of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="bubble", choices=["bubble", "hill"],
+                    help="bubble = BASELINE configs[1] (default, the metric's configuration); hill = configs[3], flow over a cosine hill on a "
+                         "terrain-following mesh of the same element count (non-affine elements, DIRICHLET inlet)")
     ap.add_argument("--decomp", default="METIS", choices=["METIS", "XYZ", "CELLID"], help="domain decomposition for --gpus > 1")
     args = ap.parse_args()
 
@@ -220,8 +223,25 @@ def main():
     # finer benchmark mesh keeps the example's acoustic Courant number instead of its dt (at dt = 0.00125 the 100^3 mesh
     # diverges after ~30 steps, in the reference's scheme as in this one).  The throughput does not depend on dt.
     dt = min(0.00125, 0.00125 * 24.0 / args.n)
+    if args.workload == "hill":
+        # BASELINE configs[3]: the hills/hill block layout extruded to 3-D, 232 x 30 x 144 elements per GPU at --cells 100,
+        # extruded further in y for more GPUs; dt keeps the Courant number of the parity case (nz = 8, dt = 0.001)
+        f = args.n / 100.0
+        hn = (max(4, round(232 * f)), max(2, round(30 * f)) * world, max(4, round(144 * f)))
+        dt = min(0.001, 0.001 * 8.0 / hn[2])
+        config["workload"] = (f"flow over a cosine hill, terrain-following 3-D hex mesh {hn[0]}x{hn[1]}x{hn[2]} = {hn[0] * hn[1] * hn[2]} elements "
+                              f"({hn[0] * hn[1] * hn[2] // world} per GPU), order {ORDER}, U = (10,0,0) DIRICHLET inlet, diffusion+buoyancy on, "
+                              f"one forward-Euler stage per step")
+        config["elements_per_gpu"] = hn[0] * hn[1] * hn[2] // world
     config["dt"] = dt
-    if world == 1:
+    if args.workload == "hill":
+        if world == 1:
+            s = host.Solver.synthetic(f"hill3d:{dt!r}", hn[0], hn[1], hn[2], ORDER)
+            s.attach(device)
+        else:
+            s = host.Solver.synthetic_part(f"hill3d:{dt!r}", hn[0], hn[1], hn[2], ORDER, rank, world, args.decomp, (1, world, 1))
+            s.attach(device, rank, world, uid_bytes)
+    elif world == 1:
         s = host.Solver.synthetic(f"bubble3d:1,1,1,{dt!r}", args.n, args.n, args.n, ORDER)
         s.attach(device)
     else:

@@ -122,12 +122,16 @@ nsemh_solver* nsemh_synthetic_part(const char* kind_, int nx, int ny, int nz, in
             for (auto& q : pr) { BCond b; b.patch = q[0]; b.type = "CYCLIC"; b.neighbor = q[1]; cyc.push_back(b); }
             s.set_fields(mkfield(1, "uniform", {0}, cyc), mkfield(3, "uniform", {1, 1, 0}, cyc), mkfield(1, "uniform", {0}, cyc),
                          mkfield(1, "uniform", {0}, cyc));
-        } else if (kind == "hill3d") {
+        } else if (kind.rfind("hill3d", 0) == 0) {
+            // "hill3d" or "hill3d:dt" (a finer mesh needs a smaller forward-Euler step, see bubble3d)
+            double dt_case = 0.001;
+            if (kind.size() > 6 && (kind[6] != ':' || std::sscanf(kind.c_str() + 7, "%lf", &dt_case) != 1 || !(dt_case > 0)))
+                throw std::runtime_error("synthetic: expected hill3d or hill3d:dt");
             const int n[3] = {nx, ny, nz};
             static HillArg ha{200.0, 1000.0, 400.0, 1400.0};
             const double lo[3] = {0, 0, 0}, hi[3] = {3400, 100.0 * ny, ha.Lz};
             s.nop[0] = s.nop[1] = s.nop[2] = order;
-            s.dt = 0.001; s.gravity = Vec3{0, 0, -9.80606};
+            s.dt = dt_case; s.gravity = Vec3{0, 0, -9.80606};
             mesh(box_grid(n, lo, hi, {"inlet", "outlet", "sides", "sides", "WALLS", "top"}, hill_map, &ha));
             const std::vector<std::string> pt = {"inlet", "outlet", "WALLS", "top", "sides"};
             std::vector<BCond> ub = all(pt, "SYMMETRY");
