@@ -22,6 +22,13 @@
 #pragma once
 #include "nsem_kernels_v2.cuh"
 
+// differentiation-matrix entry: from the shared-memory copy, or (-DNSEM_D_CONST) straight from the kernel-parameter constant bank
+#ifdef NSEM_D_CONST
+#define NSEM_DM(d, idx) P.D[d][idx]
+#else
+#define NSEM_DM(d, idx) sD[(d) * MAXN * MAXN + (idx)]
+#endif
+
 namespace nsem {
 namespace v4 {
 
@@ -255,11 +262,11 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
             {
                 double acc = 0;
 #pragma unroll
-                for (int ii = 0; ii < NX; ii++) acc += sR[0 * NP + ii * NY * NZ + j * NZ + k] * sD[0 * MAXN * MAXN + ii * NX + i];
+                for (int ii = 0; ii < NX; ii++) acc += sR[0 * NP + ii * NY * NZ + j * NZ + k] * NSEM_DM(0, ii * NX + i);
 #pragma unroll
-                for (int jj = 0; jj < NY; jj++) acc += sR[1 * NP + i * NY * NZ + jj * NZ + k] * sD[1 * MAXN * MAXN + jj * NY + j];
+                for (int jj = 0; jj < NY; jj++) acc += sR[1 * NP + i * NY * NZ + jj * NZ + k] * NSEM_DM(1, jj * NY + j);
 #pragma unroll
-                for (int kk = 0; kk < NZ; kk++) acc += sR[2 * NP + i * NY * NZ + j * NZ + kk] * sD[2 * MAXN * MAXN + kk * NZ + k];
+                for (int kk = 0; kk < NZ; kk++) acc += sR[2 * NP + i * NY * NZ + j * NZ + kk] * NSEM_DM(2, kk * NZ + k);
                 r_rho = -acc;
             }
             if (VISC) {
@@ -268,11 +275,11 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
                     const double* q = (f < 3) ? in + (1 + f) * NPS : sR + 3 * NP;
                     double d0 = 0, d1 = 0, d2 = 0;
 #pragma unroll
-                    for (int m = 0; m < NX; m++) d0 += sD[0 * MAXN * MAXN + i * NX + m] * q[m * NY * NZ + j * NZ + k];
+                    for (int m = 0; m < NX; m++) d0 += NSEM_DM(0, i * NX + m) * q[m * NY * NZ + j * NZ + k];
 #pragma unroll
-                    for (int m = 0; m < NY; m++) d1 += sD[1 * MAXN * MAXN + j * NY + m] * q[i * NY * NZ + m * NZ + k];
+                    for (int m = 0; m < NY; m++) d1 += NSEM_DM(1, j * NY + m) * q[i * NY * NZ + m * NZ + k];
 #pragma unroll
-                    for (int m = 0; m < NZ; m++) d2 += sD[2 * MAXN * MAXN + k * NZ + m] * q[i * NY * NZ + j * NZ + m];
+                    for (int m = 0; m < NZ; m++) d2 += NSEM_DM(2, k * NZ + m) * q[i * NY * NZ + j * NZ + m];
 #pragma unroll
                     for (int a = 0; a < 3; a++) {
                         const double v = Jin[a * 3 + 0] * d0 + Jin[a * 3 + 1] * d1 + Jin[a * 3 + 2] * d2;
@@ -619,11 +626,11 @@ __global__ void __launch_bounds__((CfgB<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
             for (int a = 0; a < 4; a++) {
                 double acc = 0;
 #pragma unroll
-                for (int ii = 0; ii < NX; ii++) acc += sH[(a * 3 + 0) * NPS + ii * NY * NZ + j * NZ + k] * sD[0 * MAXN * MAXN + ii * NX + i];
+                for (int ii = 0; ii < NX; ii++) acc += sH[(a * 3 + 0) * NPS + ii * NY * NZ + j * NZ + k] * NSEM_DM(0, ii * NX + i);
 #pragma unroll
-                for (int jj = 0; jj < NY; jj++) acc += sH[(a * 3 + 1) * NPS + i * NY * NZ + jj * NZ + k] * sD[1 * MAXN * MAXN + jj * NY + j];
+                for (int jj = 0; jj < NY; jj++) acc += sH[(a * 3 + 1) * NPS + i * NY * NZ + jj * NZ + k] * NSEM_DM(1, jj * NY + j);
 #pragma unroll
-                for (int kk = 0; kk < NZ; kk++) acc += sH[(a * 3 + 2) * NPS + i * NY * NZ + j * NZ + kk] * sD[2 * MAXN * MAXN + kk * NZ + k];
+                for (int kk = 0; kk < NZ; kk++) acc += sH[(a * 3 + 2) * NPS + i * NY * NZ + j * NZ + kk] * NSEM_DM(2, kk * NZ + k);
                 r[a] = rf[a] - acc;
             }
             const double ap0 = P.mrdt * cV;
