@@ -100,9 +100,42 @@ def lagrange_basis_derivative(xgl, xs):
     return d
 
 
-def _matinv(A):
-    # Gauss-Jordan in the reference (tensor.cpp:170-215); any accurate inverse agrees to rounding
-    return np.linalg.inv(A)
+def _matinv(A_):
+    """Gauss-Jordan elimination exactly as the reference does it (tensor.cpp:170-215): one bubble pass on column 0,
+    elimination without further pivoting, final row scaling."""
+    N = A_.shape[0]
+    A = np.array(A_, dtype=float).copy()
+    X = np.eye(N)
+    for i in range(N - 1, 0, -1):
+        if A[i - 1, 0] < A[i, 0]:
+            A[[i, i - 1]] = A[[i - 1, i]]
+            X[[i, i - 1]] = X[[i - 1, i]]
+    for i in range(N):
+        for j in range(N):
+            if j != i:
+                temp = A[j, i] / A[i, i]
+                for k in range(N):
+                    A[j, k] -= A[i, k] * temp
+                    X[j, k] -= X[i, k] * temp
+    for i in range(N):
+        temp = A[i, i]
+        for j in range(N):
+            A[i, j] = A[i, j] / temp
+            X[i, j] = X[i, j] / temp
+    return X
+
+
+def _matmul(A, B):
+    """matmul of tensor.cpp:218-228: sequential sums."""
+    N = A.shape[0]
+    X = np.zeros((N, N))
+    for i in range(N):
+        for j in range(N):
+            acc = 0.0
+            for k in range(N):
+                acc += A[i, k] * B[k, j]
+            X[i, j] = acc
+    return X
 
 
 class Basis:
@@ -137,13 +170,22 @@ class Basis:
                 xre = [-0.5 + xe / 2, 0.5 + xe / 2]
             psire = [lagrange_basis(x, xre[c]).reshape(ngl, ngle) for c in range(2)]
             psie = lagrange_basis(x, xe).reshape(ngl, ngle)
-            Mcc = np.einsum("q,jq,kq->jk", we / 2, psie, psie)
+            # mass matrices with the (ngl+1)-point rule, accumulated in the reference's loop order (dg.cpp:558-573)
+            Mcc = np.zeros((ngl, ngl))
+            Msc = [np.zeros((ngl, ngl)), np.zeros((ngl, ngl))]
+            Mga = [np.zeros((ngl, ngl)), np.zeros((ngl, ngl))]
+            for j in range(ngl):
+                for k in range(ngl):
+                    for q in range(ngle):
+                        Mcc[j, k] += (we[q] / 2) * psie[j, q] * psie[k, q]
+                        for c in range(2):
+                            vs = (we[q] / 2) * psie[j, q] * psire[c][k, q]
+                            Msc[c][j, k] += vs
+                            Mga[c][k, j] += vs
             iMcc = _matinv(Mcc)
             for c in range(2):
-                Msc = np.einsum("q,jq,kq->jk", we / 2, psie, psire[c])
-                Mga = Msc.T
-                self.psiRef[d * 2 + c] = (iMcc @ Msc).T.reshape(-1).copy()
-                self.psiCor[d * 2 + c] = (iMcc @ Mga).T.reshape(-1).copy()
+                self.psiRef[d * 2 + c] = _matmul(iMcc, Msc[c]).T.reshape(-1).copy()
+                self.psiCor[d * 2 + c] = _matmul(iMcc, Mga[c]).T.reshape(-1).copy()
 
     def D(self, d):
         """D[s, i] = l_i'(x_s) as an (n,n) matrix."""

@@ -167,6 +167,7 @@ class EulerOracle:
         self.Jin = geo.Jinv33 * geo.cV[: self.gB, None, None]
         self.D = [b.D(0), b.D(1), b.D(2)]
         self._build_face_tables()
+        self._build_mortar_tables()
         self.bcs: dict[str, list[BCSpec]] = {"rho": [], "U": [], "T": [], "p": [], "p_ref": [], "rho_ref": [], "g": []}
         self.step_count = 0
 
@@ -205,6 +206,110 @@ class EulerOracle:
         self.fill_ghost = np.concatenate(gh) if gh else np.zeros(0, dtype=np.int64)
         self.fill_owner = np.concatenate(ow) if ow else np.zeros(0, dtype=np.int64)
 
+
+    # ---- mortar (non-conforming, 2:1) faces: scatter/gather_non_conforming (field.h:2019-2248) -------------------
+    def _build_mortar_tables(self):
+        """Per mortar sub-face (gFMC >= 1): the coarse cell's face nodes, the half chosen along each face axis and the
+        tensor-product weights psiRef (coarse -> fine trace, field.h:2198-2208) / psiCor (fine -> coarse flux, :2082-2092)."""
+        g, t, b = self.g, self.g.topo, self.g.basis
+        NPX, NPY, NPZ = self.shape
+        NP, NPF = self.NP, self.NPF
+        FMC = np.asarray(t.FMC)
+        self.mortar_faces = np.nonzero(FMC >= 1)[0]
+        self.has_mortar = len(self.mortar_faces) > 0
+        if not self.has_mortar:
+            return
+        pos = np.full(len(g.FO), -1, dtype=np.int64)            # (face, slot) -> position in the used-slot arrays
+        pos[self.kv] = np.arange(len(self.kv))
+        n = [NPX, NPY, NPZ]
+
+        def I4(c, i, j, k):
+            return c * NP + i * NPY * NPZ + j * NPZ + k
+
+        def dot3(a, bb):
+            return (a[0] * bb[0] + a[1] * bb[1]) + a[2] * bb[2]
+
+        M = []
+        for fi in self.mortar_faces:
+            fm = FMC[fi]
+            co = t.FOC[fi] if fm == 1 else t.FNC[fi]
+            cn = t.FNC[fi] if fm == 1 else t.FOC[fi]
+            cell = t.cells[cn]
+            ids = t.faceID[cn]
+            fid = next(ids[j] for j in range(len(cell)) if cell[j] == fi)
+            cco = np.asarray(t.FC[fi], dtype=float)
+            ccn = np.zeros(3)
+            nch = 0
+            for j in range(len(cell)):
+                if ids[j] == fid:
+                    ccn = ccn + np.asarray(t.FC[cell[j]], dtype=float)
+                    nch += 1
+            ccn = ccn / float(nch)
+            if fid in (0, 1):
+                d1, d2 = 0, 1
+                kf = 0 if fid == 0 else NPZ - 1
+                node = lambda a, c2: I4(cn, a, c2, kf)
+                v0, v1, v2 = g.cC[I4(cn, 0, 0, kf)], g.cC[I4(cn, NPX - 1, 0, kf)], g.cC[I4(cn, 0, NPY - 1, kf)]
+            elif fid in (2, 3):
+                d1, d2 = 0, 2
+                jf = 0 if fid == 2 else NPY - 1
+                node = lambda a, c2: I4(cn, a, jf, c2)
+                v0, v1, v2 = g.cC[I4(cn, 0, jf, 0)], g.cC[I4(cn, NPX - 1, jf, 0)], g.cC[I4(cn, 0, jf, NPZ - 1)]
+            else:
+                d1, d2 = 1, 2
+                i_f = 0 if fid == 4 else NPX - 1
+                node = lambda a, c2: I4(cn, i_f, a, c2)
+                v0, v1, v2 = g.cC[I4(cn, i_f, 0, 0)], g.cC[I4(cn, i_f, NPY - 1, 0)], g.cC[I4(cn, i_f, 0, NPZ - 1)]
+            off1 = 0 if dot3(ccn - v0, v1 - v0) >= dot3(cco - v0, v1 - v0) else 1
+            off2 = 0 if dot3(ccn - v0, v2 - v0) >= dot3(cco - v0, v2 - v0) else 1
+            n1, n2 = n[d1], n[d2]
+            slots = np.array([fi * NPF + a * n2 + c2 for a in range(n1) for c2 in range(n2)])      # face slots (a,b), b fastest
+            nodes = np.array([node(a, c2) for a in range(n1) for c2 in range(n2)])                   # coarse face nodes, same order
+            R1, R2 = b.psiRef[d1 * 2 + off1], b.psiRef[d2 * 2 + off2]
+            C1, C2 = b.psiCor[d1 * 2 + off1], b.psiCor[d2 * 2 + off2]
+            ns = n1 * n2
+            # scatter: slot (ao,bo) <- sum over coarse (an,bn):  fx = R1[an*n1+ao], fy = R2[bn*n2+bo]
+            sfx = np.array([[R1[an * n1 + ao] for an in range(n1) for bn in range(n2)] for ao in range(n1) for bo in range(n2)])
+            sfy = np.array([[R2[bn * n2 + bo] for an in range(n1) for bn in range(n2)] for ao in range(n1) for bo in range(n2)])
+            # gather: slot (an,bn) <- sum over fine (ao,bo):  fx = C1[ao*n1+an], fy = C2[bo*n2+bn]
+            gfx = np.array([[C1[ao * n1 + an] for ao in range(n1) for bo in range(n2)] for an in range(n1) for bn in range(n2)])
+            gfy = np.array([[C2[bo * n2 + bn] for ao in range(n1) for bo in range(n2)] for an in range(n1) for bn in range(n2)])
+            assert (pos[slots] >= 0).all()
+            M.append(dict(pos=pos[slots], nodes=nodes, sfx=sfx, sfy=sfy, gfx=gfx, gfy=gfy, to_N=(fm == 1), ns=ns))
+        self.mortar = M
+
+    def scatter(self, c):
+        """(fFO, fFN) on the used slots: fFO = c[FO], fFN = c[FN]; on a mortar sub-face the coarse side's trace is the
+        projection of the coarse cell's face values onto the sub-face (scatter_non_conforming, field.h:2135-2248)."""
+        fO, fN = c[self.FOv], c[self.FNv]
+        if self.has_mortar:
+            fO, fN = fO.copy(), fN.copy()
+            tail = (1,) * (c.ndim - 1)
+            for m in self.mortar:
+                ns = m["ns"]
+                acc = np.zeros((ns,) + c.shape[1:])
+                cv = c[m["nodes"]]                                    # coarse face values, term order (an,bn)
+                for q in range(ns):
+                    acc = acc + (cv[q] * m["sfx"][:, q].reshape((ns,) + tail)) * m["sfy"][:, q].reshape((ns,) + tail)
+                (fN if m["to_N"] else fO)[m["pos"]] = acc
+        return fO, fN
+
+    def gather(self, fF):
+        """(fFO, fFN) copies of a facet field on the used slots; on a mortar sub-face the coarse side receives the
+        projection of the sub-face values onto the coarse face nodes (gather_non_conforming, field.h:2019-2132)."""
+        if not self.has_mortar:
+            return fF, fF
+        fO, fN = fF.copy(), fF.copy()
+        tail = (1,) * (fF.ndim - 1)
+        for m in self.mortar:
+            ns = m["ns"]
+            acc = np.zeros((ns,) + fF.shape[1:])
+            fv = fF[m["pos"]]                                         # sub-face values, term order (ao,bo)
+            for q in range(ns):
+                acc = acc + (fv[q] * m["gfx"][:, q].reshape((ns,) + tail)) * m["gfy"][:, q].reshape((ns,) + tail)
+            (fN if m["to_N"] else fO)[m["pos"]] = acc
+        return fO, fN
+
     # ---- face operators ----------------------------------------------------------------------
     def face_full(self, vals_valid, comps_shape=()):
         """expand values on used slots to the full (nF*NPF) facet array"""
@@ -214,12 +319,14 @@ class EulerOracle:
 
     def cds(self, c):
         fi = self.fIv.reshape((-1,) + (1,) * (c.ndim - 1))
-        return c[self.FOv] * fi + c[self.FNv] * (1 - fi)
+        fO, fN = self.scatter(c)
+        return fO * fi + fN * (1 - fi)
 
     def rusanov(self, F, q, lam):
         """fF = cds(F) - mul(unit(fN), lam*(q_N - q_O))   (field.h:2928-2943)"""
         fF = self.cds(F)
-        dq = q[self.FNv] - q[self.FOv]
+        qO, qN = self.scatter(q)
+        dq = qN - qO
         if q.ndim == 1:
             return fF - self.unit_fN * (lam * dq)[:, None]
         ldq = lam[:, None] * dq
@@ -349,14 +456,14 @@ class EulerOracle:
     def divf(self, F, q, lam):
         """divf<weak>(F,false,&flux,&q,&lambdaMax) under RUSANOV (field.h:3417-3478)."""
         fF = self.rusanov(F, q, lam)                               # on used slots
-        if F.ndim == 2:
-            flux = vdot(fF, self.fNv)
-            r = np.zeros(self.gA)
-        else:
-            flux = tdotv(fF, self.fNv)
-            r = np.zeros((self.gA, 3))
-        full = self.face_full(flux, flux.shape[1:])
-        self._accumulate_faces(r, full, full)
+        fFO, fFN = self.gather(fF)                                 # div_flux<weak>: gather_non_conforming first (field.h:3091)
+        dotN = vdot if F.ndim == 2 else tdotv
+        r = np.zeros(self.gA) if F.ndim == 2 else np.zeros((self.gA, 3))
+        flux_o = dotN(fFO, self.fNv)
+        flux_n = flux_o if fFN is fFO else dotN(fFN, self.fNv)
+        full_o = self.face_full(flux_o, flux_o.shape[1:])
+        full_n = full_o if flux_n is flux_o else self.face_full(flux_n, flux_n.shape[1:])
+        self._accumulate_faces(r, full_o, full_n)
         self.div_volume(r, F)
         self.fill_bcs(r)
         return r
@@ -364,8 +471,9 @@ class EulerOracle:
     def gradf(self, P, field_name):
         """gradf<strong>(P, per-unit-volume=true) + fillBCs(r, P.fIndex) (field.h:3328-3362, 2745-2769)."""
         fF = self.cds(P)
-        dO = fF - P[self.FOv]
-        dN = fF - P[self.FNv]
+        fFO, fFN = self.gather(fF)                                 # grad_flux<strong>: gather_non_conforming first (field.h:3056)
+        dO = fFO - P[self.FOv]
+        dN = fFN - P[self.FNv]
         if P.ndim == 1:
             co = self.fNv * dO[:, None]
             cn = self.fNv * dN[:, None]
