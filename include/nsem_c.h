@@ -60,7 +60,13 @@ typedef struct {
     const uint32_t* face_id;      /* [same] gFaceID flattened: local face id 0..5 (mesh.cpp:161-446) */
     const uint32_t* face_owner;   /* [n_faces] gFOC */
     const uint32_t* face_neigh;   /* [n_faces] gFNC */
-    const uint32_t* face_mortar;  /* [n_faces] gFMC (0 = conforming) */
+    const uint32_t* face_mortar;  /* [n_faces] gFMC: 0 = conforming, 1 / 2 = non-conforming (2:1) sub-facet whose owner /
+                                     neighbour cell is the fine one (mesh.cpp:431-444, mesh.h:89-92) */
+    /* Only read when face_mortar has non-zero entries (scatter/gather_non_conforming, field.h:2019-2248): */
+    const double* cC;             /* [n_cells_all*NP*3] node coordinates (dg.cpp:176-325): picks the half of the coarse face */
+    const double* face_center;    /* [n_faces*3] gFC (mesh.cpp:476-502) */
+    const double* psi_ref[6];     /* DG::psiRef[d*2+half][in*n+io], coarse -> fine trace (dg.cpp:576-590) */
+    const double* psi_cor[6];     /* DG::psiCor[d*2+half][io*n+in], fine -> coarse flux */
 } nsem_mesh;
 
 /* One boundary patch's condition for one field (BCondition<T>, field.h:144-173). */

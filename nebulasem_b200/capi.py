@@ -25,7 +25,9 @@ class NsemMesh(C.Structure):
     _fields_ = [("n_cells_real", C.c_uint32), ("n_cells_all", C.c_uint32), ("n_faces", C.c_uint32),
                 ("cV", _dp), ("Jinv", _dp), ("fN", _dp), ("fI", _dp), ("face_normal", _dp),
                 ("FO", _up), ("FN", _up), ("face_begin", _up), ("face_end", _up), ("all_faces", _up),
-                ("face_id", _up), ("face_owner", _up), ("face_neigh", _up), ("face_mortar", _up)]
+                ("face_id", _up), ("face_owner", _up), ("face_neigh", _up), ("face_mortar", _up),
+                # read only on non-conforming meshes (face_mortar != 0 somewhere)
+                ("cC", _dp), ("face_center", _dp), ("psi_ref", _dp * 6), ("psi_cor", _dp * 6)]
 
 
 class NsemBC(C.Structure):
@@ -154,7 +156,9 @@ class Context:
         self._ck(self.lib.nsem_set_basis(self.h, dp, wp))
 
     def upload_mesh(self, *, n_cells_real, n_cells_all, n_faces, cV, Jinv, fN, fI, face_normal, FO, FN, face_begin,
-                    face_end, all_faces, face_id, face_owner, face_neigh, face_mortar):
+                    face_end, all_faces, face_id, face_owner, face_neigh, face_mortar, cC=None, face_center=None,
+                    psi_ref=None, psi_cor=None):
+        """cC, face_center, psi_ref[6], psi_cor[6] are only needed when face_mortar marks non-conforming faces."""
         arrs = dict(cV=_f64(cV), Jinv=_f64(Jinv), fN=_f64(fN), fI=_f64(fI), face_normal=_f64(face_normal), FO=_u32(FO),
                     FN=_u32(FN), face_begin=_u32(face_begin), face_end=_u32(face_end), all_faces=_u32(all_faces),
                     face_id=_u32(face_id), face_owner=_u32(face_owner), face_neigh=_u32(face_neigh),
@@ -163,6 +167,16 @@ class Context:
         m.n_cells_real, m.n_cells_all, m.n_faces = int(n_cells_real), int(n_cells_all), int(n_faces)
         for k, a in arrs.items():
             setattr(m, k, _pd(a) if a.dtype == np.float64 else _pu(a))
+        keep = []
+        if cC is not None and face_center is not None:
+            keep += [_f64(cC), _f64(face_center)]
+            m.cC, m.face_center = _pd(keep[0]), _pd(keep[1])
+        if psi_ref is not None and psi_cor is not None:
+            pr = [_f64(x) for x in psi_ref]
+            pc = [_f64(x) for x in psi_cor]
+            keep += pr + pc
+            m.psi_ref = (_dp * 6)(*[_pd(x) for x in pr])
+            m.psi_cor = (_dp * 6)(*[_pd(x) for x in pc])
         self.n_ref_nodes = int(n_cells_all) * self.NP
         self._ck(self.lib.nsem_upload_mesh(self.h, C.byref(m)))
 

@@ -204,7 +204,9 @@ const double* nsemh_f64(nsemh_solver* h, const char* name, uint64_t* n) {
     const std::vector<double>* v = nullptr;
     if (k == "cC") v = &s.geo.cC; else if (k == "cV") v = &s.geo.cV; else if (k == "Jinv") v = &s.geo.Jinv;
     else if (k == "fN") v = &s.geo.fN; else if (k == "fC") v = &s.geo.fC; else if (k == "fI") v = &s.geo.fI;
-    else if (k == "faceNormal") v = &s.geo.faceNormal;
+    else if (k == "faceNormal") v = &s.geo.faceNormal; else if (k == "faceCenter") v = &s.geo.faceCenter;
+    else if (k.size() == 7 && k.compare(0, 6, "psiRef") == 0 && k[6] >= '0' && k[6] <= '5') v = &s.geo.psiRef[k[6] - '0'];
+    else if (k.size() == 7 && k.compare(0, 6, "psiCor") == 0 && k[6] >= '0' && k[6] <= '5') v = &s.geo.psiCor[k[6] - '0'];
     else if (k == "rho") v = &s.rho; else if (k == "U") v = &s.U; else if (k == "T") v = &s.T; else if (k == "p") v = &s.p;
     else if (k == "rho_ref") v = &s.rho_ref; else if (k == "p_ref") v = &s.p_ref; else if (k == "g") v = &s.gvec;
     if (!v) { *n = 0; return nullptr; }

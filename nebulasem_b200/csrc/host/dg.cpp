@@ -78,6 +78,44 @@ void lagrange_basis_derivative(int N, const double* xgl, int Ns, const double* x
         }
 }
 
+// matinv / matmul of tensor.cpp:170-243: Gauss-Jordan with one bubble pass on column 0 and no further pivoting, final
+// row scaling; sequential inner products
+static void matinv(int N, std::vector<double> A, std::vector<double>& X) {
+    X.assign((size_t)N * N, 0.0);
+    for (int i = 0; i < N; i++) X[(size_t)i * N + i] = 1.0;
+    for (int i = N - 1; i > 0; i--)
+        if (A[(size_t)(i - 1) * N] < A[(size_t)i * N])
+            for (int k = 0; k < N; k++) {
+                std::swap(A[(size_t)i * N + k], A[(size_t)(i - 1) * N + k]);
+                std::swap(X[(size_t)i * N + k], X[(size_t)(i - 1) * N + k]);
+            }
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < N; j++)
+            if (j != i) {
+                const double temp = A[(size_t)j * N + i] / A[(size_t)i * N + i];
+                for (int k = 0; k < N; k++) {
+                    A[(size_t)j * N + k] -= A[(size_t)i * N + k] * temp;
+                    X[(size_t)j * N + k] -= X[(size_t)i * N + k] * temp;
+                }
+            }
+    for (int i = 0; i < N; i++) {
+        const double temp = A[(size_t)i * N + i];
+        for (int j = 0; j < N; j++) {
+            A[(size_t)i * N + j] = A[(size_t)i * N + j] / temp;
+            X[(size_t)i * N + j] = X[(size_t)i * N + j] / temp;
+        }
+    }
+}
+static void matmul(int N, const std::vector<double>& A, const std::vector<double>& B, std::vector<double>& X) {
+    X.assign((size_t)N * N, 0.0);
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < N; j++) {
+            double acc = 0.0;
+            for (int k = 0; k < N; k++) acc += A[(size_t)i * N + k] * B[(size_t)k * N + j];
+            X[(size_t)i * N + j] = acc;
+        }
+}
+
 Basis::Basis(const int nop[3]) {
     NPX = nop[0] + 1; NPY = nop[1] + 1; NPZ = nop[2] + 1;
     NP = NPX * NPY * NPZ;
@@ -90,6 +128,43 @@ Basis::Basis(const int nop[3]) {
         legendre_gauss_lobatto(m, xgl[d].data(), wgl[d].data());
         lagrange_basis(m, xgl[d].data(), m, xgl[d].data(), psi[d].data());
         lagrange_basis_derivative(m, xgl[d].data(), m, xgl[d].data(), dpsi[d].data());
+        // ---- 2:1 mortar projections (dg.cpp:497-590): L2 projection between a coarse face and its two halves, mass
+        // matrices integrated with the (m+1)-point LGL rule ----
+        const int me = m + 1;
+        std::vector<double> xe(me), we(me), xre[2], psie((size_t)m * me), psire[2];
+        legendre_gauss_lobatto(me, xe.data(), we.data());
+        for (int c = 0; c < 2; c++) {
+            xre[c].assign(me, 0.0);
+            if (m != 1)
+                for (int q = 0; q < me; q++) xre[c][q] = (c == 0 ? -0.5 : 0.5) + xe[q] / 2;
+            psire[c].resize((size_t)m * me);
+            lagrange_basis(m, xgl[d].data(), me, xre[c].data(), psire[c].data());
+        }
+        lagrange_basis(m, xgl[d].data(), me, xe.data(), psie.data());
+        std::vector<double> Mcc((size_t)m * m, 0.0), Msc[2], Mga[2], iMcc, P;
+        for (int c = 0; c < 2; c++) { Msc[c].assign((size_t)m * m, 0.0); Mga[c].assign((size_t)m * m, 0.0); }
+        for (int j = 0; j < m; j++)
+            for (int k = 0; k < m; k++)
+                for (int q = 0; q < me; q++) {
+                    Mcc[(size_t)j * m + k] += (we[q] / 2) * psie[(size_t)j * me + q] * psie[(size_t)k * me + q];
+                    for (int c = 0; c < 2; c++) {
+                        const double vs = (we[q] / 2) * psie[(size_t)j * me + q] * psire[c][(size_t)k * me + q];
+                        Msc[c][(size_t)j * m + k] += vs;
+                        Mga[c][(size_t)k * m + j] += vs;
+                    }
+                }
+        matinv(m, Mcc, iMcc);
+        for (int c = 0; c < 2; c++) {
+            auto transposed = [&](const std::vector<double>& A) {
+                std::vector<double> T((size_t)m * m);
+                for (int i = 0; i < m; i++) for (int j = 0; j < m; j++) T[(size_t)j * m + i] = A[(size_t)i * m + j];
+                return T;
+            };
+            matmul(m, iMcc, Msc[c], P);
+            psiRef[d * 2 + c] = transposed(P);
+            matmul(m, iMcc, Mga[c], P);
+            psiCor[d * 2 + c] = transposed(P);
+        }
     }
 }
 
@@ -154,7 +229,13 @@ void Geometry::build(const MeshTopo& t, const Basis& b) {
     for (u32 i = 0; i < nCells; i++) { faceBegin[i] = t.cellStart[i]; faceEnd[i] = t.cellStart[i + 1]; }
     faceOwner = t.FOC; faceNeigh = t.FNC; faceMortar = t.FMC;
     faceNormal.resize((size_t)nFacets * 3);
-    for (u32 f = 0; f < nFacets; f++) for (int d = 0; d < 3; d++) faceNormal[(size_t)f * 3 + d] = t.FN[f][d];
+    faceCenter.resize((size_t)nFacets * 3);
+    for (u32 f = 0; f < nFacets; f++)
+        for (int d = 0; d < 3; d++) {
+            faceNormal[(size_t)f * 3 + d] = t.FN[f][d];
+            faceCenter[(size_t)f * 3 + d] = t.FC[f][d];
+        }
+    for (int q = 0; q < 6; q++) { psiRef[q] = b.psiRef[q]; psiCor[q] = b.psiCor[q]; }
 
     cC.assign(gALL * 3, 0.0); cV.assign(gALL, 0.0);
     for (u32 c = 0; c < nCells; c++)
@@ -184,14 +265,28 @@ void Geometry::build(const MeshTopo& t, const Basis& b) {
         const u32 ci = (u32)cs;
         const u32 c0 = t.cellStart[ci], c1 = t.cellStart[ci + 1];
         const u32 id0 = t.cellFaceID[c0], id1 = id0 ^ 1u;
-        const u32 *f1 = nullptr, *f2 = nullptr;
-        for (u32 q = c0; q < c1; q++) {
-            if (t.cellFaceID[q] == id0 && !f1) f1 = &t.facetVerts[t.facetStart[t.cellFaces[q]]];
-            else if (t.cellFaceID[q] == id1 && !f2) f2 = &t.facetVerts[t.facetStart[t.cellFaces[q]]];
-        }
-        if (!f1 || !f2) continue;   // cannot happen after fix_hex_cells
         u32 vpi[8], vidx[8];
-        t.hex_corners(f1, f2, vpi);
+        // one quadrilateral on each of the two sides that define the corners: the short route
+        int n0 = 0, n1 = 0;
+        bool simple = true;
+        for (u32 q = c0; q < c1; q++) {
+            const bool quad = (t.facetStart[t.cellFaces[q] + 1] - t.facetStart[t.cellFaces[q]] == 4);
+            if (t.cellFaceID[q] == id0) { n0++; simple = simple && quad; }
+            else if (t.cellFaceID[q] == id1) { n1++; simple = simple && quad; }
+        }
+        simple = simple && n0 == 1 && n1 == 1;
+        if (simple) {
+            const u32 *f1 = nullptr, *f2 = nullptr;
+            for (u32 q = c0; q < c1; q++) {
+                if (t.cellFaceID[q] == id0 && !f1) f1 = &t.facetVerts[t.facetStart[t.cellFaces[q]]];
+                else if (t.cellFaceID[q] == id1 && !f2) f2 = &t.facetVerts[t.facetStart[t.cellFaces[q]]];
+            }
+            if (!f1 || !f2) continue;   // cannot happen after fix_hex_cells
+            t.hex_corners(f1, f2, vpi);
+        } else {
+            // non-conforming cell: the sub-facets of the two sides are merged first (dg.cpp:190-215)
+            t.hex_corners_poly(t.merged_side(ci, id0), t.merged_side(ci, id1), vpi);
+        }
         static const int ord2[8] = {0, 1, 5, 4, 3, 2, 6, 7}, ord4[8] = {0, 3, 7, 4, 1, 2, 6, 5};
         for (int q = 0; q < 8; q++) vidx[id0 == 2 ? ord2[q] : (id0 == 4 ? ord4[q] : q)] = vpi[q];
         V3 vp[8];
@@ -326,6 +421,8 @@ nsem_mesh Geometry::as_c() const {
     m.FO = FO.data(); m.FN = FN.data(); m.face_begin = faceBegin.data(); m.face_end = faceEnd.data();
     m.all_faces = allFaces.data(); m.face_id = faceID.data(); m.face_owner = faceOwner.data();
     m.face_neigh = faceNeigh.data(); m.face_mortar = faceMortar.data();
+    m.cC = cC.data(); m.face_center = faceCenter.data();
+    for (int q = 0; q < 6; q++) { m.psi_ref[q] = psiRef[q].data(); m.psi_cor[q] = psiCor[q].data(); }
     return m;
 }
 

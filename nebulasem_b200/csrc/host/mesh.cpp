@@ -9,7 +9,11 @@
 // The element's local axes -- and therefore the node order of every field file -- depend on the facet vertex
 // order the reference leaves after visiting the cells in index order, so the cells are visited in the same
 // order here and each visit re-orients the six facets of the cell exactly as the reference does.
-// Non-conforming (AMR) cells (more than six faces, facets with hanging vertices) are rejected.
+// Non-conforming (2:1 AMR) cells -- more than six faces, several coplanar sub-facets per side -- take the general
+// route of fixHexCells: coplanar facets are grouped and merged into one polygon per side (coplanarFaces /
+// mergeFacets / mergeFacetsGroup, mesh.cpp:791-1020), the side ids and corner order come from the merged polygons,
+// every sub-facet is re-oriented against its side's polygon, and facets that share a local id are flagged in gFMC
+// (1: the owner cell is the fine one, 2: the neighbour is; mesh.cpp:431-444).
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -75,19 +79,278 @@ void MeshTopo::hex_corners(const u32* f1, const u32* f2, u32 out[8]) const {
     for (int i = 0; i < 4; i++) out[4 + i] = f2[best[i]];
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// predicates and polygon merging of the non-conforming route (mesh.cpp:791-1020)
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+constexpr double EQ_EPS = 1e-7;      // Constants::EqualEpsilon (tensor.h:462)
+inline bool equal_eps(double p, double q) {                          // tensor.h:469-474
+    const double d = std::fabs(p - q);
+    return d <= EQ_EPS || d <= EQ_EPS * std::fabs(p) || d <= EQ_EPS * std::fabs(q);
+}
+inline double dot_lr(const Vec3& a, const Vec3& b) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
+inline bool contains(const std::vector<u32>& f, u32 v) { return std::find(f.begin(), f.end(), v) != f.end(); }
+inline void rotate_left(std::vector<u32>& f, long k) {
+    const long n = (long)f.size();
+    if (n == 0) return;
+    k = ((k % n) + n) % n;
+    std::rotate(f.begin(), f.begin() + k, f.end());
+}
+}  // namespace
+
+struct PolyOps {
+    const std::vector<Vec3>& V;
+    bool point_in_line(const Vec3& v, const Vec3& v1, const Vec3& v2) const {
+        const Vec3 p = sub(v, v1), q = sub(v, v2);
+        if (!equal_eps(p[1] * q[2] - p[2] * q[1], 0.0)) return false;
+        if (!equal_eps(p[2] * q[0] - p[0] * q[2], 0.0)) return false;
+        if (!equal_eps(p[0] * q[1] - p[1] * q[0], 0.0)) return false;
+        const double e = dot_lr(sub(v, v2), sub(v1, v2));
+        if (e > 0) {
+            const double e1 = dot_lr(sub(v1, v2), sub(v1, v2));
+            if (e < e1) return true;
+        }
+        return false;
+    }
+    bool unit_normal(const std::vector<u32>& f, Vec3& n) const {
+        const Vec3 &v1 = V[f[0]], &v2 = V[f[1]];
+        for (size_t j = 1; j < f.size(); j++) {
+            const Vec3& v3 = V[f[f.size() - j]];
+            if (!point_in_line(v2, v1, v3)) {
+                const Vec3 c = cross(sub(v2, v1), sub(v3, v1));
+                n = divs(c, std::sqrt(dot_lr(c, c)));
+                return true;
+            }
+        }
+        return false;
+    }
+    bool coplanar(const std::vector<u32>& f1, const std::vector<u32>& f2) const {
+        Vec3 n1, n2;
+        if (!unit_normal(f1, n1) || !unit_normal(f2, n2)) throw Error("degenerate facet (all vertices on one line)");
+        const Vec3 c = cross(n1, n2);
+        if (equal_eps(dot_lr(c, c), 0.0)) {
+            const Vec3 v = sub(V[f2[1]], V[f1[0]]);
+            if (equal_eps(dot_lr(n1, v), 0.0)) return true;
+        }
+        return false;
+    }
+    // union of two edge-sharing coplanar polygons; false when they share no edge
+    bool merge(const std::vector<u32>& f1_, const std::vector<u32>& f2_, std::vector<u32>& out) const {
+        std::vector<u32> f1 = f1_, f2 = f2_;
+        Vec3 n1, n2;
+        if (!unit_normal(f1_, n1) || !unit_normal(f2_, n2)) throw Error("degenerate facet (all vertices on one line)");
+        if (dot_lr(n1, n2) < 0) std::reverse(f2.begin() + 1, f2.end());
+        long v1 = -1, v2 = -1;
+        for (size_t i = 0; i < f1.size(); i++) if (!contains(f2, f1[i])) { v1 = (long)i; break; }
+        for (size_t i = 0; i < f2.size(); i++) if (!contains(f1, f2[i])) { v2 = (long)i; break; }
+        bool contained = false;
+        rotate_left(f1, v1);
+        if (v2 != -1) rotate_left(f2, v2);
+        else contained = true;
+        size_t a[2] = {0, 0}, b[2] = {0, 0};
+        int count = 0;
+        for (size_t i = 0; i < f1.size(); i++)
+            for (size_t j = 0; j < f2.size(); j++)
+                if (f1[i] == f2[j]) {
+                    if (count == 0) { a[0] = i; b[0] = j; }
+                    else { a[1] = i; b[1] = j; }
+                    count++;
+                }
+        if (count < 2) return false;
+        std::vector<u32> f(f1.begin(), f1.begin() + a[0] + 1);
+        if (contained) {
+            for (size_t j = b[0] + 1; j < b[1]; j++) f.push_back(f2[j]);
+        } else {
+            for (size_t j = b[0] + 1; j < f2.size(); j++) f.push_back(f2[j]);
+            for (size_t j = 0; j < b[1] && j < f2.size(); j++) f.push_back(f2[j]);
+        }
+        for (size_t i = a[1]; i < f1.size(); i++) f.push_back(f1[i]);
+        while (point_in_line(V[f[0]], V[f.back()], V[f[1]])) rotate_left(f, 1);
+        out.swap(f);
+        return true;
+    }
+};
+
+// corner vertices of the two (possibly merged, > 4 vertices) polygons: vertices where the boundary turns by more than
+// pi/16, then the pairing of getHexCorners (mesh.cpp:113-157)
+void MeshTopo::hex_corners_poly(const std::vector<u32>& f1, const std::vector<u32>& f2, u32 out[8]) const {
+    const double PI = 3.14159265358979323846264, tol = PI / 16;
+    std::vector<u32> fm[2];
+    const std::vector<u32>* fk2[2] = {&f1, &f2};
+    for (int w = 0; w < 2; w++) {
+        const std::vector<u32>& fk = *fk2[w];
+        size_t i0 = fk.size() - 1;
+        for (size_t i = 0; i < fk.size(); i++) {
+            if (fm[w].size() >= 4) break;
+            const size_t i1 = (i == fk.size() - 1) ? 0 : i + 1;
+            const Vec3 v0 = unit(sub(V[fk[i]], V[fk[i0]])), v1 = unit(sub(V[fk[i1]], V[fk[i]]));
+            const double dt = std::max(-1.0, std::min(1.0, dot(v0, v1)));
+            const double ang = std::acos(dt);
+            if (!(ang < tol || ang >= PI - tol)) { fm[w].push_back(fk[i]); i0 = i; }
+        }
+        if (fm[w].size() != 4) throw Error("a cell side does not have four corners");
+    }
+    hex_corners(fm[0].data(), fm[1].data(), out);
+}
+
+// merged polygon of the facets of `cell` that carry local id `id` (DG::init_geom merges them the same way, dg.cpp:176-215)
+std::vector<u32> MeshTopo::merged_side(u32 cell, u32 id) const {
+    PolyOps ops{V};
+    std::vector<u32> f;
+    bool first = true;
+    for (u32 q = cellStart[cell]; q < cellStart[cell + 1]; q++) {
+        if (cellFaceID[q] != id) continue;
+        const u32 fi = cellFaces[q];
+        std::vector<u32> g(facetVerts.begin() + facetStart[fi], facetVerts.begin() + facetStart[fi + 1]);
+        if (first) { f.swap(g); first = false; }
+        else {
+            std::vector<u32> m;
+            if (!ops.merge(f, g, m)) throw Error("cell " + std::to_string(cell) + ": sub-facets of one side do not share an edge in face order");
+            f.swap(m);
+        }
+    }
+    return f;
+}
+
+void MeshTopo::fix_general_cell(u32 ci) {
+    PolyOps ops{V};
+    const u32 c0 = cellStart[ci], nfc = cellStart[ci + 1] - c0;
+    auto facet = [&](u32 fi) { return std::vector<u32>(facetVerts.begin() + facetStart[fi], facetVerts.begin() + facetStart[fi + 1]); };
+    // group coplanar faces, always seeding with the first remaining face
+    std::vector<u32> rem(cellFaces.begin() + c0, cellFaces.begin() + c0 + nfc);
+    std::vector<std::vector<u32>> cng, fng;
+    for (int grp = 0; grp < 6; grp++) {
+        if (rem.empty()) throw Error("cell " + std::to_string(ci) + " has fewer than six sides");
+        std::vector<u32> g{rem[0]}, keep;
+        const std::vector<u32> seed = facet(rem[0]);
+        for (size_t j = 1; j < rem.size(); j++) {
+            if (ops.coplanar(seed, facet(rem[j]))) g.push_back(rem[j]);
+            else keep.push_back(rem[j]);
+        }
+        rem.swap(keep);
+        // mergeFacetsGroup
+        std::vector<u32> fn = facet(g[0]);
+        std::vector<u32> rest(g.begin() + 1, g.end());
+        while (!rest.empty()) {
+            std::vector<u32> left;
+            bool repeat = false, any = false;
+            for (u32 fi : rest) {
+                std::vector<u32> m;
+                if (ops.merge(fn, facet(fi), m)) { fn.swap(m); any = true; }
+                else { repeat = true; left.push_back(fi); }
+            }
+            rest.swap(left);
+            if (!repeat) break;
+            if (!any) throw Error("cell " + std::to_string(ci) + ": coplanar facets cannot be merged into one side");
+        }
+        cng.push_back(g);
+        fng.push_back(fn);
+    }
+    if (!rem.empty()) throw Error("cell " + std::to_string(ci) + " has more than six sides");
+    int gid[6] = {-1, -1, -1, -1, -1, -1};
+    const std::vector<u32>& f0 = fng[0];
+    for (int j = 0; j < 6; j++) {
+        if (gid[j] >= 0) continue;
+        const std::vector<u32>& fj = fng[j];
+        int id = j;
+        if (j >= 1) {
+            int n01 = 0, n0l = 0;
+            for (u32 x : fj) { if (x == f0[0] || x == f0[1]) n01++; if (x == f0[0] || x == f0.back()) n0l++; }
+            if (n01 >= 2) id = 2;
+            else if (n0l >= 2) id = 4;
+            else continue;
+        }
+        gid[j] = id;
+        for (int k = 0; k < 6; k++) {
+            if (gid[k] >= 0) continue;
+            bool shares = false;
+            for (u32 x : fj) if (contains(fng[k], x)) { shares = true; break; }
+            if (!shares) { gid[k] = id ^ 1; break; }
+        }
+    }
+    for (int q = 0; q < 6; q++)
+        if (gid[q] < 0) throw Error("cell " + std::to_string(ci) + " is not a hexahedron with 3 pairs of opposite sides");
+    const Vec3 N = cross(sub(V[f0[1]], V[f0[0]]), sub(V[f0.back()], V[f0[0]]));
+    const Vec3 e = sub(V[fng[1][0]], V[f0[0]]);
+    if (dot_lr(N, e) < 0)
+        for (int q = 0; q < 6; q++) gid[q] = (gid[q] == 0) ? 1 : (gid[q] == 1 ? 0 : gid[q]);
+    int i0 = 0, i1 = 0;
+    for (int q = 0; q < 6; q++) { if (gid[q] == 0) i0 = q; else if (gid[q] == 1) i1 = q; }
+    const u32 fa = cng[i0][0], fb = cng[i1][0];
+    const u32 i0n = (FNC[fa] != ci) ? FNC[fa] : FOC[fa];
+    const u32 i1n = (FNC[fb] != ci) ? FNC[fb] : FOC[fb];
+    const bool flip = (i0n > i1n) && (ci >= i0n || ci >= i1n);
+    u32 vp[8];
+    if (!flip) hex_corners_poly(fng[i0], fng[i1], vp);
+    else {
+        u32 t[8];
+        hex_corners_poly(fng[i1], fng[i0], t);
+        for (int q = 0; q < 4; q++) { vp[q] = t[q + 4]; vp[q + 4] = t[q]; }
+    }
+    const u32 rots[6] = {vp[0], vp[4], vp[0], vp[3], vp[0], vp[1]};
+    const u32 rote[6] = {vp[1], vp[5], vp[1], vp[2], vp[3], vp[2]};
+    for (int i = 0; i < 6; i++) {
+        std::vector<u32>& fn = fng[i];
+        const u32 rs = rots[gid[i]], re = rote[gid[i]];
+        const auto itp = std::find(fn.begin(), fn.end(), rs);
+        if (itp == fn.end()) throw Error("cell " + std::to_string(ci) + ": side does not contain its reference corner");
+        rotate_left(fn, (long)(itp - fn.begin()));
+        const double d = dot_lr(unit(sub(V[fn[1]], V[fn[0]])), unit(sub(V[re], V[rs])));
+        if (d < 0.99) std::reverse(fn.begin() + 1, fn.end());
+        // orient every sub-facet of the side against the side's polygon
+        for (size_t j = 0; j < cng[i].size(); j++) {
+            const u32 fid = cng[i][j];
+            u32* fbeg = &facetVerts[facetStart[fid]];
+            const size_t fl = facetStart[fid + 1] - facetStart[fid];
+            auto in_f = [&](u32 v) { return std::find(fbeg, fbeg + fl, v) != fbeg + fl; };
+            size_t it1 = 0;
+            while (it1 < fn.size() && !in_f(fn[it1])) it1++;
+            if (it1 == fn.size()) throw Error("cell " + std::to_string(ci) + ": sub-facet shares no vertex with its side");
+            const size_t p2 = (size_t)(std::find(fbeg, fbeg + fl, fn[it1]) - fbeg);
+            std::rotate(fbeg, fbeg + p2, fbeg + fl);
+            if (j >= 2) {
+                const size_t sft = (j - 1) % fl;       // std::rotate(f.rbegin(), f.rbegin() + (j-1), f.rend()): right by j-1
+                if (sft) std::rotate(fbeg, fbeg + (fl - sft), fbeg + fl);
+            }
+            for (size_t k = 1; k < fl; k++) {
+                const auto it = std::find(fn.begin(), fn.end(), fbeg[k]);
+                if (it == fn.end()) continue;
+                const size_t it3 = (size_t)(it - fn.begin());
+                if (it1 > it3) { std::reverse(fbeg + 1, fbeg + fl); break; }
+                it1 = it3;
+            }
+        }
+    }
+    // rewrite the face list in id order (sub-facets of a side stay in their group order)
+    size_t w = 0;
+    std::vector<u32> ids;
+    for (int want = 0; want < 6; want++)
+        for (int i = 0; i < 6; i++)
+            if (gid[i] == want)
+                for (u32 fid : cng[i]) { cellFaces[c0 + w] = fid; cellFaceID[c0 + w] = (u32)want; ids.push_back((u32)want); w++; }
+    if (nfc > 6)
+        for (u32 j = 0; j < nfc; j++)
+            if (std::count(ids.begin(), ids.end(), ids[j]) > 1) {
+                const u32 f = cellFaces[c0 + j];
+                FMC[f] = (FOC[f] == ci) ? 2u : 1u;
+            }
+}
+
 void MeshTopo::fix_hex_cells() {
     FMC.assign(nFacets(), 0);
     cellFaceID.assign(cellFaces.size(), 0);
     for (u32 ci = 0; ci < nBCS; ci++) {
         const u32 c0 = cellStart[ci];
-        if (cellStart[ci + 1] - c0 != 6)
-            throw Error("cell " + std::to_string(ci) + " does not have 6 faces: non-conforming (AMR) grids are not supported by this build");
+        // conforming hexahedron (six quadrilaterals): the short route below; anything else: the general route
+        bool simple = (cellStart[ci + 1] - c0 == 6);
+        for (u32 q = c0; simple && q < cellStart[ci + 1]; q++)
+            simple = (facetStart[cellFaces[q] + 1] - facetStart[cellFaces[q]] == 4);
+        if (!simple) { fix_general_cell(ci); continue; }
         u32 fc[6];
         u32* fv[6];
         for (int q = 0; q < 6; q++) {
             fc[q] = cellFaces[c0 + q];
-            if (facetStart[fc[q] + 1] - facetStart[fc[q]] != 4)
-                throw Error("facet " + std::to_string(fc[q]) + " is not a quadrilateral: hanging nodes are not supported by this build");
             fv[q] = &facetVerts[facetStart[fc[q]]];
         }
         auto has = [&](int q, u32 v) { return fv[q][0] == v || fv[q][1] == v || fv[q][2] == v || fv[q][3] == v; };

@@ -99,10 +99,13 @@ struct MeshTopo {
     u32 nCells() const { return (u32)cellStart.size() - 1; }
     void load(const Grid& g);            // Mesh::LoadMesh
     void hex_corners(const u32* f1, const u32* f2, u32 out[8]) const;   // quads only
+    void hex_corners_poly(const std::vector<u32>& f1, const std::vector<u32>& f2, u32 out[8]) const;   // merged sides
+    std::vector<u32> merged_side(u32 cell, u32 id) const;               // polygon of all facets of `cell` with local id `id`
 
 private:
     void add_boundary_cells();
     void fix_hex_cells();
+    void fix_general_cell(u32 ci);       // non-conforming cell: coplanar sub-facets grouped and merged per side
     void calc_geometry();
     void remove_boundary(const std::vector<u32>& faces);
 };
@@ -111,6 +114,9 @@ private:
 struct Basis {
     int NPX = 1, NPY = 1, NPZ = 1, NP = 1, NPF = 1;
     std::vector<double> xgl[3], wgl[3], psi[3], dpsi[3];
+    // 2:1 mortar projections per direction d and half h (dg.cpp:550-590): psiRef[d*2+h][in*n+io] coarse -> fine trace,
+    // psiCor[d*2+h][io*n+in] fine -> coarse flux
+    std::vector<double> psiRef[6], psiCor[6];
     explicit Basis(const int nop[3]);     // DG::Nop = polynomial degree per direction
     int n(int d) const { return d == 0 ? NPX : (d == 1 ? NPY : NPZ); }
 };
@@ -121,7 +127,8 @@ void lagrange_basis_derivative(int N, const double* xgl, int Ns, const double* x
 struct Geometry {
     u32 nBCS = 0, nCells = 0, nFacets = 0;
     uint64_t gBCSfield = 0, gALL = 0;
-    std::vector<double> cC, cV, Jinv, fN, fC, fI, faceNormal;   // AoS like the reference
+    std::vector<double> cC, cV, Jinv, fN, fC, fI, faceNormal, faceCenter;   // AoS like the reference
+    std::vector<double> psiRef[6], psiCor[6];                   // copies of the basis tables (only read on non-conforming meshes)
     std::vector<u32> FO, FN, faceBegin, faceEnd, allFaces, faceID, faceOwner, faceNeigh, faceMortar;
     void build(const MeshTopo& t, const Basis& b);   // initGeomMeshFields + init_geom (fI = 0.5 on interMesh_* faces)
     nsem_mesh as_c() const;

@@ -10,6 +10,7 @@
 #include "nsem_kernels_v2.cuh"
 #include "nsem_kernels_v3.cuh"
 #include "nsem_kernels_v4.cuh"
+#include "nsem_mortar.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -124,6 +125,7 @@ struct nsem_ctx {
     bool use_v3 = false;      // warp-per-element pencil kernels (NSEM_KERNELS=v3)
     bool use_v2 = false;      // bulk-async staged kernels (3-D); NSEM_KERNELS=v1 forces the plain-load kernels
     bool use_v4 = false;      // persistent software-pipelined kernels (3-D, default); NSEM_KERNELS=v2|v1|v3 select the older generations
+    bool pref_v2 = false, pref_v3 = false, pref_v4 = false;   // what nsem_set_order selected; a non-conforming mesh falls back to v1
     bool tri = false;         // v4: metrics evaluated on the fly from the element's trilinear map (verified at upload)
     int numSMs = 148;
     double X[3][MAXN];        // LGL nodes
@@ -154,6 +156,11 @@ struct nsem_ctx {
     DevBuf<ElemRec> elemRec;
     DevBuf<double> traceA, bVec;     // face traces of sweep A (v2), area vectors of the boundary faces
     bool has_sched = false;
+    // non-conforming (mortar) faces: groups = coarse faces, subs = their sub-facets (nsem_mortar.cuh)
+    DevBuf<MortarGroup> mortarGroups;
+    DevBuf<MortarSub> mortarSubs;
+    DevBuf<double> psiRef, psiCor, mortarA, mortarB;
+    uint32_t nMortarGroups = 0, nMortarSubs = 0;
     // ghost tables
     DevBuf<uint32_t> ghostRef, bOwner;
     DevBuf<uint8_t> bFid;
@@ -507,6 +514,7 @@ extern "C" const char* nsem_kernel_info(const nsem_ctx* c) {
     if (c->use_v4) return c->tri ? "v4 persistent pipelined, metrics on the fly (trilinear map verified)" : "v4 persistent pipelined, stored metrics";
     if (c->use_v3) return "v3 warp per element";
     if (c->use_v2) return "v2 bulk-async staged";
+    if (c->nMortarGroups) return "v1 plain loads + mortar (non-conforming) face kernels";
     return "v1 plain loads";
 }
 
@@ -538,6 +546,7 @@ extern "C" int nsem_set_order(nsem_ctx* c, int NPX, int NPY, int NPZ) {
     c->use_v2 = has_v2(NPX, NPY, NPZ) && !(kv && std::strcmp(kv, "v1") == 0);
     c->use_v3 = has_v3(NPX, NPY, NPZ) && (kv && std::strcmp(kv, "v3") == 0);
     c->use_v4 = has_v4(NPX, NPY, NPZ) && !(kv && (std::strcmp(kv, "v1") == 0 || std::strcmp(kv, "v2") == 0 || std::strcmp(kv, "v3") == 0));
+    c->pref_v2 = c->use_v2; c->pref_v3 = c->use_v3; c->pref_v4 = c->use_v4;
     c->tri = false;
     return 0;
 }
@@ -623,18 +632,110 @@ extern "C" int nsem_upload_mesh(nsem_ctx* c, const nsem_mesh* m) {
             if (m->all_faces[f] == face) return (int)m->face_id[f];
         return -1;
     };
+    // ---- non-conforming (mortar) faces: groups = coarse faces with their sub-facets (nsem_mortar.cuh) ----
+    bool anyMortar = false;
+    if (m->face_mortar)
+        for (uint32_t f = 0; f < nF && !anyMortar; f++) anyMortar = m->face_mortar[f] != 0;
+    if (anyMortar) {
+        bool have = m->cC && m->face_center;
+        for (int q = 0; q < 6; q++) have = have && m->psi_ref[q] && m->psi_cor[q];
+        if (!have) { c->err = "nsem_upload_mesh: a non-conforming mesh needs cC, face_center, psi_ref and psi_cor"; return 1; }
+    }
+    // the element sweeps that know the FM_MORTAR branch are the plain-load ones (v1)
+    c->use_v2 = c->pref_v2 && !anyMortar;
+    c->use_v3 = c->pref_v3 && !anyMortar;
+    c->use_v4 = c->pref_v4 && !anyMortar;
+    std::vector<MortarGroup> mGroups;
+    std::vector<std::vector<MortarSub>> mSubs;          // per group, in the coarse cell's face order
+    std::vector<int32_t> mBlock(anyMortar ? (size_t)nB * 6 : 0, -1), mGroupOf(anyMortar ? (size_t)nB * 6 : 0, -1);
+    uint32_t nMortarBlocks = 0;
+    auto mortar_block = [&](uint32_t cell, int sid) -> uint32_t {
+        int32_t& b = mBlock[(size_t)cell * 6 + sid];
+        if (b < 0) b = (int32_t)nMortarBlocks++;
+        return (uint32_t)b;
+    };
+    auto face_dims = [&](int fid, int& d1, int& d2, int& n1, int& n2) {
+        if (fid < 2) { d1 = 0; d2 = 1; n1 = NX; n2 = NY; }
+        else if (fid < 4) { d1 = 0; d2 = 2; n1 = NX; n2 = NZ; }
+        else { d1 = 1; d2 = 2; n1 = NY; n2 = NZ; }
+    };
     for (uint32_t ci = 0; ci < nB; ci++) {
         for (uint32_t f = m->face_begin[ci]; f < m->face_end[ci]; f++) {
             const uint32_t face = m->all_faces[f];
             const int sid = (int)m->face_id[f];
             if (sid < 0 || sid > 5) { c->err = "nsem_upload_mesh: face id outside 0..5"; return 1; }
-            if (m->face_mortar && m->face_mortar[face] != 0) {
-                c->err = "nsem_upload_mesh: non-conforming (mortar) faces are not supported by this build";
-                return 1;
+            if (anyMortar && m->face_mortar[face] != 0) {
+                const uint32_t fm = m->face_mortar[face];
+                const uint32_t fo = m->face_owner[face], fn = m->face_neigh[face];
+                const uint32_t fine = (fm == 1) ? fo : fn, coarse = (fm == 1) ? fn : fo;      // field.h:2158-2159
+                if (fm > 2 || fine >= nB || coarse >= nB || (ci != fine && ci != coarse)) {
+                    c->err = "nsem_upload_mesh: inconsistent gFMC/gFOC/gFNC on a non-conforming face";
+                    return 1;
+                }
+                const size_t e6 = (size_t)ci * 6 + sid;
+                const bool own = (fo == ci);
+                int d1, d2, n1, n2;
+                face_dims(sid, d1, d2, n1, n2);
+                // my side of the reference's node maps on this facet: slot (a,b) <-> my face node (a,b)  (dg.cpp:372-404)
+                for (int a = 0; a < n1; a++)
+                    for (int b = 0; b < n2; b++) {
+                        const size_t k = (size_t)face * NPF + (size_t)a * n2 + b;
+                        const uint32_t mine = ci * (uint32_t)NP + (uint32_t)h_face_node(c, sid, a, b);
+                        if ((own ? m->FO[k] : m->FN[k]) != mine) {
+                            c->err = "nsem_upload_mesh: a non-conforming facet does not follow the tensor-product node pairing of dg.cpp:372-404";
+                            return 1;
+                        }
+                    }
+                fOther[e6] = mortar_block(ci, sid);
+                fMeta[e6] = FM_MORTAR | FM_ABSENT | FM_HALF | (own ? FM_OWNER : 0u);
+                if (ci == fine) continue;        // the sub-facet record is written from the coarse side
+                // ---- coarse side: one group per (coarse cell, local face), sub-facets in the cell's face order ----
+                int32_t& gi = mGroupOf[e6];
+                if (gi < 0) {
+                    gi = (int32_t)mGroups.size();
+                    MortarGroup g;
+                    std::memset(&g, 0, sizeof g);
+                    g.coarse = ci * (uint32_t)NPS; g.fid_c = (uint32_t)sid; g.block = fOther[e6];
+                    mGroups.push_back(g);
+                    mSubs.emplace_back();
+                }
+                const int fidf = local_id(fine, face);
+                if (fidf < 0) { c->err = "nsem_upload_mesh: face not found in its fine cell"; return 1; }
+                int e1, e2, m1, m2;
+                face_dims(fidf, e1, e2, m1, m2);
+                if (m1 != n1 || m2 != n2) { c->err = "nsem_upload_mesh: the two sides of a non-conforming facet have different node extents"; return 1; }
+                // half of the coarse face this sub-facet covers along each face axis (field.h:2174-2197)
+                double cco[3], ccn[3] = {0, 0, 0};
+                for (int d = 0; d < 3; d++) cco[d] = m->face_center[(size_t)face * 3 + d];
+                int nch = 0;
+                for (uint32_t r = m->face_begin[ci]; r < m->face_end[ci]; r++)
+                    if ((int)m->face_id[r] == sid) {
+                        for (int d = 0; d < 3; d++) ccn[d] += m->face_center[(size_t)m->all_faces[r] * 3 + d];
+                        nch++;
+                    }
+                for (int d = 0; d < 3; d++) ccn[d] /= (double)nch;
+                const double* v0 = m->cC + ((size_t)ci * NP + h_face_node(c, sid, 0, 0)) * 3;
+                const double* v1 = m->cC + ((size_t)ci * NP + h_face_node(c, sid, n1 - 1, 0)) * 3;
+                const double* v2 = m->cC + ((size_t)ci * NP + h_face_node(c, sid, 0, n2 - 1)) * 3;
+                auto dot3 = [](const double* a, const double* o, const double* b) {
+                    return ((a[0] - o[0]) * (b[0] - o[0]) + (a[1] - o[1]) * (b[1] - o[1])) + (a[2] - o[2]) * (b[2] - o[2]);
+                };
+                const uint32_t h1 = (dot3(ccn, v0, v1) >= dot3(cco, v0, v1)) ? 0u : 1u;
+                const uint32_t h2 = (dot3(ccn, v0, v2) >= dot3(cco, v0, v2)) ? 0u : 1u;
+                MortarSub sb;
+                std::memset(&sb, 0, sizeof sb);
+                sb.fine = fine * (uint32_t)NPS; sb.fid_f = (uint32_t)fidf;
+                sb.flags = h1 | (h2 << 1) | (fm == 1 ? 4u : 0u);
+                sb.block = mortar_block(fine, fidf);
+                const double* N = m->face_normal + (size_t)face * 3;
+                const double mg = std::sqrt(N[0] * N[0] + (N[1] * N[1] + N[2] * N[2]));
+                for (int d = 0; d < 3; d++) { sb.vec[d] = N[d]; sb.unit[d] = N[d] / mg; }
+                mSubs[gi].push_back(sb);
+                continue;
             }
             const size_t e6 = (size_t)ci * 6 + sid;
-            if ((fMeta[e6] & FM_FID_MASK) != FM_ABSENT) {
-                c->err = "nsem_upload_mesh: two faces with the same local id on one element (non-conforming mesh)";
+            if ((fMeta[e6] & FM_FID_MASK) != FM_ABSENT || (fMeta[e6] & FM_MORTAR)) {
+                c->err = "nsem_upload_mesh: two faces with the same local id on one element that are not flagged in face_mortar";
                 return 1;
             }
             const bool own = (m->face_owner[face] == ci);
@@ -710,6 +811,36 @@ extern "C" int nsem_upload_mesh(nsem_ctx* c, const nsem_mesh* m) {
     c->h_bFid = bFid;
 
     cudaStream_t s = c->stream;
+    {
+        std::vector<MortarSub> subs;
+        for (size_t g = 0; g < mGroups.size(); g++) {
+            mGroups[g].sub0 = (uint32_t)subs.size();
+            mGroups[g].nsub = (uint32_t)mSubs[g].size();
+            subs.insert(subs.end(), mSubs[g].begin(), mSubs[g].end());
+        }
+        c->nMortarGroups = (uint32_t)mGroups.size();
+        c->nMortarSubs = (uint32_t)subs.size();
+        CUDA_TRY(c, c->mortarGroups.upload(mGroups, s));
+        CUDA_TRY(c, c->mortarSubs.upload(subs, s));
+        std::vector<double> pr(anyMortar ? 6 * MAXN * MAXN : 0, 0.0), pc(pr.size(), 0.0);
+        if (anyMortar) {
+            const int nd[3] = {NX, NY, NZ};
+            for (int q = 0; q < 6; q++)
+                for (int e = 0; e < nd[q / 2] * nd[q / 2]; e++) {
+                    pr[(size_t)q * MAXN * MAXN + e] = m->psi_ref[q][e];
+                    pc[(size_t)q * MAXN * MAXN + e] = m->psi_cor[q][e];
+                }
+        }
+        CUDA_TRY(c, c->psiRef.upload(pr, s));
+        CUDA_TRY(c, c->psiCor.upload(pc, s));
+        CUDA_TRY(c, c->mortarA.alloc((size_t)nMortarBlocks * MORTAR_NA * MORTAR_MAXF));
+        CUDA_TRY(c, c->mortarB.alloc((size_t)nMortarBlocks * MORTAR_NB * MORTAR_MAXF));
+        if (nMortarBlocks) {
+            CUDA_TRY(c, cudaMemsetAsync(c->mortarA.p, 0, c->mortarA.n * sizeof(double), s));
+            CUDA_TRY(c, cudaMemsetAsync(c->mortarB.p, 0, c->mortarB.n * sizeof(double), s));
+        }
+        CUDA_TRY(c, cudaStreamSynchronize(s));
+    }
     CUDA_TRY(c, c->faceOther.upload(fOther, s));
     CUDA_TRY(c, c->faceMeta.upload(fMeta, s));
     CUDA_TRY(c, c->faceVec.upload(fVec, s));
@@ -1105,6 +1236,7 @@ static void fill_kparams(const nsem_ctx* c, KParams& P) {
     P.sched = c->has_sched ? c->sched.p : nullptr;
     P.faceRec = c->faceRec.p;
     P.traceA = c->traceA.p;
+    P.mortarA = c->mortarA.p; P.mortarB = c->mortarB.p;
     // stage-slot order of the v4 sweeps (CfgA / CfgB)
     {
         int q = 0;
@@ -1134,6 +1266,26 @@ static void fill_bcparams(const nsem_ctx* c, const KParams& P, BCParams& B, int 
 }
 
 static int halo_exchange(nsem_ctx* c, double* const* arrays, int nf, cudaStream_t s);
+
+// non-conforming faces: phase 0 before sweep A (old state), phase 1 before sweep B (rho_new, p', gradients of real cells)
+static cudaError_t launch_mortar(const nsem_ctx* c, const KParams& P, int phase) {
+    if (c->nMortarGroups == 0) return cudaSuccess;
+    MortarParams M;
+    std::memset(&M, 0, sizeof M);
+    M.nGroups = c->nMortarGroups;
+    M.NX = c->NX; M.NY = c->NY; M.NZ = c->NZ; M.visc = P.visc;
+    M.T0 = P.T0; M.nu = P.nu; M.iPr = P.iPr; M.gammaR = P.gamma * P.R;
+    std::memcpy(M.W, c->W, sizeof M.W);
+    M.groups = c->mortarGroups.p; M.subs = c->mortarSubs.p;
+    M.psiRef = c->psiRef.p; M.psiCor = c->psiCor.p;
+    M.rho_old = P.rho_old; M.rho_new = P.rho_new; M.T_old = P.T_old; M.p = P.p;
+    for (int d = 0; d < 3; d++) { M.U_old[d] = P.U_old[d]; M.GT[d] = P.GT[d]; }
+    for (int d = 0; d < 9; d++) M.GU[d] = P.GU[d];
+    M.outA = c->mortarA.p; M.outB = c->mortarB.p;
+    if (phase == 0) mortarA_kernel<<<c->nMortarGroups, MORTAR_MAXF, 0, c->stream>>>(M);
+    else mortarB_kernel<<<c->nMortarGroups, MORTAR_MAXF, 0, c->stream>>>(M);
+    return cudaGetLastError();
+}
 
 // One step with the halo exchanges on the comm stream overlapped with the interior elements (the reference's mul()
 // also does interior cells while the halo is in flight, field.h:2381-2415).  Elements that touch an
@@ -1190,12 +1342,13 @@ static int join_comm(nsem_ctx* c) {
 }
 
 static int one_step(nsem_ctx* c, bool timed, double* acc) {
-    if (!timed && !c->peers.empty() && c->overlap) return one_step_overlapped(c);
+    if (!timed && !c->peers.empty() && c->overlap && c->nMortarGroups == 0) return one_step_overlapped(c);
     if (join_comm(c)) return 1;
     KParams P;
     BCParams B;
     fill_kparams(c, P);
     if (timed) cudaEventRecord(c->ev[0], c->stream);
+    CUDA_TRY(c, launch_mortar(c, P, 0));
     CUDA_TRY(c, launch_sweepA(c, P));
     if (timed) cudaEventRecord(c->ev[1], c->stream);
     fill_bcparams(c, P, B, 0);
@@ -1208,6 +1361,7 @@ static int one_step(nsem_ctx* c, bool timed, double* acc) {
     }
     CUDA_TRY(c, launch_ghost_trace(c, P));
     if (timed) cudaEventRecord(c->ev[2], c->stream);
+    CUDA_TRY(c, launch_mortar(c, P, 1));
     CUDA_TRY(c, launch_sweepB(c, P));
     if (timed) cudaEventRecord(c->ev[3], c->stream);
     B.phase = 1;
@@ -1217,7 +1371,7 @@ static int one_step(nsem_ctx* c, bool timed, double* acc) {
         if (halo_exchange(c, arr, 4, c->stream)) return 1;
     }
     if (timed) cudaEventRecord(c->ev[4], c->stream);
-    c->launches += 2 + (c->nG ? 2 : 0) + ((c->nG && (c->use_v4 || (c->use_v2 && !c->use_v3))) ? 1 : 0);
+    c->launches += 2 + (c->nG ? 2 : 0) + ((c->nG && (c->use_v4 || (c->use_v2 && !c->use_v3))) ? 1 : 0) + (c->nMortarGroups ? 2 : 0);
     c->cur ^= 1;
     if (timed) {
         CUDA_TRY(c, cudaEventSynchronize(c->ev[4]));

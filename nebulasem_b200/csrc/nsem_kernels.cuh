@@ -39,6 +39,10 @@ constexpr uint32_t FM_GHOST = 6u;
 constexpr uint32_t FM_ABSENT = 7u;
 constexpr uint32_t FM_OWNER = 8u;         // this element is the face's owner (gFOC)
 constexpr uint32_t FM_HALF = 16u;         // fI = 0.5 (interior / inter-rank); else fI = 0 (physical boundary)
+constexpr uint32_t FM_MORTAR = 32u;       // non-conforming (2:1) face: the finished surface contributions of this local face are in
+                                          // the mortar buffers (nsem_mortar.cuh), block id in faceOther
+constexpr int MORTAR_NA = 13, MORTAR_NB = 4;   // values per face node: sweep A {r_rho, gU[9], gT[3]}, sweep B {r_U[3], r_theta}
+constexpr int MORTAR_MAXF = 64;                // face-node stride of a mortar block (MAXN * MAXN)
 
 struct FaceRec;
 struct ElemRec;
@@ -86,6 +90,9 @@ struct KParams {
     // rho_new theta, |U| + c} of the side that OWNS the block; block id = elem*6 + local face, ghost cells nB*6 + g
     double* traceA;
     const struct ElemRec* elemRec;   // [nB] v4 kernels: the six face records and the trilinear map of the element
+    // non-conforming faces: [blocks][MORTAR_NA | MORTAR_NB][MORTAR_MAXF] surface contributions written by mortarA/B_kernel
+    const double* mortarA;
+    const double* mortarB;
     // v4 kernels: the arrays each sweep stages, in stage-slot order (so the issuing lanes index them instead of branching)
     const double* srcA[16];
     const double* srcB[32];
@@ -241,9 +248,21 @@ sweepA_kernel(const __grid_constant__ KParams P) {
         if (!on_face(s, i, j, k, NX, NY, NZ)) continue;
         const uint32_t meta = P.faceMeta[elem * 6 + s];
         const uint32_t fid = meta & FM_FID_MASK;
-        if (fid == FM_ABSENT) continue;
         int a, b;
         const int n = face_slot<NX, NY, NZ>(s, i, j, k, a, b);
+        if (meta & FM_MORTAR) {
+            // non-conforming face: mortarA_kernel left this node's surface terms (scatter/gather_non_conforming, field.h:2019-2248)
+            const double* mc = P.mortarA + (size_t)P.faceOther[elem * 6 + s] * (MORTAR_NA * MORTAR_MAXF) + n;
+            r_rho += mc[0];
+            if (VISC) {
+#pragma unroll
+                for (int c = 0; c < 9; c++) gU[c] += mc[(1 + c) * MORTAR_MAXF];
+#pragma unroll
+                for (int c = 0; c < 3; c++) gT[c] += mc[(10 + c) * MORTAR_MAXF];
+            }
+            continue;
+        }
+        if (fid == FM_ABSENT) continue;
         const size_t oidx = (size_t)P.faceOther[elem * 6 + s] + (fid == FM_GHOST ? n : face_node<NX, NY, NZ>(fid, a, b));
         const double w = face_weight<NX, NY, NZ>(P, s, a, b);
         const double* fv = P.faceVec + (size_t)(elem * 6 + s) * 3;
@@ -384,9 +403,16 @@ sweepB_kernel(const __grid_constant__ KParams P) {
         if (!on_face(s, i, j, k, NX, NY, NZ)) continue;
         const uint32_t meta = P.faceMeta[elem * 6 + s];
         const uint32_t fid = meta & FM_FID_MASK;
-        if (fid == FM_ABSENT) continue;
         int a, b;
         const int n = face_slot<NX, NY, NZ>(s, i, j, k, a, b);
+        if (meta & FM_MORTAR) {
+            // non-conforming face: mortarB_kernel left this node's momentum and theta fluxes
+            const double* mc = P.mortarB + (size_t)P.faceOther[elem * 6 + s] * (MORTAR_NB * MORTAR_MAXF) + n;
+#pragma unroll
+            for (int c = 0; c < 4; c++) r[c] += mc[c * MORTAR_MAXF];
+            continue;
+        }
+        if (fid == FM_ABSENT) continue;
         const size_t oidx = (size_t)P.faceOther[elem * 6 + s] + (fid == FM_GHOST ? n : face_node<NX, NY, NZ>(fid, a, b));
         const double w = face_weight<NX, NY, NZ>(P, s, a, b);
         const double* fv = P.faceVec + (size_t)(elem * 6 + s) * 3;

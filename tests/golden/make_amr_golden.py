@@ -53,9 +53,9 @@ FIXED_CONTROLS = """general
     SOR_omega 1.7
     probe 0 {{}}
     gravity 0 -9.80606 0
-    npx 4
-    npy 4
-    npz 0
+    npx {npx}
+    npy {npy}
+    npz {npz}
 }}
 prepare
 {{
@@ -84,20 +84,35 @@ def edit_controls(path, **kv):
     open(path, "w").write(txt)
 
 
-def main():
-    out_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "srtb_amr")
+# name -> (example directory, mesh-file edit, controls edits for the regrid run, orders of the fixed-mesh controls)
+CASES = {
+    # 2-D, order 4: 100 -> 196 cells, 56 mortar sub-faces (two per coarse face)
+    "srtb_amr": ("srtb-amr", None, {}, dict(npx=4, npy=4, npz=0)),
+    # 3-D, order 2: 4^3 = 64 -> 372 cells (44 refined), four mortar sub-faces per coarse face
+    "srtb3d_amr": ("srtb-3d", ("wall 3{6 6 6}", "wall 3{4 4 4}"),
+                   dict(max_level=2, field_min=0.1, field_max=0.4, npx=2, npy=2, npz=2), dict(npx=2, npy=2, npz=2)),
+}
+
+
+def main(name):
+    example, mesh_edit, ctl_edit, orders = CASES[name]
+    out_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), name)
     d = tempfile.mkdtemp(prefix="golden_amr_")
     try:
         a = os.path.join(d, "amr")
-        shutil.copytree(os.path.join(REF, "examples", "atmo", "srtb-amr"), a)
-        edit_controls(os.path.join(a, "controls"), end_step=1, write_interval=1)
+        shutil.copytree(os.path.join(REF, "examples", "atmo", example), a)
+        if mesh_edit:
+            txt = open(os.path.join(a, "bubble")).read()
+            assert mesh_edit[0] in txt
+            open(os.path.join(a, "bubble"), "w").write(txt.replace(mesh_edit[0], mesh_edit[1]))
+        edit_controls(os.path.join(a, "controls"), end_step=1, write_interval=1, **ctl_edit)
         subprocess.check_call([run_ref.ref_bin("mesh"), "bubble", "-o", "grid_0.bin"], cwd=a, stdout=subprocess.DEVNULL)
         run_ref.run_euler(a, variant="parity")                    # initial regrid -> non-conforming grid_0.bin + fields
         os.makedirs(out_dir, exist_ok=True)
         for f in ("grid_0.bin", "rho0.bin", "U0.bin", "T0.bin", "p0.bin"):
             shutil.copy(os.path.join(a, f), os.path.join(out_dir, f))
         with open(os.path.join(out_dir, "controls"), "w") as fh:        # the fixed-mesh controls (no amr_step, no refinement block)
-            fh.write(FIXED_CONTROLS.format(n=NSTEPS))
+            fh.write(FIXED_CONTROLS.format(n=NSTEPS, **orders))
         f = os.path.join(d, "fixed")
         shutil.copytree(out_dir, f)
         run_ref.run_euler(f, variant="parity")
@@ -109,4 +124,5 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    for nm in (sys.argv[1:] or list(CASES)):
+        main(nm)

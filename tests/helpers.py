@@ -44,7 +44,8 @@ def device_from_oracle(orc: EulerOracle, device=0):
     face_id = np.concatenate([np.asarray(x, dtype=np.uint32) for x in t.faceID])
     ctx.upload_mesh(n_cells_real=g.nBCS, n_cells_all=g.nCells, n_faces=g.nFacets, cV=g.cV, Jinv=g.Jinv, fN=g.fN, fI=g.fI,
                     face_normal=t.FNv, FO=g.FO, FN=g.FN, face_begin=g.faceIndices[0], face_end=g.faceIndices[1],
-                    all_faces=g.allFaces, face_id=face_id, face_owner=t.FOC, face_neigh=t.FNC, face_mortar=t.FMC)
+                    all_faces=g.allFaces, face_id=face_id, face_owner=t.FOC, face_neigh=t.FNC, face_mortar=t.FMC,
+                    cC=g.cC, face_center=t.FC, psi_ref=b.psiRef, psi_cor=b.psiCor)
     ctx.set_bcs(device_bcs(orc))
     p = orc.p
     ctx.set_params(P0=p.P0, T0=p.T0, cp=p.cp, cv=p.cv, viscosity=p.viscosity, Pr=p.Pr, gravity=p.gravity, dt=p.dt,

@@ -84,6 +84,52 @@ def test_host_solver_path_matches_oracle(tmp_cases, name, kw, syn, nsteps):
         s.close()
 
 
+@pytest.mark.parametrize("fixture,nmortar", [("srtb_amr", 56), ("srtb3d_amr", 160)])
+def test_non_conforming_mesh_matches_oracle_and_reference_dump(tmp_path, fixture, nmortar):
+    """Mortar (2:1 AMR) faces, BASELINE configs[4]: the regridded rising bubble (2-D order 4: 196 cells, 56 mortar
+    sub-facets; 3-D order 2: 372 cells, 160 sub-facets; tests/golden/<fixture>, made by make_amr_golden.py from the
+    reference's own regrid).  Both entries into the CUDA path -- the oracle's arrays through the C ABI, and the C++ host
+    (non-conforming topology, merged sides, psiRef/psiCor) from the case directory -- against the oracle AND the
+    reference binary's dump after 20 steps; mass conserved to rounding by the scatter/gather pair."""
+    import shutil
+
+    from nebulasem_b200 import host
+    from oracle import case as ocase
+    src = os.path.join(os.path.dirname(__file__), "golden", fixture)
+    d = str(tmp_path / fixture)
+    shutil.copytree(src, d)
+    gold = np.load(os.path.join(src, "expected.npz"))
+    nsteps = int(gold["nsteps"])
+    orc = ocase.load_case(d, exact_order=False)
+    assert len(orc.mortar_faces) == nmortar
+    nb = orc.gB
+    mass0 = float((orc.rho[:nb] * orc.g.cV[:nb]).sum())
+    ctx = device_from_oracle(orc)
+    assert "mortar" in ctx.kernel_info, ctx.kernel_info
+    s = host.Solver.open_case(d)
+    s.attach(0)
+    ctx.step(nsteps)
+    s.step(nsteps)
+    s.download()
+    orc.run(nsteps)
+    c0 = np.sqrt(orc.gamma * orc.R * orc.p.T0)
+    for tag, (rho, U, T) in (("c-abi", ctx.download_state()[:3]), ("host", s.state()[:3])):
+        err = conserved_errors(orc, rho, U, T)
+        print(fixture, tag, err)
+        assert np.isfinite(rho).all() and np.isfinite(U).all() and np.isfinite(T).all()
+        assert err["rho"] <= TOL and err["rhoTheta"] <= TOL and err["rhoU_scaled"] <= TOL
+        # the reference binary's own dump
+        assert np.linalg.norm(rho[:nb] - gold["rho"]) <= TOL * np.linalg.norm(gold["rho"])
+        th, th_ref = rho[:nb] * (T[:nb] + orc.p.T0), gold["rho"] * (gold["T"] + orc.p.T0)
+        assert np.linalg.norm(th - th_ref) <= TOL * np.linalg.norm(th_ref)
+        mom, mom_ref = rho[:nb, None] * U[:nb], gold["rho"][:, None] * gold["U"]
+        assert np.linalg.norm(mom - mom_ref) <= TOL * np.linalg.norm(gold["rho"]) * c0
+        mass = float((rho[:nb] * orc.g.cV[:nb]).sum())
+        assert abs(mass - mass0) <= 1e-13 * abs(mass0)
+    ctx.close()
+    s.close()
+
+
 @pytest.mark.parametrize("decomp", ["METIS", "XYZ"])
 def test_two_partitions_equal_one_partition(decomp):
     """One METIS/XYZ partition per GPU with the NCCL face-trace halo == the single-partition run."""

@@ -38,6 +38,37 @@ def test_host_geometry_and_setup_bit_equal_to_oracle(tmp_cases, name, kw):
     s.close()
 
 
+@pytest.mark.parametrize("fixture", ["srtb_amr", "srtb3d_amr"])
+def test_host_non_conforming_topology_bit_equal_to_oracle(tmp_path, fixture):
+    """Non-conforming (2:1 AMR) grids written by the reference's regrid: the C++ host's general fixHexCells route (coplanar
+    sub-facets grouped and merged per side, gFMC), node geometry from merged sides and the mortar projections
+    psiRef/psiCor (dg.cpp:550-590) are bit-equal to the oracle, which is itself bit-equal to the reference on these
+    grids (tests/test_oracle_golden.py)."""
+    import shutil
+
+    from oracle import case as ocase
+    d = str(tmp_path / fixture)
+    shutil.copytree(os.path.join(ROOT, "tests", "golden", fixture), d)
+    orc = ocase.load_case(d, exact_order=False)
+    s = host.Solver.open_case(d)
+    g = orc.g
+    assert (s.nBCS, s.nCells, s.nFacets) == (g.nBCS, g.nCells, g.nFacets)
+    assert np.count_nonzero(np.asarray(g.topo.FMC)) > 0
+    for nm, ref in (("cC", g.cC), ("cV", g.cV), ("Jinv", g.Jinv), ("fN", g.fN), ("fC", g.fC), ("fI", g.fI), ("faceNormal", g.topo.FNv),
+                    ("faceCenter", g.topo.FC)):
+        assert np.array_equal(s.f64(nm), np.asarray(ref).ravel()), nm
+    for nm, ref in (("FO", g.FO), ("FN", g.FN), ("allFaces", g.allFaces), ("faceBegin", g.faceIndices[0]), ("faceEnd", g.faceIndices[1]),
+                    ("faceOwner", g.topo.FOC), ("faceNeigh", g.topo.FNC), ("faceID", np.concatenate(g.topo.faceID)),
+                    ("faceMortar", g.topo.FMC)):
+        assert np.array_equal(s.u32(nm), np.asarray(ref, dtype=np.uint32).ravel()), nm
+    for q in range(6):
+        assert np.array_equal(s.f64(f"psiRef{q}"), g.basis.psiRef[q]), q
+        assert np.array_equal(s.f64(f"psiCor{q}"), g.basis.psiCor[q]), q
+    rho, U, T, p = s.state()
+    assert np.array_equal(rho, orc.rho) and np.array_equal(U, orc.U) and np.array_equal(T, orc.T) and np.array_equal(p, orc.pp)
+    s.close()
+
+
 def test_field_dump_written_in_the_reference_format(tmp_cases):
     orc = make_oracle(tmp_cases, "bubble3d", 1, exact=False, n=2, order=2)
     s = host.Solver.open_case(orc.case_dir)

@@ -43,19 +43,21 @@ def test_fast_order_oracle_within_tolerance(tmp_cases, path):
     assert rel_l2(orc.rho[:nb] * (orc.T[:nb] + orc.p.T0), th_ref) <= 1e-13
 
 
-def test_oracle_mortar_faces_reproduce_reference_dump(tmp_path):
-    """Non-conforming mesh (196 cells, 56 mortar sub-faces, tests/golden/srtb_amr, made by make_amr_golden.py from the
-    reference's own regrid of examples/atmo/srtb-amr): the oracle's scatter/gather_non_conforming and psiRef/psiCor
-    against the reference's dump after 20 steps -- bit-identical where libm is the same."""
+@pytest.mark.parametrize("fixture,nmortar", [("srtb_amr", 56), ("srtb3d_amr", 160)])
+def test_oracle_mortar_faces_reproduce_reference_dump(tmp_path, fixture, nmortar):
+    """Non-conforming meshes made by make_amr_golden.py from the reference's own regrid (tests/golden/srtb_amr: 2-D order 4,
+    196 cells, 56 mortar sub-faces of examples/atmo/srtb-amr; tests/golden/srtb3d_amr: 3-D order 2, 372 cells, 160 mortar
+    sub-faces, four per coarse face): the oracle's scatter/gather_non_conforming and psiRef/psiCor against the
+    reference's dump after 20 steps -- bit-identical where libm is the same."""
     import shutil
 
     from oracle import case as ocase
-    src = os.path.join(os.path.dirname(__file__), "golden", "srtb_amr")
-    d = str(tmp_path / "srtb_amr")
+    src = os.path.join(os.path.dirname(__file__), "golden", fixture)
+    d = str(tmp_path / fixture)
     shutil.copytree(src, d)
     g = np.load(os.path.join(src, "expected.npz"))
     orc = ocase.load_case(d, exact_order=True)
-    assert len(orc.mortar_faces) == 56 and orc.has_mortar
+    assert len(orc.mortar_faces) == nmortar and orc.has_mortar
     orc.run(int(g["nsteps"]))
     nb = orc.gB
     for name, mine in (("rho", orc.rho), ("U", orc.U), ("T", orc.T), ("p", orc.pp)):
