@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libnsem_cuda.so")
+# NSEM_LIBDIR selects another build of the same libraries (kernel-variant experiments, profiles/variants_r1.md)
+LIB_PATH = os.path.join(os.environ.get("NSEM_LIBDIR") or os.path.join(_HERE, "lib"), "libnsem_cuda.so")
 
 BC_KINDS = {"NEUMANN": 1, "DIRICHLET": 2, "SYMMETRY": 3, "CYCLIC": 4, "GHOST": 5, "FIXED": 6, "ROBIN": 7,
             "CALC_DIRICHLET": 6}

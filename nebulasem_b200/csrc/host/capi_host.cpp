@@ -3,6 +3,7 @@
 #include <stdexcept>
 #include <cstdio>
 #include <cmath>
+#include <algorithm>
 #include <cstring>
 
 #include "nsem_host.h"
@@ -246,6 +247,26 @@ int nsemh_peers(nsemh_solver* h, int* out, int cap) {
     for (int q = 0; q < (int)h->s.peers.size() && q < cap; q++) out[q] = h->s.peers[q];
     return (int)h->s.peers.size();
 }
+// Decompose the grid file <grid_noext>.{txt,bin} into nparts (Prepare::decomposeMesh, field.cpp:1086-1257) without
+// building a solver: part_out[cell] = rank, mortar_out[face] = gFMC in the grid's own face numbering (either may be
+// NULL).  Returns the number of cells, or -1 (message via nsemh_error) -- e.g. when a non-conforming face would be cut.
+int64_t nsemh_partition_grid(const char* grid_noext, int nparts, const char* method, int px, int py, int pz,
+                             uint32_t* part_out, uint32_t* mortar_out) {
+    try {
+        const Grid g = read_grid(grid_noext);
+        const std::vector<u32> fmc = mortar_flags(g);
+        const bool amr = std::any_of(fmc.begin(), fmc.end(), [](u32 v) { return v != 0; });
+        const int pxyz[3] = {px, py, pz};
+        const std::vector<u32> part = partition_cells(g, nparts, method ? method : "METIS", pxyz, amr ? &fmc : nullptr);
+        if (part_out) std::copy(part.begin(), part.end(), part_out);
+        if (mortar_out) std::copy(fmc.begin(), fmc.end(), mortar_out);
+        return (int64_t)g.nCells();
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
 void nsemh_totals(nsemh_solver* h, double out[3]) { out[0] = h->s.mass0; out[1] = h->s.energy0; out[2] = h->s.volume0; }
 
 }  // extern "C"

@@ -75,7 +75,9 @@ void EulerSolver::set_mesh(const Grid& g) {
 
 void EulerSolver::set_mesh_partition(const Grid& global, int rank_, int nranks_, const std::string& type, const int nxyz[3]) {
     rank = rank_; nranks = nranks_;
-    const std::vector<u32> part = partition_cells(global, nranks, type, nxyz);
+    const std::vector<u32> fmc = mortar_flags(global);
+    const bool amr = std::any_of(fmc.begin(), fmc.end(), [](u32 v) { return v != 0; });
+    const std::vector<u32> part = partition_cells(global, nranks, type, nxyz, amr ? &fmc : nullptr);
     Partition P = extract_partition(global, part, rank, nranks);
     if (P.cellGlobal.empty()) throw Error("partition " + std::to_string(rank) + " is empty");
     cellGlobal = P.cellGlobal;

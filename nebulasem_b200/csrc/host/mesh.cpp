@@ -507,6 +507,24 @@ void MeshTopo::remove_boundary(const std::vector<u32>& fs) {
         for (auto& f : kv.second) f = idf[f];
 }
 
+void MeshTopo::load_flags_only(const Grid& g) {
+    V = g.V;
+    facetStart = g.facetStart; facetVerts = g.facetVerts;
+    cellStart = g.cellStart; cellFaces = g.cellFaces;
+    boundaries = g.boundaries;
+    add_boundary_cells();
+    fix_hex_cells();
+}
+
+std::vector<u32> mortar_flags(const Grid& g) {
+    bool conforming = true;
+    for (u32 c = 0; c < g.nCells() && conforming; c++) conforming = (g.cellStart[c + 1] - g.cellStart[c] == 6);
+    if (conforming) return std::vector<u32>(g.nFacets(), 0);
+    MeshTopo t;
+    t.load_flags_only(g);
+    return t.FMC;
+}
+
 void MeshTopo::load(const Grid& g) {
     V = g.V;
     facetStart = g.facetStart; facetVerts = g.facetVerts;

@@ -77,7 +77,12 @@ Grid box_grid(const int n[3], const double lo[3], const double hi[3], const std:
               void (*vertex_map)(Vec3&, const void*) = nullptr, const void* map_arg = nullptr);
 
 // ---- domain decomposition (Prepare::decomposeMesh, field.cpp:1086-1257) --------------------------------------
-std::vector<u32> partition_cells(const Grid& g, int nparts, const std::string& method, const int nxyz[3]);
+// face_mortar (gFMC in the grid's own face numbering, or nullptr): METIS edge weight 1000 on non-conforming faces so that
+// AMR families stay together (field.cpp:1037-1047); any method that still cuts one is refused (field.cpp:1215-1220)
+std::vector<u32> partition_cells(const Grid& g, int nparts, const std::string& method, const int nxyz[3],
+                                 const std::vector<u32>* face_mortar = nullptr);
+// gFMC of a grid in its own face numbering (addBoundaryCells + fixHexCells only); all zero on a conforming grid
+std::vector<u32> mortar_flags(const Grid& g);
 struct Partition {
     Grid grid;                      // local grid with interMesh_<me>_<peer> patches
     std::vector<u32> cellGlobal;    // local real cell -> global cell
@@ -98,6 +103,7 @@ struct MeshTopo {
     u32 nFacets() const { return (u32)facetStart.size() - 1; }
     u32 nCells() const { return (u32)cellStart.size() - 1; }
     void load(const Grid& g);            // Mesh::LoadMesh
+    void load_flags_only(const Grid& g); // addBoundaryCells + fixHexCells: FOC/FNC/FMC in the grid's own numbering
     void hex_corners(const u32* f1, const u32* f2, u32 out[8]) const;   // quads only
     void hex_corners_poly(const std::vector<u32>& f1, const std::vector<u32>& f2, u32 out[8]) const;   // merged sides
     std::vector<u32> merged_side(u32 cell, u32 id) const;               // polygon of all facets of `cell` with local id `id`

@@ -36,7 +36,25 @@ static void face_cells(const Grid& g, std::vector<u32>& foc, std::vector<u32>& f
         }
 }
 
-std::vector<u32> partition_cells(const Grid& g, int nparts, const std::string& method, const int nxyz[3]) {
+static std::vector<u32> partition_cells_raw(const Grid& g, int nparts, const std::string& method, const int nxyz[3],
+                                            const std::vector<u32>* face_mortar);
+
+std::vector<u32> partition_cells(const Grid& g, int nparts, const std::string& method, const int nxyz[3],
+                                 const std::vector<u32>* face_mortar) {
+    std::vector<u32> part = partition_cells_raw(g, nparts, method, nxyz, face_mortar);
+    if (face_mortar && nparts > 1) {
+        // a non-conforming face must not be cut: both sides of a mortar are evaluated by one rank (field.cpp:1215-1220)
+        std::vector<u32> foc, fnc;
+        face_cells(g, foc, fnc);
+        for (u32 f = 0; f < g.nFacets(); f++)
+            if ((*face_mortar)[f] != 0 && fnc[f] != MAX_INT && part[foc[f]] != part[fnc[f]])
+                throw Error("decomposition cuts the non-conforming face " + std::to_string(f) + ": use METIS (edge weight 1000 on mortar faces) or fewer parts");
+    }
+    return part;
+}
+
+static std::vector<u32> partition_cells_raw(const Grid& g, int nparts, const std::string& method, const int nxyz[3],
+                                            const std::vector<u32>* face_mortar) {
     const u32 nc = g.nCells();
     std::vector<u32> part(nc, 0);
     if (nparts <= 1) return part;
@@ -78,9 +96,15 @@ std::vector<u32> partition_cells(const Grid& g, int nparts, const std::string& m
         for (u32 f = 0; f < g.nFacets(); f++)
             if (fnc[f] != MAX_INT) { deg[foc[f] + 1]++; deg[fnc[f] + 1]++; }
         for (u32 c = 0; c < nc; c++) deg[c + 1] += deg[c];
-        std::vector<int64_t> adj(deg[nc]), fill(deg.begin(), deg.end() - 1);
+        std::vector<int64_t> adj(deg[nc]), wgt(deg[nc], 1), fill(deg.begin(), deg.end() - 1);
+        bool weighted = false;
         for (u32 f = 0; f < g.nFacets(); f++)
-            if (fnc[f] != MAX_INT) { adj[fill[foc[f]]++] = fnc[f]; adj[fill[fnc[f]]++] = foc[f]; }
+            if (fnc[f] != MAX_INT) {
+                const int64_t w = (face_mortar && (*face_mortar)[f] != 0) ? 1000 : 1;     // field.cpp:1037-1047
+                weighted = weighted || w != 1;
+                wgt[fill[foc[f]]] = w; adj[fill[foc[f]]++] = fnc[f];
+                wgt[fill[fnc[f]]] = w; adj[fill[fnc[f]]++] = foc[f];
+            }
         int64_t opt[40];
         METIS_SetDefaultOptions(opt);
         opt[1] = 0;      // METIS_OPTION_OBJTYPE = METIS_OBJTYPE_CUT
@@ -91,7 +115,7 @@ std::vector<u32> partition_cells(const Grid& g, int nparts, const std::string& m
         opt[17] = 0;     // METIS_OPTION_NUMBERING: C style
         int64_t nv = nc, ncon = 1, np = nparts, cut = 0;
         std::vector<int64_t> p64(nc);
-        const int rc = METIS_PartGraphKway(&nv, &ncon, deg.data(), adj.data(), nullptr, nullptr, nullptr, &np, nullptr, nullptr, opt, &cut, p64.data());
+        const int rc = METIS_PartGraphKway(&nv, &ncon, deg.data(), adj.data(), nullptr, nullptr, weighted ? wgt.data() : nullptr, &np, nullptr, nullptr, opt, &cut, p64.data());
         if (rc != 1) throw Error("METIS_PartGraphKway failed with code " + std::to_string(rc));
         for (u32 c = 0; c < nc; c++) part[c] = (u32)p64[c];
         return part;

@@ -883,6 +883,8 @@ extern "C" int nsem_upload_mesh(nsem_ctx* c, const nsem_mesh* m) {
             static const int rm9[9] = {0, 4, 8, 1, 5, 2, 3, 7, 6};      // AoS component -> row-major a*3+d
             const char* mv = std::getenv("NSEM_METRICS");
             const bool want_tri = !(mv && std::strcmp(mv, "stored") == 0);
+            const char* av = std::getenv("NSEM_AFFINE");
+            const bool want_affine = !(av && std::strcmp(av, "0") == 0);
             const unsigned nth = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
             std::vector<int> bad(nth, 0);
             auto work = [&](unsigned t) {
@@ -947,7 +949,26 @@ extern "C" int nsem_upload_mesh(nsem_ctx* c, const nsem_mesh* m) {
                         const double want = m->cV[(size_t)e * NP + node];
                         if (!(std::fabs(cv - want) <= 1e-13 * std::fabs(want))) ok = false;
                     }
-                    if (!ok) bad[t] = 1;
+                    if (!ok) { bad[t] = 1; continue; }
+                    // parallelepiped (all mixed terms vanish): Jinv*cV = A * (w_i w_j w_k / 8) with one matrix per element
+                    if (want_affine) {
+                        double scale = 0, mixed = 0;
+                        for (int q = 0; q < 3; q++) for (int a = 0; a < 3; a++) scale = std::max(scale, std::fabs(R.c[q][a]));
+                        for (int q = 3; q < 7; q++) for (int a = 0; a < 3; a++) mixed = std::max(mixed, std::fabs(R.c[q][a]));
+                        if (mixed <= 1e-13 * scale) {
+                            double J[9], Cf[9];
+                            for (int a = 0; a < 3; a++) for (int d = 0; d < 3; d++) J[a * 3 + d] = R.c[d][a];
+                            for (int a = 0; a < 3; a++)
+                                for (int d = 0; d < 3; d++) {
+                                    const int a1 = (a + 1) % 3, a2 = (a + 2) % 3, d1 = (d + 1) % 3, d2 = (d + 2) % 3;
+                                    Cf[a * 3 + d] = J[a1 * 3 + d1] * J[a2 * 3 + d2] - J[a1 * 3 + d2] * J[a2 * 3 + d1];
+                                }
+                            const double det = J[0] * Cf[0] + J[1] * Cf[1] + J[2] * Cf[2];
+                            for (int q = 0; q < 9; q++) R.c[3 + q / 3][q % 3] = Cf[q] * (R.vol / det);
+                            for (int a = 0; a < 3; a++) R.c[6][a] = 0.0;
+                            R.face[0].meta |= FM_AFFINE;
+                        }
+                    }
                 }
             };
             {

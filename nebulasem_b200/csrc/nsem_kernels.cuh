@@ -41,6 +41,7 @@ constexpr uint32_t FM_OWNER = 8u;         // this element is the face's owner (g
 constexpr uint32_t FM_HALF = 16u;         // fI = 0.5 (interior / inter-rank); else fI = 0 (physical boundary)
 constexpr uint32_t FM_MORTAR = 32u;       // non-conforming (2:1) face: the finished surface contributions of this local face are in
                                           // the mortar buffers (nsem_mortar.cuh), block id in faceOther
+constexpr uint32_t FM_AFFINE = 64u;       // on face 0 of an ElemRec: the element is a parallelepiped; c[3..5] hold Jin / (w_i w_j w_k / 8)
 constexpr int MORTAR_NA = 13, MORTAR_NB = 4;   // values per face node: sweep A {r_rho, gU[9], gT[3]}, sweep B {r_U[3], r_theta}
 constexpr int MORTAR_MAXF = 64;                // face-node stride of a mortar block (MAXN * MAXN)
 
@@ -109,7 +110,9 @@ static_assert(sizeof(FaceRec) == 64, "FaceRec must be 64 bytes");
 // x(xi) = c000 + c100 xi + c010 eta + c001 zeta + c110 xi eta + c101 xi zeta + c011 eta zeta + c111 xi eta zeta, xi in [-1,1]^3
 struct alignas(16) ElemRec {
     FaceRec face[6];
-    double c[7][3];          // c100, c010, c001, c110, c101, c011, c111
+    double c[7][3];          // c100, c010, c001, c110, c101, c011, c111; on an AFFINE element (face[0].meta & FM_AFFINE) the three
+                             // mixed terms are zero and c[3..5] instead hold A[a*3+d] = cofactor(J)[a][d] * vol / det J, so that
+                             // Jinv*cV at node (i,j,k) is A * (w_i w_j w_k / 8) without the per-node cofactors and division
     double vol;              // element volume: cV[node] = vol * w_i w_j w_k / 8 (dg.cpp:315-318)
 };
 static_assert(sizeof(ElemRec) == 560, "ElemRec must be 560 bytes");

@@ -86,6 +86,19 @@ __device__ __forceinline__ void tri_metrics(const double* __restrict__ c, double
     for (int q = 0; q < 9; q++) Jin[q] = C[q] * sc;
 }
 
+// metrics of one node from the element record (rec + 48 = ElemRec::c): the closed trilinear form, or -- the branch is uniform over the
+// CTA -- the per-element constants of a parallelepiped (box meshes, the bulk of a terrain-following mesh away from the hill)
+__device__ __forceinline__ void elem_metrics(const double* __restrict__ rec, double x0, double x1, double x2, double wcv, double Jin[9], double& cV) {
+    const double* c = rec + 48;
+    if (reinterpret_cast<const FaceRec*>(rec)->meta & FM_AFFINE) {
+        cV = c[21] * wcv;
+#pragma unroll
+        for (int q = 0; q < 9; q++) Jin[q] = c[9 + q] * wcv;
+    } else {
+        tri_metrics(c, x0, x1, x2, wcv, Jin, cV);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // sweep A (v4): one thread per node (NT = NP rounded up to whole warps), no separate face tasks.  The neighbour values of
 // the 2(NX NY + NX NZ + NY NZ) face nodes are requested one element ahead with 8-byte cp.async (LDGSTS) into a
@@ -244,7 +257,7 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
             th = in[4 * NPS + nt] + P.T0;
             if (TRI) {
                 const double wcv = ((P.W[0][i] * P.W[1][j]) * P.W[2][k]) / 8;
-                tri_metrics(rec + 48, P.X[0][i], P.X[1][j], P.X[2][k], wcv, Jin, cV);
+                elem_metrics(rec, P.X[0][i], P.X[1][j], P.X[2][k], wcv, Jin, cV);
             } else {
                 cV = in[C::A_CV * NPS + nt];
 #pragma unroll
@@ -581,7 +594,7 @@ __global__ void __launch_bounds__((CfgB<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
             double Jin[9];
             if (TRI) {
                 const double wcv = ((P.W[0][i] * P.W[1][j]) * P.W[2][k]) / 8;
-                tri_metrics(rec + 48, P.X[0][i], P.X[1][j], P.X[2][k], wcv, Jin, cV);
+                elem_metrics(rec, P.X[0][i], P.X[1][j], P.X[2][k], wcv, Jin, cV);
             } else {
                 cV = in[A_CV * NPS + nt];
 #pragma unroll

@@ -13,12 +13,12 @@ import numpy as np
 
 from . import capi
 
-HOST_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libnsem_host.so")
+HOST_LIB_PATH = os.path.join(os.environ.get("NSEM_LIBDIR") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib"), "libnsem_host.so")
 HOST_EXPORTS = ["nsemh_error", "nsemh_close", "nsemh_open_case", "nsemh_synthetic", "nsemh_synthetic_part", "nsemh_patch_faces",
                 "nsemh_peers", "nsemh_diagnostics", "nsemh_attach", "nsemh_step",
                 "nsemh_upload", "nsemh_download", "nsemh_write", "nsemh_run", "nsemh_sync", "nsemh_time",
                 "nsemh_launch_count", "nsemh_kernel_info", "nsemh_set_schedule", "nsemh_dims", "nsemh_params", "nsemh_f64", "nsemh_u32",
-                "nsemh_state_ptr", "nsemh_totals"]
+                "nsemh_state_ptr", "nsemh_totals", "nsemh_partition_grid"]
 _lib = None
 
 
@@ -67,8 +67,25 @@ def load_host_library() -> C.CDLL:
     lib.nsemh_state_ptr.restype = C.POINTER(C.c_double)
     lib.nsemh_totals.argtypes = [vp, C.POINTER(C.c_double)]
     lib.nsemh_totals.restype = None
+    lib.nsemh_partition_grid.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint32),
+                                         C.POINTER(C.c_uint32)]
+    lib.nsemh_partition_grid.restype = C.c_int64
     _lib = lib
     return lib
+
+
+def partition_grid(grid_noext: str, n_cells: int, n_faces: int, nparts: int, method: str = "METIS", pxyz=(1, 1, 1)):
+    """Prepare::decomposeMesh's cell -> rank map for a grid file (METIS | XYZ | CELLID) and the grid's gFMC flags.
+    Raises when the decomposition would cut a non-conforming face (field.cpp:1215-1220)."""
+    lib = load_host_library()
+    part = np.zeros(n_cells, dtype=np.uint32)
+    fmc = np.zeros(n_faces, dtype=np.uint32)
+    n = lib.nsemh_partition_grid(os.fspath(grid_noext).encode(), nparts, method.encode(), int(pxyz[0]), int(pxyz[1]), int(pxyz[2]),
+                                 part.ctypes.data_as(C.POINTER(C.c_uint32)), fmc.ctypes.data_as(C.POINTER(C.c_uint32)))
+    if n < 0:
+        raise capi.NsemError(lib.nsemh_error(None).decode())
+    assert n == n_cells
+    return part, fmc
 
 
 class Solver:

@@ -69,6 +69,26 @@ def test_host_non_conforming_topology_bit_equal_to_oracle(tmp_path, fixture):
     s.close()
 
 
+def test_decomposition_keeps_mortar_faces_whole():
+    """METIS k-way with edge weight 1000 on non-conforming faces (field.cpp:1037-1047) never cuts one; a decomposition
+    that would (here: by cell index) is refused like the reference does (field.cpp:1215-1220)."""
+    from oracle import mesh as omesh
+    gp = os.path.join(ROOT, "tests", "golden", "srtb3d_amr", "grid_0")
+    g = refio.read_grid(gp)
+    t = omesh.MeshTopo(g).load()
+    nc, nf = len(g.cells), len(g.facets)
+    FOC, FNC = np.asarray(t.FOC), np.asarray(t.FNC)
+    for nparts in (2, 4):
+        part, fmc = host.partition_grid(gp, nc, nf, nparts, "METIS")
+        assert np.array_equal(fmc, np.asarray(t.FMC, dtype=np.uint32))       # 3-D: no face is deleted, numbering unchanged
+        m = np.nonzero(fmc)[0]
+        assert len(m) == 160 and not (part[FOC[m]] != part[FNC[m]]).any()
+        counts = np.bincount(part, minlength=nparts)
+        assert counts.min() > 0 and counts.max() <= 1.1 * nc / nparts
+    with pytest.raises(capi.NsemError, match="non-conforming face"):
+        host.partition_grid(gp, nc, nf, 2, "CELLID")
+
+
 def test_field_dump_written_in_the_reference_format(tmp_cases):
     orc = make_oracle(tmp_cases, "bubble3d", 1, exact=False, n=2, order=2)
     s = host.Solver.open_case(orc.case_dir)
