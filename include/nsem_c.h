@@ -103,7 +103,7 @@ typedef struct {
 
 /* ---- life cycle ------------------------------------------------------------------------------------ */
 /* MP::MP / MP::~MP (src/mp/mp.cpp:17-35): one context per rank/GPU. nccl_unique_id is the 128-byte
- * ncclUniqueId shared by all ranks (NULL when nranks == 1). */
+ * ncclUniqueId shared by all ranks (NULL when nranks == 1). device < 0 selects rank % (visible devices). */
 int nsem_create(int device, int rank, int nranks, const void* nccl_unique_id, nsem_ctx** out);
 void nsem_destroy(nsem_ctx* ctx);
 const char* nsem_last_error(const nsem_ctx* ctx);          /* ctx may be NULL: error of the last failed create */

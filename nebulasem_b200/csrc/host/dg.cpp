@@ -11,6 +11,7 @@
 // results are interchangeable.
 #include <cmath>
 #include <cstring>
+#include <string>
 
 #include "nsem_host.h"
 
@@ -260,6 +261,7 @@ void Geometry::build(const MeshTopo& t, const Basis& b) {
 
     // ---- node coordinates (dg.cpp:176-325) ----
     static const int sides[12][2] = {{0, 1}, {3, 2}, {7, 6}, {4, 5}, {0, 3}, {1, 2}, {5, 6}, {4, 7}, {0, 4}, {1, 5}, {2, 6}, {3, 7}};
+    std::string corner_error;      // an exception must not leave the parallel region
 #pragma omp parallel for schedule(static)
     for (int64_t cs = 0; cs < (int64_t)nBCS; cs++) {
         const u32 ci = (u32)cs;
@@ -285,7 +287,13 @@ void Geometry::build(const MeshTopo& t, const Basis& b) {
             t.hex_corners(f1, f2, vpi);
         } else {
             // non-conforming cell: the sub-facets of the two sides are merged first (dg.cpp:190-215)
-            t.hex_corners_poly(t.merged_side(ci, id0), t.merged_side(ci, id1), vpi);
+            try {
+                t.hex_corners_poly(t.merged_side(ci, id0), t.merged_side(ci, id1), vpi);
+            } catch (const std::exception& e) {
+#pragma omp critical
+                corner_error = e.what();
+                continue;
+            }
         }
         static const int ord2[8] = {0, 1, 5, 4, 3, 2, 6, 7}, ord4[8] = {0, 3, 7, 4, 1, 2, 6, 5};
         for (int q = 0; q < 8; q++) vidx[id0 == 2 ? ord2[q] : (id0 == 4 ? ord4[q] : q)] = vpi[q];
@@ -314,6 +322,8 @@ void Geometry::build(const MeshTopo& t, const Basis& b) {
                     cV[idx] *= wg[0][i] * wg[1][j] * wg[2][k] / 8;
                 }
     }
+
+    if (!corner_error.empty()) throw Error(corner_error);
 
     // ---- face node maps and weights (dg.cpp:328-410) ----
     const int face_map[6] = {0, NPZ - 1, 0, NPY - 1, 0, NPX - 1};

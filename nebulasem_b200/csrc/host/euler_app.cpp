@@ -9,6 +9,8 @@
 //   Iteration::next     src/solvers/iteration.h:62-84 (dump every write_interval steps)
 #include <algorithm>
 #include <cmath>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -57,6 +59,11 @@ void EulerSolver::read_controls(const std::string& case_dir) {
     buoyancy = ctl.yes("euler", "buoyancy", buoyancy);
     diffusion = ctl.yes("euler", "diffusion", diffusion);
     problem_init = ctl.str("euler", "problem_init", problem_init);
+    decomp_type = ctl.str("decomposition", "type", decomp_type);
+    {
+        const Vec3 n = ctl.vec("decomposition", "n", Vec3{1, 1, 1});
+        for (int d = 0; d < 3; d++) decomp_n[d] = std::max(1, (int)n[d]);
+    }
     if (ctl.str("general", "convection_scheme", "RUSANOV") != "RUSANOV")
         throw Error("only convection_scheme RUSANOV is implemented on the GPU path");
     // BDF1, AB1 and RK1..RK4 are the same single forward-Euler stage on this path (SURVEY finding 1)
@@ -75,6 +82,7 @@ void EulerSolver::set_mesh(const Grid& g) {
 
 void EulerSolver::set_mesh_partition(const Grid& global, int rank_, int nranks_, const std::string& type, const int nxyz[3]) {
     rank = rank_; nranks = nranks_;
+    nGlobalCells = global.nCells();
     const std::vector<u32> fmc = mortar_flags(global);
     const bool amr = std::any_of(fmc.begin(), fmc.end(), [](u32 v) { return v != 0; });
     const std::vector<u32> part = partition_cells(global, nranks, type, nxyz, amr ? &fmc : nullptr);
@@ -85,7 +93,13 @@ void EulerSolver::set_mesh_partition(const Grid& global, int rank_, int nranks_,
     set_mesh(P.grid);
 }
 
-void EulerSolver::load_mesh(int step) { set_mesh(read_grid(dir + "/" + meshName + "_" + std::to_string(step))); }
+void EulerSolver::load_mesh(int step) {
+    const Grid g = read_grid(dir + "/" + meshName + "_" + std::to_string(step));
+    // one process per partition: every rank decomposes the same global grid the same way (Prepare::decomposeMesh does it
+    // once on rank 0 and hands the parts over through grid<r>/ files, field.cpp:1086-1443) and keeps its own part
+    if (nranks > 1) set_mesh_partition(g, rank, nranks, decomp_type, decomp_n);
+    else { nGlobalCells = g.nCells(); set_mesh(g); }
+}
 
 // ---------------------------------------------------------------------------------------------------------
 std::vector<double> init_field(const FieldFile& ff, const Geometry& g, const Vec3& gravity) {
@@ -239,10 +253,28 @@ void EulerSolver::set_fields(const FieldFile& frho, const FieldFile& fU, const F
     apply_bcs(rho, 1, bc_rho);
 }
 
+// raw node values of a field file are in the GLOBAL real-cell order: keep this partition's cells
+static FieldFile localize(FieldFile ff, const std::vector<u32>& cellGlobal, u32 nGlobalCells, int NP) {
+    if (ff.values.empty()) return ff;
+    const size_t per = (size_t)NP * ff.comps;
+    if (ff.values.size() < (size_t)nGlobalCells * per) throw Error("field file holds fewer node values than the global grid has nodes");
+    std::vector<double> v(cellGlobal.size() * per);
+    for (size_t l = 0; l < cellGlobal.size(); l++)
+        std::copy(ff.values.begin() + (size_t)cellGlobal[l] * per, ff.values.begin() + ((size_t)cellGlobal[l] + 1) * per, v.begin() + l * per);
+    ff.values.swap(v);
+    return ff;
+}
+
 void EulerSolver::read_fields(int step) {
     const std::string s = std::to_string(step);
-    set_fields(read_field(dir + "/rho" + s, 1), read_field(dir + "/U" + s, 3), read_field(dir + "/T" + s, 1),
-               read_field(dir + "/p" + s, 1));
+    FieldFile frho = read_field(dir + "/rho" + s, 1), fU = read_field(dir + "/U" + s, 3), fT = read_field(dir + "/T" + s, 1),
+              fp = read_field(dir + "/p" + s, 1);
+    if (nranks > 1) {
+        const int NP = Basis(nop).NP;
+        frho = localize(frho, cellGlobal, nGlobalCells, NP); fU = localize(fU, cellGlobal, nGlobalCells, NP);
+        fT = localize(fT, cellGlobal, nGlobalCells, NP); fp = localize(fp, cellGlobal, nGlobalCells, NP);
+    }
+    set_fields(frho, fU, fT, fp);
 }
 
 static std::vector<BCond> scale_bcs(const std::vector<BCond>& src) {
@@ -459,10 +491,60 @@ void EulerSolver::download() {
 void EulerSolver::write_fields(int index) {
     const std::string s = std::to_string(index);
     const uint64_t n = geo.gBCSfield;
-    write_field(dir + "/rho" + s, binary_out, 1, rho.data(), n, bc_rho);
-    write_field(dir + "/U" + s, binary_out, 3, U.data(), n, bc_U);
-    write_field(dir + "/T" + s, binary_out, 1, T.data(), n, bc_T);
-    write_field(dir + "/p" + s, binary_out, 1, p.data(), n, bc_p);
+    std::string out = dir;
+    if (nranks > 1) {
+        out = dir + "/grid" + std::to_string(rank);
+        ::mkdir(out.c_str(), 0777);
+    }
+    write_field(out + "/rho" + s, binary_out, 1, rho.data(), n, bc_rho);
+    write_field(out + "/U" + s, binary_out, 3, U.data(), n, bc_U);
+    write_field(out + "/T" + s, binary_out, 1, T.data(), n, bc_T);
+    write_field(out + "/p" + s, binary_out, 1, p.data(), n, bc_p);
+    if (nranks > 1) {
+        // local real cell -> global cell, then the marker rank 0's merge waits for (written last, renamed into place)
+        FILE* f = std::fopen((out + "/cells" + s + ".tmp").c_str(), "wb");
+        if (!f) throw Error("cannot write " + out + "/cells" + s);
+        const u32 nc = (u32)cellGlobal.size();
+        std::fwrite(&nc, sizeof nc, 1, f);
+        std::fwrite(cellGlobal.data(), sizeof(u32), nc, f);
+        std::fclose(f);
+        if (std::rename((out + "/cells" + s + ".tmp").c_str(), (out + "/cells" + s).c_str()) != 0) throw Error("cannot rename the cell map in " + out);
+    }
+}
+
+void EulerSolver::merge_fields(int index) {
+    if (nranks <= 1 || rank != 0) return;
+    const std::string s = std::to_string(index);
+    const int NP = Basis(nop).NP;
+    const char* names[4] = {"rho", "U", "T", "p"};
+    const int comps[4] = {1, 3, 1, 1};
+    const std::vector<BCond>* bcs[4] = {&bc_rho, &bc_U, &bc_T, &bc_p};
+    std::vector<std::vector<u32>> maps(nranks);
+    for (int r = 0; r < nranks; r++) {
+        const std::string path = dir + "/grid" + std::to_string(r) + "/cells" + s;
+        FILE* f = nullptr;
+        for (int tries = 0; tries < 6000 && !(f = std::fopen(path.c_str(), "rb")); tries++) ::usleep(100000);   // <= 10 min
+        if (!f) throw Error("merge: rank " + std::to_string(r) + " never wrote " + path);
+        u32 nc = 0;
+        if (std::fread(&nc, sizeof nc, 1, f) != 1) { std::fclose(f); throw Error("merge: short read of " + path); }
+        maps[r].resize(nc);
+        const size_t got = std::fread(maps[r].data(), sizeof(u32), nc, f);
+        std::fclose(f);
+        if (got != nc) throw Error("merge: short read of " + path);
+    }
+    for (int q = 0; q < 4; q++) {
+        const size_t per = (size_t)NP * comps[q];
+        std::vector<double> all((size_t)nGlobalCells * per, 0.0);
+        for (int r = 0; r < nranks; r++) {
+            const FieldFile ff = read_field(dir + "/grid" + std::to_string(r) + "/" + names[q] + s, comps[q]);
+            if (ff.values.size() < maps[r].size() * per) throw Error(std::string("merge: ") + names[q] + s + " of rank " + std::to_string(r) + " is too short");
+            for (size_t l = 0; l < maps[r].size(); l++)
+                std::copy(ff.values.begin() + l * per, ff.values.begin() + (l + 1) * per, all.begin() + (size_t)maps[r][l] * per);
+        }
+        std::vector<BCond> gb;      // the physical patches; the interMesh_* GHOST conditions exist only inside a partition
+        for (const auto& b : *bcs[q]) if (b.type != "GHOST") gb.push_back(b);
+        write_field(dir + "/" + names[q] + s, binary_out, comps[q], all.data(), (uint64_t)nGlobalCells * NP, gb);
+    }
 }
 
 void EulerSolver::run() {
@@ -476,7 +558,8 @@ void EulerSolver::run() {
         if (upto % write_interval == 0) {
             download();
             write_fields((int)(upto / write_interval));
-            std::printf("Time %f : wrote fields %ld\n", upto * dt, upto / write_interval);
+            merge_fields((int)(upto / write_interval));
+            if (rank == 0) std::printf("Time %f : wrote fields %ld\n", upto * dt, upto / write_interval);
         }
     }
     if (nsem_sync(ctx)) throw Error(nsem_last_error(ctx));

@@ -1,18 +1,67 @@
 // euler_main.cpp -- `euler ./controls`: drop-in for the reference solver binary (apps/euler/euler.cpp:296-302).
 // Reads the same controls / grid / field files from the current directory, runs the time loop on the GPU through
-// the C ABI and writes the same rho/U/T/p<k>.{bin,txt} dumps.  One process per GPU/partition.
+// the C ABI and writes the same rho/U/T/p<k>.{bin,txt} dumps.
+//
+// One process per GPU/partition, launched the way the reference is (`mpirun -np N euler ./controls`, test.sh) or by
+// any launcher that exports a rank and a world size: this binary links no MPI, it reads the launcher's environment
+// (OMPI_COMM_WORLD_RANK/SIZE, PMI_RANK/SIZE, SLURM_PROCID/NTASKS, torchrun's RANK/WORLD_SIZE, or NSEM_RANK/NSEM_WORLD).
+// Every rank decomposes the global grid identically (decomposition{type n}, METIS by default) and keeps its part; the
+// ncclUniqueId travels from rank 0 to the others through a file in the case directory (the reference hands its
+// partitions over through the file system too, field.cpp:1086-1443); fields are dumped per rank into grid<r>/ and merged
+// by rank 0 into the case directory in global node order (Prepare::mergeFields).
+//   NSEM_DEVICE   device index (default: local rank, else rank % visible devices)
+//   NSEM_DRYRUN=k (k >= 1) set-up only, no GPU: decompose, read and initialise the fields, dump them as index k
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <string>
 
 #include "nsem_host.h"
+
+static bool env_int(const char* name, int& out) {
+    const char* v = std::getenv(name);
+    if (!v || !*v) return false;
+    out = std::atoi(v);
+    return true;
+}
+
+// rank 0 publishes the 128-byte ncclUniqueId, the others wait for a file younger than their own start
+static void share_unique_id(const std::string& dir, int rank, unsigned char id[128]) {
+    const std::string path = dir + "/.nsem_nccl_id", tmp = path + ".tmp";
+    if (rank == 0) {
+        if (nsem_get_unique_id(id)) throw nsemh::Error(nsem_last_error(nullptr));
+        FILE* f = std::fopen(tmp.c_str(), "wb");
+        if (!f || std::fwrite(id, 1, 128, f) != 128) throw nsemh::Error("cannot write " + tmp);
+        std::fclose(f);
+        if (std::rename(tmp.c_str(), path.c_str()) != 0) throw nsemh::Error("cannot publish " + path);
+        return;
+    }
+    const time_t t0 = std::time(nullptr);
+    for (int tries = 0; tries < 3000; tries++) {                  // <= 5 min
+        struct stat st;
+        if (::stat(path.c_str(), &st) == 0 && st.st_size == 128 && st.st_mtime >= t0 - 30) {
+            FILE* f = std::fopen(path.c_str(), "rb");
+            if (f) {
+                const size_t got = std::fread(id, 1, 128, f);
+                std::fclose(f);
+                if (got == 128) return;
+            }
+        }
+        ::usleep(100000);
+    }
+    throw nsemh::Error("rank " + std::to_string(rank) + ": rank 0 never published " + path);
+}
 
 int main(int argc, char* argv[]) {
     if (argc < 2 || !std::strcmp(argv[1], "-h")) {
         std::printf("Usage:\n  %s <inputfile>\nOptions:\n  -h          --  Display this message\n\n", argv[0]);
         return argc < 2 ? 1 : 0;
     }
+    int rank = 0, world = 1, local = -1;
     try {
         nsemh::EulerSolver s;
         std::string ctl = argv[1];
@@ -23,18 +72,35 @@ int main(int argc, char* argv[]) {
             std::fprintf(stderr, "euler: the input file must be named `controls`\n");
             return 1;
         }
+        if (!(env_int("NSEM_RANK", rank) && env_int("NSEM_WORLD", world)) &&
+            !(env_int("OMPI_COMM_WORLD_RANK", rank) && env_int("OMPI_COMM_WORLD_SIZE", world)) &&
+            !(env_int("PMI_RANK", rank) && env_int("PMI_SIZE", world)) &&
+            !(env_int("SLURM_PROCID", rank) && env_int("SLURM_NTASKS", world)) &&
+            !(env_int("RANK", rank) && env_int("WORLD_SIZE", world))) { rank = 0; world = 1; }
+        if (world < 1 || rank < 0 || rank >= world) throw nsemh::Error("inconsistent rank/world size in the environment");
+        if (!env_int("NSEM_DEVICE", local) && !env_int("OMPI_COMM_WORLD_LOCAL_RANK", local) && !env_int("LOCAL_RANK", local) &&
+            !env_int("SLURM_LOCALID", local)) local = -1;                     // -1: rank % visible devices (nsem_create)
+        s.rank = rank; s.nranks = world;
         s.read_controls(dir);
         const int step = (int)(s.start_step / s.write_interval);
         s.load_mesh(step);
         s.read_fields(step);
         s.setup();
-        const char* dev = std::getenv("NSEM_DEVICE");
-        s.attach_device(dev ? std::atoi(dev) : 0);
-        s.run();
-        std::printf("Exiting application run with 1 processes\n");
+        const char* dry = std::getenv("NSEM_DRYRUN");
+        if (dry && std::atoi(dry) > 0) {
+            s.write_fields(std::atoi(dry));
+            s.merge_fields(std::atoi(dry));
+        } else {
+            unsigned char id[128];
+            if (world > 1) share_unique_id(dir, rank, id);
+            s.attach_device(world > 1 ? local : (local < 0 ? 0 : local), rank, world, world > 1 ? id : nullptr);
+            s.run();
+            if (rank == 0 && world > 1) ::unlink((dir + "/.nsem_nccl_id").c_str());
+        }
+        if (rank == 0) std::printf("Exiting application run with %d processes\n", world);
         return 0;
     } catch (const std::exception& e) {
-        std::fprintf(stderr, "euler: %s\n", e.what());
+        std::fprintf(stderr, "euler[%d/%d]: %s\n", rank, world, e.what());
         return 1;
     }
 }

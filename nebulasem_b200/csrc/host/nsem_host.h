@@ -171,6 +171,9 @@ struct EulerSolver {
     bool buoyancy = true, diffusion = true, binary_out = true;
     std::string time_scheme = "BDF1", problem_init = "NONE";
     long start_step = 0, end_step = 2, write_interval = 20;
+    // decomposition{type n} (field.cpp:486-492): METIS | XYZ (n = parts per axis) | CELLID
+    std::string decomp_type = "METIS";
+    int decomp_n[3] = {1, 1, 1};
 
     MeshTopo topo;
     Geometry geo;
@@ -187,6 +190,7 @@ struct EulerSolver {
     // decompose `global` into nranks parts (type METIS | XYZ | CELLID) and keep part `rank` (decomposeMesh)
     void set_mesh_partition(const Grid& global, int rank, int nranks, const std::string& type, const int nxyz[3]);
     int rank = 0, nranks = 1;
+    u32 nGlobalCells = 0;                                 // real cells of the undecomposed grid
     std::vector<u32> cellGlobal;                          // local real cell -> global cell (identity on 1 rank)
     std::vector<int> peers;
     void exchange_setup_halos();                          // the applyExplicitBCs(...,true) halos of euler.cpp:105-146
@@ -197,7 +201,10 @@ struct EulerSolver {
     void upload_state();
     void step(int n);                                     // time-loop body on the GPU
     void download();
-    void write_fields(int index);                         // Mesh::write_fields
+    void write_fields(int index);                         // Mesh::write_fields; with nranks > 1 into <case>/grid<rank>/ like the
+                                                          // reference's per-rank working directories (field.cpp:1436-1440)
+    void merge_fields(int index);                         // rank 0: grid<r>/<field><index> of all ranks -> <case>/<field><index>
+                                                          // in global node order (Prepare::mergeFields, field.cpp:1446-1496)
     void run();                                           // Iteration loop: steps + dumps every write_interval
 
     void apply_bcs(std::vector<double>& f, int comps, std::vector<BCond>& bcs);   // applyExplicitBCs on the host

@@ -424,7 +424,8 @@ extern "C" int nsem_create(int device, int rank, int nranks, const void* nccl_un
         g_create_error = std::string("nsem_create: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback";
         return 1;
     }
-    if (device < 0 || device >= ndev) {
+    if (device < 0) device = rank % ndev;      // one process per GPU of the node, ranks round-robin over the visible devices
+    if (device >= ndev) {
         g_create_error = "nsem_create: device index out of range";
         return 1;
     }

@@ -1,0 +1,94 @@
+"""The drop-in `euler ./controls` binary (nebulasem_b200/csrc/host/euler_main.cpp), one process per partition.
+
+CPU part (NSEM_DRYRUN: set-up only, no GPU): N processes decompose the same case, read their share of the field files,
+dump per rank into grid<r>/ and rank 0 merges -- the merged dump must be bit-equal to the single-process dump.
+GPU part: the binary against the oracle on one GPU, and 2 processes == 1 process on two GPUs."""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from nebulasem_b200 import build
+from oracle import case as ocase
+from oracle import cases as ocases
+from oracle import refio
+from tests.helpers import conserved_errors
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run_euler(case_dir, world, dry=None, timeout=600):
+    procs = []
+    for r in range(world):
+        env = dict(os.environ)
+        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "OMPI_COMM_WORLD_RANK", "PMI_RANK", "SLURM_PROCID"):
+            env.pop(k, None)
+        if dry is not None:
+            env["NSEM_DRYRUN"] = str(dry)
+        if world > 1:
+            env.update(NSEM_RANK=str(r), NSEM_WORLD=str(world))
+        procs.append(subprocess.Popen([build.EULER_BIN, "./controls"], cwd=case_dir, env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE, text=True))
+    for p in procs:
+        out, err = p.communicate(timeout=timeout)
+        assert p.returncode == 0, (out[-1500:], err[-1500:])
+
+
+def make_case(tmp_path, name):
+    a = str(tmp_path / (name + "_1"))
+    if name.endswith("_amr"):
+        shutil.copytree(os.path.join(ROOT, "tests", "golden", name), a)
+        os.remove(os.path.join(a, "expected.npz"))
+    else:
+        ocases.CASES[name](n=4, order=2).write(a, 5)
+    return a
+
+
+@pytest.mark.parametrize("name,world", [("bubble3d", 2), ("bubble3d", 3), ("srtb3d_amr", 2)])
+def test_partitioned_setup_merges_to_the_single_process_fields(tmp_path, name, world):
+    a = make_case(tmp_path, name)
+    b = str(tmp_path / (name + "_n"))
+    shutil.copytree(a, b)
+    run_euler(a, 1, dry=7)
+    run_euler(b, world, dry=7)
+    for f in ("rho7", "U7", "T7", "p7"):
+        va, vb = refio.read_field_values(os.path.join(a, f)), refio.read_field_values(os.path.join(b, f))
+        assert va.shape == vb.shape and np.array_equal(va, vb), f
+        fa, fb = refio.read_field(os.path.join(a, f)), refio.read_field(os.path.join(b, f))
+        assert [(x.patch, x.kind) for x in fa.bcs] == [(x.patch, x.kind) for x in fb.bcs]       # no interMesh_* patch in the merged file
+    assert sorted(d for d in os.listdir(b) if d.startswith("grid") and os.path.isdir(os.path.join(b, d))) == [f"grid{r}" for r in range(world)]
+
+
+@pytest.mark.gpu
+def test_euler_binary_matches_oracle(tmp_path):
+    """`euler ./controls` on one GPU: 5 steps of the 4^3 order-2 bubble, dump 1 against the oracle."""
+    a = make_case(tmp_path, "bubble3d")
+    orc = ocase.load_case(a, exact_order=False)
+    run_euler(a, 1)
+    orc.run(5)
+    rho, U, T = (refio.read_field_values(os.path.join(a, f + "1")) for f in ("rho", "U", "T"))
+    assert rho.shape[0] == orc.gB                       # dumps hold the real nodes
+    err = conserved_errors(orc, rho[:, 0], U, T[:, 0])
+    print(err)
+    assert err["rho"] <= 1e-11 and err["rhoTheta"] <= 1e-11 and err["rhoU_scaled"] <= 1e-11
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["bubble3d", "srtb3d_amr"])
+def test_two_processes_equal_one_process(tmp_path, name):
+    """Two `euler` processes (METIS halves, NCCL halo, id through the case directory) write the same merged dump as one
+    process, bit for bit -- also on the non-conforming mesh, whose mortar faces the decomposition keeps whole."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    a = make_case(tmp_path, name)
+    b = str(tmp_path / (name + "_n"))
+    shutil.copytree(a, b)
+    run_euler(a, 1)
+    run_euler(b, 2)
+    idx = 1
+    for f in ("rho", "U", "T", "p"):
+        va, vb = refio.read_field_values(os.path.join(a, f + str(idx))), refio.read_field_values(os.path.join(b, f + str(idx)))
+        assert va.shape == vb.shape and np.array_equal(va, vb), f
