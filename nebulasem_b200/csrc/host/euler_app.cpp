@@ -71,6 +71,12 @@ void EulerSolver::read_controls(const std::string& case_dir) {
     if (!(ts == "BDF1" || ts == "AB1" || ts == "RK1" || ts == "RK2" || ts == "RK3" || ts == "RK4"))
         throw Error("time_scheme " + ts + " is not implemented on the GPU path (BDF1, AB1, RK1-RK4 are)");
     if (ctl.yes("general", "is_spherical", false)) throw Error("spherical meshes are not implemented on the GPU path");
+    // AmrIteration (iteration.h:94-147) regrids before step 1 and every amr_step dumps; that pipeline (Prepare::refineMesh, MeshObject::refineMesh,
+    // refineField) is not part of this build, which RUNS on non-conforming grids but does not create them: refuse instead of silently
+    // computing on the unrefined grid
+    if (ctl.integer("general", "amr_step", 0) != 0 && !std::getenv("NSEM_IGNORE_AMR_STEP"))
+        throw Error("controls ask for adaptive regridding (amr_step): the regrid is not implemented on the GPU path; remove amr_step to run on "
+                    "the grid as it is (grids the reference has already refined are supported), or set NSEM_IGNORE_AMR_STEP=1");
     if (ctl.str("general", "state", "STEADY") != "TRANSIENT") throw Error("state must be TRANSIENT");
 }
 

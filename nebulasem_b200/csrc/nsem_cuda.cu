@@ -299,11 +299,18 @@ struct Launch {
     // ---- v4: persistent, software-pipelined (cubic 3-D orders) ----
     static constexpr bool has_v4 = (NX == NY && NY == NZ && NX > 1) && v4::CfgB<NX, NY, NZ, true, false>::smem <= 227 * 1024 &&
                                    v4::CfgA<NX, NY, NZ, true, false>::smem <= 227 * 1024 && v4::CfgA<NX, NY, NZ, true, false>::ok;
+    // shared-memory carve-out of the v4 sweeps: all of it by default; NSEM_V4_CARVEOUT_A / _B (percent of the 228 KB) leave more L1 to the
+    // 8-byte neighbour gathers and the stores when the resident CTAs need less (sweep A: 4 x 41 KB = 72 %)
+    static int carveout(const char* var) {
+        const char* v = std::getenv(var);
+        const int pct = v ? std::atoi(v) : 0;
+        return (pct > 0 && pct <= 100) ? pct : (int)cudaSharedmemCarveoutMaxShared;
+    }
     template <class K>
-    static cudaError_t go4(K kernel, size_t smem, int nt, int minb, const KParams& P, int sms, cudaStream_t s) {
+    static cudaError_t go4(K kernel, size_t smem, int nt, int minb, const KParams& P, int sms, cudaStream_t s, const char* carve_var) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout(carve_var));
         if (e != cudaSuccess) return e;
         const uint64_t want = (uint64_t)sms * (uint64_t)minb;
         const unsigned grid = (unsigned)std::min<uint64_t>(P.nB, want);
@@ -315,13 +322,15 @@ struct Launch {
     static cudaError_t sweepA4t(const KParams& P, int sms, cudaStream_t s) {
         using C4 = v4::CfgA<NX, NY, NZ, VISC, TRI>;
         constexpr int MB = C4::minb(NSEM_V4_REGS_A);
-        return go4(v4::sweepA_v4<NX, NY, NZ, VISC, TRI, MB>, C4::smem, C4::NT, MB, P, sms, s);
+        if (P.mortarA) return go4(v4::sweepA_v4<NX, NY, NZ, VISC, TRI, MB, true>, C4::smem, C4::NT, MB, P, sms, s, "NSEM_V4_CARVEOUT_A");     // non-conforming mesh
+        return go4(v4::sweepA_v4<NX, NY, NZ, VISC, TRI, MB>, C4::smem, C4::NT, MB, P, sms, s, "NSEM_V4_CARVEOUT_A");
     }
     template <bool VISC, bool TRI>
     static cudaError_t sweepB4t(const KParams& P, int sms, cudaStream_t s) {
         using C4 = v4::CfgB<NX, NY, NZ, VISC, TRI>;
         constexpr int MB = C4::minb(NSEM_V4_REGS_B);
-        return go4(v4::sweepB_v4<NX, NY, NZ, VISC, TRI, MB>, C4::smem, C4::NT, MB, P, sms, s);
+        if (P.mortarB) return go4(v4::sweepB_v4<NX, NY, NZ, VISC, TRI, MB, true>, C4::smem, C4::NT, MB, P, sms, s, "NSEM_V4_CARVEOUT_B");
+        return go4(v4::sweepB_v4<NX, NY, NZ, VISC, TRI, MB>, C4::smem, C4::NT, MB, P, sms, s, "NSEM_V4_CARVEOUT_B");
     }
     static cudaError_t sweepA4(const KParams& P, bool tri, int sms, cudaStream_t s) {
         if constexpr (has_v4) {
@@ -512,6 +521,9 @@ extern "C" int nsem_get_unique_id(void* out128) {
 extern "C" uint64_t nsem_launch_count(const nsem_ctx* c) { return c->launches; }
 
 extern "C" const char* nsem_kernel_info(const nsem_ctx* c) {
+    if (c->use_v4 && c->nMortarGroups)
+        return c->tri ? "v4 persistent pipelined, metrics on the fly (trilinear map verified) + mortar (non-conforming) face kernels"
+                      : "v4 persistent pipelined, stored metrics + mortar (non-conforming) face kernels";
     if (c->use_v4) return c->tri ? "v4 persistent pipelined, metrics on the fly (trilinear map verified)" : "v4 persistent pipelined, stored metrics";
     if (c->use_v3) return "v3 warp per element";
     if (c->use_v2) return "v2 bulk-async staged";
@@ -642,10 +654,15 @@ extern "C" int nsem_upload_mesh(nsem_ctx* c, const nsem_mesh* m) {
         for (int q = 0; q < 6; q++) have = have && m->psi_ref[q] && m->psi_cor[q];
         if (!have) { c->err = "nsem_upload_mesh: a non-conforming mesh needs cC, face_center, psi_ref and psi_cor"; return 1; }
     }
-    // the element sweeps that know the FM_MORTAR branch are the plain-load ones (v1)
-    c->use_v2 = c->pref_v2 && !anyMortar;
-    c->use_v3 = c->pref_v3 && !anyMortar;
-    c->use_v4 = c->pref_v4 && !anyMortar;
+    // the element sweeps that know the FM_MORTAR branch: the persistent ones (v4, cubic 3-D orders; NSEM_MORTAR_V1=1 keeps them off) and
+    // the plain-load ones (v1, every order)
+    {
+        const char* mv1 = std::getenv("NSEM_MORTAR_V1");
+        const bool v4ok = !(mv1 && std::strcmp(mv1, "1") == 0);
+        c->use_v2 = c->pref_v2 && !anyMortar;
+        c->use_v3 = c->pref_v3 && !anyMortar;
+        c->use_v4 = c->pref_v4 && (!anyMortar || v4ok);
+    }
     std::vector<MortarGroup> mGroups;
     std::vector<std::vector<MortarSub>> mSubs;          // per group, in the coarse cell's face order
     std::vector<int32_t> mBlock(anyMortar ? (size_t)nB * 6 : 0, -1), mGroupOf(anyMortar ? (size_t)nB * 6 : 0, -1);

@@ -144,7 +144,9 @@ __device__ __forceinline__ int fresh_tid() {
     return t;
 }
 
-template <int NX, int NY, int NZ, bool VISC, bool TRI, int MINB>
+// MORTAR: the mesh has non-conforming faces (FM_MORTAR): such a face takes its finished surface terms from the mortar buffers
+// (nsem_mortar.cuh) instead of a two-point flux.  A separate instantiation, so conforming meshes run exactly the code they ran before.
+template <int NX, int NY, int NZ, bool VISC, bool TRI, int MINB, bool MORTAR = false>
 __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweepA_v4(const __grid_constant__ KParams P) {
     using C = CfgA<NX, NY, NZ, VISC, TRI>;
     using Tk = Tasks<NX, NY, NZ>;
@@ -191,6 +193,7 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
                 Tk::decode(task, fs, fa, fb);
                 const FaceRec* fr = reinterpret_cast<const FaceRec*>(sRec + slot * RECD) + fs;
                 const uint32_t other = fr->other, fid = fr->meta & FM_FID_MASK;
+                if (MORTAR && (fr->meta & FM_MORTAR)) continue;          // `other` is a mortar block id there, nothing to gather
                 const int fslot = (fs < 2) ? fa * NY + fb : fa * NZ + fb;
                 const size_t oidx = (size_t)other + (fid == FM_GHOST ? fslot : face_node<NX, NY, NZ>(fid, fa, fb));
                 double* g = sG + buf * 5 * NFTP + task;
@@ -330,6 +333,19 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
                     const double fw = (ax == 0) ? wi * wj / 4 : (ax == 1 ? wi * wk / 4 : wj * wk / 4);      // face_weight()
                     const FaceRec* fr = reinterpret_cast<const FaceRec*>(rec) + s;
                     const uint32_t meta = fr->meta;
+                    if (MORTAR && (meta & FM_MORTAR)) {
+                        // non-conforming face: mortarA_kernel left this node's surface terms (scatter/gather_non_conforming, field.h:2019-2248)
+                        const int mslot = (ax == 0) ? i * NY + j : (ax == 1 ? i * NZ + k : j * NZ + k);
+                        const double* mc = P.mortarA + (size_t)fr->other * (MORTAR_NA * MORTAR_MAXF) + mslot;
+                        r_rho += mc[0];
+                        if (VISC) {
+#pragma unroll
+                            for (int c = 0; c < 9; c++) gU[c] += mc[(1 + c) * MORTAR_MAXF];
+#pragma unroll
+                            for (int c = 0; c < 3; c++) gT[c] += mc[(10 + c) * MORTAR_MAXF];
+                        }
+                        continue;
+                    }
                     const double xr = gx[0 * NFTP + ti], xu0 = gx[1 * NFTP + ti], xu1 = gx[2 * NFTP + ti], xu2 = gx[3 * NFTP + ti];
                     const double xth = gx[4 * NFTP + ti] + P.T0;
                     // written for "my side" / "other side": with fI in {0, 1/2} this is bitwise cds() = fI*owner + (1-fI)*neighbour
@@ -453,7 +469,7 @@ struct CfgB {
     }
 };
 
-template <int NX, int NY, int NZ, bool VISC, bool TRI, int MINB>
+template <int NX, int NY, int NZ, bool VISC, bool TRI, int MINB, bool MORTAR = false>
 __global__ void __launch_bounds__((CfgB<NX, NY, NZ, VISC, TRI>::NT), MINB) sweepB_v4(const __grid_constant__ KParams P) {
     using C = CfgB<NX, NY, NZ, VISC, TRI>;
     constexpr int NP = C::NP, NPS = C::NPS, NT = C::NT, NIN = C::NIN, TBS = C::TBS, NPF = C::NPF, NISS = C::NISS;
@@ -568,6 +584,14 @@ __global__ void __launch_bounds__((CfgB<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
                     const FaceRec* fr = reinterpret_cast<const FaceRec*>(rec) + s;
                     const uint32_t meta = fr->meta;
                     const uint32_t fid = meta & FM_FID_MASK;
+                    if (MORTAR && (meta & FM_MORTAR)) {
+                        // non-conforming face: mortarB_kernel left this node's momentum and theta fluxes
+                        const int mslot = (ax == 0) ? fa * NY + fb : fa * NZ + fb;
+                        const double* mc = P.mortarB + (size_t)fr->other * (MORTAR_NB * MORTAR_MAXF) + mslot;
+#pragma unroll
+                        for (int c = 0; c < 4; c++) rf[c] += mc[c * MORTAR_MAXF];
+                        continue;
+                    }
                     const bool own = meta & FM_OWNER;
                     const double al = (meta & FM_HALF) ? 0.5 : 0.0;
                     const double N[3] = {fr->vec[0] * fw, fr->vec[1] * fw, fr->vec[2] * fw};

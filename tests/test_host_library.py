@@ -121,6 +121,14 @@ def test_errors_are_reported_not_swallowed(tmp_cases):
     s = host.Solver.open_case(orc.case_dir)
     with pytest.raises(capi.NsemError, match="no device attached|no CPU fallback"):
         s.step(1)        # the hot path has no CPU fallback
+    # adaptive regridding (AmrIteration, iteration.h:94-147) is not part of this build: asked for, it is refused, not skipped
+    import shutil
+    amr = os.path.join(str(tmp_cases), "asks_for_amr")
+    shutil.copytree(orc.case_dir, amr)
+    txt = open(os.path.join(amr, "controls")).read().replace("end_step", "amr_step 1\n    end_step", 1)
+    open(os.path.join(amr, "controls"), "w").write(txt)
+    with pytest.raises(capi.NsemError, match="amr_step"):
+        host.Solver.open_case(amr)
 
 
 def test_c_abi_exports_every_declared_symbol():
