@@ -299,18 +299,24 @@ struct Launch {
     // ---- v4: persistent, software-pipelined (cubic 3-D orders) ----
     static constexpr bool has_v4 = (NX == NY && NY == NZ && NX > 1) && v4::CfgB<NX, NY, NZ, true, false>::smem <= 227 * 1024 &&
                                    v4::CfgA<NX, NY, NZ, true, false>::smem <= 227 * 1024 && v4::CfgA<NX, NY, NZ, true, false>::ok;
-    // shared-memory carve-out of the v4 sweeps: all of it by default; NSEM_V4_CARVEOUT_A / _B (percent of the 228 KB) leave more L1 to the
-    // 8-byte neighbour gathers and the stores when the resident CTAs need less (sweep A: 4 x 41 KB = 72 %)
-    static int carveout(const char* var) {
+    // shared-memory carve-out of the v4 sweeps.  Sweep A gathers its neighbour values with 8-byte cp.async through L1, so it asks for no more
+    // shared memory than its resident CTAs need (order 4: 4 x 41 KB -> the 164 KB configuration, 92 KB of L1: sweep A -12 %,
+    // profiles/r1_variants.md); sweep B streams everything by bulk copies and keeps the maximum.  NSEM_V4_CARVEOUT_A / _B (percent of
+    // 228 KB) override.
+    static int carveout(const char* var, int default_pct) {
         const char* v = std::getenv(var);
-        const int pct = v ? std::atoi(v) : 0;
+        const int pct = v ? std::atoi(v) : default_pct;
         return (pct > 0 && pct <= 100) ? pct : (int)cudaSharedmemCarveoutMaxShared;
     }
+    static constexpr int carve_pct(size_t smem, int minb) {
+        // smallest percentage of 228 KB that holds minb CTAs (1 KB reserved per CTA)
+        return (int)(((smem + 1024) * (size_t)minb * 100 + 228 * 1024 - 1) / (228 * 1024));
+    }
     template <class K>
-    static cudaError_t go4(K kernel, size_t smem, int nt, int minb, const KParams& P, int sms, cudaStream_t s, const char* carve_var) {
+    static cudaError_t go4(K kernel, size_t smem, int nt, int minb, const KParams& P, int sms, cudaStream_t s, const char* carve_var, int carve_default) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout(carve_var));
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout(carve_var, carve_default));
         if (e != cudaSuccess) return e;
         const uint64_t want = (uint64_t)sms * (uint64_t)minb;
         const unsigned grid = (unsigned)std::min<uint64_t>(P.nB, want);
@@ -322,15 +328,15 @@ struct Launch {
     static cudaError_t sweepA4t(const KParams& P, int sms, cudaStream_t s) {
         using C4 = v4::CfgA<NX, NY, NZ, VISC, TRI>;
         constexpr int MB = C4::minb(NSEM_V4_REGS_A);
-        if (P.mortarA) return go4(v4::sweepA_v4<NX, NY, NZ, VISC, TRI, MB, true>, C4::smem, C4::NT, MB, P, sms, s, "NSEM_V4_CARVEOUT_A");     // non-conforming mesh
-        return go4(v4::sweepA_v4<NX, NY, NZ, VISC, TRI, MB>, C4::smem, C4::NT, MB, P, sms, s, "NSEM_V4_CARVEOUT_A");
+        if (P.mortarA) return go4(v4::sweepA_v4<NX, NY, NZ, VISC, TRI, MB, true>, C4::smem, C4::NT, MB, P, sms, s, "NSEM_V4_CARVEOUT_A", carve_pct(C4::smem, MB));     // non-conforming mesh
+        return go4(v4::sweepA_v4<NX, NY, NZ, VISC, TRI, MB>, C4::smem, C4::NT, MB, P, sms, s, "NSEM_V4_CARVEOUT_A", carve_pct(C4::smem, MB));
     }
     template <bool VISC, bool TRI>
     static cudaError_t sweepB4t(const KParams& P, int sms, cudaStream_t s) {
         using C4 = v4::CfgB<NX, NY, NZ, VISC, TRI>;
         constexpr int MB = C4::minb(NSEM_V4_REGS_B);
-        if (P.mortarB) return go4(v4::sweepB_v4<NX, NY, NZ, VISC, TRI, MB, true>, C4::smem, C4::NT, MB, P, sms, s, "NSEM_V4_CARVEOUT_B");
-        return go4(v4::sweepB_v4<NX, NY, NZ, VISC, TRI, MB>, C4::smem, C4::NT, MB, P, sms, s, "NSEM_V4_CARVEOUT_B");
+        if (P.mortarB) return go4(v4::sweepB_v4<NX, NY, NZ, VISC, TRI, MB, true>, C4::smem, C4::NT, MB, P, sms, s, "NSEM_V4_CARVEOUT_B", 0);
+        return go4(v4::sweepB_v4<NX, NY, NZ, VISC, TRI, MB>, C4::smem, C4::NT, MB, P, sms, s, "NSEM_V4_CARVEOUT_B", 0);
     }
     static cudaError_t sweepA4(const KParams& P, bool tri, int sms, cudaStream_t s) {
         if constexpr (has_v4) {
