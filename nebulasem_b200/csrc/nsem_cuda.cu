@@ -300,7 +300,7 @@ struct Launch {
     static constexpr bool has_v4 = (NX == NY && NY == NZ && NX > 1) && v4::CfgB<NX, NY, NZ, true, false>::smem <= 227 * 1024 &&
                                    v4::CfgA<NX, NY, NZ, true, false>::smem <= 227 * 1024 && v4::CfgA<NX, NY, NZ, true, false>::ok;
     // shared-memory carve-out of the v4 sweeps.  Sweep A gathers its neighbour values with 8-byte cp.async through L1, so it asks for no more
-    // shared memory than its resident CTAs need (order 4: 4 x 41 KB -> the 164 KB configuration, 92 KB of L1: sweep A -12 %,
+    // shared memory than its resident CTAs need (order 4: 4 x 41 KB = 71 % -> the 164 KB configuration instead of 228 KB: sweep A -11 %,
     // profiles/r1_variants.md); sweep B streams everything by bulk copies and keeps the maximum.  NSEM_V4_CARVEOUT_A / _B (percent of
     // 228 KB) override.
     static int carveout(const char* var, int default_pct) {

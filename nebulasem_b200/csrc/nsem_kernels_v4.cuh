@@ -22,8 +22,9 @@
 #pragma once
 #include "nsem_kernels_v2.cuh"
 
-// differentiation-matrix entry: from the shared-memory copy, or (-DNSEM_D_CONST) straight from the kernel-parameter constant bank
-#ifdef NSEM_D_CONST
+// differentiation-matrix entry: straight from the kernel-parameter constant bank (30 fewer shared-memory loads per node in sweep A: -3 %,
+// profiles/r1_variants.md), or (-DNSEM_D_SMEM) from the shared-memory copy
+#ifndef NSEM_D_SMEM
 #define NSEM_DM(d, idx) P.D[d][idx]
 #else
 #define NSEM_DM(d, idx) sD[(d) * MAXN * MAXN + (idx)]

@@ -1,0 +1,45 @@
+"""compute-sanitizer target (no pytest, no torch): a few steps of every kernel family on small meshes.
+    compute-sanitizer --tool memcheck python tests/sanitize_check.py
+Covers: v4 sweeps (conforming 3-D), v4 + mortar kernels (3-D non-conforming), v1 + mortar kernels (2-D non-conforming and 3-D with
+NSEM_MORTAR_V1=1), v1 2-D, the boundary/ghost-trace kernels, upload/download."""
+import os
+import shutil
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from nebulasem_b200 import host  # noqa: E402
+
+
+def run(s, nsteps, tag):
+    s.attach(0)
+    info = s.kernel_info
+    s.step(nsteps)
+    s.download()
+    rho, U, T, p = s.state()
+    ok = np.isfinite(rho).all() and np.isfinite(U).all() and np.isfinite(T).all()
+    print("SANITIZE", tag, "|", info, "| finite:", bool(ok), flush=True)
+    s.close()
+    return ok
+
+
+def main():
+    ok = True
+    ok &= run(host.Solver.synthetic("bubble3d", 3, 3, 3, 4), 3, "bubble3d 3^3 order 4")
+    ok &= run(host.Solver.synthetic("bubble2d", 4, 1, 4, 4), 3, "bubble2d 4x4 order 4")
+    ok &= run(host.Solver.synthetic("hill3d", 6, 2, 4, 3), 3, "hill3d 6x2x4 order 3")
+    with tempfile.TemporaryDirectory() as d:
+        for fixture, env in (("srtb3d_amr", "0"), ("srtb3d_amr", "1"), ("srtb_amr", "0")):
+            os.environ["NSEM_MORTAR_V1"] = env
+            c = os.path.join(d, fixture + env)
+            shutil.copytree(os.path.join(ROOT, "tests", "golden", fixture), c)
+            ok &= run(host.Solver.open_case(c), 3, f"{fixture} NSEM_MORTAR_V1={env}")
+    print("SANITIZE_DONE", "OK" if ok else "NOT FINITE", flush=True)
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
