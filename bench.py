@@ -60,54 +60,85 @@ def algorithmic_bytes_per_node(kernel_info: str, visc: bool = True) -> dict:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock, power and clock-event (throttle) reasons DURING the timed region (B200_PROFILING.md recipe), polled every few
+    milliseconds from NVML -- the source `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` reads; a piped nvidia-smi
+    block-buffers its output and loses most samples of a 0.2 s region.  Falls back to one nvidia-smi query per sample."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, device: int):
         self.device = device
-        self.proc = None
-        self.lines = []
+        self.samples = []            # (sm_mhz, sm_max_mhz, power_w, reasons:set)
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.nvml = None
+        self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(device).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid if not uuid.startswith("GPU-") else uuid).encode())
+            except Exception:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                idx = int(vis.split(",")[device]) if vis and vis.split(",")[device].isdigit() else device
+                h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nvml, self.handle = pynvml, h
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _one_nvml(self):
+        n, h = self.nvml, self.handle
+        sm = float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM))
+        try:
+            pw = n.nvmlDeviceGetPowerUsage(h) / 1000.0
+        except Exception:
+            pw = float("nan")
+        try:
+            bits = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            bits = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        rs = set()
+        for name, attr in (("hw_slowdown", "nvmlClocksThrottleReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                           ("sw_thermal_slowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksThrottleReasonSwPowerCap")):
+            if bits & getattr(n, attr, 0):
+                rs.add(name)
+        return sm, self.smax, pw, rs
+
+    def _one_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip().splitlines()[0]
+        f = [x.strip() for x in out.split(",")]
+        rs = {name for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]) if val.lower().startswith("active")}
+        return float(f[0]), float(f[1]), float(f[2]), rs
+
+    def _loop(self):
+        one = self._one_nvml if self.nvml else self._one_smi
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(one())
+            except Exception:
+                pass
+            self.stop_flag.wait(0.004)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
     def stop(self) -> dict:
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons, power = [], [], set(), []
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+        self.stop_flag.set()
+        if self.thread:
+            self.thread.join(timeout=6)
+        if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(smax), "power_w_max": max(power), "samples": len(sm),
-                "reasons": sorted(reasons)}
+        sm = sorted(x[0] for x in self.samples)
+        reasons = set().union(*[x[3] for x in self.samples])
+        pw = [x[2] for x in self.samples if x[2] == x[2]]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(x[1] for x in self.samples), "power_w_max": max(pw) if pw else None,
+                "samples": len(sm), "source": "nvml" if self.nvml else "nvidia-smi", "reasons": sorted(reasons)}
 
 
 def measured_peak_gbs():

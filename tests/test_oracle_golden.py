@@ -72,3 +72,25 @@ def test_oracle_mortar_faces_reproduce_reference_dump(tmp_path, fixture, nmortar
     orc2.run(5)
     m1 = float((orc2.rho[:nb] * orc2.g.cV[:nb]).sum())
     assert abs(m1 - m0) <= 1e-13 * abs(m0)
+
+
+@pytest.mark.parametrize("order", [1, 2, 3, 4, 5, 6, 7])
+def test_mortar_projections_preserve_constants_and_integrals(order):
+    """psiRef/psiCor (dg.cpp:550-590): the coarse -> fine projection reproduces constants on each half, and the fine -> coarse
+    projection conserves the integral (a flux through the two halves equals the flux the coarse face receives) -- what makes the
+    scatter/gather pair of a 2:1 face conservative."""
+    from oracle.dg import Basis
+    b = Basis((order, order, order))
+    n = order + 1
+    w = b.wgl[0]
+    rng = np.random.default_rng(order)
+    for h in range(2):
+        R = b.psiRef[h].reshape(n, n)          # [in, io]
+        assert np.allclose(R.sum(axis=0), 1.0, atol=1e-12)
+    # gather: a sub-facet carries HALF the coarse face's area with the FULL quadrature weights (fN = gFN_sub * w_a w_b / 4), so the
+    # projection of its flux must keep the weighted sum: sum_in w_in (f @ psiCor_h)[in] == sum_io w_io f[io]
+    for h in range(2):
+        f = rng.standard_normal(n)
+        coarse = f @ b.psiCor[h].reshape(n, n)                       # coarse[in] = sum_io f[io] psiCor[h][io*n+in]
+        lhs, rhs = float((w * coarse).sum()), float((w * f).sum())
+        assert abs(lhs - rhs) <= 1e-12 * max(1.0, abs(rhs))
