@@ -126,6 +126,14 @@ int nsem_set_schedule(nsem_ctx* ctx, const uint32_t* order, uint32_t n);
  * rho, U (AoS 3), T (perturbation theta - T0, euler.cpp:181,286), p (perturbation p - p_ref). */
 int nsem_upload_state(nsem_ctx* ctx, const double* rho, const double* U, const double* T, const double* p);
 int nsem_download_state(nsem_ctx* ctx, double* rho, double* U, double* T, double* p);
+/* Pipelined variants for drivers that stream batches through the device: both only ENQUEUE and return.  The upload copies on a
+ * copy-in stream into its own staging buffer and converts the layout on the compute stream, ordered after everything enqueued
+ * before it; the download converts on the compute stream into a second staging buffer and copies out on a copy-out stream, so
+ * the download of one batch overlaps the upload of the next (PCIe is full duplex).  Host arrays passed to the upload must stay
+ * unchanged, and arrays passed to the download are complete, after nsem_sync().  NULL arrays are skipped.  Page-lock the arrays
+ * (nsem_pin_host), pageable memory makes the copies synchronous. */
+int nsem_upload_state_async(nsem_ctx* ctx, const double* rho, const double* U, const double* T, const double* p);
+int nsem_download_state_async(nsem_ctx* ctx, double* rho, double* U, double* T, double* p);
 /* Page-lock a host array that will be passed to upload/download repeatedly and outlives the context (the solver's
  * field storage); optional, transfers from pageable memory work too. Unregistered by nsem_destroy. */
 int nsem_pin_host(nsem_ctx* ctx, const void* ptr, uint64_t bytes);

@@ -49,7 +49,7 @@ class NsemHaloPeer(C.Structure):
 
 EXPORTS = ["nsem_create", "nsem_destroy", "nsem_last_error", "nsem_get_unique_id", "nsem_set_order", "nsem_set_basis",
            "nsem_upload_mesh", "nsem_set_bcs", "nsem_set_halo", "nsem_set_params", "nsem_set_schedule",
-           "nsem_pin_host", "nsem_upload_state", "nsem_download_state", "nsem_upload_ref", "nsem_upload_geopotential", "nsem_euler_step", "nsem_exchange_state_halos", "nsem_diagnostics",
+           "nsem_pin_host", "nsem_upload_state", "nsem_download_state", "nsem_upload_state_async", "nsem_download_state_async", "nsem_upload_ref", "nsem_upload_geopotential", "nsem_euler_step", "nsem_exchange_state_halos", "nsem_diagnostics",
            "nsem_sync", "nsem_time_steps", "nsem_launch_count", "nsem_kernel_info"]
 
 _lib = None
@@ -81,6 +81,8 @@ def load_library() -> C.CDLL:
     lib.nsem_pin_host.argtypes = [vp, vp, C.c_uint64]
     lib.nsem_upload_state.argtypes = [vp, _dp, _dp, _dp, _dp]
     lib.nsem_download_state.argtypes = [vp, _dp, _dp, _dp, _dp]
+    lib.nsem_upload_state_async.argtypes = [vp, _dp, _dp, _dp, _dp]
+    lib.nsem_download_state_async.argtypes = [vp, _dp, _dp, _dp, _dp]
     lib.nsem_upload_ref.argtypes = [vp, _dp, _dp, _dp]
     lib.nsem_upload_geopotential.argtypes = [vp, _dp]
     lib.nsem_euler_step.argtypes = [vp, C.c_int]

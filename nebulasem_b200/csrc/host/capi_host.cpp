@@ -165,6 +165,8 @@ int nsemh_attach(nsemh_solver* h, int device, int rank, int nranks, const void* 
 int nsemh_step(nsemh_solver* h, int n) { GUARD(h->s.step(n)) }
 int nsemh_upload(nsemh_solver* h) { GUARD(h->s.upload_state()) }
 int nsemh_download(nsemh_solver* h) { GUARD(h->s.download()) }
+int nsemh_upload_async(nsemh_solver* h) { GUARD(h->s.upload_state_async()) }
+int nsemh_download_async(nsemh_solver* h) { GUARD(h->s.download_async()) }
 int nsemh_write(nsemh_solver* h, int index) { GUARD(h->s.write_fields(index)) }
 int nsemh_run(nsemh_solver* h) { GUARD(h->s.run()) }
 int nsemh_sync(nsemh_solver* h) { GUARD(if (nsem_sync(h->s.ctx)) throw Error(nsem_last_error(h->s.ctx))) }
@@ -210,6 +212,7 @@ const double* nsemh_f64(nsemh_solver* h, const char* name, uint64_t* n) {
     else if (k.size() == 7 && k.compare(0, 6, "psiCor") == 0 && k[6] >= '0' && k[6] <= '5') v = &s.geo.psiCor[k[6] - '0'];
     else if (k == "rho") v = &s.rho; else if (k == "U") v = &s.U; else if (k == "T") v = &s.T; else if (k == "p") v = &s.p;
     else if (k == "rho_ref") v = &s.rho_ref; else if (k == "p_ref") v = &s.p_ref; else if (k == "g") v = &s.gvec;
+    else if (k == "out_rho") v = &s.out_rho; else if (k == "out_U") v = &s.out_U; else if (k == "out_T") v = &s.out_T; else if (k == "out_p") v = &s.out_p;
     if (!v) { *n = 0; return nullptr; }
     *n = v->size();
     return v->data();

@@ -486,6 +486,21 @@ void EulerSolver::exchange_setup_halos() {
 void EulerSolver::upload_state() {
     if (nsem_upload_state(ctx, rho.data(), U.data(), T.data(), p.data())) throw Error(nsem_last_error(ctx));
 }
+void EulerSolver::upload_state_async() {
+    if (!ctx) throw Error("EulerSolver::upload_state_async: no device attached");
+    if (nsem_upload_state_async(ctx, rho.data(), U.data(), T.data(), p.data())) throw Error(nsem_last_error(ctx));
+}
+void EulerSolver::download_async() {
+    if (!ctx) throw Error("EulerSolver::download_async: no device attached");
+    if (out_rho.size() != rho.size()) {
+        out_rho.assign(rho.size(), 0.0); out_U.assign(U.size(), 0.0); out_T.assign(T.size(), 0.0); out_p.assign(p.size(), 0.0);
+        for (std::vector<double>* v : {&out_rho, &out_U, &out_T, &out_p}) nsem_pin_host(ctx, v->data(), v->size() * sizeof(double));
+    }
+    if (nsem_download_state_async(ctx, out_rho.data(), out_U.data(), out_T.data(), out_p.data())) throw Error(nsem_last_error(ctx));
+}
+void EulerSolver::sync() {
+    if (ctx && nsem_sync(ctx)) throw Error(nsem_last_error(ctx));
+}
 void EulerSolver::step(int n) {
     if (!ctx) throw Error("EulerSolver::step: no device attached (there is no CPU fallback)");
     if (nsem_euler_step(ctx, n)) throw Error(nsem_last_error(ctx));

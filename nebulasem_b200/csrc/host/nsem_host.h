@@ -199,6 +199,12 @@ struct EulerSolver {
     void setup();                                         // euler.cpp:58-176 (reference state, rho from p, BCs)
     void attach_device(int device, int rank = 0, int nranks = 1, const void* uid = nullptr);   // C-ABI uploads
     void upload_state();
+    // pipelined batches (nsem_upload_state_async / nsem_download_state_async): the download lands in out_* so that the next upload can
+    // read rho/U/T/p while it is in flight; results are complete after sync()
+    std::vector<double> out_rho, out_U, out_T, out_p;
+    void upload_state_async();
+    void download_async();
+    void sync();
     void step(int n);                                     // time-loop body on the GPU
     void download();
     void write_fields(int index);                         // Mesh::write_fields; with nranks > 1 into <case>/grid<rank>/ like the

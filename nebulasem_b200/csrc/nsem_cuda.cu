@@ -171,6 +171,14 @@ struct nsem_ctx {
     DevBuf<BCRec> bcRecs;
     // staging for layout conversion
     DevBuf<double> stage;
+    // pipelined transfers (nsem_upload_state_async / nsem_download_state_async): one staging buffer per direction, copies on their own
+    // streams so that the download of one batch overlaps the upload of the next (PCIe is full duplex)
+    DevBuf<double> stageIn, stageOut;          // [6][n_cells_all*NP]: rho, U(3), T, p in the reference layout
+    DevBuf<double*> ptrTabAsync;               // [4 fields][3] device pointers for the conversion kernels
+    DevBuf<int> compMapAsync;
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    cudaEvent_t evH2D = nullptr, evScatter = nullptr, evGather = nullptr, evD2H = nullptr;
+    bool asyncReady = false, scatterPending = false, d2hPending = false;
     DevBuf<double*> ptrTab;
     DevBuf<int> compMap;
 
@@ -504,6 +512,9 @@ extern "C" void nsem_destroy(nsem_ctx* c) {
 #endif
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     for (auto& r : c->pinned) cudaHostUnregister(const_cast<void*>(r.first));
+    for (cudaEvent_t e : {c->evH2D, c->evScatter, c->evGather, c->evD2H}) if (e) cudaEventDestroy(e);
+    if (c->h2d) cudaStreamDestroy(c->h2d);
+    if (c->d2h) cudaStreamDestroy(c->d2h);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->comm) cudaStreamDestroy(c->comm);
     delete c;
@@ -539,8 +550,10 @@ extern "C" const char* nsem_kernel_info(const nsem_ctx* c) {
 
 extern "C" int nsem_sync(nsem_ctx* c) {
     CUDA_TRY(c, cudaSetDevice(c->device));
+    if (c->h2d) CUDA_TRY(c, cudaStreamSynchronize(c->h2d));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->comm));
+    if (c->d2h) CUDA_TRY(c, cudaStreamSynchronize(c->d2h));
     return 0;
 }
 
@@ -1231,6 +1244,97 @@ extern "C" int nsem_download_state(nsem_ctx* c, double* rho, double* U, double* 
     return 0;
 }
 
+// ---- pipelined transfers -----------------------------------------------------------------------------------
+static int join_comm_fwd(nsem_ctx* c);      // = join_comm (defined with the step): make the compute stream see an in-flight halo exchange
+static int async_setup(nsem_ctx* c) {
+    if (c->asyncReady && c->stageIn.n >= (size_t)c->nRefNodes * 6) return 0;
+    CUDA_TRY(c, c->stageIn.alloc((size_t)c->nRefNodes * 6));
+    CUDA_TRY(c, c->stageOut.alloc((size_t)c->nRefNodes * 6));
+    if (!c->ptrTabAsync.p) { CUDA_TRY(c, c->ptrTabAsync.alloc(12)); CUDA_TRY(c, c->compMapAsync.alloc(3)); }
+    if (!c->h2d) {
+        CUDA_TRY(c, cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
+        CUDA_TRY(c, cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking));
+        for (cudaEvent_t* e : {&c->evH2D, &c->evScatter, &c->evGather, &c->evD2H}) CUDA_TRY(c, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    }
+    const int cm[3] = {0, 1, 2};
+    CUDA_TRY(c, cudaMemcpyAsync(c->compMapAsync.p, cm, sizeof cm, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->asyncReady = true;
+    c->scatterPending = c->d2hPending = false;
+    return 0;
+}
+
+// field q of {rho, U, T, p}: components and offset (in nodes) inside a staging buffer
+static const int kAsyncComps[4] = {1, 3, 1, 1};
+static const int kAsyncOff[4] = {0, 1, 4, 5};
+
+extern "C" int nsem_upload_state_async(nsem_ctx* c, const double* rho, const double* U, const double* T, const double* p) {
+    if (!c->have_mesh) { c->err = "nsem_upload_state_async: no mesh"; return 1; }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (async_setup(c)) return 1;
+    if (join_comm_fwd(c)) return 1;
+    const int k = c->cur;
+    const double* host[4] = {rho, U, T, p};
+    double* dst[4][3] = {{c->rho[k].p, nullptr, nullptr}, {c->U[k][0].p, c->U[k][1].p, c->U[k][2].p}, {c->T[k].p, nullptr, nullptr}, {c->p.p, nullptr, nullptr}};
+    // the staging buffer is free once the conversion kernels of the previous upload have read it
+    if (c->scatterPending) CUDA_TRY(c, cudaStreamWaitEvent(c->h2d, c->evScatter, 0));
+    for (int q = 0; q < 4; q++)
+        if (host[q])
+            CUDA_TRY(c, cudaMemcpyAsync(c->stageIn.p + (size_t)kAsyncOff[q] * c->nRefNodes, host[q], (size_t)c->nRefNodes * kAsyncComps[q] * sizeof(double),
+                                        cudaMemcpyHostToDevice, c->h2d));
+    CUDA_TRY(c, cudaEventRecord(c->evH2D, c->h2d));
+    // conversion on the compute stream: after everything already enqueued there (a pending download's gather reads the same state arrays)
+    CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->evH2D, 0));
+    CUDA_TRY(c, cudaMemcpyAsync(c->ptrTabAsync.p, dst, sizeof dst, cudaMemcpyHostToDevice, c->stream));
+    const uint64_t n = (uint64_t)c->nB * c->NP + (uint64_t)c->nG * c->NPF;
+    for (int q = 0; q < 4; q++)
+        if (host[q]) {
+            scatter_to_device<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->stageIn.p + (size_t)kAsyncOff[q] * c->nRefNodes, kAsyncComps[q],
+                                                                                 c->ptrTabAsync.p + q * 3, c->compMapAsync.p, c->nB, c->NP, c->NPS, c->nG,
+                                                                                 c->NPF, c->GPS, c->ghostRef.p, c->ghostBase);
+            c->launches++;
+        }
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaEventRecord(c->evScatter, c->stream));
+    c->scatterPending = true;
+    c->have_state = true;
+    return 0;
+}
+
+extern "C" int nsem_download_state_async(nsem_ctx* c, double* rho, double* U, double* T, double* p) {
+    if (!c->have_state) { c->err = "nsem_download_state_async: no state"; return 1; }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (async_setup(c)) return 1;
+    if (join_comm_fwd(c)) return 1;
+    const int k = c->cur;
+    double* host[4] = {rho, U, T, p};
+    const double* src[4][3] = {{c->rho[k].p, nullptr, nullptr}, {c->U[k][0].p, c->U[k][1].p, c->U[k][2].p}, {c->T[k].p, nullptr, nullptr}, {c->p.p, nullptr, nullptr}};
+    // the outgoing staging buffer is free once the previous download's copies have left it
+    if (c->d2hPending) CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->evD2H, 0));
+    CUDA_TRY(c, cudaMemcpyAsync(c->ptrTabAsync.p, src, sizeof src, cudaMemcpyHostToDevice, c->stream));
+    const uint64_t n = (uint64_t)c->nB * c->NP + (uint64_t)c->nG * c->NPF;
+    for (int q = 0; q < 4; q++)
+        if (host[q]) {
+            double* st = c->stageOut.p + (size_t)kAsyncOff[q] * c->nRefNodes;
+            const size_t bytes = (size_t)c->nRefNodes * kAsyncComps[q] * sizeof(double), realBytes = (size_t)c->nB * c->NP * kAsyncComps[q] * sizeof(double);
+            CUDA_TRY(c, cudaMemsetAsync(reinterpret_cast<char*>(st) + realBytes, 0, bytes - realBytes, c->stream));
+            gather_from_device<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(st, kAsyncComps[q], (const double* const*)(c->ptrTabAsync.p + q * 3),
+                                                                                  c->compMapAsync.p, c->nB, c->NP, c->NPS, c->nG, c->NPF, c->GPS,
+                                                                                  c->ghostRef.p, c->ghostBase);
+            c->launches++;
+        }
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaEventRecord(c->evGather, c->stream));
+    CUDA_TRY(c, cudaStreamWaitEvent(c->d2h, c->evGather, 0));
+    for (int q = 0; q < 4; q++)
+        if (host[q])
+            CUDA_TRY(c, cudaMemcpyAsync(host[q], c->stageOut.p + (size_t)kAsyncOff[q] * c->nRefNodes, (size_t)c->nRefNodes * kAsyncComps[q] * sizeof(double),
+                                        cudaMemcpyDeviceToHost, c->d2h));
+    CUDA_TRY(c, cudaEventRecord(c->evD2H, c->d2h));
+    c->d2hPending = true;
+    return 0;
+}
+
 extern "C" int nsem_upload_ref(nsem_ctx* c, const double* rho_ref, const double* p_ref, const double* g) {
     if (!c->have_mesh) { c->err = "nsem_upload_ref: no mesh"; return 1; }
     CUDA_TRY(c, cudaSetDevice(c->device));
@@ -1385,6 +1489,8 @@ static int join_comm(nsem_ctx* c) {
     }
     return 0;
 }
+
+static int join_comm_fwd(nsem_ctx* c) { return join_comm(c); }
 
 static int one_step(nsem_ctx* c, bool timed, double* acc) {
     if (!timed && !c->peers.empty() && c->overlap && c->nMortarGroups == 0) return one_step_overlapped(c);

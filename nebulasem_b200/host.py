@@ -16,7 +16,7 @@ from . import capi
 HOST_LIB_PATH = os.path.join(os.environ.get("NSEM_LIBDIR") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib"), "libnsem_host.so")
 HOST_EXPORTS = ["nsemh_error", "nsemh_close", "nsemh_open_case", "nsemh_synthetic", "nsemh_synthetic_part", "nsemh_patch_faces",
                 "nsemh_peers", "nsemh_diagnostics", "nsemh_attach", "nsemh_step",
-                "nsemh_upload", "nsemh_download", "nsemh_write", "nsemh_run", "nsemh_sync", "nsemh_time",
+                "nsemh_upload", "nsemh_download", "nsemh_upload_async", "nsemh_download_async", "nsemh_write", "nsemh_run", "nsemh_sync", "nsemh_time",
                 "nsemh_launch_count", "nsemh_kernel_info", "nsemh_set_schedule", "nsemh_dims", "nsemh_params", "nsemh_f64", "nsemh_u32",
                 "nsemh_state_ptr", "nsemh_totals", "nsemh_partition_grid"]
 _lib = None
@@ -46,7 +46,7 @@ def load_host_library() -> C.CDLL:
     lib.nsemh_patch_faces.restype = C.c_uint64
     lib.nsemh_peers.argtypes = [vp, C.POINTER(C.c_int), C.c_int]
     lib.nsemh_attach.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
-    for n in ("nsemh_upload", "nsemh_download", "nsemh_run", "nsemh_sync"):
+    for n in ("nsemh_upload", "nsemh_download", "nsemh_upload_async", "nsemh_download_async", "nsemh_run", "nsemh_sync"):
         getattr(lib, n).argtypes = [vp]
     lib.nsemh_step.argtypes = [vp, C.c_int]
     lib.nsemh_write.argtypes = [vp, C.c_int]
@@ -195,6 +195,18 @@ class Solver:
 
     def download(self):
         self._ck(self.lib.nsemh_download(self.h))
+
+    def upload_async(self):
+        """Enqueue the upload of the host state (pipelined batches); see nsem_upload_state_async."""
+        self._ck(self.lib.nsemh_upload_async(self.h))
+
+    def download_async(self):
+        """Enqueue the download of the device state into the out_* host arrays; complete after sync()."""
+        self._ck(self.lib.nsemh_download_async(self.h))
+
+    def state_out(self):
+        """(rho, U, T, p) as the last download_async() + sync() left them."""
+        return self.f64("out_rho"), self.f64("out_U").reshape(-1, 3), self.f64("out_T"), self.f64("out_p")
 
     def sync(self):
         self._ck(self.lib.nsemh_sync(self.h))
