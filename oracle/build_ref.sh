@@ -3,7 +3,7 @@
 # /root/reference) into oracle/_ref/ as the parity oracle and CPU baseline.
 # TEST INFRASTRUCTURE ONLY: nothing in nebulasem_b200/ links or calls these binaries.
 #
-#   oracle/_ref/parity/{euler,mesh,prepare,geomdump}   -O2 -ffp-contract=off          (parity oracle)
+#   oracle/_ref/parity/{euler,mesh,prepare,geomdump,refinedump}   -O2 -ffp-contract=off          (parity oracle)
 #   oracle/_ref/fast/{euler,mesh}                       -O3 -funroll-loops -march=x86-64-v3 -fopenmp
 #                                                        (the reference's release flags, CMakeLists.txt:36-37,
 #                                                         with a portable -march so the binary also runs on the GPU box)
@@ -33,7 +33,7 @@ build_variant() {
     local dir="$OUT/$name"
     local stamp="$dir/.flags"
     if [ -f "$stamp" ] && [ "$(cat "$stamp")" = "$flags" ] && [ -x "$dir/euler" ] && [ -x "$dir/mesh" ] \
-       && [ "$HERE/tools/geomdump.cpp" -ot "$dir/euler" ]; then
+       && [ "$HERE/tools/geomdump.cpp" -ot "$dir/euler" ] && [ -x "$dir/refinedump" ] && [ "$HERE/tools/refinedump.cpp" -ot "$dir/refinedump" ]; then
         echo "build_ref: $name up to date"; return
     fi
     echo "build_ref: compiling $name ($flags)"
@@ -51,6 +51,7 @@ build_variant() {
     g++ -std=c++17 $flags -DUSE_DOUBLE -DUSE_EXPR_TMPL -w $INC "$R/apps/mesh/meshApp.cpp" "$dir/libnebulasem.a" -o "$dir/mesh" &
     g++ -std=c++17 $flags -DUSE_DOUBLE -DUSE_EXPR_TMPL -w $INC "$R/apps/prepare/prepareApp.cpp" "$dir/libnebulasem.a" -o "$dir/prepare" &
     g++ -std=c++17 $flags -DUSE_DOUBLE -DUSE_EXPR_TMPL -w $INC "$HERE/tools/geomdump.cpp" "$dir/libnebulasem.a" -o "$dir/geomdump" &
+    g++ -std=c++17 $flags -DUSE_DOUBLE -DUSE_EXPR_TMPL -w $INC "$HERE/tools/refinedump.cpp" "$dir/libnebulasem.a" -o "$dir/refinedump" &
     wait
     rm -rf "$dir/obj" "$dir/libnebulasem.a"      # keep oracle/_ref small: it travels to the GPU box with every gpurun
     echo "$flags" > "$stamp"
