@@ -163,6 +163,37 @@ uint64_t nsem_launch_count(const nsem_ctx* ctx);
  * metrics on the fly (trilinear map verified)", "v4 persistent pipelined, stored metrics", "v2", "v1". */
 const char* nsem_kernel_info(const nsem_ctx* ctx);
 
+/* ---- adaptive mesh refinement ----------------------------------------------------------------------- */
+/* One regrid as MeshObject::refineMesh (src/mesh/mesh.cpp:2216-2748) reports it and MeshField::refineField
+ * (src/field/field.h:1863-2015) consumes it; all arrays are the ones Prepare::refineMesh (field.cpp:884-906) passes on. */
+typedef struct {
+    uint32_t n_cells_new;         /* nCells: real cells of the regridded mesh */
+    const uint32_t* refine_map;   /* families [nchildren, old parent, child_0 ..]: children index cell_map */
+    uint32_t n_refine_map;
+    const uint32_t* coarse_map;   /* families [nchildren, first, old child_0 ..]: new cell = cell_map[first] */
+    uint32_t n_coarse_map;
+    const uint32_t* cell_map;     /* intermediate cell index -> new cell, 1u << 31 (Constants::MAX_INT) = removed */
+    uint32_t n_cell_map;
+    const double* old_cV;         /* gCV of the old mesh [old real cells] */
+    const double* old_cC;         /* gCC of the old mesh [*3] */
+    const double* new_cV;         /* gCV of the regridded mesh (gCV[id1] in field.h:1983) */
+    const double* new_cC;         /* gCC of the regridded mesh */
+    const double* old_node_cC;    /* Mesh::cC of the old mesh [old real cells*NP*3]: corner nodes orient the children */
+    const double* psi_ref[6];     /* DG::psiRef[d*2+half] (dg.cpp:576-590) */
+    const double* psi_cor[6];     /* DG::psiCor[d*2+half] */
+} nsem_regrid;
+/* MeshField::refineField for rho, U, T, p at once, device to device: `old_ctx` holds the old mesh and the state,
+ * `new_ctx` (same device, same order) the regridded mesh (nsem_upload_mesh); its real nodes receive the transferred
+ * state -- copied, interpolated onto the children of a split cell with the mass-fix factor, or projected from the
+ * children of a merged cell -- in the reference's floating-point operation order (bit-identical results).  The
+ * reference writes the transferred fields to files and re-reads them; ghost cells and p are then rebuilt by the solver
+ * set-up: nsem_restart_state. */
+int nsem_refine_state(nsem_ctx* old_ctx, const nsem_regrid* regrid, nsem_ctx* new_ctx);
+/* The restart branch of the solver set-up (apps/euler/euler.cpp:150-162) on the device: p = P0 (rho (T+T0) R / P0)^gamma
+ * - p_ref on the real nodes, then the boundary conditions of rho, p, U, T into the ghost cells (applyExplicitBCs) and,
+ * with nranks > 1, nsem_exchange_state_halos (collective).  Needs mesh, params, BCs, reference state and state. */
+int nsem_restart_state(nsem_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif

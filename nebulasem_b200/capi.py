@@ -47,10 +47,22 @@ class NsemHaloPeer(C.Structure):
     _fields_ = [("peer_rank", C.c_int32), ("n_faces", C.c_uint32), ("faces", _up)]
 
 
+class NsemRegrid(C.Structure):
+    """nsem_regrid of include/nsem_c.h: one regrid as MeshObject::refineMesh reports it."""
+    _fields_ = [("n_cells_new", C.c_uint32),
+                ("refine_map", C.POINTER(C.c_uint32)), ("n_refine_map", C.c_uint32),
+                ("coarse_map", C.POINTER(C.c_uint32)), ("n_coarse_map", C.c_uint32),
+                ("cell_map", C.POINTER(C.c_uint32)), ("n_cell_map", C.c_uint32),
+                ("old_cV", C.POINTER(C.c_double)), ("old_cC", C.POINTER(C.c_double)),
+                ("new_cV", C.POINTER(C.c_double)), ("new_cC", C.POINTER(C.c_double)),
+                ("old_node_cC", C.POINTER(C.c_double)),
+                ("psi_ref", C.POINTER(C.c_double) * 6), ("psi_cor", C.POINTER(C.c_double) * 6)]
+
+
 EXPORTS = ["nsem_create", "nsem_destroy", "nsem_last_error", "nsem_get_unique_id", "nsem_set_order", "nsem_set_basis",
            "nsem_upload_mesh", "nsem_set_bcs", "nsem_set_halo", "nsem_set_params", "nsem_set_schedule",
            "nsem_pin_host", "nsem_upload_state", "nsem_download_state", "nsem_upload_state_async", "nsem_download_state_async", "nsem_upload_ref", "nsem_upload_geopotential", "nsem_euler_step", "nsem_exchange_state_halos", "nsem_diagnostics",
-           "nsem_sync", "nsem_time_steps", "nsem_launch_count", "nsem_kernel_info"]
+           "nsem_sync", "nsem_time_steps", "nsem_launch_count", "nsem_kernel_info", "nsem_refine_state", "nsem_restart_state"]
 
 _lib = None
 
@@ -83,6 +95,8 @@ def load_library() -> C.CDLL:
     lib.nsem_download_state.argtypes = [vp, _dp, _dp, _dp, _dp]
     lib.nsem_upload_state_async.argtypes = [vp, _dp, _dp, _dp, _dp]
     lib.nsem_download_state_async.argtypes = [vp, _dp, _dp, _dp, _dp]
+    lib.nsem_refine_state.argtypes = [vp, C.POINTER(NsemRegrid), vp]
+    lib.nsem_restart_state.argtypes = [vp]
     lib.nsem_upload_ref.argtypes = [vp, _dp, _dp, _dp]
     lib.nsem_upload_geopotential.argtypes = [vp, _dp]
     lib.nsem_euler_step.argtypes = [vp, C.c_int]

@@ -167,6 +167,13 @@ int nsemh_upload(nsemh_solver* h) { GUARD(h->s.upload_state()) }
 int nsemh_download(nsemh_solver* h) { GUARD(h->s.download()) }
 int nsemh_upload_async(nsemh_solver* h) { GUARD(h->s.upload_state_async()) }
 int nsemh_download_async(nsemh_solver* h) { GUARD(h->s.download_async()) }
+// AMR field transfer on the device: solver `h` (regridded mesh) takes the state of `old` (EulerSolver::adopt_refined_state)
+int nsemh_adopt_refined_state(nsemh_solver* h, nsemh_solver* old, const uint32_t* refineMap, uint32_t nr, const uint32_t* coarseMap, uint32_t nc,
+                              const uint32_t* cellMap, uint32_t nm, int restart) {
+    GUARD(h->s.adopt_refined_state(old->s, std::vector<u32>(refineMap, refineMap + nr), std::vector<u32>(coarseMap, coarseMap + nc),
+                                   std::vector<u32>(cellMap, cellMap + nm), restart != 0))
+}
+int nsemh_restart_state(nsemh_solver* h) { GUARD(h->s.restart_state()) }
 int nsemh_write(nsemh_solver* h, int index) { GUARD(h->s.write_fields(index)) }
 int nsemh_run(nsemh_solver* h) { GUARD(h->s.run()) }
 int nsemh_sync(nsemh_solver* h) { GUARD(if (nsem_sync(h->s.ctx)) throw Error(nsem_last_error(h->s.ctx))) }
@@ -205,6 +212,8 @@ const double* nsemh_f64(nsemh_solver* h, const char* name, uint64_t* n) {
     EulerSolver& s = h->s;
     const std::string k = name;
     const std::vector<double>* v = nullptr;
+    if (k == "gCC") { *n = s.topo.CC.size() * 3; return s.topo.CC.empty() ? nullptr : s.topo.CC.data()->data(); }   // cell centroids (mesh.cpp:450-577)
+    if (k == "gCV") v = &s.topo.CV; else
     if (k == "cC") v = &s.geo.cC; else if (k == "cV") v = &s.geo.cV; else if (k == "Jinv") v = &s.geo.Jinv;
     else if (k == "fN") v = &s.geo.fN; else if (k == "fC") v = &s.geo.fC; else if (k == "fI") v = &s.geo.fI;
     else if (k == "faceNormal") v = &s.geo.faceNormal; else if (k == "faceCenter") v = &s.geo.faceCenter;

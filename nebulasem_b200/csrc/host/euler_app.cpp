@@ -501,6 +501,30 @@ void EulerSolver::download_async() {
 void EulerSolver::sync() {
     if (ctx && nsem_sync(ctx)) throw Error(nsem_last_error(ctx));
 }
+void EulerSolver::adopt_refined_state(EulerSolver& old, const std::vector<u32>& refineMap, const std::vector<u32>& coarseMap,
+                                      const std::vector<u32>& cellMap, bool restart) {
+    if (!ctx || !old.ctx) throw Error("EulerSolver::adopt_refined_state: both solvers must be attached to the device (there is no CPU fallback)");
+    for (int d = 0; d < 3; d++)
+        if (nop[d] != old.nop[d]) throw Error("EulerSolver::adopt_refined_state: polynomial orders differ");
+    Basis b(nop);
+    // gCV / gCC as std::vector<Vec3> are contiguous triples
+    nsem_regrid g;
+    std::memset(&g, 0, sizeof g);
+    g.n_cells_new = geo.nBCS;
+    g.refine_map = refineMap.data(); g.n_refine_map = (u32)refineMap.size();
+    g.coarse_map = coarseMap.data(); g.n_coarse_map = (u32)coarseMap.size();
+    g.cell_map = cellMap.data(); g.n_cell_map = (u32)cellMap.size();
+    g.old_cV = old.topo.CV.data(); g.old_cC = old.topo.CC.data()->data();
+    g.new_cV = topo.CV.data(); g.new_cC = topo.CC.data()->data();
+    g.old_node_cC = old.geo.cC.data();
+    for (int q = 0; q < 6; q++) { g.psi_ref[q] = b.psiRef[q].data(); g.psi_cor[q] = b.psiCor[q].data(); }
+    if (nsem_refine_state(old.ctx, &g, ctx)) throw Error(nsem_last_error(ctx));
+    if (restart && nsem_restart_state(ctx)) throw Error(nsem_last_error(ctx));
+}
+void EulerSolver::restart_state() {
+    if (!ctx) throw Error("EulerSolver::restart_state: no device attached (there is no CPU fallback)");
+    if (nsem_restart_state(ctx)) throw Error(nsem_last_error(ctx));
+}
 void EulerSolver::step(int n) {
     if (!ctx) throw Error("EulerSolver::step: no device attached (there is no CPU fallback)");
     if (nsem_euler_step(ctx, n)) throw Error(nsem_last_error(ctx));

@@ -206,6 +206,12 @@ struct EulerSolver {
     void download_async();
     void sync();
     void step(int n);                                     // time-loop body on the GPU
+    // AMR regrid with the state resident on the device (the field transfer of Prepare::refineMesh, field.cpp:884-906): `old` holds the
+    // mesh before the regrid and the state, this solver the regridded mesh (attached to the same device); the maps are those of
+    // MeshObject::refineMesh.  nsem_refine_state, then (restart) the set-up's restart branch nsem_restart_state (euler.cpp:150-162).
+    void adopt_refined_state(EulerSolver& old, const std::vector<u32>& refineMap, const std::vector<u32>& coarseMap,
+                             const std::vector<u32>& cellMap, bool restart);
+    void restart_state();                                 // nsem_restart_state: p from rho, ghost cells from the resident state
     void download();
     void write_fields(int index);                         // Mesh::write_fields; with nranks > 1 into <case>/grid<rank>/ like the
                                                           // reference's per-rank working directories (field.cpp:1436-1440)

@@ -11,6 +11,7 @@
 #include "nsem_kernels_v3.cuh"
 #include "nsem_kernels_v4.cuh"
 #include "nsem_mortar.cuh"
+#include "nsem_amr.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -1736,5 +1737,194 @@ extern "C" int nsem_diagnostics(nsem_ctx* c, double out[6]) {
     CUDA_TRY(c, cudaMemcpyAsync(h, res, sizeof h, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     out[0] = h[0]; out[1] = h[1]; out[2] = h[2] / count; out[3] = h[3]; out[4] = h[4]; out[5] = h[5];
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// AMR: device-resident field transfer at a regrid (MeshField::refineField, field.h:1863-2015) and the restart
+// branch of the solver set-up (euler.cpp:150-162); kernels in nsem_amr.cuh
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+constexpr uint32_t kAmrRemoved = 1u << 31;      // Constants::MAX_INT (tensor.h:455): cellMap entry of a cell that no longer exists
+
+// which half of the parent a child covers along each element axis (field.h:1899-1909, 1949-1959): `nodes` = coordinates of the
+// NP nodes of the cell whose nodes are the inputs (the child when merging, the parent when splitting)
+uint32_t amr_child_half(const double* nodes, int NX, int NY, int NZ, const double* ccc, const double* ccp) {
+    const double* v0 = nodes;
+    const double* vv[3] = {nodes + (size_t)(NX - 1) * NY * NZ * 3, nodes + (size_t)(NY - 1) * NZ * 3, nodes + (size_t)(NZ - 1) * 3};
+    uint32_t bits = 0;
+    for (int d = 0; d < 3; d++) {
+        double da = 0.0, db = 0.0;
+        for (int k = 0; k < 3; k++) {
+            const double e = vv[d][k] - v0[k];
+            da += (ccc[k] - v0[k]) * e;
+            db += (ccp[k] - v0[k]) * e;
+        }
+        if (!(da <= db)) bits |= 1u << d;
+    }
+    return bits;
+}
+
+// flat family lists [n, first, kid_0 .. kid_{n-1}]* -> offsets of the families; false when malformed
+bool amr_parse(const uint32_t* m, uint32_t len, std::vector<uint32_t>& starts) {
+    uint32_t i = 0;
+    while (i < len) {
+        if (i + 2 > len) return false;
+        const uint32_t n = m[i];
+        if (n == 0 || n > (uint32_t)amr::MAXKIDS || i + 2 + n > len) return false;
+        starts.push_back(i);
+        i += n + 2;
+    }
+    return true;
+}
+}  // namespace
+
+extern "C" int nsem_refine_state(nsem_ctx* o, const nsem_regrid* r, nsem_ctx* c) {
+    if (!o || !c || !r) { if (c) c->err = "nsem_refine_state: null argument"; return 1; }
+    if (!(o->have_mesh && o->have_state)) { c->err = "nsem_refine_state: the old context has no state"; return 1; }
+    if (!c->have_mesh) { c->err = "nsem_refine_state: upload the regridded mesh into the new context first"; return 1; }
+    if (o == c) { c->err = "nsem_refine_state: old and new context must differ"; return 1; }
+    if (o->device != c->device) { c->err = "nsem_refine_state: both contexts must live on the same device"; return 1; }
+    if (o->NX != c->NX || o->NY != c->NY || o->NZ != c->NZ) { c->err = "nsem_refine_state: polynomial orders differ"; return 1; }
+    if (r->n_cells_new != c->nB) { c->err = "nsem_refine_state: n_cells_new does not match the mesh of the new context"; return 1; }
+    if (r->n_cell_map < o->nB) { c->err = "nsem_refine_state: cell_map shorter than the old mesh"; return 1; }
+    if (!r->cell_map || !r->old_cV || !r->old_cC || !r->new_cV || !r->new_cC || !r->old_node_cC || (r->n_refine_map && !r->refine_map) ||
+        (r->n_coarse_map && !r->coarse_map)) { c->err = "nsem_refine_state: missing array"; return 1; }
+    for (int q = 0; q < 6; q++)
+        if (!r->psi_ref[q] || !r->psi_cor[q]) { c->err = "nsem_refine_state: psi_ref / psi_cor tables are required"; return 1; }
+    const int NX = o->NX, NY = o->NY, NZ = o->NZ, NP = o->NP;
+    const uint32_t nOld = o->nB, nNew = c->nB;
+
+    // ---- task tables on the host ----
+    std::vector<uint8_t> written(nNew, 0);
+    std::vector<uint32_t> copyOld, copyNew;
+    for (uint32_t i = 0; i < nOld; i++) {
+        const uint32_t id = r->cell_map[i];
+        if (id == kAmrRemoved) continue;
+        if (id >= nNew) { c->err = "nsem_refine_state: cell_map entry out of range"; return 1; }
+        copyOld.push_back(i); copyNew.push_back(id);
+        written[id] = 1;
+    }
+    std::vector<uint32_t> sStarts, mStarts;
+    if (!amr_parse(r->refine_map, r->n_refine_map, sStarts) || !amr_parse(r->coarse_map, r->n_coarse_map, mStarts)) {
+        c->err = "nsem_refine_state: malformed refine_map / coarse_map (families of 1..8 children expected)"; return 1;
+    }
+    std::vector<amr::Family> merges(mStarts.size()), splits(sStarts.size());
+    for (size_t f = 0; f < mStarts.size(); f++) {
+        const uint32_t* m = r->coarse_map + mStarts[f];
+        amr::Family& F = merges[f];
+        std::memset(&F, 0, sizeof F);
+        if (m[1] >= r->n_cell_map || r->cell_map[m[1]] >= nNew) { c->err = "nsem_refine_state: coarse_map parent out of range"; return 1; }
+        F.base = r->cell_map[m[1]];
+        F.n = m[0];
+        for (uint32_t j = 0; j < F.n; j++) {
+            const uint32_t id1 = m[2 + j];
+            if (id1 >= nOld) { c->err = "nsem_refine_state: coarse_map child out of range"; return 1; }
+            F.kid[j] = id1;
+            F.cv[j] = r->old_cV[id1];
+            F.half[j] = amr_child_half(r->old_node_cC + (size_t)id1 * NP * 3, NX, NY, NZ, r->old_cC + (size_t)id1 * 3, r->new_cC + (size_t)F.base * 3);
+        }
+        written[F.base] = 1;
+    }
+    for (size_t f = 0; f < sStarts.size(); f++) {
+        const uint32_t* m = r->refine_map + sStarts[f];
+        amr::Family& F = splits[f];
+        std::memset(&F, 0, sizeof F);
+        if (m[1] >= nOld) { c->err = "nsem_refine_state: refine_map parent out of range"; return 1; }
+        F.base = m[1];
+        F.n = m[0];
+        F.cvBase = r->old_cV[F.base];
+        for (uint32_t j = 0; j < F.n; j++) {
+            if (m[2 + j] >= r->n_cell_map || r->cell_map[m[2 + j]] >= nNew) { c->err = "nsem_refine_state: refine_map child out of range"; return 1; }
+            const uint32_t id1 = r->cell_map[m[2 + j]];
+            F.kid[j] = id1;
+            F.cv[j] = r->new_cV[id1];
+            F.half[j] = amr_child_half(r->old_node_cC + (size_t)F.base * NP * 3, NX, NY, NZ, r->new_cC + (size_t)id1 * 3, r->old_cC + (size_t)F.base * 3);
+            written[id1] = 1;
+        }
+    }
+    for (uint32_t i = 0; i < nNew; i++)
+        if (!written[i]) { c->err = "nsem_refine_state: new cell " + std::to_string(i) + " is neither copied, split from nor merged into"; return 1; }
+    std::vector<double> psiR(6 * 64, 0.0), psiC(6 * 64, 0.0), wnode(NP);
+    const int nd[3] = {NX, NY, NZ};
+    for (int q = 0; q < 6; q++) {
+        const int n = nd[q / 2];
+        std::memcpy(psiR.data() + q * 64, r->psi_ref[q], sizeof(double) * n * n);
+        std::memcpy(psiC.data() + q * 64, r->psi_cor[q], sizeof(double) * n * n);
+    }
+    for (int i = 0, q = 0; i < NX; i++)
+        for (int j = 0; j < NY; j++)
+            for (int k = 0; k < NZ; k++, q++) wnode[q] = ((o->W[0][i] * o->W[1][j]) * o->W[2][k]) / 8;
+
+    // ---- device ----
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (join_comm(o)) { c->err = o->err; return 1; }
+    CUDA_TRY(c, cudaStreamSynchronize(o->stream));
+    cudaStream_t s = c->stream;
+    DevBuf<double> dPsiR, dPsiC, dW;
+    DevBuf<amr::Family> dMerge, dSplit;
+    DevBuf<uint32_t> dCo, dCn;
+    CUDA_TRY(c, dPsiR.upload(psiR, s)); CUDA_TRY(c, dPsiC.upload(psiC, s)); CUDA_TRY(c, dW.upload(wnode, s));
+    CUDA_TRY(c, dMerge.upload(merges, s)); CUDA_TRY(c, dSplit.upload(splits, s));
+    CUDA_TRY(c, dCo.upload(copyOld, s)); CUDA_TRY(c, dCn.upload(copyNew, s));
+    amr::Params A;
+    std::memset(&A, 0, sizeof A);
+    A.NX = NX; A.NY = NY; A.NZ = NZ; A.NP = NP;
+    A.npsSrc = (uint32_t)o->NPS; A.npsDst = (uint32_t)c->NPS;
+    const int ko = o->cur, kn = c->cur;
+    const double* in[amr::NCOMP] = {o->rho[ko].p, o->U[ko][0].p, o->U[ko][1].p, o->U[ko][2].p, o->T[ko].p, o->p.p};
+    double* out[amr::NCOMP] = {c->rho[kn].p, c->U[kn][0].p, c->U[kn][1].p, c->U[kn][2].p, c->T[kn].p, c->p.p};
+    for (int f = 0; f < amr::NCOMP; f++) { A.in[f] = in[f]; A.out[f] = out[f]; }
+    A.wnode = dW.p;
+    A.copyOld = dCo.p; A.copyNew = dCn.p; A.nCopy = (uint32_t)copyOld.size();
+    const unsigned threads = (unsigned)((NP + 31) / 32 * 32);
+    const size_t smem = (size_t)(amr::NCOMP * NP + 2 * amr::NCOMP) * sizeof(double);
+    if (A.nCopy) {
+        const uint64_t n = (uint64_t)A.nCopy * NP;
+        amr::copy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(A);
+        c->launches++;
+    }
+    if (!merges.empty()) {
+        A.psi = dPsiC.p; A.fam = dMerge.p;
+        amr::merge_kernel<<<(unsigned)merges.size(), threads, smem, s>>>(A);
+        c->launches++;
+    }
+    if (!splits.empty()) {
+        A.psi = dPsiR.p; A.fam = dSplit.p;
+        amr::split_kernel<<<(unsigned)splits.size(), threads, smem, s>>>(A);
+        c->launches++;
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaStreamSynchronize(s));       // the task tables are freed on return
+    c->have_state = true;
+    return 0;
+}
+
+extern "C" int nsem_restart_state(nsem_ctx* c) {
+    if (check_ready(c, "nsem_restart_state")) return 1;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (join_comm(c)) return 1;
+    KParams P;
+    BCParams B;
+    fill_kparams(c, P);
+    const int k = c->cur;
+    const uint64_t nReal = (uint64_t)c->nB * c->NP;
+    amr::pressure_from_density_kernel<<<(unsigned)((nReal + 255) / 256), 256, 0, c->stream>>>(nReal, c->NP, c->NPS, P.P0, P.T0, P.R, P.gamma, c->rho[k].p,
+                                                                                           c->T[k].p, c->p_ref.p, c->p.p);
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    // ghost cells from the CURRENT state: the BC pass of sweep A (rho, p from the owner's EOS) without the gradients,
+    // then the BC pass of sweep B (U, T)
+    fill_bcparams(c, P, B, 0);
+    B.visc = 0;
+    B.rho_new = c->rho[k].p; B.T_old = c->T[k].p; B.p = c->p.p;
+    for (int d = 0; d < 3; d++) B.U_new[d] = c->U[k][d].p;
+    B.T_new = c->T[k].p;
+    CUDA_TRY(c, launch_bc(c, B));
+    B.phase = 1;
+    CUDA_TRY(c, launch_bc(c, B));
+    if (c->nG) c->launches += 2;
+    if (!c->peers.empty()) return nsem_exchange_state_halos(c);
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return 0;
 }

@@ -16,7 +16,7 @@ from . import capi
 HOST_LIB_PATH = os.path.join(os.environ.get("NSEM_LIBDIR") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib"), "libnsem_host.so")
 HOST_EXPORTS = ["nsemh_error", "nsemh_close", "nsemh_open_case", "nsemh_synthetic", "nsemh_synthetic_part", "nsemh_patch_faces",
                 "nsemh_peers", "nsemh_diagnostics", "nsemh_attach", "nsemh_step",
-                "nsemh_upload", "nsemh_download", "nsemh_upload_async", "nsemh_download_async", "nsemh_write", "nsemh_run", "nsemh_sync", "nsemh_time",
+                "nsemh_upload", "nsemh_download", "nsemh_upload_async", "nsemh_download_async", "nsemh_adopt_refined_state", "nsemh_restart_state", "nsemh_write", "nsemh_run", "nsemh_sync", "nsemh_time",
                 "nsemh_launch_count", "nsemh_kernel_info", "nsemh_set_schedule", "nsemh_dims", "nsemh_params", "nsemh_f64", "nsemh_u32",
                 "nsemh_state_ptr", "nsemh_totals", "nsemh_partition_grid"]
 _lib = None
@@ -46,9 +46,11 @@ def load_host_library() -> C.CDLL:
     lib.nsemh_patch_faces.restype = C.c_uint64
     lib.nsemh_peers.argtypes = [vp, C.POINTER(C.c_int), C.c_int]
     lib.nsemh_attach.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
-    for n in ("nsemh_upload", "nsemh_download", "nsemh_upload_async", "nsemh_download_async", "nsemh_run", "nsemh_sync"):
+    for n in ("nsemh_upload", "nsemh_download", "nsemh_upload_async", "nsemh_download_async", "nsemh_restart_state", "nsemh_run", "nsemh_sync"):
         getattr(lib, n).argtypes = [vp]
     lib.nsemh_step.argtypes = [vp, C.c_int]
+    u32p = C.POINTER(C.c_uint32)
+    lib.nsemh_adopt_refined_state.argtypes = [vp, vp, u32p, C.c_uint32, u32p, C.c_uint32, u32p, C.c_uint32, C.c_int]
     lib.nsemh_write.argtypes = [vp, C.c_int]
     lib.nsemh_time.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.nsemh_diagnostics.argtypes = [vp, C.POINTER(C.c_double)]
@@ -195,6 +197,20 @@ class Solver:
 
     def download(self):
         self._ck(self.lib.nsemh_download(self.h))
+
+    def adopt_refined_state(self, old: "Solver", refine_map, coarse_map, cell_map, restart: bool = True):
+        """AMR regrid with the state resident on the device: this solver (regridded mesh, attached) takes the state of `old` (mesh before
+        the regrid, attached to the same device) -- MeshField::refineField for rho, U, T, p (nsem_refine_state), then with `restart` the
+        set-up's restart branch: p from rho, ghost cells (nsem_restart_state).  The maps are those of MeshObject::refineMesh."""
+        maps = [np.ascontiguousarray(m, dtype=np.uint32) for m in (refine_map, coarse_map, cell_map)]
+        args = []
+        for m in maps:
+            args += [m.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_uint32(m.size)]
+        self._ck(self.lib.nsemh_adopt_refined_state(self.h, old.h, *args, 1 if restart else 0))
+
+    def restart_state(self):
+        """The set-up's restart branch on the device (euler.cpp:150-162): p from rho, ghost cells of rho, p, U, T (nsem_restart_state)."""
+        self._ck(self.lib.nsemh_restart_state(self.h))
 
     def upload_async(self):
         """Enqueue the upload of the host state (pipelined batches); see nsem_upload_state_async."""

@@ -10,7 +10,9 @@ For each case (2-D order 4 from examples/atmo/srtb-amr, 3-D order 2 from example
    one fine cell (a level-2 cell), so that copy, refinement and coarsening all occur with fields that are no longer
    polynomial on the parent;
 3. per pass one .npz: what refineField was given (maps, volumes, centroids, old node coordinates, psiRef/psiCor/wgl),
-   the fields before, and the fields the reference wrote after the transfer.
+   the fields before, and the fields the reference wrote after the transfer;
+4. per stage (0 = uniform grid, 1 = after pass 1, 2 = after pass 2) a fixed-mesh case directory <name>/stage<k>/ with the
+   grid and the field files of that stage as the reference wrote them (index 0), which the C++ host opens in the GPU tests.
 The reference ships no golden vectors of its own.
 """
 import os
@@ -24,7 +26,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import refio, run_ref  # noqa: E402
-from make_amr_golden import edit_controls  # noqa: E402
+from make_amr_golden import FIXED_CONTROLS, edit_controls  # noqa: E402
 
 REF = os.environ.get("NSEM_REFERENCE", "/root/reference")
 NSTEPS = 20
@@ -38,6 +40,17 @@ def refinedump(case, cells_txt, out_name):
     for n in FIELDS:
         d["post:" + n] = refio.read_field_values(os.path.join(case, f"{n}1"))
     return d
+
+
+def save_stage(case, out_dir, name, k, grid_index, orders):
+    """controls + grid + fields of dump 1 as a fixed-mesh case that starts at step 0"""
+    st = os.path.join(out_dir, name, f"stage{k}")
+    os.makedirs(st, exist_ok=True)
+    shutil.copy(os.path.join(case, f"grid_{grid_index}.bin"), os.path.join(st, "grid_0.bin"))
+    for n in FIELDS:
+        shutil.copy(os.path.join(case, f"{n}1.bin"), os.path.join(st, f"{n}0.bin"))
+    with open(os.path.join(st, "controls"), "w") as fh:
+        fh.write(FIXED_CONTROLS.format(n=NSTEPS, **orders))
 
 
 def pack(d):
@@ -72,9 +85,11 @@ def main():
             edit_controls(os.path.join(a, "controls"), end_step=NSTEPS, write_interval=NSTEPS, amr_step=None, **ctl)
             subprocess.check_call([run_ref.ref_bin("mesh"), "bubble", "-o", "grid_0.bin"], cwd=a, stdout=subprocess.DEVNULL)
             run_ref.run_euler(a, variant="parity")                     # fields of dump 1 on the uniform grid
+            save_stage(a, out_dir, name, 0, 0, ctl)
             cid = lambda e: (e[0] * n[1] + e[1]) * n[2] + e[2]          # block-generated element order (hexMesh.cpp:322-342)
             # pass 1: split the block
             p1 = refinedump(a, cells_line("r", [cid(e) for e in block]), "pass1.bin")
+            save_stage(a, out_dir, name, 1, 1, ctl)
             # pass 2: merge the first (and in 2-D also the last) family again, split two untouched coarse cells and the child of a
             # middle family that lies nearest the centre of the block (all its face neighbours are level-1 cells)
             rm, cm = p1["refineMap"].astype(np.int64), p1["cellMap"].astype(np.int64)
@@ -93,6 +108,7 @@ def main():
             coarse_old = [cid((0, 0, 0)), cid((n[0] - 1, n[1] - 1, n[2] - 1))]
             split = [cm[c] for c in coarse_old] + [fine]
             p2 = refinedump(a, cells_line("r", split) + cells_line("c", merge), "pass2.bin")
+            save_stage(a, out_dir, name, 2, 1, ctl)
             for tag, p in (("pass1", p1), ("pass2", p2)):
                 np.savez_compressed(os.path.join(out_dir, f"{name}_{tag}.npz"), **pack(p))
                 dims = p["dims"]
