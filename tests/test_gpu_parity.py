@@ -1,10 +1,12 @@
 """GPU parity: CUDA path (through the C ABI) vs the numpy oracle on the same seeded cases.  -m gpu"""
+import ast
+import glob
 import os
 
 import numpy as np
 import pytest
 
-from tests.helpers import conserved_errors, device_from_oracle, make_oracle
+from tests.helpers import conserved_errors, device_from_oracle, make_oracle, rel_l2
 
 pytestmark = pytest.mark.gpu
 
@@ -38,6 +40,30 @@ def test_steps_match_oracle(tmp_cases, name, kw, nsteps):
     assert err["rhoTheta"] <= TOL
     assert err["rhoU_scaled"] <= TOL
     ctx.close()
+
+
+_GOLD = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("path", _GOLD, ids=[os.path.basename(q)[:-4] for q in _GOLD])
+def test_device_matches_the_reference_binary_dumps(tmp_cases, path):
+    """The CUDA path against the dumps of the UNMODIFIED reference binary (tests/golden/*.npz, made by make_golden.py), at their full
+    step counts -- among them 100 steps of examples/atmo/srtb (BASELINE configs[0], north_star: <= 1e-11 after 100 steps) --
+    with no oracle run in between."""
+    g = np.load(path)
+    case, kw, nsteps = str(g["case"]), ast.literal_eval(str(g["kwargs"])), int(g["nsteps"])
+    orc = make_oracle(tmp_cases, case, nsteps, exact=False, **kw)
+    ctx = device_from_oracle(orc)
+    ctx.step(nsteps)
+    rho, U, T, p = ctx.download_state()
+    ctx.close()
+    nb, T0 = orc.gB, orc.p.T0
+    c0 = np.sqrt(orc.gamma * orc.R * T0)
+    err = dict(rho=rel_l2(rho[:nb], g["rho"]),
+               rhoTheta=rel_l2(rho[:nb] * (T[:nb] + T0), g["rho"] * (g["T"] + T0)),
+               rhoU_scaled=rel_l2(rho[:nb, None] * U[:nb], g["rho"][:, None] * g["U"], scale=np.linalg.norm(g["rho"]) * c0))
+    print(os.path.basename(path), nsteps, err)
+    assert err["rho"] <= TOL and err["rhoTheta"] <= TOL and err["rhoU_scaled"] <= TOL, err
 
 
 def test_non_trilinear_metrics_run_the_stored_metric_kernels(tmp_cases):
