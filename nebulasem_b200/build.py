@@ -45,7 +45,7 @@ HOST_FLAGS = ["-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-fopenmp", "-W
 
 def build_host(force: bool = False) -> str:
     hdir = os.path.join(CSRC, "host")
-    srcs = [os.path.join(hdir, f) for f in ("io.cpp", "mesh.cpp", "dg.cpp", "partition.cpp", "euler_app.cpp", "capi_host.cpp")]
+    srcs = [os.path.join(hdir, f) for f in ("io.cpp", "mesh.cpp", "dg.cpp", "partition.cpp", "euler_app.cpp", "amr.cpp", "capi_host.cpp")]
     metis = os.path.join(os.path.dirname(os.path.dirname(NVCC)), "targets", "x86_64-linux", "lib", "libmetis_static.a")
     metis_flags = ["-DNSEM_WITH_METIS"] if os.path.exists(metis) else []
     metis_libs = [metis] if os.path.exists(metis) else []

@@ -11,7 +11,7 @@
 using namespace nsemh;
 
 struct nsemh_solver {
-    EulerSolver s;
+    std::unique_ptr<EulerSolver> sp{new EulerSolver()};    // replaced by the solver on the regridded mesh at an AMR regrid
     std::string err;
 };
 static std::string g_err;
@@ -53,10 +53,10 @@ void nsemh_close(nsemh_solver* h) { delete h; }
 nsemh_solver* nsemh_open_case(const char* dir, int step) {
     nsemh_solver* h = new nsemh_solver();
     try {
-        h->s.read_controls(dir);
-        h->s.load_mesh(step);
-        h->s.read_fields(step);
-        h->s.setup();
+        (*h->sp).read_controls(dir);
+        (*h->sp).load_mesh(step);
+        (*h->sp).read_fields(step);
+        (*h->sp).setup();
         return h;
     } catch (const std::exception& e) {
         g_err = e.what();
@@ -71,7 +71,7 @@ nsemh_solver* nsemh_open_case(const char* dir, int step) {
 nsemh_solver* nsemh_synthetic_part(const char* kind_, int nx, int ny, int nz, int order, int rank, int nranks,
                                    const char* decomp, int px, int py, int pz) {
     nsemh_solver* h = new nsemh_solver();
-    EulerSolver& s = h->s;
+    EulerSolver& s = (*h->sp);
     const std::string kind = kind_;
     const int pxyz[3] = {px, py, pz};
     auto mesh = [&](const Grid& g) {
@@ -157,51 +157,73 @@ nsemh_solver* nsemh_synthetic(const char* kind, int nx, int ny, int nz, int orde
     return nsemh_synthetic_part(kind, nx, ny, nz, order, 0, 1, "METIS", 1, 1, 1);
 }
 
-#define GUARD(body)                         \
-    try { body; return 0; }                 \
+#define GUARD(...)                          \
+    try { __VA_ARGS__; return 0; }          \
     catch (const std::exception& e) { h->err = e.what(); return 1; }
 
-int nsemh_attach(nsemh_solver* h, int device, int rank, int nranks, const void* uid) { GUARD(h->s.attach_device(device, rank, nranks, uid)) }
-int nsemh_step(nsemh_solver* h, int n) { GUARD(h->s.step(n)) }
-int nsemh_upload(nsemh_solver* h) { GUARD(h->s.upload_state()) }
-int nsemh_download(nsemh_solver* h) { GUARD(h->s.download()) }
-int nsemh_upload_async(nsemh_solver* h) { GUARD(h->s.upload_state_async()) }
-int nsemh_download_async(nsemh_solver* h) { GUARD(h->s.download_async()) }
+int nsemh_attach(nsemh_solver* h, int device, int rank, int nranks, const void* uid) { GUARD((*h->sp).attach_device(device, rank, nranks, uid)) }
+int nsemh_step(nsemh_solver* h, int n) { GUARD((*h->sp).step(n)) }
+int nsemh_upload(nsemh_solver* h) { GUARD((*h->sp).upload_state()) }
+int nsemh_download(nsemh_solver* h) { GUARD((*h->sp).download()) }
+int nsemh_upload_async(nsemh_solver* h) { GUARD((*h->sp).upload_state_async()) }
+int nsemh_download_async(nsemh_solver* h) { GUARD((*h->sp).download_async()) }
 // AMR field transfer on the device: solver `h` (regridded mesh) takes the state of `old` (EulerSolver::adopt_refined_state)
 int nsemh_adopt_refined_state(nsemh_solver* h, nsemh_solver* old, const uint32_t* refineMap, uint32_t nr, const uint32_t* coarseMap, uint32_t nc,
                               const uint32_t* cellMap, uint32_t nm, int restart) {
-    GUARD(h->s.adopt_refined_state(old->s, std::vector<u32>(refineMap, refineMap + nr), std::vector<u32>(coarseMap, coarseMap + nc),
+    GUARD((*h->sp).adopt_refined_state((*old->sp), std::vector<u32>(refineMap, refineMap + nr), std::vector<u32>(coarseMap, coarseMap + nc),
                                    std::vector<u32>(cellMap, cellMap + nm), restart != 0))
 }
-int nsemh_restart_state(nsemh_solver* h) { GUARD(h->s.restart_state()) }
-int nsemh_write(nsemh_solver* h, int index) { GUARD(h->s.write_fields(index)) }
-int nsemh_run(nsemh_solver* h) { GUARD(h->s.run()) }
-int nsemh_sync(nsemh_solver* h) { GUARD(if (nsem_sync(h->s.ctx)) throw Error(nsem_last_error(h->s.ctx))) }
+// AMR regrid in memory (amr.cpp): the handle continues as the solver on the regridded mesh, state transferred on the device when attached.
+// refine / coarsen: one flag per current cell; NULL, NULL = tag by the refinement{} indicator of the controls.
+int nsemh_regrid(nsemh_solver* h, const uint8_t* refine, const uint8_t* coarsen, uint32_t n) {
+    GUARD(std::unique_ptr<EulerSolver> nw = (refine && coarsen)
+              ? (*h->sp).regridded(std::vector<uint8_t>(refine, refine + n), std::vector<uint8_t>(coarsen, coarsen + n))
+              : (*h->sp).regridded_by_indicator();
+          h->sp = std::move(nw))
+}
+int nsemh_enable_amr(nsemh_solver* h, double dx, double dy, double dz, const char* field, double fmin, double fmax, int max_level, int buffer_zone) {
+    GUARD(EulerSolver& s = *h->sp;
+          if (!s.forest) throw Error("nsemh_enable_amr: the solver has no AMR forest (create it with NSEM_AMR=1 or amr_step in the controls)");
+          s.refine_params.dir = Vec3{dx, dy, dz}; s.forest->dir = s.refine_params.dir;
+          if (field && *field) s.refine_params.field = field;
+          s.refine_params.field_min = fmin; s.refine_params.field_max = fmax; s.refine_params.max_level = max_level;
+          s.refine_params.buffer_zone = buffer_zone)
+}
+int nsemh_cell_levels(nsemh_solver* h, int32_t* out, uint32_t n) {
+    GUARD(if (!(*h->sp).forest) throw Error("nsemh_cell_levels: no AMR forest");
+          const std::vector<int> l = (*h->sp).forest->levels();
+          if (l.size() != n) throw Error("nsemh_cell_levels: one entry per real cell expected");
+          std::copy(l.begin(), l.end(), out))
+}
+int nsemh_restart_state(nsemh_solver* h) { GUARD((*h->sp).restart_state()) }
+int nsemh_write(nsemh_solver* h, int index) { GUARD((*h->sp).write_fields(index)) }
+int nsemh_run(nsemh_solver* h) { GUARD(run_case(h->sp)) }
+int nsemh_sync(nsemh_solver* h) { GUARD(if (nsem_sync((*h->sp).ctx)) throw Error(nsem_last_error((*h->sp).ctx))) }
 int nsemh_time(nsemh_solver* h, int nsteps, double* ms, double* per_kernel) {
-    GUARD(if (!h->s.ctx) throw Error("no device attached"); if (nsem_time_steps(h->s.ctx, nsteps, ms, per_kernel)) throw Error(nsem_last_error(h->s.ctx)))
+    GUARD(if (!(*h->sp).ctx) throw Error("no device attached"); if (nsem_time_steps((*h->sp).ctx, nsteps, ms, per_kernel)) throw Error(nsem_last_error((*h->sp).ctx)))
 }
 // {courant max, min, avg, mass, energy, volume} of the CURRENT device state + the initial totals mass0/energy0/volume0
 int nsemh_diagnostics(nsemh_solver* h, double out[9]) {
-    GUARD(if (!h->s.ctx) throw Error("no device attached"); if (nsem_diagnostics(h->s.ctx, out)) throw Error(nsem_last_error(h->s.ctx));
-          out[6] = h->s.mass0; out[7] = h->s.energy0; out[8] = h->s.volume0)
+    GUARD(if (!(*h->sp).ctx) throw Error("no device attached"); if (nsem_diagnostics((*h->sp).ctx, out)) throw Error(nsem_last_error((*h->sp).ctx));
+          out[6] = (*h->sp).mass0; out[7] = (*h->sp).energy0; out[8] = (*h->sp).volume0)
 }
-uint64_t nsemh_launch_count(nsemh_solver* h) { return h->s.ctx ? nsem_launch_count(h->s.ctx) : 0; }
-const char* nsemh_kernel_info(nsemh_solver* h) { return h->s.ctx ? nsem_kernel_info(h->s.ctx) : ""; }
+uint64_t nsemh_launch_count(nsemh_solver* h) { return (*h->sp).ctx ? nsem_launch_count((*h->sp).ctx) : 0; }
+const char* nsemh_kernel_info(nsemh_solver* h) { return (*h->sp).ctx ? nsem_kernel_info((*h->sp).ctx) : ""; }
 int nsemh_set_schedule(nsemh_solver* h, const uint32_t* order, uint32_t n) {
-    GUARD(if (nsem_set_schedule(h->s.ctx, order, n)) throw Error(nsem_last_error(h->s.ctx)))
+    GUARD(if (nsem_set_schedule((*h->sp).ctx, order, n)) throw Error(nsem_last_error((*h->sp).ctx)))
 }
 
 // out = {NPX, NPY, NPZ, NP, NPF, nBCS, nCells, nFacets, gBCSfield, gALL}
 int nsemh_dims(nsemh_solver* h, uint64_t out[10]) {
-    Basis b(h->s.nop);
-    const Geometry& g = h->s.geo;
+    Basis b((*h->sp).nop);
+    const Geometry& g = (*h->sp).geo;
     const uint64_t v[10] = {(uint64_t)b.NPX, (uint64_t)b.NPY, (uint64_t)b.NPZ, (uint64_t)b.NP, (uint64_t)b.NPF,
                             g.nBCS, g.nCells, g.nFacets, g.gBCSfield, g.gALL};
     std::memcpy(out, v, sizeof v);
     return 0;
 }
 int nsemh_params(nsemh_solver* h, double out[12]) {
-    const EulerSolver& s = h->s;
+    const EulerSolver& s = (*h->sp);
     const double v[12] = {s.P0, s.T0, s.cp, s.cv, s.viscosity, s.Pr, s.gravity[0], s.gravity[1], s.gravity[2], s.dt,
                           (double)s.buoyancy, (double)s.diffusion};
     std::memcpy(out, v, sizeof v);
@@ -209,7 +231,7 @@ int nsemh_params(nsemh_solver* h, double out[12]) {
 }
 
 const double* nsemh_f64(nsemh_solver* h, const char* name, uint64_t* n) {
-    EulerSolver& s = h->s;
+    EulerSolver& s = (*h->sp);
     const std::string k = name;
     const std::vector<double>* v = nullptr;
     if (k == "gCC") { *n = s.topo.CC.size() * 3; return s.topo.CC.empty() ? nullptr : s.topo.CC.data()->data(); }   // cell centroids (mesh.cpp:450-577)
@@ -227,19 +249,20 @@ const double* nsemh_f64(nsemh_solver* h, const char* name, uint64_t* n) {
     return v->data();
 }
 const uint32_t* nsemh_u32(nsemh_solver* h, const char* name, uint64_t* n) {
-    EulerSolver& s = h->s;
+    EulerSolver& s = (*h->sp);
     const std::string k = name;
     const std::vector<u32>* v = nullptr;
     if (k == "FO") v = &s.geo.FO; else if (k == "FN") v = &s.geo.FN; else if (k == "faceBegin") v = &s.geo.faceBegin;
     else if (k == "faceEnd") v = &s.geo.faceEnd; else if (k == "allFaces") v = &s.geo.allFaces; else if (k == "faceID") v = &s.geo.faceID;
     else if (k == "cellGlobal") v = &s.cellGlobal;
+    else if (k == "refineMap") v = &s.last_maps.refineMap; else if (k == "coarseMap") v = &s.last_maps.coarseMap; else if (k == "cellMap") v = &s.last_maps.cellMap;
     else if (k == "faceOwner") v = &s.geo.faceOwner; else if (k == "faceNeigh") v = &s.geo.faceNeigh; else if (k == "faceMortar") v = &s.geo.faceMortar;
     if (!v) { *n = 0; return nullptr; }
     *n = v->size();
     return v->data();
 }
 double* nsemh_state_ptr(nsemh_solver* h, const char* name) {
-    EulerSolver& s = h->s;
+    EulerSolver& s = (*h->sp);
     const std::string k = name;
     if (k == "rho") return s.rho.data();
     if (k == "U") return s.U.data();
@@ -249,15 +272,15 @@ double* nsemh_state_ptr(nsemh_solver* h, const char* name) {
 }
 // faces of boundary patch `name` (local ids); returns the count, copies at most cap entries
 uint64_t nsemh_patch_faces(nsemh_solver* h, const char* name, uint32_t* out, uint64_t cap) {
-    auto it = h->s.topo.boundaries.find(name);
-    if (it == h->s.topo.boundaries.end()) return 0;
+    auto it = (*h->sp).topo.boundaries.find(name);
+    if (it == (*h->sp).topo.boundaries.end()) return 0;
     for (uint64_t q = 0; q < it->second.size() && q < cap; q++) out[q] = it->second[q];
     return it->second.size();
 }
 // number of neighbouring ranks; copies them to out (ascending)
 int nsemh_peers(nsemh_solver* h, int* out, int cap) {
-    for (int q = 0; q < (int)h->s.peers.size() && q < cap; q++) out[q] = h->s.peers[q];
-    return (int)h->s.peers.size();
+    for (int q = 0; q < (int)(*h->sp).peers.size() && q < cap; q++) out[q] = (*h->sp).peers[q];
+    return (int)(*h->sp).peers.size();
 }
 // Decompose the grid file <grid_noext>.{txt,bin} into nparts (Prepare::decomposeMesh, field.cpp:1086-1257) without
 // building a solver: part_out[cell] = rank, mortar_out[face] = gFMC in the grid's own face numbering (either may be
@@ -279,6 +302,6 @@ int64_t nsemh_partition_grid(const char* grid_noext, int nparts, const char* met
     }
 }
 
-void nsemh_totals(nsemh_solver* h, double out[3]) { out[0] = h->s.mass0; out[1] = h->s.energy0; out[2] = h->s.volume0; }
+void nsemh_totals(nsemh_solver* h, double out[3]) { out[0] = (*h->sp).mass0; out[1] = (*h->sp).energy0; out[2] = (*h->sp).volume0; }
 
 }  // extern "C"

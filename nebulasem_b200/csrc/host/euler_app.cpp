@@ -71,12 +71,19 @@ void EulerSolver::read_controls(const std::string& case_dir) {
     if (!(ts == "BDF1" || ts == "AB1" || ts == "RK1" || ts == "RK2" || ts == "RK3" || ts == "RK4"))
         throw Error("time_scheme " + ts + " is not implemented on the GPU path (BDF1, AB1, RK1-RK4 are)");
     if (ctl.yes("general", "is_spherical", false)) throw Error("spherical meshes are not implemented on the GPU path");
-    // AmrIteration (iteration.h:94-147) regrids before step 1 and every amr_step dumps; that pipeline (Prepare::refineMesh, MeshObject::refineMesh,
-    // refineField) is not part of this build, which RUNS on non-conforming grids but does not create them: refuse instead of silently
-    // computing on the unrefined grid
-    if (ctl.integer("general", "amr_step", 0) != 0 && !std::getenv("NSEM_IGNORE_AMR_STEP"))
-        throw Error("controls ask for adaptive regridding (amr_step): the regrid is not implemented on the GPU path; remove amr_step to run on "
-                    "the grid as it is (grids the reference has already refined are supported), or set NSEM_IGNORE_AMR_STEP=1");
+    // AmrIteration (iteration.h:94-147): a regrid before step 1 and after every amr_step dumps; here in memory (amr.cpp), the state stays
+    // on the device (nsem_refine_state).  NSEM_IGNORE_AMR_STEP=1 runs on the grid as it is.
+    amr_step = std::getenv("NSEM_IGNORE_AMR_STEP") ? 0 : ctl.integer("general", "amr_step", 0);
+    refine_params.dir = ctl.vec("refinement", "direction", refine_params.dir);
+    refine_params.field = ctl.str("refinement", "field", refine_params.field);
+    refine_params.field_max = ctl.num("refinement", "field_max", refine_params.field_max);
+    refine_params.field_min = ctl.num("refinement", "field_min", refine_params.field_min);
+    refine_params.max_level = (int)ctl.integer("refinement", "max_level", refine_params.max_level);
+    refine_params.buffer_zone = (int)ctl.integer("refinement", "buffer_zone", refine_params.buffer_zone);
+    refine_params.limit = ctl.integer("refinement", "limit", refine_params.limit);
+    if (amr_step != 0 && nranks > 1)
+        throw Error("controls ask for adaptive regridding (amr_step) on " + std::to_string(nranks) + " partitions: the in-memory regrid runs on one "
+                    "partition (repartitioning a regridded mesh is not built); run one process or set NSEM_IGNORE_AMR_STEP=1");
     if (ctl.str("general", "state", "STEADY") != "TRANSIENT") throw Error("state must be TRANSIENT");
 }
 
@@ -84,6 +91,13 @@ void EulerSolver::set_mesh(const Grid& g) {
     topo.load(g);
     Basis b(nop);
     geo.build(topo, b);
+    // the AMR forest starts from the grid as loaded (conforming hexahedra); only built when a regrid can follow
+    forest.reset();
+    if (amr_step != 0 || std::getenv("NSEM_AMR")) {
+        forest = std::make_shared<AmrForest>();
+        try { forest->init(g, refine_params.dir); }
+        catch (const Error&) { forest.reset(); }      // a grid that is already non-conforming cannot seed the forest: regridded() says so
+    }
 }
 
 void EulerSolver::set_mesh_partition(const Grid& global, int rank_, int nranks_, const std::string& type, const int nxyz[3]) {
@@ -244,6 +258,7 @@ void EulerSolver::set_fields(const FieldFile& frho, const FieldFile& fU, const F
     T = init_field(fT, geo, gravity);
     rho = init_field(frho, geo, gravity);
     bc_p = fp.bcs; bc_U = fU.bcs; bc_T = fT.bcs; bc_rho = frho.bcs;
+    file_bc_p = fp.bcs; file_bc_U = fU.bcs; file_bc_T = fT.bcs; file_bc_rho = frho.bcs;
     for (const auto& kv : topo.boundaries)
         if (kv.first.find("interMesh") != std::string::npos)
             for (auto* list : {&bc_p, &bc_U, &bc_T, &bc_rho}) {
@@ -434,6 +449,7 @@ static std::vector<u32> morton_schedule(const MeshTopo& t) {
 void EulerSolver::attach_device(int device, int rank, int nranks, const void* uid) {
     if (ctx) { nsem_destroy(ctx); ctx = nullptr; }
     if (nsem_create(device, rank, nranks, uid, &ctx)) throw Error(nsem_last_error(nullptr));
+    device_id = device;
     auto ck = [&](int rc) { if (rc) throw Error(nsem_last_error(ctx)); };
     Basis b(nop);
     ck(nsem_set_order(ctx, b.NPX, b.NPY, b.NPZ));
@@ -608,6 +624,32 @@ void EulerSolver::run() {
         }
     }
     if (nsem_sync(ctx)) throw Error(nsem_last_error(ctx));
+}
+
+
+// AmrIteration (iteration.h:94-147) around Iteration: with amr_step != 0 a regrid before the first step and after every amr_step dumps.
+// The solver object is replaced by the one on the regridded mesh; the grid of every regrid is written as <mesh>_<dump>.txt.
+void run_case(std::unique_ptr<EulerSolver>& s) {
+    if (s->amr_step == 0) { s->run(); return; }
+    auto regrid = [&](long dump) {
+        std::unique_ptr<EulerSolver> n = s->regridded_by_indicator();
+        const u32 before = s->geo.nBCS;
+        s = std::move(n);
+        write_grid_text(s->dir + "/" + s->meshName + "_" + std::to_string(dump) + ".txt", s->forest->grid());
+        std::printf("Regrid at dump %ld: %u -> %u cells\n", dump, before, s->geo.nBCS);
+    };
+    const long last = s->end_step;
+    long dump = s->start_step;
+    regrid(dump);
+    while (dump * s->write_interval < last) {
+        const long upto = std::min(last, (dump + s->amr_step) * s->write_interval);
+        s->start_step = dump;
+        s->end_step = upto;
+        s->run();
+        s->end_step = last;
+        dump = upto / s->write_interval;
+        if (upto < last) regrid(dump);
+    }
 }
 
 }  // namespace nsemh

@@ -63,7 +63,8 @@ int main(int argc, char* argv[]) {
     }
     int rank = 0, world = 1, local = -1;
     try {
-        nsemh::EulerSolver s;
+        std::unique_ptr<nsemh::EulerSolver> sp(new nsemh::EulerSolver());
+        nsemh::EulerSolver& s = *sp;
         std::string ctl = argv[1];
         std::string dir = ".";
         const size_t slash = ctl.find_last_of('/');
@@ -94,7 +95,7 @@ int main(int argc, char* argv[]) {
             unsigned char id[128];
             if (world > 1) share_unique_id(dir, rank, id);
             s.attach_device(world > 1 ? local : (local < 0 ? 0 : local), rank, world, world > 1 ? id : nullptr);
-            s.run();
+            nsemh::run_case(sp);        // `s` is gone after a regrid: nothing below touches it
             if (rank == 0 && world > 1) ::unlink((dir + "/.nsem_nccl_id").c_str());
         }
         if (rank == 0) std::printf("Exiting application run with %d processes\n", world);

@@ -13,6 +13,7 @@
 #include <array>
 #include <cstdint>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -160,6 +161,43 @@ std::vector<double> init_field(const FieldFile& ff, const Geometry& g, const Vec
 void write_field(const std::string& path_noext, bool binary, int comps, const double* v, uint64_t n_nodes,
                  const std::vector<BCond>& bcs);
 
+// ---- adaptive regrid in memory (amr.cpp): Prepare::refineMesh tagging + MeshObject::refineMesh -----------------------
+struct RefineParams {                // refinement{} of the controls (Controls::enrollRefine, field.cpp:474-482; defaults field.h:18-40)
+    Vec3 dir{0, 0, 0};
+    std::string field = "U";
+    double field_max = 0.6, field_min = 0.2;
+    int max_level = 1, buffer_zone = 2;
+    long limit = 100000;
+};
+struct AmrForest {
+    struct Node {
+        u32 v[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // corners c0..c7 <-> (xi,eta,zeta) bits 000 100 110 010 001 101 111 011
+        int level = 0, parent = -1, child0 = -1, nchild = 0;
+    };
+    struct Maps { std::vector<u32> refineMap, coarseMap, cellMap; };    // as MeshObject::refineMesh returns them (mesh.cpp:2216-2748)
+    std::vector<Vec3> V;
+    std::vector<Node> nodes;
+    std::vector<int> leaves;                   // node of every cell of the current grid, in cell order
+    std::map<std::array<u32, 2>, u32> edgeMid;
+    std::map<std::array<u32, 4>, u32> faceMid;
+    std::map<std::array<u32, 4>, std::string> patchOf;    // boundary quads of every level -> patch name
+    Vec3 dir{0, 0, 0};
+    void init(const Grid& conforming_hex_grid, const Vec3& direction);
+    Maps regrid(const std::vector<uint8_t>& refine, const std::vector<uint8_t>& coarsen);   // one flag per current cell
+    Grid grid() const;                         // the current grid in the reference's format
+    std::vector<int> levels() const;
+    std::vector<std::vector<u32>> families() const;
+private:
+    int split_mask(const Node& n) const;
+    u32 mid_vertex(const std::vector<u32>& of);
+    void split(int node);
+};
+struct EulerSolver;
+// Prepare::refineMesh's tagging (field.cpp:606-620, 696-824): normalised indicator sqrt(|field|) (cV^0.125 / max), element means against
+// field_max / field_min, buffer zone, limits, whole families only, 2:1 balance across faces.  `levels` = refinement level per cell.
+void amr_tag_cells(const EulerSolver& s, const RefineParams& rp, const std::vector<int>& levels, const std::vector<std::vector<u32>>& families,
+                   std::vector<uint8_t>& refine, std::vector<uint8_t>& coarsen);
+
 // ---- the solver app ------------------------------------------------------------------------------------------------
 struct EulerSolver {
     Controls ctl;
@@ -212,6 +250,17 @@ struct EulerSolver {
     void adopt_refined_state(EulerSolver& old, const std::vector<u32>& refineMap, const std::vector<u32>& coarseMap,
                              const std::vector<u32>& cellMap, bool restart);
     void restart_state();                                 // nsem_restart_state: p from rho, ghost cells from the resident state
+    // AMR in memory (AmrIteration::next, iteration.h:124-141, without the files): the forest persists across regrids
+    std::shared_ptr<AmrForest> forest;
+    RefineParams refine_params;
+    long amr_step = 0;
+    AmrForest::Maps last_maps;                            // maps of the regrid that produced this solver's mesh
+    std::vector<BCond> file_bc_rho, file_bc_U, file_bc_T, file_bc_p;   // boundary conditions as the field files state them
+    int device_id = -1;
+    // the solver on the regridded mesh: same controls and boundary conditions, mesh from the forest after regrid(refine, coarsen), set-up
+    // done; when this solver is attached the new one is attached to the same device and takes the state (adopt_refined_state, restart)
+    std::unique_ptr<EulerSolver> regridded(const std::vector<uint8_t>& refine, const std::vector<uint8_t>& coarsen);
+    std::unique_ptr<EulerSolver> regridded_by_indicator();   // amr_tag_cells on the downloaded state, then regridded()
     void download();
     void write_fields(int index);                         // Mesh::write_fields; with nranks > 1 into <case>/grid<rank>/ like the
                                                           // reference's per-rank working directories (field.cpp:1436-1440)
@@ -225,5 +274,7 @@ private:
     std::vector<std::vector<u32>> keep_faces_;
     void build_c_bcs();
 };
+
+void run_case(std::unique_ptr<EulerSolver>& s);          // EulerSolver::run, with the AMR cycle around it when amr_step != 0
 
 }  // namespace nsemh

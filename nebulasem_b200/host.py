@@ -16,7 +16,7 @@ from . import capi
 HOST_LIB_PATH = os.path.join(os.environ.get("NSEM_LIBDIR") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib"), "libnsem_host.so")
 HOST_EXPORTS = ["nsemh_error", "nsemh_close", "nsemh_open_case", "nsemh_synthetic", "nsemh_synthetic_part", "nsemh_patch_faces",
                 "nsemh_peers", "nsemh_diagnostics", "nsemh_attach", "nsemh_step",
-                "nsemh_upload", "nsemh_download", "nsemh_upload_async", "nsemh_download_async", "nsemh_adopt_refined_state", "nsemh_restart_state", "nsemh_write", "nsemh_run", "nsemh_sync", "nsemh_time",
+                "nsemh_upload", "nsemh_download", "nsemh_upload_async", "nsemh_download_async", "nsemh_adopt_refined_state", "nsemh_restart_state", "nsemh_regrid", "nsemh_enable_amr", "nsemh_cell_levels", "nsemh_write", "nsemh_run", "nsemh_sync", "nsemh_time",
                 "nsemh_launch_count", "nsemh_kernel_info", "nsemh_set_schedule", "nsemh_dims", "nsemh_params", "nsemh_f64", "nsemh_u32",
                 "nsemh_state_ptr", "nsemh_totals", "nsemh_partition_grid"]
 _lib = None
@@ -50,6 +50,10 @@ def load_host_library() -> C.CDLL:
         getattr(lib, n).argtypes = [vp]
     lib.nsemh_step.argtypes = [vp, C.c_int]
     u32p = C.POINTER(C.c_uint32)
+    u8p = C.POINTER(C.c_uint8)
+    lib.nsemh_regrid.argtypes = [vp, u8p, u8p, C.c_uint32]
+    lib.nsemh_enable_amr.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_char_p, C.c_double, C.c_double, C.c_int, C.c_int]
+    lib.nsemh_cell_levels.argtypes = [vp, C.POINTER(C.c_int32), C.c_uint32]
     lib.nsemh_adopt_refined_state.argtypes = [vp, vp, u32p, C.c_uint32, u32p, C.c_uint32, u32p, C.c_uint32, C.c_int]
     lib.nsemh_write.argtypes = [vp, C.c_int]
     lib.nsemh_time.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -98,14 +102,17 @@ class Solver:
         if not handle:
             raise capi.NsemError(self.lib.nsemh_error(None).decode())
         self.h = C.c_void_p(handle)
-        d = (C.c_uint64 * 10)()
-        self.lib.nsemh_dims(self.h, d)
-        (self.NPX, self.NPY, self.NPZ, self.NP, self.NPF, self.nBCS, self.nCells, self.nFacets, self.gBCSfield,
-         self.gALL) = [int(x) for x in d]
+        self._refresh_dims()
         p = (C.c_double * 12)()
         self.lib.nsemh_params(self.h, p)
         self.params = dict(P0=p[0], T0=p[1], cp=p[2], cv=p[3], viscosity=p[4], Pr=p[5], gravity=(p[6], p[7], p[8]),
                            dt=p[9], buoyancy=bool(p[10]), diffusion=bool(p[11]))
+
+    def _refresh_dims(self):
+        d = (C.c_uint64 * 10)()
+        self.lib.nsemh_dims(self.h, d)
+        (self.NPX, self.NPY, self.NPZ, self.NP, self.NPF, self.nBCS, self.nCells, self.nFacets, self.gBCSfield,
+         self.gALL) = [int(x) for x in d]
 
     @classmethod
     def open_case(cls, case_dir: str, step: int = 0) -> "Solver":
@@ -207,6 +214,31 @@ class Solver:
         for m in maps:
             args += [m.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_uint32(m.size)]
         self._ck(self.lib.nsemh_adopt_refined_state(self.h, old.h, *args, 1 if restart else 0))
+
+    # ---- AMR in memory (amr.cpp).  The solver must have been created with NSEM_AMR=1 in the environment or amr_step in its controls.
+    def enable_amr(self, direction=(0.0, 0.0, 0.0), field="T", field_min=0.2, field_max=0.6, max_level=1, buffer_zone=2):
+        """refinement{} parameters (Controls::enrollRefine); direction = the axis that is never split (2-D refinement), zero = 3-D."""
+        self._ck(self.lib.nsemh_enable_amr(self.h, float(direction[0]), float(direction[1]), float(direction[2]), field.encode(),
+                                           float(field_min), float(field_max), int(max_level), int(buffer_zone)))
+
+    def regrid(self, refine=None, coarsen=None):
+        """Regrid: this handle continues as the solver on the new mesh; when attached, the state is transferred on the device
+        (nsem_refine_state + nsem_restart_state) and the old context is destroyed.  refine / coarsen: one flag per cell; both None =
+        tag by the refinement indicator.  The maps of the regrid are u32("refineMap" | "coarseMap" | "cellMap")."""
+        if refine is None and coarsen is None:
+            self._ck(self.lib.nsemh_regrid(self.h, None, None, 0))
+        else:
+            r = np.ascontiguousarray(refine, dtype=np.uint8)
+            c = np.ascontiguousarray(coarsen, dtype=np.uint8)
+            assert r.size == self.nBCS and c.size == self.nBCS
+            u8p = C.POINTER(C.c_uint8)
+            self._ck(self.lib.nsemh_regrid(self.h, r.ctypes.data_as(u8p), c.ctypes.data_as(u8p), r.size))
+        self._refresh_dims()
+
+    def cell_levels(self) -> np.ndarray:
+        out = np.zeros(self.nBCS, dtype=np.int32)
+        self._ck(self.lib.nsemh_cell_levels(self.h, out.ctypes.data_as(C.POINTER(C.c_int32)), out.size))
+        return out
 
     def restart_state(self):
         """The set-up's restart branch on the device (euler.cpp:150-162): p from rho, ghost cells of rho, p, U, T (nsem_restart_state)."""
