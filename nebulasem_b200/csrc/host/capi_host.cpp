@@ -259,7 +259,8 @@ const uint32_t* nsemh_u32(nsemh_solver* h, const char* name, uint64_t* n) {
     else if (k == "faceOwner") v = &s.geo.faceOwner; else if (k == "faceNeigh") v = &s.geo.faceNeigh; else if (k == "faceMortar") v = &s.geo.faceMortar;
     if (!v) { *n = 0; return nullptr; }
     *n = v->size();
-    return v->data();
+    static const uint32_t none = 0;                    // a known but empty array is not an unknown name
+    return v->empty() ? &none : v->data();
 }
 double* nsemh_state_ptr(nsemh_solver* h, const char* name) {
     EulerSolver& s = (*h->sp);

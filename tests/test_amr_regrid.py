@@ -1,0 +1,272 @@
+"""Adaptive regrid in memory (nebulasem_b200/csrc/host/amr.cpp): own octree regrid + tagging against the reference's regrids.
+
+The regrid is not a restatement of MeshObject::refineMesh (cell order and local frames differ), so grids are compared as SETS of cells
+(centroid, volume), facet and mortar-face counts, and fields through cell/node coordinates:
+  * tests/golden/refine_field/<case>/stage{0,1,2}: two regrids each of a 2-D and a 3-D case driven through the reference's refineMesh;
+  * tests/golden/srtb3d_amr, srtb_amr: the reference's own initial regrid (its tagging) of examples/atmo/srtb-3d (4^3) and srtb-amr.
+"""
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+RF = os.path.join(GOLD, "refine_field")
+CASES = [("3d_o2", (0, 0, 0)), ("2d_o4", (0, 0, 1))]
+
+
+@pytest.fixture(autouse=True)
+def _amr_env(monkeypatch):
+    monkeypatch.setenv("NSEM_AMR", "1")          # solvers created in these tests keep an AMR forest
+
+
+def cell_signature(s):
+    n = s.nBCS
+    a = np.concatenate([s.f64("gCC")[:3 * n].reshape(n, 3), s.f64("gCV")[:n, None]], axis=1)
+    return a[np.lexsort(np.round(a, 6).T[::-1])]
+
+
+def same_cells(a, b):
+    assert a.nBCS == b.nBCS and a.nFacets == b.nFacets
+    assert int((a.u32("faceMortar") > 0).sum()) == int((b.u32("faceMortar") > 0).sum())
+    sa, sb = cell_signature(a), cell_signature(b)
+    assert np.abs(sa - sb).max() <= 1e-12 * np.abs(sb).max()
+
+
+def match_cells(mine, ref, ids):
+    """cells of `mine` at the centroids of cells `ids` of `ref`"""
+    cm = mine.f64("gCC")[:3 * mine.nBCS].reshape(-1, 3)
+    cr = ref.f64("gCC").reshape(-1, 3)
+    out = []
+    for i in ids:
+        d = np.abs(cm - cr[i]).sum(axis=1)
+        j = int(np.argmin(d))
+        assert d[j] <= 1e-6
+        out.append(j)
+    return out
+
+
+def regrid_like_the_reference(name, direction, k, s, ref_prev):
+    """apply pass k of the golden case to solver s (whose cells are those of ref_prev in another order)"""
+    from nebulasem_b200 import host
+    g = np.load(os.path.join(RF, f"{name}_pass{k}.npz"))
+    r = np.zeros(s.nBCS, np.uint8)
+    c = np.zeros(s.nBCS, np.uint8)
+    r[match_cells(s, ref_prev, g["rCells"])] = 1
+    c[match_cells(s, ref_prev, np.nonzero(g["cCells"])[0])] = 1
+    s.regrid(r, c)
+    ref = host.Solver.open_case(os.path.join(RF, name, f"stage{k}"))
+    return g, ref
+
+
+@pytest.mark.parametrize("name,direction", CASES)
+def test_regrid_produces_the_cells_of_the_reference_regrid(name, direction):
+    from nebulasem_b200 import host
+    s = host.Solver.open_case(os.path.join(RF, name, "stage0"))
+    s.enable_amr(direction=direction)
+    prev = host.Solver.open_case(os.path.join(RF, name, "stage0"))
+    for k in (1, 2):
+        g, ref = regrid_like_the_reference(name, direction, k, s, prev)
+        same_cells(s, ref)
+        # the maps describe the regrid the way MeshObject::refineMesh does: every new cell is copied, split from or merged into
+        rm, cmap, km = s.u32("refineMap").astype(np.int64), s.u32("cellMap").astype(np.int64), s.u32("coarseMap").astype(np.int64)
+        assert len(rm) == len(g["refineMap"]) and len(km) == len(g["coarseMap"])
+        covered = np.zeros(s.nBCS, bool)
+        n_old = prev.nBCS
+        covered[cmap[:n_old][cmap[:n_old] != (1 << 31)]] = True
+        i = 0
+        while i < len(rm):
+            covered[cmap[rm[i + 2:i + 2 + rm[i]]]] = True
+            i += rm[i] + 2
+        i = 0
+        while i < len(km):
+            covered[cmap[km[i + 1]]] = True
+            i += km[i] + 2
+        assert covered.all()
+        lv = s.cell_levels()
+        assert lv.max() == k and lv.min() == 0
+        prev.close()
+        prev = ref
+    s.close()
+    prev.close()
+
+
+def test_tagging_reproduces_the_reference_initial_regrid_3d():
+    """refinement{field T, field_min 0.1, field_max 0.4, max_level 2} on the 4^3 bubble: the reference's own initial regrid
+    (tests/golden/srtb3d_amr, made by make_amr_golden.py) refines the same 44 cells."""
+    from nebulasem_b200 import host
+    s = host.Solver.synthetic("bubble3d", 4, 4, 4, 2)
+    s.enable_amr(direction=(0, 0, 0), field="T", field_min=0.1, field_max=0.4, max_level=2, buffer_zone=2)
+    s.regrid()
+    ref = host.Solver.open_case(os.path.join(GOLD, "srtb3d_amr"))
+    assert s.nBCS == 372
+    same_cells(s, ref)
+    s.close()
+    ref.close()
+
+
+FIELD_TXT = """size {comps}
+internal 1
+{{
+    {init}
+}}
+boundary 3
+{{
+    top {{
+        type {bc}
+    }}
+    bottom {{
+        type {bc}
+    }}
+    sides {{
+        type {bc}
+    }}
+}}
+"""
+
+
+def test_tagging_reproduces_the_reference_initial_regrid_2d(tmp_path):
+    """examples/atmo/srtb-amr (x-y plane, refinement{direction 0 0 1, field T, 0.4 / 0.5, max_level 2}): the reference's initial regrid
+    (tests/golden/srtb_amr) refines 32 of the 100 cells; the case is rebuilt here from the uniform grid and the example's initial fields."""
+    from nebulasem_b200 import host
+    d = tmp_path / "srtb_amr_start"
+    shutil.copytree(os.path.join(RF, "2d_o4", "stage0"), d)
+    for f in ("rho0.bin", "U0.bin", "T0.bin", "p0.bin"):
+        os.remove(d / f)
+    (d / "rho0.txt").write_text(FIELD_TXT.format(comps=1, init="uniform 0", bc="NEUMANN"))
+    (d / "p0.txt").write_text(FIELD_TXT.format(comps=1, init="uniform 0", bc="NEUMANN"))
+    (d / "U0.txt").write_text(FIELD_TXT.format(comps=3, init="uniform 0 0 0", bc="SYMMETRY"))
+    (d / "T0.txt").write_text(FIELD_TXT.format(comps=1, init="cosine 0 0.5    500 350 50   250 250 1000", bc="NEUMANN"))
+    s = host.Solver.open_case(str(d))
+    s.enable_amr(direction=(0, 0, 1), field="T", field_min=0.4, field_max=0.5, max_level=2, buffer_zone=2)
+    s.regrid()
+    ref = host.Solver.open_case(os.path.join(GOLD, "srtb_amr"))
+    assert s.nBCS == 196
+    same_cells(s, ref)
+    s.close()
+    ref.close()
+
+
+def test_regrid_refuses_what_it_cannot_do(monkeypatch):
+    from nebulasem_b200 import capi, host
+    s = host.Solver.open_case(os.path.join(GOLD, "srtb3d_amr"))        # already non-conforming: cannot seed the forest
+    with pytest.raises(capi.NsemError, match="no AMR forest"):
+        s.regrid()
+    s.close()
+    monkeypatch.delenv("NSEM_AMR")
+    s = host.Solver.synthetic("bubble3d", 3, 3, 3, 2)                  # no forest was asked for
+    with pytest.raises(capi.NsemError, match="no AMR forest"):
+        s.regrid(np.zeros(27, np.uint8), np.zeros(27, np.uint8))
+    s.close()
+
+
+def fields_by_coordinates(mine, ref, ref_fields):
+    """reference node values re-ordered to the nodes of `mine`: cells matched by centroid, nodes inside a cell by coordinates"""
+    NP, n = mine.NP, mine.nBCS
+    cells = match_cells(ref, mine, range(n))                             # ref cell of every cell of mine
+    xm = mine.f64("cC")[:n * NP * 3].reshape(n, NP, 3)
+    xr = ref.f64("cC")[:n * NP * 3].reshape(n, NP, 3)
+    idx = np.empty((n, NP), dtype=np.int64)
+    for c in range(n):
+        d = np.abs(xm[c][:, None, :] - xr[cells[c]][None, :, :]).sum(axis=2)
+        j = d.argmin(axis=1)
+        assert d[np.arange(NP), j].max() <= 1e-6 and len(set(j)) == NP
+        idx[c] = cells[c] * NP + j
+    idx = idx.reshape(-1)
+    return [np.asarray(f).reshape(ref.nBCS * NP, -1)[idx] for f in ref_fields]
+
+
+@pytest.mark.parametrize("name,direction", CASES)
+def test_regrid_maps_and_geometry_transfer_to_the_reference_fields(name, direction):
+    """The maps and the geometry of the own regrid, fed to the (reference-pinned) numpy transfer oracle, give the fields the reference
+    wrote after ITS regrid, node by node through coordinates: what nsem_refine_state receives from EulerSolver::regridded is right."""
+    from nebulasem_b200 import host
+    from oracle import amr
+    s = host.Solver.open_case(os.path.join(RF, name, "stage0"))
+    s.enable_amr(direction=direction)
+    prev = host.Solver.open_case(os.path.join(RF, name, "stage0"))
+    g1 = np.load(os.path.join(RF, f"{name}_pass1.npz"))
+    npts = tuple(int(x) for x in g1["dims"][:3])
+    NP = s.NP
+    fields = [g1["pre_rho"].reshape(-1, 1), g1["pre_U"].reshape(-1, 3), g1["pre_T"].reshape(-1, 1)]
+    fields = [f[:s.nBCS * NP] for f in fields]
+    for k in (1, 2):
+        n_old = s.nBCS
+        oldCV, oldCC, cC_old = s.f64("gCV")[:n_old], s.f64("gCC")[:3 * n_old], s.f64("cC")[:n_old * NP * 3]
+        g, ref = regrid_like_the_reference(name, direction, k, s, prev)
+        n_new = s.nBCS
+        args = (npts, s.u32("refineMap"), s.u32("coarseMap"), s.u32("cellMap"), n_new, oldCV, oldCC, s.f64("gCC")[:3 * n_new],
+                s.f64("gCV")[:n_new], cC_old, [g[f"psiRef{i}"] for i in range(6)], [g[f"psiCor{i}"] for i in range(6)],
+                [g[f"wgl{i}"] for i in range(3)])
+        fields = [amr.refine_field(f, *args) for f in fields]
+        want = fields_by_coordinates(s, ref, [g["post_rho"], g["post_U"], g["post_T"]])
+        for nm, mine, w in zip(("rho", "U", "T"), fields, want):
+            assert np.abs(mine - w).max() <= 1e-13 * max(np.abs(w).max(), 1e-300), (k, nm)
+        prev.close()
+        prev = ref
+    s.close()
+    prev.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------------
+# GPU
+# ---------------------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,direction", CASES)
+def test_regrid_and_device_transfer_reproduce_the_reference_fields(name, direction):
+    """Own regrid + nsem_refine_state == the fields the reference wrote after ITS regrid, compared node by node through coordinates
+    (cell order and local frames differ, so the sums run in another order: 1e-13 relative instead of bit-identical)."""
+    from nebulasem_b200 import host
+    s = host.Solver.open_case(os.path.join(RF, name, "stage0"))
+    s.enable_amr(direction=direction)
+    s.attach(0)
+    prev = host.Solver.open_case(os.path.join(RF, name, "stage0"))
+    g1 = np.load(os.path.join(RF, f"{name}_pass1.npz"))
+    n = s.nBCS * s.NP
+    rho, U, T, p = [x.copy() for x in s.state()]                         # stage0 has the reference's cell order: set the pre-regrid fields
+    rho[:n], U[:n], T[:n], p[:n] = g1["pre_rho"].reshape(-1)[:n], g1["pre_U"].reshape(-1, 3)[:n], g1["pre_T"].reshape(-1)[:n], g1["pre_p"].reshape(-1)[:n]
+    s.set_state(rho, U, T, p)
+    s.upload()
+    for k in (1, 2):
+        g, ref = regrid_like_the_reference(name, direction, k, s, prev)
+        s.download()
+        nn = s.nBCS * s.NP
+        want = fields_by_coordinates(s, ref, [g["post_rho"], g["post_U"], g["post_T"]])
+        for nm, comps, dev, w in zip(("rho", "U", "T"), (1, 3, 1), s.state()[:3], want):
+            dev = np.asarray(dev).reshape(-1, comps)[:nn]
+            assert np.abs(dev - w).max() <= 1e-13 * max(np.abs(w).max(), 1e-300), (k, nm)
+        prev.close()
+        prev = ref
+    s.close()
+    prev.close()
+
+
+@pytest.mark.gpu
+def test_amr_cycle_on_the_device_conserves_mass():
+    """regrid by the indicator -> steps -> regrid -> steps on one B200, the state never leaving the device: finite, mass as at the start
+    (the transfer restores every family's integral, the fluxes on the non-conforming grid are conservative), cells follow the bubble."""
+    from nebulasem_b200 import host
+    s = host.Solver.synthetic("bubble3d", 4, 4, 4, 2)
+    s.enable_amr(direction=(0, 0, 0), field="T", field_min=0.1, field_max=0.4, max_level=2, buffer_zone=2)
+    s.attach(0)
+
+    def mass():
+        s.download()
+        n = s.gBCSfield
+        return float((s.state()[0][:n] * s.f64("cV")[:n]).sum())
+
+    m0 = mass()
+    cells = [s.nBCS]
+    for cycle in range(3):
+        s.regrid()
+        cells.append(s.nBCS)
+        assert abs(mass() - m0) <= 1e-12 * abs(m0), cycle
+        s.step(10)
+        assert abs(mass() - m0) <= 1e-12 * abs(m0), cycle
+    rho, U, T, p = s.state()
+    assert all(np.isfinite(x).all() for x in (rho, U, T, p))
+    assert cells[1] == 372 and s.cell_levels().max() >= 1
+    assert "mortar" in s.kernel_info
+    s.close()

@@ -92,3 +92,35 @@ def test_two_processes_equal_one_process(tmp_path, name):
     for f in ("rho", "U", "T", "p"):
         va, vb = refio.read_field_values(os.path.join(a, f + str(idx))), refio.read_field_values(os.path.join(b, f + str(idx)))
         assert va.shape == vb.shape and np.array_equal(va, vb), f
+
+
+@pytest.mark.gpu
+def test_euler_binary_runs_the_amr_cycle(tmp_path):
+    """`euler ./controls` with amr_step (BASELINE configs[4] in small): regrid before step 1 and after every dump, in memory, the state
+    transferred on the device; every dump matches the grid of its regrid, mass stays what it was (1e-12)."""
+    a = str(tmp_path / "bubble3d_amr_cycle")
+    ocases.CASES["bubble3d"](n=4, order=2).write(a, 15)
+    ctl = open(os.path.join(a, "controls")).read()
+    ctl = ctl.replace("write_interval 15", "write_interval 5\n    amr_step 1")
+    ctl += "refinement\n{\n    direction 0 0 0\n    field T\n    field_min 0.1\n    field_max 0.4\n    max_level 2\n    limit 100000\n}\n"
+    open(os.path.join(a, "controls"), "w").write(ctl)
+    run_euler(a, 1)
+    from nebulasem_b200 import host
+    masses = []
+    for dump, grid in ((1, 0), (2, 1), (3, 2)):          # dump k was computed on the grid written at regrid k-1
+        assert os.path.exists(os.path.join(a, f"grid_{grid}.txt"))
+        rho = refio.read_field_values(os.path.join(a, f"rho{dump}"))[:, 0]
+        T = refio.read_field_values(os.path.join(a, f"T{dump}"))[:, 0]
+        case = str(tmp_path / f"check{dump}")
+        os.makedirs(case)
+        shutil.copy(os.path.join(a, f"grid_{grid}.txt"), os.path.join(case, "grid_0.txt"))
+        for f in ("rho", "U", "T", "p"):
+            shutil.copy(os.path.join(a, f"{f}{dump}.bin"), os.path.join(case, f"{f}0.bin"))
+        open(os.path.join(case, "controls"), "w").write(ctl.replace("amr_step 1", ""))
+        s = host.Solver.open_case(case)
+        assert rho.shape[0] == s.gBCSfield and np.isfinite(rho).all() and np.isfinite(T).all()
+        masses.append(float((rho * s.f64("cV")[:s.gBCSfield]).sum()))
+        if dump == 1:
+            assert s.nBCS == 372                        # the reference's initial regrid of this case refines the same 44 cells
+        s.close()
+    assert max(abs(m - masses[0]) for m in masses) <= 1e-12 * abs(masses[0]), masses

@@ -121,14 +121,24 @@ def test_errors_are_reported_not_swallowed(tmp_cases):
     s = host.Solver.open_case(orc.case_dir)
     with pytest.raises(capi.NsemError, match="no device attached|no CPU fallback"):
         s.step(1)        # the hot path has no CPU fallback
-    # adaptive regridding (AmrIteration, iteration.h:94-147) is not part of this build: asked for, it is refused, not skipped
+    # adaptive regridding (AmrIteration, iteration.h:94-147): asked for, the solver keeps an AMR forest over the grid (tests/test_amr_regrid.py);
+    # a grid that is already non-conforming cannot seed it and a regrid on it is refused, not skipped
     import shutil
     amr = os.path.join(str(tmp_cases), "asks_for_amr")
     shutil.copytree(orc.case_dir, amr)
     txt = open(os.path.join(amr, "controls")).read().replace("end_step", "amr_step 1\n    end_step", 1)
     open(os.path.join(amr, "controls"), "w").write(txt)
-    with pytest.raises(capi.NsemError, match="amr_step"):
-        host.Solver.open_case(amr)
+    s = host.Solver.open_case(amr)
+    assert (s.cell_levels() == 0).all()
+    s.close()
+    amr2 = os.path.join(str(tmp_cases), "asks_for_amr_on_a_regridded_grid")
+    shutil.copytree(os.path.join(ROOT, "tests", "golden", "srtb3d_amr"), amr2)
+    txt = open(os.path.join(amr2, "controls")).read().replace("end_step", "amr_step 1\n    end_step", 1)
+    open(os.path.join(amr2, "controls"), "w").write(txt)
+    s = host.Solver.open_case(amr2)
+    with pytest.raises(capi.NsemError, match="no AMR forest"):
+        s.regrid()
+    s.close()
 
 
 def test_c_abi_exports_every_declared_symbol():
