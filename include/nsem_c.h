@@ -126,6 +126,10 @@ int nsem_set_schedule(nsem_ctx* ctx, const uint32_t* order, uint32_t n);
  * rho, U (AoS 3), T (perturbation theta - T0, euler.cpp:181,286), p (perturbation p - p_ref). */
 int nsem_upload_state(nsem_ctx* ctx, const double* rho, const double* U, const double* T, const double* p);
 int nsem_download_state(nsem_ctx* ctx, double* rho, double* U, double* T, double* p);
+/* Operator-level view for unit parity: the results of gradf<strong>(U) and gradf<strong>(T) + fillBCs(r, fIndex) (field.h:3328-3362,
+ * 2731-2769) of the last nsem_euler_step, per unit volume, ghost nodes included: grad_U as Tensor (9 per node, XX,YY,ZZ,XY,YZ,XZ,YX,ZY,ZX
+ * with G[ab] = d_a U_b), grad_T as Vector.  Only with diffusion on (euler.cpp:189-190); NULL arrays are skipped. */
+int nsem_download_gradients(nsem_ctx* ctx, double* grad_U, double* grad_T);
 /* Pipelined variants for drivers that stream batches through the device: both only ENQUEUE and return.  The upload copies on a
  * copy-in stream into its own staging buffer and converts the layout on the compute stream, ordered after everything enqueued
  * before it; the download converts on the compute stream into a second staging buffer and copies out on a copy-out stream, so

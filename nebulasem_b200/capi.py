@@ -62,7 +62,7 @@ class NsemRegrid(C.Structure):
 EXPORTS = ["nsem_create", "nsem_destroy", "nsem_last_error", "nsem_get_unique_id", "nsem_set_order", "nsem_set_basis",
            "nsem_upload_mesh", "nsem_set_bcs", "nsem_set_halo", "nsem_set_params", "nsem_set_schedule",
            "nsem_pin_host", "nsem_upload_state", "nsem_download_state", "nsem_upload_state_async", "nsem_download_state_async", "nsem_upload_ref", "nsem_upload_geopotential", "nsem_euler_step", "nsem_exchange_state_halos", "nsem_diagnostics",
-           "nsem_sync", "nsem_time_steps", "nsem_launch_count", "nsem_kernel_info", "nsem_refine_state", "nsem_restart_state"]
+           "nsem_sync", "nsem_time_steps", "nsem_launch_count", "nsem_kernel_info", "nsem_refine_state", "nsem_restart_state", "nsem_download_gradients"]
 
 _lib = None
 
@@ -95,6 +95,7 @@ def load_library() -> C.CDLL:
     lib.nsem_download_state.argtypes = [vp, _dp, _dp, _dp, _dp]
     lib.nsem_upload_state_async.argtypes = [vp, _dp, _dp, _dp, _dp]
     lib.nsem_download_state_async.argtypes = [vp, _dp, _dp, _dp, _dp]
+    lib.nsem_download_gradients.argtypes = [vp, _dp, _dp]
     lib.nsem_refine_state.argtypes = [vp, C.POINTER(NsemRegrid), vp]
     lib.nsem_restart_state.argtypes = [vp]
     lib.nsem_upload_ref.argtypes = [vp, _dp, _dp, _dp]
@@ -253,6 +254,13 @@ class Context:
         rho, U, T, p = np.zeros(n), np.zeros((n, 3)), np.zeros(n), np.zeros(n)
         self._ck(self.lib.nsem_download_state(self.h, _pd(rho), _pd(U), _pd(T), _pd(p)))
         return rho, U, T, p
+
+    def download_gradients(self):
+        """(gradf<strong>(U) as [n, 9] in the reference's Tensor order, gradf<strong>(T) as [n, 3]) of the last step."""
+        n = self.n_ref_nodes
+        gU, gT = np.zeros((n, 9)), np.zeros((n, 3))
+        self._ck(self.lib.nsem_download_gradients(self.h, _pd(gU), _pd(gT)))
+        return gU, gT
 
     def upload_ref(self, rho_ref, p_ref, g=None, gh=None):
         a, b = _f64(rho_ref), _f64(p_ref)

@@ -11,6 +11,9 @@
 // is the same set of cells (tests/test_amr_regrid.py compares centroids, volumes and mortar faces with the reference's own regrid).
 #include <algorithm>
 #include <cmath>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <functional>
 
 #include "nsem_host.h"
@@ -454,11 +457,22 @@ std::unique_ptr<EulerSolver> EulerSolver::regridded(const std::vector<uint8_t>& 
     n->refine_params = refine_params; n->amr_step = amr_step;
     n->mass0 = mass0; n->energy0 = energy0; n->volume0 = volume0;
     n->forest = forest;
+    const bool verbose = std::getenv("NSEM_VERBOSE") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        const auto t1 = std::chrono::steady_clock::now();
+        if (verbose) std::printf("regrid: %-28s %.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+        t0 = t1;
+    };
     n->last_maps = forest->regrid(refine, coarsen);
+    lap("forest regrid");
     const Grid g = forest->grid();
+    lap("grid emission");
     n->topo.load(g);
+    lap("topology (MeshTopo::load)");
     Basis b(nop);
     n->geo.build(n->topo, b);
+    lap("node geometry");
     auto blank = [](int comps, const std::vector<BCond>& bcs) {
         FieldFile f;
         f.comps = comps;
@@ -469,9 +483,12 @@ std::unique_ptr<EulerSolver> EulerSolver::regridded(const std::vector<uint8_t>& 
     n->set_fields(blank(1, file_bc_rho), blank(3, file_bc_U), blank(1, file_bc_T), blank(1, file_bc_p));
     n->setup();                                         // reference state, gravity, BC tables on the new mesh (the fields are overwritten below)
     n->mass0 = mass0; n->energy0 = energy0; n->volume0 = volume0;
+    lap("fields + set-up");
     if (ctx) {
         n->attach_device(device_id);
+        lap("attach (mesh upload)");
         n->adopt_refined_state(*this, n->last_maps.refineMap, n->last_maps.coarseMap, n->last_maps.cellMap, true);
+        lap("device transfer + restart");
     }
     return n;
 }

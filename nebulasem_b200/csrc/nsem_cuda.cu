@@ -1245,8 +1245,35 @@ extern "C" int nsem_download_state(nsem_ctx* c, double* rho, double* U, double* 
     return 0;
 }
 
-// ---- pipelined transfers -----------------------------------------------------------------------------------
 static int join_comm_fwd(nsem_ctx* c);      // = join_comm (defined with the step): make the compute stream see an in-flight halo exchange
+
+// Operator-level view for unit parity: what gradf<strong>(U) and gradf<strong>(T) + fillBCs(r, fIndex) (field.h:3328-3362,
+// 2731-2769) produced in the last step, in the reference's AoS layouts.  The fused sweeps keep these per-unit-volume gradients in HBM between
+// sweep A and sweep B, so no extra kernel is needed.
+extern "C" int nsem_download_gradients(nsem_ctx* c, double* gradU, double* gradT) {
+    if (!c->have_state) { c->err = "nsem_download_gradients: no state"; return 1; }
+    if (!(c->prm.diffusion && c->prm.viscosity != 0.0)) { c->err = "nsem_download_gradients: the gradients are only evaluated when diffusion is on"; return 1; }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (join_comm_fwd(c)) return 1;
+    if (gradU) {
+        // Tensor AoS order XX,YY,ZZ,XY,YZ,XZ,YX,ZY,ZX (tensor.h:452-454) <- row-major G[a*3+b] = d_a U_b
+        const int rm[9] = {0, 4, 8, 1, 5, 2, 3, 7, 6};
+        std::vector<double> tmp((size_t)c->nRefNodes * 3);
+        for (int g = 0; g < 3; g++) {
+            const double* src[3] = {c->GU[rm[3 * g]].p, c->GU[rm[3 * g + 1]].p, c->GU[rm[3 * g + 2]].p};
+            if (from_device(c, tmp.data(), 3, src)) return 1;
+            for (uint64_t i = 0; i < c->nRefNodes; i++)
+                for (int k = 0; k < 3; k++) gradU[i * 9 + 3 * g + k] = tmp[i * 3 + k];
+        }
+    }
+    if (gradT) {
+        const double* src[3] = {c->GT[0].p, c->GT[1].p, c->GT[2].p};
+        if (from_device(c, gradT, 3, src)) return 1;
+    }
+    return 0;
+}
+
+// ---- pipelined transfers -----------------------------------------------------------------------------------
 static int async_setup(nsem_ctx* c) {
     if (c->asyncReady && c->stageIn.n >= (size_t)c->nRefNodes * 6) return 0;
     CUDA_TRY(c, c->stageIn.alloc((size_t)c->nRefNodes * 6));

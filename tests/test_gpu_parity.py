@@ -66,6 +66,32 @@ def test_device_matches_the_reference_binary_dumps(tmp_cases, path):
     assert err["rho"] <= TOL and err["rhoTheta"] <= TOL and err["rhoU_scaled"] <= TOL, err
 
 
+@pytest.mark.parametrize("name,kw", [("bubble3d", dict(n=3, order=3)), ("hill3d", dict(nx=6, ny=2, nz=4, order=3)), ("bubble2d", dict(n=5, order=4))])
+def test_gradient_operator_matches_oracle(tmp_cases, name, kw):
+    """Operator-level parity: gradf<strong>(U), gradf<strong>(theta) + fillBCs(r, fIndex) as the fused sweep A leaves
+    them (nsem_download_gradients) against the oracle's gradf (field.h:3328-3362, 2731-2769), ghost nodes included."""
+    orc = make_oracle(tmp_cases, name, 4, exact=False, **kw)
+    orc.run(3)                                                      # a state with velocity
+    ctx = device_from_oracle(orc)
+    GU = orc.gradf(orc.U, "U")                                      # [node, a, b] = d_a U_b
+    GT = orc.gradf(orc.T + orc.p.T0, "T")
+    ctx.step(1)
+    dU, dT = ctx.download_gradients()
+    ctx.close()
+    rm = [0, 4, 8, 1, 5, 2, 3, 7, 6]                                # Tensor AoS order <- row-major a*3+b
+    GU = GU.reshape(-1, 9)[:, rm]
+    nb = orc.gB
+    touched = np.zeros(GU.shape[0], bool)                           # real nodes + the ghost nodes a boundary face touches
+    touched[:nb] = True
+    touched[np.abs(dU).sum(axis=1) + np.abs(dT).sum(axis=1) > 0] = True
+    sU, sT = np.abs(GU[:nb]).max(), np.abs(GT[:nb]).max()
+    assert sU > 0 and sT > 0
+    assert np.abs(dU[:nb] - GU[:nb]).max() <= 1e-11 * sU
+    assert np.abs(dT[:nb] - GT[:nb]).max() <= 1e-10 * sT        # theta carries the 300 K offset: eps * 300 * |D| / h on both sides
+    assert np.abs(dU[touched] - GU[touched]).max() <= 1e-11 * sU
+    assert np.abs(dT[touched] - GT[touched]).max() <= 1e-10 * sT
+
+
 def test_non_trilinear_metrics_run_the_stored_metric_kernels(tmp_cases):
     """A mesh whose Jinv no trilinear map reproduces (curved elements) must be detected by nsem_upload_mesh and run the
     stored-metric instantiation of the v4 kernels -- and still match the oracle fed with the same metrics."""
