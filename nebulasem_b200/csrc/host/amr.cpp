@@ -445,7 +445,12 @@ std::unique_ptr<EulerSolver> EulerSolver::regridded(const std::vector<uint8_t>& 
     if (nranks > 1) throw Error("EulerSolver::regridded: the in-memory regrid runs on one partition (repartitioning a regridded mesh is not built)");
     for (const std::vector<BCond>* l : {&file_bc_rho, &file_bc_U, &file_bc_T, &file_bc_p})
         for (const BCond& b : *l)
+        {
             if (!b.fixed.empty()) throw Error("EulerSolver::regridded: boundary conditions with frozen per-face values cannot follow a regrid");
+            // the reference refines the owner cells of paired CYCLIC faces together and pairs the faces by their position in the two patches
+            // (field.cpp:827-858, field.h:2662-2664); neither is built here
+            if (b.type == "CYCLIC") throw Error("EulerSolver::regridded: CYCLIC patches cannot follow a regrid yet (paired faces must be refined together)");
+        }
     if (!forest) throw Error("EulerSolver::regridded: no AMR forest (the mesh must come from set_mesh/load_mesh of a conforming hexahedral grid)");
     std::unique_ptr<EulerSolver> n(new EulerSolver());
     n->ctl = ctl; n->dir = dir; n->meshName = meshName;

@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 
 #include "nsem_host.h"
 
@@ -103,14 +104,25 @@ void EulerSolver::set_mesh(const Grid& g) {
 void EulerSolver::set_mesh_partition(const Grid& global, int rank_, int nranks_, const std::string& type, const int nxyz[3]) {
     rank = rank_; nranks = nranks_;
     nGlobalCells = global.nCells();
+    const bool verbose = std::getenv("NSEM_VERBOSE") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        const auto t1 = std::chrono::steady_clock::now();
+        if (verbose) std::printf("decompose[%d]: %-34s %.3f s\n", rank, what, std::chrono::duration<double>(t1 - t0).count());
+        t0 = t1;
+    };
     const std::vector<u32> fmc = mortar_flags(global);
+    lap("mortar flags of the global grid");
     const bool amr = std::any_of(fmc.begin(), fmc.end(), [](u32 v) { return v != 0; });
     const std::vector<u32> part = partition_cells(global, nranks, type, nxyz, amr ? &fmc : nullptr);
+    lap("partition_cells");
     Partition P = extract_partition(global, part, rank, nranks);
+    lap("extract_partition");
     if (P.cellGlobal.empty()) throw Error("partition " + std::to_string(rank) + " is empty");
     cellGlobal = P.cellGlobal;
     peers = P.peers;
     set_mesh(P.grid);
+    lap("local topology + node geometry");
 }
 
 void EulerSolver::load_mesh(int step) {

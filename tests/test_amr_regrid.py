@@ -149,10 +149,45 @@ def test_tagging_reproduces_the_reference_initial_regrid_2d(tmp_path):
     ref.close()
 
 
+@pytest.mark.parametrize("case,direction,max_level", [("bubble3d", (0, 0, 0), 2), ("bubble2d", (0, 1, 0), 3)])
+def test_amr_cycles_keep_the_grid_valid(case, direction, max_level):
+    """Eight regrids that chase a bubble jumping around the domain (refinement and coarsening mixed, up to three levels): every grid loads
+    through the topology code, the volume is that of the domain, neighbours across a face differ by at most one level, and the faces
+    where they differ are exactly the mortar faces."""
+    from nebulasem_b200 import host
+    rng = np.random.default_rng(7)
+    two_d = case == "bubble2d"
+    s = host.Solver.synthetic(case, 4, 1 if two_d else 4, 4, 2)
+    s.enable_amr(direction=direction, field="T", field_min=0.15, field_max=0.4, max_level=max_level, buffer_zone=1)
+    vol0 = s.f64("gCV")[:s.nBCS].sum()
+    seen_levels, counts = set(), []
+    for cycle in range(8):
+        x = s.f64("cC").reshape(-1, 3)
+        ctr = np.array([200 + 600 * rng.random(), 50 if two_d else 200 + 600 * rng.random(), 200 + 600 * rng.random()])
+        r = np.linalg.norm((x - ctr) * (np.array([1, 0, 1]) if two_d else 1), axis=1) / 250
+        s.set_state(T=np.where(r < 1, 0.25 * (1 + np.cos(np.pi * r)), 0.0))
+        s.regrid()
+        lv = s.cell_levels()
+        fo, fn, fm = s.u32("faceOwner"), s.u32("faceNeigh"), s.u32("faceMortar")
+        inner = fn < s.nBCS
+        jump = np.abs(lv[fo[inner]] - lv[fn[inner]])
+        assert jump.max() <= 1 and lv.max() <= max_level
+        assert int((jump == 1).sum()) == int((fm > 0).sum())
+        assert abs(s.f64("gCV")[:s.nBCS].sum() - vol0) <= 1e-12 * vol0
+        seen_levels.update(lv.tolist())
+        counts.append(s.nBCS)
+    assert 2 in seen_levels and len(set(counts)) > 3          # deeper levels were reached, cells were both added and removed
+    s.close()
+
+
 def test_regrid_refuses_what_it_cannot_do(monkeypatch):
     from nebulasem_b200 import capi, host
     s = host.Solver.open_case(os.path.join(GOLD, "srtb3d_amr"))        # already non-conforming: cannot seed the forest
     with pytest.raises(capi.NsemError, match="no AMR forest"):
+        s.regrid()
+    s.close()
+    s = host.Solver.synthetic("vortex", 4, 4, 1, 2)                     # CYCLIC patches pair their faces by position in the patch
+    with pytest.raises(capi.NsemError, match="CYCLIC"):
         s.regrid()
     s.close()
     monkeypatch.delenv("NSEM_AMR")
