@@ -486,9 +486,10 @@ std::unique_ptr<EulerSolver> EulerSolver::regridded(const std::vector<uint8_t>& 
         return f;
     };
     n->set_fields(blank(1, file_bc_rho), blank(3, file_bc_U), blank(1, file_bc_T), blank(1, file_bc_p));
+    lap("blank fields + BC tables");
     n->setup();                                         // reference state, gravity, BC tables on the new mesh (the fields are overwritten below)
     n->mass0 = mass0; n->energy0 = energy0; n->volume0 = volume0;
-    lap("fields + set-up");
+    lap("set-up (reference state)");
     if (ctx) {
         n->attach_device(device_id);
         lap("attach (mesh upload)");
