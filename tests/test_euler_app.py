@@ -124,3 +124,21 @@ def test_euler_binary_runs_the_amr_cycle(tmp_path):
             assert s.nBCS == 372                        # the reference's initial regrid of this case refines the same 44 cells
         s.close()
     assert max(abs(m - masses[0]) for m in masses) <= 1e-12 * abs(masses[0]), masses
+
+
+def test_amr_on_several_partitions_is_refused_not_skipped(tmp_path):
+    """amr_step with more than one process: the in-memory regrid runs on one partition, so the binary says so and exits non-zero
+    (NSEM_IGNORE_AMR_STEP=1 runs on the grid as it is)."""
+    a = str(tmp_path / "amr_two_ranks")
+    ocases.CASES["bubble3d"](n=4, order=2).write(a, 5)
+    ctl = open(os.path.join(a, "controls")).read().replace("end_step", "amr_step 1\n    end_step", 1)
+    open(os.path.join(a, "controls"), "w").write(ctl)
+    env = dict(os.environ, NSEM_RANK="0", NSEM_WORLD="2", NSEM_DRYRUN="1")
+    out = subprocess.run([build.EULER_BIN, "./controls"], cwd=a, env=env, capture_output=True, text=True, timeout=120)
+    assert out.returncode != 0 and "one partition" in out.stderr, out.stderr[-500:]
+    env["NSEM_IGNORE_AMR_STEP"] = "1"
+    procs = [subprocess.Popen([build.EULER_BIN, "./controls"], cwd=a, env=dict(env, NSEM_RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True) for r in range(2)]
+    for p in procs:
+        o, e = p.communicate(timeout=120)
+        assert p.returncode == 0, e[-500:]
