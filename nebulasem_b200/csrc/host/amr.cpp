@@ -14,6 +14,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <functional>
 
 #include "nsem_host.h"
@@ -345,6 +346,74 @@ Grid AmrForest::grid() const {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// persistence
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+const char kForestMagic[8] = {'N', 'S', 'E', 'M', 'F', 'R', 'S', '1'};
+struct Writer {
+    FILE* f;
+    template <class T> void pod(const T& v) { if (std::fwrite(&v, sizeof(T), 1, f) != 1) throw Error("AmrForest::save: write failed"); }
+    template <class T> void arr(const T* p, size_t n) { if (n && std::fwrite(p, sizeof(T), n, f) != n) throw Error("AmrForest::save: write failed"); }
+};
+struct Reader {
+    FILE* f;
+    template <class T> T pod() { T v; if (std::fread(&v, sizeof(T), 1, f) != 1) throw Error("AmrForest::load: truncated file"); return v; }
+    template <class T> void arr(T* p, size_t n) { if (n && std::fread(p, sizeof(T), n, f) != n) throw Error("AmrForest::load: truncated file"); }
+};
+}  // namespace
+
+void AmrForest::save(const std::string& path) const {
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f) throw Error("AmrForest::save: cannot open " + path);
+    try {
+        Writer w{f};
+        w.arr(kForestMagic, 8);
+        w.arr(dir.data(), 3);
+        w.pod<uint64_t>(V.size());
+        for (const Vec3& v : V) w.arr(v.data(), 3);
+        w.pod<uint64_t>(nodes.size());
+        for (const Node& n : nodes) { w.arr(n.v, 8); const int32_t q[4] = {n.level, n.parent, n.child0, n.nchild}; w.arr(q, 4); }
+        w.pod<uint64_t>(leaves.size());
+        for (int l : leaves) w.pod<int32_t>(l);
+        w.pod<uint64_t>(edgeMid.size());
+        for (const auto& kv : edgeMid) { w.arr(kv.first.data(), 2); w.pod<u32>(kv.second); }
+        w.pod<uint64_t>(faceMid.size());
+        for (const auto& kv : faceMid) { w.arr(kv.first.data(), 4); w.pod<u32>(kv.second); }
+        w.pod<uint64_t>(patchOf.size());
+        for (const auto& kv : patchOf) { w.arr(kv.first.data(), 4); w.pod<u32>((u32)kv.second.size()); w.arr(kv.second.data(), kv.second.size()); }
+    } catch (...) { std::fclose(f); throw; }
+    std::fclose(f);
+}
+
+void AmrForest::load(const std::string& path) {
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) throw Error("AmrForest::load: cannot open " + path);
+    try {
+        Reader r{f};
+        char magic[8];
+        r.arr(magic, 8);
+        if (std::memcmp(magic, kForestMagic, 8) != 0) throw Error("AmrForest::load: " + path + " is not a forest file");
+        r.arr(dir.data(), 3);
+        V.resize(r.pod<uint64_t>());
+        for (Vec3& v : V) r.arr(v.data(), 3);
+        nodes.resize(r.pod<uint64_t>());
+        for (Node& n : nodes) { r.arr(n.v, 8); int32_t q[4]; r.arr(q, 4); n.level = q[0]; n.parent = q[1]; n.child0 = q[2]; n.nchild = q[3]; }
+        leaves.resize(r.pod<uint64_t>());
+        for (int& l : leaves) { l = r.pod<int32_t>(); if (l < 0 || (size_t)l >= nodes.size()) throw Error("AmrForest::load: leaf out of range"); }
+        edgeMid.clear(); faceMid.clear(); patchOf.clear();
+        for (uint64_t n = r.pod<uint64_t>(); n > 0; n--) { Key2 k; r.arr(k.data(), 2); edgeMid[k] = r.pod<u32>(); }
+        for (uint64_t n = r.pod<uint64_t>(); n > 0; n--) { Key4 k; r.arr(k.data(), 4); faceMid[k] = r.pod<u32>(); }
+        for (uint64_t n = r.pod<uint64_t>(); n > 0; n--) {
+            Key4 k; r.arr(k.data(), 4);
+            std::string name(r.pod<u32>(), ' ');
+            r.arr(&name[0], name.size());
+            patchOf[k] = name;
+        }
+    } catch (...) { std::fclose(f); throw; }
+    std::fclose(f);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // tagging (Prepare::calcQOI + the first half of Prepare::refineMesh, field.cpp:606-620, 696-824)
 // ---------------------------------------------------------------------------------------------------------
 void amr_tag_cells(const EulerSolver& s, const RefineParams& rp, const std::vector<int>& levels, const std::vector<std::vector<u32>>& families,
@@ -497,6 +566,13 @@ std::unique_ptr<EulerSolver> EulerSolver::regridded(const std::vector<uint8_t>& 
         lap("device transfer + restart");
     }
     return n;
+}
+
+void EulerSolver::write_amr_grid(long dump) const {
+    if (!forest) throw Error("EulerSolver::write_amr_grid: no AMR forest");
+    const std::string base = dir + "/" + meshName + "_" + std::to_string(dump);
+    write_grid_text(base + ".txt", forest->grid());
+    forest->save(base + ".forest");
 }
 
 std::unique_ptr<EulerSolver> EulerSolver::regridded_by_indicator() {

@@ -189,6 +189,7 @@ int nsemh_enable_amr(nsemh_solver* h, double dx, double dy, double dz, const cha
           s.refine_params.field_min = fmin; s.refine_params.field_max = fmax; s.refine_params.max_level = max_level;
           s.refine_params.buffer_zone = buffer_zone)
 }
+int nsemh_write_amr_grid(nsemh_solver* h, int dump) { GUARD((*h->sp).write_amr_grid(dump)) }
 int nsemh_cell_levels(nsemh_solver* h, int32_t* out, uint32_t n) {
     GUARD(if (!(*h->sp).forest) throw Error("nsemh_cell_levels: no AMR forest");
           const std::vector<int> l = (*h->sp).forest->levels();

@@ -96,9 +96,17 @@ void EulerSolver::set_mesh(const Grid& g) {
     forest.reset();
     if (amr_step != 0 || std::getenv("NSEM_AMR")) {
         forest = std::make_shared<AmrForest>();
-        try { forest->init(g, refine_params.dir); }
-        catch (const Error&) { forest.reset(); }      // a grid that is already non-conforming cannot seed the forest: regridded() says so
+        struct stat st;
+        if (!forest_file.empty() && ::stat(forest_file.c_str(), &st) == 0) {
+            // restart of an AMR run: the forest that emitted this grid was saved next to it
+            forest->load(forest_file);
+            if (forest->leaves.size() != g.nCells()) throw Error(forest_file + " does not belong to the grid next to it");
+        } else {
+            try { forest->init(g, refine_params.dir); }
+            catch (const Error&) { forest.reset(); }  // a grid that is already non-conforming cannot seed the forest: regridded() says so
+        }
     }
+    forest_file.clear();
 }
 
 void EulerSolver::set_mesh_partition(const Grid& global, int rank_, int nranks_, const std::string& type, const int nxyz[3]) {
@@ -127,6 +135,7 @@ void EulerSolver::set_mesh_partition(const Grid& global, int rank_, int nranks_,
 
 void EulerSolver::load_mesh(int step) {
     const Grid g = read_grid(dir + "/" + meshName + "_" + std::to_string(step));
+    forest_file = dir + "/" + meshName + "_" + std::to_string(step) + ".forest";
     // one process per partition: every rank decomposes the same global grid the same way (Prepare::decomposeMesh does it
     // once on rank 0 and hands the parts over through grid<r>/ files, field.cpp:1086-1443) and keeps its own part
     if (nranks > 1) set_mesh_partition(g, rank, nranks, decomp_type, decomp_n);
@@ -647,7 +656,7 @@ void run_case(std::unique_ptr<EulerSolver>& s) {
         std::unique_ptr<EulerSolver> n = s->regridded_by_indicator();
         const u32 before = s->geo.nBCS;
         s = std::move(n);
-        write_grid_text(s->dir + "/" + s->meshName + "_" + std::to_string(dump) + ".txt", s->forest->grid());
+        s->write_amr_grid(dump);
         std::printf("Regrid at dump %ld: %u -> %u cells\n", dump, before, s->geo.nBCS);
     };
     const long last = s->end_step;

@@ -187,6 +187,10 @@ struct AmrForest {
     Grid grid() const;                         // the current grid in the reference's format
     std::vector<int> levels() const;
     std::vector<std::vector<u32>> families() const;
+    // the forest next to the grid it emitted (<mesh>_<dump>.forest), so that an AMR run can be restarted from a dump; own binary format
+    // (the reference keeps amrTree_<k>.bin, a different tree over a different cell order)
+    void save(const std::string& path) const;
+    void load(const std::string& path);
 private:
     int split_mask(const Node& n) const;
     u32 mid_vertex(const std::vector<u32>& of);
@@ -257,10 +261,12 @@ struct EulerSolver {
     AmrForest::Maps last_maps;                            // maps of the regrid that produced this solver's mesh
     std::vector<BCond> file_bc_rho, file_bc_U, file_bc_T, file_bc_p;   // boundary conditions as the field files state them
     int device_id = -1;
+    std::string forest_file;                              // set by load_mesh: <mesh>_<step>.forest, read by set_mesh when it exists
     // the solver on the regridded mesh: same controls and boundary conditions, mesh from the forest after regrid(refine, coarsen), set-up
     // done; when this solver is attached the new one is attached to the same device and takes the state (adopt_refined_state, restart)
     std::unique_ptr<EulerSolver> regridded(const std::vector<uint8_t>& refine, const std::vector<uint8_t>& coarsen);
     std::unique_ptr<EulerSolver> regridded_by_indicator();   // amr_tag_cells on the downloaded state, then regridded()
+    void write_amr_grid(long dump) const;                 // <mesh>_<dump>.txt + <mesh>_<dump>.forest in the case directory
     void download();
     void write_fields(int index);                         // Mesh::write_fields; with nranks > 1 into <case>/grid<rank>/ like the
                                                           // reference's per-rank working directories (field.cpp:1436-1440)

@@ -180,6 +180,39 @@ def test_amr_cycles_keep_the_grid_valid(case, direction, max_level):
     s.close()
 
 
+def test_amr_run_restarts_from_a_dump(tmp_path):
+    """The forest is saved next to the grid of every regrid (<mesh>_<dump>.forest): a solver opened from that dump continues the AMR
+    run exactly like the one that wrote it (same levels, same cells in the same order after the next regrid, coarsening included)."""
+    from nebulasem_b200 import host
+    d = tmp_path / "restart"
+    shutil.copytree(os.path.join(RF, "3d_o2", "stage0"), d)
+
+    def blob(s, ctr):
+        x = s.f64("cC").reshape(-1, 3)
+        r = np.linalg.norm(x - np.asarray(ctr, dtype=float), axis=1) / 250
+        s.set_state(T=np.where(r < 1, 0.25 * (1 + np.cos(np.pi * r)), 0.0))
+
+    a = host.Solver.open_case(str(d))
+    a.enable_amr(direction=(0, 0, 0), field="T", field_min=0.15, field_max=0.4, max_level=2, buffer_zone=1)
+    blob(a, (400, 400, 400))
+    a.regrid()
+    blob(a, (400, 400, 400))
+    a.write(1)
+    a.write_amr_grid(1)
+    b = host.Solver.open_case(str(d), 1)                       # grid_1.txt + grid_1.forest + the fields of dump 1
+    b.enable_amr(direction=(0, 0, 0), field="T", field_min=0.15, field_max=0.4, max_level=2, buffer_zone=1)
+    assert b.nBCS == a.nBCS and np.array_equal(b.cell_levels(), a.cell_levels())
+    assert np.array_equal(b.f64("gCC"), a.f64("gCC")) and np.array_equal(b.state()[2][:b.gBCSfield], a.state()[2][:a.gBCSfield])
+    for s in (a, b):
+        blob(s, (650, 600, 550))                                # the bubble has moved: the old families merge, new cells split
+        s.regrid()
+    assert a.nBCS == b.nBCS and np.array_equal(a.f64("gCC"), b.f64("gCC")) and np.array_equal(a.cell_levels(), b.cell_levels())
+    assert len(a.u32("coarseMap")) > 0 and np.array_equal(a.u32("coarseMap"), b.u32("coarseMap"))
+    assert np.array_equal(a.u32("refineMap"), b.u32("refineMap"))
+    a.close()
+    b.close()
+
+
 def test_regrid_refuses_what_it_cannot_do(monkeypatch):
     from nebulasem_b200 import capi, host
     s = host.Solver.open_case(os.path.join(GOLD, "srtb3d_amr"))        # already non-conforming: cannot seed the forest
