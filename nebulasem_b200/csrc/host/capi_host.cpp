@@ -5,6 +5,8 @@
 #include <cmath>
 #include <algorithm>
 #include <cstring>
+#include <chrono>
+#include <cstdlib>
 
 #include "nsem_host.h"
 
@@ -74,9 +76,18 @@ nsemh_solver* nsemh_synthetic_part(const char* kind_, int nx, int ny, int nz, in
     EulerSolver& s = (*h->sp);
     const std::string kind = kind_;
     const int pxyz[3] = {px, py, pz};
+    const bool verbose = std::getenv("NSEM_VERBOSE") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        const auto t1 = std::chrono::steady_clock::now();
+        if (verbose) std::printf("synthetic[%d]: %-30s %.3f s\n", rank, what, std::chrono::duration<double>(t1 - t0).count());
+        t0 = t1;
+    };
     auto mesh = [&](const Grid& g) {
+        lap("box_grid");
         if (nranks > 1) s.set_mesh_partition(g, rank, nranks, decomp ? decomp : "METIS", pxyz);
         else s.set_mesh(g);
+        lap("set_mesh");
     };
     try {
         s.time_scheme = "BDF1";
@@ -144,7 +155,9 @@ nsemh_solver* nsemh_synthetic_part(const char* kind_, int nx, int ny, int nz, in
         } else {
             throw Error("unknown synthetic case " + kind);
         }
+        lap("set_fields");
         s.setup();
+        lap("setup");
         return h;
     } catch (const std::exception& e) {
         g_err = e.what();

@@ -239,7 +239,8 @@ void Geometry::build(const MeshTopo& t, const Basis& b) {
     for (int q = 0; q < 6; q++) { psiRef[q] = b.psiRef[q]; psiCor[q] = b.psiCor[q]; }
 
     cC.assign(gALL * 3, 0.0); cV.assign(gALL, 0.0);
-    for (u32 c = 0; c < nCells; c++)
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < (int64_t)nCells; c++)
         for (int q = 0; q < NP; q++) {
             const uint64_t i = (uint64_t)c * NP + q;
             cV[i] = t.CV[c];
@@ -247,7 +248,8 @@ void Geometry::build(const MeshTopo& t, const Basis& b) {
         }
     const size_t nfn = (size_t)nFacets * NPF;
     fC.resize(nfn * 3); fN.resize(nfn * 3); fI.resize(nfn);
-    for (u32 f = 0; f < nFacets; f++)
+#pragma omp parallel for schedule(static)
+    for (int64_t f = 0; f < (int64_t)nFacets; f++)
         for (int q = 0; q < NPF; q++)
             for (int d = 0; d < 3; d++) {
                 fC[((size_t)f * NPF + q) * 3 + d] = t.FC[f][d];
@@ -415,7 +417,8 @@ void Geometry::build(const MeshTopo& t, const Basis& b) {
     }
 
     // ---- fI (field.cpp:257-270): 0 on physical boundary faces, 0.5 elsewhere (ghost faces of other ranks too) ----
-    for (size_t k = 0; k < nfn; k++) fI[k] = (FN[k] >= gBCSfield) ? 0.0 : 0.5;
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < (int64_t)nfn; k++) fI[k] = (FN[k] >= gBCSfield) ? 0.0 : 0.5;
     for (const auto& kv : t.boundaries)
         if (kv.first.find("interMesh") != std::string::npos)
             for (u32 f : kv.second)

@@ -89,9 +89,18 @@ void EulerSolver::read_controls(const std::string& case_dir) {
 }
 
 void EulerSolver::set_mesh(const Grid& g) {
+    const bool verbose = std::getenv("NSEM_VERBOSE") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        const auto t1 = std::chrono::steady_clock::now();
+        if (verbose) std::printf("set_mesh[%d]: %-32s %.3f s\n", rank, what, std::chrono::duration<double>(t1 - t0).count());
+        t0 = t1;
+    };
     topo.load(g);
+    lap("topology (MeshTopo::load)");
     Basis b(nop);
     geo.build(topo, b);
+    lap("node geometry (Geometry::build)");
     // the AMR forest starts from the grid as loaded (conforming hexahedra); only built when a regrid can follow
     forest.reset();
     if (amr_step != 0 || std::getenv("NSEM_AMR")) {
