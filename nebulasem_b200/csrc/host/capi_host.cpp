@@ -211,6 +211,7 @@ int nsemh_cell_levels(nsemh_solver* h, int32_t* out, uint32_t n) {
 }
 int nsemh_restart_state(nsemh_solver* h) { GUARD((*h->sp).restart_state()) }
 int nsemh_write(nsemh_solver* h, int index) { GUARD((*h->sp).write_fields(index)) }
+int nsemh_write_vtk(nsemh_solver* h, int index) { GUARD((*h->sp).write_vtk(index)) }
 int nsemh_run(nsemh_solver* h) { GUARD(run_case(h->sp)) }
 int nsemh_sync(nsemh_solver* h) { GUARD(if (nsem_sync((*h->sp).ctx)) throw Error(nsem_last_error((*h->sp).ctx))) }
 int nsemh_time(nsemh_solver* h, int nsteps, double* ms, double* per_kernel) {

@@ -53,13 +53,25 @@ void EulerSolver::read_controls(const std::string& case_dir) {
     dt = ctl.num("general", "dt", dt);
     gravity = ctl.vec("general", "gravity", gravity);
     time_scheme = ctl.str("general", "time_scheme", time_scheme);
-    start_step = ctl.integer("general", "start_step", start_step);
     end_step = ctl.integer("general", "end_step", end_step);
-    write_interval = ctl.integer("general", "write_interval", write_interval);
+    write_interval = std::max(1L, ctl.integer("general", "write_interval", write_interval));
+    // the controls count start_step in time steps; the run starts from dump start_step / write_interval (AmrIteration, iteration.h:102),
+    // which is what the member holds from here on
+    start_step = ctl.integer("general", "start_step", 0) / write_interval;
     binary_out = ctl.str("general", "write_format", "BINARY") != "TEXT";
     buoyancy = ctl.yes("euler", "buoyancy", buoyancy);
     diffusion = ctl.yes("euler", "diffusion", diffusion);
     problem_init = ctl.str("euler", "problem_init", problem_init);
+    // prepare{fields N { ... }} and vtk{} as apps/prepare reads them (prepareApp.cpp:63-102); NSEM_VTK=1 (or vtk{on_dump YES}, an addition) also
+    // writes <mesh><k>.vtk next to every dump, straight from the downloaded state
+    if (ctl.has("prepare", "fields")) {
+        vtk_fields.clear();
+        const auto& v = ctl.blocks.at("prepare").at("fields");
+        for (size_t i = 1; i < v.size(); i++) if (v[i] != "{" && v[i] != "}") vtk_fields.push_back(v[i]);
+    }
+    vtk_cell_value = ctl.yes("vtk", "write_cell_value", vtk_cell_value);
+    vtk_polyhedral = ctl.yes("vtk", "write_polyhedral", vtk_polyhedral);
+    vtk_on_dump = ctl.yes("vtk", "on_dump", false) || (std::getenv("NSEM_VTK") && std::atoi(std::getenv("NSEM_VTK")) > 0);
     decomp_type = ctl.str("decomposition", "type", decomp_type);
     {
         const Vec3 n = ctl.vec("decomposition", "n", Vec3{1, 1, 1});
@@ -142,7 +154,15 @@ void EulerSolver::set_mesh_partition(const Grid& global, int rank_, int nranks_,
     lap("local topology + node geometry");
 }
 
-void EulerSolver::load_mesh(int step) {
+static bool grid_exists(const std::string& path_noext) {
+    struct stat st;
+    return ::stat((path_noext + ".txt").c_str(), &st) == 0 || ::stat((path_noext + ".bin").c_str(), &st) == 0;
+}
+void EulerSolver::load_mesh(int step_) {
+    // findLastRefinedGrid (field.cpp:79-91): the newest <mesh>_<k>, k <= step; a run restarted from dump k of a fixed mesh reads <mesh>_0
+    int step = step_;
+    while (step >= 0 && !grid_exists(dir + "/" + meshName + "_" + std::to_string(step))) step--;
+    if (step < 0) step = step_;
     const Grid g = read_grid(dir + "/" + meshName + "_" + std::to_string(step));
     forest_file = dir + "/" + meshName + "_" + std::to_string(step) + ".forest";
     // one process per partition: every rank decomposes the same global grid the same way (Prepare::decomposeMesh does it
@@ -603,6 +623,23 @@ void EulerSolver::write_fields(int index) {
     }
 }
 
+void EulerSolver::write_vtk(int index) const {
+    std::string out = dir;
+    if (nranks > 1) {
+        out = dir + "/grid" + std::to_string(rank);      // prepare -vtk works inside grid<rank>/ too (prepareApp.cpp:104-109)
+        ::mkdir(out.c_str(), 0777);
+    }
+    std::vector<VtkField> fl;
+    for (const auto& name : vtk_fields) {
+        if (name == "rho") fl.push_back({name, 1, rho.data()});
+        else if (name == "U") fl.push_back({name, 3, U.data()});
+        else if (name == "T") fl.push_back({name, 1, T.data()});
+        else if (name == "p") fl.push_back({name, 1, p.data()});
+        // a name without a field is skipped like a name without a file is (Prepare::createFields, field.cpp:556-590)
+    }
+    nsemh::write_vtk(out + "/" + meshName + std::to_string(index) + ".vtk", Basis(nop), geo.cC.data(), geo.nBCS, fl, vtk_cell_value, vtk_polyhedral);
+}
+
 void EulerSolver::merge_fields(int index) {
     if (nranks <= 1 || rank != 0) return;
     const std::string s = std::to_string(index);
@@ -650,6 +687,7 @@ void EulerSolver::run() {
             download();
             write_fields((int)(upto / write_interval));
             merge_fields((int)(upto / write_interval));
+            if (vtk_on_dump) write_vtk((int)(upto / write_interval));
             if (rank == 0) std::printf("Time %f : wrote fields %ld\n", upto * dt, upto / write_interval);
         }
     }

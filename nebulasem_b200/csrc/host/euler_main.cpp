@@ -11,6 +11,9 @@
 // by rank 0 into the case directory in global node order (Prepare::mergeFields).
 //   NSEM_DEVICE   device index (default: local rank, else rank % visible devices)
 //   NSEM_DRYRUN=k (k >= 1) set-up only, no GPU: decompose, read and initialise the fields, dump them as index k
+//   NSEM_VTK=1    also write <mesh><k>.vtk next to every dump (the file `prepare ./controls -vtk -start k` would make of it)
+// `euler ./controls -vtk [-start i] [-stop j]` converts existing dumps i..j-1 of the case directory (the merged, global ones) to VTK on the
+// host, no GPU involved: the post-processing step of the reference's workflow (apps/prepare/prepareApp.cpp:26-27,118-124) for this solver's fields.
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -58,7 +61,8 @@ static void share_unique_id(const std::string& dir, int rank, unsigned char id[1
 
 int main(int argc, char* argv[]) {
     if (argc < 2 || !std::strcmp(argv[1], "-h")) {
-        std::printf("Usage:\n  %s <inputfile>\nOptions:\n  -h          --  Display this message\n\n", argv[0]);
+        std::printf("Usage:\n  %s <inputfile> <Options>\nOptions:\n  -vtk        --  Convert data to VTK format\n  -start <i>  --  Start at time step <i>\n"
+                    "  -stop <i>   --  Stop before time step <i>\n  -h          --  Display this message\n\n", argv[0]);
         return argc < 2 ? 1 : 0;
     }
     int rank = 0, world = 1, local = -1;
@@ -81,9 +85,30 @@ int main(int argc, char* argv[]) {
         if (world < 1 || rank < 0 || rank >= world) throw nsemh::Error("inconsistent rank/world size in the environment");
         if (!env_int("NSEM_DEVICE", local) && !env_int("OMPI_COMM_WORLD_LOCAL_RANK", local) && !env_int("LOCAL_RANK", local) &&
             !env_int("SLURM_LOCALID", local)) local = -1;                     // -1: rank % visible devices (nsem_create)
+        bool to_vtk = false;
+        int vtk_start = 0, vtk_stop = 0;
+        for (int i = 2; i < argc; i++) {
+            if (!std::strcmp(argv[i], "-vtk")) to_vtk = true;
+            else if (!std::strcmp(argv[i], "-start") && i + 1 < argc) { vtk_start = std::atoi(argv[++i]); vtk_stop = vtk_start + 1; }
+            else if (!std::strcmp(argv[i], "-stop") && i + 1 < argc) vtk_stop = std::atoi(argv[++i]);
+            else throw nsemh::Error(std::string("unknown option ") + argv[i]);
+        }
+        if (to_vtk) {
+            if (rank != 0) return 0;                       // the merged dumps are global: one process converts them
+            rank = 0; world = 1;
+            s.read_controls(dir);
+            std::printf("Converting result to VTK format.\n");
+            for (int k = vtk_start; k < vtk_stop; k++) {
+                s.load_mesh(k);
+                s.read_fields(k);
+                s.write_vtk(k);
+            }
+            std::printf("Exiting application run with %d processes\n", world);
+            return 0;
+        }
         s.rank = rank; s.nranks = world;
         s.read_controls(dir);
-        const int step = (int)(s.start_step / s.write_interval);
+        const int step = (int)s.start_step;       // dump index (read_controls divides by write_interval)
         s.load_mesh(step);
         s.read_fields(step);
         s.setup();

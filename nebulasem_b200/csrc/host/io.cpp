@@ -361,4 +361,77 @@ void write_field(const std::string& path_noext, bool binary, int comps, const do
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// VTK (Vtk::write_vtk, src/vtk/vtk.cpp:41-287, the DG branch `NPMAT > 1` :125-286; field blocks MeshField::writeVtkCellAll, field.h:1059-1071)
+// ---------------------------------------------------------------------------------------------------------
+void write_vtk(const std::string& path, const Basis& b, const double* cC, u32 nBCS, const std::vector<VtkField>& fields,
+               bool write_cell_value, bool write_polyhedral) {
+    const u32 NPX = (u32)b.NPX, NPY = (u32)b.NPY, NPZ = (u32)b.NPZ, NP = (u32)b.NP;
+    if (NP <= 1) throw Error("write_vtk: the finite-volume branch (one node per cell) of Vtk::write_vtk is outside the dGSEM path");
+    std::ofstream of(path);
+    if (!of) throw Error("cannot write " + path);
+    std::vector<char> buf(1 << 22);
+    of.rdbuf()->pubsetbuf(buf.data(), (std::streamsize)buf.size());
+    const uint64_t nNodes = (uint64_t)nBCS * NP;
+    of << (write_polyhedral ? "# vtk DataFile Version 2.0\n" : "# vtk DataFile Version 1.0\n");
+    of << "Data produced by FV/DG solver consisting of fields and grid.\nASCII\nDATASET UNSTRUCTURED_GRID\n";
+    of << "POINTS " << nNodes << " double\n";
+    of.precision(12);
+    for (uint64_t i = 0; i < nNodes; i++) of << cC[i * 3] << " " << cC[i * 3 + 1] << " " << cC[i * 3 + 2] << " \n";
+    of.precision(6);
+    // every element is cut into the sub-cells spanned by neighbouring LGL nodes: points, lines, quads or hexahedra (vtk.cpp:136-264)
+    const int ext[3] = {NPX > 1, NPY > 1, NPZ > 1};
+    const int dim = ext[0] + ext[1] + ext[2];
+    const u32 nr = NPX > 1 ? NPX - 1 : 1, ns = NPY > 1 ? NPY - 1 : 1, nt = NPZ > 1 ? NPZ - 1 : 1;
+    const uint64_t ncells = (uint64_t)nBCS * nr * ns * nt;
+    const int nverts = 1 << dim;
+    static const int vtk_type[4] = {1, 3, 9, 12};
+    auto idx = [&](u32 c, u32 r, u32 s, u32 t) { return (uint64_t)c * NP + (uint64_t)r * NPY * NPZ + (uint64_t)s * NPZ + t; };
+    // corner offsets (dr,ds,dt) in the reference's order: the first extended axis runs first, quads and hexahedra counter-clockwise
+    int axes[3], na = 0;
+    for (int d = 0; d < 3; d++) if (ext[d]) axes[na++] = d;
+    int off[8][3] = {};
+    if (dim == 1) off[1][axes[0]] = 1;
+    else if (dim >= 2) {
+        static const int q[4][2] = {{0, 0}, {1, 0}, {1, 1}, {0, 1}};
+        for (int k = 0; k < nverts; k++) {
+            off[k][axes[0]] = q[k & 3][0];
+            off[k][axes[1]] = q[k & 3][1];
+            if (dim == 3) off[k][axes[2]] = k >> 2;
+        }
+    }
+    of << "CELLS " << ncells << " " << ncells * (uint64_t)(nverts + 1) << "\n";
+    for (u32 c = 0; c < nBCS; c++)
+        for (u32 r = 0; r < nr; r++)
+            for (u32 s = 0; s < ns; s++)
+                for (u32 t = 0; t < nt; t++) {
+                    of << nverts << " ";
+                    for (int k = 0; k < nverts; k++) of << idx(c, r + off[k][0], s + off[k][1], t + off[k][2]) << " ";
+                    of << "\n";
+                }
+    of << "CELL_TYPES " << ncells << "\n";
+    for (uint64_t i = 0; i < ncells; i++) of << vtk_type[dim] << "\n";
+    if (write_cell_value) {
+        of << "CELL_DATA " << ncells << "\nFIELD attributes 1\ncellID  1 " << ncells << " int\n";
+        for (uint64_t i = 0; i < ncells; i++) of << i << "\n";
+    }
+    of << "POINT_DATA " << nNodes << "\nFIELD attributes " << fields.size() << "\n";
+    // forEachCellField order (field.h:1192-1197): the scalar fields first, then the vector fields, each in the order of the list
+    for (int want : {1, 3, 6, 9})
+        for (const auto& f : fields) {
+            if (f.comps != want) continue;
+            of << f.name << " " << f.comps << " " << nNodes << " double\n";
+            for (uint64_t i = 0; i < nNodes; i++) {
+                if (f.comps == 1) of << f.v[i] << "\n";
+                else {
+                    for (int d = 0; d < f.comps; d++) of << f.v[i * f.comps + d] << " ";
+                    of << "\n";
+                }
+            }
+            of << "\n";
+        }
+    of.close();
+    if (!of) throw Error("short write of " + path);
+}
+
 }  // namespace nsemh

@@ -160,6 +160,11 @@ FieldFile read_field(const std::string& path_noext, int comps_expected);
 std::vector<double> init_field(const FieldFile& ff, const Geometry& g, const Vec3& gravity);
 void write_field(const std::string& path_noext, bool binary, int comps, const double* v, uint64_t n_nodes,
                  const std::vector<BCond>& bcs);
+// <mesh><step>.vtk as `prepare ./controls -vtk` writes it for a dGSEM case (Vtk::write_vtk, vtk.cpp:125-286): the LGL nodes as points, every
+// element cut into (NPX-1)(NPY-1)(NPZ-1) sub-cells, cellID per sub-cell, the fields as point data (scalars first, then vectors)
+struct VtkField { std::string name; int comps; const double* v; };
+void write_vtk(const std::string& path, const Basis& b, const double* cC, u32 nBCS, const std::vector<VtkField>& fields,
+               bool write_cell_value = true, bool write_polyhedral = false);
 
 // ---- adaptive regrid in memory (amr.cpp): Prepare::refineMesh tagging + MeshObject::refineMesh -----------------------
 struct RefineParams {                // refinement{} of the controls (Controls::enrollRefine, field.cpp:474-482; defaults field.h:18-40)
@@ -212,7 +217,7 @@ struct EulerSolver {
     Vec3 gravity{0, 0, -9.860616};
     bool buoyancy = true, diffusion = true, binary_out = true;
     std::string time_scheme = "BDF1", problem_init = "NONE";
-    long start_step = 0, end_step = 2, write_interval = 20;
+    long start_step = 0, end_step = 2, write_interval = 20;   // start_step: the DUMP the run starts from (controls' start_step / write_interval)
     // decomposition{type n} (field.cpp:486-492): METIS | XYZ (n = parts per axis) | CELLID
     std::string decomp_type = "METIS";
     int decomp_n[3] = {1, 1, 1};
@@ -272,6 +277,11 @@ struct EulerSolver {
                                                           // reference's per-rank working directories (field.cpp:1436-1440)
     void merge_fields(int index);                         // rank 0: grid<r>/<field><index> of all ranks -> <case>/<field><index>
                                                           // in global node order (Prepare::mergeFields, field.cpp:1446-1496)
+    // Prepare::convertVTK (prepare.cpp:9-17) without the round trip through the field files: <mesh><index>.vtk from the state on the host
+    // (after download()), fields and order from prepare{fields} of the controls, options from vtk{}; per rank into grid<rank>/ like the dumps
+    std::vector<std::string> vtk_fields{"U", "T", "p", "rho"};
+    bool vtk_cell_value = true, vtk_polyhedral = false, vtk_on_dump = false;
+    void write_vtk(int index) const;
     void run();                                           // Iteration loop: steps + dumps every write_interval
 
     void apply_bcs(std::vector<double>& f, int comps, std::vector<BCond>& bcs);   // applyExplicitBCs on the host

@@ -16,7 +16,7 @@ from . import capi
 HOST_LIB_PATH = os.path.join(os.environ.get("NSEM_LIBDIR") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib"), "libnsem_host.so")
 HOST_EXPORTS = ["nsemh_error", "nsemh_close", "nsemh_open_case", "nsemh_synthetic", "nsemh_synthetic_part", "nsemh_patch_faces",
                 "nsemh_peers", "nsemh_diagnostics", "nsemh_attach", "nsemh_step",
-                "nsemh_upload", "nsemh_download", "nsemh_upload_async", "nsemh_download_async", "nsemh_adopt_refined_state", "nsemh_restart_state", "nsemh_regrid", "nsemh_enable_amr", "nsemh_cell_levels", "nsemh_write_amr_grid", "nsemh_write", "nsemh_run", "nsemh_sync", "nsemh_time",
+                "nsemh_upload", "nsemh_download", "nsemh_upload_async", "nsemh_download_async", "nsemh_adopt_refined_state", "nsemh_restart_state", "nsemh_regrid", "nsemh_enable_amr", "nsemh_cell_levels", "nsemh_write_amr_grid", "nsemh_write", "nsemh_write_vtk", "nsemh_run", "nsemh_sync", "nsemh_time",
                 "nsemh_launch_count", "nsemh_kernel_info", "nsemh_set_schedule", "nsemh_dims", "nsemh_params", "nsemh_f64", "nsemh_u32",
                 "nsemh_state_ptr", "nsemh_totals", "nsemh_partition_grid"]
 _lib = None
@@ -57,6 +57,7 @@ def load_host_library() -> C.CDLL:
     lib.nsemh_adopt_refined_state.argtypes = [vp, vp, u32p, C.c_uint32, u32p, C.c_uint32, u32p, C.c_uint32, C.c_int]
     lib.nsemh_write.argtypes = [vp, C.c_int]
     lib.nsemh_write_amr_grid.argtypes = [vp, C.c_int]
+    lib.nsemh_write_vtk.argtypes = [vp, C.c_int]
     lib.nsemh_time.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.nsemh_diagnostics.argtypes = [vp, C.POINTER(C.c_double)]
     lib.nsemh_launch_count.argtypes = [vp]
@@ -267,6 +268,10 @@ class Solver:
 
     def write(self, index: int):
         self._ck(self.lib.nsemh_write(self.h, int(index)))
+
+    def write_vtk(self, index: int):
+        """<mesh><index>.vtk from the state on the host, as `prepare ./controls -vtk -start index` writes it (Vtk::write_vtk, vtk.cpp:125-286)."""
+        self._ck(self.lib.nsemh_write_vtk(self.h, int(index)))
 
     def run(self):
         self._ck(self.lib.nsemh_run(self.h))

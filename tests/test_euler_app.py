@@ -142,3 +142,25 @@ def test_amr_on_several_partitions_is_refused_not_skipped(tmp_path):
     for p in procs:
         o, e = p.communicate(timeout=120)
         assert p.returncode == 0, e[-500:]
+
+
+def test_restart_reads_the_dump_start_step_names_and_the_newest_older_grid(tmp_path):
+    """start_step counts time steps: the run resumes from dump start_step / write_interval (AmrIteration, iteration.h:102) on the newest
+    grid <mesh>_<k>, k <= dump (findLastRefinedGrid, field.cpp:79-91) -- a fixed-mesh case only has grid_0."""
+    gold = os.path.join(ROOT, "tests", "golden", "vtk", "bubble3d_n2_o2")            # controls + grid_0.txt + the reference's dump 1
+    a = str(tmp_path / "restart")
+    shutil.copytree(gold, a)
+    ctl = open(os.path.join(a, "controls")).read()
+    assert "start_step 0" in ctl and "write_interval 4" in ctl
+    open(os.path.join(a, "controls"), "w").write(ctl.replace("start_step 0", "start_step 4").replace("end_step 4", "end_step 8"))
+    run_euler(a, 1, dry=9)
+    for f in ("U", "T"):
+        assert np.array_equal(refio.read_field_values(os.path.join(a, f + "9")), refio.read_field_values(os.path.join(a, f + "1"))), f
+    # the first cycle of a run recomputes rho from p and T even on a restart (ait.start(), euler.cpp:136-149), and the dumped p is the one the
+    # last step started from (euler.cpp:211): rho comes back to ~1e-10, not bitwise -- the reference's own restart behaviour
+    r9, r1 = refio.read_field_values(os.path.join(a, "rho9")), refio.read_field_values(os.path.join(a, "rho1"))
+    assert 0 < np.abs(r9 - r1).max() <= 1e-8 * np.abs(r1).max()
+    # a dump that does not exist is an error, not a silent fresh start
+    open(os.path.join(a, "controls"), "w").write(ctl.replace("start_step 0", "start_step 8").replace("end_step 4", "end_step 12"))
+    out = subprocess.run([build.EULER_BIN, "./controls"], cwd=a, env=dict(os.environ, NSEM_DRYRUN="9"), capture_output=True, text=True, timeout=60)
+    assert out.returncode != 0 and "rho2" in out.stderr, out.stderr[-300:]

@@ -38,6 +38,28 @@ def test_host_geometry_and_setup_bit_equal_to_oracle(tmp_cases, name, kw):
     s.close()
 
 
+def test_host_setup_from_a_dump_bit_equal_to_oracle(tmp_path):
+    """open_case(dir, 1): the fields of the reference's dump 1 on grid_0 (the newest grid <= 1), set up as a run resuming there is
+    (rho from p; tests/test_oracle_vs_reference.py pins that against the reference) -- bit-equal to the oracle on the same files."""
+    import shutil
+
+    from oracle import case as ocase
+    gold = os.path.join(ROOT, "tests", "golden", "vtk", "bubble3d_n2_o2")
+    d = str(tmp_path / "resumed")
+    shutil.copytree(gold, d)
+    d2 = str(tmp_path / "as_step0")
+    os.makedirs(d2)
+    shutil.copy(os.path.join(d, "controls"), d2)
+    shutil.copy(os.path.join(d, "grid_0.txt"), d2)
+    for f in ("rho", "U", "T", "p"):
+        shutil.copy(os.path.join(d, f + "1.bin"), os.path.join(d2, f + "0.bin"))
+    orc = ocase.load_case(d2, exact_order=False)
+    s = host.Solver.open_case(d, 1)
+    rho, U, T, p = s.state()
+    assert np.array_equal(rho, orc.rho) and np.array_equal(U, orc.U) and np.array_equal(T, orc.T) and np.array_equal(p, orc.pp)
+    s.close()
+
+
 @pytest.mark.parametrize("fixture", ["srtb_amr", "srtb3d_amr"])
 def test_host_non_conforming_topology_bit_equal_to_oracle(tmp_path, fixture):
     """Non-conforming (2:1 AMR) grids written by the reference's regrid: the C++ host's general fixHexCells route (coplanar

@@ -1,0 +1,96 @@
+"""VTK output: `euler ./controls -vtk` and EulerSolver::write_vtk against the files the reference's own
+`prepare ./controls -vtk` wrote (Vtk::write_vtk, src/vtk/vtk.cpp:125-286) -- byte for byte.  Host only, no GPU."""
+import glob
+import gzip
+import os
+import shutil
+import subprocess
+
+import pytest
+
+from nebulasem_b200 import build
+from oracle import cases as ocases
+from oracle import run_ref
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vtk")
+FIXTURES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLD, "*")) if os.path.isdir(p))
+
+
+def convert(case_dir, *args):
+    out = subprocess.run([build.EULER_BIN, "./controls", "-vtk", *args], cwd=case_dir, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-500:] + out.stderr[-500:]
+    return out.stdout
+
+
+def test_fixtures_present():
+    assert FIXTURES == ["bubble2d_n3_o3", "bubble3d_n2_o2", "hill3d_3x1x2_o2"]
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_vtk_byte_identical_to_reference_fixture(tmp_path, name):
+    d = str(tmp_path / name)
+    shutil.copytree(os.path.join(GOLD, name), d)
+    with gzip.open(os.path.join(d, "grid1.vtk.gz"), "rb") as f:
+        want = f.read()
+    assert "Converting result to VTK format." in convert(d, "-start", "1")
+    got = open(os.path.join(d, "grid1.vtk"), "rb").read()
+    assert got == want
+    if name.startswith("hill3d"):
+        assert b"CELL_DATA" not in got                  # vtk{write_cell_value NO}
+    else:
+        assert b"cellID  1 " in got
+
+
+def test_solver_object_writes_the_same_file(tmp_path):
+    """write_vtk of an opened case (the call the run loop makes after a download with NSEM_VTK=1) == the command-line conversion."""
+    from nebulasem_b200 import host
+    d = str(tmp_path / "case")
+    shutil.copytree(os.path.join(GOLD, "bubble2d_n3_o3"), d)
+    with gzip.open(os.path.join(d, "grid1.vtk.gz"), "rb") as f:
+        want = f.read()
+    s = host.Solver.open_case(d, 1)          # grid_0 is the newest grid <= dump 1 (findLastRefinedGrid, field.cpp:79-91)
+    s.write_vtk(7)
+    s.close()
+    # open_case runs the set-up (p from rho, euler.cpp:150-162), so p may differ in the last printed digit: compare everything but p
+    got = open(os.path.join(d, "grid7.vtk"), "rb").read()
+    cut = lambda b: b[:b.index(b"\np 1 ")] + b[b.index(b"\nrho 1 "):]
+    assert cut(got) == cut(want)
+
+
+def test_range_of_dumps_and_field_selection(tmp_path):
+    """-start i -stop j converts dumps i..j-1; prepare{fields} selects and orders the fields (scalars first, then vectors)."""
+    d = str(tmp_path / "case")
+    shutil.copytree(os.path.join(GOLD, "bubble3d_n2_o2"), d)
+    for f in ("rho", "U", "T", "p"):
+        shutil.copy(os.path.join(d, f + "1.bin"), os.path.join(d, f + "2.bin"))
+    ctl = open(os.path.join(d, "controls")).read().replace("fields 4 { U T p rho }", "fields 2 { U rho }")
+    assert "fields 2 { U rho }" in ctl
+    open(os.path.join(d, "controls"), "w").write(ctl)
+    convert(d, "-start", "1", "-stop", "3")
+    a, b = (open(os.path.join(d, f"grid{k}.vtk"), "rb").read() for k in (1, 2))
+    assert a == b and b"FIELD attributes 2\nrho 1 216 double" in a and b"\nU 3 216 double" in a and b"\nT 1 " not in a
+    assert a.index(b"rho 1 216") < a.index(b"U 3 216")
+
+
+def test_unknown_option_is_an_error(tmp_path):
+    d = str(tmp_path / "case")
+    shutil.copytree(os.path.join(GOLD, "bubble3d_n2_o2"), d)
+    out = subprocess.run([build.EULER_BIN, "./controls", "-vtx"], cwd=d, capture_output=True, text=True, timeout=60)
+    assert out.returncode != 0 and "unknown option" in out.stderr
+
+
+@pytest.mark.skipif(not run_ref.have_ref("parity"), reason="oracle/_ref/parity not built")
+@pytest.mark.parametrize("case,kw,nsteps", [
+    ("vortex", dict(n=3, order=4), 3),
+    ("bubble2d", dict(n=4, order=2), 2),
+])
+def test_vtk_byte_identical_to_reference_live(tmp_path, case, kw, nsteps):
+    """Fresh cases through the reference's euler + prepare and through this repo's converter."""
+    d = str(tmp_path / case)
+    ocases.CASES[case](**kw).write(d, nsteps)
+    run_ref.run_euler(d, variant="parity")
+    out = subprocess.run([run_ref.ref_bin("prepare"), "./controls", "-vtk", "-start", "1"], cwd=d, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-500:]
+    os.rename(os.path.join(d, "grid1.vtk"), os.path.join(d, "ref1.vtk"))
+    convert(d, "-start", "1")
+    assert open(os.path.join(d, "grid1.vtk"), "rb").read() == open(os.path.join(d, "ref1.vtk"), "rb").read()
