@@ -94,3 +94,40 @@ def test_vtk_byte_identical_to_reference_live(tmp_path, case, kw, nsteps):
     os.rename(os.path.join(d, "grid1.vtk"), os.path.join(d, "ref1.vtk"))
     convert(d, "-start", "1")
     assert open(os.path.join(d, "grid1.vtk"), "rb").read() == open(os.path.join(d, "ref1.vtk"), "rb").read()
+
+
+@pytest.mark.gpu
+def test_binary_resumes_from_the_reference_dump_and_writes_vtk_on_dumps(tmp_path):
+    """`start_step 4` on the reference's dump 1 (fixture): the binary runs steps 5..8 on the GPU, writes dump 2 and, with NSEM_VTK=1,
+    grid2.vtk from the downloaded state.  Dump 2 against the oracle set up on dump 1's fields (which is bit-identical to the reference
+    resumed the same way, tests/test_oracle_vs_reference.py); the VTK against the conversion of that dump."""
+    import numpy as np
+
+    from oracle import case as ocase
+    from oracle import refio
+    from tests.helpers import conserved_errors
+    d = str(tmp_path / "resumed")
+    shutil.copytree(os.path.join(GOLD, "bubble3d_n2_o2"), d)
+    d0 = str(tmp_path / "as_step0")
+    os.makedirs(d0)
+    for f in ("rho", "U", "T", "p"):
+        shutil.copy(os.path.join(d, f + "1.bin"), os.path.join(d0, f + "0.bin"))
+    shutil.copy(os.path.join(d, "grid_0.txt"), d0)
+    shutil.copy(os.path.join(d, "controls"), d0)
+    orc = ocase.load_case(d0, exact_order=False)
+    orc.run(4)
+    ctl = open(os.path.join(d, "controls")).read()
+    open(os.path.join(d, "controls"), "w").write(ctl.replace("start_step 0", "start_step 4").replace("end_step 4", "end_step 8"))
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    out = subprocess.run([build.EULER_BIN, "./controls"], cwd=d, env=dict(env, NSEM_VTK="1"), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-800:] + out.stderr[-800:]
+    rho, U, T = (refio.read_field_values(os.path.join(d, f + "2")) for f in ("rho", "U", "T"))
+    err = conserved_errors(orc, rho[:, 0], U, T[:, 0])
+    print(err)
+    assert err["rho"] <= 1e-11 and err["rhoTheta"] <= 1e-11 and err["rhoU_scaled"] <= 1e-11
+    on_dump = open(os.path.join(d, "grid2.vtk"), "rb").read()
+    os.rename(os.path.join(d, "grid2.vtk"), os.path.join(d, "on_dump.vtk"))
+    convert(d, "-start", "2")
+    converted = open(os.path.join(d, "grid2.vtk"), "rb").read()
+    cut = lambda b: b[:b.index(b"\np 1 ")] + b[b.index(b"\nrho 1 "):]     # the conversion's set-up recomputes p from rho
+    assert cut(on_dump) == cut(converted) and b"POINT_DATA 216" in on_dump
