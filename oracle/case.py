@@ -43,6 +43,12 @@ def init_field(ff: refio.FieldFile, geo: Geometry, gravity) -> np.ndarray:
                     pw = 2.0 if kind == "cosine2" else 1.0
                     c = libm.pow_(1.0 + libm.cos_(Rr * PI), pw)
                     out += value[None, :] + (pert / 2)[None, :] * c[:, None]
+        elif kind == "gaussian-outside":                 # field.h:1468-1485 (examples/atmo/ctbs)
+            _, value, pert, center, r1, r2 = ini
+            Rr = (vmag(geo.cC - center[None, :]) - r1) / r2
+            v = libm.exp_(-Rr * Rr)
+            v = np.array([1.0 if r <= 0 else (0.0 if equal(float(x), 0.0) else x) for x, r in zip(v, Rr)])
+            out += value[None, :] + pert[None, :] * v[:, None]
         elif kind == "hydrostatic":
             _, p0, scale, expon = ini
             gh = geo.cC @ np.asarray(gravity, dtype=float)

@@ -1,0 +1,73 @@
+"""The reference's OWN euler examples (every non-spherical `solver euler` directory under examples/: isentropic, atmo/{ctbs, dc, lrtb,
+srtb, srtb-3d, srtb-amr, srtb-amr-hill, srtb-amr-zaxis, srtb-curved, srtb-inclined}), as fixtures made by
+tests/golden/make_examples_golden.py: the example's case files, the grid the reference's mesher made of its block file, and the dump of the
+unmodified reference binary after 3 steps.
+
+CPU: the numpy oracle is bit-identical to the reference on every one of them; the C++ host reads the same files and arrives at the same
+geometry and set-up state, bit for bit.  GPU: the CUDA path from those files against the reference's dump (<= 1e-11, north_star).
+(Named test_zz_* so that the GPU part runs after the core parity tests.)"""
+import glob
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+from oracle import case as ocase
+from tests.helpers import rel_l2
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "examples")
+NAMES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLD, "*")) if os.path.isdir(p))
+TOL = 1e-11
+
+
+def test_all_example_fixtures_present():
+    assert NAMES == ["ctbs", "dc", "isentropic", "lrtb", "srtb", "srtb-3d", "srtb-amr", "srtb-amr-hill", "srtb-amr-zaxis", "srtb-curved",
+                     "srtb-inclined"]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_and_host_setup_on_the_reference_examples(tmp_path, name):
+    from nebulasem_b200 import host
+    d = str(tmp_path / name)
+    shutil.copytree(os.path.join(GOLD, name), d)
+    exp = np.load(os.path.join(d, "expected.npz"))
+    orc = ocase.load_case(d, exact_order=True)
+    s = host.Solver.open_case(d)
+    g = orc.g
+    assert (s.nBCS, s.nCells, s.nFacets) == (g.nBCS, g.nCells, g.nFacets)
+    for nm, ref in (("cC", g.cC), ("cV", g.cV), ("Jinv", g.Jinv), ("fN", g.fN), ("fC", g.fC), ("fI", g.fI)):
+        assert np.array_equal(s.f64(nm), np.asarray(ref).ravel()), nm
+    for nm, ref in (("FO", g.FO), ("FN", g.FN), ("allFaces", g.allFaces)):
+        assert np.array_equal(s.u32(nm), np.asarray(ref, dtype=np.uint32).ravel()), nm
+    rho, U, T, p = s.state()
+    assert np.array_equal(rho, orc.rho) and np.array_equal(U, orc.U) and np.array_equal(T, orc.T) and np.array_equal(p, orc.pp)
+    assert np.array_equal(s.f64("rho_ref"), orc.rho_ref) and np.array_equal(s.f64("p_ref"), orc.p_ref)
+    s.close()
+    orc.run(int(exp["nsteps"]))
+    nb = orc.gB
+    assert np.array_equal(orc.rho[:nb], exp["rho"]) and np.array_equal(orc.U[:nb], exp["U"])
+    assert np.array_equal(orc.T[:nb], exp["T"]) and np.array_equal(orc.pp[:nb], exp["p"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+def test_device_runs_the_reference_examples(tmp_path, name):
+    from nebulasem_b200 import host
+    d = str(tmp_path / name)
+    shutil.copytree(os.path.join(GOLD, name), d)
+    exp = np.load(os.path.join(d, "expected.npz"))
+    s = host.Solver.open_case(d)
+    T0, cp, cv = s.params["T0"], s.params["cp"], s.params["cv"]
+    s.attach(0)
+    s.step(int(exp["nsteps"]))
+    s.download()
+    rho, U, T, p = s.state()
+    nb = s.gBCSfield
+    s.close()
+    c0 = np.sqrt(cp / cv * (cp - cv) * T0)
+    err = dict(rho=rel_l2(rho[:nb], exp["rho"]),
+               rhoTheta=rel_l2(rho[:nb] * (T[:nb] + T0), exp["rho"] * (exp["T"] + T0)),
+               rhoU_scaled=rel_l2(rho[:nb, None] * U[:nb], exp["rho"][:, None] * exp["U"], scale=np.linalg.norm(exp["rho"]) * c0))
+    print(name, err)
+    assert err["rho"] <= TOL and err["rhoTheta"] <= TOL and err["rhoU_scaled"] <= TOL, err
