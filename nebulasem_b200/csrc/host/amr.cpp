@@ -107,12 +107,57 @@ int AmrForest::split_mask(const Node& n) const {
     return 7 & ~(1 << best);
 }
 
+// MeshObject::calcFaceCenter (mesh.cpp:1166-1188): fan of triangles around the vertex average, centroids weighted by the triangle areas.
+// On a parallelogram this is the vertex average; on a general quadrilateral (terrain-following grids) it is not.  `area2` = sum of the
+// fan's cross products (twice the area vector).
+static Vec3 corrected_face_centre(const std::vector<Vec3>& V, const u32 q[4], Vec3* area2 = nullptr) {
+    Vec3 c0{0, 0, 0};
+    for (int j = 0; j < 4; j++) for (int d = 0; d < 3; d++) c0[d] += V[q[j]][d];
+    for (int d = 0; d < 3; d++) c0[d] /= 4.0;
+    Vec3 ct{0, 0, 0}, nsum{0, 0, 0};
+    double ntot = 0;
+    for (int j = 0; j < 4; j++) {
+        const Vec3 &v2 = V[q[j]], &v3 = V[q[(j + 1) % 4]];
+        const double a[3] = {v2[0] - c0[0], v2[1] - c0[1], v2[2] - c0[2]}, b[3] = {v3[0] - c0[0], v3[1] - c0[1], v3[2] - c0[2]};
+        const double n[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+        const double m = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+        for (int d = 0; d < 3; d++) { ct[d] += m * ((c0[d] + v2[d] + v3[d]) / 3.0); nsum[d] += n[d]; }
+        ntot += m;
+    }
+    if (area2) *area2 = nsum;
+    if (ntot == 0) return c0;
+    return Vec3{ct[0] / ntot, ct[1] / ntot, ct[2] / ntot};
+}
+
 u32 AmrForest::mid_vertex(const std::vector<u32>& of) {
-    // the vertex in the middle of 2 (edge), 4 (face) or 8 (cell) vertices; edges and faces are shared through the maps
+    // the vertex in the middle of 2 (edge), 4 (face) or 8 (cell) parent corners, placed where MeshObject::refineMesh places it: edge
+    // midpoint (mesh.cpp:1296), corrected face centre (refineFacet, mesh.cpp:1251-1253), cell centroid (calcCellCenter, mesh.cpp:1192-1243,
+    // used at mesh.cpp:1647).  `of` lists the corners in lexicographic (x, y, z) order; edges and faces are shared through the maps
     auto make = [&]() {
         Vec3 s{0, 0, 0};
-        for (u32 v : of) for (int d = 0; d < 3; d++) s[d] += V[v][d];
-        for (int d = 0; d < 3; d++) s[d] /= (double)of.size();
+        if (of.size() == 4) {
+            const u32 q[4] = {of[0], of[1], of[3], of[2]};                        // lexicographic -> around the face
+            s = corrected_face_centre(V, q);
+        } else if (of.size() == 8) {
+            static const int kFace[6][4] = {{0, 1, 3, 2}, {4, 5, 7, 6}, {0, 1, 5, 4}, {2, 3, 7, 6}, {0, 2, 6, 4}, {1, 3, 7, 5}};
+            Vec3 c0{0, 0, 0};
+            for (u32 v : of) for (int d = 0; d < 3; d++) c0[d] += V[v][d];
+            for (int d = 0; d < 3; d++) c0[d] /= 8.0;
+            Vec3 ct{0, 0, 0};
+            double vt = 0;
+            for (int f = 0; f < 6; f++) {
+                const u32 q[4] = {of[kFace[f][0]], of[kFace[f][1]], of[kFace[f][2]], of[kFace[f][3]]};
+                Vec3 a2;
+                const Vec3 fc = corrected_face_centre(V, q, &a2);
+                const double vi = std::fabs((c0[0] - fc[0]) * a2[0] + (c0[1] - fc[1]) * a2[1] + (c0[2] - fc[2]) * a2[2]) / 2.0;   // 3 x pyramid volume
+                for (int d = 0; d < 3; d++) ct[d] += vi * (3 * fc[d] + c0[d]) / 4.0;
+                vt += vi;
+            }
+            s = vt == 0 ? c0 : Vec3{ct[0] / vt, ct[1] / vt, ct[2] / vt};
+        } else {
+            for (u32 v : of) for (int d = 0; d < 3; d++) s[d] += V[v][d];
+            for (int d = 0; d < 3; d++) s[d] /= (double)of.size();
+        }
         V.push_back(s);
         return (u32)V.size() - 1;
     };

@@ -71,3 +71,30 @@ def test_device_runs_the_reference_examples(tmp_path, name):
                rhoU_scaled=rel_l2(rho[:nb, None] * U[:nb], exp["rho"][:, None] * exp["U"], scale=np.linalg.norm(exp["rho"]) * c0))
     print(name, err)
     assert err["rho"] <= TOL and err["rhoTheta"] <= TOL and err["rhoU_scaled"] <= TOL, err
+
+
+@pytest.mark.parametrize("name,cells", [("srtb-amr", (100, 196)), ("srtb-3d", (216, 608)), ("srtb-amr-hill", (484, 802))])
+def test_initial_regrid_of_the_amr_examples_matches_the_reference(tmp_path, monkeypatch, name, cells):
+    """The examples that ship with `amr_step 1`: the reference regrids before step 1 (tagging by the example's refinement{} block, then
+    MeshObject::refineMesh).  The in-memory regrid (amr.cpp) tags the same cells and places the new vertices where the reference does --
+    also on the terrain-following srtb-amr-hill grid, whose face centres are not vertex averages (calcFaceCenter, mesh.cpp:1166-1188):
+    same cells (centroid, volume to 1e-12), same facet and mortar-face counts."""
+    from nebulasem_b200 import host
+    monkeypatch.setenv("NSEM_AMR", "1")                  # the fixture's controls have amr_step removed; keep the forest and refinement{}
+    d = str(tmp_path / name)
+    shutil.copytree(os.path.join(GOLD, name), d)
+    exp = np.load(os.path.join(d, "initial_regrid.npz"))
+    s = host.Solver.open_case(d)
+    assert s.nBCS == cells[0]
+    s.regrid()
+    assert s.nBCS == cells[1] == len(exp["CV"]) and s.nFacets == int(exp["n_facets"])
+    assert int((s.u32("faceMortar") > 0).sum()) == int(exp["n_mortar"])
+    n = s.nBCS
+    mine = np.concatenate([s.f64("gCC")[:3 * n].reshape(n, 3), s.f64("gCV")[:n, None]], axis=1)
+    ref = np.concatenate([exp["CC"], exp["CV"][:, None]], axis=1)
+    s.close()
+    order = lambda a: a[np.lexsort(np.round(a, 6).T[::-1])]
+    mine, ref = order(mine), order(ref)
+    err = np.abs(mine - ref).max(axis=0) / np.abs(ref).max(axis=0)
+    print(name, err)
+    assert np.all(err <= 1e-12), err
