@@ -156,7 +156,7 @@ def run_reference_sample(n_side: int, steps: int, warmup: int, threads: int | No
     from oracle import cases, run_ref          # test infrastructure, allowed here (cpu_baseline / reference arm only)
     variant = "fast" if run_ref.have_ref("fast") else "parity"
     if not run_ref.have_ref(variant):
-        return {"unavailable": "oracle/_ref has no compiled reference (run oracle/build_ref.sh where /root/reference exists)"}
+        return run_oracle_port_sample(steps, warmup)
     threads = threads or os.cpu_count() or 1
     d = tempfile.mkdtemp(prefix="nsem_ref_")
     try:
@@ -176,6 +176,27 @@ def run_reference_sample(n_side: int, steps: int, warmup: int, threads: int | No
                 "sample": f"bubble3d {n_side}^3 elements order {ORDER} ({nodes} nodes), {steps} steps after {warmup} warm-up, "
                           f"oracle/_ref/{variant}/euler (unmodified reference, 1 rank x {threads} OpenMP threads; no MPI in the image)",
                 "ms_per_step": t_ms / steps}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def run_oracle_port_sample(steps: int, warmup: int, n_side: int = 4) -> dict:
+    """No compiled reference on this box (oracle/_ref is built where /root/reference exists and travels with the repo): time the numpy
+    restatement instead ("port", one thread, a much smaller sample -- it is a checker, not a fast CPU code)."""
+    from oracle import case as ocase
+    from oracle import cases
+    d = tempfile.mkdtemp(prefix="nsem_port_")
+    try:
+        cases.bubble3d(n=n_side, order=ORDER, scheme="AB1").write(d, end_step=warmup + steps)
+        orc = ocase.load_case(d, exact_order=False)
+        orc.run(warmup)
+        t0 = time.time()
+        orc.run(steps)
+        t_ms = (time.time() - t0) * 1e3
+        nodes = n_side ** 3 * NP
+        return {"value": 5.0 * nodes * steps / (t_ms * 1e-3), "unit": "DOF-updates/s", "cores": 1, "kind": "port",
+                "sample": f"bubble3d {n_side}^3 elements order {ORDER} ({nodes} nodes), {steps} steps after {warmup} warm-up, numpy oracle "
+                          f"(oracle/euler.py; oracle/_ref absent on this box)", "ms_per_step": t_ms / steps}
     finally:
         shutil.rmtree(d, ignore_errors=True)
 
