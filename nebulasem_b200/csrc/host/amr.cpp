@@ -461,6 +461,8 @@ void AmrForest::load(const std::string& path) {
 // ---------------------------------------------------------------------------------------------------------
 // tagging (Prepare::calcQOI + the first half of Prepare::refineMesh, field.cpp:606-620, 696-824)
 // ---------------------------------------------------------------------------------------------------------
+static bool pair_cyclic_owners(const EulerSolver& s, std::vector<uint8_t>& refine, std::vector<uint8_t>& coarsen, bool check_only);
+
 void amr_tag_cells(const EulerSolver& s, const RefineParams& rp, const std::vector<int>& levels, const std::vector<std::vector<u32>>& families,
                    std::vector<uint8_t>& refine, std::vector<uint8_t>& coarsen) {
     const u32 nB = s.geo.nBCS;
@@ -550,6 +552,100 @@ void amr_tag_cells(const EulerSolver& s, const RefineParams& rp, const std::vect
             if (!all) for (u32 c : fam) if (coarsen[c]) { coarsen[c] = 0; changed = true; }
         }
     }
+    // owner cells of paired CYCLIC faces go together (field.cpp:826-858), then whole families again (field.cpp:860-875)
+    pair_cyclic_owners(s, refine, coarsen, false);
+    for (const auto& fam : families) {
+        bool all = true;
+        for (u32 c : fam) all &= (coarsen[c] != 0);
+        if (!all) for (u32 c : fam) coarsen[c] = 0;
+    }
+}
+
+// (patch, neighbor) of every CYCLIC condition the field files state, each pair once (field.cpp:828-838)
+static std::vector<std::array<std::string, 2>> cyclic_pairs(const EulerSolver& s) {
+    std::vector<std::array<std::string, 2>> out;
+    for (const std::vector<BCond>* l : {&s.file_bc_rho, &s.file_bc_U, &s.file_bc_T, &s.file_bc_p})
+        for (const BCond& b : *l) {
+            if (b.type != "CYCLIC") continue;
+            bool seen = false;
+            for (const auto& pr : out) seen |= (pr[0] == b.patch || pr[1] == b.patch);
+            if (!seen) out.push_back({b.patch, b.neighbor});
+        }
+    return out;
+}
+
+// the owner cells of paired CYCLIC faces are refined together and coarsened together (field.cpp:826-858): face j of a patch is paired with
+// face j of its neighbor patch.  check_only: report a violation instead of repairing it (explicit flags)
+static bool pair_cyclic_owners(const EulerSolver& s, std::vector<uint8_t>& refine, std::vector<uint8_t>& coarsen, bool check_only) {
+    bool consistent = true;
+    for (const auto& pr : cyclic_pairs(s)) {
+        auto i1 = s.topo.boundaries.find(pr[0]), i2 = s.topo.boundaries.find(pr[1]);
+        if (i1 == s.topo.boundaries.end() || i2 == s.topo.boundaries.end() || i1->second.size() != i2->second.size())
+            throw Error("CYCLIC patches " + pr[0] + "/" + pr[1] + " missing or of different size");
+        for (size_t j = 0; j < i1->second.size(); j++) {
+            const u32 c1 = s.topo.FOC[i1->second[j]], c2 = s.topo.FOC[i2->second[j]];
+            if (check_only) { consistent &= (refine[c1] == refine[c2]) && (coarsen[c1] == coarsen[c2]); continue; }
+            if (refine[c1] && !refine[c2]) { refine[c2] = 1; coarsen[c2] = 0; }
+            else if (refine[c2] && !refine[c1]) { refine[c1] = 1; coarsen[c1] = 0; }
+            else if (refine[c1] && refine[c2]) {}
+            else if (!coarsen[c1] || !coarsen[c2]) coarsen[c1] = coarsen[c2] = 0;
+        }
+    }
+    return consistent;
+}
+
+// After a regrid the faces of a CYCLIC patch and of its neighbor patch are paired by position again (field.h:2662-2664 pairs face j with
+// face j): the neighbor's list is reordered so that face j lies opposite face j of the patch (same bounding-box centre up to the translation
+// between the two patches).  Throws when the two sides were not refined alike.
+static void repair_cyclic_order(Grid& g, const std::vector<std::array<std::string, 2>>& pairs) {
+    auto centre = [&](u32 f) {
+        Vec3 lo{1e300, 1e300, 1e300}, hi{-1e300, -1e300, -1e300};
+        for (u32 k = g.facetStart[f]; k < g.facetStart[f + 1]; k++)
+            for (int d = 0; d < 3; d++) { lo[d] = std::min(lo[d], g.V[g.facetVerts[k]][d]); hi[d] = std::max(hi[d], g.V[g.facetVerts[k]][d]); }
+        return Vec3{(lo[0] + hi[0]) / 2, (lo[1] + hi[1]) / 2, (lo[2] + hi[2]) / 2};
+    };
+    for (const auto& pr : pairs) {
+        auto i1 = g.boundaries.find(pr[0]), i2 = g.boundaries.find(pr[1]);
+        if (i1 == g.boundaries.end() || i2 == g.boundaries.end() || i1->second.size() != i2->second.size())
+            throw Error("regrid: CYCLIC patches " + pr[0] + "/" + pr[1] + " were not refined alike (paired faces must be refined together)");
+        const std::vector<u32>&A = i1->second;
+        std::vector<u32>& B = i2->second;
+        if (A.empty()) continue;
+        std::vector<Vec3> ca(A.size()), cb(B.size());
+        Vec3 ma{0, 0, 0}, mb{0, 0, 0}, lo{1e300, 1e300, 1e300}, hi{-1e300, -1e300, -1e300};
+        for (size_t j = 0; j < A.size(); j++) {
+            ca[j] = centre(A[j]); cb[j] = centre(B[j]);
+            for (int d = 0; d < 3; d++) { lo[d] = std::min(lo[d], ca[j][d]); hi[d] = std::max(hi[d], ca[j][d]); }
+        }
+        // translation between the patches: difference of the patches' own bounding-box centres (independent of how the faces are listed)
+        Vec3 la{1e300, 1e300, 1e300}, ha{-1e300, -1e300, -1e300}, lb = la, hb = ha;
+        for (size_t j = 0; j < A.size(); j++)
+            for (int d = 0; d < 3; d++) {
+                la[d] = std::min(la[d], ca[j][d]); ha[d] = std::max(ha[d], ca[j][d]);
+                lb[d] = std::min(lb[d], cb[j][d]); hb[d] = std::max(hb[d], cb[j][d]);
+            }
+        double scale = 0;
+        for (int d = 0; d < 3; d++) { ma[d] = (la[d] + ha[d]) / 2; mb[d] = (lb[d] + hb[d]) / 2; scale = std::max(scale, std::max(ha[d] - la[d], std::fabs(mb[d] - ma[d]))); }
+        const double tol = 1e-9 * (scale > 0 ? scale : 1.0);
+        std::vector<u32> nb(B.size(), MAX_INT);
+        std::vector<uint8_t> used(B.size(), 0);
+        for (size_t j = 0; j < A.size(); j++) {
+            size_t best = B.size();
+            // same position first (the usual case: both lists come out of the forest in the same order), then a search
+            auto close = [&](size_t k) {
+                double e = 0;
+                for (int d = 0; d < 3; d++) e = std::max(e, std::fabs((cb[k][d] - mb[d]) - (ca[j][d] - ma[d])));
+                return e <= tol;
+            };
+            if (!used[j] && close(j)) best = j;
+            else for (size_t k = 0; k < B.size() && best == B.size(); k++) if (!used[k] && close(k)) best = k;
+            if (best == B.size())
+                throw Error("regrid: CYCLIC patches " + pr[0] + "/" + pr[1] + " were not refined alike (paired faces must be refined together)");
+            used[best] = 1;
+            nb[j] = B[best];
+        }
+        B = nb;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -561,10 +657,17 @@ std::unique_ptr<EulerSolver> EulerSolver::regridded(const std::vector<uint8_t>& 
         for (const BCond& b : *l)
         {
             if (!b.fixed.empty()) throw Error("EulerSolver::regridded: boundary conditions with frozen per-face values cannot follow a regrid");
-            // the reference refines the owner cells of paired CYCLIC faces together and pairs the faces by their position in the two patches
-            // (field.cpp:827-858, field.h:2662-2664); neither is built here
-            if (b.type == "CYCLIC") throw Error("EulerSolver::regridded: CYCLIC patches cannot follow a regrid yet (paired faces must be refined together)");
         }
+    // the reference refines the owner cells of paired CYCLIC faces together (field.cpp:826-858; amr_tag_cells does) and pairs the faces by
+    // their position in the two patches (field.h:2662-2664; repair_cyclic_order below).  Flags that split a pair are refused before the
+    // forest is touched
+    const std::vector<std::array<std::string, 2>> cyc = cyclic_pairs(*this);
+    if (!cyc.empty()) {
+        std::vector<uint8_t> r = refine, c = coarsen;
+        if (r.size() != topo.nBCS || c.size() != topo.nBCS) throw Error("EulerSolver::regridded: one refine and one coarsen flag per cell expected");
+        if (!pair_cyclic_owners(*this, r, c, true))
+            throw Error("EulerSolver::regridded: the owner cells of paired CYCLIC faces must be refined (or coarsened) together");
+    }
     if (!forest) throw Error("EulerSolver::regridded: no AMR forest (the mesh must come from set_mesh/load_mesh of a conforming hexahedral grid)");
     std::unique_ptr<EulerSolver> n(new EulerSolver());
     n->ctl = ctl; n->dir = dir; n->meshName = meshName;
@@ -585,7 +688,8 @@ std::unique_ptr<EulerSolver> EulerSolver::regridded(const std::vector<uint8_t>& 
     };
     n->last_maps = forest->regrid(refine, coarsen);
     lap("forest regrid");
-    const Grid g = forest->grid();
+    Grid g = forest->grid();
+    repair_cyclic_order(g, cyc);
     lap("grid emission");
     n->topo.load(g);
     lap("topology (MeshTopo::load)");

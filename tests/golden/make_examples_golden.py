@@ -27,8 +27,8 @@ from oracle.mesh import MeshTopo  # noqa: E402
 
 EXAMPLES = "/root/reference/examples"
 NSTEPS = 3
-AMR_CASES = ("srtb-3d", "srtb-amr", "srtb-amr-hill")        # amr_step examples without CYCLIC patches (isentropic) whose regrid the reference
-                                                             # survives (it segfaults on srtb-amr-zaxis in this build)
+AMR_CASES = ("isentropic", "srtb-3d", "srtb-amr", "srtb-amr-hill")    # the amr_step examples whose regrid the reference survives (it
+                                                                       # segfaults on srtb-amr-zaxis in this build)
 CASES = ["isentropic", "atmo/ctbs", "atmo/dc", "atmo/lrtb", "atmo/srtb", "atmo/srtb-3d", "atmo/srtb-amr", "atmo/srtb-amr-hill",
          "atmo/srtb-amr-zaxis", "atmo/srtb-curved", "atmo/srtb-inclined"]
 

@@ -219,9 +219,13 @@ def test_regrid_refuses_what_it_cannot_do(monkeypatch):
     with pytest.raises(capi.NsemError, match="no AMR forest"):
         s.regrid()
     s.close()
-    s = host.Solver.synthetic("vortex", 4, 4, 1, 2)                     # CYCLIC patches pair their faces by position in the patch
+    s = host.Solver.synthetic("vortex", 4, 4, 1, 2)                     # CYCLIC patches pair their faces by position in the patch:
+    r = np.zeros(16, np.uint8)                                          # a corner cell without its periodic images
+    r[0] = 1
     with pytest.raises(capi.NsemError, match="CYCLIC"):
-        s.regrid()
+        s.regrid(r, np.zeros(16, np.uint8))
+    s.enable_amr(direction=(0, 0, 1), field="U", field_min=0.2, field_max=0.6, max_level=1, buffer_zone=2)
+    s.regrid()                                                          # tagged by the indicator, pairs stay together
     s.close()
     monkeypatch.delenv("NSEM_AMR")
     s = host.Solver.synthetic("bubble3d", 3, 3, 3, 2)                  # no forest was asked for
@@ -337,4 +341,50 @@ def test_amr_cycle_on_the_device_conserves_mass():
     assert all(np.isfinite(x).all() for x in (rho, U, T, p))
     assert cells[1] == 372 and s.cell_levels().max() >= 1
     assert "mortar" in s.kernel_info
+    s.close()
+
+
+def test_cyclic_patches_follow_a_regrid(tmp_path):
+    """examples/isentropic (CYCLIC in x and y): cells that touch a periodic patch are refined together with the owners of the paired faces
+    (field.cpp:826-858), and after the regrid face j of a patch lies opposite face j of its neighbor patch again (the pairing
+    applyExplicitBCs relies on, field.h:2662-2664).  Explicit flags that split a pair are refused before the forest is touched."""
+    from nebulasem_b200 import host
+    d = str(tmp_path / "isentropic")
+    shutil.copytree(os.path.join(GOLD, "examples", "isentropic"), d)
+    s = host.Solver.open_case(d)
+    s.enable_amr(direction=(0, 0, 1), field="T", field_min=0.15, field_max=0.4, max_level=2, buffer_zone=1)
+    fc = lambda: s.f64("faceCenter").reshape(-1, 3)
+    import re
+    pairs = re.findall(r"(\w+)\s*\{\s*type\s+CYCLIC\s+neighbor\s+(\w+)", open(os.path.join(d, "U0.txt")).read())
+    assert len(pairs) == 4                                       # 2 periodic directions, each stated from both sides
+    n0 = s.nBCS
+    # an explicit request that refines one side of a periodic pair only
+    left = s.patch_faces(pairs[0][0])
+    r = np.zeros(s.nBCS, np.uint8)
+    r[s.u32("faceOwner")[left[0]]] = 1
+    with pytest.raises(Exception, match="CYCLIC"):
+        s.regrid(r, np.zeros(s.nBCS, np.uint8))
+    assert s.nBCS == n0 and s.cell_levels().max() == 0           # nothing happened
+    # a blob on the corner of the domain: the tagging refines it on all four periodic images
+    x = s.f64("cC").reshape(-1, 3)
+    lo, hi = x.min(axis=0), x.max(axis=0)
+    rr = np.linalg.norm((x - np.array([lo[0], lo[1], 0.0]))[:, :2], axis=1) / (0.3 * (hi[0] - lo[0]))
+    s.set_state(T=np.where(rr < 1, 0.25 * (1 + np.cos(np.pi * rr)), 0.0))
+    for cycle in range(2):
+        s.regrid()
+        c = fc()
+        for a, b in pairs:
+            fa, fb = s.patch_faces(a), s.patch_faces(b)
+            assert len(fa) == len(fb) > 0
+            shift = c[fb] - c[fa]
+            assert np.abs(shift - shift[0]).max() <= 1e-9 * np.abs(hi - lo).max(), (a, b)
+            lv = s.cell_levels()
+            own = s.u32("faceOwner")
+            assert np.array_equal(lv[own[fa]], lv[own[fb]])
+        x = s.f64("cC").reshape(-1, 3)
+        rr = np.linalg.norm((x - np.array([lo[0], lo[1], 0.0]))[:, :2], axis=1) / (0.3 * (hi[0] - lo[0]))
+        s.set_state(T=np.where(rr < 1, 0.25 * (1 + np.cos(np.pi * rr)), 0.0))
+    lv = s.cell_levels()
+    own = s.u32("faceOwner")
+    assert s.nBCS > n0 and lv.max() == 2 and lv[own[s.patch_faces(pairs[0][0])]].max() >= 1     # the periodic patches were refined
     s.close()
