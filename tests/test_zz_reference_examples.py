@@ -100,3 +100,44 @@ def test_initial_regrid_of_the_amr_examples_matches_the_reference(tmp_path, monk
     err = np.abs(mine - ref).max(axis=0) / scale
     print(name, err)
     assert np.all(err <= 1e-12), err
+
+
+@pytest.mark.gpu
+def test_device_amr_across_periodic_patches_conserves_mass(tmp_path, monkeypatch):
+    """examples/isentropic on one B200 with a blob on the corner of the periodic domain: two regrids (to level 2) refine cells on the CYCLIC
+    patches on all four periodic images, the state stays on the device (nsem_refine_state), and 10 steps after each regrid conserve mass --
+    which they only do if the re-paired periodic faces see each other's traces node by node."""
+    from nebulasem_b200 import host
+    monkeypatch.setenv("NSEM_AMR", "1")
+    d = str(tmp_path / "isentropic")
+    shutil.copytree(os.path.join(GOLD, "isentropic"), d)
+    s = host.Solver.open_case(d)
+    s.enable_amr(direction=(0, 0, 1), field="T", field_min=0.15, field_max=0.4, max_level=2, buffer_zone=1)
+    s.attach(0)
+    x = s.f64("cC").reshape(-1, 3)
+    lo, hi = x.min(axis=0), x.max(axis=0)
+
+    def blob():
+        x = s.f64("cC").reshape(-1, 3)
+        r = np.linalg.norm((x - np.array([lo[0], lo[1], 0.0]))[:, :2], axis=1) / (0.3 * (hi[0] - lo[0]))
+        return np.where(r < 1, 0.25 * (1 + np.cos(np.pi * r)), 0.0)
+
+    def mass():
+        s.download()
+        n = s.gBCSfield
+        return float((s.state()[0][:n] * s.f64("cV")[:n]).sum())
+
+    s.set_state(T=blob())
+    s.upload()
+    volume = float(s.f64("cV")[:s.gBCSfield].sum())
+    m0 = mass()
+    n0 = s.nBCS
+    for cycle in range(2):
+        s.regrid()
+        assert abs(mass() - m0) <= 1e-11 * volume, cycle
+        s.step(10)
+        assert abs(mass() - m0) <= 1e-11 * volume, cycle
+    assert all(np.isfinite(v).all() for v in s.state())
+    lv, own = s.cell_levels(), s.u32("faceOwner")
+    assert s.nBCS > n0 and lv.max() >= 1 and lv[own[s.patch_faces("inx")]].max() >= 1 and lv[own[s.patch_faces("outy")]].max() >= 1
+    s.close()
