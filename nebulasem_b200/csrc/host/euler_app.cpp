@@ -678,11 +678,29 @@ void EulerSolver::merge_fields(int index) {
 void EulerSolver::run() {
     // Iteration (iteration.h:18-84): steps start_step*write_interval+1 .. end_step, dump when i % write_interval == 0
     long i = write_interval * start_step + 1;
+    const bool diag = (nranks == 1 || std::getenv("NSEM_DIAGNOSTICS"));
+    double m0 = mass0, e0 = energy0, v0 = volume0;
+    if (diag && nranks > 1 && i <= end_step) {          // the set-up's totals are those of this partition: take the global ones from the device
+        double dg[6];
+        if (nsem_diagnostics(ctx, dg)) throw Error(nsem_last_error(ctx));
+        m0 = dg[3]; e0 = dg[4]; v0 = dg[5];
+    }
     while (i <= end_step) {
         long next_dump = ((i + write_interval - 1) / write_interval) * write_interval;
         long upto = std::min(next_dump, end_step);
         step((int)(upto - i + 1));
         i = upto + 1;
+        // the lines the reference prints when its print timer fires and on the last step (euler.cpp:260-283, iteration.h:68-70): here at every
+        // dump and at the end.  On several partitions the sums are an ncclAllReduce every rank must join: opt-in (NSEM_DIAGNOSTICS=1)
+        if ((upto % write_interval == 0 || upto == end_step) && diag) {
+            double dg[6];
+            if (nsem_diagnostics(ctx, dg)) throw Error(nsem_last_error(ctx));
+            if (rank == 0) {
+                std::printf("Time %f\n", upto * dt);
+                std::printf("Courant number: Max: %g Min: %g Avg: %g\n", dg[0], dg[1], dg[2]);
+                std::printf("Mass loss: %.12g Energy loss %.12g Volume loss %.12g\n", (m0 - dg[3]) / m0, (e0 - dg[4]) / e0, (v0 - dg[5]) / v0);
+            }
+        }
         if (upto % write_interval == 0) {
             download();
             write_fields((int)(upto / write_interval));

@@ -121,6 +121,8 @@ def test_binary_resumes_from_the_reference_dump_and_writes_vtk_on_dumps(tmp_path
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
     out = subprocess.run([build.EULER_BIN, "./controls"], cwd=d, env=dict(env, NSEM_VTK="1"), capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-800:] + out.stderr[-800:]
+    # the reference's diagnostics lines (euler.cpp:276-281) at the dump
+    assert "Courant number: Max: " in out.stdout and "Mass loss: " in out.stdout and "Energy loss " in out.stdout, out.stdout[-800:]
     rho, U, T = (refio.read_field_values(os.path.join(d, f + "2")) for f in ("rho", "U", "T"))
     err = conserved_errors(orc, rho[:, 0], U, T[:, 0])
     print(err)
