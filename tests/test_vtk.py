@@ -133,3 +133,16 @@ def test_binary_resumes_from_the_reference_dump_and_writes_vtk_on_dumps(tmp_path
     converted = open(os.path.join(d, "grid2.vtk"), "rb").read()
     cut = lambda b: b[:b.index(b"\np 1 ")] + b[b.index(b"\nrho 1 "):]     # the conversion's set-up recomputes p from rho
     assert cut(on_dump) == cut(converted) and b"POINT_DATA 216" in on_dump
+
+
+@pytest.mark.skipif(not run_ref.have_ref("parity"), reason="oracle/_ref/parity not built")
+@pytest.mark.parametrize("fixture", ["srtb_amr", "srtb3d_amr"])
+def test_vtk_of_a_non_conforming_grid_byte_identical_live(tmp_path, fixture):
+    """The grids the reference's own regrid wrote (2:1 hanging nodes, merged sides): same file as the reference's prepare."""
+    d = str(tmp_path / fixture)
+    shutil.copytree(os.path.join(os.path.dirname(GOLD), fixture), d)
+    out = subprocess.run([run_ref.ref_bin("prepare"), "./controls", "-vtk", "-start", "0"], cwd=d, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-500:]
+    os.rename(os.path.join(d, "grid0.vtk"), os.path.join(d, "ref0.vtk"))
+    convert(d, "-start", "0")
+    assert open(os.path.join(d, "grid0.vtk"), "rb").read() == open(os.path.join(d, "ref0.vtk"), "rb").read()
