@@ -388,3 +388,27 @@ def test_cyclic_patches_follow_a_regrid(tmp_path):
     own = s.u32("faceOwner")
     assert s.nBCS > n0 and lv.max() == 2 and lv[own[s.patch_faces(pairs[0][0])]].max() >= 1     # the periodic patches were refined
     s.close()
+
+
+def test_regrids_of_a_terrain_following_mesh_keep_its_volume():
+    """3-D regrids (refinement and coarsening, two levels) of the non-affine hill mesh: the new vertices sit at the reference's corrected face
+    centres and cell centroids, the children tile their parents -- cell volumes and the nodal quadrature volume stay what they were."""
+    from nebulasem_b200 import host
+    s = host.Solver.synthetic("hill3d", 6, 3, 4, 2)
+    s.enable_amr(direction=(0, 0, 0), field="T", field_min=0.15, field_max=0.4, max_level=2, buffer_zone=1)
+    v0, q0 = s.f64("gCV")[:s.nBCS].sum(), s.f64("cV")[:s.gBCSfield].sum()
+    rng = np.random.default_rng(3)
+    x = s.f64("cC").reshape(-1, 3)
+    lo, hi = x.min(axis=0), x.max(axis=0)
+    counts, levels = [], set()
+    for cycle in range(4):
+        x = s.f64("cC").reshape(-1, 3)
+        ctr = lo + (hi - lo) * rng.random(3) * np.array([1, 1, 0.5])
+        r = np.linalg.norm((x - ctr) / (0.3 * (hi - lo)), axis=1)
+        s.set_state(T=np.where(r < 1, 0.25 * (1 + np.cos(np.pi * r)), 0.0))
+        s.regrid()
+        assert abs(s.f64("gCV")[:s.nBCS].sum() - v0) <= 1e-14 * v0 and abs(s.f64("cV")[:s.gBCSfield].sum() - q0) <= 1e-14 * q0, cycle
+        counts.append(s.nBCS)
+        levels.update(s.cell_levels().tolist())
+    assert 2 in levels and min(counts[1:]) < max(counts)          # deeper levels were reached, cells were removed again
+    s.close()
