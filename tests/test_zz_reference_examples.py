@@ -141,3 +141,20 @@ def test_device_amr_across_periodic_patches_conserves_mass(tmp_path, monkeypatch
     lv, own = s.cell_levels(), s.u32("faceOwner")
     assert s.nBCS > n0 and lv.max() >= 1 and lv[own[s.patch_faces("inx")]].max() >= 1 and lv[own[s.patch_faces("outy")]].max() >= 1
     s.close()
+
+
+def test_initial_regrid_of_the_zaxis_example_tags_what_the_reference_tags(tmp_path, monkeypatch):
+    """examples/atmo/srtb-amr-zaxis (x-z plane, refinement{direction 0 1 0}): the reference binary tags 24 cells ("Refining 24 Coarsening 0")
+    and then crashes inside its own regrid (both builds of oracle/_ref, so there is no grid to compare with); the in-memory regrid
+    refines 24 cells in the plane: 100 - 24 + 4 * 24 = 172 cells, one level, 2:1 across faces."""
+    from nebulasem_b200 import host
+    monkeypatch.setenv("NSEM_AMR", "1")
+    d = str(tmp_path / "zaxis")
+    shutil.copytree(os.path.join(GOLD, "srtb-amr-zaxis"), d)
+    s = host.Solver.open_case(d)
+    assert s.nBCS == 100
+    s.regrid()
+    lv = s.cell_levels()
+    assert s.nBCS == 172 and int((lv == 1).sum()) == 96 and lv.max() == 1
+    assert abs(s.f64("gCV")[:s.nBCS].sum() - 1000.0 * 100.0 * 1000.0) <= 1e-6          # the 1 km x 100 m x 1 km slab
+    s.close()
