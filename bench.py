@@ -202,6 +202,68 @@ def run_oracle_port_sample(steps: int, warmup: int, n_side: int = 4) -> dict:
 
 
 # ------------------------------------------------------------------------------------------------------
+def broadcast_unique_id(rank: int) -> bytes:
+    """A fresh ncclUniqueId from rank 0 for one nsem context group (torch.distributed is only the plumbing that carries it)."""
+    import ctypes
+
+    import torch
+    import torch.distributed as dist
+    from nebulasem_b200 import capi
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        buf = ctypes.create_string_buffer(128)
+        if capi.load_library().nsem_get_unique_id(buf) != 0:
+            raise SystemExit("bench.py: ncclGetUniqueId failed")
+        uid = torch.tensor(list(buf.raw), dtype=torch.uint8, device="cuda")
+    dist.broadcast(uid, 0)
+    return bytes(uid.cpu().tolist())
+
+
+def mp_parity_check(rank: int, world: int, device: int, decomp: str, pgrid, nsteps: int = 10) -> dict:
+    """Multi-GPU correctness where the driver can see it: the SAME small rising-bubble case stepped as `world` partitions (one per GPU,
+    halo exchange as in the timed run) and as ONE partition on rank 0's GPU; the gathered fields must agree bit for bit (the face sums
+    of an element have a fixed order and both sides of a cut face see identical traces).  Matches ASYNC_COMM,
+    field.h:2255-2324 (with the gradients exchanged too, SURVEY finding 5)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from nebulasem_b200 import host
+    n = (4 * pgrid[0], 4 * pgrid[1], 4 * pgrid[2])
+    uid = broadcast_unique_id(rank)
+    s = host.Solver.synthetic_part("bubble3d", n[0], n[1], n[2], ORDER, rank, world, decomp, pgrid)
+    s.attach(device, rank, world, uid)
+    s.step(nsteps)
+    s.download()
+    rho, U, T, _ = s.state()
+    nb = s.gBCSfield
+    cg = torch.tensor(s.u32("cellGlobal").astype(np.int64), device="cuda")
+    ncell = n[0] * n[1] * n[2]
+    out = torch.zeros((ncell, NP, 5), dtype=torch.float64, device="cuda")
+    out[cg] = torch.tensor(np.concatenate([rho[:nb, None], U[:nb], T[:nb, None]], axis=1).reshape(s.nBCS, NP, 5), device="cuda")
+    dist.all_reduce(out)                  # the partitions are disjoint: the sum assembles the global field
+    kinfo = s.kernel_info
+    s.close()
+    res = None
+    if rank == 0:
+        ref = host.Solver.synthetic("bubble3d", n[0], n[1], n[2], ORDER)
+        ref.attach(device)
+        ref.step(nsteps)
+        ref.download()
+        r1, U1, T1, _ = ref.state()
+        nb1 = ref.gBCSfield
+        ref.close()
+        one = np.concatenate([r1[:nb1, None], U1[:nb1], T1[:nb1, None]], axis=1).reshape(ncell, NP, 5)
+        got = out.cpu().numpy()
+        res = {"bitwise": bool(np.array_equal(got, one)), "max_abs_diff": float(np.abs(got - one).max()),
+               "case": f"bubble3d {n[0]}x{n[1]}x{n[2]} elements order {ORDER}, {nsteps} steps, {world} {decomp} partitions vs 1 partition",
+               "kernels": kinfo}
+    flag = torch.tensor([1 if (res is None or res["bitwise"]) else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    if int(flag.item()) == 0:
+        raise SystemExit(f"bench.py: {world} partitions differ from one partition: {res}")
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -230,6 +292,14 @@ def main():
         if rank != 0:
             return 0
         r = run_reference_sample(args.ref_n, steps, warmup)
+        # the reference cannot hold the 100^3 mesh (15.9 GB per MeshMatrix object): its arm runs a bounded sample of the
+        # same workload and says so where the driver compares configurations
+        config = dict(config)
+        config["workload"] = (f"rising thermal bubble 3-D synthetic hex mesh, order {ORDER}, SAMPLE of {args.ref_n}^3 = {args.ref_n ** 3} elements "
+                              f"({args.ref_n ** 3 * NP} LGL nodes) of the {args.n}^3-element workload, diffusion+buoyancy on, one forward-Euler "
+                              f"stage per step; per-DOF throughput on the host cores")
+        config["elements_per_gpu"] = args.ref_n ** 3
+        config["sample_of"] = f"{args.n}^3 elements per GPU"
         line = {"impl": "reference", "metric": "dGSEM Euler DOF-updates/s per stage", "unit": "DOF-updates/s", "n_gpus": args.gpus,
                 "steps": steps, "warmup": warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": config}
@@ -254,19 +324,12 @@ def main():
     import torch.distributed as dist
     pgrid = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(world, (world, 1, 1))
     uid_bytes = None
+    mp_parity = None
     if world > 1:
         # one process per GPU; torch.distributed is plumbing (rendezvous, barrier, max-over-ranks), the halo is NCCL
         dist.init_process_group("nccl", device_id=torch.device("cuda", device))
-        import ctypes
-        from nebulasem_b200 import capi
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            buf = ctypes.create_string_buffer(128)
-            if capi.load_library().nsem_get_unique_id(buf) != 0:
-                raise SystemExit("bench.py: ncclGetUniqueId failed")
-            uid = torch.tensor(list(buf.raw), dtype=torch.uint8, device="cuda")
-        dist.broadcast(uid, 0)
-        uid_bytes = bytes(uid.cpu().tolist())
+        mp_parity = mp_parity_check(rank, world, device, args.decomp, pgrid)
+        uid_bytes = broadcast_unique_id(rank)
         config["parallelism"] = (f"{world} partitions ({args.decomp}), one per GPU, global mesh {args.n * pgrid[0]}x{args.n * pgrid[1]}x"
                                  f"{args.n * pgrid[2]} elements on a {1000 * pgrid[0]}x{1000 * pgrid[1]}x{1000 * pgrid[2]} m domain (element size as at N=1), NCCL face-trace halo")
 
@@ -437,6 +500,8 @@ def main():
             "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config, "node_updates_per_s": value / 5.0, "roofline": roofline,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "setup_s": t_setup}
+    if mp_parity is not None:
+        line["mp_parity"] = mp_parity
     print(json.dumps(line), flush=True)
     s.close()
     if world > 1:

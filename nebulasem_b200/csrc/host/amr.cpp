@@ -657,6 +657,12 @@ std::unique_ptr<EulerSolver> EulerSolver::regridded(const std::vector<uint8_t>& 
         for (const BCond& b : *l)
         {
             if (!b.fixed.empty()) throw Error("EulerSolver::regridded: boundary conditions with frozen per-face values cannot follow a regrid");
+            // CALC_DIRICHLET freezes the values the patch holds when the condition is first applied; the set-up below runs on blank fields
+            // (the state arrives afterwards, on the device), so such a patch would freeze zeros -- the reference re-reads the refined
+            // fields and freezes those.  Refused rather than silently wrong (the shipped AMR cases use NEUMANN / SYMMETRY / CYCLIC)
+            if (b.type == "CALC_DIRICHLET")
+                throw Error("EulerSolver::regridded: a CALC_DIRICHLET patch (" + b.patch + ") cannot follow an in-memory regrid: its frozen values "
+                            "would be taken from the blank set-up fields");
         }
     // the reference refines the owner cells of paired CYCLIC faces together (field.cpp:826-858; amr_tag_cells does) and pairs the faces by
     // their position in the two patches (field.h:2662-2664; repair_cyclic_order below).  Flags that split a pair are refused before the
@@ -678,6 +684,8 @@ std::unique_ptr<EulerSolver> EulerSolver::regridded(const std::vector<uint8_t>& 
     n->start_step = start_step; n->end_step = end_step; n->write_interval = write_interval; n->decomp_type = decomp_type;
     n->refine_params = refine_params; n->amr_step = amr_step;
     n->mass0 = mass0; n->energy0 = energy0; n->volume0 = volume0;
+    n->vtk_fields = vtk_fields; n->vtk_cell_value = vtk_cell_value; n->vtk_polyhedral = vtk_polyhedral; n->vtk_on_dump = vtk_on_dump;
+    n->launch_nonce = launch_nonce;
     n->forest = forest;
     const bool verbose = std::getenv("NSEM_VERBOSE") != nullptr;
     auto t0 = std::chrono::steady_clock::now();
@@ -720,7 +728,9 @@ std::unique_ptr<EulerSolver> EulerSolver::regridded(const std::vector<uint8_t>& 
 void EulerSolver::write_amr_grid(long dump) const {
     if (!forest) throw Error("EulerSolver::write_amr_grid: no AMR forest");
     const std::string base = dir + "/" + meshName + "_" + std::to_string(dump);
-    write_grid_text(base + ".txt", forest->grid());
+    // the reference writes the refined grid in the dump format (Mesh::write_mesh under write_format, field.cpp:74,930)
+    if (binary_out) write_grid_binary(base + ".bin", forest->grid());
+    else write_grid_text(base + ".txt", forest->grid());
     forest->save(base + ".forest");
 }
 

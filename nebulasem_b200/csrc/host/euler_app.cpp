@@ -118,11 +118,15 @@ void EulerSolver::set_mesh(const Grid& g) {
     if (amr_step != 0 || std::getenv("NSEM_AMR")) {
         forest = std::make_shared<AmrForest>();
         struct stat st;
+        bool loaded = false;
         if (!forest_file.empty() && ::stat(forest_file.c_str(), &st) == 0) {
-            // restart of an AMR run: the forest that emitted this grid was saved next to it
+            // restart of an AMR run: the forest that emitted this grid was saved next to it.  A forest that does not match (the case's own
+            // conforming <mesh>_0.txt read again next to the <mesh>_0.bin + .forest an earlier run's initial regrid left) is not this grid's
             forest->load(forest_file);
-            if (forest->leaves.size() != g.nCells()) throw Error(forest_file + " does not belong to the grid next to it");
-        } else {
+            loaded = forest->leaves.size() == g.nCells();
+        }
+        if (!loaded) {
+            forest = std::make_shared<AmrForest>();
             try { forest->init(g, refine_params.dir); }
             catch (const Error&) { forest.reset(); }  // a grid that is already non-conforming cannot seed the forest: regridded() says so
         }
@@ -606,6 +610,7 @@ void EulerSolver::write_fields(int index) {
     if (nranks > 1) {
         out = dir + "/grid" + std::to_string(rank);
         ::mkdir(out.c_str(), 0777);
+        ::unlink((out + "/cells" + s).c_str());          // a marker of an earlier run must not vouch for files that are being rewritten
     }
     write_field(out + "/rho" + s, binary_out, 1, rho.data(), n, bc_rho);
     write_field(out + "/U" + s, binary_out, 3, U.data(), n, bc_U);
@@ -616,6 +621,7 @@ void EulerSolver::write_fields(int index) {
         FILE* f = std::fopen((out + "/cells" + s + ".tmp").c_str(), "wb");
         if (!f) throw Error("cannot write " + out + "/cells" + s);
         const u32 nc = (u32)cellGlobal.size();
+        std::fwrite(&launch_nonce, sizeof launch_nonce, 1, f);      // this launch's stamp (euler_main.cpp: share_launch_blob)
         std::fwrite(&nc, sizeof nc, 1, f);
         std::fwrite(cellGlobal.data(), sizeof(u32), nc, f);
         std::fclose(f);
@@ -650,9 +656,18 @@ void EulerSolver::merge_fields(int index) {
     std::vector<std::vector<u32>> maps(nranks);
     for (int r = 0; r < nranks; r++) {
         const std::string path = dir + "/grid" + std::to_string(r) + "/cells" + s;
+        // the marker is written last and carries this launch's nonce: a marker an earlier run left behind is not this dump
         FILE* f = nullptr;
-        for (int tries = 0; tries < 6000 && !(f = std::fopen(path.c_str(), "rb")); tries++) ::usleep(100000);   // <= 10 min
-        if (!f) throw Error("merge: rank " + std::to_string(r) + " never wrote " + path);
+        for (int tries = 0; tries < 6000; tries++) {                                                             // <= 10 min
+            if ((f = std::fopen(path.c_str(), "rb"))) {
+                uint64_t stamp = 0;
+                if (std::fread(&stamp, sizeof stamp, 1, f) == 1 && stamp == launch_nonce) break;
+                std::fclose(f);
+                f = nullptr;
+            }
+            ::usleep(100000);
+        }
+        if (!f) throw Error("merge: rank " + std::to_string(r) + " never wrote " + path + " in this launch");
         u32 nc = 0;
         if (std::fread(&nc, sizeof nc, 1, f) != 1) { std::fclose(f); throw Error("merge: short read of " + path); }
         maps[r].resize(nc);

@@ -22,6 +22,7 @@
 #include <cstring>
 #include <ctime>
 #include <string>
+#include <vector>
 
 #include "nsem_host.h"
 
@@ -32,31 +33,92 @@ static bool env_int(const char* name, int& out) {
     return true;
 }
 
-// rank 0 publishes the 128-byte ncclUniqueId, the others wait for a file younger than their own start
-static void share_unique_id(const std::string& dir, int rank, unsigned char id[128]) {
-    const std::string path = dir + "/.nsem_nccl_id", tmp = path + ".tmp";
+// Launch handshake through the case directory (the reference hands its partitions over through the file system too): rank 0 hands every
+// other rank the 128-byte ncclUniqueId and a 64-bit launch nonce (it stamps the per-dump markers rank 0's merge waits for).  Nothing here
+// trusts a file's age: every rank r > 0 draws a fresh random nonce and keeps a hello file `.nsem_hello.<r>` alive; rank 0 removes whatever a
+// crashed earlier launch left behind BEFORE it does anything else, publishes `.nsem_nccl_id` = blob + the nonces it has seen, and a rank
+// accepts that file only if it carries its own nonce -- a stale file cannot.  Rank 0 returns once every rank has acknowledged.
+static uint64_t random_u64() {
+    uint64_t v = 0;
+    FILE* f = std::fopen("/dev/urandom", "rb");
+    if (f) { if (std::fread(&v, sizeof v, 1, f) != 1) v = 0; std::fclose(f); }
+    if (v == 0) v = ((uint64_t)::getpid() << 32) ^ (uint64_t)std::time(nullptr) ^ 0x9e3779b97f4a7c15ull;
+    return v;
+}
+static bool read_exact(const std::string& path, void* buf, size_t n) {
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) return false;
+    const size_t got = std::fread(buf, 1, n, f);
+    unsigned char extra;
+    const bool more = std::fread(&extra, 1, 1, f) == 1;
+    std::fclose(f);
+    return got == n && !more;
+}
+static void write_atomic(const std::string& path, const void* buf, size_t n) {
+    const std::string tmp = path + ".tmp" + std::to_string(::getpid());
+    FILE* f = std::fopen(tmp.c_str(), "wb");
+    if (!f || std::fwrite(buf, 1, n, f) != n) { if (f) std::fclose(f); throw nsemh::Error("cannot write " + tmp); }
+    std::fclose(f);
+    if (std::rename(tmp.c_str(), path.c_str()) != 0) throw nsemh::Error("cannot publish " + path);
+}
+struct LaunchBlob { unsigned char id[128]; uint64_t nonce; };
+static void share_launch_blob(const std::string& dir, int rank, int world, bool with_id, LaunchBlob& blob) {
+    const std::string idf = dir + "/.nsem_nccl_id";
+    auto hello = [&](int r) { return dir + "/.nsem_hello." + std::to_string(r); };
+    auto ack = [&](int r) { return dir + "/.nsem_ack." + std::to_string(r); };
+    const size_t fsize = sizeof(LaunchBlob) + 8 * (size_t)(world - 1);
+    const int max_tries = 6000;                                   // <= 10 min
     if (rank == 0) {
-        if (nsem_get_unique_id(id)) throw nsemh::Error(nsem_last_error(nullptr));
-        FILE* f = std::fopen(tmp.c_str(), "wb");
-        if (!f || std::fwrite(id, 1, 128, f) != 128) throw nsemh::Error("cannot write " + tmp);
-        std::fclose(f);
-        if (std::rename(tmp.c_str(), path.c_str()) != 0) throw nsemh::Error("cannot publish " + path);
-        return;
+        ::unlink(idf.c_str());
+        for (int r = 1; r < world; r++) { ::unlink(hello(r).c_str()); ::unlink(ack(r).c_str()); }
+        std::memset(&blob, 0, sizeof blob);
+        if (with_id && nsem_get_unique_id(blob.id)) throw nsemh::Error(nsem_last_error(nullptr));
+        blob.nonce = random_u64();
+        std::vector<uint64_t> seen(world, 0), published(world, 0);
+        bool have_published = false;
+        for (int tries = 0; tries < max_tries; tries++) {
+            bool all = true;
+            for (int r = 1; r < world; r++) all &= read_exact(hello(r), &seen[r], 8) && seen[r] != 0;
+            if (all && (!have_published || seen != published)) {
+                std::vector<unsigned char> buf(fsize);
+                std::memcpy(buf.data(), &blob, sizeof blob);
+                std::memcpy(buf.data() + sizeof blob, seen.data() + 1, 8 * (size_t)(world - 1));
+                write_atomic(idf, buf.data(), fsize);
+                published = seen;
+                have_published = true;
+            }
+            if (have_published) {
+                bool acked = true;
+                for (int r = 1; r < world; r++) { uint64_t a = 0; acked &= read_exact(ack(r), &a, 8) && a == published[r]; }
+                if (acked) {
+                    ::unlink(idf.c_str());
+                    for (int r = 1; r < world; r++) { ::unlink(hello(r).c_str()); ::unlink(ack(r).c_str()); }
+                    return;
+                }
+            }
+            ::usleep(100000);
+        }
+        ::unlink(idf.c_str());
+        throw nsemh::Error("rank 0: the other ranks never answered the launch handshake in " + dir);
     }
-    const time_t t0 = std::time(nullptr);
-    for (int tries = 0; tries < 3000; tries++) {                  // <= 5 min
-        struct stat st;
-        if (::stat(path.c_str(), &st) == 0 && st.st_size == 128 && st.st_mtime >= t0 - 30) {
-            FILE* f = std::fopen(path.c_str(), "rb");
-            if (f) {
-                const size_t got = std::fread(id, 1, 128, f);
-                std::fclose(f);
-                if (got == 128) return;
+    const uint64_t mine = random_u64();
+    std::vector<unsigned char> buf(fsize);
+    for (int tries = 0; tries < max_tries; tries++) {
+        uint64_t cur = 0;
+        if (!(read_exact(hello(rank), &cur, 8) && cur == mine)) write_atomic(hello(rank), &mine, 8);      // rank 0's start-up sweep may remove it
+        if (read_exact(idf, buf.data(), fsize)) {
+            uint64_t slot = 0;
+            std::memcpy(&slot, buf.data() + sizeof blob + 8 * (size_t)(rank - 1), 8);
+            if (slot == mine) {
+                std::memcpy(&blob, buf.data(), sizeof blob);
+                write_atomic(ack(rank), &mine, 8);
+                return;
             }
         }
         ::usleep(100000);
     }
-    throw nsemh::Error("rank " + std::to_string(rank) + ": rank 0 never published " + path);
+    ::unlink(hello(rank).c_str());
+    throw nsemh::Error("rank " + std::to_string(rank) + ": rank 0 never answered the launch handshake in " + dir);
 }
 
 int main(int argc, char* argv[]) {
@@ -113,15 +175,17 @@ int main(int argc, char* argv[]) {
         s.read_fields(step);
         s.setup();
         const char* dry = std::getenv("NSEM_DRYRUN");
-        if (dry && std::atoi(dry) > 0) {
+        const bool dryrun = dry && std::atoi(dry) > 0;
+        LaunchBlob blob;
+        std::memset(&blob, 0, sizeof blob);
+        if (world > 1) share_launch_blob(dir, rank, world, !dryrun, blob);
+        s.launch_nonce = blob.nonce;
+        if (dryrun) {
             s.write_fields(std::atoi(dry));
             s.merge_fields(std::atoi(dry));
         } else {
-            unsigned char id[128];
-            if (world > 1) share_unique_id(dir, rank, id);
-            s.attach_device(world > 1 ? local : (local < 0 ? 0 : local), rank, world, world > 1 ? id : nullptr);
+            s.attach_device(world > 1 ? local : (local < 0 ? 0 : local), rank, world, world > 1 ? blob.id : nullptr);
             nsemh::run_case(sp);        // `s` is gone after a regrid: nothing below touches it
-            if (rank == 0 && world > 1) ::unlink((dir + "/.nsem_nccl_id").c_str());
         }
         if (rank == 0) std::printf("Exiting application run with %d processes\n", world);
         return 0;

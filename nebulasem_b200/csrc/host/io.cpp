@@ -231,6 +231,39 @@ void write_grid_text(const std::string& path, const Grid& g) {
     std::fclose(f);
 }
 
+// the same grammar through Util::ofstream_bin (util.h:191-226): u32 counts, f64 coordinates, every symbol and name a 1-byte length + bytes
+void write_grid_binary(const std::string& path, const Grid& g) {
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f) throw Error("cannot write " + path);
+    auto sym = [&](const std::string& w) { const unsigned char n = (unsigned char)w.size(); std::fwrite(&n, 1, 1, f); std::fwrite(w.data(), 1, n, f); };
+    auto u = [&](u32 v) { std::fwrite(&v, 4, 1, f); };
+    u((u32)g.V.size()); sym("{");
+    for (const auto& v : g.V) std::fwrite(v.data(), 8, 3, f);
+    sym("}");
+    u(g.nFacets()); sym("{");
+    for (u32 i = 0; i < g.nFacets(); i++) {
+        u(g.facetStart[i + 1] - g.facetStart[i]); sym("{");
+        std::fwrite(g.facetVerts.data() + g.facetStart[i], 4, g.facetStart[i + 1] - g.facetStart[i], f);
+        sym("}");
+    }
+    sym("}");
+    u(g.nCells()); sym("{");
+    for (u32 i = 0; i < g.nCells(); i++) {
+        u(g.cellStart[i + 1] - g.cellStart[i]); sym("{");
+        std::fwrite(g.cellFaces.data() + g.cellStart[i], 4, g.cellStart[i + 1] - g.cellStart[i], f);
+        sym("}");
+    }
+    sym("}");
+    u((u32)g.boundaries.size()); sym("{");
+    for (const auto& kv : g.boundaries) {
+        sym(kv.first); u((u32)kv.second.size()); sym("{");
+        std::fwrite(kv.second.data(), 4, kv.second.size(), f);
+        sym("}");
+    }
+    sym("}");
+    if (std::fclose(f) != 0) throw Error("short write of " + path);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Field files (readInternal_/readBoundary_ field.h:1412-1552; writeInternal_/writeBoundary_ :1588-1663)
 // ---------------------------------------------------------------------------------------------------------
@@ -330,6 +363,8 @@ void write_field(const std::string& path_noext, bool binary, int comps, const do
             if (!near_zero(b.shape)) { o.str("shape"); o.d(b.shape); }
             if (!near_zero(std::sqrt(mt))) { o.str("tvalue"); for (int d = 0; d < comps; d++) o.d(b.tvalue[d]); }
             if (!near_zero(b.tshape)) { o.str("tshape"); o.d(b.tshape); }
+            if (!(near_zero(b.dir[0]) && near_zero(b.dir[1]) && near_zero(b.dir[2] - 1))) { o.str("dir"); for (int d = 0; d < 3; d++) o.d(b.dir[d]); }
+            if (b.zMax > 0) { o.str("zMin"); o.d(b.zMin); o.str("zMax"); o.d(b.zMax); }
             if (!b.neighbor.empty()) { o.str("neighbor"); o.str(b.neighbor); }
             o.str("}");
         }
@@ -346,13 +381,20 @@ void write_field(const std::string& path_noext, bool binary, int comps, const do
         std::fprintf(f, "}\nboundary %u\n{\n", (u32)bcs.size());
         for (const auto& b : bcs) {
             std::fprintf(f, "%s\n{\n\ttype %s\n", b.patch.c_str(), b.type.c_str());
-            double mv = 0;
-            for (int d = 0; d < comps; d++) mv += b.value[d] * b.value[d];
-            if (!near_zero(std::sqrt(mv))) {
-                std::fprintf(f, "\tvalue ");
-                for (int d = 0; d < comps; d++) std::fprintf(f, "%.12g ", b.value[d]);
+            double mv = 0, mt = 0;
+            for (int d = 0; d < comps; d++) { mv += b.value[d] * b.value[d]; mt += b.tvalue[d] * b.tvalue[d]; }
+            auto put = [&](const char* key, const double* x, int n) {      // scalars print bare, vectors with a space after every component
+                std::fprintf(f, "\t%s ", key);
+                if (n == 1) std::fprintf(f, "%.12g", x[0]);
+                else for (int d = 0; d < n; d++) std::fprintf(f, "%.12g ", x[d]);
                 std::fprintf(f, "\n");
-            }
+            };
+            if (!near_zero(std::sqrt(mv))) put("value", b.value, comps);
+            if (!near_zero(b.shape)) put("shape", &b.shape, 1);
+            if (!near_zero(std::sqrt(mt))) put("tvalue", b.tvalue, comps);
+            if (!near_zero(b.tshape)) put("tshape", &b.tshape, 1);
+            if (!(near_zero(b.dir[0]) && near_zero(b.dir[1]) && near_zero(b.dir[2] - 1))) put("dir", b.dir.data(), 3);
+            if (b.zMax > 0) { put("zMin", &b.zMin, 1); put("zMax", &b.zMax, 1); }
             if (!b.neighbor.empty()) std::fprintf(f, "\tneighbor %s\n", b.neighbor.c_str());
             std::fprintf(f, "}\n");
         }

@@ -73,6 +73,7 @@ struct Grid {
 };
 Grid read_grid(const std::string& path_noext);
 void write_grid_text(const std::string& path, const Grid& g);
+void write_grid_binary(const std::string& path, const Grid& g);
 // structured box of n cells on [lo,hi]; sides x-,x+,y-,y+,z-,z+ -> patch names; optional terrain map
 Grid box_grid(const int n[3], const double lo[3], const double hi[3], const std::array<std::string, 6>& patches,
               void (*vertex_map)(Vec3&, const void*) = nullptr, const void* map_arg = nullptr);
@@ -227,6 +228,7 @@ struct EulerSolver {
     std::vector<double> rho, U, T, p, rho_ref, p_ref, gvec, gh;
     std::vector<BCond> bc_rho, bc_U, bc_T, bc_p, bc_rho_ref, bc_p_ref, bc_g;
     double mass0 = 0, energy0 = 0, volume0 = 0;
+    uint64_t launch_nonce = 0;                  // stamp of this launch on the per-dump markers (euler_main.cpp: share_launch_blob)
 
     nsem_ctx* ctx = nullptr;
     ~EulerSolver();

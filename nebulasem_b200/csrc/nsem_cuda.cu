@@ -146,7 +146,8 @@ struct nsem_ctx {
     std::vector<uint8_t> h_bFid;
 
     // node arrays
-    DevBuf<double> rho[2], U[2][3], T[2], p, GU[9], GT[3], Jinv[9], cV, rho_ref, p_ref, gfield[3], gh, diagPartial;
+    DevBuf<double> rho[2], U[2][3], T[2], S[2], p, GU[9], GT[3], Jinv[9], cV, rho_ref, p_ref, gfield[3], gh, diagPartial;
+    bool speed_valid = false;  // S[cur] = |U| + c of the current state (kept by sweep B + the ghost update; recomputed after the state was set from outside)
     bool has_gh = false;
     int cur = 0;
     bool has_gfield = false;
@@ -218,10 +219,14 @@ struct nsem_ctx {
 // ---------------------------------------------------------------------------------------------------------
 // dispatch over the compiled (NX,NY,NZ) instantiations
 // ---------------------------------------------------------------------------------------------------------
+#ifdef NSEM_ONLY_ORDER4_3D      // kernel-variant experiments (profiles/): compile the bench instantiation only
+#define NSEM_ORDERS(X) X(5, 5, 5)
+#else
 #define NSEM_ORDERS(X)                                                                            \
     X(2, 2, 2) X(3, 3, 3) X(4, 4, 4) X(5, 5, 5) X(6, 6, 6) X(7, 7, 7) X(8, 8, 8)                  \
     X(2, 1, 2) X(3, 1, 3) X(4, 1, 4) X(5, 1, 5) X(6, 1, 6) X(7, 1, 7) X(8, 1, 8)                  \
     X(2, 2, 1) X(3, 3, 1) X(4, 4, 1) X(5, 5, 1) X(6, 6, 1) X(7, 7, 1) X(8, 8, 1)
+#endif
 
 template <int NX, int NY, int NZ>
 struct Launch {
@@ -1032,6 +1037,8 @@ extern "C" int nsem_upload_mesh(nsem_ctx* c, const nsem_mesh* m) {
     for (int b = 0; b < 2; b++) {
         CUDA_TRY(c, c->rho[b].alloc(nN));
         CUDA_TRY(c, c->T[b].alloc(nN));
+        CUDA_TRY(c, c->S[b].alloc(nN));
+        CUDA_TRY(c, cudaMemsetAsync(c->S[b].p, 0, nN * 8, s));
         for (int d = 0; d < 3; d++) CUDA_TRY(c, c->U[b][d].alloc(nN));
         CUDA_TRY(c, cudaMemsetAsync(c->rho[b].p, 0, nN * 8, s));
         CUDA_TRY(c, cudaMemsetAsync(c->T[b].p, 0, nN * 8, s));
@@ -1227,6 +1234,7 @@ extern "C" int nsem_upload_state(nsem_ctx* c, const double* rho, const double* U
     if (to_device(c, T, 1, d1)) return 1;
     if (p) { d1[0] = c->p.p; if (to_device(c, p, 1, d1)) return 1; }
     c->have_state = true;
+    c->speed_valid = false;
     return 0;
 }
 
@@ -1326,6 +1334,7 @@ extern "C" int nsem_upload_state_async(nsem_ctx* c, const double* rho, const dou
     CUDA_TRY(c, cudaEventRecord(c->evScatter, c->stream));
     c->scatterPending = true;
     c->have_state = true;
+    c->speed_valid = false;
     return 0;
 }
 
@@ -1397,6 +1406,7 @@ static void fill_kparams(const nsem_ctx* c, KParams& P) {
     P.visc = (q.diffusion && q.viscosity != 0.0) ? 1 : 0;
     P.has_gfield = c->has_gfield ? 1 : 0;
     { const char* pr = std::getenv("NSEM_PROBE"); P.probe = pr ? std::atoi(pr) : 0; }
+    { const char* rn = std::getenv("NSEM_RUN"); P.run = rn ? (uint32_t)std::max(1, std::atoi(rn)) : 1u; }
     std::memcpy(P.D, c->D, sizeof P.D);
     std::memcpy(P.W, c->W, sizeof P.W);
     std::memcpy(P.X, c->X, sizeof P.X);
@@ -1404,6 +1414,7 @@ static void fill_kparams(const nsem_ctx* c, KParams& P) {
     P.elemRec = c->elemRec.p;
     P.rho_old = c->rho[k].p; P.rho_new = c->rho[o].p;
     P.T_old = c->T[k].p; P.T_new = c->T[o].p;
+    P.S_old = c->S[k].p; P.S_new = c->S[o].p;
     for (int d = 0; d < 3; d++) { P.U_old[d] = c->U[k][d].p; P.U_new[d] = c->U[o][d].p; P.gfield[d] = c->gfield[d].p; }
     P.p = c->p.p;
     for (int d = 0; d < 9; d++) { P.GU[d] = c->GU[d].p; P.Jinv[d] = c->Jinv[d].p; }
@@ -1418,12 +1429,12 @@ static void fill_kparams(const nsem_ctx* c, KParams& P) {
     {
         int q = 0;
         P.srcA[q++] = P.rho_old; for (int d = 0; d < 3; d++) P.srcA[q++] = P.U_old[d];
-        P.srcA[q++] = P.T_old; P.srcA[q++] = P.p_ref;
+        P.srcA[q++] = P.T_old; P.srcA[q++] = P.p_ref; P.srcA[q++] = P.S_old;
         for (int d = 0; d < 9; d++) P.srcA[q++] = P.Jinv[d];
         P.srcA[q++] = P.cV;
         q = 0;
         P.srcB[q++] = P.rho_old; P.srcB[q++] = P.rho_new; for (int d = 0; d < 3; d++) P.srcB[q++] = P.U_old[d];
-        P.srcB[q++] = P.T_old; P.srcB[q++] = P.p;
+        P.srcB[q++] = P.T_old; P.srcB[q++] = P.p; P.srcB[q++] = P.S_old; P.srcB[q++] = P.rho_ref;
         if (P.visc) { for (int d = 0; d < 9; d++) P.srcB[q++] = P.GU[d]; for (int d = 0; d < 3; d++) P.srcB[q++] = P.GT[d]; }
         for (int d = 0; d < 9; d++) P.srcB[q++] = P.Jinv[d];
         P.srcB[q++] = P.cV;
@@ -1440,6 +1451,7 @@ static void fill_bcparams(const nsem_ctx* c, const KParams& P, BCParams& B, int 
     for (int d = 0; d < 9; d++) B.GU[d] = P.GU[d];
     for (int d = 0; d < 3; d++) { B.GT[d] = P.GT[d]; B.U_new[d] = P.U_new[d]; }
     B.T_new = P.T_new;
+    B.S_new = P.S_new;
 }
 
 static int halo_exchange(nsem_ctx* c, double* const* arrays, int nf, cudaStream_t s);
@@ -1464,6 +1476,19 @@ static cudaError_t launch_mortar(const nsem_ctx* c, const KParams& P, int phase)
     return cudaGetLastError();
 }
 
+// S[cur] after the state was set from outside a step (upload, regrid transfer, restart, halo exchange of the initial state)
+static int ensure_speed(nsem_ctx* c) {
+    if (c->speed_valid) return 0;
+    const int k = c->cur;
+    const uint64_t n = c->nNodes;
+    speed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->prm.T0, (c->prm.cp / c->prm.cv) * (c->prm.cp - c->prm.cv), c->U[k][0].p,
+                                                                    c->U[k][1].p, c->U[k][2].p, c->T[k].p, c->S[k].p);
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    c->speed_valid = true;
+    return 0;
+}
+
 // One step with the halo exchanges on the comm stream overlapped with the interior elements (the reference's mul()
 // also does interior cells while the halo is in flight, field.h:2381-2415).  Elements that touch an
 // inter-partition face go first in each sweep, their traces are packed and exchanged while the interior runs:
@@ -1473,6 +1498,7 @@ static int one_step_overlapped(nsem_ctx* c) {
     KParams P;
     BCParams B;
     fill_kparams(c, P);
+    if (ensure_speed(c)) return 1;
     KParams PI = P, PH = P;
     PI.sched = c->schedInt.p; PI.nB = c->nInt;
     PH.sched = c->schedHalo.p; PH.nB = c->nHalo;
@@ -1497,8 +1523,8 @@ static int one_step_overlapped(nsem_ctx* c) {
     CUDA_TRY(c, cudaEventRecord(c->evB, s));
     CUDA_TRY(c, cudaStreamWaitEvent(cs, c->evB, 0));
     {
-        double* arr[4] = {P.U_new[0], P.U_new[1], P.U_new[2], P.T_new};
-        if (halo_exchange(c, arr, 4, cs)) return 1;
+        double* arr[5] = {P.U_new[0], P.U_new[1], P.U_new[2], P.T_new, P.S_new};
+        if (halo_exchange(c, arr, 5, cs)) return 1;
     }
     CUDA_TRY(c, cudaEventRecord(c->evCB, cs));
     c->cbPending = true;
@@ -1526,6 +1552,7 @@ static int one_step(nsem_ctx* c, bool timed, double* acc) {
     KParams P;
     BCParams B;
     fill_kparams(c, P);
+    if (ensure_speed(c)) return 1;
     if (timed) cudaEventRecord(c->ev[0], c->stream);
     CUDA_TRY(c, launch_mortar(c, P, 0));
     CUDA_TRY(c, launch_sweepA(c, P));
@@ -1546,8 +1573,8 @@ static int one_step(nsem_ctx* c, bool timed, double* acc) {
     B.phase = 1;
     CUDA_TRY(c, launch_bc(c, B));
     if (!c->peers.empty()) {
-        double* arr[4] = {P.U_new[0], P.U_new[1], P.U_new[2], P.T_new};
-        if (halo_exchange(c, arr, 4, c->stream)) return 1;
+        double* arr[5] = {P.U_new[0], P.U_new[1], P.U_new[2], P.T_new, P.S_new};
+        if (halo_exchange(c, arr, 5, c->stream)) return 1;
     }
     if (timed) cudaEventRecord(c->ev[4], c->stream);
     c->launches += 2 + (c->nG ? 2 : 0) + ((c->nG && (c->use_v4 || (c->use_v2 && !c->use_v3))) ? 1 : 0) + (c->nMortarGroups ? 2 : 0);
@@ -1710,6 +1737,7 @@ extern "C" int nsem_exchange_state_halos(nsem_ctx* c) {
     const int k = c->cur;
     double* arr[8] = {c->rho[k].p, c->U[k][0].p, c->U[k][1].p, c->U[k][2].p, c->T[k].p, c->p.p, c->rho_ref.p, c->p_ref.p};
     if (halo_exchange(c, arr, 8, c->stream)) return 1;
+    c->speed_valid = false;
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -1924,6 +1952,7 @@ extern "C" int nsem_refine_state(nsem_ctx* o, const nsem_regrid* r, nsem_ctx* c)
     CUDA_TRY(c, cudaGetLastError());
     CUDA_TRY(c, cudaStreamSynchronize(s));       // the task tables are freed on return
     c->have_state = true;
+    c->speed_valid = false;
     return 0;
 }
 
@@ -1951,6 +1980,7 @@ extern "C" int nsem_restart_state(nsem_ctx* c) {
     B.phase = 1;
     CUDA_TRY(c, launch_bc(c, B));
     if (c->nG) c->launches += 2;
+    c->speed_valid = false;
     if (!c->peers.empty()) return nsem_exchange_state_halos(c);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return 0;

@@ -57,6 +57,7 @@ struct KParams {
     double mrdt, mdt;            // -1/dt, -dt
     int buoyancy, visc, has_gfield;
     int sms;                     // SM count (v4: rotates the heavy warp roles between the CTAs that share an SM)
+    uint32_t run;                // v4 sweep A: consecutive schedule positions one CTA handles in a row (RunIter); 0/1 = grid-stride order
     int probe;                   // diagnostics only (NSEM_PROBE): 1 = stream the inputs and skip the arithmetic, 2 = also skip the gathers
     // basis
     double D[3][MAXN * MAXN];    // D[d][s*n+i] = l_i'(x_s)
@@ -74,6 +75,10 @@ struct KParams {
     // sweep B out
     double* U_new[3];
     double* T_new;
+    // |U| + c = |U| + sqrt(gamma R theta) of every node (lambdaMax, euler.cpp:186), kept next to the state it belongs to: sweep B (and the
+    // ghost update after it) writes S_new with U_new/T_new, the v4 sweeps of the next step read S_old -- no square roots in sweep A
+    const double* S_old;
+    double* S_new;
     // geometry
     const double* Jinv[9];       // row-major [a*3+d] = d xi_d / d x_a
     const double* cV;
@@ -95,7 +100,7 @@ struct KParams {
     const double* mortarA;
     const double* mortarB;
     // v4 kernels: the arrays each sweep stages, in stage-slot order (so the issuing lanes index them instead of branching)
-    const double* srcA[16];
+    const double* srcA[20];
     const double* srcB[32];
 };
 static_assert(sizeof(KParams) <= 4000, "KParams must fit the kernel parameter space");
@@ -170,6 +175,20 @@ __device__ __forceinline__ double eos_pressure(double P0, double R, double gamma
 #else
     return __dmul_rn(P0, exp(__dmul_rn(gamma, log(x))));
 #endif
+}
+
+// |U| + c of one side (lambdaMax, euler.cpp:186)
+__device__ __forceinline__ double side_speed(const double u[3], double th, double gammaR) {
+    return sqrt(u[0] * u[0] + (u[1] * u[1] + u[2] * u[2])) + sqrt(gammaR * th);
+}
+// S = |U| + c of every device node (real and ghost) of the CURRENT state: run once after the state was set from outside a step (upload,
+// regrid transfer, restart); inside the time loop sweep B and the ghost update keep it current.
+__global__ void __launch_bounds__(256) speed_kernel(uint64_t n, double T0, double gammaR, const double* __restrict__ u0, const double* __restrict__ u1,
+                                                    const double* __restrict__ u2, const double* __restrict__ T, double* __restrict__ S) {
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const double u[3] = {u0[q], u1[q], u2[q]};
+    S[q] = side_speed(u, T[q] + T0, gammaR);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -526,6 +545,7 @@ struct BCParams {
     double* GT[3];
     double* U_new[3];
     double* T_new;
+    double* S_new;                   // |U| + c of the ghost nodes, written with U_new/T_new in phase 1 (may be null)
 };
 
 __device__ __forceinline__ double bc_scalar(int kind, double owner, const BCRec& rc, double peer, double fixedv) {
@@ -667,6 +687,11 @@ __global__ void __launch_bounds__(256) bc_kernel(const __grid_constant__ BCParam
                 B.T_new[gi] = v;
             }
         }
+        // |U| + c of the ghost node, from the values just stored (the v4 sweep A of the next step reads it instead of taking square roots)
+        if (B.S_new && B.kind[2][g] != 5 && B.kind[3][g] != 5) {
+            const double gu[3] = {B.U_new[0][gi], B.U_new[1][gi], B.U_new[2][gi]};
+            B.S_new[gi] = side_speed(gu, B.T_new[gi] + B.T0, B.gamma * B.R);
+        }
     }
 }
 
@@ -682,10 +707,6 @@ __host__ __device__ constexpr int trace_bs(int npf) { return pad_to(7 * npf, 16)
 struct SideState {
     double rho_o, rho_n, u[3], th, pp, gU[9], gT[3];
 };
-// |U| + c of one side (lambdaMax, euler.cpp:186)
-__device__ __forceinline__ double side_speed(const double u[3], double th, double gammaR) {
-    return sqrt(u[0] * u[0] + (u[1] * u[1] + u[2] * u[2])) + sqrt(gammaR * th);
-}
 // The five N-dependent trace components are linear in N: out[c] = sum_b K[c][b] N_b.  The coefficients depend on the node
 // only, so a node that lies on several faces evaluates them once.  Every producer of a trace (sweep A, the "my side" of
 // sweep B, the ghost-cell kernel) goes through these two functions, with the operation order pinned by explicit

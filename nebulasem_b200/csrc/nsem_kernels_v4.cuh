@@ -119,12 +119,13 @@ struct CfgA {
     static constexpr bool ok = true;
     static constexpr int TBS = trace_bs(NPF);
     static constexpr int NFTP = pad_to(NFT, 2);
-    static constexpr int NIN = TRI ? 6 : 16;                            // rho, U(3), T, p_ref, [Jinv(9), cV]
-    static constexpr int A_PREF = 5, A_J = 6, A_CV = 15;
+    static constexpr int NIN = TRI ? 7 : 17;                            // rho, U(3), T, p_ref, S, [Jinv(9), cV]
+    static constexpr int A_PREF = 5, A_S = 6, A_J = 7, A_CV = 16;
+    static constexpr int NGV = 6;                                       // gathered per face node: rho, U(3), T, S
     static constexpr int oIn = 0;
     static constexpr int oRec = oIn + 2 * NIN * NPS;
-    static constexpr int oG = oRec + 3 * RECD;                          // [2][5][NFTP] neighbour values of the face nodes
-    static constexpr int oR = oG + 2 * 5 * NFTP;                        // [4][NP]: contravariant mass flux (3), theta
+    static constexpr int oG = oRec + 3 * RECD;                          // [2][NGV][NFTP] neighbour values of the face nodes
+    static constexpr int oR = oG + 2 * NGV * NFTP;                      // [4][NP]: contravariant mass flux (3), theta
     static constexpr int oTr = oR + pad_to(4 * NP, 2);                  // [6][TBS]
     static constexpr int oD = oTr + 6 * TBS;
     static constexpr int oBar = oD + 3 * MAXN * MAXN;
@@ -145,6 +146,29 @@ __device__ __forceinline__ int fresh_tid() {
     return t;
 }
 
+// Order in which one persistent CTA walks the elements: RUNS of `run` consecutive schedule positions, the runs dealt round-robin to the
+// CTAs (run c of CTA b starts at position (c * gridDim + b) * run).  With run = 1 this is the plain grid-stride loop.  On a structured
+// mesh consecutive elements are k-neighbours, so with run > 1 the element across a k-face is the one this CTA handled a moment ago (or
+// handles next): its values are in L2 (or in this CTA's own shared-memory ring) instead of being fetched a second time from DRAM while
+// another CTA streams them.
+struct RunIter {
+    uint32_t base, r;          // start of the current run, offset inside it
+    bool valid;
+    __device__ __forceinline__ uint32_t pos() const { return base + r; }
+    __device__ __forceinline__ static RunIter first(uint32_t nB, uint32_t run) {
+        RunIter it;
+        it.base = blockIdx.x * run; it.r = 0; it.valid = it.base < nB;
+        return it;
+    }
+    __device__ __forceinline__ RunIter next(uint32_t nB, uint32_t run) const {
+        RunIter n = *this;
+        if (!valid) return n;
+        if (r + 1 < run && base + r + 1 < nB) { n.r = r + 1; return n; }
+        n.base = base + gridDim.x * run; n.r = 0; n.valid = n.base < nB;
+        return n;
+    }
+};
+
 // MORTAR: the mesh has non-conforming faces (FM_MORTAR): such a face takes its finished surface terms from the mortar buffers
 // (nsem_mortar.cuh) instead of a two-point flux.  A separate instantiation, so conforming meshes run exactly the code they ran before.
 template <int NX, int NY, int NZ, bool VISC, bool TRI, int MINB, bool MORTAR = false>
@@ -152,21 +176,21 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
     using C = CfgA<NX, NY, NZ, VISC, TRI>;
     using Tk = Tasks<NX, NY, NZ>;
     constexpr int NP = C::NP, NPS = C::NPS, NFT = C::NFT, NT = C::NT, NIN = C::NIN, TBS = C::TBS, NPF = C::NPF, NISS = C::NISS;
-    constexpr int NFTP = C::NFTP, TCS = trace_cs(NPF);
+    constexpr int NFTP = C::NFTP, TCS = trace_cs(NPF), NGV = C::NGV;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* const sm = reinterpret_cast<double*>(smem_raw);
     double* const sIn = sm + C::oIn;         // [2][NIN][NPS]
     double* const sRec = sm + C::oRec;       // [3][RECD]
-    double* const sG = sm + C::oG;           // [2][5][NFTP]
+    double* const sG = sm + C::oG;           // [2][NGV][NFTP]
     double* const sR = sm + C::oR;           // [4][NP]
     double* const sTr = sm + C::oTr;         // [6][TBS]
     double* const sD = sm + C::oD;           // [3][MAXN*MAXN]
     uint64_t* const bars = reinterpret_cast<uint64_t*>(sm + C::oBar);   // full[2], rec[3]
 
     const int tid = threadIdx.x;
-    const uint32_t stride = gridDim.x;
-    uint32_t seq = blockIdx.x;
-    if (seq >= P.nB) return;
+    const uint32_t run = P.run ? P.run : 1u;
+    RunIter cur = RunIter::first(P.nB, run);
+    if (!cur.valid) return;
     const int iss = ((tid & 31) == 31 && (tid >> 5) < NISS) ? (tid >> 5) : -1;
 
     auto elem_of = [&](uint32_t q) -> uint32_t { return P.sched ? P.sched[q] : q; };
@@ -197,12 +221,13 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
                 if (MORTAR && (fr->meta & FM_MORTAR)) continue;          // `other` is a mortar block id there, nothing to gather
                 const int fslot = (fs < 2) ? fa * NY + fb : fa * NZ + fb;
                 const size_t oidx = (size_t)other + (fid == FM_GHOST ? fslot : face_node<NX, NY, NZ>(fid, fa, fb));
-                double* g = sG + buf * 5 * NFTP + task;
+                double* g = sG + buf * NGV * NFTP + task;
                 cp_async8(g + 0 * NFTP, P.rho_old + oidx);
                 cp_async8(g + 1 * NFTP, P.U_old[0] + oidx);
                 cp_async8(g + 2 * NFTP, P.U_old[1] + oidx);
                 cp_async8(g + 3 * NFTP, P.U_old[2] + oidx);
                 cp_async8(g + 4 * NFTP, P.T_old + oidx);
+                cp_async8(g + 5 * NFTP, P.S_old + oidx);
             }
         }
         cp_async_commit();
@@ -215,11 +240,12 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
         mbar_fence_init();
     }
     __syncthreads();
+    RunIter nx1 = cur.next(P.nB, run);
     if (iss == 0) {
-        issue_rec(0, elem_of(seq));
-        if (seq + stride < P.nB) issue_rec(1, elem_of(seq + stride));
+        issue_rec(0, elem_of(cur.pos()));
+        if (nx1.valid) issue_rec(1, elem_of(nx1.pos()));
     }
-    if (iss >= 0) issue_arrays(0, elem_of(seq));
+    if (iss >= 0) issue_arrays(0, elem_of(cur.pos()));
     for (int q = tid; q < 3 * MAXN * MAXN; q += NT) sD[q] = P.D[q / (MAXN * MAXN)][q % (MAXN * MAXN)];
     mbar_wait(&bars[2], 0);
     issue_gathers(0, 0);
@@ -227,13 +253,13 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
     int st = 0, rs = 0;                    // stage (= gather table) / record slot of the current element
     uint32_t it = 0;
     for (;;) {
-        const uint32_t elem = elem_of(seq);
-        const uint32_t nxt = seq + stride, nxt2 = nxt + stride;
-        const bool hasNext = nxt < P.nB;
+        const uint32_t elem = elem_of(cur.pos());
+        const RunIter nx2 = nx1.next(P.nB, run);
+        const bool hasNext = nx1.valid;
         const int rs1 = (rs == 2) ? 0 : rs + 1, rs2 = (rs1 == 2) ? 0 : rs1 + 1;
         if (iss >= 0) {
-            if (hasNext) issue_arrays(st ^ 1, elem_of(nxt));
-            if (iss == 0 && nxt2 < P.nB) issue_rec(rs2, elem_of(nxt2));
+            if (hasNext) issue_arrays(st ^ 1, elem_of(nx1.pos()));
+            if (iss == 0 && hasNext && nx2.valid) issue_rec(rs2, elem_of(nx2.pos()));
             if (iss == NISS - 1) bulk_wait_read0();       // the previous element's trace blocks have left sTr
         }
         if (it > 0) mbar_wait(&bars[2 + rs], (it / 3) & 1u);           // this element's record
@@ -247,7 +273,7 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
         }
         mbar_wait(&bars[st], (it >> 1) & 1u);
         const double* const in = sIn + (size_t)st * NIN * NPS;
-        const double* const gx = sG + st * 5 * NFTP;
+        const double* const gx = sG + st * NGV * NFTP;
         const double* const rec = sRec + rs * RECD;
 
         // ---- node: contravariant mass flux, theta ----
@@ -277,7 +303,7 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
         if (nodeT) {
             double r_rho, gU[9], gT[3];
             {
-                double acc = 0;
+                double acc = 0;         // (one chain: three chains, one per direction, measured 2 % slower, profiles/r2_variants.md)
 #pragma unroll
                 for (int ii = 0; ii < NX; ii++) acc += sR[0 * NP + ii * NY * NZ + j * NZ + k] * NSEM_DM(0, ii * NX + i);
 #pragma unroll
@@ -311,19 +337,7 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
             const double wi = P.W[0][i], wj = P.W[1][j], wk = P.W[2][k];
             double S = 0;
             if (onAny) {
-                const double uu[3] = {u0, u1, u2};
-                S = side_speed(uu, th, P.gamma * P.R);                  // |U| + c of this node: lambdaMax here, trace below
-                // |U| + c of the other side of the (up to) three faces, evaluated together so that the square roots overlap
-                double Sx[3];
-#pragma unroll
-                for (int ax = 0; ax < 3; ax++) {
-                    const bool on = (ax == 0) ? onK : (ax == 1 ? onJ : onI);
-                    const int cx = (ax == 0) ? k : (ax == 1 ? j : i);
-                    const int s = 2 * ax + (cx != 0 ? 1 : 0);
-                    const int ti = on ? ((ax == 0) ? Tk::index(s, i, j) : (ax == 1 ? Tk::index(s, i, k) : Tk::index(s, j, k))) : 0;
-                    const double xu[3] = {gx[1 * NFTP + ti], gx[2 * NFTP + ti], gx[3 * NFTP + ti]};
-                    Sx[ax] = side_speed(xu, gx[4 * NFTP + ti] + P.T0, P.gamma * P.R);
-                }
+                S = in[C::A_S * NPS + nt];                              // |U| + c of this node (written with the state): lambdaMax here, trace below
 #pragma unroll
                 for (int ax = 0; ax < 3; ax++) {
                     const bool on = (ax == 0) ? onK : (ax == 1 ? onJ : onI);
@@ -356,7 +370,7 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
                     const double sg = own ? 1.0 : -1.0;                                // (q_n - q_o) = sg * (q_other - q_mine)
                     const double N0 = fr->vec[0] * fw, N1 = fr->vec[1] * fw, N2 = fr->vec[2] * fw;      // fN[k] = gFN * w_a w_b / 4
                     const double nN = fr->unit[0] * N0 + fr->unit[1] * N1 + fr->unit[2] * N2;           // unit(fN).fN
-                    const double lam = (S * wo + Sx[ax] * wx) / 2;                                      // cds(|U| + c) / 2
+                    const double lam = (S * wo + gx[5 * NFTP + ti] * wx) / 2;                             // cds(|U| + c) / 2
                     const double fm = rho * (u0 * N0 + u1 * N1 + u2 * N2), fx = xr * (xu0 * N0 + xu1 * N1 + xu2 * N2);
                     const double flux = (fm * wo + fx * wx) - lam * (sg * (xr - rho)) * nN;
                     r_rho += sg * flux;
@@ -429,7 +443,8 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
             bulk_commit();
         }
         if (!hasNext) break;
-        seq = nxt;
+        cur = nx1;
+        nx1 = nx2;
         st ^= 1;
         rs = rs1;
         it++;
@@ -451,9 +466,9 @@ struct CfgB {
     static constexpr int NT = pad_to(NP, 32);
     static constexpr int NISS = (NT / 32) < 4 ? (NT / 32) : 4;         // issuing threads: lane 31 of the first warps
     static constexpr int TBS = trace_bs(NPF);
-    // staged arrays: rho_old, rho_new, U(3), T, p, [GU(9), GT(3)], [Jinv(9), cV]   (rho_ref comes straight from global memory)
-    static constexpr int B_RO = 0, B_RN = 1, B_U = 2, B_T = 5, B_P = 6, B_GU = 7, B_GT = 16;
-    static constexpr int B_J = VISC ? 19 : 7, B_CV = B_J + 9;
+    // staged arrays: rho_old, rho_new, U(3), T, p, S, rho_ref, [GU(9), GT(3)], [Jinv(9), cV]
+    static constexpr int B_RO = 0, B_RN = 1, B_U = 2, B_T = 5, B_P = 6, B_S = 7, B_RR = 8, B_GU = 9, B_GT = 18;
+    static constexpr int B_J = VISC ? 21 : 9, B_CV = B_J + 9;
     static constexpr int NIN = B_J + (TRI ? 0 : 10);
     static constexpr int oIn = 0;
     static constexpr int oT = oIn + 2 * NIN * NPS;                      // [6][TBS] neighbour traces (single buffer)
@@ -572,7 +587,7 @@ __global__ void __launch_bounds__((CfgB<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
             const bool onK = (k == 0 || k == NZ - 1), onJ = (j == 0 || j == NY - 1), onI = (i == 0 || i == NX - 1);
             if (onK || onJ || onI) {
                 TraceCoef K;
-                trace_coef(me, side_speed(me.u, me.th, P.gamma * P.R), P.nu, P.iPr, VISC, K);
+                trace_coef(me, in[C::B_S * NPS + nt], P.nu, P.iPr, VISC, K);
                 const double wi = P.W[0][i], wj = P.W[1][j], wk = P.W[2][k];
 #pragma unroll
                 for (int ax = 0; ax < 3; ax++) {
@@ -658,7 +673,7 @@ __global__ void __launch_bounds__((CfgB<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
             issue_traces(rs1);
         }
         if (nodeT) {
-            const double rref = P.buoyancy ? P.rho_ref[idx] : 0.0;
+            const double rref = P.buoyancy ? in[C::B_RR * NPS + nt] : 0.0;
             double r[4];
 #pragma unroll
             for (int a = 0; a < 4; a++) {
@@ -677,14 +692,19 @@ __global__ void __launch_bounds__((CfgB<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
             if (P.has_gfield) { g[0] = P.gfield[0][idx]; g[1] = P.gfield[1][idx]; g[2] = P.gfield[2][idx]; }
             const double drho = P.buoyancy ? (rho_nw - rref) : 0.0;
             const double rap = 1.0 / ap;                 // x = Su / ap (solve.cpp:563-570) as one reciprocal and 4 products
+            double un[3];
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 const double Su = (r[c] - (drho * g[c]) * cV) + (u[c] * rho_o) * ap0;
-                P.U_new[c][idx] = Su * rap;
+                un[c] = Su * rap;
+                P.U_new[c][idx] = un[c];
             }
             {
                 const double Su = r[3] + (th * rho_o) * ap0;
-                P.T_new[idx] = Su * rap - P.T0;
+                const double Tn = Su * rap - P.T0;
+                P.T_new[idx] = Tn;
+                // |U| + c of the new state, from the values as stored (every other producer of S reads them back from memory)
+                P.S_new[idx] = side_speed(un, Tn + P.T0, P.gamma * P.R);
             }
         }
         fence_async_smem();                    // the in-place fluxes (generic writes) precede the next bulk copies into this stage

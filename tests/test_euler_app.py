@@ -108,12 +108,12 @@ def test_euler_binary_runs_the_amr_cycle(tmp_path):
     from nebulasem_b200 import host
     masses = []
     for dump, grid in ((1, 0), (2, 1), (3, 2)):          # dump k was computed on the grid written at regrid k-1
-        assert os.path.exists(os.path.join(a, f"grid_{grid}.txt"))
+        assert os.path.exists(os.path.join(a, f"grid_{grid}.bin"))        # write_format BINARY (the default): the regridded grids are .bin
         rho = refio.read_field_values(os.path.join(a, f"rho{dump}"))[:, 0]
         T = refio.read_field_values(os.path.join(a, f"T{dump}"))[:, 0]
         case = str(tmp_path / f"check{dump}")
         os.makedirs(case)
-        shutil.copy(os.path.join(a, f"grid_{grid}.txt"), os.path.join(case, "grid_0.txt"))
+        shutil.copy(os.path.join(a, f"grid_{grid}.bin"), os.path.join(case, "grid_0.bin"))
         for f in ("rho", "U", "T", "p"):
             shutil.copy(os.path.join(a, f"{f}{dump}.bin"), os.path.join(case, f"{f}0.bin"))
         open(os.path.join(case, "controls"), "w").write(ctl.replace("amr_step 1", ""))
