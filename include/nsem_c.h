@@ -130,6 +130,23 @@ int nsem_download_state(nsem_ctx* ctx, double* rho, double* U, double* T, double
  * 2731-2769) of the last nsem_euler_step, per unit volume, ghost nodes included: grad_U as Tensor (9 per node, XX,YY,ZZ,XY,YZ,XZ,YX,ZY,ZX
  * with G[ab] = d_a U_b), grad_T as Vector.  Only with diffusion on (euler.cpp:189-190); NULL arrays are skipped. */
 int nsem_download_gradients(nsem_ctx* ctx, double* grad_U, double* grad_T);
+
+/* ---- operator-level entry points (unit parity).  Each evaluates ONE of the reference's operators on the state the context
+ * holds and leaves that state untouched.  Element-face layout of the FACET outputs: value[(elem * 6 + local_face) * NPF + slot], the
+ * face seen from each of its elements, in the face owner's frame (both elements of an interior face report the same number).
+ *   nsem_op_cds          cds(cell)                 src/field/field.h:2881-2893
+ *   nsem_op_rusanov      rusanov(rho U, rho, lambdaMax) . fN of the mass equation   field.h:2928-2943 (+ div_flux :3093-3114), euler.cpp:186,200-203
+ *   nsem_op_gradf_strong gradf<strong>(U), gradf<strong>(theta) + fillBCs   field.h:3328-3362, 2731-2769 (Tensor / Vector AoS as nsem_download_gradients)
+ *   nsem_op_divf_weak    divf<weak> residuals of the rho-, U- and theta-equations before src/addTemporal/Solve   field.h:3417-3478, euler.cpp:195-258
+ *   nsem_op_apply_bcs    applyExplicitBCs of one field (NSEM_F_RHO, NSEM_F_U, NSEM_F_T)   field.h:2586-2727
+ *   nsem_op_halo         ASYNC_COMM of the current state   field.h:2255-2324
+ * (the update itself, SolveTexplicit solve.cpp:563-570, is nsem_euler_step: it has no form apart from the residual it divides) */
+int nsem_op_cds(nsem_ctx* ctx, const double* cell_field, double* facet_out);
+int nsem_op_rusanov(nsem_ctx* ctx, double* facet_flux);
+int nsem_op_gradf_strong(nsem_ctx* ctx, double* grad_U, double* grad_T);
+int nsem_op_divf_weak(nsem_ctx* ctx, double* r_rho, double* r_U, double* r_T);
+int nsem_op_apply_bcs(nsem_ctx* ctx, int field, double* values);
+int nsem_op_halo(nsem_ctx* ctx);
 /* Pipelined variants for drivers that stream batches through the device: both only ENQUEUE and return.  The upload copies on a
  * copy-in stream into its own staging buffer and converts the layout on the compute stream, ordered after everything enqueued
  * before it; the download converts on the compute stream into a second staging buffer and copies out on a copy-out stream, so
@@ -166,6 +183,8 @@ uint64_t nsem_launch_count(const nsem_ctx* ctx);
 /* Which kernel generation and metric path the context runs after nsem_upload_mesh, e.g. "v4 persistent pipelined,
  * metrics on the fly (trilinear map verified)", "v4 persistent pipelined, stored metrics", "v2", "v1". */
 const char* nsem_kernel_info(const nsem_ctx* ctx);
+/* transport of the halo exchange (replaces MP::isend/irecieve/waitall, src/mp/mp.h:117-131): "peer memory ...", "nccl send/recv" or "none" */
+const char* nsem_halo_info(const nsem_ctx* ctx);
 
 /* ---- adaptive mesh refinement ----------------------------------------------------------------------- */
 /* One regrid as MeshObject::refineMesh (src/mesh/mesh.cpp:2216-2748) reports it and MeshField::refineField

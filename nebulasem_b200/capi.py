@@ -62,7 +62,8 @@ class NsemRegrid(C.Structure):
 EXPORTS = ["nsem_create", "nsem_destroy", "nsem_last_error", "nsem_get_unique_id", "nsem_set_order", "nsem_set_basis",
            "nsem_upload_mesh", "nsem_set_bcs", "nsem_set_halo", "nsem_set_params", "nsem_set_schedule",
            "nsem_pin_host", "nsem_upload_state", "nsem_download_state", "nsem_upload_state_async", "nsem_download_state_async", "nsem_upload_ref", "nsem_upload_geopotential", "nsem_euler_step", "nsem_exchange_state_halos", "nsem_diagnostics",
-           "nsem_sync", "nsem_time_steps", "nsem_launch_count", "nsem_kernel_info", "nsem_refine_state", "nsem_restart_state", "nsem_download_gradients"]
+           "nsem_sync", "nsem_time_steps", "nsem_launch_count", "nsem_kernel_info", "nsem_refine_state", "nsem_restart_state", "nsem_download_gradients",
+           "nsem_op_cds", "nsem_op_rusanov", "nsem_op_gradf_strong", "nsem_op_divf_weak", "nsem_op_apply_bcs", "nsem_op_halo", "nsem_halo_info"]
 
 _lib = None
 
@@ -96,6 +97,14 @@ def load_library() -> C.CDLL:
     lib.nsem_upload_state_async.argtypes = [vp, _dp, _dp, _dp, _dp]
     lib.nsem_download_state_async.argtypes = [vp, _dp, _dp, _dp, _dp]
     lib.nsem_download_gradients.argtypes = [vp, _dp, _dp]
+    lib.nsem_op_cds.argtypes = [vp, _dp, _dp]
+    lib.nsem_op_rusanov.argtypes = [vp, _dp]
+    lib.nsem_op_gradf_strong.argtypes = [vp, _dp, _dp]
+    lib.nsem_op_divf_weak.argtypes = [vp, _dp, _dp, _dp]
+    lib.nsem_op_apply_bcs.argtypes = [vp, C.c_int, _dp]
+    lib.nsem_op_halo.argtypes = [vp]
+    lib.nsem_halo_info.argtypes = [vp]
+    lib.nsem_halo_info.restype = C.c_char_p
     lib.nsem_refine_state.argtypes = [vp, C.POINTER(NsemRegrid), vp]
     lib.nsem_restart_state.argtypes = [vp]
     lib.nsem_upload_ref.argtypes = [vp, _dp, _dp, _dp]
@@ -261,6 +270,39 @@ class Context:
         gU, gT = np.zeros((n, 9)), np.zeros((n, 3))
         self._ck(self.lib.nsem_download_gradients(self.h, _pd(gU), _pd(gT)))
         return gU, gT
+
+    # ---- operator-level views: one reference operator at a time on the current state ----
+    def op_gradf_strong(self):
+        n = self.n_ref_nodes
+        gU, gT = np.zeros((n, 9)), np.zeros((n, 3))
+        self._ck(self.lib.nsem_op_gradf_strong(self.h, _pd(gU), _pd(gT)))
+        return gU, gT
+
+    def op_divf_weak(self):
+        """(r_rho [n], r_U [n,3], r_T [n]): divf<weak> of the three equations before src/addTemporal/Solve."""
+        n = self.n_ref_nodes
+        r, rU, rT = np.zeros(n), np.zeros((n, 3)), np.zeros(n)
+        self._ck(self.lib.nsem_op_divf_weak(self.h, _pd(r), _pd(rU), _pd(rT)))
+        return r, rU, rT
+
+    def op_rusanov(self, n_cells_real: int, npf: int):
+        """rusanov mass flux . fN per (element, local face, slot), owner's frame: [n_cells_real, 6, NPF]."""
+        out = np.zeros((n_cells_real, 6, npf))
+        self._ck(self.lib.nsem_op_rusanov(self.h, _pd(out)))
+        return out
+
+    def op_cds(self, field, n_cells_real: int, npf: int):
+        f = _f64(field)
+        assert f.size == self.n_ref_nodes
+        out = np.zeros((n_cells_real, 6, npf))
+        self._ck(self.lib.nsem_op_cds(self.h, _pd(f), _pd(out)))
+        return out
+
+    def op_apply_bcs(self, field: str, values):
+        v = np.array(values, dtype=np.float64, order="C", copy=True)
+        assert v.size == self.n_ref_nodes * (3 if field == "U" else 1)
+        self._ck(self.lib.nsem_op_apply_bcs(self.h, {"rho": 0, "U": 2, "T": 3}[field], _pd(v)))
+        return v
 
     def upload_ref(self, rho_ref, p_ref, g=None, gh=None):
         a, b = _f64(rho_ref), _f64(p_ref)

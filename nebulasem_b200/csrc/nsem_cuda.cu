@@ -8,9 +8,9 @@
 #include "../../include/nsem_c.h"
 #include "nsem_kernels.cuh"
 #include "nsem_kernels_v2.cuh"
-#include "nsem_kernels_v3.cuh"
 #include "nsem_kernels_v4.cuh"
 #include "nsem_mortar.cuh"
+#include "nsem_halo.cuh"
 #include "nsem_amr.cuh"
 
 #include <algorithm>
@@ -24,6 +24,7 @@
 
 #ifdef NSEM_WITH_NCCL
 #include <dlfcn.h>
+#include <unistd.h>
 #include <nccl.h>   // types only: the library is resolved at run time (see NcclApi) so that this .so carries no
                     // link-time NCCL dependency and shares whichever libnccl.so.2 the process already loaded
                     // (torch bundles its own; two different NCCL builds in one process do not mix)
@@ -34,12 +35,6 @@
 #endif
 #ifndef NSEM_V4_REGS_B
 #define NSEM_V4_REGS_B 128
-#endif
-#ifndef NSEM_V3_MINB_A
-#define NSEM_V3_MINB_A 4
-#endif
-#ifndef NSEM_V3_MINB_B
-#define NSEM_V3_MINB_B 4
 #endif
 
 using namespace nsem;
@@ -123,10 +118,9 @@ struct nsem_ctx {
     cudaStream_t stream = nullptr, comm = nullptr;
     mutable std::string err;
     uint64_t launches = 0;
-    bool use_v3 = false;      // warp-per-element pencil kernels (NSEM_KERNELS=v3)
     bool use_v2 = false;      // bulk-async staged kernels (3-D); NSEM_KERNELS=v1 forces the plain-load kernels
-    bool use_v4 = false;      // persistent software-pipelined kernels (3-D, default); NSEM_KERNELS=v2|v1|v3 select the older generations
-    bool pref_v2 = false, pref_v3 = false, pref_v4 = false;   // what nsem_set_order selected; a non-conforming mesh falls back to v1
+    bool use_v4 = false;      // persistent software-pipelined kernels (3-D, default); NSEM_KERNELS=v2|v1 select the older generations
+    bool pref_v2 = false, pref_v4 = false;   // what nsem_set_order selected; a non-conforming mesh falls back to v1
     bool tri = false;         // v4: metrics evaluated on the fly from the element's trilinear map (verified at upload)
     int numSMs = 148;
     double X[3][MAXN];        // LGL nodes
@@ -213,8 +207,17 @@ struct nsem_ctx {
     uint32_t nInt = 0, nHalo = 0;
     cudaEvent_t evA = nullptr, evCA = nullptr, evB = nullptr, evCB = nullptr;
     bool cbPending = false;                   // an exchange of U_new/T_new is in flight on the comm stream
+    // halo over peer memory (nsem_halo.cuh): my receive window, the neighbours' windows mapped through CUDA IPC
+    bool p2p = false;
+    void* winBase = nullptr;
+    uint64_t nRecvSlots = 0;
+    struct Remote { void* base = nullptr; bool ipc = false; uint64_t nRecv = 0, offForMe = 0; uint32_t myIdx = 0; };
+    std::vector<Remote> remotes;
+    unsigned long long haloEpoch[HALO_KINDS] = {0, 0, 0};
     bool overlap = false;                     // NSEM_OVERLAP=1: halo elements first, exchange overlapped with the interior (measured slower)
 };
+
+static int halo_check(nsem_ctx* c);       // halo over peer memory: did a neighbour fail to deliver? (defined with nsem_set_halo)
 
 // ---------------------------------------------------------------------------------------------------------
 // dispatch over the compiled (NX,NY,NZ) instantiations
@@ -279,35 +282,6 @@ struct Launch {
         if constexpr (has_v2) {
             if (P.visc) return go2(v2::sweepB_v2<NX, NY, NZ, EPB2, true, C2::minb(C2::smemB(true), 128)>, C2::smemB(true), P, s);
             return go2(v2::sweepB_v2<NX, NY, NZ, EPB2, false, C2::minb(C2::smemB(false), 128)>, C2::smemB(false), P, s);
-        } else return cudaErrorInvalidValue;
-    }
-    // ---- v3: one warp per element, one thread per k-pencil (isotropic 3-D orders with N*N <= 32) ----
-    static constexpr bool has_v3 = (NX == NY && NY == NZ && NX > 1 && NX * NX <= 32);
-    static constexpr int N3 = has_v3 ? NX : 2;
-    static constexpr int WPB3 = 2;
-    using C3 = v3::Cfg3<N3>;
-    template <class K>
-    static cudaError_t go3(K kernel, size_t smem, const KParams& P, cudaStream_t s) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) return e;
-        const unsigned grid = (P.nB + WPB3 - 1) / WPB3;
-        kernel<<<grid, WPB3 * 32, smem, s>>>(P);
-        return cudaGetLastError();
-    }
-    static cudaError_t sweepA3(const KParams& P, cudaStream_t s) {
-        if constexpr (has_v3) {
-            const size_t smem = (size_t)WPB3 * C3::smemA_w * sizeof(double);
-            if (P.visc) return go3(v3::sweepA_v3<N3, WPB3, true, NSEM_V3_MINB_A>, smem, P, s);
-            return go3(v3::sweepA_v3<N3, WPB3, false, NSEM_V3_MINB_A>, smem, P, s);
-        } else return cudaErrorInvalidValue;
-    }
-    static cudaError_t sweepB3(const KParams& P, cudaStream_t s) {
-        if constexpr (has_v3) {
-            const size_t smem = (size_t)WPB3 * C3::smemB_w * sizeof(double);
-            if (P.visc) return go3(v3::sweepB_v3<N3, WPB3, true, NSEM_V3_MINB_B>, smem, P, s);
-            return go3(v3::sweepB_v3<N3, WPB3, false, NSEM_V3_MINB_B>, smem, P, s);
         } else return cudaErrorInvalidValue;
     }
     // ---- v4: persistent, software-pipelined (cubic 3-D orders) ----
@@ -399,27 +373,20 @@ static bool has_v4(int nx, int ny, int nz) {
     return false;
 }
 
-static bool has_v3(int nx, int ny, int nz) {
-#define X(a, b, c) if (nx == a && ny == b && nz == c) return Launch<a, b, c>::has_v3;
-    NSEM_ORDERS(X)
-#undef X
-    return false;
-}
-
 static cudaError_t launch_sweepA(const nsem_ctx* c, const KParams& P) {
-#define X(a, b, cc) if (c->NX == a && c->NY == b && c->NZ == cc) return c->use_v4 ? Launch<a, b, cc>::sweepA4(P, c->tri, c->numSMs, c->stream) : c->use_v3 ? Launch<a, b, cc>::sweepA3(P, c->stream) : c->use_v2 ? Launch<a, b, cc>::sweepA2(P, c->stream) : Launch<a, b, cc>::sweepA(P, c->stream);
+#define X(a, b, cc) if (c->NX == a && c->NY == b && c->NZ == cc) return c->use_v4 ? Launch<a, b, cc>::sweepA4(P, c->tri, c->numSMs, c->stream) : c->use_v2 ? Launch<a, b, cc>::sweepA2(P, c->stream) : Launch<a, b, cc>::sweepA(P, c->stream);
     NSEM_ORDERS(X)
 #undef X
     return cudaErrorInvalidValue;
 }
 static cudaError_t launch_sweepB(const nsem_ctx* c, const KParams& P) {
-#define X(a, b, cc) if (c->NX == a && c->NY == b && c->NZ == cc) return c->use_v4 ? Launch<a, b, cc>::sweepB4(P, c->tri, c->numSMs, c->stream) : c->use_v3 ? Launch<a, b, cc>::sweepB3(P, c->stream) : c->use_v2 ? Launch<a, b, cc>::sweepB2(P, c->stream) : Launch<a, b, cc>::sweepB(P, c->stream);
+#define X(a, b, cc) if (c->NX == a && c->NY == b && c->NZ == cc) return c->use_v4 ? Launch<a, b, cc>::sweepB4(P, c->tri, c->numSMs, c->stream) : c->use_v2 ? Launch<a, b, cc>::sweepB2(P, c->stream) : Launch<a, b, cc>::sweepB(P, c->stream);
     NSEM_ORDERS(X)
 #undef X
     return cudaErrorInvalidValue;
 }
 static cudaError_t launch_ghost_trace(const nsem_ctx* c, const KParams& P) {
-    if (!(c->use_v4 || (c->use_v2 && !c->use_v3))) return cudaSuccess;       // only the v2/v4 sweep B consumes face traces
+    if (!(c->use_v4 || c->use_v2)) return cudaSuccess;       // only the v2/v4 sweep B consumes face traces
     GhostTraceParams G;
     std::memset(&G, 0, sizeof G);
     G.nB = c->nB; G.nG = c->nG; G.ghostBase = c->ghostBase;
@@ -509,6 +476,15 @@ extern "C" int nsem_create(int device, int rank, int nranks, const void* nccl_un
     return 0;
 }
 
+static void halo_p2p_release(nsem_ctx* c) {
+    for (auto& r : c->remotes)
+        if (r.base && r.ipc) cudaIpcCloseMemHandle(r.base);
+    c->remotes.clear();
+    if (c->winBase) cudaFree(c->winBase);
+    c->winBase = nullptr;
+    c->p2p = false;
+}
+
 extern "C" void nsem_destroy(nsem_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
@@ -516,6 +492,7 @@ extern "C" void nsem_destroy(nsem_ctx* c) {
 #ifdef NSEM_WITH_NCCL
     if (c->nccl) g_nccl.CommDestroy(c->nccl);
 #endif
+    halo_p2p_release(c);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     for (auto& r : c->pinned) cudaHostUnregister(const_cast<void*>(r.first));
     for (cudaEvent_t e : {c->evH2D, c->evScatter, c->evGather, c->evD2H}) if (e) cudaEventDestroy(e);
@@ -543,12 +520,17 @@ extern "C" int nsem_get_unique_id(void* out128) {
 
 extern "C" uint64_t nsem_launch_count(const nsem_ctx* c) { return c->launches; }
 
+// transport of the face-trace halo: "peer memory" (stores into the neighbours' windows over NVLink, nsem_halo.cuh), "nccl", or "none"
+extern "C" const char* nsem_halo_info(const nsem_ctx* c) {
+    if (c->nranks <= 1 || c->peers.empty()) return "none";
+    return c->p2p ? "peer memory (CUDA IPC windows, NVLink stores + flags)" : "nccl send/recv";
+}
+
 extern "C" const char* nsem_kernel_info(const nsem_ctx* c) {
     if (c->use_v4 && c->nMortarGroups)
         return c->tri ? "v4 persistent pipelined, metrics on the fly (trilinear map verified) + mortar (non-conforming) face kernels"
                       : "v4 persistent pipelined, stored metrics + mortar (non-conforming) face kernels";
     if (c->use_v4) return c->tri ? "v4 persistent pipelined, metrics on the fly (trilinear map verified)" : "v4 persistent pipelined, stored metrics";
-    if (c->use_v3) return "v3 warp per element";
     if (c->use_v2) return "v2 bulk-async staged";
     if (c->nMortarGroups) return "v1 plain loads + mortar (non-conforming) face kernels";
     return "v1 plain loads";
@@ -560,7 +542,7 @@ extern "C" int nsem_sync(nsem_ctx* c) {
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->comm));
     if (c->d2h) CUDA_TRY(c, cudaStreamSynchronize(c->d2h));
-    return 0;
+    return halo_check(c);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -582,9 +564,8 @@ extern "C" int nsem_set_order(nsem_ctx* c, int NPX, int NPY, int NPZ) {
     c->have_basis = c->have_mesh = c->have_state = c->have_ref = c->have_bcs = false;
     const char* kv = std::getenv("NSEM_KERNELS");
     c->use_v2 = has_v2(NPX, NPY, NPZ) && !(kv && std::strcmp(kv, "v1") == 0);
-    c->use_v3 = has_v3(NPX, NPY, NPZ) && (kv && std::strcmp(kv, "v3") == 0);
-    c->use_v4 = has_v4(NPX, NPY, NPZ) && !(kv && (std::strcmp(kv, "v1") == 0 || std::strcmp(kv, "v2") == 0 || std::strcmp(kv, "v3") == 0));
-    c->pref_v2 = c->use_v2; c->pref_v3 = c->use_v3; c->pref_v4 = c->use_v4;
+    c->use_v4 = has_v4(NPX, NPY, NPZ) && !(kv && (std::strcmp(kv, "v1") == 0 || std::strcmp(kv, "v2") == 0));
+    c->pref_v2 = c->use_v2; c->pref_v4 = c->use_v4;
     c->tri = false;
     return 0;
 }
@@ -685,7 +666,6 @@ extern "C" int nsem_upload_mesh(nsem_ctx* c, const nsem_mesh* m) {
         const char* mv1 = std::getenv("NSEM_MORTAR_V1");
         const bool v4ok = !(mv1 && std::strcmp(mv1, "1") == 0);
         c->use_v2 = c->pref_v2 && !anyMortar;
-        c->use_v3 = c->pref_v3 && !anyMortar;
         c->use_v4 = c->pref_v4 && (!anyMortar || v4ok);
     }
     std::vector<MortarGroup> mGroups;
@@ -1241,6 +1221,7 @@ extern "C" int nsem_upload_state(nsem_ctx* c, const double* rho, const double* U
 extern "C" int nsem_download_state(nsem_ctx* c, double* rho, double* U, double* T, double* p) {
     if (!c->have_state) { c->err = "nsem_download_state: no state"; return 1; }
     CUDA_TRY(c, cudaSetDevice(c->device));
+    if (halo_check(c)) return 1;
     const int k = c->cur;
     const double* s1[3] = {c->rho[k].p, nullptr, nullptr};
     if (rho && from_device(c, rho, 1, s1)) return 1;
@@ -1454,7 +1435,7 @@ static void fill_bcparams(const nsem_ctx* c, const KParams& P, BCParams& B, int 
     B.S_new = P.S_new;
 }
 
-static int halo_exchange(nsem_ctx* c, double* const* arrays, int nf, cudaStream_t s);
+static int halo_exchange(nsem_ctx* c, double* const* arrays, int nf, cudaStream_t s, int kind);
 
 // non-conforming faces: phase 0 before sweep A (old state), phase 1 before sweep B (rho_new, p', gradients of real cells)
 static cudaError_t launch_mortar(const nsem_ctx* c, const KParams& P, int phase) {
@@ -1511,7 +1492,7 @@ static int one_step_overlapped(nsem_ctx* c) {
         double* arr[14] = {P.rho_new, P.p};
         int nf = 2;
         if (P.visc) { for (int q = 0; q < 9; q++) arr[nf++] = P.GU[q]; for (int q = 0; q < 3; q++) arr[nf++] = P.GT[q]; }
-        if (halo_exchange(c, arr, nf, cs)) return 1;
+        if (halo_exchange(c, arr, nf, cs, 0)) return 1;
     }
     CUDA_TRY(c, cudaEventRecord(c->evCA, cs));
     if (c->nInt) CUDA_TRY(c, launch_sweepA(c, PI));
@@ -1524,7 +1505,7 @@ static int one_step_overlapped(nsem_ctx* c) {
     CUDA_TRY(c, cudaStreamWaitEvent(cs, c->evB, 0));
     {
         double* arr[5] = {P.U_new[0], P.U_new[1], P.U_new[2], P.T_new, P.S_new};
-        if (halo_exchange(c, arr, 5, cs)) return 1;
+        if (halo_exchange(c, arr, 5, cs, 1)) return 1;
     }
     CUDA_TRY(c, cudaEventRecord(c->evCB, cs));
     c->cbPending = true;
@@ -1547,7 +1528,7 @@ static int join_comm(nsem_ctx* c) {
 static int join_comm_fwd(nsem_ctx* c) { return join_comm(c); }
 
 static int one_step(nsem_ctx* c, bool timed, double* acc) {
-    if (!timed && !c->peers.empty() && c->overlap && c->nMortarGroups == 0) return one_step_overlapped(c);
+    if (!timed && !c->peers.empty() && c->overlap && !c->p2p && c->nMortarGroups == 0) return one_step_overlapped(c);
     if (join_comm(c)) return 1;
     KParams P;
     BCParams B;
@@ -1563,7 +1544,7 @@ static int one_step(nsem_ctx* c, bool timed, double* acc) {
         double* arr[14] = {P.rho_new, P.p};
         int nf = 2;
         if (P.visc) { for (int q = 0; q < 9; q++) arr[nf++] = P.GU[q]; for (int q = 0; q < 3; q++) arr[nf++] = P.GT[q]; }
-        if (halo_exchange(c, arr, nf, c->stream)) return 1;
+        if (halo_exchange(c, arr, nf, c->stream, 0)) return 1;
     }
     CUDA_TRY(c, launch_ghost_trace(c, P));
     if (timed) cudaEventRecord(c->ev[2], c->stream);
@@ -1574,10 +1555,10 @@ static int one_step(nsem_ctx* c, bool timed, double* acc) {
     CUDA_TRY(c, launch_bc(c, B));
     if (!c->peers.empty()) {
         double* arr[5] = {P.U_new[0], P.U_new[1], P.U_new[2], P.T_new, P.S_new};
-        if (halo_exchange(c, arr, 5, c->stream)) return 1;
+        if (halo_exchange(c, arr, 5, c->stream, 1)) return 1;
     }
     if (timed) cudaEventRecord(c->ev[4], c->stream);
-    c->launches += 2 + (c->nG ? 2 : 0) + ((c->nG && (c->use_v4 || (c->use_v2 && !c->use_v3))) ? 1 : 0) + (c->nMortarGroups ? 2 : 0);
+    c->launches += 2 + (c->nG ? 2 : 0) + ((c->nG && (c->use_v4 || c->use_v2)) ? 1 : 0) + (c->nMortarGroups ? 2 : 0);
     c->cur ^= 1;
     if (timed) {
         CUDA_TRY(c, cudaEventSynchronize(c->ev[4]));
@@ -1634,12 +1615,221 @@ extern "C" int nsem_time_steps(nsem_ctx* c, int nsteps, double* ms, double* per_
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// operator-level entry points: the reference's operators one at a time, on the state the context holds, for unit parity
+// against the oracle.  They run the same kernels as the step (KParams::op_mode makes a sweep store its divf residual instead of the
+// update) and use the `new` halves of the ping-pong buffers as scratch; the current state is not touched.
+// ---------------------------------------------------------------------------------------------------------
+static int op_begin(nsem_ctx* c, const char* who, KParams& P) {
+    if (check_ready(c, who)) return 1;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (join_comm(c)) return 1;
+    fill_kparams(c, P);
+    return ensure_speed(c);
+}
+// sweep A (+ the ghost update and, on several partitions, the halo after it) exactly as the step runs them
+static int op_run_first_half(nsem_ctx* c, const KParams& P) {
+    BCParams B;
+    CUDA_TRY(c, launch_mortar(c, P, 0));
+    CUDA_TRY(c, launch_sweepA(c, P));
+    fill_bcparams(c, P, B, 0);
+    CUDA_TRY(c, launch_bc(c, B));
+    c->launches += 1 + (c->nG ? 1 : 0) + (c->nMortarGroups ? 1 : 0);
+    if (!c->peers.empty()) {
+        double* arr[14] = {P.rho_new, P.p};
+        int nf = 2;
+        if (P.visc) { for (int q = 0; q < 9; q++) arr[nf++] = P.GU[q]; for (int q = 0; q < 3; q++) arr[nf++] = P.GT[q]; }
+        if (halo_exchange(c, arr, nf, c->stream, 0)) return 1;
+    }
+    return 0;
+}
+
+// divf<weak> (field.h:3417-3478: volume term + rusanov faces + div_flux) of the three equations of euler.cpp:195-258 on the current state:
+// r_rho = divf(rho U, rho, lambda); r_U = divf(Fc (x) U + I p' - mu grad U, rho_new U, lambda); r_T = divf(Fc theta - mu/Pr grad theta,
+// rho_new theta, lambda) -- the residuals BEFORE src/addTemporal/Solve.  Reference layouts (scalar / AoS vector over n_cells_all * NP
+// nodes; ghost entries are not meaningful).  Any pointer may be NULL.
+extern "C" int nsem_op_divf_weak(nsem_ctx* c, double* r_rho, double* r_U, double* r_T) {
+    KParams P;
+    if (op_begin(c, "nsem_op_divf_weak", P)) return 1;
+    if (r_rho) {
+        KParams Q = P;
+        Q.op_mode = 1;
+        CUDA_TRY(c, launch_mortar(c, Q, 0));
+        CUDA_TRY(c, launch_sweepA(c, Q));
+        c->launches += 1 + (c->nMortarGroups ? 1 : 0);
+        const double* src[3] = {P.rho_new, nullptr, nullptr};
+        if (from_device(c, r_rho, 1, src)) return 1;
+    }
+    if (r_U || r_T) {
+        if (op_run_first_half(c, P)) return 1;
+        CUDA_TRY(c, launch_ghost_trace(c, P));
+        CUDA_TRY(c, launch_mortar(c, P, 1));
+        KParams Q = P;
+        Q.op_mode = 1;
+        CUDA_TRY(c, launch_sweepB(c, Q));
+        c->launches += 2 + (c->nMortarGroups ? 1 : 0);
+        if (r_U) { const double* src[3] = {P.U_new[0], P.U_new[1], P.U_new[2]}; if (from_device(c, r_U, 3, src)) return 1; }
+        if (r_T) { const double* src[3] = {P.T_new, nullptr, nullptr}; if (from_device(c, r_T, 1, src)) return 1; }
+    }
+    return 0;
+}
+
+// rusanov(rho U, rho, lambda) . fN (field.h:2928-2943 contracted as div_flux does, :3093-3114) of the mass equation on every element face
+// node, in the face OWNER's frame: flux[(elem*6 + local face) * NPF + slot], slot = the face-node index of dg.cpp:372-404.  Both elements
+// of an interior face report the same number (that is what makes the scheme conservative).  Mortar faces report 0 (their flux lives on
+// the sub-facets, nsem_mortar.cuh).  
+extern "C" int nsem_op_rusanov(nsem_ctx* c, double* flux) {
+    KParams P;
+    if (op_begin(c, "nsem_op_rusanov", P)) return 1;
+    const size_t n = (size_t)c->nB * 6 * c->NPF;
+    DevBuf<double> d;
+    CUDA_TRY(c, d.alloc(n));
+    CUDA_TRY(c, cudaMemsetAsync(d.p, 0, n * sizeof(double), c->stream));
+    P.op_mode = 1;
+    P.op_flux = d.p;
+    // the persistent and the plain-load sweep A report the flux; the bulk-staged generation (NSEM_KERNELS=v2, stored metrics) hands over to
+    // the plain-load one
+    const bool v2 = c->use_v2;
+    if (!c->use_v4) c->use_v2 = false;
+    cudaError_t e = launch_mortar(c, P, 0);
+    if (e == cudaSuccess) e = launch_sweepA(c, P);
+    c->use_v2 = v2;
+    CUDA_TRY(c, e);
+    c->launches += 1 + (c->nMortarGroups ? 1 : 0);
+    CUDA_TRY(c, cudaMemcpyAsync(flux, d.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// cds(f) (field.h:2881-2893) of a scalar cell field given in the reference layout (n_cells_all * NP values, ghost cells included), same
+// output layout as nsem_op_rusanov
+extern "C" int nsem_op_cds(nsem_ctx* c, const double* field, double* out) {
+    KParams P;
+    if (op_begin(c, "nsem_op_cds", P)) return 1;
+    double* dst[3] = {P.rho_new, nullptr, nullptr};
+    if (to_device(c, field, 1, dst)) return 1;
+    const size_t n = (size_t)c->nB * 6 * c->NPF;
+    DevBuf<double> d;
+    CUDA_TRY(c, d.alloc(n));
+    cudaError_t e = cudaErrorInvalidValue;
+#define X(a, b, cc) if (c->NX == a && c->NY == b && c->NZ == cc) { op_cds_kernel<a, b, cc><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(P, P.rho_new, d.p); e = cudaGetLastError(); }
+    NSEM_ORDERS(X)
+#undef X
+    CUDA_TRY(c, e);
+    c->launches++;
+    CUDA_TRY(c, cudaMemcpyAsync(out, d.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// gradf<strong>(U), gradf<strong>(theta) + fillBCs(r, fIndex) (field.h:3328-3362, 2731-2769) of the CURRENT state (nsem_download_gradients
+// returns what the last step left behind)
+extern "C" int nsem_op_gradf_strong(nsem_ctx* c, double* grad_U, double* grad_T) {
+    KParams P;
+    if (op_begin(c, "nsem_op_gradf_strong", P)) return 1;
+    if (!P.visc) { c->err = "nsem_op_gradf_strong: the gradients are only evaluated when diffusion is on"; return 1; }
+    if (op_run_first_half(c, P)) return 1;
+    return nsem_download_gradients(c, grad_U, grad_T);
+}
+
+// applyExplicitBCs (field.h:2586-2727) on one field given in the reference layout: the ghost entries of `values` are replaced by what
+// the field's boundary conditions make of the owner values.  field = NSEM_F_RHO, NSEM_F_U (3 components) or NSEM_F_T (the condition acts
+// on theta = T + T0 and T0 is subtracted again, euler.cpp:258,286); NSEM_F_P is tied to the equation of state inside the step and has
+// no stand-alone form.
+extern "C" int nsem_op_apply_bcs(nsem_ctx* c, int field, double* values) {
+    KParams P;
+    if (op_begin(c, "nsem_op_apply_bcs", P)) return 1;
+    if (!(field == NSEM_F_RHO || field == NSEM_F_U || field == NSEM_F_T)) { c->err = "nsem_op_apply_bcs: field must be NSEM_F_RHO, NSEM_F_U or NSEM_F_T"; return 1; }
+    BCParams B;
+    fill_bcparams(c, P, B, field == NSEM_F_RHO ? 0 : 1);
+    B.visc = 0;
+    B.S_new = nullptr;
+    double* d3[3] = {P.U_new[0], P.U_new[1], P.U_new[2]};
+    double* d1[3] = {field == NSEM_F_RHO ? P.rho_new : P.T_new, nullptr, nullptr};
+    const int comps = field == NSEM_F_U ? 3 : 1;
+    if (to_device(c, values, comps, field == NSEM_F_U ? d3 : d1)) return 1;
+    CUDA_TRY(c, launch_bc(c, B));
+    if (c->nG) c->launches++;
+    return from_device(c, values, comps, field == NSEM_F_U ? d3 : d1);
+}
+
+// ASYNC_COMM (field.h:2255-2324) on the current state: the halo of rho, U, T, p and the reference state (= nsem_exchange_state_halos)
+extern "C" int nsem_op_halo(nsem_ctx* c) { return nsem_exchange_state_halos(c); }
+
+// Map the neighbours' receive windows (nsem_halo.cuh).  Collective over the ranks that share faces: the IPC handles and the slot offsets
+// travel once, through NCCL point-to-point; if ANY rank cannot map a neighbour (no peer access, handles refused) every rank keeps the NCCL
+// transport -- the choice is agreed with an all-reduce so that no rank waits for a flag nobody will set.  NSEM_HALO=nccl forces NCCL.
+static int halo_p2p_setup(nsem_ctx* c) {
+    halo_p2p_release(c);
+    for (auto& e : c->haloEpoch) e = 0;
+#ifdef NSEM_WITH_NCCL
+    const char* mode = std::getenv("NSEM_HALO");
+    int want = !(mode && std::strcmp(mode, "nccl") == 0) && (int)c->peers.size() <= HALO_MAX_PEERS;
+    const int np = (int)c->peers.size();
+    c->nRecvSlots = c->nSendSlots;             // the same faces in both directions
+    struct Msg { cudaIpcMemHandle_t h; uint64_t nRecv, offForYou, raw; uint32_t yourIdx, pid; };
+    std::vector<Msg> out(np), in(np);
+    if (want) {
+        const size_t bytes = HALO_HEADER_BYTES + halo_window_doubles(c->nRecvSlots) * sizeof(double);
+        if (cudaMalloc(&c->winBase, bytes) != cudaSuccess) { cudaGetLastError(); c->winBase = nullptr; want = 0; }
+        else CUDA_TRY(c, cudaMemsetAsync(c->winBase, 0, HALO_HEADER_BYTES, c->stream));
+    }
+    cudaIpcMemHandle_t h;
+    std::memset(&h, 0, sizeof h);
+    if (want && cudaIpcGetMemHandle(&h, c->winBase) != cudaSuccess) { cudaGetLastError(); want = 0; }
+    for (int p = 0; p < np; p++) out[p] = Msg{h, c->nRecvSlots, c->peers[p].off, (uint64_t)(uintptr_t)c->winBase, (uint32_t)p, (uint32_t)getpid()};
+    DevBuf<unsigned char> dOut, dIn;
+    DevBuf<int> dFlag;
+    CUDA_TRY(c, dOut.alloc((size_t)np * sizeof(Msg)));
+    CUDA_TRY(c, dIn.alloc((size_t)np * sizeof(Msg)));
+    CUDA_TRY(c, dFlag.alloc(1));
+    CUDA_TRY(c, cudaMemcpyAsync(dOut.p, out.data(), (size_t)np * sizeof(Msg), cudaMemcpyHostToDevice, c->stream));
+    ncclResult_t r = g_nccl.GroupStart();
+    for (int p = 0; p < np && r == ncclSuccess; p++) {
+        r = g_nccl.Send(dOut.p + (size_t)p * sizeof(Msg), sizeof(Msg), ncclChar, c->peers[p].rank, c->nccl, c->stream);
+        if (r == ncclSuccess) r = g_nccl.Recv(dIn.p + (size_t)p * sizeof(Msg), sizeof(Msg), ncclChar, c->peers[p].rank, c->nccl, c->stream);
+    }
+    ncclResult_t r2 = g_nccl.GroupEnd();
+    if (r != ncclSuccess || r2 != ncclSuccess) { c->err = std::string("halo set-up: ") + g_nccl.GetErrorString(r != ncclSuccess ? r : r2); return 1; }
+    CUDA_TRY(c, cudaMemcpyAsync(in.data(), dIn.p, (size_t)np * sizeof(Msg), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    int ok = want;
+    c->remotes.assign(np, nsem_ctx::Remote{});
+    for (int p = 0; p < np && ok; p++) {
+        nsem_ctx::Remote& rm = c->remotes[p];
+        rm.nRecv = in[p].nRecv; rm.offForMe = in[p].offForYou; rm.myIdx = in[p].yourIdx;
+        if (in[p].raw == 0) { ok = 0; break; }
+        if (in[p].pid == (uint32_t)getpid()) rm.base = reinterpret_cast<void*>((uintptr_t)in[p].raw);      // same address space
+        else if (cudaIpcOpenMemHandle(&rm.base, in[p].h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess) rm.ipc = true;
+        else { cudaGetLastError(); rm.base = nullptr; ok = 0; }
+    }
+    // every rank of the communicator takes part (ranks without neighbours included): the transport is one decision
+    CUDA_TRY(c, cudaMemcpyAsync(dFlag.p, &ok, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    if (g_nccl.AllReduce(dFlag.p, dFlag.p, 1, ncclInt, ncclMin, c->nccl, c->stream) != ncclSuccess) { c->err = "halo set-up: ncclAllReduce failed"; return 1; }
+    CUDA_TRY(c, cudaMemcpyAsync(&ok, dFlag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (ok) c->p2p = !c->peers.empty();
+    else halo_p2p_release(c);
+#endif
+    return 0;
+}
+
+// a neighbour that never arrived (halo_pull_kernel gave up): reported where the host synchronises anyway
+static int halo_check(nsem_ctx* c) {
+    if (!c->p2p) return 0;
+    int e = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(&e, static_cast<char*>(c->winBase) + HALO_KINDS * HALO_MAX_PEERS * 8 + 8, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (e) { c->err = "halo exchange: neighbour #" + std::to_string(e - 1) + " (rank " + std::to_string(c->peers[e - 1].rank) + ") never delivered its face traces"; return 1; }
+    return 0;
+}
+
 extern "C" int nsem_set_halo(nsem_ctx* c, const nsem_halo_peer* peers, uint32_t n_peers) {
     if (!c->have_mesh) { c->err = "nsem_set_halo: no mesh"; return 1; }
     CUDA_TRY(c, cudaSetDevice(c->device));
     c->peers.clear();
     c->nSendSlots = 0;
-    if (n_peers == 0) return 0;
+    if (n_peers == 0) return c->nranks > 1 ? halo_p2p_setup(c) : 0;      // the transport is agreed by all ranks, neighbours or not
     if (c->nranks <= 1) { c->err = "nsem_set_halo: context was created for a single rank"; return 1; }
     const int NPF = c->NPF, GPS = c->GPS, NPS = c->NPS;
     std::vector<uint32_t> nodes;
@@ -1694,15 +1884,50 @@ extern "C" int nsem_set_halo(nsem_ctx* c, const nsem_halo_peer* peers, uint32_t 
     const char* ov = std::getenv("NSEM_OVERLAP");
     c->overlap = (ov && std::strcmp(ov, "1") == 0);
     c->cbPending = false;
-    return 0;
+    return halo_p2p_setup(c);
 }
 
 // pack the owner-side face values of `nf` arrays and exchange them with every peer on stream `s`:
 // send from the packed buffer, receive straight into the ghost region [ghostBase + g0*GPS, +nf*GPS) of each array
-static int halo_exchange(nsem_ctx* c, double* const* arrays, int nf, cudaStream_t s) {
+static int halo_exchange(nsem_ctx* c, double* const* arrays, int nf, cudaStream_t s, int kind) {
     if (c->peers.empty()) return 0;
+    if (nf > 16 || nf > halo_kind_fields(kind)) { c->err = "halo_exchange: too many fields"; return 1; }
+    if (c->p2p) {
+        // two kernels: stores into the neighbours' windows over NVLink + flags, then wait for the neighbours' flags and fill the ghost cells
+        const int np = (int)c->peers.size();
+        const unsigned long long epoch = ++c->haloEpoch[kind];
+        const int parity = (int)(epoch & 1ull);
+        char* base = static_cast<char*>(c->winBase);
+        HaloPushParams H;
+        std::memset(&H, 0, sizeof H);
+        H.nfields = nf; H.npeers = np; H.nslots = c->nSendSlots; H.node = c->sendNodes.p; H.epoch = epoch;
+        H.counter = reinterpret_cast<unsigned int*>(base + HALO_KINDS * HALO_MAX_PEERS * 8);
+        for (int f = 0; f < nf; f++) H.src[f] = arrays[f];
+        HaloPullParams R;
+        std::memset(&R, 0, sizeof R);
+        R.nfields = nf; R.npeers = np; R.nslots = c->nRecvSlots; R.stride = c->nRecvSlots; R.ghostBase = c->ghostBase; R.epoch = epoch;
+        R.win = reinterpret_cast<const double*>(base + HALO_HEADER_BYTES) + halo_region_offset(kind, parity, c->nRecvSlots);
+        R.flag = reinterpret_cast<const unsigned long long*>(base) + (size_t)kind * HALO_MAX_PEERS;
+        R.error = reinterpret_cast<int*>(base + HALO_KINDS * HALO_MAX_PEERS * 8 + 8);
+        { const char* t = std::getenv("NSEM_HALO_TIMEOUT_S"); R.timeout_ns = (unsigned long long)((t ? std::atof(t) : 30.0) * 1e9); }
+        for (int f = 0; f < nf; f++) R.dst[f] = arrays[f];
+        for (int p = 0; p < np; p++) {
+            const nsem_ctx::Remote& rm = c->remotes[p];
+            char* rb = static_cast<char*>(rm.base);
+            H.off[p] = R.off[p] = c->peers[p].off;
+            H.win[p] = reinterpret_cast<double*>(rb + HALO_HEADER_BYTES) + halo_region_offset(kind, parity, rm.nRecv) + rm.offForMe;
+            H.stride[p] = rm.nRecv;
+            H.flag[p] = reinterpret_cast<unsigned long long*>(rb) + (size_t)kind * HALO_MAX_PEERS + rm.myIdx;
+            R.ghostOff[p] = (uint64_t)c->peers[p].g0 * c->GPS;
+        }
+        H.off[np] = R.off[np] = c->nSendSlots;
+        halo_push_kernel<<<(unsigned)((H.nslots + 255) / 256), 256, 0, s>>>(H);
+        halo_pull_kernel<<<(unsigned)((R.nslots + 255) / 256), 256, 0, s>>>(R);
+        c->launches += 2;
+        CUDA_TRY(c, cudaGetLastError());
+        return 0;
+    }
 #ifdef NSEM_WITH_NCCL
-    if (nf > 16) { c->err = "halo_exchange: too many fields"; return 1; }
     PackParams H;
     std::memset(&H, 0, sizeof H);
     H.nfields = nf; H.nslots = c->nSendSlots; H.node = c->sendNodes.p; H.dst = c->sendBuf.p;
@@ -1736,7 +1961,7 @@ extern "C" int nsem_exchange_state_halos(nsem_ctx* c) {
     CUDA_TRY(c, cudaSetDevice(c->device));
     const int k = c->cur;
     double* arr[8] = {c->rho[k].p, c->U[k][0].p, c->U[k][1].p, c->U[k][2].p, c->T[k].p, c->p.p, c->rho_ref.p, c->p_ref.p};
-    if (halo_exchange(c, arr, 8, c->stream)) return 1;
+    if (halo_exchange(c, arr, 8, c->stream, 2)) return 1;
     c->speed_valid = false;
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return 0;

@@ -57,6 +57,12 @@ struct KParams {
     double mrdt, mdt;            // -1/dt, -dt
     int buoyancy, visc, has_gfield;
     int sms;                     // SM count (v4: rotates the heavy warp roles between the CTAs that share an SM)
+    // operator-level views (nsem_op_*, unit parity against the reference's own operators): op_mode bit 0 = the sweeps store the RESIDUAL
+    // of divf<weak> (field.h:3417-3478) where they would store the updated field (r_rho -> rho_new; r_U, r_theta -> U_new, T_new);
+    // op_flux (plain-load sweep A only) = the rusanov mass flux . fN (field.h:2928-2943, 3093-3114) of every element face node,
+    // [elem*6 + local face][NPF], in the owner's frame
+    int op_mode;
+    double* op_flux;
     uint32_t run;                // v4 sweep A: consecutive schedule positions one CTA handles in a row (RunIter); 0/1 = grid-stride order
     int probe;                   // diagnostics only (NSEM_PROBE): 1 = stream the inputs and skip the arithmetic, 2 = also skip the gathers
     // basis
@@ -191,6 +197,31 @@ __global__ void __launch_bounds__(256) speed_kernel(uint64_t n, double T0, doubl
     S[q] = side_speed(u, T[q] + T0, gammaR);
 }
 
+// cds(cell field) (field.h:2881-2893): fF = fI * fFO + (1 - fI) * fFN on every element face node, [elem*6 + local face][NPF]; a face is
+// evaluated from both of its elements and both write the same value (bitwise: fI is 0 or 1/2).  Operator-level view only (nsem_op_cds).
+template <int NX, int NY, int NZ>
+__global__ void __launch_bounds__(256) op_cds_kernel(const __grid_constant__ KParams P, const double* __restrict__ f, double* __restrict__ out) {
+    using Dm = Dims<NX, NY, NZ>;
+    constexpr int NPF = Dm::NPF, NPS = Dm::NPS;
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (uint64_t)P.nB * 6 * NPF) return;
+    const uint32_t ef = (uint32_t)(gid / NPF);
+    const int n = (int)(gid % NPF), s = (int)(ef % 6);
+    const uint32_t elem = ef / 6;
+    const uint32_t meta = P.faceMeta[ef];
+    const uint32_t fid = meta & FM_FID_MASK;
+    bool valid;
+    const int ln = face_node_from_slot<NX, NY, NZ>(s, n, valid);
+    if (!valid || fid == FM_ABSENT || (meta & FM_MORTAR)) { out[gid] = 0.0; return; }
+    int a, b;
+    if (s < 2) { a = n / NY; b = n % NY; } else { a = n / NZ; b = n % NZ; }
+    const size_t oidx = (size_t)P.faceOther[ef] + (fid == FM_GHOST ? n : face_node<NX, NY, NZ>(fid, a, b));
+    const bool own = meta & FM_OWNER;
+    const double al = (meta & FM_HALF) ? 0.5 : 0.0;
+    const double mine = f[(size_t)elem * NPS + ln], other = f[oidx];
+    out[gid] = own ? (mine * al + other * (1 - al)) : (other * al + mine * (1 - al));
+}
+
 // ---------------------------------------------------------------------------------------------------
 // sweep A
 // ---------------------------------------------------------------------------------------------------
@@ -309,6 +340,7 @@ sweepA_kernel(const __grid_constant__ KParams P) {
         const double fo = rho_o * (uo0 * N0 + uo1 * N1 + uo2 * N2), fn = rho_n * (un0 * N0 + un1 * N1 + un2 * N2);
         const double flux = (fo * al + fn * (1 - al)) - lam * (rho_n - rho_o) * nN;
         r_rho += own ? flux : -flux;
+        if (P.op_flux) P.op_flux[((size_t)elem * 6 + s) * Dm::NPF + n] = flux;
         if (VISC) {
             // grad_flux<strong>: r[c1] += fN (x) (cds(P) - P_o) ; r[c2] -= fN (x) (cds(P) - P_n)
             const double sgn = own ? 1.0 : -1.0;
@@ -327,7 +359,7 @@ sweepA_kernel(const __grid_constant__ KParams P) {
 
     // ---- rho update (addTemporal<1> field.h:3875-3920, SolveTexplicit solve.cpp:563-570) ----
     const double ap0 = (-1.0 / P.dt) * cV;
-    const double rho_new = (r_rho + rho * ap0) / ap0;
+    const double rho_new = (P.op_mode & 1) ? r_rho : (r_rho + rho * ap0) / ap0;
     P.rho_new[idx] = rho_new;
     // p = P0 (rho T R / P0)^gamma ; p -= p_ref   (euler.cpp:211-213)
     P.p[idx] = __dsub_rn(eos_pressure(P.P0, P.R, P.gamma, rho_new, th), P.p_ref[idx]);
@@ -502,11 +534,11 @@ sweepB_kernel(const __grid_constant__ KParams P) {
 #pragma unroll
     for (int c = 0; c < 3; c++) {
         const double Su = (r[c] - (drho * g[c]) * cV) + (u[c] * rho_o) * ap0;
-        P.U_new[c][idx] = Su / ap;
+        P.U_new[c][idx] = (P.op_mode & 1) ? r[c] : Su / ap;
     }
     {
         const double Su = r[3] + (th * rho_o) * ap0;
-        P.T_new[idx] = Su / ap - P.T0;                                      // euler.cpp:286
+        P.T_new[idx] = (P.op_mode & 1) ? r[3] : Su / ap - P.T0;             // euler.cpp:286
     }
 }
 

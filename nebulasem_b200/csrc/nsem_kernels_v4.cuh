@@ -209,6 +209,9 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
     };
     // request the neighbour values of every face node of the element whose record sits in `slot` into table `buf`
     auto issue_gathers = [&](int slot, int buf) {
+#ifdef NSEM_EXP_NOGATHER       // timing experiment only (wrong results): what sweep A costs without its neighbour gathers
+        if (slot >= 0) { cp_async_commit(); return; }
+#endif
         const int t = fresh_tid();
 #pragma unroll
         for (int ps = 0; ps < C::NPASS; ps++) {
@@ -374,6 +377,7 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
                     const double fm = rho * (u0 * N0 + u1 * N1 + u2 * N2), fx = xr * (xu0 * N0 + xu1 * N1 + xu2 * N2);
                     const double flux = (fm * wo + fx * wx) - lam * (sg * (xr - rho)) * nN;
                     r_rho += sg * flux;
+                    if (P.op_flux) P.op_flux[((size_t)elem * 6 + s) * NPF + ((ax == 0) ? i * NY + j : (ax == 1 ? i * NZ + k : j * NZ + k))] = flux;   // nsem_op_rusanov
                     if (VISC) {
                         // grad_flux<strong>: r += (+-fN) (x) (cds(q) - q_mine)
                         const double q0_ = (u0 * wo + xu0 * wx) - u0, q1_ = (u1 * wo + xu1 * wx) - u1, q2_ = (u2 * wo + xu2 * wx) - u2;
@@ -394,7 +398,7 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
             const size_t idx = (size_t)elem * NPS + nt;
             const double rcV = 1.0 / cV;
             const double ap0 = P.mrdt * cV;
-            const double rho_new = (r_rho + rho * ap0) * (rcV * P.mdt);
+            const double rho_new = (P.op_mode & 1) ? r_rho : (r_rho + rho * ap0) * (rcV * P.mdt);
             const double ppn = __dsub_rn(eos_pressure(P.P0, P.R, P.gamma, rho_new, th), in[C::A_PREF * NPS + nt]);
             P.rho_new[idx] = rho_new;
             P.p[idx] = ppn;
@@ -696,12 +700,12 @@ __global__ void __launch_bounds__((CfgB<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 const double Su = (r[c] - (drho * g[c]) * cV) + (u[c] * rho_o) * ap0;
-                un[c] = Su * rap;
+                un[c] = (P.op_mode & 1) ? r[c] : Su * rap;
                 P.U_new[c][idx] = un[c];
             }
             {
                 const double Su = r[3] + (th * rho_o) * ap0;
-                const double Tn = Su * rap - P.T0;
+                const double Tn = (P.op_mode & 1) ? r[3] : Su * rap - P.T0;
                 P.T_new[idx] = Tn;
                 // |U| + c of the new state, from the values as stored (every other producer of S reads them back from memory)
                 P.S_new[idx] = side_speed(un, Tn + P.T0, P.gamma * P.R);

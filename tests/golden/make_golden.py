@@ -24,6 +24,10 @@ FIXTURES = [
     ("vortex_n6_o3_s50", "vortex", dict(n=6, order=3), 50),
     ("vortex_n4_o6_s20", "vortex", dict(n=4, order=6), 20),
     ("hill3d_6x2x4_o3_s10", "hill3d", dict(nx=6, ny=2, nz=4, order=3), 10),
+    # north_star: "after 100 RK steps" -- 3-D cases at the full step count (round 2)
+    ("bubble3d_n3_o4_s100", "bubble3d", dict(n=3, order=4), 100),
+    ("hill3d_6x2x4_o3_s100", "hill3d", dict(nx=6, ny=2, nz=4, order=3), 100),
+    ("vortex_n4_o4_s100", "vortex", dict(n=4, order=4), 100),
 ]
 
 
@@ -35,9 +39,27 @@ def main():
             cases.CASES[case](**kw).write(d, nsteps)
             run_ref.run_euler(d, variant="parity")
             dump = run_ref.read_dump(d, 1)
+            # the reference against itself: the same sources built with its release flags (-O3, FMA contraction; oracle/_ref/fast) on the
+            # same case.  SURVEY finding 6: the self-relative momentum error of ANY faithful implementation is only meaningful against this
+            # spread (p - p_ref cancels in the early bubble momentum), so the parity tests assert rhoU_self <= 3 x spread
+            d2 = tempfile.mkdtemp(prefix="golden_fast_")
+            try:
+                cases.CASES[case](**kw).write(d2, nsteps)
+                run_ref.run_euler(d2, variant="fast", threads=1)
+                fast = run_ref.read_dump(d2, 1)
+            finally:
+                shutil.rmtree(d2, ignore_errors=True)
+            T0 = 300.0
+            ctl = open(os.path.join(d, "controls")).read().split()
+            if "T0" in ctl:
+                T0 = float(ctl[ctl.index("T0") + 1])
+            rel = lambda a, b: float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300))
+            spread = dict(rho=rel(fast["rho"], dump["rho"]), rhoU_self=rel(fast["rho"][:, None] * fast["U"], dump["rho"][:, None] * dump["U"]),
+                          rhoTheta=rel(fast["rho"] * (fast["T"] + T0), dump["rho"] * (dump["T"] + T0)))
             np.savez_compressed(os.path.join(out_dir, fname + ".npz"), case=case, kwargs=repr(kw), nsteps=nsteps,
-                                rho=dump["rho"], U=dump["U"], T=dump["T"], p=dump["p"])
-            print(fname, {k: v.shape for k, v in dump.items()})
+                                rho=dump["rho"], U=dump["U"], T=dump["T"], p=dump["p"],
+                                spread_rho=spread["rho"], spread_rhoU_self=spread["rhoU_self"], spread_rhoTheta=spread["rhoTheta"])
+            print(fname, {k: v.shape for k, v in dump.items()}, "O2-vs-O3 spread:", spread)
         finally:
             shutil.rmtree(d, ignore_errors=True)
 

@@ -38,6 +38,8 @@ def main():
     s.attach(local, rank, world, uid_bytes)
     s.step(nsteps)
     s.download()
+    if rank == 0:
+        print("halo transport:", s.halo_info)
     rho, U, T, p = s.state()
     nb = s.gBCSfield
     NP = s.NP

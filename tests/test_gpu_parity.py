@@ -61,9 +61,14 @@ def test_device_matches_the_reference_binary_dumps(tmp_cases, path):
     c0 = np.sqrt(orc.gamma * orc.R * T0)
     err = dict(rho=rel_l2(rho[:nb], g["rho"]),
                rhoTheta=rel_l2(rho[:nb] * (T[:nb] + T0), g["rho"] * (g["T"] + T0)),
-               rhoU_scaled=rel_l2(rho[:nb, None] * U[:nb], g["rho"][:, None] * g["U"], scale=np.linalg.norm(g["rho"]) * c0))
-    print(os.path.basename(path), nsteps, err)
+               rhoU_scaled=rel_l2(rho[:nb, None] * U[:nb], g["rho"][:, None] * g["U"], scale=np.linalg.norm(g["rho"]) * c0),
+               rhoU_self=rel_l2(rho[:nb, None] * U[:nb], g["rho"][:, None] * g["U"]))
+    spread = float(g["spread_rhoU_self"])
+    print(os.path.basename(path), nsteps, err, "reference -O2 vs -O3 rhoU_self spread:", spread)
     assert err["rho"] <= TOL and err["rhoTheta"] <= TOL and err["rhoU_scaled"] <= TOL, err
+    # SURVEY finding 6 / 8(c), the second half of the momentum criterion: self-relative rho*U within 1e-11, or -- where the reference's own
+    # -O2 and -O3 builds differ by more than that on this very case (the fixture holds their measured spread) -- within 3 x that spread
+    assert err["rhoU_self"] <= max(TOL, 3.0 * spread), (err, spread)
 
 
 @pytest.mark.parametrize("name,kw", [("bubble3d", dict(n=3, order=3)), ("hill3d", dict(nx=6, ny=2, nz=4, order=3)), ("bubble2d", dict(n=5, order=4))])
@@ -309,13 +314,14 @@ print("MASS_LOSS", d["mass_loss"], "VOLUME_LOSS", d["volume_loss"])
     import tempfile
     outs = {}
     with tempfile.TemporaryDirectory() as td:
-        for tag, env in (("v1", {"NSEM_KERNELS": "v1"}), ("v2", {"NSEM_KERNELS": "v2"}), ("v3", {"NSEM_KERNELS": "v3"}),
+        for tag, env in (("v1", {"NSEM_KERNELS": "v1"}), ("v2", {"NSEM_KERNELS": "v2"}),
                          ("v2m", {"NSEM_KERNELS": "v2", "NSEM_SCHEDULE": "morton"}), ("v4", {}), ("v4m", {"NSEM_SCHEDULE": "morton"}),
-                         ("v4s", {"NSEM_METRICS": "stored"})):
+                         ("v4s", {"NSEM_METRICS": "stored"}),
+                         ("v4r", {"NSEM_RUN": "32"})):
             f = os.path.join(td, tag + ".npy")
             r = subprocess.run([sys.executable, "-c", code, f], env={**os.environ, **env}, capture_output=True, text=True, timeout=900)
             assert r.returncode == 0, r.stderr[-2000:]
-            want = {"v1": "v1", "v2": "v2", "v3": "v3", "v2m": "v2", "v4": "on the fly", "v4m": "on the fly", "v4s": "stored metrics"}[tag]
+            want = {"v1": "v1", "v2": "v2", "v2m": "v2", "v4": "on the fly", "v4m": "on the fly", "v4s": "stored metrics", "v4r": "on the fly"}[tag]
             assert want in r.stdout.split("KERNELS")[1].splitlines()[0], (tag, r.stdout)
             loss = float(r.stdout.split("MASS_LOSS")[1].split()[0])
             assert abs(loss) <= 1e-13, (tag, loss)
@@ -324,7 +330,8 @@ print("MASS_LOSS", d["mass_loss"], "VOLUME_LOSS", d["volume_loss"])
     assert np.isfinite(ref).all()
     assert np.array_equal(outs["v2"], outs["v2m"])            # the schedule never changes the result
     assert np.array_equal(outs["v4"], outs["v4m"])
-    for tag in ("v2", "v3", "v4", "v4s"):
+    assert np.array_equal(outs["v4"], outs["v4r"])            # nor do the runs of consecutive elements one CTA handles (RunIter)
+    for tag in ("v2", "v4", "v4s"):
         a = outs[tag]
         assert np.linalg.norm(a[:, 0] - ref[:, 0]) / np.linalg.norm(ref[:, 0]) <= 1e-13
         assert np.linalg.norm(a[:, 0] * (a[:, 4] + 300) - ref[:, 0] * (ref[:, 4] + 300)) / np.linalg.norm(ref[:, 0] * (ref[:, 4] + 300)) <= 1e-13
