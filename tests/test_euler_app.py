@@ -164,3 +164,76 @@ def test_restart_reads_the_dump_start_step_names_and_the_newest_older_grid(tmp_p
     open(os.path.join(a, "controls"), "w").write(ctl.replace("start_step 0", "start_step 8").replace("end_step 4", "end_step 12"))
     out = subprocess.run([build.EULER_BIN, "./controls"], cwd=a, env=dict(os.environ, NSEM_DRYRUN="9"), capture_output=True, text=True, timeout=60)
     assert out.returncode != 0 and "rho2" in out.stderr, out.stderr[-300:]
+
+
+@pytest.mark.gpu
+def test_amr_run_matches_the_reference_run(tmp_path):
+    """BASELINE configs[4]: examples/atmo/srtb-amr exactly as it ships (amr_step 1), write_interval 50, 100 steps, through the drop-in
+    `euler ./controls` on one GPU against the dump the UNMODIFIED reference binary wrote of the same run (tests/golden/amr_run/, made by
+    make_amr_run_golden.py).  Both do what iteration.h:94-147 + euler.cpp:57-287 prescribe: start-branch set-up on the coarse grid, regrid
+    (same 32 cells tagged: 100 -> 196), restart branch on the regridded grid, 50 steps, dump, regrid by the indicator of the dumped state
+    (38 refined, 60 coarsened: 265 cells), 50 steps, dump.  The in-memory forest numbers cells and local frames differently from the
+    reference's facet splitting, so cells are matched by centroid and nodes by position; then rho, rho*theta <= 1e-11 and rho*U <= 1e-11 of
+    ||rho|| c0 (north_star), on a mesh with non-conforming faces, after two regrids and their field transfers."""
+    from nebulasem_b200 import host
+    src = os.path.join(ROOT, "tests", "golden", "amr_run", "srtb-amr")
+    a = str(tmp_path / "srtb-amr")
+    shutil.copytree(src, a)
+    exp = np.load(os.path.join(a, "expected.npz"))
+    os.remove(os.path.join(a, "expected.npz"))
+    run_euler(a, 1, timeout=900)
+    nsteps, interval = int(exp["nsteps"]), int(exp["interval"])
+    scale = np.abs(exp["node_xyz"]).max()
+    T0, c0 = 300.0, np.sqrt(1004.67 / 715.5 * (1004.67 - 715.5) * 300.0)
+    rel = lambda x, y, sc=None: float(np.linalg.norm((x - y).ravel()) / (np.linalg.norm(y.ravel()) if sc is None else sc))
+    # half way: dump 1 = 50 steps on the grid of the initial regrid, against the reference run stopped there (its full run overwrites the
+    # files of dump 1 with the fields transferred to the next grid)
+    h = str(tmp_path / "half")
+    os.makedirs(h)
+    shutil.copy(os.path.join(a, "grid_0.bin"), os.path.join(h, "grid_0.bin"))
+    for f in ("rho", "U", "T", "p"):
+        shutil.copy(os.path.join(a, f"{f}1.bin"), os.path.join(h, f"{f}0.bin"))
+    import re
+    open(os.path.join(h, "controls"), "w").write(re.sub(r"(?m)^\s*amr_step\s+\d+\s*\n", "", open(os.path.join(a, "controls")).read()))
+    s = host.Solver.open_case(h)                                  # for the geometry of that grid only: the set-up's start branch would
+    n = s.gBCSfield                                               # recompute rho from the dumped p (which step 50 formed with theta of step 49)
+    rho, U, T = (refio.read_field_values(os.path.join(a, f"{f}1")) for f in ("rho", "U", "T"))
+    rho, T = rho[:, 0], T[:, 0]
+    kx = lambda x: np.round(x / scale * 1e7).astype(np.int64)
+    # DG nodes on element faces are duplicated: a node is identified by its position AND the centroid of its cell
+    mine = np.concatenate([kx(np.repeat(s.f64("gCC")[:3 * s.nBCS].reshape(-1, 3), s.NP, axis=0)), kx(s.f64("cC").reshape(-1, 3)[:n])], axis=1)
+    s.close()
+    assert n == exp["half_node_xyz"].shape[0], (n, exp["half_node_xyz"].shape)
+    ref = np.concatenate([kx(np.repeat(exp["grid0_CC"], int(exp["NP"]), axis=0)), kx(exp["half_node_xyz"])], axis=1)
+    om, orf = np.lexsort(mine.T[::-1]), np.lexsort(ref.T[::-1])
+    assert np.array_equal(mine[om], ref[orf]), "the initial regrids differ"
+    r_m, U_m, T_m, r_r, U_r, T_r = rho[:n][om], U[:n][om], T[:n][om], exp["half_rho"][orf], exp["half_U"][orf], exp["half_T"][orf]
+    err = dict(rho=rel(r_m, r_r), rhoTheta=rel(r_m * (T_m + T0), r_r * (T_r + T0)),
+               rhoU_scaled=rel(r_m[:, None] * U_m, r_r[:, None] * U_r, np.linalg.norm(r_r) * c0))
+    print("after 50 steps on the first regridded grid:", err)
+    assert err["rho"] <= 1e-11 and err["rhoTheta"] <= 1e-11 and err["rhoU_scaled"] <= 1e-11, err
+    s = host.Solver.open_case(a, nsteps // interval)             # grid of the last regrid + the last dump
+    nb, NP = s.nBCS, s.NP
+    assert nb == exp["grid1_CC"].shape[0], (nb, exp["grid1_CC"].shape)
+    n = s.gBCSfield
+    rho, U, T = (refio.read_field_values(os.path.join(a, f"{f}{nsteps // interval}")) for f in ("rho", "U", "T"))
+    rho, T = rho[:, 0], T[:, 0]
+    xyz = s.f64("cC").reshape(-1, 3)[:n]
+    cc = np.repeat(s.f64("gCC")[:3 * nb].reshape(nb, 3), NP, axis=0)
+    s.close()
+    key = lambda c, x: np.round(np.concatenate([c, x], axis=1) / scale * 1e7).astype(np.int64)
+    mine = key(cc, xyz)
+    ref = key(np.repeat(exp["grid1_CC"], int(exp["NP"]), axis=0), exp["node_xyz"])
+    om, orf = np.lexsort(mine.T[::-1]), np.lexsort(ref.T[::-1])
+    assert np.array_equal(mine[om], ref[orf]), "the two runs do not end on the same grid"
+    r_m, U_m, T_m = rho[:n][om], U[:n][om], T[:n][om]
+    r_r, U_r, T_r = exp["rho"][orf], exp["U"][orf], exp["T"][orf]
+    err = dict(rho=rel(r_m, r_r), rhoTheta=rel(r_m * (T_m + T0), r_r * (T_r + T0)),
+               rhoU_scaled=rel(r_m[:, None] * U_m, r_r[:, None] * U_r, np.linalg.norm(r_r) * c0))
+    print("AMR run vs the reference run:", err)
+    d = np.abs(r_m - r_r)
+    worst = np.argsort(d)[-5:]
+    print("rho: nodes with |diff| > 1e-12:", int((d > 1e-12).sum()), "of", d.size, "worst:", [(float(d[i]), exp["node_xyz"][orf][i].round(2).tolist(), float(exp["node_cV"][orf][i])) for i in worst])
+    dm = float((r_m * exp["node_cV"][orf]).sum() - (r_r * exp["node_cV"][orf]).sum())
+    print("mass difference", dm, "of", float((r_r * exp["node_cV"][orf]).sum()), "mean diff", float((r_m - r_r).mean()), "T diff max", float(np.abs(T_m - T_r).max()))
+    assert err["rho"] <= 1e-11 and err["rhoTheta"] <= 1e-11 and err["rhoU_scaled"] <= 1e-11, err
