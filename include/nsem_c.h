@@ -147,6 +147,15 @@ int nsem_op_gradf_strong(nsem_ctx* ctx, double* grad_U, double* grad_T);
 int nsem_op_divf_weak(nsem_ctx* ctx, double* r_rho, double* r_U, double* r_T);
 int nsem_op_apply_bcs(nsem_ctx* ctx, int field, double* values);
 int nsem_op_halo(nsem_ctx* ctx);
+
+/* ---- explicit scalar advection (apps/convection/convection.cpp:113-137: dT/dt + div(T U) = 0 with RUSANOV and a one-stage scheme) ----
+ * The transported scalar takes the place of rho in the context (nsem_upload_state(ctx, scalar, U, zeros, zeros); its boundary conditions
+ * are set under NSEM_F_RHO) and one step is the mass-equation half of the euler step with lambdaMax = cds(mag(U)) / 2 (:105).
+ * problem_init: 0 = NONE (the wind is the uploaded U), 1 = LEVEQUE (the deformational wind of convection.cpp:74-82, re-evaluated on the
+ * device before every step at time step * dt with period etime = end_step * dt; needs the node coordinates Mesh::cC). */
+int nsem_upload_coords(nsem_ctx* ctx, const double* cC);
+int nsem_set_convection(nsem_ctx* ctx, int problem_init, double etime, long first_step);
+int nsem_convection_step(nsem_ctx* ctx, int nsteps);
 /* Pipelined variants for drivers that stream batches through the device: both only ENQUEUE and return.  The upload copies on a
  * copy-in stream into its own staging buffer and converts the layout on the compute stream, ordered after everything enqueued
  * before it; the download converts on the compute stream into a second staging buffer and copies out on a copy-out stream, so

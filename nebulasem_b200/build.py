@@ -40,7 +40,7 @@ HOST_LIB = os.path.join(LIBDIR, "libnsem_host.so")
 EULER_BIN = os.path.join(LIBDIR, "euler")
 CXX = os.environ.get("NSEM_CXX", "g++")   # the image's $CXX wrapper (/opt/gcc) lacks libgomp.spec
 # -ffp-contract=off: geometry and reference-state arithmetic must round like the reference's own -O2 build
-HOST_FLAGS = ["-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-fopenmp", "-Wall", "-Wno-unknown-pragmas"]
+HOST_FLAGS = ["-O3", "-std=c++17", "-ffp-contract=off", "-fPIC", "-fopenmp", "-Wall", "-Wno-unknown-pragmas"]
 
 
 def build_host(force: bool = False) -> str:

@@ -63,7 +63,7 @@ EXPORTS = ["nsem_create", "nsem_destroy", "nsem_last_error", "nsem_get_unique_id
            "nsem_upload_mesh", "nsem_set_bcs", "nsem_set_halo", "nsem_set_params", "nsem_set_schedule",
            "nsem_pin_host", "nsem_upload_state", "nsem_download_state", "nsem_upload_state_async", "nsem_download_state_async", "nsem_upload_ref", "nsem_upload_geopotential", "nsem_euler_step", "nsem_exchange_state_halos", "nsem_diagnostics",
            "nsem_sync", "nsem_time_steps", "nsem_launch_count", "nsem_kernel_info", "nsem_refine_state", "nsem_restart_state", "nsem_download_gradients",
-           "nsem_op_cds", "nsem_op_rusanov", "nsem_op_gradf_strong", "nsem_op_divf_weak", "nsem_op_apply_bcs", "nsem_op_halo", "nsem_halo_info"]
+           "nsem_op_cds", "nsem_op_rusanov", "nsem_op_gradf_strong", "nsem_op_divf_weak", "nsem_op_apply_bcs", "nsem_op_halo", "nsem_halo_info", "nsem_upload_coords", "nsem_set_convection", "nsem_convection_step"]
 
 _lib = None
 
@@ -104,6 +104,9 @@ def load_library() -> C.CDLL:
     lib.nsem_op_apply_bcs.argtypes = [vp, C.c_int, _dp]
     lib.nsem_op_halo.argtypes = [vp]
     lib.nsem_halo_info.argtypes = [vp]
+    lib.nsem_upload_coords.argtypes = [vp, _dp]
+    lib.nsem_set_convection.argtypes = [vp, C.c_int, C.c_double, C.c_long]
+    lib.nsem_convection_step.argtypes = [vp, C.c_int]
     lib.nsem_halo_info.restype = C.c_char_p
     lib.nsem_refine_state.argtypes = [vp, C.POINTER(NsemRegrid), vp]
     lib.nsem_restart_state.argtypes = [vp]
@@ -270,6 +273,18 @@ class Context:
         gU, gT = np.zeros((n, 9)), np.zeros((n, 3))
         self._ck(self.lib.nsem_download_gradients(self.h, _pd(gU), _pd(gT)))
         return gU, gT
+
+    # ---- explicit scalar advection (apps/convection) ----
+    def upload_coords(self, cC):
+        a = _f64(cC)
+        assert a.size == self.n_ref_nodes * 3
+        self._ck(self.lib.nsem_upload_coords(self.h, _pd(a)))
+
+    def set_convection(self, problem_init: str = "NONE", etime: float = 1.0, first_step: int = 1):
+        self._ck(self.lib.nsem_set_convection(self.h, {"NONE": 0, "LEVEQUE": 1}[problem_init], float(etime), int(first_step)))
+
+    def convection_step(self, nsteps=1):
+        self._ck(self.lib.nsem_convection_step(self.h, int(nsteps)))
 
     # ---- operator-level views: one reference operator at a time on the current state ----
     def op_gradf_strong(self):

@@ -10,6 +10,9 @@
 // fN = A_face * w_a w_b / 4 (SURVEY finding 4); the same definitions are used here so that field files and
 // results are interchangeable.
 #include <cmath>
+#include <cstdlib>
+#include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <string>
 
@@ -225,6 +228,13 @@ void Geometry::build(const MeshTopo& t, const Basis& b) {
     if (gALL + NP >= 0xffffffffull) throw Error("mesh exceeds the 32-bit node index of the reference layout");
     auto I4 = [&](uint64_t c, int i, int j, int k) { return (u32)(c * NP + (uint64_t)i * NPY * NPZ + j * NPZ + k); };
 
+    const bool verbose = std::getenv("NSEM_VERBOSE") != nullptr;
+    auto tl = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        const auto t1 = std::chrono::steady_clock::now();
+        if (verbose) std::printf("  geometry: %-34s %.3f s\n", what, std::chrono::duration<double>(t1 - tl).count());
+        tl = t1;
+    };
     faceBegin.resize(nCells); faceEnd.resize(nCells);
     allFaces = t.cellFaces; faceID = t.cellFaceID;
     for (u32 i = 0; i < nCells; i++) { faceBegin[i] = t.cellStart[i]; faceEnd[i] = t.cellStart[i + 1]; }
@@ -258,6 +268,7 @@ void Geometry::build(const MeshTopo& t, const Basis& b) {
     FO.assign(nfn, (u32)gALL);
     FN.assign(nfn, (u32)gALL);
 
+    lap("tables + array fills");
     const double* xg[3] = {b.xgl[0].data(), b.xgl[1].data(), b.xgl[2].data()};
     const double* wg[3] = {b.wgl[0].data(), b.wgl[1].data(), b.wgl[2].data()};
 
@@ -326,6 +337,7 @@ void Geometry::build(const MeshTopo& t, const Basis& b) {
     }
 
     if (!corner_error.empty()) throw Error(corner_error);
+    lap("node coordinates");
 
     // ---- face node maps and weights (dg.cpp:328-410) ----
     const int face_map[6] = {0, NPZ - 1, 0, NPY - 1, 0, NPX - 1};
@@ -367,6 +379,7 @@ void Geometry::build(const MeshTopo& t, const Basis& b) {
         }
     }
 
+    lap("face node maps");
     // ---- Jinv (dg.cpp:413-476), AoS XX,YY,ZZ,XY,YZ,XZ,YX,ZY,ZX ----
     Jinv.assign(gBCSfield * 9, 0.0);
     const double* D[3] = {b.dpsi[0].data(), b.dpsi[1].data(), b.dpsi[2].data()};
@@ -416,6 +429,7 @@ void Geometry::build(const MeshTopo& t, const Basis& b) {
                 }
     }
 
+    lap("Jinv");
     // ---- fI (field.cpp:257-270): 0 on physical boundary faces, 0.5 elsewhere (ghost faces of other ranks too) ----
 #pragma omp parallel for schedule(static)
     for (int64_t k = 0; k < (int64_t)nfn; k++) fI[k] = (FN[k] >= gBCSfield) ? 0.0 : 0.5;

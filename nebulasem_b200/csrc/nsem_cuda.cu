@@ -141,6 +141,12 @@ struct nsem_ctx {
 
     // node arrays
     DevBuf<double> rho[2], U[2][3], T[2], S[2], p, GU[9], GT[3], Jinv[9], cV, rho_ref, p_ref, gfield[3], gh, diagPartial;
+    // explicit scalar advection (apps/convection): the scalar lives in the rho slot, lambdaMax = cds(|U|)/2 (no sound speed: R = 0 in the kernels)
+    bool convection = false;
+    int conv_init = 0;                 // 0 = the wind is the uploaded U, 1 = LEVEQUE (re-evaluated at every step)
+    double conv_etime = 1.0;           // end_step * dt: the period of the analytic wind
+    long conv_step = 0;                // steps taken (Iteration::get_step() - 1)
+    DevBuf<double> xyz[3];             // node coordinates (analytic wind only)
     bool speed_valid = false;  // S[cur] = |U| + c of the current state (kept by sweep B + the ghost update; recomputed after the state was set from outside)
     bool has_gh = false;
     int cur = 0;
@@ -1379,7 +1385,7 @@ static void fill_kparams(const nsem_ctx* c, KParams& P) {
     const int k = c->cur, o = 1 - c->cur;
     P.nB = c->nB; P.nG = c->nG; P.ghostBase = c->ghostBase;
     const nsem_params& q = c->prm;
-    P.P0 = q.P0; P.T0 = q.T0; P.R = q.cp - q.cv; P.gamma = q.cp / q.cv; P.nu = q.viscosity; P.iPr = 1 / q.Pr; P.dt = q.dt;
+    P.P0 = q.P0; P.T0 = q.T0; P.R = c->convection ? 0.0 : q.cp - q.cv; P.gamma = q.cp / q.cv; P.nu = q.viscosity; P.iPr = 1 / q.Pr; P.dt = q.dt;
     for (int d = 0; d < 3; d++) P.g[d] = q.gravity[d];
     P.mrdt = -1.0 / q.dt; P.mdt = -q.dt;
     P.buoyancy = q.buoyancy;
@@ -1462,7 +1468,7 @@ static int ensure_speed(nsem_ctx* c) {
     if (c->speed_valid) return 0;
     const int k = c->cur;
     const uint64_t n = c->nNodes;
-    speed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->prm.T0, (c->prm.cp / c->prm.cv) * (c->prm.cp - c->prm.cv), c->U[k][0].p,
+    speed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->prm.T0, c->convection ? 0.0 : (c->prm.cp / c->prm.cv) * (c->prm.cp - c->prm.cv), c->U[k][0].p,
                                                                     c->U[k][1].p, c->U[k][2].p, c->T[k].p, c->S[k].p);
     c->launches++;
     CUDA_TRY(c, cudaGetLastError());
@@ -1751,6 +1757,71 @@ extern "C" int nsem_op_apply_bcs(nsem_ctx* c, int field, double* values) {
     CUDA_TRY(c, launch_bc(c, B));
     if (c->nG) c->launches++;
     return from_device(c, values, comps, field == NSEM_F_U ? d3 : d1);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// explicit scalar advection: apps/convection/convection.cpp:113-137 on the kernels of the euler path.
+//     M = divf(Fc * T, false, &F, &T, &lambdaMax); addTemporal<1>(M); Solve(M)      with Fc = U, lambdaMax = cds(mag(U)) / 2
+// is the mass equation of the euler step with the transported scalar in the place of rho and no sound speed in lambdaMax, so the scalar
+// is kept in the rho slot of the state (nsem_upload_state(ctx, scalar, U, NULL...), boundary conditions under NSEM_F_RHO) and a step is
+// sweep A (inviscid instantiation, R = 0) + the ghost update of rho + the halo; the other outputs of the sweep are not used.
+// problem_init: 0 = the wind is the uploaded U; 1 = LEVEQUE, re-evaluated on the device at time step * dt before every step
+// (convection.cpp:74-82,114-121; needs nsem_upload_coords).  etime = end_step * dt; first_step = the step the next call starts with.
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int nsem_set_convection(nsem_ctx* c, int problem_init, double etime, long first_step) {
+    if (problem_init < 0 || problem_init > 1) { c->err = "nsem_set_convection: problem_init must be 0 (NONE) or 1 (LEVEQUE); the spherical winds need a spherical mesh"; return 1; }
+    if (problem_init == 1 && !c->xyz[0].p) { c->err = "nsem_set_convection: LEVEQUE needs the node coordinates (nsem_upload_coords)"; return 1; }
+    c->convection = true;
+    c->conv_init = problem_init;
+    c->conv_etime = etime;
+    c->conv_step = first_step - 1;
+    c->speed_valid = false;
+    return 0;
+}
+
+// Mesh::cC (node coordinates, AoS, n_cells_all * NP entries, ghost cells included)
+extern "C" int nsem_upload_coords(nsem_ctx* c, const double* cC) {
+    if (!c->have_mesh) { c->err = "nsem_upload_coords: no mesh"; return 1; }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    for (int d = 0; d < 3; d++) CUDA_TRY(c, c->xyz[d].alloc(c->nNodes));
+    double* dst[3] = {c->xyz[0].p, c->xyz[1].p, c->xyz[2].p};
+    return to_device(c, cC, 3, dst);
+}
+
+extern "C" int nsem_convection_step(nsem_ctx* c, int nsteps) {
+    if (!c->convection) { c->err = "nsem_convection_step: call nsem_set_convection first"; return 1; }
+    if (check_ready(c, "nsem_convection_step")) return 1;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (join_comm(c)) return 1;
+    for (int st = 0; st < nsteps; st++) {
+        const int k = c->cur;
+        c->conv_step++;
+        if (c->conv_init == 1) {
+            const uint64_t n = c->nNodes;
+            wind_leveque_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, (double)c->conv_step * c->prm.dt, c->conv_etime, c->xyz[0].p, c->xyz[1].p,
+                                                                                   c->U[k][0].p, c->U[k][1].p, c->U[k][2].p);
+            c->launches++;
+            c->speed_valid = false;
+        }
+        if (ensure_speed(c)) return 1;                 // S = |U| (R = 0)
+        KParams P;
+        BCParams B;
+        fill_kparams(c, P);
+        P.visc = 0; P.buoyancy = 0;
+        CUDA_TRY(c, launch_mortar(c, P, 0));
+        CUDA_TRY(c, launch_sweepA(c, P));
+        fill_bcparams(c, P, B, 0);
+        CUDA_TRY(c, launch_bc(c, B));
+        c->launches += 1 + (c->nG ? 1 : 0) + (c->nMortarGroups ? 1 : 0);
+        if (!c->peers.empty()) {
+            double* arr[2] = {P.rho_new, P.p};
+            if (halo_exchange(c, arr, 2, c->stream, 0)) return 1;
+        }
+        // the new scalar becomes the current one; U, T and S stay where they are
+        std::swap(c->rho[0].p, c->rho[1].p);
+        std::swap(c->rho[0].n, c->rho[1].n);
+    }
+    return 0;
 }
 
 // ASYNC_COMM (field.h:2255-2324) on the current state: the halo of rho, U, T, p and the reference state (= nsem_exchange_state_halos)

@@ -197,6 +197,20 @@ __global__ void __launch_bounds__(256) speed_kernel(uint64_t n, double T0, doubl
     S[q] = side_speed(u, T[q] + T0, gammaR);
 }
 
+// LeVeque's deformational wind (apps/convection/convection.cpp:74-82, init_wind_field, re-evaluated at every step): on EVERY node, ghost
+// nodes included (they carry their owner's coordinates), u = sin^2(pi x) sin(2 pi y) cos(pi t / period), v = -sin^2(pi y) sin(2 pi x) cos(..)
+__global__ void __launch_bounds__(256) wind_leveque_kernel(uint64_t n, double time, double period, const double* __restrict__ x, const double* __restrict__ y,
+                                                            double* __restrict__ u0, double* __restrict__ u1, double* __restrict__ u2) {
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    constexpr double PI = 3.14159265358979323846264;      // Constants::PI
+    const double ct = cos(PI * time / period);
+    const double sx = sin(PI * x[q]), sy = sin(PI * y[q]);
+    u0[q] = pow(sx, 2.0) * sin(2 * PI * y[q]) * ct;
+    u1[q] = -pow(sy, 2.0) * sin(2 * PI * x[q]) * ct;
+    u2[q] = 0.0;
+}
+
 // cds(cell field) (field.h:2881-2893): fF = fI * fFO + (1 - fI) * fFN on every element face node, [elem*6 + local face][NPF]; a face is
 // evaluated from both of its elements and both write the same value (bitwise: fI is 0 or 1/2).  Operator-level view only (nsem_op_cds).
 template <int NX, int NY, int NZ>

@@ -3,7 +3,7 @@
 # /root/reference) into oracle/_ref/ as the parity oracle and CPU baseline.
 # TEST INFRASTRUCTURE ONLY: nothing in nebulasem_b200/ links or calls these binaries.
 #
-#   oracle/_ref/parity/{euler,mesh,prepare,geomdump,refinedump}   -O2 -ffp-contract=off          (parity oracle)
+#   oracle/_ref/parity/{euler,convection,mesh,prepare,geomdump,refinedump}   -O2 -ffp-contract=off          (parity oracle)
 #   oracle/_ref/fast/{euler,mesh}                       -O3 -funroll-loops -march=x86-64-v3 -fopenmp
 #                                                        (the reference's release flags, CMakeLists.txt:36-37,
 #                                                         with a portable -march so the binary also runs on the GPU box)
@@ -33,7 +33,7 @@ build_variant() {
     local dir="$OUT/$name"
     local stamp="$dir/.flags"
     if [ -f "$stamp" ] && [ "$(cat "$stamp")" = "$flags" ] && [ -x "$dir/euler" ] && [ -x "$dir/mesh" ] \
-       && [ "$HERE/tools/geomdump.cpp" -ot "$dir/euler" ] && [ -x "$dir/refinedump" ] && [ "$HERE/tools/refinedump.cpp" -ot "$dir/refinedump" ]; then
+       && [ "$HERE/tools/geomdump.cpp" -ot "$dir/euler" ] && [ -x "$dir/refinedump" ] && [ "$HERE/tools/refinedump.cpp" -ot "$dir/refinedump" ] && [ -x "$dir/convection" ]; then
         echo "build_ref: $name up to date"; return
     fi
     echo "build_ref: compiling $name ($flags)"
@@ -49,6 +49,7 @@ build_variant() {
     ar rcs "$dir/libnebulasem.a" "$dir"/obj/*.o
     g++ -std=c++17 $flags -DUSE_DOUBLE -DUSE_EXPR_TMPL -w $INC "$R/apps/euler/euler.cpp" "$dir/libnebulasem.a" -o "$dir/euler" &
     g++ -std=c++17 $flags -DUSE_DOUBLE -DUSE_EXPR_TMPL -w $INC "$R/apps/mesh/meshApp.cpp" "$dir/libnebulasem.a" -o "$dir/mesh" &
+    g++ -std=c++17 $flags -DUSE_DOUBLE -DUSE_EXPR_TMPL -w $INC "$R/apps/convection/convection.cpp" "$dir/libnebulasem.a" -o "$dir/convection" &
     g++ -std=c++17 $flags -DUSE_DOUBLE -DUSE_EXPR_TMPL -w $INC "$R/apps/prepare/prepareApp.cpp" "$dir/libnebulasem.a" -o "$dir/prepare" &
     g++ -std=c++17 $flags -DUSE_DOUBLE -DUSE_EXPR_TMPL -w $INC "$HERE/tools/geomdump.cpp" "$dir/libnebulasem.a" -o "$dir/geomdump" &
     g++ -std=c++17 $flags -DUSE_DOUBLE -DUSE_EXPR_TMPL -w $INC "$HERE/tools/refinedump.cpp" "$dir/libnebulasem.a" -o "$dir/refinedump" &

@@ -87,3 +87,25 @@ def load_case(case_dir: str, exact_order: bool = True, step: int = 0) -> EulerOr
     orc = EulerOracle(geo, params, exact_order=exact_order)
     orc.setup(fields["rho"], fields["U"], fields["T"], fields["p"], bcs)
     return orc
+
+
+def load_convection_case(case_dir: str, exact_order: bool = True, step: int = 0):
+    """The same for `solver convection` (apps/convection): fields U and T, controls block convection{problem_init}."""
+    from .convection import ConvectionOracle
+    blocks = refio.read_controls(os.path.join(case_dir, "controls"))
+    gen = blocks["general"]
+    mesh_name = gen.get("mesh", ["grid"])[0]
+    nop = [int(gen.get(k, ["0"])[0]) for k in ("npx", "npy", "npz")]
+    grid = refio.read_grid(os.path.join(case_dir, f"{mesh_name}_{step}"))
+    topo = MeshTopo(grid).load()
+    geo = Geometry(topo, Basis(nop))
+    params = Params.from_controls(blocks)
+    fields, bcs = {}, {}
+    for name in ("U", "T"):
+        ff = refio.read_field(os.path.join(case_dir, f"{name}{step}"))
+        fields[name] = init_field(ff, geo, params.gravity)
+        bcs[name] = bind_bcs(ff, topo)
+    orc = ConvectionOracle(geo, params, exact_order=exact_order)
+    orc.setup_convection(fields["T"], fields["U"], bcs, blocks.get("convection", {}).get("problem_init", ["NONE"])[0],
+                         int(gen.get("end_step", ["1"])[0]))
+    return orc

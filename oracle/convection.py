@@ -1,0 +1,53 @@
+"""numpy restatement of the reference's explicit scalar advection app -- TEST INFRASTRUCTURE ONLY (the checker of
+nsem_convection_step; nothing under nebulasem_b200/ imports it).
+
+apps/convection/convection.cpp:18-150:  dT/dt + div(T U) = 0 on the dGSEM operators of the euler path:
+    Fc = flxc(U) = U, lambdaMax = cds(mag(U)) / 2                                   (:103-105, 119-121)
+    M = divf(Fc * T, false, &F, &T, &lambdaMax); addTemporal<1>(M, t_UR); Solve(M)    (:129-135)
+with the optional analytic wind of LeVeque's deformation test re-evaluated at every step (:42-87, 114-121).  One reference step is one
+forward-Euler stage for BDF1 / AB1 / RK1 (SURVEY finding 1), like the euler path."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import libm
+from .euler import EulerOracle, vmag
+
+PI = 3.14159265358979323846264          # Constants::PI
+
+
+class ConvectionOracle(EulerOracle):
+    def setup_convection(self, T, U, bcs: dict, problem_init: str = "NONE", end_step: int = 1):
+        self.bcs["T"] = bcs.get("T", [])
+        self.bcs["U"] = bcs.get("U", [])
+        self.T, self.U = T.copy(), U.copy()
+        # MeshField::read_ applies the BCs right after reading (field.h:1562-1565)
+        self.apply_bcs("U", self.U)
+        self.apply_bcs("T", self.T)
+        self.problem_init = problem_init
+        self.end_step = end_step
+        self.scalar0 = float(np.sum((self.T * self.g.cV)[: self.gB]))
+
+    def wind(self, time: float, etime: float):
+        """init_wind_field, LEVEQUE branch (convection.cpp:74-82), on EVERY entry of U (ghost cells carry their owner's coordinates)."""
+        x, y = self.g.cC[:, 0], self.g.cC[:, 1]
+        period = etime
+        ct = libm.cos_(np.array([PI * time / period]))[0]
+        u = libm.pow_(libm.sin_(PI * x), 2.0) * libm.sin_(2 * PI * y) * ct
+        v = -libm.pow_(libm.sin_(PI * y), 2.0) * libm.sin_(2 * PI * x) * ct
+        return np.stack([u, v, np.zeros_like(u)], axis=1)
+
+    def step(self):
+        P = self.p
+        i = self.step_count + 1                                      # Iteration::get_step() inside the loop
+        if self.problem_init == "LEVEQUE":
+            self.U = self.wind(i * P.dt, self.end_step * P.dt)
+        lam = self.cds(vmag(self.U)) / 2
+        fq = self.U * self.T[:, None]
+        r = self.divf(fq, self.T, lam)
+        ap0 = (-1.0 / P.dt) * self.g.cV
+        Su = (r + self.T * ap0) if P.time_scheme.startswith("BDF") else (self.T * ap0 + r)
+        T = Su / ap0
+        self.apply_bcs("T", T)
+        self.T = T
+        self.step_count += 1

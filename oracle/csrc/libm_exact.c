@@ -17,3 +17,6 @@ void nsem_or_exp(const double* x, double* out, size_t n) {
 void nsem_or_cos(const double* x, double* out, size_t n) {
     for (size_t i = 0; i < n; i++) out[i] = cos(x[i]);
 }
+void nsem_or_sin(const double* x, double* out, size_t n) {
+    for (size_t i = 0; i < n; i++) out[i] = sin(x[i]);
+}

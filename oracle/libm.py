@@ -26,7 +26,7 @@ def _get():
         _lib = ctypes.CDLL(_SO)
         dp = ctypes.POINTER(ctypes.c_double)
         _lib.nsem_or_pow.argtypes = [dp, ctypes.c_double, dp, ctypes.c_size_t]
-        for n in ("nsem_or_sqrt", "nsem_or_exp", "nsem_or_cos"):
+        for n in ("nsem_or_sqrt", "nsem_or_exp", "nsem_or_cos", "nsem_or_sin"):
             getattr(_lib, n).argtypes = [dp, dp, ctypes.c_size_t]
     return _lib
 
@@ -59,3 +59,7 @@ def exp_(x):
 
 def cos_(x):
     return _unary("nsem_or_cos", x)
+
+
+def sin_(x):
+    return _unary("nsem_or_sin", x)

@@ -1,0 +1,103 @@
+"""Explicit scalar advection on the device (-m gpu): nsem_convection_step against the dump of the UNMODIFIED reference
+binary oracle/_ref/parity/convection on examples/atmo/advection-leveque (tests/golden/convection/, made by make_convection_golden.py:
+2-D order 4, 256 elements, LeVeque's deformational wind re-evaluated every step, RUSANOV, AB1, 40 steps) and against the oracle's
+restatement (oracle/convection.py, bit-identical to that dump on the CPU: tests/test_oracle_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import case as ocase
+from tests.helpers import rel_l2
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "convection", "advection-leveque")
+
+
+def device_from_convection_oracle(orc, device=0):
+    """An nsem context holding the oracle's mesh, the scalar in the rho slot (its boundary conditions under rho), the wind in U."""
+    from nebulasem_b200 import capi
+    g, b, t = orc.g, orc.g.basis, orc.g.topo
+    ctx = capi.Context(device)
+    ctx.set_order(b.NPX, b.NPY, b.NPZ)
+    ctx.set_basis(b.dpsi, b.wgl)
+    face_id = np.concatenate([np.asarray(x, dtype=np.uint32) for x in t.faceID])
+    ctx.upload_mesh(n_cells_real=g.nBCS, n_cells_all=g.nCells, n_faces=g.nFacets, cV=g.cV, Jinv=g.Jinv, fN=g.fN, fI=g.fI,
+                    face_normal=t.FNv, FO=g.FO, FN=g.FN, face_begin=g.faceIndices[0], face_end=g.faceIndices[1],
+                    all_faces=g.allFaces, face_id=face_id, face_owner=t.FOC, face_neigh=t.FNC, face_mortar=t.FMC,
+                    cC=g.cC, face_center=t.FC, psi_ref=b.psiRef, psi_cor=b.psiCor)
+    bcs = []
+    for dev_field, orc_field in (("rho", "T"), ("p", "T"), ("U", "U"), ("T", "T")):
+        for bc in orc.bcs[orc_field]:
+            d = dict(field=dev_field, kind=bc.kind, faces=bc.faces, value=bc.value, shape=bc.shape,
+                     tvalue=bc.tvalue if bc.tvalue is not None else 0.0, tshape=bc.tshape, zMin=bc.zMin)
+            if bc.kind == "CYCLIC":
+                d["peer_faces"] = bc.neighbor_faces
+            bcs.append(d)
+    ctx.set_bcs(bcs)
+    p = orc.p
+    ctx.set_params(P0=p.P0, T0=p.T0, cp=p.cp, cv=p.cv, viscosity=0.0, Pr=p.Pr, gravity=(0.0, 0.0, 0.0), dt=p.dt, buoyancy=False, diffusion=False)
+    zeros = np.zeros(orc.gA)
+    ctx.upload_ref(zeros, zeros, None)
+    ctx.upload_state(orc.T, orc.U, zeros, zeros)
+    ctx.upload_coords(g.cC)
+    ctx.set_convection(orc.problem_init, orc.end_step * p.dt, 1)
+    return ctx
+
+
+def test_oracle_convection_is_bit_identical_to_the_reference_binary():
+    exp = np.load(os.path.join(GOLD, "expected.npz"))
+    orc = ocase.load_convection_case(GOLD, exact_order=True)
+    orc.run(int(exp["nsteps"]))
+    nb = orc.gB
+    assert np.array_equal(orc.T[:nb], exp["T"]) and np.array_equal(orc.U[:nb], exp["U"])
+
+
+@pytest.mark.gpu
+def test_device_convection_matches_the_reference_binary():
+    exp = np.load(os.path.join(GOLD, "expected.npz"))
+    nsteps = int(exp["nsteps"])
+    orc = ocase.load_convection_case(GOLD, exact_order=False)
+    ctx = device_from_convection_oracle(orc)
+    n0 = ctx.launch_count
+    ctx.convection_step(nsteps)
+    T, U, _, _ = ctx.download_state()
+    launches = ctx.launch_count - n0
+    info = ctx.kernel_info
+    ctx.close()
+    nb = orc.gB
+    err_T = rel_l2(T[:nb], exp["T"])
+    err_U = np.abs(U[:nb] - exp["U"]).max()
+    mass = float(((T[:nb] - exp["T"]) * orc.g.cV[:nb]).sum() / (exp["T"] * orc.g.cV[:nb]).sum())
+    print(info, "launches", launches, "scalar rel L2 vs the reference:", err_T, "wind max abs diff:", err_U, "scalar integral diff:", mass)
+    assert launches >= 3 * nsteps                                  # wind + speed + sweep (+ ghost update) every step
+    assert np.isfinite(T).all() and err_T <= 1e-11 and err_U <= 1e-13 and abs(mass) <= 1e-13
+    orc.run(nsteps)
+    assert rel_l2(T[:nb], orc.T[:nb]) <= 1e-11
+
+
+@pytest.mark.gpu
+def test_device_convection_3d_frozen_wind_matches_oracle(tmp_path):
+    """The same operator through the persistent 3-D sweeps (order 4, 27 elements, problem_init NONE: the wind is the uploaded field, a
+    smooth rotation about the vertical axis with shear), against the oracle."""
+    from oracle import cases as ocases
+    from oracle.convection import ConvectionOracle
+    from oracle.case import load_case
+    d = str(tmp_path / "box")
+    ocases.CASES["bubble3d"](n=3, order=4).write(d, 10)
+    e = load_case(d, exact_order=False)                               # geometry, boundary patches, dt of the euler case
+    orc = ConvectionOracle(e.g, e.p, exact_order=False)
+    x = (e.g.cC - e.g.cC[:orc.gB].min(axis=0)) / np.ptp(e.g.cC[:orc.gB], axis=0)
+    U = 40.0 * np.stack([-(x[:, 1] - 0.5) * (1 + 0.3 * x[:, 2]), (x[:, 0] - 0.5) * (1 + 0.3 * x[:, 2]), 0.2 * np.sin(2 * np.pi * x[:, 0])], axis=1)
+    r = np.linalg.norm(x - np.array([0.5, 0.3, 0.5]), axis=1) / 0.3
+    T = np.where(r < 1, 0.5 * (1 + np.cos(np.pi * r)), 0.0)
+    orc.setup_convection(T, U, {"T": e.bcs["T"], "U": e.bcs["U"]}, "NONE", 10)
+    ctx = device_from_convection_oracle(orc)
+    ctx.convection_step(10)
+    Td, Ud, _, _ = ctx.download_state()
+    info = ctx.kernel_info
+    ctx.close()
+    orc.run(10)
+    nb = orc.gB
+    err = rel_l2(Td[:nb], orc.T[:nb])
+    print(info, "3-D frozen wind, 10 steps, scalar rel L2 vs the oracle:", err, "scalar moved by", rel_l2(orc.T[:nb], T[:nb]))
+    assert info.startswith("v4") and err <= 1e-11 and rel_l2(orc.T[:nb], T[:nb]) > 1e-3
