@@ -220,6 +220,11 @@ struct nsem_ctx {
     struct Remote { void* base = nullptr; bool ipc = false; uint64_t nRecv = 0, offForMe = 0; uint32_t myIdx = 0; };
     std::vector<Remote> remotes;
     unsigned long long haloEpoch[HALO_KINDS] = {0, 0, 0};
+    // halo fused into the persistent sweeps: tables for (kind 0 | 1) x parity, per ghost cell {neighbour, first slot in its window},
+    // schedule with the partition-boundary elements first
+    bool fused = false;
+    DevBuf<HaloFuse> haloFuse;                // [2 kinds][2 parities]
+    DevBuf<uint32_t> haloGhost, schedFused;
     bool overlap = false;                     // NSEM_OVERLAP=1: halo elements first, exchange overlapped with the interior (measured slower)
 };
 
@@ -489,6 +494,7 @@ static void halo_p2p_release(nsem_ctx* c) {
     if (c->winBase) cudaFree(c->winBase);
     c->winBase = nullptr;
     c->p2p = false;
+    c->fused = false;
 }
 
 extern "C" void nsem_destroy(nsem_ctx* c) {
@@ -1441,7 +1447,7 @@ static void fill_bcparams(const nsem_ctx* c, const KParams& P, BCParams& B, int 
     B.S_new = P.S_new;
 }
 
-static int halo_exchange(nsem_ctx* c, double* const* arrays, int nf, cudaStream_t s, int kind);
+static int halo_exchange(nsem_ctx* c, double* const* arrays, int nf, cudaStream_t s, int kind, unsigned long long pushed_epoch);
 
 // non-conforming faces: phase 0 before sweep A (old state), phase 1 before sweep B (rho_new, p', gradients of real cells)
 static cudaError_t launch_mortar(const nsem_ctx* c, const KParams& P, int phase) {
@@ -1498,7 +1504,7 @@ static int one_step_overlapped(nsem_ctx* c) {
         double* arr[14] = {P.rho_new, P.p};
         int nf = 2;
         if (P.visc) { for (int q = 0; q < 9; q++) arr[nf++] = P.GU[q]; for (int q = 0; q < 3; q++) arr[nf++] = P.GT[q]; }
-        if (halo_exchange(c, arr, nf, cs, 0)) return 1;
+        if (halo_exchange(c, arr, nf, cs, 0, 0)) return 1;
     }
     CUDA_TRY(c, cudaEventRecord(c->evCA, cs));
     if (c->nInt) CUDA_TRY(c, launch_sweepA(c, PI));
@@ -1511,7 +1517,7 @@ static int one_step_overlapped(nsem_ctx* c) {
     CUDA_TRY(c, cudaStreamWaitEvent(cs, c->evB, 0));
     {
         double* arr[5] = {P.U_new[0], P.U_new[1], P.U_new[2], P.T_new, P.S_new};
-        if (halo_exchange(c, arr, 5, cs, 1)) return 1;
+        if (halo_exchange(c, arr, 5, cs, 1, 0)) return 1;
     }
     CUDA_TRY(c, cudaEventRecord(c->evCB, cs));
     c->cbPending = true;
@@ -1540,8 +1546,23 @@ static int one_step(nsem_ctx* c, bool timed, double* acc) {
     BCParams B;
     fill_kparams(c, P);
     if (ensure_speed(c)) return 1;
+    // halo fused into the persistent sweeps: they store the partition-boundary values into the neighbours' windows themselves, boundary
+    // elements first, so the transfer runs under the interior elements (the reference's mul() does interior cells while its halo is in
+    // flight too, field.h:2381-2415)
+    const bool fuse = c->fused && c->use_v4 && !c->has_sched && !c->peers.empty();
+    unsigned long long epA = 0, epB = 0;
+    if (fuse) {
+        epA = ++c->haloEpoch[0];
+        epB = ++c->haloEpoch[1];
+        // NSEM_HALO_FIRST=0: mesh order (every CTA reports when it runs out of work; the stores still overlap the sweep, the flags come last)
+        static const bool halo_first = !(std::getenv("NSEM_HALO_FIRST") && std::strcmp(std::getenv("NSEM_HALO_FIRST"), "0") == 0);
+        P.sched = halo_first ? c->schedFused.p : nullptr;
+        P.nHalo = halo_first ? c->nHalo : c->nB;
+        P.haloGhost = c->haloGhost.p;
+    }
     if (timed) cudaEventRecord(c->ev[0], c->stream);
     CUDA_TRY(c, launch_mortar(c, P, 0));
+    if (fuse) { P.halo = c->haloFuse.p + (0 * 2 + (int)(epA & 1ull)); P.haloEpoch = epA; }
     CUDA_TRY(c, launch_sweepA(c, P));
     if (timed) cudaEventRecord(c->ev[1], c->stream);
     fill_bcparams(c, P, B, 0);
@@ -1550,18 +1571,19 @@ static int one_step(nsem_ctx* c, bool timed, double* acc) {
         double* arr[14] = {P.rho_new, P.p};
         int nf = 2;
         if (P.visc) { for (int q = 0; q < 9; q++) arr[nf++] = P.GU[q]; for (int q = 0; q < 3; q++) arr[nf++] = P.GT[q]; }
-        if (halo_exchange(c, arr, nf, c->stream, 0)) return 1;
+        if (halo_exchange(c, arr, nf, c->stream, 0, epA)) return 1;
     }
     CUDA_TRY(c, launch_ghost_trace(c, P));
     if (timed) cudaEventRecord(c->ev[2], c->stream);
     CUDA_TRY(c, launch_mortar(c, P, 1));
+    if (fuse) { P.halo = c->haloFuse.p + (1 * 2 + (int)(epB & 1ull)); P.haloEpoch = epB; }
     CUDA_TRY(c, launch_sweepB(c, P));
     if (timed) cudaEventRecord(c->ev[3], c->stream);
     B.phase = 1;
     CUDA_TRY(c, launch_bc(c, B));
     if (!c->peers.empty()) {
         double* arr[5] = {P.U_new[0], P.U_new[1], P.U_new[2], P.T_new, P.S_new};
-        if (halo_exchange(c, arr, 5, c->stream, 1)) return 1;
+        if (halo_exchange(c, arr, 5, c->stream, 1, epB)) return 1;
     }
     if (timed) cudaEventRecord(c->ev[4], c->stream);
     c->launches += 2 + (c->nG ? 2 : 0) + ((c->nG && (c->use_v4 || c->use_v2)) ? 1 : 0) + (c->nMortarGroups ? 2 : 0);
@@ -1645,7 +1667,7 @@ static int op_run_first_half(nsem_ctx* c, const KParams& P) {
         double* arr[14] = {P.rho_new, P.p};
         int nf = 2;
         if (P.visc) { for (int q = 0; q < 9; q++) arr[nf++] = P.GU[q]; for (int q = 0; q < 3; q++) arr[nf++] = P.GT[q]; }
-        if (halo_exchange(c, arr, nf, c->stream, 0)) return 1;
+        if (halo_exchange(c, arr, nf, c->stream, 0, 0)) return 1;
     }
     return 0;
 }
@@ -1815,7 +1837,7 @@ extern "C" int nsem_convection_step(nsem_ctx* c, int nsteps) {
         c->launches += 1 + (c->nG ? 1 : 0) + (c->nMortarGroups ? 1 : 0);
         if (!c->peers.empty()) {
             double* arr[2] = {P.rho_new, P.p};
-            if (halo_exchange(c, arr, 2, c->stream, 0)) return 1;
+            if (halo_exchange(c, arr, 2, c->stream, 0, 0)) return 1;
         }
         // the new scalar becomes the current one; U, T and S stay where they are
         std::swap(c->rho[0].p, c->rho[1].p);
@@ -1881,6 +1903,48 @@ static int halo_p2p_setup(nsem_ctx* c) {
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     if (ok) c->p2p = !c->peers.empty();
     else halo_p2p_release(c);
+    if (c->p2p) {
+        // tables of the fused variant (the v4 sweeps store into the windows themselves; opt-in, see below)
+        const char* fz = std::getenv("NSEM_HALO_FUSED");
+        std::vector<HaloFuse> hf(4);
+        char* base = static_cast<char*>(c->winBase);
+        for (int kind = 0; kind < 2; kind++)
+            for (int parity = 0; parity < 2; parity++) {
+                HaloFuse& H = hf[kind * 2 + parity];
+                std::memset(&H, 0, sizeof H);
+                H.npeers = np;
+                H.counter = reinterpret_cast<unsigned int*>(base + HALO_KINDS * HALO_MAX_PEERS * 8);
+                for (int p = 0; p < np; p++) {
+                    const nsem_ctx::Remote& rm = c->remotes[p];
+                    char* rb = static_cast<char*>(rm.base);
+                    H.win[p] = reinterpret_cast<double*>(rb + HALO_HEADER_BYTES) + halo_region_offset(kind, parity, rm.nRecv) + rm.offForMe;
+                    H.stride[p] = rm.nRecv;
+                    H.flag[p] = reinterpret_cast<unsigned long long*>(rb) + (size_t)kind * HALO_MAX_PEERS + rm.myIdx;
+                }
+            }
+        std::vector<uint32_t> hg((size_t)c->nG * 2, 0xffffffffu);
+        for (int p = 0; p < np; p++)
+            for (uint32_t j = 0; j < c->peers[p].nf; j++) {
+                hg[(size_t)(c->peers[p].g0 + j) * 2] = (uint32_t)p;
+                hg[(size_t)(c->peers[p].g0 + j) * 2 + 1] = j * (uint32_t)c->GPS;
+            }
+        std::vector<uint32_t> order;
+        {
+            std::vector<uint8_t> isHalo(c->nB, 0);
+            for (const auto& P : c->peers)
+                for (uint32_t j = 0; j < P.nf; j++) isHalo[c->h_bOwner[P.g0 + j]] = 1;
+            for (uint32_t e = 0; e < c->nB; e++) if (isHalo[e]) order.push_back(e);
+            for (uint32_t e = 0; e < c->nB; e++) if (!isHalo[e]) order.push_back(e);
+        }
+        CUDA_TRY(c, c->haloFuse.upload(hf, c->stream));
+        CUDA_TRY(c, c->haloGhost.upload(hg, c->stream));
+        CUDA_TRY(c, c->schedFused.upload(order, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        // measured on 2 B200 (profiles/r2k_halo_fused_vs_push_2gpu.log): the fused variant is bit-identical but 5-8 % SLOWER than the two
+        // small kernels (the boundary-first schedule costs the sweeps their streaming order, the strided remote stores ride on their
+        // critical path, and the transfer it hides is only 0.06 ms), so it is opt-in: NSEM_HALO_FUSED=1
+        c->fused = (fz && std::strcmp(fz, "1") == 0);
+    }
 #endif
     return 0;
 }
@@ -1960,13 +2024,14 @@ extern "C" int nsem_set_halo(nsem_ctx* c, const nsem_halo_peer* peers, uint32_t 
 
 // pack the owner-side face values of `nf` arrays and exchange them with every peer on stream `s`:
 // send from the packed buffer, receive straight into the ghost region [ghostBase + g0*GPS, +nf*GPS) of each array
-static int halo_exchange(nsem_ctx* c, double* const* arrays, int nf, cudaStream_t s, int kind) {
+static int halo_exchange(nsem_ctx* c, double* const* arrays, int nf, cudaStream_t s, int kind, unsigned long long pushed_epoch) {
     if (c->peers.empty()) return 0;
     if (nf > 16 || nf > halo_kind_fields(kind)) { c->err = "halo_exchange: too many fields"; return 1; }
     if (c->p2p) {
         // two kernels: stores into the neighbours' windows over NVLink + flags, then wait for the neighbours' flags and fill the ghost cells
+        // (pushed_epoch != 0: the sweep that produced the arrays has already stored and flagged them, only the second kernel runs)
         const int np = (int)c->peers.size();
-        const unsigned long long epoch = ++c->haloEpoch[kind];
+        const unsigned long long epoch = pushed_epoch ? pushed_epoch : ++c->haloEpoch[kind];
         const int parity = (int)(epoch & 1ull);
         char* base = static_cast<char*>(c->winBase);
         HaloPushParams H;
@@ -1992,9 +2057,9 @@ static int halo_exchange(nsem_ctx* c, double* const* arrays, int nf, cudaStream_
             R.ghostOff[p] = (uint64_t)c->peers[p].g0 * c->GPS;
         }
         H.off[np] = R.off[np] = c->nSendSlots;
-        halo_push_kernel<<<(unsigned)((H.nslots + 255) / 256), 256, 0, s>>>(H);
+        if (!pushed_epoch) { halo_push_kernel<<<(unsigned)((H.nslots + 255) / 256), 256, 0, s>>>(H); c->launches++; }
         halo_pull_kernel<<<(unsigned)((R.nslots + 255) / 256), 256, 0, s>>>(R);
-        c->launches += 2;
+        c->launches++;
         CUDA_TRY(c, cudaGetLastError());
         return 0;
     }
@@ -2032,7 +2097,7 @@ extern "C" int nsem_exchange_state_halos(nsem_ctx* c) {
     CUDA_TRY(c, cudaSetDevice(c->device));
     const int k = c->cur;
     double* arr[8] = {c->rho[k].p, c->U[k][0].p, c->U[k][1].p, c->U[k][2].p, c->T[k].p, c->p.p, c->rho_ref.p, c->p_ref.p};
-    if (halo_exchange(c, arr, 8, c->stream, 2)) return 1;
+    if (halo_exchange(c, arr, 8, c->stream, 2, 0)) return 1;
     c->speed_valid = false;
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return 0;

@@ -47,6 +47,15 @@ constexpr int MORTAR_MAXF = 64;                // face-node stride of a mortar b
 
 struct FaceRec;
 struct ElemRec;
+// Halo fused into the sweeps (nsem_halo.cuh): where the persistent sweeps store the face values of their partition-boundary nodes --
+// straight into the neighbours' receive windows over NVLink -- and how the last CTA past its boundary elements publishes the epoch.
+struct HaloFuse {
+    double* win[32];                 // neighbour's region (kind, parity), at the slot where this rank's block starts
+    uint64_t stride[32];             // doubles between two fields there
+    unsigned long long* flag[32];    // neighbour's arrival flag for (kind, this rank)
+    unsigned int* counter;           // local: CTAs that are past their boundary elements
+    int npeers;
+};
 struct KParams {
     // sizes
     uint32_t nB;                 // real elements
@@ -63,6 +72,13 @@ struct KParams {
     // [elem*6 + local face][NPF], in the owner's frame
     int op_mode;
     double* op_flux;
+    // halo fused into the v4 sweeps (null = the separate halo_push_kernel does it): table for this exchange, its epoch, per ghost cell
+    // {neighbour index or 0xffffffff, first slot of the cell in the neighbour's window}, and the number of leading schedule positions
+    // that hold the partition-boundary elements (the CTAs report once they are past them)
+    const HaloFuse* halo;
+    unsigned long long haloEpoch;
+    const uint32_t* haloGhost;
+    uint32_t nHalo;
     uint32_t run;                // v4 sweep A: consecutive schedule positions one CTA handles in a row (RunIter); 0/1 = grid-stride order
     int probe;                   // diagnostics only (NSEM_PROBE): 1 = stream the inputs and skip the arithmetic, 2 = also skip the gathers
     // basis

@@ -169,6 +169,22 @@ struct RunIter {
     }
 };
 
+// Halo fused into the sweep: every CTA reports ONCE, when it is past the partition-boundary elements (they come first in the schedule) or
+// has run out of work; the last one to report publishes the exchange's epoch in the neighbours' flag words.  All threads call it.
+__device__ __forceinline__ void halo_report(const KParams& P) {
+    __syncthreads();                                   // every thread's stores into the neighbours' windows have been issued
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const HaloFuse* H = P.halo;
+        if (atomicAdd(H->counter, 1u) == gridDim.x - 1) {
+            *H->counter = 0;
+            __threadfence_system();
+            for (int p = 0; p < H->npeers; p++)
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(H->flag[p]), "l"(P.haloEpoch) : "memory");
+        }
+    }
+}
+
 // MORTAR: the mesh has non-conforming faces (FM_MORTAR): such a face takes its finished surface terms from the mortar buffers
 // (nsem_mortar.cuh) instead of a two-point flux.  A separate instantiation, so conforming meshes run exactly the code they ran before.
 template <int NX, int NY, int NZ, bool VISC, bool TRI, int MINB, bool MORTAR = false>
@@ -190,7 +206,10 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
     const int tid = threadIdx.x;
     const uint32_t run = P.run ? P.run : 1u;
     RunIter cur = RunIter::first(P.nB, run);
-    if (!cur.valid) return;
+    if (!cur.valid) {
+        if (P.halo) halo_report(P);        // a CTA without work still counts
+        return;
+    }
     const int iss = ((tid & 31) == 31 && (tid >> 5) < NISS) ? (tid >> 5) : -1;
 
     auto elem_of = [&](uint32_t q) -> uint32_t { return P.sched ? P.sched[q] : q; };
@@ -255,7 +274,9 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
 
     int st = 0, rs = 0;                    // stage (= gather table) / record slot of the current element
     uint32_t it = 0;
+    bool reported = (P.halo == nullptr);
     for (;;) {
+        if (!reported && cur.pos() >= P.nHalo) { halo_report(P); reported = true; }
         const uint32_t elem = elem_of(cur.pos());
         const RunIter nx2 = nx1.next(P.nB, run);
         const bool hasNext = nx1.valid;
@@ -409,6 +430,30 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
 #pragma unroll
                 for (int c = 0; c < 3; c++) { gT[c] *= rcV; P.GT[c][idx] = gT[c]; }
             }
+            // ---- partition boundary: this node's values go straight into the neighbour's receive window (NVLink stores) ----
+            if (P.halo && onAny) {
+#pragma unroll
+                for (int ax = 0; ax < 3; ax++) {
+                    const bool on = (ax == 0) ? onK : (ax == 1 ? onJ : onI);
+                    if (!on) continue;
+                    const int cx = (ax == 0) ? k : (ax == 1 ? j : i);
+                    const FaceRec* fr = reinterpret_cast<const FaceRec*>(rec) + (2 * ax + (cx != 0 ? 1 : 0));
+                    if ((fr->meta & FM_FID_MASK) != FM_GHOST || (MORTAR && (fr->meta & FM_MORTAR))) continue;
+                    const uint32_t g = (uint32_t)((fr->other - P.ghostBase) / Dims<NX, NY, NZ>::GPS);
+                    const uint32_t peer = P.haloGhost[2 * g];
+                    if (peer == 0xffffffffu) continue;
+                    const int slot = (ax == 0) ? i * NY + j : (ax == 1 ? i * NZ + k : j * NZ + k);
+                    double* w = P.halo->win[peer] + P.haloGhost[2 * g + 1] + slot;
+                    const uint64_t hs = P.halo->stride[peer];
+                    w[0] = rho_new; w[hs] = ppn;
+                    if (VISC) {
+#pragma unroll
+                        for (int c = 0; c < 9; c++) w[(2 + c) * hs] = gU[c];
+#pragma unroll
+                        for (int c = 0; c < 3; c++) w[(11 + c) * hs] = gT[c];
+                    }
+                }
+            }
             // ---- this side's face traces for sweep B of the neighbours (and of the peers behind a partition boundary) ----
             if (onAny) {
                 SideState q;
@@ -454,6 +499,7 @@ __global__ void __launch_bounds__((CfgA<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
         it++;
     }
     if (iss == NISS - 1) bulk_wait0();
+    if (!reported) halo_report(P);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -507,7 +553,10 @@ __global__ void __launch_bounds__((CfgB<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
     const int tid = threadIdx.x;
     const uint32_t stride = gridDim.x;
     uint32_t seq = blockIdx.x;
-    if (seq >= P.nB) return;
+    if (seq >= P.nB) {
+        if (P.halo) halo_report(P);
+        return;
+    }
     // issuing threads: lane 31 of the first NISS warps, each owning every NISS-th bulk copy
     const int iss = ((tid & 31) == 31 && (tid >> 5) < NISS) ? (tid >> 5) : -1;
 
@@ -554,7 +603,9 @@ __global__ void __launch_bounds__((CfgB<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
 
     int st = 0, rs = 0;
     uint32_t it = 0;
+    bool reported = (P.halo == nullptr);
     for (;;) {
+        if (!reported && seq >= P.nHalo) { halo_report(P); reported = true; }
         const uint32_t elem = elem_of(seq);
         const uint32_t nxt = seq + stride, nxt2 = nxt + stride;
         const bool hasNext = nxt < P.nB;
@@ -708,7 +759,27 @@ __global__ void __launch_bounds__((CfgB<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
                 const double Tn = (P.op_mode & 1) ? r[3] : Su * rap - P.T0;
                 P.T_new[idx] = Tn;
                 // |U| + c of the new state, from the values as stored (every other producer of S reads them back from memory)
-                P.S_new[idx] = side_speed(un, Tn + P.T0, P.gamma * P.R);
+                const double Sn = side_speed(un, Tn + P.T0, P.gamma * P.R);
+                P.S_new[idx] = Sn;
+                // ---- partition boundary: U, T, S of this node into the neighbour's receive window ----
+                if (P.halo) {
+                    const bool onK = (k == 0 || k == NZ - 1), onJ = (j == 0 || j == NY - 1), onI = (i == 0 || i == NX - 1);
+#pragma unroll
+                    for (int ax = 0; ax < 3; ax++) {
+                        const bool on = (ax == 0) ? onK : (ax == 1 ? onJ : onI);
+                        if (!on) continue;
+                        const int cx = (ax == 0) ? k : (ax == 1 ? j : i);
+                        const FaceRec* fr = reinterpret_cast<const FaceRec*>(rec) + (2 * ax + (cx != 0 ? 1 : 0));
+                        if ((fr->meta & FM_FID_MASK) != FM_GHOST || (MORTAR && (fr->meta & FM_MORTAR))) continue;
+                        const uint32_t g = (uint32_t)((fr->other - P.ghostBase) / Dims<NX, NY, NZ>::GPS);
+                        const uint32_t peer = P.haloGhost[2 * g];
+                        if (peer == 0xffffffffu) continue;
+                        const int slot = (ax == 0) ? i * NY + j : (ax == 1 ? i * NZ + k : j * NZ + k);
+                        double* w = P.halo->win[peer] + P.haloGhost[2 * g + 1] + slot;
+                        const uint64_t hs = P.halo->stride[peer];
+                        w[0] = un[0]; w[hs] = un[1]; w[2 * hs] = un[2]; w[3 * hs] = Tn; w[4 * hs] = Sn;
+                    }
+                }
             }
         }
         fence_async_smem();                    // the in-place fluxes (generic writes) precede the next bulk copies into this stage
@@ -719,6 +790,7 @@ __global__ void __launch_bounds__((CfgB<NX, NY, NZ, VISC, TRI>::NT), MINB) sweep
         rs = rs1;
         it++;
     }
+    if (!reported) halo_report(P);
 }
 
 }  // namespace v4
