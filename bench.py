@@ -427,6 +427,15 @@ def main():
     pk_steps = max(2, steps // 2)
     ms_pk_total, pk = s.time_steps(pk_steps, per_kernel=True)
     barrier()
+    per_rank = None
+    if world > 1:
+        # every rank's own kernel times (sweep A, ghost update + halo, sweep B, ghost update + halo; ms per step) and element count: the step
+        # is paced by the slowest partition twice per step (one halo after each sweep)
+        mine = torch.tensor([pk[0] / pk_steps, pk[1] / pk_steps, pk[2] / pk_steps, pk[3] / pk_steps, float(s.nBCS), float(s.nCells - s.nBCS)],
+                            dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [[round(float(v), 4) for v in t.tolist()] for t in allr]
     value = 5.0 * nodes * steps / (ms * 1e-3)
 
     # finite-state sanity after all those steps (a diverged run would be a meaningless number)
@@ -530,6 +539,8 @@ def main():
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "setup_s": t_setup}
     if mp_parity is not None:
         line["mp_parity"] = mp_parity
+    if per_rank is not None:
+        line["per_rank"] = {"columns": ["sweepA_ms", "bcA_halo_ms", "sweepB_ms", "bcB_halo_ms", "elements", "ghost_cells"], "rows": per_rank}
     print(json.dumps(line), flush=True)
     s.close()
     if world > 1:

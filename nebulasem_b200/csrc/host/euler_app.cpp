@@ -149,6 +149,19 @@ void EulerSolver::set_mesh_partition(const Grid& global, int rank_, int nranks_,
     const bool amr = std::any_of(fmc.begin(), fmc.end(), [](u32 v) { return v != 0; });
     const std::vector<u32> part = partition_cells(global, nranks, type, nxyz, amr ? &fmc : nullptr);
     lap("partition_cells");
+    if (verbose && rank == 0) {
+        // quality of the partition: cells and cut faces per part (the step time follows the largest of both)
+        std::vector<uint64_t> cells(nranks, 0), cut(nranks, 0);
+        for (u32 c = 0; c < global.nCells(); c++) cells[part[c]]++;
+        std::vector<u32> owner(global.nFacets(), MAX_INT);
+        for (u32 c = 0; c < global.nCells(); c++)
+            for (u32 q = global.cellStart[c]; q < global.cellStart[c + 1]; q++) {
+                const u32 f = global.cellFaces[q];
+                if (owner[f] == MAX_INT) owner[f] = c;
+                else if (part[owner[f]] != part[c]) { cut[part[owner[f]]]++; cut[part[c]]++; }
+            }
+        for (int r = 0; r < nranks; r++) std::printf("decompose: part %d: %llu cells, %llu cut faces\n", r, (unsigned long long)cells[r], (unsigned long long)cut[r]);
+    }
     Partition P = extract_partition(global, part, rank, nranks);
     lap("extract_partition");
     if (P.cellGlobal.empty()) throw Error("partition " + std::to_string(rank) + " is empty");
