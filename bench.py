@@ -411,6 +411,18 @@ def main():
     ms, _ = s.time_steps(steps, per_kernel=False)
     barrier()
     clocks = sampler.stop()
+    clocks_per_rank = None
+    if world > 1:
+        # every rank samples ITS GPU during the timed region: the job is paced by the slowest partition twice per step, so one GPU that the
+        # board's power management holds below the others shows up as lost scaling efficiency
+        smp = sorted(x[0] for x in sampler.samples) or [0.0]
+        pw = [x[2] for x in sampler.samples if x[2] == x[2]] or [0.0]
+        capped = sum(1 for x in sampler.samples if "sw_power_cap" in x[3])
+        mine = torch.tensor([smp[len(smp) // 2], smp[0], max(pw), capped / max(1, len(sampler.samples))], dtype=torch.float64, device="cuda")
+        allc = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allc, mine)
+        clocks_per_rank = {"columns": ["sm_mhz_median", "sm_mhz_min", "power_w_max", "fraction_of_samples_power_capped"],
+                           "rows": [[round(float(v), 3) for v in t.tolist()] for t in allc]}
     launches = s.launch_count - launches0
     if world > 1:
         config["halo"] = s.halo_info
@@ -539,6 +551,8 @@ def main():
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "setup_s": t_setup}
     if mp_parity is not None:
         line["mp_parity"] = mp_parity
+    if clocks_per_rank is not None:
+        line["clocks_per_rank"] = clocks_per_rank
     if per_rank is not None:
         line["per_rank"] = {"columns": ["sweepA_ms", "bcA_halo_ms", "sweepB_ms", "bcB_halo_ms", "elements", "ghost_cells"], "rows": per_rank}
     print(json.dumps(line), flush=True)

@@ -60,6 +60,11 @@ def build_host(force: bool = False) -> str:
         cmd = [CXX, *HOST_FLAGS, main, "-o", EULER_BIN, "-L" + LIBDIR, "-lnsem_host", "-lnsem_cuda", "-Wl,-rpath,$ORIGIN"]
         print("[nebulasem_b200.build]", " ".join(cmd), flush=True)
         subprocess.check_call(cmd)
+    # the same program under the reference's other app name on this path (apps/convection): the solver is chosen by the controls file
+    conv = os.path.join(LIBDIR, "convection")
+    if force or not _newer(conv, [EULER_BIN]):
+        import shutil
+        shutil.copy2(EULER_BIN, conv)
     return HOST_LIB
 
 

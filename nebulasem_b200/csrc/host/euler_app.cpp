@@ -39,7 +39,13 @@ void EulerSolver::read_controls(const std::string& case_dir) {
     dir = case_dir;
     ctl = Controls::read(dir + "/controls");
     const std::string solver = ctl.str("general", "solver", "euler");
-    if (solver != "euler") throw Error("Incorrect solver euler used instead of " + solver + ".");   // wrapper.cpp:32-38
+    if (solver != "euler" && solver != "convection") throw Error("Incorrect solver euler used instead of " + solver + ".");   // wrapper.cpp:32-38
+    convection = (solver == "convection");
+    if (convection) {
+        conv_init = ctl.str("convection", "problem_init", "NONE");          // convection.cpp:26-29
+        if (conv_init != "NONE" && conv_init != "LEVEQUE")
+            throw Error("convection{problem_init " + conv_init + "}: the Lauritzen winds need a spherical mesh, which is not on the GPU path");
+    }
     meshName = ctl.str("general", "mesh", "grid");
     nop[0] = (int)ctl.integer("general", "npx", 0);
     nop[1] = (int)ctl.integer("general", "npy", 0);
@@ -355,6 +361,20 @@ static FieldFile localize(FieldFile ff, const std::vector<u32>& cellGlobal, u32 
 
 void EulerSolver::read_fields(int step) {
     const std::string s = std::to_string(step);
+    if (convection) {
+        // VectorCellField U("U"), ScalarCellField T("T") (convection.cpp:39-40); the scalar takes the rho slot, the other two stay zero
+        FieldFile fU = read_field(dir + "/U" + s, 3), fT = read_field(dir + "/T" + s, 1);
+        if (nranks > 1) {
+            const int NP = Basis(nop).NP;
+            fU = localize(fU, cellGlobal, nGlobalCells, NP); fT = localize(fT, cellGlobal, nGlobalCells, NP);
+        }
+        FieldFile zero;
+        zero.comps = 1;
+        zero.inits.push_back({"uniform", std::vector<double>(1, 0.0)});
+        zero.bcs = fT.bcs;
+        set_fields(fT, fU, zero, zero);
+        return;
+    }
     FieldFile frho = read_field(dir + "/rho" + s, 1), fU = read_field(dir + "/U" + s, 3), fT = read_field(dir + "/T" + s, 1),
               fp = read_field(dir + "/p" + s, 1);
     if (nranks > 1) {
@@ -377,6 +397,15 @@ static std::vector<BCond> scale_bcs(const std::vector<BCond>& src) {
 }
 
 void EulerSolver::setup() {
+    if (convection) {
+        // nothing of the euler set-up applies (convection.cpp:89-111): no reference state, no gravity; total scalar for the loss line
+        const uint64_t gA = geo.gALL, gB = geo.gBCSfield;
+        gvec.assign(gA * 3, 0.0); gh.assign(gA, 0.0); rho_ref.assign(gA, 0.0); p_ref.assign(gA, 0.0);
+        buoyancy = false; diffusion = false;
+        scalar0 = 0; volume0 = 0;
+        for (uint64_t i = 0; i < gB; i++) { scalar0 += rho[i] * geo.cV[i]; volume0 += geo.cV[i]; }
+        return;
+    }
     const uint64_t gA = geo.gALL, gB = geo.gBCSfield;
     const double R = cp - cv, gamma = cp / cv;
     if (problem_init == "ISENTROPIC_VORTEX") {        // euler.cpp:80-95
@@ -560,6 +589,10 @@ void EulerSolver::attach_device(int device, int rank, int nranks, const void* ui
         ck(nsem_set_halo(ctx, hp.data(), (u32)hp.size()));
         exchange_setup_halos();
     }
+    if (convection) {
+        ck(nsem_upload_coords(ctx, geo.cC.data()));
+        ck(nsem_set_convection(ctx, conv_init == "LEVEQUE" ? 1 : 0, (double)end_step * dt, write_interval * start_step + 1));
+    }
 }
 
 void EulerSolver::exchange_setup_halos() {
@@ -610,7 +643,7 @@ void EulerSolver::restart_state() {
 }
 void EulerSolver::step(int n) {
     if (!ctx) throw Error("EulerSolver::step: no device attached (there is no CPU fallback)");
-    if (nsem_euler_step(ctx, n)) throw Error(nsem_last_error(ctx));
+    if (convection ? nsem_convection_step(ctx, n) : nsem_euler_step(ctx, n)) throw Error(nsem_last_error(ctx));
 }
 void EulerSolver::download() {
     if (nsem_download_state(ctx, rho.data(), U.data(), T.data(), p.data())) throw Error(nsem_last_error(ctx));
@@ -625,10 +658,15 @@ void EulerSolver::write_fields(int index) {
         ::mkdir(out.c_str(), 0777);
         ::unlink((out + "/cells" + s).c_str());          // a marker of an earlier run must not vouch for files that are being rewritten
     }
-    write_field(out + "/rho" + s, binary_out, 1, rho.data(), n, bc_rho);
-    write_field(out + "/U" + s, binary_out, 3, U.data(), n, bc_U);
-    write_field(out + "/T" + s, binary_out, 1, T.data(), n, bc_T);
-    write_field(out + "/p" + s, binary_out, 1, p.data(), n, bc_p);
+    if (convection) {
+        write_field(out + "/T" + s, binary_out, 1, rho.data(), n, bc_rho);          // the scalar lives in the rho slot
+        write_field(out + "/U" + s, binary_out, 3, U.data(), n, bc_U);
+    } else {
+        write_field(out + "/rho" + s, binary_out, 1, rho.data(), n, bc_rho);
+        write_field(out + "/U" + s, binary_out, 3, U.data(), n, bc_U);
+        write_field(out + "/T" + s, binary_out, 1, T.data(), n, bc_T);
+        write_field(out + "/p" + s, binary_out, 1, p.data(), n, bc_p);
+    }
     if (nranks > 1) {
         // local real cell -> global cell, then the marker rank 0's merge waits for (written last, renamed into place)
         FILE* f = std::fopen((out + "/cells" + s + ".tmp").c_str(), "wb");
@@ -706,7 +744,7 @@ void EulerSolver::merge_fields(int index) {
 void EulerSolver::run() {
     // Iteration (iteration.h:18-84): steps start_step*write_interval+1 .. end_step, dump when i % write_interval == 0
     long i = write_interval * start_step + 1;
-    const bool diag = (nranks == 1 || std::getenv("NSEM_DIAGNOSTICS"));
+    const bool diag = !convection && (nranks == 1 || std::getenv("NSEM_DIAGNOSTICS"));
     double m0 = mass0, e0 = energy0, v0 = volume0;
     if (diag && nranks > 1 && i <= end_step) {          // the set-up's totals are those of this partition: take the global ones from the device
         double dg[6];
@@ -731,6 +769,11 @@ void EulerSolver::run() {
         }
         if (upto % write_interval == 0) {
             download();
+            if (convection && nranks == 1) {             // convection.cpp:139-149
+                double sc = 0;
+                for (uint64_t q = 0; q < geo.gBCSfield; q++) sc += rho[q] * geo.cV[q];
+                std::printf("Time %f\nScalar loss: %.12g Volume loss: %.12g\n", upto * dt, (scalar0 - sc) / scalar0, 0.0);
+            }
             write_fields((int)(upto / write_interval));
             merge_fields((int)(upto / write_interval));
             if (vtk_on_dump) write_vtk((int)(upto / write_interval));

@@ -228,6 +228,11 @@ struct EulerSolver {
     std::vector<double> rho, U, T, p, rho_ref, p_ref, gvec, gh;
     std::vector<BCond> bc_rho, bc_U, bc_T, bc_p, bc_rho_ref, bc_p_ref, bc_g;
     double mass0 = 0, energy0 = 0, volume0 = 0;
+    // `solver convection` (apps/convection/convection.cpp: dT/dt + div(T U) = 0): the transported scalar is kept where the euler solver keeps
+    // rho (members rho / bc_rho, file T<k>), the wind in U; problem_init LEVEQUE re-evaluates the wind on the device at every step
+    bool convection = false;
+    std::string conv_init = "NONE";
+    double scalar0 = 0;
     uint64_t launch_nonce = 0;                  // stamp of this launch on the per-dump markers (euler_main.cpp: share_launch_blob)
 
     nsem_ctx* ctx = nullptr;

@@ -101,3 +101,27 @@ def test_device_convection_3d_frozen_wind_matches_oracle(tmp_path):
     err = rel_l2(Td[:nb], orc.T[:nb])
     print(info, "3-D frozen wind, 10 steps, scalar rel L2 vs the oracle:", err, "scalar moved by", rel_l2(orc.T[:nb], T[:nb]))
     assert info.startswith("v4") and err <= 1e-11 and rel_l2(orc.T[:nb], T[:nb]) > 1e-3
+
+
+@pytest.mark.gpu
+def test_convection_binary_matches_the_reference_binary(tmp_path):
+    """The drop-in app: `convection ./controls` (nebulasem_b200/lib/convection, the same program as lib/euler, the solver chosen by the
+    controls) on the reference's own example files writes the T/U dump the reference binary wrote."""
+    import shutil
+    import subprocess
+
+    from nebulasem_b200 import build
+    from oracle import refio
+    d = str(tmp_path / "advection-leveque")
+    shutil.copytree(GOLD, d)
+    exp = np.load(os.path.join(d, "expected.npz"))
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    r = subprocess.run([os.path.join(os.path.dirname(build.EULER_BIN), "convection"), "./controls"], cwd=d, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-1500:])
+    assert "Scalar loss" in r.stdout
+    T = refio.read_field_values(os.path.join(d, "T1"))[:, 0]
+    U = refio.read_field_values(os.path.join(d, "U1"))
+    n = exp["T"].shape[0]
+    err = rel_l2(T[:n], exp["T"])
+    print("convection binary vs the reference binary, scalar rel L2:", err, r.stdout.strip().splitlines()[-3:])
+    assert err <= 1e-11 and np.abs(U[:n] - exp["U"]).max() <= 1e-13
