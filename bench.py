@@ -408,7 +408,10 @@ def main():
     barrier()
     sampler = ClockSampler(device)
     sampler.start()
+    if world > 1:
+        s.halo_wait_ms()                                     # reset the wait counters
     ms, _ = s.time_steps(steps, per_kernel=False)
+    halo_wait = s.halo_wait_ms() if world > 1 else None      # this rank's time inside the timed region spent waiting for its neighbours
     barrier()
     clocks = sampler.stop()
     clocks_per_rank = None
@@ -418,10 +421,12 @@ def main():
         smp = sorted(x[0] for x in sampler.samples) or [0.0]
         pw = [x[2] for x in sampler.samples if x[2] == x[2]] or [0.0]
         capped = sum(1 for x in sampler.samples if "sw_power_cap" in x[3])
-        mine = torch.tensor([smp[len(smp) // 2], smp[0], max(pw), capped / max(1, len(sampler.samples))], dtype=torch.float64, device="cuda")
+        mine = torch.tensor([smp[len(smp) // 2], smp[0], max(pw), capped / max(1, len(sampler.samples)), halo_wait[0] / steps, halo_wait[1] / steps],
+                            dtype=torch.float64, device="cuda")
         allc = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allc, mine)
-        clocks_per_rank = {"columns": ["sm_mhz_median", "sm_mhz_min", "power_w_max", "fraction_of_samples_power_capped"],
+        clocks_per_rank = {"columns": ["sm_mhz_median", "sm_mhz_min", "power_w_max", "fraction_of_samples_power_capped",
+                                       "wait_for_neighbours_after_A_ms_per_step", "wait_for_neighbours_after_B_ms_per_step"],
                            "rows": [[round(float(v), 3) for v in t.tolist()] for t in allc]}
     launches = s.launch_count - launches0
     if world > 1:

@@ -194,6 +194,8 @@ uint64_t nsem_launch_count(const nsem_ctx* ctx);
 const char* nsem_kernel_info(const nsem_ctx* ctx);
 /* transport of the halo exchange (replaces MP::isend/irecieve/waitall, src/mp/mp.h:117-131): "peer memory ...", "nccl send/recv" or "none" */
 const char* nsem_halo_info(const nsem_ctx* ctx);
+/* diagnostics: ms spent waiting for the neighbours' halo flags since the last call: after sweep A, after sweep B, state exchanges */
+int nsem_halo_wait_ms(nsem_ctx* ctx, double out[3]);
 
 /* ---- adaptive mesh refinement ----------------------------------------------------------------------- */
 /* One regrid as MeshObject::refineMesh (src/mesh/mesh.cpp:2216-2748) reports it and MeshField::refineField

@@ -225,6 +225,7 @@ int nsemh_diagnostics(nsemh_solver* h, double out[9]) {
 uint64_t nsemh_launch_count(nsemh_solver* h) { return (*h->sp).ctx ? nsem_launch_count((*h->sp).ctx) : 0; }
 const char* nsemh_kernel_info(nsemh_solver* h) { return (*h->sp).ctx ? nsem_kernel_info((*h->sp).ctx) : ""; }
 const char* nsemh_halo_info(nsemh_solver* h) { return (*h->sp).ctx ? nsem_halo_info((*h->sp).ctx) : ""; }
+int nsemh_halo_wait_ms(nsemh_solver* h, double out[3]) { GUARD(if (nsem_halo_wait_ms((*h->sp).ctx, out)) throw Error(nsem_last_error((*h->sp).ctx))) }
 int nsemh_set_schedule(nsemh_solver* h, const uint32_t* order, uint32_t n) {
     GUARD(if (nsem_set_schedule((*h->sp).ctx, order, n)) throw Error(nsem_last_error((*h->sp).ctx)))
 }

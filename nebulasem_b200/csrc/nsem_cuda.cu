@@ -1959,6 +1959,22 @@ static int halo_check(nsem_ctx* c) {
     return 0;
 }
 
+// Diagnostics of the peer-memory halo: the time (ms) this rank's compute stream has spent, since the last call, inside halo_pull_kernel
+// waiting for its neighbours' flags -- [0] after sweep A, [1] after sweep B, [2] state exchanges.  It is the skew between partitions
+// (a neighbour that is slower, or started later), not transfer time.  Zeros when the transport is NCCL.
+extern "C" int nsem_halo_wait_ms(nsem_ctx* c, double out[3]) {
+    out[0] = out[1] = out[2] = 0.0;
+    if (!c->p2p) return 0;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    unsigned long long ns[3] = {0, 0, 0};
+    char* w = static_cast<char*>(c->winBase) + HALO_KINDS * HALO_MAX_PEERS * 8 + 16;
+    CUDA_TRY(c, cudaMemcpyAsync(ns, w, sizeof ns, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(w, 0, sizeof ns, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 3; k++) out[k] = (double)ns[k] * 1e-6;
+    return 0;
+}
+
 extern "C" int nsem_set_halo(nsem_ctx* c, const nsem_halo_peer* peers, uint32_t n_peers) {
     if (!c->have_mesh) { c->err = "nsem_set_halo: no mesh"; return 1; }
     CUDA_TRY(c, cudaSetDevice(c->device));
@@ -2045,6 +2061,7 @@ static int halo_exchange(nsem_ctx* c, double* const* arrays, int nf, cudaStream_
         R.win = reinterpret_cast<const double*>(base + HALO_HEADER_BYTES) + halo_region_offset(kind, parity, c->nRecvSlots);
         R.flag = reinterpret_cast<const unsigned long long*>(base) + (size_t)kind * HALO_MAX_PEERS;
         R.error = reinterpret_cast<int*>(base + HALO_KINDS * HALO_MAX_PEERS * 8 + 8);
+        R.wait_ns = reinterpret_cast<unsigned long long*>(base + HALO_KINDS * HALO_MAX_PEERS * 8 + 16) + kind;
         { const char* t = std::getenv("NSEM_HALO_TIMEOUT_S"); R.timeout_ns = (unsigned long long)((t ? std::atof(t) : 30.0) * 1e9); }
         for (int f = 0; f < nf; f++) R.dst[f] = arrays[f];
         for (int p = 0; p < np; p++) {

@@ -95,6 +95,7 @@ struct HaloPullParams {
     unsigned long long epoch;
     unsigned long long timeout_ns;
     int* error;                                     // set when a neighbour never arrived (the host reports it at the next synchronisation)
+    unsigned long long* wait_ns;                    // += the time block 0 spent waiting for the neighbours' flags (diagnostics: nsem_halo_wait_ms)
 };
 
 __global__ void __launch_bounds__(256) halo_pull_kernel(const __grid_constant__ HaloPullParams H) {
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(256) halo_pull_kernel(const __grid_constant__ 
             }
             if (!ok) break;
         }
+        if (blockIdx.x == 0) atomicAdd(H.wait_ns, global_timer_ns() - t0);
     }
     __syncthreads();
     if (!ok) return;

@@ -17,7 +17,7 @@ HOST_LIB_PATH = os.path.join(os.environ.get("NSEM_LIBDIR") or os.path.join(os.pa
 HOST_EXPORTS = ["nsemh_error", "nsemh_close", "nsemh_open_case", "nsemh_synthetic", "nsemh_synthetic_part", "nsemh_patch_faces",
                 "nsemh_peers", "nsemh_diagnostics", "nsemh_attach", "nsemh_step",
                 "nsemh_upload", "nsemh_download", "nsemh_upload_async", "nsemh_download_async", "nsemh_adopt_refined_state", "nsemh_restart_state", "nsemh_regrid", "nsemh_enable_amr", "nsemh_cell_levels", "nsemh_write_amr_grid", "nsemh_write", "nsemh_write_vtk", "nsemh_run", "nsemh_sync", "nsemh_time",
-                "nsemh_launch_count", "nsemh_kernel_info", "nsemh_halo_info", "nsemh_set_schedule", "nsemh_dims", "nsemh_params", "nsemh_f64", "nsemh_u32",
+                "nsemh_launch_count", "nsemh_kernel_info", "nsemh_halo_info", "nsemh_halo_wait_ms", "nsemh_set_schedule", "nsemh_dims", "nsemh_params", "nsemh_f64", "nsemh_u32",
                 "nsemh_state_ptr", "nsemh_totals", "nsemh_partition_grid"]
 _lib = None
 
@@ -66,6 +66,7 @@ def load_host_library() -> C.CDLL:
     lib.nsemh_kernel_info.restype = C.c_char_p
     lib.nsemh_halo_info.argtypes = [vp]
     lib.nsemh_halo_info.restype = C.c_char_p
+    lib.nsemh_halo_wait_ms.argtypes = [vp, C.POINTER(C.c_double)]
     lib.nsemh_set_schedule.argtypes = [vp, C.POINTER(C.c_uint32), C.c_uint32]
     lib.nsemh_dims.argtypes = [vp, C.POINTER(C.c_uint64)]
     lib.nsemh_params.argtypes = [vp, C.POINTER(C.c_double)]
@@ -305,6 +306,12 @@ class Solver:
     @property
     def kernel_info(self) -> str:
         return self.lib.nsemh_kernel_info(self.h).decode()
+
+    def halo_wait_ms(self):
+        """ms this rank's stream waited for its neighbours' halo flags since the last call: (after sweep A, after sweep B, state exchanges)."""
+        out = (C.c_double * 3)()
+        self._ck(self.lib.nsemh_halo_wait_ms(self.h, out))
+        return [float(x) for x in out]
 
     @property
     def halo_info(self) -> str:
