@@ -1399,7 +1399,14 @@ static void fill_kparams(const nsem_ctx* c, KParams& P) {
     P.visc = (q.diffusion && q.viscosity != 0.0) ? 1 : 0;
     P.has_gfield = c->has_gfield ? 1 : 0;
     { const char* pr = std::getenv("NSEM_PROBE"); P.probe = pr ? std::atoi(pr) : 0; }
-    { const char* rn = std::getenv("NSEM_RUN"); P.run = rn ? (uint32_t)std::max(1, std::atoi(rn)) : 1u; }
+    // sweep A walks runs of consecutive elements per CTA (RunIter): on a structured mesh the k-face neighbours are then the CTA's own previous
+    // / next element and their gathered values hit L2 (sweep A's DRAM reads fall from 21 to 11 KB per element; 1 % of the step under the
+    // power cap, profiles/r2_variants.md).  32 per run when every CTA still gets at least four runs, shorter runs on small meshes.
+    {
+        const char* rn = std::getenv("NSEM_RUN");
+        const uint32_t ctas = (uint32_t)c->numSMs * 4u;
+        P.run = rn ? (uint32_t)std::max(1, std::atoi(rn)) : std::min(32u, std::max(1u, c->nB / (4u * ctas)));
+    }
     std::memcpy(P.D, c->D, sizeof P.D);
     std::memcpy(P.W, c->W, sizeof P.W);
     std::memcpy(P.X, c->X, sizeof P.X);
