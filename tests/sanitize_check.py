@@ -2,7 +2,7 @@
     compute-sanitizer --tool memcheck python tests/sanitize_check.py
 Covers: v4 sweeps (conforming 3-D), v4 + mortar kernels (3-D non-conforming), v1 + mortar kernels (2-D non-conforming and 3-D with
 NSEM_MORTAR_V1=1), v1 2-D, the boundary/ghost-trace kernels, upload/download, the pipelined transfers and the AMR field-transfer kernels
-(copy / merge / split + restart pass).  NSEM_SANITIZE_ONLY=amr runs the last group alone."""
+(copy / merge / split + restart pass), the run schedule of sweep A and the scalar-advection mode.  NSEM_SANITIZE_ONLY=amr runs the AMR group alone."""
 import os
 import shutil
 import sys
@@ -67,6 +67,13 @@ def main():
             shutil.copytree(os.path.join(ROOT, "tests", "golden", fixture), c)
             ok &= run(host.Solver.open_case(c), 3, f"{fixture} NSEM_MORTAR_V1={env}")
     ok &= run_amr()
+    # round 2: runs of consecutive elements per CTA (RunIter with run > 1 needs >= 4 runs per CTA: 18^3 elements), S kept with the state,
+    # and the scalar-advection mode of the sweeps with the wind re-evaluated on the device (the reference's own LeVeque example)
+    ok &= run(host.Solver.synthetic("bubble3d", 18, 18, 18, 2), 2, "bubble3d 18^3 order 2 (runs of elements per CTA)")
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "leveque")
+        shutil.copytree(os.path.join(ROOT, "tests", "golden", "convection", "advection-leveque"), c)
+        ok &= run(host.Solver.open_case(c), 3, "convection advection-leveque")
     print("SANITIZE_DONE", "OK" if ok else "NOT FINITE", flush=True)
     sys.exit(0 if ok else 1)
 
