@@ -154,6 +154,9 @@ int nsem_op_halo(nsem_ctx* ctx);
  * problem_init: 0 = NONE (the wind is the uploaded U), 1 = LEVEQUE (the deformational wind of convection.cpp:74-82, re-evaluated on the
  * device before every step at time step * dt with period etime = end_step * dt; needs the node coordinates Mesh::cC). */
 int nsem_upload_coords(nsem_ctx* ctx, const double* cC);
+/* Mesh::sphere_radius (src/mesh/mesh.cpp:32) of a cubed-sphere mesh (general{is_spherical YES}); read by problem_init 2 / 3 =
+ * LAURITZEN_0 / LAURITZEN_1 (convection.cpp:55-72), the deformational winds on the sphere. */
+int nsem_set_sphere(nsem_ctx* ctx, double radius);
 int nsem_set_convection(nsem_ctx* ctx, int problem_init, double etime, long first_step);
 int nsem_convection_step(nsem_ctx* ctx, int nsteps);
 /* Pipelined variants for drivers that stream batches through the device: both only ENQUEUE and return.  The upload copies on a

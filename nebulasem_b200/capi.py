@@ -63,7 +63,7 @@ EXPORTS = ["nsem_create", "nsem_destroy", "nsem_last_error", "nsem_get_unique_id
            "nsem_upload_mesh", "nsem_set_bcs", "nsem_set_halo", "nsem_set_params", "nsem_set_schedule",
            "nsem_pin_host", "nsem_upload_state", "nsem_download_state", "nsem_upload_state_async", "nsem_download_state_async", "nsem_upload_ref", "nsem_upload_geopotential", "nsem_euler_step", "nsem_exchange_state_halos", "nsem_diagnostics",
            "nsem_sync", "nsem_time_steps", "nsem_launch_count", "nsem_kernel_info", "nsem_refine_state", "nsem_restart_state", "nsem_download_gradients",
-           "nsem_op_cds", "nsem_op_rusanov", "nsem_op_gradf_strong", "nsem_op_divf_weak", "nsem_op_apply_bcs", "nsem_op_halo", "nsem_halo_info", "nsem_halo_wait_ms", "nsem_upload_coords", "nsem_set_convection", "nsem_convection_step"]
+           "nsem_op_cds", "nsem_op_rusanov", "nsem_op_gradf_strong", "nsem_op_divf_weak", "nsem_op_apply_bcs", "nsem_op_halo", "nsem_halo_info", "nsem_halo_wait_ms", "nsem_upload_coords", "nsem_set_sphere", "nsem_set_convection", "nsem_convection_step"]
 
 _lib = None
 
@@ -106,6 +106,7 @@ def load_library() -> C.CDLL:
     lib.nsem_halo_info.argtypes = [vp]
     lib.nsem_upload_coords.argtypes = [vp, _dp]
     lib.nsem_set_convection.argtypes = [vp, C.c_int, C.c_double, C.c_long]
+    lib.nsem_set_sphere.argtypes = [vp, C.c_double]
     lib.nsem_convection_step.argtypes = [vp, C.c_int]
     lib.nsem_halo_info.restype = C.c_char_p
     lib.nsem_halo_wait_ms.argtypes = [vp, _dp]
@@ -281,8 +282,12 @@ class Context:
         assert a.size == self.n_ref_nodes * 3
         self._ck(self.lib.nsem_upload_coords(self.h, _pd(a)))
 
+    def set_sphere(self, radius: float):
+        self._ck(self.lib.nsem_set_sphere(self.h, float(radius)))
+
     def set_convection(self, problem_init: str = "NONE", etime: float = 1.0, first_step: int = 1):
-        self._ck(self.lib.nsem_set_convection(self.h, {"NONE": 0, "LEVEQUE": 1}[problem_init], float(etime), int(first_step)))
+        kinds = {"NONE": 0, "LEVEQUE": 1, "LAURITZEN_0": 2, "LAURITZEN_1": 3}
+        self._ck(self.lib.nsem_set_convection(self.h, kinds[problem_init], float(etime), int(first_step)))
 
     def convection_step(self, nsteps=1):
         self._ck(self.lib.nsem_convection_step(self.h, int(nsteps)))

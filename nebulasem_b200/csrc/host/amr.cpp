@@ -653,6 +653,11 @@ static void repair_cyclic_order(Grid& g, const std::vector<std::array<std::strin
 // ---------------------------------------------------------------------------------------------------------
 std::unique_ptr<EulerSolver> EulerSolver::regridded(const std::vector<uint8_t>& refine, const std::vector<uint8_t>& coarsen) {
     if (nranks > 1) throw Error("EulerSolver::regridded: the in-memory regrid runs on one partition (repartitioning a regridded mesh is not built)");
+    for (const std::vector<BCond>* l : {&bc_rho, &bc_U, &bc_T, &bc_p})
+        for (const BCond& b : *l)
+            if (b.held)
+                throw Error("EulerSolver::regridded: patch " + b.patch + " has no boundary condition for one of the fields; the values its boundary "
+                            "cells keep cannot follow an in-memory regrid");
     for (const std::vector<BCond>* l : {&file_bc_rho, &file_bc_U, &file_bc_T, &file_bc_p})
         for (const BCond& b : *l)
         {

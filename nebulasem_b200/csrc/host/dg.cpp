@@ -182,6 +182,7 @@ inline V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
 inline V3 operator-(V3 a) { return {-a.x, -a.y, -a.z}; }
 inline V3 operator*(double s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }   // AddScalarOperators: each component * s
 inline V3 toV(const Vec3& a) { return {a[0], a[1], a[2]}; }
+inline double mag3(V3 a) { return std::sqrt(a.x * a.x + (a.y * a.y + a.z * a.z)); }   // Unroll<3>::dot nests to the right
 
 // tensor.h:522-571, same term order
 inline V3 interp_face(double r, double s, V3 x00, V3 x01, V3 x10, V3 x11, V3 xr0, V3 xr1, V3 x0s, V3 x1s) {
@@ -225,6 +226,7 @@ void Geometry::build(const MeshTopo& t, const Basis& b) {
     nBCS = t.nBCS; nCells = t.nCells(); nFacets = t.nFacets();
     gBCSfield = (uint64_t)nBCS * NP;
     gALL = (uint64_t)nCells * NP;
+    spherical = t.spherical; sphere_radius = t.sphere_radius;
     if (gALL + NP >= 0xffffffffull) throw Error("mesh exceeds the 32-bit node index of the reference layout");
     auto I4 = [&](uint64_t c, int i, int j, int k) { return (u32)(c * NP + (uint64_t)i * NPY * NPZ + j * NPZ + k); };
 
@@ -275,6 +277,7 @@ void Geometry::build(const MeshTopo& t, const Basis& b) {
     // ---- node coordinates (dg.cpp:176-325) ----
     static const int sides[12][2] = {{0, 1}, {3, 2}, {7, 6}, {4, 5}, {0, 3}, {1, 2}, {5, 6}, {4, 7}, {0, 4}, {1, 5}, {2, 6}, {3, 7}};
     std::string corner_error;      // an exception must not leave the parallel region
+    const bool sph = t.spherical;
 #pragma omp parallel for schedule(static)
     for (int64_t cs = 0; cs < (int64_t)nBCS; cs++) {
         const u32 ci = (u32)cs;
@@ -320,6 +323,8 @@ void Geometry::build(const MeshTopo& t, const Basis& b) {
                     for (int w = 0; w < 12; w++) {
                         const double m = (w < 4) ? rx : (w < 8 ? ry : rz);
                         vd[w] = (1 - m) * vp[sides[w][0]] + m * vp[sides[w][1]];
+                        // on the sphere every blended point is pushed back to the blended radius (dg.cpp:257-285)
+                        if (sph) vd[w] = (((1 - m) * mag3(vp[sides[w][0]]) + m * mag3(vp[sides[w][1]])) / mag3(vd[w])) * vd[w];
                     }
                     vf[0] = interp_face(rx, ry, vp[0], vp[3], vp[1], vp[2], vd[0], vd[1], vd[4], vd[5]);
                     vf[1] = interp_face(rx, ry, vp[4], vp[7], vp[5], vp[6], vd[3], vd[2], vd[7], vd[6]);
@@ -327,9 +332,14 @@ void Geometry::build(const MeshTopo& t, const Basis& b) {
                     vf[3] = interp_face(rx, rz, vp[3], vp[7], vp[2], vp[6], vd[1], vd[2], vd[11], vd[10]);
                     vf[4] = interp_face(ry, rz, vp[0], vp[4], vp[3], vp[7], vd[4], vd[7], vd[8], vd[11]);
                     vf[5] = interp_face(ry, rz, vp[1], vp[5], vp[2], vp[6], vd[5], vd[6], vd[9], vd[10]);
-                    const V3 v = interp_cell(rx, ry, rz, vp[0], vp[4], vp[3], vp[7], vp[1], vp[5], vp[2], vp[6], vd[0], vd[3],
+                    if (sph) {
+                        static const int ir0[6] = {0, 3, 0, 1, 4, 5};
+                        for (int w = 0; w < 6; w++) vf[w] = (mag3(vd[ir0[w]]) / mag3(vf[w])) * vf[w];
+                    }
+                    V3 v = interp_cell(rx, ry, rz, vp[0], vp[4], vp[3], vp[7], vp[1], vp[5], vp[2], vp[6], vd[0], vd[3],
                                              vd[1], vd[2], vd[4], vd[7], vd[5], vd[6], vd[8], vd[11], vd[9], vd[10], vf[4],
                                              vf[5], vf[2], vf[3], vf[0], vf[1]);
+                    if (sph) v = (mag3(vd[8]) / mag3(v)) * v;
                     const u32 idx = I4(ci, i, j, k);
                     cC[(size_t)idx * 3 + 0] = v.x; cC[(size_t)idx * 3 + 1] = v.y; cC[(size_t)idx * 3 + 2] = v.z;
                     cV[idx] *= wg[0][i] * wg[1][j] * wg[2][k] / 8;

@@ -43,8 +43,12 @@ void EulerSolver::read_controls(const std::string& case_dir) {
     convection = (solver == "convection");
     if (convection) {
         conv_init = ctl.str("convection", "problem_init", "NONE");          // convection.cpp:26-29
-        if (conv_init != "NONE" && conv_init != "LEVEQUE")
-            throw Error("convection{problem_init " + conv_init + "}: the Lauritzen winds need a spherical mesh, which is not on the GPU path");
+        if (conv_init != "NONE" && conv_init != "LEVEQUE" && conv_init != "LAURITZEN_0" && conv_init != "LAURITZEN_1")
+            throw Error("convection{problem_init " + conv_init + "} is not one of NONE, LEVEQUE, LAURITZEN_0, LAURITZEN_1");
+        const bool sph = ctl.yes("general", "is_spherical", false);
+        // init_wind_field leaves u, v unset in the other combinations (convection.cpp:55-82)
+        if ((conv_init == "LEVEQUE" && sph) || (conv_init.rfind("LAURITZEN", 0) == 0 && !sph))
+            throw Error("convection{problem_init " + conv_init + "} needs general{is_spherical " + (sph ? "NO" : "YES") + "}");
     }
     meshName = ctl.str("general", "mesh", "grid");
     nop[0] = (int)ctl.integer("general", "npx", 0);
@@ -89,7 +93,10 @@ void EulerSolver::read_controls(const std::string& case_dir) {
     const std::string& ts = time_scheme;
     if (!(ts == "BDF1" || ts == "AB1" || ts == "RK1" || ts == "RK2" || ts == "RK3" || ts == "RK4"))
         throw Error("time_scheme " + ts + " is not implemented on the GPU path (BDF1, AB1, RK1-RK4 are)");
-    if (ctl.yes("general", "is_spherical", false)) throw Error("spherical meshes are not implemented on the GPU path");
+    // cubed-sphere shells (field.cpp:516-519): the mesh loader projects the grid onto the sphere, set-up uses radial gravity
+    topo.spherical = ctl.yes("general", "is_spherical", false);
+    topo.sphere_radius = ctl.num("general", "sphere_radius", topo.sphere_radius);
+    topo.sphere_height = ctl.num("general", "sphere_height", topo.sphere_height);
     // AmrIteration (iteration.h:94-147): a regrid before step 1 and after every amr_step dumps; here in memory (amr.cpp), the state stays
     // on the device (nsem_refine_state).  NSEM_IGNORE_AMR_STEP=1 runs on the grid as it is.
     amr_step = std::getenv("NSEM_IGNORE_AMR_STEP") ? 0 : ctl.integer("general", "amr_step", 0);
@@ -100,6 +107,8 @@ void EulerSolver::read_controls(const std::string& case_dir) {
     refine_params.max_level = (int)ctl.integer("refinement", "max_level", refine_params.max_level);
     refine_params.buffer_zone = (int)ctl.integer("refinement", "buffer_zone", refine_params.buffer_zone);
     refine_params.limit = ctl.integer("refinement", "limit", refine_params.limit);
+    if (amr_step != 0 && topo.spherical)
+        throw Error("adaptive regridding of a spherical mesh (field.cpp:638-645,921-924) is not built; set NSEM_IGNORE_AMR_STEP=1 to run on the grid as it is");
     if (amr_step != 0 && nranks > 1)
         throw Error("controls ask for adaptive regridding (amr_step) on " + std::to_string(nranks) + " partitions: the in-memory regrid runs on one "
                     "partition (repartitioning a regridded mesh is not built); run one process or set NSEM_IGNORE_AMR_STEP=1");
@@ -216,6 +225,14 @@ std::vector<double> init_field(const FieldFile& ff, const Geometry& g, const Vec
                 double q[3];
                 for (int d = 0; d < 3; d++) q[d] = (g.cC[i * 3 + d] - center[d]) / radius[d];
                 double R = mag3(q);
+                if (g.spherical) {
+                    // centre given as (radius, latitude, longitude); distance along the great circle (field.h:1441-1444)
+                    const double* x = &g.cC[i * 3];
+                    const double sr = mag3(x), lat = std::atan2(x[2], std::sqrt(x[0] * x[0] + x[1] * x[1])), lon = std::atan2(x[1], x[0]);
+                    double dd = (center[0] + sr) / 2;
+                    dd *= std::acos(std::sin(center[1]) * std::sin(lat) + std::cos(center[1]) * std::cos(lat) * std::cos(center[2] - lon));
+                    R = dd / mag3(radius);
+                }
                 for (int d = 0; d < c; d++) {
                     double val = value[d];
                     if (in.kind == "gaussian") {
@@ -251,7 +268,7 @@ std::vector<double> init_field(const FieldFile& ff, const Geometry& g, const Vec
         } else if (in.kind == "hydrostatic") {
             const double *p0 = a, scale = a[c], expon = a[c + 1];
             for (uint64_t i = 0; i < gA; i++) {
-                const double gh = dot3(&g.cC[i * 3], gravity.data());
+                const double gh = g.spherical ? -(mag3(&g.cC[i * 3]) - g.sphere_radius) * mag3(gravity.data()) : dot3(&g.cC[i * 3], gravity.data());
                 for (int d = 0; d < c; d++) out[i * c + d] += p0[d] * std::pow(1.0 + scale * gh, expon);
             }
         }
@@ -375,14 +392,46 @@ void EulerSolver::read_fields(int step) {
         set_fields(fT, fU, zero, zero);
         return;
     }
-    FieldFile frho = read_field(dir + "/rho" + s, 1), fU = read_field(dir + "/U" + s, 3), fT = read_field(dir + "/T" + s, 1),
-              fp = read_field(dir + "/p" + s, 1);
+    FieldFile frho;
+    struct stat st;
+    if (step != 0 || ::stat((dir + "/rho" + s + ".txt").c_str(), &st) == 0 || ::stat((dir + "/rho" + s + ".bin").c_str(), &st) == 0) {
+        frho = read_field(dir + "/rho" + s, 1);
+    } else {
+        // MeshField::read skips a file that is not there (field.h:1579-1585; examples/atmo/hydro-sphere ships no rho0): the start branch
+        // forms rho from p and T on every entry, boundary cells included, and with no conditions to apply they keep that value for the run.
+        // Only for the initial state: a dump that is not there stays an error
+        frho.comps = 1;
+        frho.inits.push_back({"uniform", std::vector<double>(1, 0.0)});
+    }
+    FieldFile fU = read_field(dir + "/U" + s, 3), fT = read_field(dir + "/T" + s, 1), fp = read_field(dir + "/p" + s, 1);
     if (nranks > 1) {
         const int NP = Basis(nop).NP;
         frho = localize(frho, cellGlobal, nGlobalCells, NP); fU = localize(fU, cellGlobal, nGlobalCells, NP);
         fT = localize(fT, cellGlobal, nGlobalCells, NP); fp = localize(fp, cellGlobal, nGlobalCells, NP);
     }
     set_fields(frho, fU, fT, fp);
+}
+
+void EulerSolver::hold_unlisted_patches(const std::vector<double>& F, int comps, std::vector<BCond>& bcs) {
+    const int NPF = Basis(nop).NPF;
+    for (const auto& kv : topo.boundaries) {
+        if (kv.second.empty() || kv.first.find("interMesh") != std::string::npos) continue;
+        bool listed = false;
+        for (const auto& b : bcs) listed = listed || b.patch == kv.first;
+        if (listed) continue;
+        BCond b;
+        b.patch = kv.first;
+        b.type = "CALC_DIRICHLET";
+        b.held = true;
+        b.fixed.assign(kv.second.size() * (size_t)NPF * comps, 0.0);
+        for (size_t j = 0; j < kv.second.size(); j++)
+            for (int n = 0; n < NPF; n++) {
+                const u32 c2 = geo.FN[(size_t)kv.second[j] * NPF + n];
+                if (c2 >= geo.gALL) continue;
+                for (int d = 0; d < comps; d++) b.fixed[(j * NPF + n) * comps + d] = F[(size_t)c2 * comps + d];
+            }
+        bcs.push_back(std::move(b));
+    }
 }
 
 static std::vector<BCond> scale_bcs(const std::vector<BCond>& src) {
@@ -433,6 +482,12 @@ void EulerSolver::setup() {
     if (buoyancy) {                                    // euler.cpp:105-123
 #pragma omp parallel for schedule(static)
         for (uint64_t i = 0; i < gA; i++) {
+            if (geo.spherical) {                       // gravity points to the centre of the sphere, euler.cpp:109-111
+                const double r = mag3(&geo.cC[i * 3]), mg = mag3(gravity.data());
+                for (int d = 0; d < 3; d++) gvec[i * 3 + d] = -(geo.cC[i * 3 + d] / r) * mg;
+                gh[i] = -(r - geo.sphere_radius) * mg;
+                continue;
+            }
             for (int d = 0; d < 3; d++) gvec[i * 3 + d] = gravity[d];
             gh[i] = dot3(&gvec[i * 3], &geo.cC[i * 3]);
         }
@@ -456,6 +511,12 @@ void EulerSolver::setup() {
     bc_rho_ref = scale_bcs(bc_rho);
     apply_bcs(rho_ref, 1, bc_rho_ref);
     for (uint64_t i = 0; i < gA; i++) p[i] -= p_ref[i];
+    // a boundary patch a field has no condition for keeps the values its boundary cells hold now: on the device (two state buffers) that is
+    // a frozen-value condition
+    hold_unlisted_patches(rho, 1, bc_rho);
+    hold_unlisted_patches(U, 3, bc_U);
+    hold_unlisted_patches(T, 1, bc_T);
+    hold_unlisted_patches(p, 1, bc_p);
     // totals (euler.cpp:164-176)
     mass0 = energy0 = volume0 = 0;
     for (uint64_t i = 0; i < gB; i++) {
@@ -569,7 +630,7 @@ void EulerSolver::attach_device(int device, int rank, int nranks, const void* ui
     for (int d = 0; d < 3; d++) q.gravity[d] = gravity[d];
     q.buoyancy = buoyancy; q.diffusion = diffusion;
     ck(nsem_set_params(ctx, &q));
-    ck(nsem_upload_ref(ctx, rho_ref.data(), p_ref.data(), nullptr));
+    ck(nsem_upload_ref(ctx, rho_ref.data(), p_ref.data(), (geo.spherical && buoyancy) ? gvec.data() : nullptr));
     ck(nsem_upload_geopotential(ctx, gh.data()));
     // the field storage lives as long as the solver: page-lock it once for the per-dump transfers
     for (std::vector<double>* v : {&rho, &U, &T, &p}) nsem_pin_host(ctx, v->data(), v->size() * sizeof(double));
@@ -591,7 +652,9 @@ void EulerSolver::attach_device(int device, int rank, int nranks, const void* ui
     }
     if (convection) {
         ck(nsem_upload_coords(ctx, geo.cC.data()));
-        ck(nsem_set_convection(ctx, conv_init == "LEVEQUE" ? 1 : 0, (double)end_step * dt, write_interval * start_step + 1));
+        if (geo.spherical) ck(nsem_set_sphere(ctx, geo.sphere_radius));
+        const int kind = conv_init == "LEVEQUE" ? 1 : (conv_init == "LAURITZEN_0" ? 2 : (conv_init == "LAURITZEN_1" ? 3 : 0));
+        ck(nsem_set_convection(ctx, kind, (double)end_step * dt, write_interval * start_step + 1));
     }
 }
 

@@ -343,7 +343,10 @@ struct BinOut {
 }  // namespace
 
 void write_field(const std::string& path_noext, bool binary, int comps, const double* v, uint64_t n_nodes,
-                 const std::vector<BCond>& bcs) {
+                 const std::vector<BCond>& all_bcs) {
+    // conditions the set-up added for patches the field file does not list (hold_unlisted_patches) are not part of the file
+    std::vector<BCond> bcs;
+    for (const auto& b : all_bcs) if (!b.held) bcs.push_back(b);
     auto near_zero = [](double x) { return std::fabs(x) <= 1e-7; };
     if (binary) {
         FILE* f = std::fopen((path_noext + ".bin").c_str(), "wb");

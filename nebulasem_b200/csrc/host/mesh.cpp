@@ -458,10 +458,104 @@ void MeshTopo::calc_geometry() {
         CC[i] = divs(C, Vt);
         CV[i] = Vt / 3.0;
     }
+    if (spherical) sphere_geometry();
     for (u32 i = nBCS; i < nc; i++) {
         const u32 fi = cellFaces[cellStart[i]];
         CV[i] = CV[FOC[fi]];
         CC[i] = FC[fi];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// cubed-sphere shells (Mesh::is_spherical): vertices projected onto two radii, then centres, face areas and cell
+// volumes corrected to the curved elements
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+// (radius, latitude, longitude), tensor.h:598-605
+inline Vec3 cart_to_sphere(const Vec3& c) {
+    return Vec3{mag(c), std::atan2(c[2], std::sqrt(c[0] * c[0] + c[1] * c[1])), std::atan2(c[1], c[0])};
+}
+// tensor.h:608-612
+inline double geodesic_distance(const Vec3& s1, const Vec3& s2) {
+    double d = (s1[0] + s2[0]) / 2;
+    d *= std::acos(std::sin(s1[1]) * std::sin(s2[1]) + std::cos(s1[1]) * std::cos(s2[1]) * std::cos(s1[2] - s2[2]));
+    return d;
+}
+// tensor.h:624-635
+inline double spherical_triangle_area(double radius, const Vec3& v0, const Vec3& v1, const Vec3& v2) {
+    const Vec3 a = unit(v0), b = unit(v1), c = unit(v2);
+    double t = std::fabs(dot(a, cross(b, c)));
+    t /= (1 + dot(a, b) + dot(b, c) + dot(a, c));
+    return 2 * std::atan(t) * radius * radius;
+}
+// equal(Scalar, Scalar) with Constants::EqualEpsilon = 1e-7, tensor.h:460-480
+inline bool near(double p, double q) {
+    const double tol = 1e-7, delta = std::fabs(p - q);
+    return delta <= tol || delta <= tol * std::fabs(p) || delta <= tol * std::fabs(q);
+}
+}  // namespace
+
+// Mesh::MeshObject::ExtrudeMesh, mesh.cpp:723-750: the grid file holds a shell between two concentric cubes; the cube a vertex lies on
+// (its largest |coordinate|) picks the radius it is projected to.  The SMALLER cube goes to the OUTER radius, as in the reference.
+void MeshTopo::extrude() {
+    double minh = 1e30, maxh = 0;
+    auto height = [](const Vec3& v) { return std::max(std::max(std::fabs(v[0]), std::fabs(v[1])), std::fabs(v[2])); };
+    for (const Vec3& v : V) {
+        const double h = height(v);
+        if (h > maxh) maxh = h;
+        if (h < minh) minh = h;
+    }
+    const double radiusi = sphere_radius, radiuso = sphere_radius + sphere_height;
+    for (Vec3& v : V) {
+        const double f = (height(v) - minh) / (maxh - minh);
+        v = mul(unit(v), f * radiusi + (1 - f) * radiuso);
+    }
+}
+
+// mesh.cpp:520-570.  Sides 0 and 1 of every cell are its two radial faces (the block mesher's third direction).
+void MeshTopo::sphere_geometry() {
+    for (u32 i = 0; i < nBCS; i++) {
+        const u32* c = &cellFaces[cellStart[i]];
+        if (cellStart[i + 1] - cellStart[i] != 6) throw Error("spherical meshes need conforming hexahedra (cell " + std::to_string(i) + ")");
+        const double radiusb = mag(V[facetVerts[facetStart[c[0]]]]);
+        const double radiust = mag(V[facetVerts[facetStart[c[1]]]]);
+        CC[i] = mul(CC[i], (radiusb + radiust) / (2 * mag(CC[i])));
+        FC[c[0]] = mul(FC[c[0]], radiusb / mag(FC[c[0]]));
+        FC[c[1]] = mul(FC[c[1]], radiust / mag(FC[c[1]]));
+        for (int j = 2; j < 6; j++) {
+            FC[c[j]] = mul(FC[c[j]], (radiusb + radiust) / (2 * mag(FC[c[j]])));
+            // area of a vertical face: half the geodesic length of its outline times the shell thickness
+            double d = 0;
+            const u32 s = facetStart[c[j]], n = facetStart[c[j] + 1] - s;
+            for (u32 k = 0; k < n; k++) {
+                const Vec3& v0 = V[facetVerts[s + k]];
+                const Vec3& v1 = V[facetVerts[s + (k == n - 1 ? 0 : k + 1)]];
+                const Vec3 r0 = unit(v0), r1 = unit(v1);
+                if (near(r0[0], r1[0]) && near(r0[1], r1[1]) && near(r0[2], r1[2])) continue;
+                d += geodesic_distance(cart_to_sphere(v0), cart_to_sphere(v1));
+            }
+            d /= 2;
+            const double area = std::fabs(radiust - radiusb) * d;
+            FN[c[j]] = mul(unit(FN[c[j]]), area);
+        }
+    }
+    for (u32 i = 0; i < nBCS; i++) {
+        const u32* c = &cellFaces[cellStart[i]];
+        double area = 0;
+        for (int k = 0; k < 2; k++) {
+            const u32 s = facetStart[c[k]], n = facetStart[c[k] + 1] - s;
+            const double radius = mag(V[facetVerts[s]]);
+            const Vec3& fc = FC[c[k]];
+            double a = 0;
+            for (u32 j = 0; j < n; j++)
+                a += spherical_triangle_area(radius, V[facetVerts[s + j]], V[facetVerts[s + (j == n - 1 ? 0 : j + 1)]], fc);
+            FN[c[k]] = mul(unit(FN[c[k]]), a);
+            area += a;
+        }
+        area /= 2;
+        const double radiusb = mag(V[facetVerts[facetStart[c[0]]]]);
+        const double radiust = mag(V[facetVerts[facetStart[c[1]]]]);
+        CV[i] = std::fabs(radiust - radiusb) * area;
     }
 }
 
@@ -532,6 +626,7 @@ void MeshTopo::load(const Grid& g) {
     boundaries = g.boundaries;
     add_boundary_cells();
     fix_hex_cells();
+    if (spherical) extrude();
     calc_geometry();
     std::vector<u32> del = boundaries["delete"];
     boundaries.erase("delete");

@@ -102,6 +102,9 @@ struct MeshTopo {
     std::vector<u32> FOC, FNC, FMC;
     std::vector<Vec3> FC, FN, CC;
     std::vector<double> CV;
+    // Mesh::is_spherical / sphere_radius / sphere_height (mesh.cpp:31-33): set before load()
+    bool spherical = false;
+    double sphere_radius = 6371220.0, sphere_height = 10000.0;
     u32 nFacets() const { return (u32)facetStart.size() - 1; }
     u32 nCells() const { return (u32)cellStart.size() - 1; }
     void load(const Grid& g);            // Mesh::LoadMesh
@@ -115,6 +118,8 @@ private:
     void fix_hex_cells();
     void fix_general_cell(u32 ci);       // non-conforming cell: coplanar sub-facets grouped and merged per side
     void calc_geometry();
+    void extrude();                      // ExtrudeMesh: the cube shell of the grid file projected onto the sphere
+    void sphere_geometry();              // curved-element corrections of calcGeometry
     void remove_boundary(const std::vector<u32>& faces);
 };
 
@@ -135,6 +140,8 @@ void lagrange_basis_derivative(int N, const double* xgl, int Ns, const double* x
 struct Geometry {
     u32 nBCS = 0, nCells = 0, nFacets = 0;
     uint64_t gBCSfield = 0, gALL = 0;
+    bool spherical = false;               // copied from the topology by build()
+    double sphere_radius = 0;
     std::vector<double> cC, cV, Jinv, fN, fC, fI, faceNormal, faceCenter;   // AoS like the reference
     std::vector<double> psiRef[6], psiCor[6];                   // copies of the basis tables (only read on non-conforming meshes)
     std::vector<u32> FO, FN, faceBegin, faceEnd, allFaces, faceID, faceOwner, faceNeigh, faceMortar;
@@ -149,6 +156,7 @@ struct BCond {                       // BCondition<T>, field.h:144-173
     double shape = 0, tshape = 0, zMin = 0, zMax = 0;
     Vec3 dir{0, 0, 1};
     std::vector<double> fixed;       // frozen CALC_DIRICHLET values [nfaces*NPF*comps]
+    bool held = false;               // not from the field file: a patch without a condition keeps its set-up values (hold_unlisted_patches)
 };
 struct FieldFile {
     int comps = 1;
@@ -292,6 +300,7 @@ struct EulerSolver {
     void run();                                           // Iteration loop: steps + dumps every write_interval
 
     void apply_bcs(std::vector<double>& f, int comps, std::vector<BCond>& bcs);   // applyExplicitBCs on the host
+    void hold_unlisted_patches(const std::vector<double>& f, int comps, std::vector<BCond>& bcs);
 private:
     std::vector<nsem_bc> c_bcs_;
     std::vector<std::vector<u32>> keep_faces_;

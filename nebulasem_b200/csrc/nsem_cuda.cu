@@ -151,6 +151,7 @@ struct nsem_ctx {
     bool has_gh = false;
     int cur = 0;
     bool has_gfield = false;
+    double sphere_radius = 0;
     // element-face tables
     DevBuf<uint32_t> faceOther, faceMeta, sched;
     DevBuf<double> faceVec, faceUnit;
@@ -1794,17 +1795,26 @@ extern "C" int nsem_op_apply_bcs(nsem_ctx* c, int field, double* values) {
 // is the mass equation of the euler step with the transported scalar in the place of rho and no sound speed in lambdaMax, so the scalar
 // is kept in the rho slot of the state (nsem_upload_state(ctx, scalar, U, NULL...), boundary conditions under NSEM_F_RHO) and a step is
 // sweep A (inviscid instantiation, R = 0) + the ghost update of rho + the halo; the other outputs of the sweep are not used.
-// problem_init: 0 = the wind is the uploaded U; 1 = LEVEQUE, re-evaluated on the device at time step * dt before every step
-// (convection.cpp:74-82,114-121; needs nsem_upload_coords).  etime = end_step * dt; first_step = the step the next call starts with.
+// problem_init: 0 = the wind is the uploaded U; 1 = LEVEQUE, 2 / 3 = LAURITZEN_0 / LAURITZEN_1 (spherical meshes, nsem_set_sphere), re-evaluated
+// on the device at time step * dt before every step (convection.cpp:55-82,114-121; needs nsem_upload_coords).  etime = end_step * dt; first_step = the step the next call starts with.
 // ---------------------------------------------------------------------------------------------------------
 extern "C" int nsem_set_convection(nsem_ctx* c, int problem_init, double etime, long first_step) {
-    if (problem_init < 0 || problem_init > 1) { c->err = "nsem_set_convection: problem_init must be 0 (NONE) or 1 (LEVEQUE); the spherical winds need a spherical mesh"; return 1; }
-    if (problem_init == 1 && !c->xyz[0].p) { c->err = "nsem_set_convection: LEVEQUE needs the node coordinates (nsem_upload_coords)"; return 1; }
+    if (problem_init < 0 || problem_init > 3) { c->err = "nsem_set_convection: problem_init must be 0 (NONE), 1 (LEVEQUE), 2 (LAURITZEN_0) or 3 (LAURITZEN_1)"; return 1; }
+    if (problem_init >= 1 && !c->xyz[0].p) { c->err = "nsem_set_convection: the analytic winds need the node coordinates (nsem_upload_coords)"; return 1; }
+    if (problem_init >= 2 && !(c->sphere_radius > 0)) { c->err = "nsem_set_convection: the Lauritzen winds need the radius of the sphere (nsem_set_sphere)"; return 1; }
     c->convection = true;
     c->conv_init = problem_init;
     c->conv_etime = etime;
     c->conv_step = first_step - 1;
     c->speed_valid = false;
+    return 0;
+}
+
+// Mesh::sphere_radius of a cubed-sphere mesh (mesh.cpp:32): only the Lauritzen winds read it, everything else of a spherical case is in
+// the uploaded geometry and the per-node gravity
+extern "C" int nsem_set_sphere(nsem_ctx* c, double radius) {
+    if (!(radius > 0)) { c->err = "nsem_set_sphere: radius must be positive"; return 1; }
+    c->sphere_radius = radius;
     return 0;
 }
 
@@ -1829,6 +1839,13 @@ extern "C" int nsem_convection_step(nsem_ctx* c, int nsteps) {
             const uint64_t n = c->nNodes;
             wind_leveque_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, (double)c->conv_step * c->prm.dt, c->conv_etime, c->xyz[0].p, c->xyz[1].p,
                                                                                    c->U[k][0].p, c->U[k][1].p, c->U[k][2].p);
+            c->launches++;
+            c->speed_valid = false;
+        } else if (c->conv_init >= 2) {
+            const uint64_t n = c->nNodes;
+            wind_lauritzen_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->conv_init - 2, (double)c->conv_step * c->prm.dt, c->conv_etime,
+                                                                                     c->sphere_radius, c->xyz[0].p, c->xyz[1].p, c->xyz[2].p, c->U[k][0].p,
+                                                                                     c->U[k][1].p, c->U[k][2].p);
             c->launches++;
             c->speed_valid = false;
         }

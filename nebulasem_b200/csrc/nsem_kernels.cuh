@@ -227,6 +227,31 @@ __global__ void __launch_bounds__(256) wind_leveque_kernel(uint64_t n, double ti
     u2[q] = 0.0;
 }
 
+// Lauritzen's deformational winds on the sphere (convection.cpp:55-72 with cart_to_sphere and wind_field, tensor.h:598-621): zonal and
+// meridional components from latitude/longitude of the node, turned into a Cartesian vector.  kind 0 = LAURITZEN_0, 1 = LAURITZEN_1.
+__global__ void __launch_bounds__(256) wind_lauritzen_kernel(uint64_t n, int kind, double time, double period, double radius, const double* __restrict__ x,
+                                                              const double* __restrict__ y, const double* __restrict__ z, double* __restrict__ u0,
+                                                              double* __restrict__ u1, double* __restrict__ u2) {
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    constexpr double PI = 3.14159265358979323846264;      // Constants::PI
+    const double RoT = radius / period;
+    const double ct = cos(PI * time / period);
+    const double lat = atan2(z[q], sqrt(x[q] * x[q] + y[q] * y[q])), lon = atan2(y[q], x[q]);
+    const double lambda = lon - 2.0 * PI * time / period;
+    double u, v;
+    if (kind == 0) {
+        u = 10.0 * RoT * pow(sin(lambda), 2.0) * sin(2.0 * lat) * ct + 2.0 * PI * RoT * cos(lat);
+        v = 10.0 * RoT * sin(2.0 * lambda) * cos(lat) * ct;
+    } else {
+        u = -5.0 * RoT * pow(sin(0.5 * lambda), 2.0) * sin(2.0 * lat) * pow(cos(lat), 2.0) * ct + 2.0 * PI * RoT * cos(lat);
+        v = 2.5 * RoT * sin(lambda) * pow(cos(lat), 3.0) * ct;
+    }
+    u0[q] = -u * sin(lon) - v * sin(lat) * cos(lon);
+    u1[q] = +u * cos(lon) - v * sin(lat) * sin(lon);
+    u2[q] = +v * cos(lat);
+}
+
 // cds(cell field) (field.h:2881-2893): fF = fI * fFO + (1 - fI) * fFN on every element face node, [elem*6 + local face][NPF]; a face is
 // evaluated from both of its elements and both write the same value (bitwise: fI is 0 or 1/2).  Operator-level view only (nsem_op_cds).
 template <int NX, int NY, int NZ>

@@ -5,6 +5,7 @@ Mesh::LoadMesh (src/field/field.cpp:95-167), MeshField::read (src/field/field.h:
 """
 from __future__ import annotations
 
+import math
 import os
 
 import numpy as np
@@ -30,7 +31,16 @@ def init_field(ff: refio.FieldFile, geo: Geometry, gravity) -> np.ndarray:
             out += ini[1][None, :]
         elif kind in ("cosine", "cosine2", "linear", "gaussian"):
             _, value, pert, center, radius = ini
-            Rr = vmag((geo.cC - center[None, :]) / radius[None, :])
+            if getattr(geo, "spherical", False):
+                # centre given as (radius, latitude, longitude); great-circle distance over |radius| (field.h:1441-1444)
+                sr = vmag(geo.cC)
+                lat = libm.atan2_(geo.cC[:, 2], libm.sqrt_(geo.cC[:, 0] * geo.cC[:, 0] + geo.cC[:, 1] * geo.cC[:, 1]))
+                lon = libm.atan2_(geo.cC[:, 1], geo.cC[:, 0])
+                d = (center[0] + sr) / 2
+                d = d * libm.acos_(math.sin(center[1]) * libm.sin_(lat) + math.cos(center[1]) * libm.cos_(lat) * libm.cos_(center[2] - lon))
+                Rr = d / float(vmag(radius[None, :])[0])
+            else:
+                Rr = vmag((geo.cC - center[None, :]) / radius[None, :])
             if kind == "gaussian":
                 v = libm.exp_(-Rr * Rr)
                 v = np.array([0.0 if equal(float(x), 0.0) else x for x in v])
@@ -51,7 +61,10 @@ def init_field(ff: refio.FieldFile, geo: Geometry, gravity) -> np.ndarray:
             out += value[None, :] + pert[None, :] * v[:, None]
         elif kind == "hydrostatic":
             _, p0, scale, expon = ini
-            gh = geo.cC @ np.asarray(gravity, dtype=float)
+            if getattr(geo, "spherical", False):
+                gh = -(vmag(geo.cC) - geo.sphere_radius) * float(vmag(np.asarray(gravity, dtype=float)[None, :])[0])
+            else:
+                gh = geo.cC @ np.asarray(gravity, dtype=float)
             out += p0[None, :] * libm.pow_(1.0 + scale * gh, expon)[:, None]
         else:
             raise NotImplementedError(kind)
@@ -76,12 +89,20 @@ def load_case(case_dir: str, exact_order: bool = True, step: int = 0) -> EulerOr
     mesh_name = gen.get("mesh", ["grid"])[0]
     nop = [int(gen.get(k, ["0"])[0]) for k in ("npx", "npy", "npz")]
     grid = refio.read_grid(os.path.join(case_dir, f"{mesh_name}_{step}"))
-    topo = MeshTopo(grid).load()
-    geo = Geometry(topo, Basis(nop))
     params = Params.from_controls(blocks)
+    topo = MeshTopo(grid)
+    topo.spherical, topo.sphere_radius, topo.sphere_height = params.is_spherical, params.sphere_radius, params.sphere_height
+    topo.load()
+    geo = Geometry(topo, Basis(nop))
     fields, bcs = {}, {}
     for name in ("p", "U", "T", "rho"):
-        ff = refio.read_field(os.path.join(case_dir, f"{name}{step}"))
+        base = os.path.join(case_dir, f"{name}{step}")
+        if name == "rho" and not (os.path.exists(base + ".txt") or os.path.exists(base + ".bin")):
+            # MeshField::read skips a file that is not there (field.h:1579-1585; examples/atmo/hydro-sphere ships no rho0): the start
+            # branch forms rho from p and T on every entry and, with no conditions to apply, boundary cells keep what Solve leaves there
+            fields[name], bcs[name] = np.zeros(geo.gALL), []
+            continue
+        ff = refio.read_field(base)
         fields[name] = init_field(ff, geo, params.gravity)
         bcs[name] = bind_bcs(ff, topo)
     orc = EulerOracle(geo, params, exact_order=exact_order)
@@ -97,9 +118,11 @@ def load_convection_case(case_dir: str, exact_order: bool = True, step: int = 0)
     mesh_name = gen.get("mesh", ["grid"])[0]
     nop = [int(gen.get(k, ["0"])[0]) for k in ("npx", "npy", "npz")]
     grid = refio.read_grid(os.path.join(case_dir, f"{mesh_name}_{step}"))
-    topo = MeshTopo(grid).load()
-    geo = Geometry(topo, Basis(nop))
     params = Params.from_controls(blocks)
+    topo = MeshTopo(grid)
+    topo.spherical, topo.sphere_radius, topo.sphere_height = params.is_spherical, params.sphere_radius, params.sphere_height
+    topo.load()
+    geo = Geometry(topo, Basis(nop))
     fields, bcs = {}, {}
     for name in ("U", "T"):
         ff = refio.read_field(os.path.join(case_dir, f"{name}{step}"))

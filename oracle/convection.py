@@ -4,7 +4,7 @@ nsem_convection_step; nothing under nebulasem_b200/ imports it).
 apps/convection/convection.cpp:18-150:  dT/dt + div(T U) = 0 on the dGSEM operators of the euler path:
     Fc = flxc(U) = U, lambdaMax = cds(mag(U)) / 2                                   (:103-105, 119-121)
     M = divf(Fc * T, false, &F, &T, &lambdaMax); addTemporal<1>(M, t_UR); Solve(M)    (:129-135)
-with the optional analytic wind of LeVeque's deformation test re-evaluated at every step (:42-87, 114-121).  One reference step is one
+with the optional analytic wind of LeVeque's deformation test, or Lauritzen's two on the sphere, re-evaluated at every step (:42-87, 114-121).  One reference step is one
 forward-Euler stage for BDF1 / AB1 / RK1 (SURVEY finding 1), like the euler path."""
 from __future__ import annotations
 
@@ -33,6 +33,25 @@ class ConvectionOracle(EulerOracle):
         x, y = self.g.cC[:, 0], self.g.cC[:, 1]
         period = etime
         ct = libm.cos_(np.array([PI * time / period]))[0]
+        if self.problem_init.startswith("LAURITZEN"):
+            # deformational flow on the sphere (convection.cpp:59-72; wind_field, tensor.h:615-621)
+            if not self.p.is_spherical:
+                raise NotImplementedError("the Lauritzen winds need is_spherical YES (the reference leaves u, v unset otherwise)")
+            z = self.g.cC[:, 2]
+            lat = libm.atan2_(z, libm.sqrt_(x * x + y * y))
+            lon = libm.atan2_(y, x)
+            RoT = self.p.sphere_radius / period
+            lam = lon - 2.0 * PI * time / period
+            if self.problem_init == "LAURITZEN_0":
+                u = 10.0 * RoT * libm.pow_(libm.sin_(lam), 2.0) * libm.sin_(2.0 * lat) * ct + 2.0 * PI * RoT * libm.cos_(lat)
+                v = 10.0 * RoT * libm.sin_(2.0 * lam) * libm.cos_(lat) * ct
+            else:
+                u = -5.0 * RoT * libm.pow_(libm.sin_(0.5 * lam), 2.0) * libm.sin_(2.0 * lat) * libm.pow_(libm.cos_(lat), 2.0) * ct \
+                    + 2.0 * PI * RoT * libm.cos_(lat)
+                v = 2.5 * RoT * libm.sin_(lam) * libm.pow_(libm.cos_(lat), 3.0) * ct
+            return np.stack([-u * libm.sin_(lon) - v * libm.sin_(lat) * libm.cos_(lon),
+                             +u * libm.cos_(lon) - v * libm.sin_(lat) * libm.sin_(lon),
+                             +v * libm.cos_(lat)], axis=1)
         u = libm.pow_(libm.sin_(PI * x), 2.0) * libm.sin_(2 * PI * y) * ct
         v = -libm.pow_(libm.sin_(PI * y), 2.0) * libm.sin_(2 * PI * x) * ct
         return np.stack([u, v, np.zeros_like(u)], axis=1)
@@ -40,7 +59,7 @@ class ConvectionOracle(EulerOracle):
     def step(self):
         P = self.p
         i = self.step_count + 1                                      # Iteration::get_step() inside the loop
-        if self.problem_init == "LEVEQUE":
+        if self.problem_init != "NONE":
             self.U = self.wind(i * P.dt, self.end_step * P.dt)
         lam = self.cds(vmag(self.U)) / 2
         fq = self.U * self.T[:, None]

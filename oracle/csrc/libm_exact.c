@@ -20,3 +20,9 @@ void nsem_or_cos(const double* x, double* out, size_t n) {
 void nsem_or_sin(const double* x, double* out, size_t n) {
     for (size_t i = 0; i < n; i++) out[i] = sin(x[i]);
 }
+void nsem_or_acos(const double* x, double* out, size_t n) {
+    for (size_t i = 0; i < n; i++) out[i] = acos(x[i]);
+}
+void nsem_or_atan2(const double* y, const double* x, double* out, size_t n) {
+    for (size_t i = 0; i < n; i++) out[i] = atan2(y[i], x[i]);
+}

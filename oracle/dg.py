@@ -249,6 +249,11 @@ class Geometry:
         FN = np.full(nF * NPF, gALL, dtype=np.int64)
         V = topo.V
         xgl, wgl = b.xgl, b.wgl
+        sph = bool(getattr(topo, "spherical", False))
+        self.spherical, self.sphere_radius = sph, float(getattr(topo, "sphere_radius", 0.0))
+
+        def mag3(a):    # Unroll<3>::dot nests to the right
+            return math.sqrt(float(a[0] * a[0] + (a[1] * a[1] + a[2] * a[2])))
 
         # ---- node coordinates by transfinite interpolation (dg.cpp:176-325) ----
         sides = [(0, 1), (3, 2), (7, 6), (4, 5), (0, 3), (1, 2), (5, 6), (4, 7), (0, 4), (1, 5), (2, 6), (3, 7)]
@@ -286,11 +291,14 @@ class Geometry:
                         rz = (xgl[2][k] + 1) / 2
                         m = [rx] * 4 + [ry] * 4 + [rz] * 4
                         vd = [(1 - m[w]) * ev[w][0] + m[w] * ev[w][1] for w in range(12)]
+                        if sph:     # every blended point goes back to the blended radius (ADDV/ADDF/ADDC, dg.cpp:257-285)
+                            vd = [vd[w] * (((1 - m[w]) * mag3(ev[w][0]) + m[w] * mag3(ev[w][1])) / mag3(vd[w])) for w in range(12)]
                         vf = [None] * 6
 
                         def addf(rr, rs, i00, i01, i10, i11, ir0, ir1, i0s, i1s):
-                            return interpolate_face(rr, rs, vp[i00], vp[i01], vp[i10], vp[i11],
-                                                    vd[ir0], vd[ir1], vd[i0s], vd[i1s])
+                            x = interpolate_face(rr, rs, vp[i00], vp[i01], vp[i10], vp[i11],
+                                                 vd[ir0], vd[ir1], vd[i0s], vd[i1s])
+                            return (mag3(vd[ir0]) / mag3(x)) * x if sph else x
                         vf[0] = addf(rx, ry, 0, 3, 1, 2, 0, 1, 4, 5)
                         vf[1] = addf(rx, ry, 4, 7, 5, 6, 3, 2, 7, 6)
                         vf[2] = addf(rx, rz, 0, 4, 1, 5, 0, 3, 8, 9)
@@ -302,6 +310,8 @@ class Geometry:
                                              vd[0], vd[3], vd[1], vd[2], vd[4], vd[7], vd[5], vd[6],
                                              vd[8], vd[11], vd[9], vd[10],
                                              vf[4], vf[5], vf[2], vf[3], vf[0], vf[1])
+                        if sph:
+                            v = (mag3(vd[8]) / mag3(v)) * v
                         idx = I4(ci, i, j, k)
                         cC[idx] = v
                         cV[idx] *= wgl[0][i] * wgl[1][j] * wgl[2][k] / 8

@@ -57,6 +57,9 @@ class Params:
     diffusion: bool = True
     time_scheme: str = "BDF1"                  # BDF1 | AB1 | RK1..RK4 (all one forward-Euler stage on this path)
     problem_init: str = "NONE"
+    is_spherical: bool = False                 # Mesh::is_spherical / sphere_radius / sphere_height, mesh.cpp:31-33
+    sphere_radius: float = 6371220.0
+    sphere_height: float = 10000.0
 
     @staticmethod
     def from_controls(blocks: dict) -> "Params":
@@ -84,6 +87,10 @@ class Params:
             p.diffusion = yes(e["diffusion"][0])
         if "problem_init" in e:
             p.problem_init = e["problem_init"][0]
+        if "is_spherical" in g:
+            p.is_spherical = yes(g["is_spherical"][0])
+        p.sphere_radius = f(g, "sphere_radius", p.sphere_radius)
+        p.sphere_height = f(g, "sphere_height", p.sphere_height)
         return p
 
 
@@ -579,8 +586,14 @@ class EulerOracle:
             self.rho = (P.P0 / (R * (self.T + P.T0))) * libm.pow_((self.pp + P.P0) / P.P0, 1 / gamma) - (P.P0 / (R * P.T0))
         if P.buoyancy:
             grav = np.array(P.gravity, dtype=float)
-            self.gvec = np.tile(grav, (self.gA, 1))
-            self.gh = vdot(self.gvec, g.cC)
+            if P.is_spherical:      # gravity towards the centre of the sphere, euler.cpp:109-111
+                r = vmag(g.cC)
+                mg = float(vmag(grav[None, :])[0])
+                self.gvec = -(g.cC / r[:, None]) * mg
+                self.gh = -(r - P.sphere_radius) * mg
+            else:
+                self.gvec = np.tile(grav, (self.gA, 1))
+                self.gh = vdot(self.gvec, g.cC)
             # fixedBCs<Vector>(U,g): every BC of U becomes CALC_DIRICHLET for g (field.h:2779-2795)
             self.bcs["g"] = [BCSpec("CALC_DIRICHLET", bc.faces, np.zeros(3)) for bc in self.bcs["U"]]
             self.apply_bcs("g", self.gvec)

@@ -26,8 +26,9 @@ def _get():
         _lib = ctypes.CDLL(_SO)
         dp = ctypes.POINTER(ctypes.c_double)
         _lib.nsem_or_pow.argtypes = [dp, ctypes.c_double, dp, ctypes.c_size_t]
-        for n in ("nsem_or_sqrt", "nsem_or_exp", "nsem_or_cos", "nsem_or_sin"):
+        for n in ("nsem_or_sqrt", "nsem_or_exp", "nsem_or_cos", "nsem_or_sin", "nsem_or_acos"):
             getattr(_lib, n).argtypes = [dp, dp, ctypes.c_size_t]
+        _lib.nsem_or_atan2.argtypes = [dp, dp, dp, ctypes.c_size_t]
     return _lib
 
 
@@ -63,3 +64,15 @@ def cos_(x):
 
 def sin_(x):
     return _unary("nsem_or_sin", x)
+
+
+def acos_(x):
+    return _unary("nsem_or_acos", x)
+
+
+def atan2_(y, x):
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(x)
+    _get().nsem_or_atan2(_p(y), _p(x), _p(out), x.size)
+    return out

@@ -4,7 +4,9 @@ Follows (all in /root/reference):
   addBoundaryCells     src/mesh/mesh.cpp:55-109
   getHexCorners        src/mesh/mesh.cpp:113-157
   fixHexCells          src/mesh/mesh.cpp:161-446   (non USE_HEX_REFINEMENT branch)
-  calcGeometry         src/mesh/mesh.cpp:450-577   (non spherical)
+  calcGeometry         src/mesh/mesh.cpp:450-577   (with the cubed-sphere corrections :520-570)
+  ExtrudeMesh          src/mesh/mesh.cpp:723-750   (is_spherical)
+  cart_to_sphere/geodesic_distance/spherical_triangle_area   src/tensor/tensor.h:598-635
   removeBoundary       src/mesh/mesh.cpp:581-669
   pointInLine/calcUnitNormal/coplanarFaces/mergeFacets/mergeFacetsGroup  mesh.cpp:791-1020
   LoadMesh             src/field/field.cpp:95-167
@@ -38,8 +40,42 @@ def _unit(v):
     return v / math.sqrt(float(v @ v))
 
 
+def _dot(a, b) -> float:
+    """Unroll<3>::dot nests to the right (tensor.h:124-127)"""
+    return float(a[0] * b[0] + (a[1] * b[1] + a[2] * b[2]))
+
+
+def _mag(a) -> float:
+    return math.sqrt(_dot(a, a))
+
+
+def cart_to_sphere(c):
+    """(radius, latitude, longitude), tensor.h:598-605; math.* is the platform libm the reference binary links"""
+    return np.array([_mag(c), math.atan2(c[2], math.sqrt(float(c[0] * c[0] + c[1] * c[1]))), math.atan2(c[1], c[0])])
+
+
+def geodesic_distance(s1, s2) -> float:
+    """tensor.h:608-612"""
+    d = (s1[0] + s2[0]) / 2
+    d *= math.acos(math.sin(s1[1]) * math.sin(s2[1]) + math.cos(s1[1]) * math.cos(s2[1]) * math.cos(s1[2] - s2[2]))
+    return float(d)
+
+
+def spherical_triangle_area(radius: float, v0, v1, v2) -> float:
+    """tensor.h:624-635"""
+    a, b, c = v0 / _mag(v0), v1 / _mag(v1), v2 / _mag(v2)
+    t = abs(_dot(a, _cross(b, c)))
+    t /= (1 + _dot(a, b) + _dot(b, c) + _dot(a, c))
+    return 2 * math.atan(t) * radius * radius
+
+
 class MeshTopo:
     """State of Mesh::MeshObject after LoadMesh (before the DG node expansion)."""
+
+    # Mesh::is_spherical / sphere_radius / sphere_height (mesh.cpp:31-33); set before load()
+    spherical = False
+    sphere_radius = 6371220.0
+    sphere_height = 10000.0
 
     def __init__(self, grid: Grid):
         self.V = np.array(grid.vertices, dtype=np.float64)
@@ -349,11 +385,66 @@ class MeshTopo:
                 Vt += Vi
             CC[i] = C / Vt
             CV[i] = Vt / 3.0
+        if self.spherical:
+            self._sphere_geometry(FC, FNv, CC, CV)
         for i in range(self.nBCS, nc):
             fi = self.cells[i][0]
             CV[i] = CV[self.FOC[fi]]
             CC[i] = FC[fi]
         self.FC, self.FNv, self.CC, self.CV = FC, FNv, CC, CV
+
+    # ---- cubed-sphere shells ------------------------------------------------------------------
+    def extrude(self):
+        """ExtrudeMesh (mesh.cpp:723-750): the grid file holds a shell between two concentric cubes; the cube a vertex lies on (its largest
+        |coordinate|) picks the radius it is projected to -- the SMALLER cube goes to the OUTER radius, as in the reference."""
+        V = self.V
+        h = [max(max(abs(float(v[0])), abs(float(v[1]))), abs(float(v[2]))) for v in V]
+        minh, maxh = min(h + [1e30]), max(h + [0.0])
+        ri, ro = self.sphere_radius, self.sphere_radius + self.sphere_height
+        for i in range(len(V)):
+            f = (h[i] - minh) / (maxh - minh)
+            V[i] = (V[i] / _mag(V[i])) * (f * ri + (1 - f) * ro)
+
+    def _sphere_geometry(self, FC, FNv, CC, CV):
+        """mesh.cpp:520-570: centres pushed to the shell radii, vertical face areas from the geodesic length of their outline, radial face
+        areas from spherical triangles, volumes = thickness x mean radial area.  Sides 0 and 1 of a cell are its two radial faces."""
+        V = self.V
+        for i in range(self.nBCS):
+            c = self.cells[i]
+            rb = _mag(V[self.facets[c[0]][0]])
+            rt = _mag(V[self.facets[c[1]][0]])
+            CC[i] = ((rb + rt) / (2 * _mag(CC[i]))) * CC[i]
+            FC[c[0]] = (rb / _mag(FC[c[0]])) * FC[c[0]]
+            FC[c[1]] = (rt / _mag(FC[c[1]])) * FC[c[1]]
+            for j in range(2, 6):
+                FC[c[j]] = ((rb + rt) / (2 * _mag(FC[c[j]]))) * FC[c[j]]
+                d = 0.0
+                f = self.facets[c[j]]
+                for k in range(len(f)):
+                    v0 = V[f[k]]
+                    v1 = V[f[0 if k == len(f) - 1 else k + 1]]
+                    r0, r1 = v0 / _mag(v0), v1 / _mag(v1)
+                    if equal(r0[0], r1[0]) and equal(r0[1], r1[1]) and equal(r0[2], r1[2]):
+                        continue
+                    d += geodesic_distance(cart_to_sphere(v0), cart_to_sphere(v1))
+                d /= 2
+                area = abs(rt - rb) * d
+                FNv[c[j]] = area * (FNv[c[j]] / _mag(FNv[c[j]]))
+        for i in range(self.nBCS):
+            c = self.cells[i]
+            area = 0.0
+            for k in range(2):
+                f = self.facets[c[k]]
+                radius = _mag(V[f[0]])
+                a = 0.0
+                for j in range(len(f)):
+                    a += spherical_triangle_area(radius, V[f[j]], V[f[0 if j == len(f) - 1 else j + 1]], FC[c[k]])
+                FNv[c[k]] = a * (FNv[c[k]] / _mag(FNv[c[k]]))
+                area += a
+            area /= 2
+            rb = _mag(V[self.facets[c[0]][0]])
+            rt = _mag(V[self.facets[c[1]][0]])
+            CV[i] = abs(rt - rb) * area
 
     # ---- removeBoundary ("delete" patch of 2-D meshes) ----------------------------------------
     def remove_boundary(self, fs):
@@ -399,6 +490,8 @@ class MeshTopo:
     def load(self):
         self.add_boundary_cells()
         self.fix_hex_cells()
+        if self.spherical:
+            self.extrude()
         self.calc_geometry()
         fs = self.boundaries.pop("delete")
         self.remove_boundary(fs)

@@ -1,0 +1,94 @@
+"""Golden fixtures for cubed-sphere shells (general{is_spherical YES}), made with the UNMODIFIED reference binaries
+oracle/_ref/parity/{mesh,geomdump,euler,convection}:
+
+    python tests/golden/make_sphere_golden.py        (build container: /root/reference + oracle/build_ref.sh)
+
+  hydro-sphere      examples/atmo/hydro-sphere (3-D shell, radial gravity, hydrostatic reference state) at 4 x 4 x 2 cells per panel,
+                    order 2, with a warm blob added to T0 through the great-circle `cosine` initialiser so that something moves
+  acoustic-sphere   examples/atmo/acoustic-sphere (one radial layer with its two shells deleted: a 2-D surface; viscosity 30) at
+                    4 x 4 cells per panel, order 3, with the example's own pressure pulse
+  advection-sphere  examples/atmo/advection-sphere (scalar advection, Lauritzen's deformational wind re-evaluated every step) at
+                    4 x 4 cells per panel, order 3
+
+Each fixture holds the case (controls, grid_0.txt, field files), the reference's geometry arrays after Mesh::LoadMesh (geomdump:
+ExtrudeMesh + the curved-element corrections of calcGeometry + the radial rescale of the node placement) and its dump after NSTEPS
+steps.  The block file of the example is kept except for the number of divisions."""
+import os
+import re
+import shutil
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import refio, run_ref  # noqa: E402
+
+EX = "/root/reference/examples/atmo"
+GEOM = ("cC", "cV", "Jinv", "fN", "fC", "fI", "FO", "FN", "gFC", "gFN", "gCV", "gCC", "vertices")
+
+
+def sub(ctl, key, val):
+    assert re.search(rf"(?m)^(\s*){key}\s+\S+", ctl), key
+    return re.sub(rf"(?m)^(\s*){key}\s+\S+", rf"\g<1>{key} {val}", ctl)
+
+
+def make(name, solver, div, nop, nsteps, dt, edits=None, field_edits=None, end_step=None):
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "sphere", name)
+    d = os.path.join(tempfile.mkdtemp(prefix="sphere_golden_"), name)
+    shutil.copytree(os.path.join(EX, name), d)
+    for f in os.listdir(d):
+        os.chmod(os.path.join(d, f), 0o644)
+    blk = open(os.path.join(d, "sphere")).read()
+    blk, n = re.subn(r"linear 3\{\d+ \d+ \d+\}", "linear 3{%d %d %d}" % div, blk)
+    assert n == 6
+    open(os.path.join(d, "sphere"), "w").write(blk)
+    m = subprocess.run([run_ref.ref_bin("mesh"), "sphere", "-o", "grid_0.txt"], cwd=d, capture_output=True, text=True, timeout=600)
+    assert m.returncode == 0, m.stdout[-1000:] + m.stderr[-1000:]
+    ctl = open(os.path.join(d, "controls")).read()
+    for k, v in (("end_step", end_step or nsteps), ("write_interval", nsteps), ("dt", dt), ("npx", nop[0]), ("npy", nop[1]), ("npz", nop[2])):
+        ctl = sub(ctl, k, v)
+    if re.search(r"(?m)^\s*write_format", ctl):
+        ctl = sub(ctl, "write_format", "BINARY")
+    ctl = re.sub(r"(?m)^\s*amr_step\s+\d+\s*\n", "", ctl)
+    for k, v in (edits or {}).items():
+        ctl = sub(ctl, k, v)
+    open(os.path.join(d, "controls"), "w").write(ctl)
+    for f, text in (field_edits or {}).items():
+        open(os.path.join(d, f), "w").write(text)
+    shutil.rmtree(out, ignore_errors=True)
+    os.makedirs(out)
+    for f in os.listdir(d):
+        if f == "controls" or f == "grid_0.txt" or re.fullmatch(r"[A-Za-z]+0\.txt", f):
+            shutil.copy(os.path.join(d, f), os.path.join(out, f))
+    g = subprocess.run([run_ref.ref_bin("geomdump"), "./controls", "geom.bin", solver], cwd=d, capture_output=True, text=True, timeout=600)
+    assert g.returncode == 0, g.stdout[-1000:] + g.stderr[-1000:]
+    geom = refio.read_geomdump(os.path.join(d, "geom.bin"))
+    r = subprocess.run([run_ref.ref_bin(solver), "./controls"], cwd=d, capture_output=True, text=True, timeout=1800)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    exp = {"nsteps": nsteps}
+    for f in (("rho", "U", "T", "p") if solver == "euler" else ("U", "T")):
+        v = refio.read_field_values(os.path.join(d, f + "1"))
+        exp[f] = v[:, 0] if v.shape[1] == 1 else v
+        if os.path.exists(os.path.join(d, f + "0.bin")):           # the convection app writes the wind of step 0 back to dump 0
+            shutil.copy(os.path.join(d, f + "0.bin"), os.path.join(d, "start_" + f + ".bin"))      # next to U0.txt the reader takes the .txt
+            v0 = refio.read_field_values(os.path.join(d, "start_" + f))
+            exp[f + "_start"] = v0[:, 0] if v0.shape[1] == 1 else v0
+    np.savez_compressed(os.path.join(out, "expected.npz"), dims=geom["dims"], **{k: geom[k] for k in GEOM}, **exp)
+    print(name, "dims", geom["dims"][:10], {k: (float(np.abs(exp[k]).max()), float(np.abs(exp[k] - np.mean(exp[k], axis=0)).max())) for k in exp if k != "nsteps"})
+
+
+def main():
+    # mid-shell radius 6371220 + 5000; centre given as (radius, latitude, longitude), radius of the blob as an arc length
+    warm = "size 1\ninternal 2\n{\n    uniform 0\n    cosine 0 2   6376220 0.3 0.5   3000000 0 0\n}\n" \
+           "boundary 2\n{\n    top {\n        type NEUMANN\n    }\n    bottom {\n        type NEUMANN\n    }\n}\n"
+    make("hydro-sphere", "euler", (4, 4, 2), (2, 2, 2), 20, 1.0, field_edits={"T0.txt": warm})
+    make("acoustic-sphere", "euler", (4, 4, 1), (3, 3, 0), 30, 30)
+    # the wind's period is end_step * dt (convection.cpp:48-50,103): the 12 days of the example in 4800 steps, compared after the first 48
+    make("advection-sphere", "convection", (4, 4, 1), (3, 3, 0), 48, 216, edits={"time_scheme": "AB1"}, end_step=4800)
+
+
+if __name__ == "__main__":
+    main()
