@@ -34,7 +34,12 @@ enum nsem_bc_kind {
     NSEM_BC_GHOST = 5,        /* inter-partition face: filled by the halo exchange (field.h:2605-2606, 2255-2324) */
     NSEM_BC_FIXED = 6,        /* frozen per-node values: CALC_DIRICHLET/POWER/LOG/PARABOLIC/INVERSE after their
                                  first evaluation (field.h:2691-2718) */
-    NSEM_BC_ROBIN = 7         /* ghost = shape*value + (1-shape)*(owner + tvalue*|dx|) (field.h:2677-2680) */
+    NSEM_BC_ROBIN = 7,        /* ghost = shape*value + (1-shape)*(owner + tvalue*|dx|) (field.h:2677-2680) */
+    NSEM_BC_UNLISTED = 8      /* rho only: the field file names no condition for the patch, so nothing overwrites what
+                                 SolveTexplicit leaves in the boundary cell (solve.cpp:563-565): the owner's residual (fillBCs,
+                                 field.h:2731-2743) over the boundary cell's own volume, i.e. ghost += (owner_new - owner_old) *
+                                 cV_owner / cV_ghost; `fixed` holds that volume ratio per face node (examples/atmo/hydro-sphere
+                                 ships no rho0 file) */
 };
 
 /* Field ids for BC tables and op-level calls. */
@@ -81,7 +86,7 @@ typedef struct {
     double tvalue[3];
     double tshape;
     double zMin;
-    const double* fixed;          /* NSEM_BC_FIXED: [n_faces*NPF*comps] */
+    const double* fixed;          /* NSEM_BC_FIXED: [n_faces*NPF*comps]; NSEM_BC_UNLISTED: volume ratios [n_faces*NPF] */
 } nsem_bc;
 
 /* Scalars of general{} / euler{} that the step needs (apps/utils/properties.cpp:14-34, euler.cpp:19-48,

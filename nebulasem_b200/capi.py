@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.environ.get("NSEM_LIBDIR") or os.path.join(_HERE, "lib"), "libnsem_cuda.so")
 
 BC_KINDS = {"NEUMANN": 1, "DIRICHLET": 2, "SYMMETRY": 3, "CYCLIC": 4, "GHOST": 5, "FIXED": 6, "ROBIN": 7,
-            "CALC_DIRICHLET": 6}
+            "CALC_DIRICHLET": 6, "UNLISTED": 8}
 FIELDS = {"rho": 0, "p": 1, "U": 2, "T": 3}
 
 _dp = C.POINTER(C.c_double)

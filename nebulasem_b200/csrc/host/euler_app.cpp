@@ -281,7 +281,7 @@ void EulerSolver::apply_bcs(std::vector<double>& F, int comps, std::vector<BCond
     const int NPF = Basis(nop).NPF;
     const uint64_t gA = geo.gALL;
     for (auto& bc : bcs) {
-        if (bc.type == "GHOST") continue;
+        if (bc.type == "GHOST" || bc.type == "UNLISTED") continue;
         auto it = topo.boundaries.find(bc.patch);
         if (it == topo.boundaries.end() || it->second.empty()) continue;
         const std::vector<u32>& faces = it->second;
@@ -412,25 +412,35 @@ void EulerSolver::read_fields(int step) {
     set_fields(frho, fU, fT, fp);
 }
 
-void EulerSolver::hold_unlisted_patches(const std::vector<double>& F, int comps, std::vector<BCond>& bcs) {
+void EulerSolver::mark_unlisted_patches() {
+    // A boundary patch the field file has no condition for: nothing overwrites what SolveTexplicit leaves in its boundary cells
+    // (solve.cpp:563-581), the owner's residual (fillBCs, field.h:2731-2743) over the boundary cell's own volume.  examples/atmo/hydro-sphere
+    // ships no rho0 file, so rho is such a field there; the device continues those cells the same way (NSEM_BC_UNLISTED, volume ratios in
+    // `fixed`).  For U, T and p the boundary cells would also pick up source terms and the equation of state: refused.
     const int NPF = Basis(nop).NPF;
+    struct L { const char* name; std::vector<BCond>* bcs; } lists[4] = {{"rho", &bc_rho}, {"U", &bc_U}, {"T", &bc_T}, {"p", &bc_p}};
     for (const auto& kv : topo.boundaries) {
         if (kv.second.empty() || kv.first.find("interMesh") != std::string::npos) continue;
-        bool listed = false;
-        for (const auto& b : bcs) listed = listed || b.patch == kv.first;
-        if (listed) continue;
-        BCond b;
-        b.patch = kv.first;
-        b.type = "CALC_DIRICHLET";
-        b.held = true;
-        b.fixed.assign(kv.second.size() * (size_t)NPF * comps, 0.0);
-        for (size_t j = 0; j < kv.second.size(); j++)
-            for (int n = 0; n < NPF; n++) {
-                const u32 c2 = geo.FN[(size_t)kv.second[j] * NPF + n];
-                if (c2 >= geo.gALL) continue;
-                for (int d = 0; d < comps; d++) b.fixed[(j * NPF + n) * comps + d] = F[(size_t)c2 * comps + d];
-            }
-        bcs.push_back(std::move(b));
+        for (auto& l : lists) {
+            bool listed = false;
+            for (const auto& b : *l.bcs) listed = listed || b.patch == kv.first;
+            if (listed) continue;
+            if (l.bcs != &bc_rho)
+                throw Error(std::string("field ") + l.name + " has no boundary condition on patch " + kv.first + " (only rho may go without one on the GPU path)");
+            BCond b;
+            b.patch = kv.first;
+            b.type = "UNLISTED";
+            b.held = true;
+            b.fixed.assign(kv.second.size() * (size_t)NPF, 0.0);
+            for (size_t j = 0; j < kv.second.size(); j++)
+                for (int n = 0; n < NPF; n++) {
+                    const size_t k = (size_t)kv.second[j] * NPF + n;
+                    const u32 c1 = geo.FO[k], c2 = geo.FN[k];
+                    if (c2 >= geo.gALL) continue;
+                    b.fixed[j * NPF + n] = geo.cV[c1] / geo.cV[c2];
+                }
+            l.bcs->push_back(std::move(b));
+        }
     }
 }
 
@@ -511,12 +521,7 @@ void EulerSolver::setup() {
     bc_rho_ref = scale_bcs(bc_rho);
     apply_bcs(rho_ref, 1, bc_rho_ref);
     for (uint64_t i = 0; i < gA; i++) p[i] -= p_ref[i];
-    // a boundary patch a field has no condition for keeps the values its boundary cells hold now: on the device (two state buffers) that is
-    // a frozen-value condition
-    hold_unlisted_patches(rho, 1, bc_rho);
-    hold_unlisted_patches(U, 3, bc_U);
-    hold_unlisted_patches(T, 1, bc_T);
-    hold_unlisted_patches(p, 1, bc_p);
+    mark_unlisted_patches();
     // totals (euler.cpp:164-176)
     mass0 = energy0 = volume0 = 0;
     for (uint64_t i = 0; i < gB; i++) {
@@ -537,6 +542,7 @@ static int kind_of(const std::string& t) {
     if (t == "GHOST") return NSEM_BC_GHOST;
     if (t == "CALC_DIRICHLET") return NSEM_BC_FIXED;
     if (t == "ROBIN") return NSEM_BC_ROBIN;
+    if (t == "UNLISTED") return NSEM_BC_UNLISTED;
     throw Error("boundary condition type " + t + " is not implemented on the GPU path");
 }
 
@@ -563,7 +569,7 @@ void EulerSolver::build_c_bcs() {
             }
             for (int d = 0; d < 3; d++) { c.value[d] = b.value[d]; c.tvalue[d] = b.tvalue[d]; }
             c.shape = b.shape; c.tshape = b.tshape; c.zMin = b.zMin;
-            if (c.kind == NSEM_BC_FIXED) {
+            if (c.kind == NSEM_BC_FIXED || c.kind == NSEM_BC_UNLISTED) {
                 if (b.fixed.empty()) throw Error("CALC_DIRICHLET on " + b.patch + " has no frozen values yet");
                 c.fixed = b.fixed.data();
             }

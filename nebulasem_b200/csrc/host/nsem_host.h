@@ -156,7 +156,7 @@ struct BCond {                       // BCondition<T>, field.h:144-173
     double shape = 0, tshape = 0, zMin = 0, zMax = 0;
     Vec3 dir{0, 0, 1};
     std::vector<double> fixed;       // frozen CALC_DIRICHLET values [nfaces*NPF*comps]
-    bool held = false;               // not from the field file: a patch without a condition keeps its set-up values (hold_unlisted_patches)
+    bool held = false;               // not from the field file: added by mark_unlisted_patches for a patch rho has no condition for
 };
 struct FieldFile {
     int comps = 1;
@@ -300,7 +300,7 @@ struct EulerSolver {
     void run();                                           // Iteration loop: steps + dumps every write_interval
 
     void apply_bcs(std::vector<double>& f, int comps, std::vector<BCond>& bcs);   // applyExplicitBCs on the host
-    void hold_unlisted_patches(const std::vector<double>& f, int comps, std::vector<BCond>& bcs);
+    void mark_unlisted_patches();         // patches rho has no condition for (NSEM_BC_UNLISTED)
 private:
     std::vector<nsem_bc> c_bcs_;
     std::vector<std::vector<u32>> keep_faces_;

@@ -1116,14 +1116,15 @@ extern "C" int nsem_set_bcs(nsem_ctx* c, const nsem_bc* bcs, uint32_t nb) {
     for (uint32_t q = 0; q < nb; q++) {
         const nsem_bc& b = bcs[q];
         if (b.field < 0 || b.field >= 4) { c->err = "nsem_set_bcs: bad field id"; return 1; }
-        if (b.kind < NSEM_BC_NEUMANN || b.kind > NSEM_BC_ROBIN) { c->err = "nsem_set_bcs: unsupported BC kind"; return 1; }
+        if (b.kind < NSEM_BC_NEUMANN || b.kind > NSEM_BC_UNLISTED) { c->err = "nsem_set_bcs: unsupported BC kind"; return 1; }
+        if (b.kind == NSEM_BC_UNLISTED && b.field != NSEM_F_RHO) { c->err = "nsem_set_bcs: only rho may go without a condition on a patch (NSEM_BC_UNLISTED)"; return 1; }
         const int comps = (b.field == NSEM_F_U) ? 3 : 1;
         BCRec r{};
         for (int d = 0; d < 3; d++) { r.value[d] = b.value[d]; r.tvalue[d] = b.tvalue[d]; }
         r.shape = b.shape; r.tshape = b.tshape; r.zMin = b.zMin;
         recs.push_back(r);
         const uint32_t ri = (uint32_t)recs.size() - 1;
-        if (b.kind == NSEM_BC_FIXED && fixedv[b.field].empty()) fixedv[b.field].assign((size_t)nG * NPF * comps, 0.0);
+        if ((b.kind == NSEM_BC_FIXED || b.kind == NSEM_BC_UNLISTED) && fixedv[b.field].empty()) fixedv[b.field].assign((size_t)nG * NPF * comps, 0.0);
         for (uint32_t j = 0; j < b.n_faces; j++) {
             const uint32_t face = b.faces[j];
             if (face >= c->nF || c->h_face_neigh[face] < nB) {
@@ -1139,8 +1140,8 @@ extern "C" int nsem_set_bcs(nsem_ctx* c, const nsem_bc* bcs, uint32_t nb) {
                 if (pf >= c->nF || c->h_face_neigh[pf] < nB) { c->err = "nsem_set_bcs: CYCLIC peer is not a boundary face"; return 1; }
                 peer[b.field][g] = c->h_face_neigh[pf] - nB;
             }
-            if (b.kind == NSEM_BC_FIXED) {
-                if (!b.fixed) { c->err = "nsem_set_bcs: FIXED needs values"; return 1; }
+            if (b.kind == NSEM_BC_FIXED || b.kind == NSEM_BC_UNLISTED) {
+                if (!b.fixed) { c->err = "nsem_set_bcs: FIXED needs values, UNLISTED the volume ratios"; return 1; }
                 for (int n = 0; n < NPF * comps; n++)
                     fixedv[b.field][((size_t)g * NPF) * comps + n] = b.fixed[((size_t)j * NPF) * comps + n];
             }
@@ -1448,7 +1449,7 @@ static void fill_bcparams(const nsem_ctx* c, const KParams& P, BCParams& B, int 
     B.bOwner = c->bOwner.p; B.bFid = c->bFid.p; B.bUnit = c->bUnit.p;
     for (int f = 0; f < 4; f++) { B.kind[f] = c->bcKind[f].p; B.rec[f] = c->bcRec[f].p; B.peer[f] = c->bcPeer[f].p; B.fixedv[f] = c->bcFixed[f].p; }
     B.recs = c->bcRecs.p;
-    B.rho_new = P.rho_new; B.p = P.p; B.T_old = P.T_old; B.p_ref = P.p_ref;
+    B.rho_new = P.rho_new; B.rho_old = P.rho_old; B.p = P.p; B.T_old = P.T_old; B.p_ref = P.p_ref;
     for (int d = 0; d < 9; d++) B.GU[d] = P.GU[d];
     for (int d = 0; d < 3; d++) { B.GT[d] = P.GT[d]; B.U_new[d] = P.U_new[d]; }
     B.T_new = P.T_new;

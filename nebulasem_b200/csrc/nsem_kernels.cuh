@@ -625,6 +625,7 @@ struct BCParams {
     const BCRec* recs;
     // fields
     double* rho_new;
+    const double* rho_old;           // UNLISTED boundary cells continue from their old value
     double* p;
     const double* T_old;
     const double* p_ref;
@@ -688,8 +689,10 @@ __global__ void __launch_bounds__(256) bc_kernel(const __grid_constant__ BCParam
             const int kd = B.kind[0][g];
             if (kd != 5) {
                 const double peer = (kd == 4) ? B.rho_new[peer_node(0)] : 0.0;
-                const double fx = (kd == 6) ? B.fixedv[0][(size_t)g * NPF + n] : 0.0;
-                B.rho_new[gi] = bc_scalar(kd, B.rho_new[oi], B.recs[B.rec[0][g]], peer, fx);
+                const double fx = (kd == 6 || kd == 8) ? B.fixedv[0][(size_t)g * NPF + n] : 0.0;
+                // UNLISTED: no condition overwrites what Solve left there, the owner's residual over the boundary cell's volume
+                B.rho_new[gi] = (kd == 8) ? B.rho_old[gi] + (B.rho_new[oi] - B.rho_old[oi]) * fx
+                                          : bc_scalar(kd, B.rho_new[oi], B.recs[B.rec[0][g]], peer, fx);
             }
         }
         // p: the BC acts on the full pressure, then p -= p_ref (euler.cpp:211-213)
