@@ -67,6 +67,24 @@ nsemh_solver* nsemh_open_case(const char* dir, int step) {
     }
 }
 
+// The same for partition `rank` of `nranks`: every rank decomposes the case's grid the way the controls say (decomposition{type, n}) and
+// keeps its part, fields localized through the cell map (what lib/euler does under a multi-process launch).
+nsemh_solver* nsemh_open_case_part(const char* dir, int step, int rank, int nranks) {
+    nsemh_solver* h = new nsemh_solver();
+    try {
+        (*h->sp).rank = rank; (*h->sp).nranks = nranks;
+        (*h->sp).read_controls(dir);
+        (*h->sp).load_mesh(step);
+        (*h->sp).read_fields(step);
+        (*h->sp).setup();
+        return h;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        delete h;
+        return nullptr;
+    }
+}
+
 // In-memory synthetic cases (same definitions as oracle/cases.py): kind in {bubble2d, bubble3d, vortex, hill3d}.
 // nranks > 1: the global grid is decomposed (decomp = METIS | XYZ | CELLID; XYZ uses px*py*pz = nranks) and only
 // partition `rank` is kept (Prepare::decomposeMesh, field.cpp:1086-1257).

@@ -182,6 +182,16 @@ void EulerSolver::set_mesh_partition(const Grid& global, int rank_, int nranks_,
     if (P.cellGlobal.empty()) throw Error("partition " + std::to_string(rank) + " is empty");
     cellGlobal = P.cellGlobal;
     peers = P.peers;
+    if (topo.spherical) {
+        // ExtrudeMesh scales by the extremes of the vertices it sees (mesh.cpp:735-741); a part need not reach both shells, so every part
+        // projects with the whole grid's extremes and lands on the single-partition mesh bit for bit
+        double minh = 1e30, maxh = 0;
+        for (const Vec3& v : global.V) {
+            const double h = std::max(std::max(std::fabs(v[0]), std::fabs(v[1])), std::fabs(v[2]));
+            maxh = std::max(maxh, h); minh = std::min(minh, h);
+        }
+        topo.shell_h[0] = minh; topo.shell_h[1] = maxh;
+    }
     set_mesh(P.grid);
     lap("local topology + node geometry");
 }

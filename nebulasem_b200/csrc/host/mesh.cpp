@@ -505,6 +505,7 @@ void MeshTopo::extrude() {
         if (h > maxh) maxh = h;
         if (h < minh) minh = h;
     }
+    if (shell_h[1] > 0) { minh = shell_h[0]; maxh = shell_h[1]; }
     const double radiusi = sphere_radius, radiuso = sphere_radius + sphere_height;
     for (Vec3& v : V) {
         const double f = (height(v) - minh) / (maxh - minh);

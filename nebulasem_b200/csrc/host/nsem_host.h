@@ -105,6 +105,9 @@ struct MeshTopo {
     // Mesh::is_spherical / sphere_radius / sphere_height (mesh.cpp:31-33): set before load()
     bool spherical = false;
     double sphere_radius = 6371220.0, sphere_height = 10000.0;
+    // the two cubes of the WHOLE grid (smallest and largest max|coordinate| over its vertices); when set (shell_h[1] > 0) extrude() uses
+    // them instead of this mesh's own extremes, so that a partition that does not reach both shells is projected like the whole mesh
+    double shell_h[2] = {0, 0};
     u32 nFacets() const { return (u32)facetStart.size() - 1; }
     u32 nCells() const { return (u32)cellStart.size() - 1; }
     void load(const Grid& g);            // Mesh::LoadMesh

@@ -14,7 +14,7 @@ import numpy as np
 from . import capi
 
 HOST_LIB_PATH = os.path.join(os.environ.get("NSEM_LIBDIR") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib"), "libnsem_host.so")
-HOST_EXPORTS = ["nsemh_error", "nsemh_close", "nsemh_open_case", "nsemh_synthetic", "nsemh_synthetic_part", "nsemh_patch_faces",
+HOST_EXPORTS = ["nsemh_error", "nsemh_close", "nsemh_open_case", "nsemh_open_case_part", "nsemh_synthetic", "nsemh_synthetic_part", "nsemh_patch_faces",
                 "nsemh_peers", "nsemh_diagnostics", "nsemh_attach", "nsemh_step",
                 "nsemh_upload", "nsemh_download", "nsemh_upload_async", "nsemh_download_async", "nsemh_adopt_refined_state", "nsemh_restart_state", "nsemh_regrid", "nsemh_enable_amr", "nsemh_cell_levels", "nsemh_write_amr_grid", "nsemh_write", "nsemh_write_vtk", "nsemh_run", "nsemh_sync", "nsemh_time",
                 "nsemh_launch_count", "nsemh_kernel_info", "nsemh_halo_info", "nsemh_halo_wait_ms", "nsemh_set_schedule", "nsemh_dims", "nsemh_params", "nsemh_f64", "nsemh_u32",
@@ -37,6 +37,8 @@ def load_host_library() -> C.CDLL:
     lib.nsemh_close.restype = None
     lib.nsemh_open_case.argtypes = [C.c_char_p, C.c_int]
     lib.nsemh_open_case.restype = vp
+    lib.nsemh_open_case_part.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int]
+    lib.nsemh_open_case_part.restype = vp
     lib.nsemh_synthetic.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.nsemh_synthetic.restype = vp
     lib.nsemh_synthetic_part.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int,
@@ -120,9 +122,14 @@ class Solver:
          self.gALL) = [int(x) for x in d]
 
     @classmethod
-    def open_case(cls, case_dir: str, step: int = 0) -> "Solver":
+    def open_case(cls, case_dir: str, step: int = 0, rank: int = 0, nranks: int = 1) -> "Solver":
+        """The euler (or convection) app's set-up on a case directory; nranks > 1 keeps partition `rank` of the decomposition the controls name."""
         lib = load_host_library()
-        return cls(lib.nsemh_open_case(os.fspath(case_dir).encode(), step))
+        if nranks == 1:
+            return cls(lib.nsemh_open_case(os.fspath(case_dir).encode(), step))
+        s = cls(lib.nsemh_open_case_part(os.fspath(case_dir).encode(), step, rank, nranks))
+        s.rank, s.nranks = rank, nranks
+        return s
 
     @classmethod
     def synthetic(cls, kind: str, nx: int, ny: int, nz: int, order: int) -> "Solver":

@@ -34,7 +34,12 @@ def main():
         v = [int(x) for x in os.environ["MP_CHECK_MESH"].split(",")]
         n, order, nsteps = tuple(v[:3]), v[3], v[4]
     pxyz = {2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(world, (world, 1, 1))
-    s = host.Solver.synthetic_part(kind, *n, order, rank, world, decomp, pxyz)
+    case_dir = os.environ.get("MP_CHECK_CASE")     # a case directory instead (decomposition as its controls say), e.g. tests/golden/sphere/hydro-sphere
+    if case_dir:
+        nsteps = int(os.environ.get("MP_CHECK_STEPS", "12"))
+        s = host.Solver.open_case(case_dir, 0, rank, world)
+    else:
+        s = host.Solver.synthetic_part(kind, *n, order, rank, world, decomp, pxyz)
     s.attach(local, rank, world, uid_bytes)
     s.step(nsteps)
     s.download()
@@ -45,13 +50,17 @@ def main():
     NP = s.NP
     cg = torch.tensor(s.u32("cellGlobal").astype(np.int64), device="cuda")
     ncell_global = n[0] * n[1] * n[2]
+    if case_dir:
+        cnt = torch.tensor([s.nBCS], dtype=torch.int64, device="cuda")
+        dist.all_reduce(cnt)
+        ncell_global = int(cnt.item())
     out = torch.zeros((ncell_global, NP, 5), dtype=torch.float64, device="cuda")
     loc = np.concatenate([rho[:nb, None], U[:nb], T[:nb, None]], axis=1).reshape(s.nBCS, NP, 5)
     out[cg] = torch.tensor(loc, device="cuda")
     dist.all_reduce(out)          # partitions are disjoint: the sum assembles the global field
     ok = True
     if rank == 0:
-        ref = host.Solver.synthetic(kind, *n, order)
+        ref = host.Solver.open_case(case_dir) if case_dir else host.Solver.synthetic(kind, *n, order)
         ref.attach(local)
         ref.step(nsteps)
         ref.download()

@@ -98,6 +98,36 @@ def test_host_sphere_geometry_and_setup_bit_equal_to_oracle(tmp_path, name):
     s.close()
 
 
+def test_partitions_of_the_shell_are_projected_like_the_whole_mesh(tmp_path):
+    """ExtrudeMesh scales by the extremes of the vertices it sees (mesh.cpp:735-741), and a part of a two-layer shell need not reach both
+    cubes: every part projects with the whole grid's extremes, so its elements are the single-partition ones bit for bit (set-up included)."""
+    from nebulasem_b200 import host
+    d = str(tmp_path / "hydro-sphere")
+    shutil.copytree(os.path.join(GOLD, "hydro-sphere"), d)
+    g = host.Solver.open_case(d)
+    NP = g.NP
+    cC_g = g.f64("cC").reshape(-1, 3)[: g.gBCSfield].reshape(g.nBCS, -1)
+    J_g = g.f64("Jinv")[: g.gBCSfield * 9].reshape(g.nBCS, -1)
+    rho_g, U_g, T_g, p_g = [a[: g.gBCSfield].reshape(g.nBCS, -1) for a in g.state()]
+    gv_g = g.f64("g").reshape(-1, 3)[: g.gBCSfield].reshape(g.nBCS, -1)
+    seen = np.zeros(g.nBCS, dtype=int)
+    nparts, one_shell_only = 5, 0
+    for r in range(nparts):
+        p = host.Solver.open_case(d, 0, r, nparts)
+        cg = p.u32("cellGlobal")
+        seen[cg] += 1
+        rad = np.linalg.norm(p.f64("cC").reshape(-1, 3)[: p.gBCSfield], axis=1)
+        one_shell_only += int(rad.max() - rad.min() < 0.75 * 10000.0)
+        assert np.array_equal(p.f64("cC").reshape(-1, 3)[: p.gBCSfield].reshape(p.nBCS, -1), cC_g[cg])
+        assert np.array_equal(p.f64("Jinv")[: p.gBCSfield * 9].reshape(p.nBCS, -1), J_g[cg])
+        rho, U, T, pp = [a[: p.gBCSfield].reshape(p.nBCS, -1) for a in p.state()]
+        assert np.array_equal(rho, rho_g[cg]) and np.array_equal(T, T_g[cg]) and np.array_equal(pp, p_g[cg])
+        assert np.array_equal(p.f64("g").reshape(-1, 3)[: p.gBCSfield].reshape(p.nBCS, -1), gv_g[cg])
+        p.close()
+    assert (seen == 1).all()
+    g.close()
+
+
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["hydro-sphere", "acoustic-sphere", "advection-sphere"])
@@ -136,3 +166,23 @@ def test_device_run_on_the_sphere_matches_the_reference_binary(tmp_path, name):
         assert np.isfinite(e) and e <= TOL, (k, e)
     if name != "advection-sphere":
         assert errs_self <= max(TOL, 3.0 * spread), (errs_self, spread)
+
+
+@pytest.mark.gpu
+def test_two_partitions_of_the_shell_equal_one_partition(tmp_path):
+    """hydro-sphere split over two GPUs (METIS, as its controls say; halo across panel edges, rho without a condition on top/bottom in both
+    parts) == the single-partition run."""
+    import subprocess
+    import sys
+
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = str(tmp_path / "hydro-sphere")
+    shutil.copytree(os.path.join(GOLD, "hydro-sphere"), d)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29519", os.path.join(root, "tests", "mp_gpu_check.py"), "METIS"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, MP_CHECK_CASE=d, MP_CHECK_STEPS="20"))
+    print(out.stdout[-3000:], out.stderr[-3000:])
+    assert out.returncode == 0 and "MP_CHECK_OK" in out.stdout
