@@ -112,6 +112,12 @@ typedef struct {
 int nsem_create(int device, int rank, int nranks, const void* nccl_unique_id, nsem_ctx** out);
 void nsem_destroy(nsem_ctx* ctx);
 const char* nsem_last_error(const nsem_ctx* ctx);          /* ctx may be NULL: error of the last failed create */
+/* In-place sum of a HOST array over the ranks of the context's communicator (MP::allreduce, src/mp/mp.h:93-104); dtype 0 = double,
+ * 1 = unsigned byte.  Collective.  The host side of a regrid on several partitions uses it to assemble the whole-domain state (every rank
+ * fills its own cells, zeros elsewhere) and to pass a fresh communicator id from rank 0 to everybody (Prepare::mergeFields +
+ * decomposeMesh around refineMesh, src/field/field.cpp:1086-1496). */
+int nsem_allreduce_host(nsem_ctx* ctx, void* buf, uint64_t count, int dtype);
+int nsem_device(const nsem_ctx* ctx);                      /* the CUDA device ordinal nsem_create resolved (device < 0: rank % visible devices) */
 int nsem_get_unique_id(void* out128);                      /* ncclGetUniqueId for rank 0 to broadcast */
 
 /* ---- set-up ---------------------------------------------------------------------------------------- */

@@ -651,6 +651,20 @@ static void repair_cyclic_order(Grid& g, const std::vector<std::array<std::strin
 // ---------------------------------------------------------------------------------------------------------
 // the solver on the regridded mesh
 // ---------------------------------------------------------------------------------------------------------
+void EulerSolver::copy_run_parameters(EulerSolver& n) const {
+    n.ctl = ctl; n.dir = dir; n.meshName = meshName;
+    for (int d = 0; d < 3; d++) { n.nop[d] = nop[d]; n.decomp_n[d] = decomp_n[d]; }
+    n.viscosity = viscosity; n.Pr = Pr; n.T0 = T0; n.P0 = P0; n.cp = cp; n.cv = cv; n.dt = dt; n.gravity = gravity;
+    n.buoyancy = buoyancy; n.diffusion = diffusion; n.binary_out = binary_out;
+    n.time_scheme = time_scheme; n.problem_init = "NONE";
+    n.start_step = start_step; n.end_step = end_step; n.write_interval = write_interval; n.decomp_type = decomp_type;
+    n.refine_params = refine_params; n.amr_step = amr_step;
+    n.mass0 = mass0; n.energy0 = energy0; n.volume0 = volume0;
+    n.vtk_fields = vtk_fields; n.vtk_cell_value = vtk_cell_value; n.vtk_polyhedral = vtk_polyhedral; n.vtk_on_dump = vtk_on_dump;
+    n.launch_nonce = launch_nonce;
+    n.topo.spherical = topo.spherical; n.topo.sphere_radius = topo.sphere_radius; n.topo.sphere_height = topo.sphere_height;
+}
+
 std::unique_ptr<EulerSolver> EulerSolver::regridded(const std::vector<uint8_t>& refine, const std::vector<uint8_t>& coarsen) {
     if (nranks > 1) throw Error("EulerSolver::regridded: the in-memory regrid runs on one partition (repartitioning a regridded mesh is not built)");
     for (const std::vector<BCond>* l : {&bc_rho, &bc_U, &bc_T, &bc_p})
@@ -681,16 +695,7 @@ std::unique_ptr<EulerSolver> EulerSolver::regridded(const std::vector<uint8_t>& 
     }
     if (!forest) throw Error("EulerSolver::regridded: no AMR forest (the mesh must come from set_mesh/load_mesh of a conforming hexahedral grid)");
     std::unique_ptr<EulerSolver> n(new EulerSolver());
-    n->ctl = ctl; n->dir = dir; n->meshName = meshName;
-    for (int d = 0; d < 3; d++) { n->nop[d] = nop[d]; n->decomp_n[d] = decomp_n[d]; }
-    n->viscosity = viscosity; n->Pr = Pr; n->T0 = T0; n->P0 = P0; n->cp = cp; n->cv = cv; n->dt = dt; n->gravity = gravity;
-    n->buoyancy = buoyancy; n->diffusion = diffusion; n->binary_out = binary_out;
-    n->time_scheme = time_scheme; n->problem_init = "NONE";
-    n->start_step = start_step; n->end_step = end_step; n->write_interval = write_interval; n->decomp_type = decomp_type;
-    n->refine_params = refine_params; n->amr_step = amr_step;
-    n->mass0 = mass0; n->energy0 = energy0; n->volume0 = volume0;
-    n->vtk_fields = vtk_fields; n->vtk_cell_value = vtk_cell_value; n->vtk_polyhedral = vtk_polyhedral; n->vtk_on_dump = vtk_on_dump;
-    n->launch_nonce = launch_nonce;
+    copy_run_parameters(*n);
     n->forest = forest;
     const bool verbose = std::getenv("NSEM_VERBOSE") != nullptr;
     auto t0 = std::chrono::steady_clock::now();
@@ -704,6 +709,7 @@ std::unique_ptr<EulerSolver> EulerSolver::regridded(const std::vector<uint8_t>& 
     Grid g = forest->grid();
     repair_cyclic_order(g, cyc);
     lap("grid emission");
+    if (keep_regrid_grid) { n->regrid_grid = std::make_shared<Grid>(g); n->keep_regrid_grid = true; }
     n->topo.load(g);
     lap("topology (MeshTopo::load)");
     Basis b(nop);

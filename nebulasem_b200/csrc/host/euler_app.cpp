@@ -109,9 +109,6 @@ void EulerSolver::read_controls(const std::string& case_dir) {
     refine_params.limit = ctl.integer("refinement", "limit", refine_params.limit);
     if (amr_step != 0 && topo.spherical)
         throw Error("adaptive regridding of a spherical mesh (field.cpp:638-645,921-924) is not built; set NSEM_IGNORE_AMR_STEP=1 to run on the grid as it is");
-    if (amr_step != 0 && nranks > 1)
-        throw Error("controls ask for adaptive regridding (amr_step) on " + std::to_string(nranks) + " partitions: the in-memory regrid runs on one "
-                    "partition (repartitioning a regridded mesh is not built); run one process or set NSEM_IGNORE_AMR_STEP=1");
     if (ctl.str("general", "state", "STEADY") != "TRANSIENT") throw Error("state must be TRANSIENT");
 }
 
@@ -130,7 +127,7 @@ void EulerSolver::set_mesh(const Grid& g) {
     lap("node geometry (Geometry::build)");
     // the AMR forest starts from the grid as loaded (conforming hexahedra); only built when a regrid can follow
     forest.reset();
-    if (amr_step != 0 || std::getenv("NSEM_AMR")) {
+    if ((amr_step != 0 || std::getenv("NSEM_AMR")) && nranks == 1) {       // a partition has no forest: the whole-domain solver regrids (run_case)
         forest = std::make_shared<AmrForest>();
         struct stat st;
         bool loaded = false;
@@ -622,7 +619,7 @@ static std::vector<u32> morton_schedule(const MeshTopo& t) {
 void EulerSolver::attach_device(int device, int rank, int nranks, const void* uid) {
     if (ctx) { nsem_destroy(ctx); ctx = nullptr; }
     if (nsem_create(device, rank, nranks, uid, &ctx)) throw Error(nsem_last_error(nullptr));
-    device_id = device;
+    device_id = nsem_device(ctx);
     auto ck = [&](int rc) { if (rc) throw Error(nsem_last_error(ctx)); };
     Basis b(nop);
     ck(nsem_set_order(ctx, b.NPX, b.NPY, b.NPZ));
@@ -865,8 +862,109 @@ void EulerSolver::run() {
 
 // AmrIteration (iteration.h:94-147) around Iteration: with amr_step != 0 a regrid before the first step and after every amr_step dumps.
 // The solver object is replaced by the one on the regridded mesh; the grid of every regrid is written as <mesh>_<dump>.txt.
+// The AMR cycle on several partitions.  The reference merges the fields on rank 0, refines there and decomposes again (Prepare::mergeFields,
+// refineMesh, decomposeMesh: field.cpp:1086-1496).  Here every rank keeps, next to its partition, a whole-domain solver on its own GPU that
+// exists for the regrids only: at a regrid the parts' states are summed into it (nsem_allreduce_host: every rank fills its own cells), it
+// regrids exactly like a one-partition run (same tags, same forest, field transfer + restart branch on the device), and every rank cuts its
+// new part from the emitted grid (mortar-weighted METIS: non-conforming faces are never cut) and takes its cells' values.  All ranks compute
+// the same regrid, so nothing but the state and a fresh communicator id crosses between them.
+static void run_case_partitioned(std::unique_ptr<EulerSolver>& s) {
+    const int rank = s->rank, nranks = s->nranks, device = s->device_id;
+    const bool verbose = std::getenv("NSEM_VERBOSE") != nullptr;
+    if (!s->ctx) throw Error("run_case: the partition is not attached to a device");
+    if (s->convection) throw Error("run_case: adaptive regridding of the convection app on several partitions is not built");
+    const int NP = Basis(s->nop).NP;
+    // the whole-domain solver: the case as one partition would set it up (no dumps, no prints)
+    std::unique_ptr<EulerSolver> G(new EulerSolver());
+    G->rank = 0; G->nranks = 1;
+    G->read_controls(s->dir);
+    G->launch_nonce = s->launch_nonce;
+    G->keep_regrid_grid = true;
+    G->load_mesh((int)G->start_step);
+    G->read_fields((int)G->start_step);
+    G->setup();
+    if (!G->forest) throw Error("run_case: the grid of dump " + std::to_string(G->start_step) + " cannot seed the AMR forest (it must be conforming, or have its .forest file)");
+    G->attach_device(device);
+    auto regrid = [&](long dump) {
+        // 1. whole-domain state from the parts
+        s->download();
+        const uint64_t nG = (uint64_t)s->nGlobalCells * NP;
+        if (nG != G->geo.gBCSfield) throw Error("run_case: the partitions and the whole-domain solver are not on the same grid");
+        std::vector<double> all(nG * 6, 0.0);
+        for (size_t l = 0; l < s->cellGlobal.size(); l++)
+            for (int q = 0; q < NP; q++) {
+                const uint64_t src = (uint64_t)l * NP + q, dst = ((uint64_t)s->cellGlobal[l] * NP + q) * 6;
+                all[dst] = s->rho[src];
+                for (int d = 0; d < 3; d++) all[dst + 1 + d] = s->U[src * 3 + d];
+                all[dst + 4] = s->T[src];
+                all[dst + 5] = s->p[src];
+            }
+        if (nsem_allreduce_host(s->ctx, all.data(), all.size(), 0)) throw Error(nsem_last_error(s->ctx));
+        for (uint64_t i = 0; i < nG; i++) {
+            G->rho[i] = all[i * 6];
+            for (int d = 0; d < 3; d++) G->U[i * 3 + d] = all[i * 6 + 1 + d];
+            G->T[i] = all[i * 6 + 4];
+            G->p[i] = all[i * 6 + 5];
+        }
+        G->apply_bcs(G->rho, 1, G->bc_rho); G->apply_bcs(G->U, 3, G->bc_U); G->apply_bcs(G->T, 1, G->bc_T); G->apply_bcs(G->p, 1, G->bc_p);
+        G->upload_state();
+        // 2. the one-partition regrid: tags, forest, new mesh, device transfer + restart branch
+        std::unique_ptr<EulerSolver> Gn = G->regridded_by_indicator();
+        Gn->download();
+        if (rank == 0) {
+            Gn->write_amr_grid(dump);
+            std::printf("Regrid at dump %ld: %u -> %u cells\n", dump, G->geo.nBCS, Gn->geo.nBCS);
+        }
+        // 3. this rank's part of the new grid with its cells' values
+        std::unique_ptr<EulerSolver> n(new EulerSolver());
+        s->copy_run_parameters(*n);
+        n->set_mesh_partition(*Gn->regrid_grid, rank, nranks, n->decomp_type, n->decomp_n);
+        auto blank = [](int comps, const std::vector<BCond>& bcs) {
+            FieldFile f;
+            f.comps = comps;
+            f.inits.push_back({"uniform", std::vector<double>(comps, 0.0)});
+            f.bcs = bcs;
+            return f;
+        };
+        n->set_fields(blank(1, s->file_bc_rho), blank(3, s->file_bc_U), blank(1, s->file_bc_T), blank(1, s->file_bc_p));
+        n->setup();
+        n->mass0 = s->mass0; n->energy0 = s->energy0; n->volume0 = s->volume0;
+        for (size_t l = 0; l < n->cellGlobal.size(); l++)
+            for (int q = 0; q < NP; q++) {
+                const uint64_t dst = (uint64_t)l * NP + q, src = (uint64_t)n->cellGlobal[l] * NP + q;
+                n->rho[dst] = Gn->rho[src];
+                for (int d = 0; d < 3; d++) n->U[dst * 3 + d] = Gn->U[src * 3 + d];
+                n->T[dst] = Gn->T[src];
+                n->p[dst] = Gn->p[src];
+            }
+        n->apply_bcs(n->rho, 1, n->bc_rho); n->apply_bcs(n->U, 3, n->bc_U); n->apply_bcs(n->T, 1, n->bc_T); n->apply_bcs(n->p, 1, n->bc_p);
+        // 4. a communicator for the new parts: rank 0 draws the id, the old communicator carries it
+        unsigned char id[128];
+        std::memset(id, 0, sizeof id);
+        if (rank == 0 && nsem_get_unique_id(id)) throw Error(nsem_last_error(nullptr));
+        if (nsem_allreduce_host(s->ctx, id, sizeof id, 1)) throw Error(nsem_last_error(s->ctx));
+        n->attach_device(device, rank, nranks, id);
+        if (verbose) std::printf("regrid[%d]: part of %zu cells, %zu neighbours\n", rank, n->cellGlobal.size(), n->peers.size());
+        s = std::move(n);
+        G = std::move(Gn);
+    };
+    const long last = s->end_step;
+    long dump = s->start_step;
+    regrid(dump);
+    while (dump * s->write_interval < last) {
+        const long upto = std::min(last, (dump + s->amr_step) * s->write_interval);
+        s->start_step = dump;
+        s->end_step = upto;
+        s->run();
+        s->end_step = last;
+        dump = upto / s->write_interval;
+        if (upto < last) regrid(dump);
+    }
+}
+
 void run_case(std::unique_ptr<EulerSolver>& s) {
     if (s->amr_step == 0) { s->run(); return; }
+    if (s->nranks > 1) { run_case_partitioned(s); return; }
     auto regrid = [&](long dump) {
         std::unique_ptr<EulerSolver> n = s->regridded_by_indicator();
         const u32 before = s->geo.nBCS;

@@ -289,6 +289,10 @@ struct EulerSolver {
     // done; when this solver is attached the new one is attached to the same device and takes the state (adopt_refined_state, restart)
     std::unique_ptr<EulerSolver> regridded(const std::vector<uint8_t>& refine, const std::vector<uint8_t>& coarsen);
     std::unique_ptr<EulerSolver> regridded_by_indicator();   // amr_tag_cells on the downloaded state, then regridded()
+    void copy_run_parameters(EulerSolver& n) const;       // controls, physics, AMR and output settings (not the mesh, fields or device)
+    // regrid on several partitions (run_case): the whole-domain solver keeps the grid its regrid emitted so that the parts can be cut from it
+    bool keep_regrid_grid = false;
+    std::shared_ptr<Grid> regrid_grid;
     void write_amr_grid(long dump) const;                 // <mesh>_<dump>.txt + <mesh>_<dump>.forest in the case directory
     void download();
     void write_fields(int index);                         // Mesh::write_fields; with nranks > 1 into <case>/grid<rank>/ like the

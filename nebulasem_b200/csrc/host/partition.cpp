@@ -38,11 +38,41 @@ static void face_cells(const Grid& g, std::vector<u32>& foc, std::vector<u32>& f
 }
 
 static std::vector<u32> partition_cells_raw(const Grid& g, int nparts, const std::string& method, const int nxyz[3],
-                                            const std::vector<u32>* face_mortar);
+                                            const std::vector<u32>* cluster_root);
+
+// Cells joined by non-conforming faces form clusters that must stay in one part (both sides of a mortar are evaluated by one rank,
+// field.cpp:1215-1220): root[c] = the smallest cell index of c's cluster.
+static std::vector<u32> mortar_clusters(const Grid& g, const std::vector<u32>& face_mortar) {
+    std::vector<u32> foc, fnc, root(g.nCells());
+    face_cells(g, foc, fnc);
+    for (u32 c = 0; c < g.nCells(); c++) root[c] = c;
+    auto find = [&](u32 c) { while (root[c] != c) { root[c] = root[root[c]]; c = root[c]; } return c; };
+    for (u32 f = 0; f < g.nFacets(); f++)
+        if (face_mortar[f] != 0 && fnc[f] != MAX_INT) {
+            const u32 a = find(foc[f]), b = find(fnc[f]);
+            if (a != b) root[std::max(a, b)] = std::min(a, b);
+        }
+    for (u32 c = 0; c < g.nCells(); c++) root[c] = find(c);
+    return root;
+}
 
 std::vector<u32> partition_cells(const Grid& g, int nparts, const std::string& method, const int nxyz[3],
                                  const std::vector<u32>* face_mortar) {
-    std::vector<u32> part = partition_cells_raw(g, nparts, method, nxyz, face_mortar);
+    std::vector<u32> part;
+    if (face_mortar && nparts > 1) {
+        // the reference weighs mortar faces 1000 in the METIS graph (field.cpp:1037-1047), which makes cutting one unlikely but not
+        // impossible (a tight balance on a few hundred cells does it).  Here the clusters are contracted first: METIS sees one vertex of
+        // weight |cluster| per cluster (the edge weights count the faces between clusters), the other methods place a cluster where its
+        // first cell goes -- a non-conforming face cannot be cut
+        const std::vector<u32> root = mortar_clusters(g, *face_mortar);
+        if (method == "METIS") part = partition_cells_raw(g, nparts, method, nxyz, &root);
+        else {
+            part = partition_cells_raw(g, nparts, method, nxyz, nullptr);
+            for (u32 c = 0; c < g.nCells(); c++) part[c] = part[root[c]];
+        }
+    } else {
+        part = partition_cells_raw(g, nparts, method, nxyz, nullptr);
+    }
     if (face_mortar && nparts > 1) {
         // a non-conforming face must not be cut: both sides of a mortar are evaluated by one rank (field.cpp:1215-1220)
         std::vector<u32> foc, fnc;
@@ -55,7 +85,7 @@ std::vector<u32> partition_cells(const Grid& g, int nparts, const std::string& m
 }
 
 static std::vector<u32> partition_cells_raw(const Grid& g, int nparts, const std::string& method, const int nxyz[3],
-                                            const std::vector<u32>* face_mortar) {
+                                            const std::vector<u32>* cluster_root) {
     const u32 nc = g.nCells();
     std::vector<u32> part(nc, 0);
     if (nparts <= 1) return part;
@@ -93,19 +123,56 @@ static std::vector<u32> partition_cells_raw(const Grid& g, int nparts, const std
 #ifdef NSEM_WITH_METIS
         std::vector<u32> foc, fnc;
         face_cells(g, foc, fnc);
-        std::vector<int64_t> deg(nc + 1, 0);
-        for (u32 f = 0; f < g.nFacets(); f++)
-            if (fnc[f] != MAX_INT) { deg[foc[f] + 1]++; deg[fnc[f] + 1]++; }
-        for (u32 c = 0; c < nc; c++) deg[c + 1] += deg[c];
-        std::vector<int64_t> adj(deg[nc]), wgt(deg[nc], 1), fill(deg.begin(), deg.end() - 1);
-        bool weighted = false;
-        for (u32 f = 0; f < g.nFacets(); f++)
-            if (fnc[f] != MAX_INT) {
-                const int64_t w = (face_mortar && (*face_mortar)[f] != 0) ? 1000 : 1;     // field.cpp:1037-1047
-                weighted = weighted || w != 1;
-                wgt[fill[foc[f]]] = w; adj[fill[foc[f]]++] = fnc[f];
-                wgt[fill[fnc[f]]] = w; adj[fill[fnc[f]]++] = foc[f];
+        // vertices of the graph: cells, or clusters of cells joined by non-conforming faces (cluster_root)
+        std::vector<u32> vid(nc);
+        std::vector<int64_t> vw;
+        if (cluster_root) {
+            std::vector<u32> id(nc, MAX_INT);
+            for (u32 c = 0; c < nc; c++) {
+                const u32 r = (*cluster_root)[c];
+                if (id[r] == MAX_INT) { id[r] = (u32)vw.size(); vw.push_back(0); }
+                vid[c] = id[r];
+                vw[vid[c]]++;
             }
+        } else {
+            for (u32 c = 0; c < nc; c++) vid[c] = c;
+        }
+        const u32 nvx = cluster_root ? (u32)vw.size() : nc;
+        if ((int)nvx < nparts) throw Error("decomposition: " + std::to_string(nvx) + " clusters of cells joined by non-conforming faces cannot fill " + std::to_string(nparts) + " parts");
+        // edges between different vertices, parallel faces merged into one weighted edge
+        std::vector<std::pair<uint64_t, int64_t>> ed;
+        ed.reserve((size_t)g.nFacets() * 2);
+        for (u32 f = 0; f < g.nFacets(); f++)
+            if (fnc[f] != MAX_INT && vid[foc[f]] != vid[fnc[f]]) {
+                const u32 a = vid[foc[f]], b = vid[fnc[f]];
+                ed.push_back({((uint64_t)a << 32) | b, 1});
+                ed.push_back({((uint64_t)b << 32) | a, 1});
+            }
+        std::sort(ed.begin(), ed.end());
+        std::vector<int64_t> deg(nvx + 1, 0), adj, wgt;
+        bool weighted = false;
+        if (!cluster_root) {
+            // conforming grid: the element graph with the neighbours in face order (one edge per face, field.cpp:1010-1047)
+            ed.clear();
+            for (u32 f = 0; f < g.nFacets(); f++)
+                if (fnc[f] != MAX_INT) { deg[foc[f] + 1]++; deg[fnc[f] + 1]++; }
+            for (u32 c = 0; c < nc; c++) deg[c + 1] += deg[c];
+            adj.assign(deg[nc], 0); wgt.assign(deg[nc], 1);
+            std::vector<int64_t> fill(deg.begin(), deg.end() - 1);
+            for (u32 f = 0; f < g.nFacets(); f++)
+                if (fnc[f] != MAX_INT) { adj[fill[foc[f]]++] = fnc[f]; adj[fill[fnc[f]]++] = foc[f]; }
+        }
+        for (size_t i = 0; i < ed.size();) {
+            size_t j = i;
+            int64_t w = 0;
+            while (j < ed.size() && ed[j].first == ed[i].first) { w += ed[j].second; j++; }
+            adj.push_back((int64_t)(ed[i].first & 0xffffffffu));
+            wgt.push_back(w);
+            weighted = weighted || w != 1;
+            deg[(ed[i].first >> 32) + 1]++;
+            i = j;
+        }
+        if (cluster_root) for (u32 v = 0; v < nvx; v++) deg[v + 1] += deg[v];
         int64_t opt[40];
         METIS_SetDefaultOptions(opt);
         opt[1] = 0;      // METIS_OPTION_OBJTYPE = METIS_OBJTYPE_CUT
@@ -118,11 +185,12 @@ static std::vector<u32> partition_cells_raw(const Grid& g, int nparts, const std
         // partition gives the same answer bit for bit (tests/mp_gpu_check.py).
         { const char* uf = std::getenv("NSEM_METIS_UFACTOR"); opt[16] = uf ? std::max(1, std::atoi(uf)) : 1; }
         opt[17] = 0;     // METIS_OPTION_NUMBERING: C style
-        int64_t nv = nc, ncon = 1, np = nparts, cut = 0;
-        std::vector<int64_t> p64(nc);
-        const int rc = METIS_PartGraphKway(&nv, &ncon, deg.data(), adj.data(), nullptr, nullptr, weighted ? wgt.data() : nullptr, &np, nullptr, nullptr, opt, &cut, p64.data());
+        int64_t nv = nvx, ncon = 1, np = nparts, cut = 0;
+        std::vector<int64_t> p64(nvx);
+        const int rc = METIS_PartGraphKway(&nv, &ncon, deg.data(), adj.data(), cluster_root ? vw.data() : nullptr, nullptr, weighted ? wgt.data() : nullptr, &np,
+                                           nullptr, nullptr, opt, &cut, p64.data());
         if (rc != 1) throw Error("METIS_PartGraphKway failed with code " + std::to_string(rc));
-        for (u32 c = 0; c < nc; c++) part[c] = (u32)p64[c];
+        for (u32 c = 0; c < nc; c++) part[c] = (u32)p64[vid[c]];
         return part;
 #else
         throw Error("this build has no METIS (libmetis_static.a of the CUDA toolkit was not found)");

@@ -518,6 +518,8 @@ extern "C" void nsem_destroy(nsem_ctx* c) {
 
 extern "C" const char* nsem_last_error(const nsem_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
 
+extern "C" int nsem_device(const nsem_ctx* c) { return c ? c->device : -1; }
+
 extern "C" int nsem_get_unique_id(void* out128) {
 #ifdef NSEM_WITH_NCCL
     ncclUniqueId id;
@@ -2196,6 +2198,33 @@ extern "C" int nsem_diagnostics(nsem_ctx* c, double out[6]) {
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     out[0] = h[0]; out[1] = h[1]; out[2] = h[2] / count; out[3] = h[3]; out[4] = h[4]; out[5] = h[5];
     return 0;
+}
+
+// Sum of a host array over the ranks of the context's communicator, in place (MP::allreduce, mp.h:93-104): what the host side needs
+// around a regrid on several partitions -- assembling the whole-domain state from the parts (every rank fills its own cells, zeros
+// elsewhere: the sum is exact) and handing a fresh communicator id from rank 0 to everybody.  dtype 0 = double, 1 = unsigned byte.
+extern "C" int nsem_allreduce_host(nsem_ctx* c, void* buf, uint64_t count, int dtype) {
+    if (dtype != 0 && dtype != 1) { c->err = "nsem_allreduce_host: dtype must be 0 (double) or 1 (unsigned byte)"; return 1; }
+    if (c->nranks <= 1 || count == 0) return 0;
+#ifdef NSEM_WITH_NCCL
+    if (!c->nccl) { c->err = "nsem_allreduce_host: the context has no communicator"; return 1; }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (join_comm(c)) return 1;
+    const size_t bytes = (size_t)count * (dtype == 0 ? sizeof(double) : 1);
+    const size_t words = (bytes + sizeof(double) - 1) / sizeof(double);
+    DevBuf<double> tmp;
+    CUDA_TRY(c, tmp.alloc(words));
+    CUDA_TRY(c, cudaMemcpyAsync(tmp.p, buf, bytes, cudaMemcpyHostToDevice, c->stream));
+    const ncclResult_t r = g_nccl.AllReduce(tmp.p, tmp.p, (size_t)count, dtype == 0 ? ncclDouble : ncclUint8, ncclSum, c->nccl, c->stream);
+    if (r != ncclSuccess) { c->err = std::string("nsem_allreduce_host: ") + g_nccl.GetErrorString(r); tmp.release(); return 1; }
+    CUDA_TRY(c, cudaMemcpyAsync(buf, tmp.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    tmp.release();
+    return 0;
+#else
+    c->err = "nsem_allreduce_host: built without NCCL";
+    return 1;
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -35,3 +35,26 @@ def test_partitions_tile_the_mesh_and_keep_element_geometry(decomp, nparts, pxyz
         for q in p.peers():
             assert len(p.patch_faces(f"interMesh_{r}_{q}")) > 0
     assert (seen == 1).all()
+
+
+@pytest.mark.parametrize("fixture", ["srtb_amr", "srtb3d_amr"])
+@pytest.mark.parametrize("method,nparts", [("METIS", 2), ("METIS", 3), ("METIS", 5), ("CELLID", 3)])
+def test_decomposition_never_cuts_a_non_conforming_face(fixture, method, nparts):
+    """Cells joined by 2:1 faces are contracted into one graph vertex before METIS (the other methods place such a cluster where its first
+    cell goes), so no decomposition of a regridded mesh can separate the two sides of a mortar (field.cpp:1215-1220; the reference only
+    weighs those edges 1000, which a tight balance on a few hundred cells can still cut).  partition_grid raises if a cut slips through."""
+    from oracle import refio
+    d = os.path.join(ROOT, "tests", "golden", fixture)
+    g = refio.read_grid(os.path.join(d, "grid_0"))
+    part, fmc = host.partition_grid(os.path.join(d, "grid_0"), len(g.cells), len(g.facets), nparts, method)
+    assert np.count_nonzero(fmc) > 0
+    sizes = np.bincount(part, minlength=nparts)
+    assert sizes.sum() == len(g.cells) and (sizes > 0).all(), sizes
+    # both cells of every flagged face in the same part
+    owner = {}
+    for c, faces in enumerate(g.cells):
+        for f in faces:
+            owner.setdefault(f, []).append(c)
+    for f, cs in owner.items():
+        if fmc[f] and len(cs) == 2:
+            assert part[cs[0]] == part[cs[1]], f
