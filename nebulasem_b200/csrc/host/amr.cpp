@@ -91,8 +91,16 @@ void AmrForest::init(const Grid& g, const Vec3& direction) {
 }
 
 int AmrForest::split_mask(const Node& n) const {
-    const double dl = std::sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+    double dl = std::sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
     if (dl == 0) return 7;
+    Vec3 dir = this->dir;
+    if (spherical) {
+        // on a cubed sphere the axis that is never split is the radial one: uDir = unit(cell centre) (mesh.cpp:1299)
+        dir = Vec3{0, 0, 0};
+        for (int k = 0; k < 8; k++) for (int d = 0; d < 3; d++) dir[d] += V[n.v[k]][d];
+        dl = std::sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+        if (dl == 0) return 7;
+    }
     const int far[3] = {1, 3, 4};
     int best = 0;
     double bestv = -1;
@@ -464,7 +472,7 @@ void AmrForest::load(const std::string& path) {
 static bool pair_cyclic_owners(const EulerSolver& s, std::vector<uint8_t>& refine, std::vector<uint8_t>& coarsen, bool check_only);
 
 void amr_tag_cells(const EulerSolver& s, const RefineParams& rp, const std::vector<int>& levels, const std::vector<std::vector<u32>>& families,
-                   std::vector<uint8_t>& refine, std::vector<uint8_t>& coarsen) {
+                   std::vector<uint8_t>& refine, std::vector<uint8_t>& coarsen, const std::vector<double>* node_volumes) {
     const u32 nB = s.geo.nBCS;
     const int NP = Basis(s.nop).NP;
     const uint64_t n = (uint64_t)nB * NP;
@@ -475,7 +483,8 @@ void amr_tag_cells(const EulerSolver& s, const RefineParams& rp, const std::vect
     else if (rp.field == "U") { f = &s.U; comps = 3; }
     else throw Error("refinement{field " + rp.field + "}: rho, U, T or p expected");
     // qoi = sqrt(|f|) * (cV^(1/8) / max), normalised to max 1 (calcQOI, field.cpp:606-620)
-    const std::vector<double>& cV = s.geo.cV;
+    const std::vector<double>& cV = node_volumes ? *node_volumes : s.geo.cV;
+    if (cV.size() < n) throw Error("amr_tag_cells: node volumes do not cover the mesh");
     std::vector<double> qoi(n);
     double maxdx = -1e30;
     for (uint64_t i = 0; i < n; i++) maxdx = std::max(maxdx, std::fabs(std::pow(cV[i], 0.125)));
@@ -749,7 +758,20 @@ std::unique_ptr<EulerSolver> EulerSolver::regridded_by_indicator() {
     if (!forest) throw Error("EulerSolver::regridded_by_indicator: no AMR forest");
     if (ctx) download();
     std::vector<uint8_t> refine, coarsen;
-    amr_tag_cells(*this, refine_params, forest->levels(), forest->families(), refine, coarsen);
+    if (topo.spherical) {
+        // Prepare::refineMesh loads a spherical mesh twice (field.cpp:638-645): projected, for the volumes the field transfer uses, and
+        // then as the grid file has it -- the cube shell, still with the spherical corrections of calcGeometry and of the node placement --
+        // and it is THAT load's node volumes calcQOI weighs the indicator with (field.cpp:606-620)
+        MeshTopo flat;
+        flat.spherical = true; flat.sphere_radius = topo.sphere_radius; flat.sphere_height = topo.sphere_height; flat.no_extrude = true;
+        flat.load(forest->grid());
+        if (flat.nBCS != topo.nBCS) throw Error("regridded_by_indicator: the forest's grid and the solver's mesh differ");
+        Geometry fg;
+        fg.build(flat, Basis(nop));
+        amr_tag_cells(*this, refine_params, forest->levels(), forest->families(), refine, coarsen, &fg.cV);
+    } else {
+        amr_tag_cells(*this, refine_params, forest->levels(), forest->families(), refine, coarsen, nullptr);
+    }
     return regridded(refine, coarsen);
 }
 

@@ -107,8 +107,6 @@ void EulerSolver::read_controls(const std::string& case_dir) {
     refine_params.max_level = (int)ctl.integer("refinement", "max_level", refine_params.max_level);
     refine_params.buffer_zone = (int)ctl.integer("refinement", "buffer_zone", refine_params.buffer_zone);
     refine_params.limit = ctl.integer("refinement", "limit", refine_params.limit);
-    if (amr_step != 0 && topo.spherical)
-        throw Error("adaptive regridding of a spherical mesh (field.cpp:638-645,921-924) is not built; set NSEM_IGNORE_AMR_STEP=1 to run on the grid as it is");
     if (ctl.str("general", "state", "STEADY") != "TRANSIENT") throw Error("state must be TRANSIENT");
 }
 
@@ -143,6 +141,7 @@ void EulerSolver::set_mesh(const Grid& g) {
             catch (const Error&) { forest.reset(); }  // a grid that is already non-conforming cannot seed the forest: regridded() says so
         }
     }
+    if (forest) forest->spherical = topo.spherical;
     forest_file.clear();
 }
 

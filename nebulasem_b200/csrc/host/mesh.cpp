@@ -517,7 +517,9 @@ void MeshTopo::extrude() {
 void MeshTopo::sphere_geometry() {
     for (u32 i = 0; i < nBCS; i++) {
         const u32* c = &cellFaces[cellStart[i]];
-        if (cellStart[i + 1] - cellStart[i] != 6) throw Error("spherical meshes need conforming hexahedra (cell " + std::to_string(i) + ")");
+        // a cell next to refined ones lists more than six facets (its split sides); like the reference the loop below visits entries 2..5
+        // only -- every sub-facet is one of the entries 2..5 of the fine cell on its other side
+        if (cellStart[i + 1] - cellStart[i] < 6) throw Error("spherical meshes need hexahedral cells (cell " + std::to_string(i) + ")");
         const double radiusb = mag(V[facetVerts[facetStart[c[0]]]]);
         const double radiust = mag(V[facetVerts[facetStart[c[1]]]]);
         CC[i] = mul(CC[i], (radiusb + radiust) / (2 * mag(CC[i])));
@@ -627,7 +629,7 @@ void MeshTopo::load(const Grid& g) {
     boundaries = g.boundaries;
     add_boundary_cells();
     fix_hex_cells();
-    if (spherical) extrude();
+    if (spherical && !no_extrude) extrude();
     calc_geometry();
     std::vector<u32> del = boundaries["delete"];
     boundaries.erase("delete");

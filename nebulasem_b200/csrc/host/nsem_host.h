@@ -108,6 +108,7 @@ struct MeshTopo {
     // the two cubes of the WHOLE grid (smallest and largest max|coordinate| over its vertices); when set (shell_h[1] > 0) extrude() uses
     // them instead of this mesh's own extremes, so that a partition that does not reach both shells is projected like the whole mesh
     double shell_h[2] = {0, 0};
+    bool no_extrude = false;             // LoadMesh(step, first, extrude = false): the cube shell as the grid file has it (the AMR tagging's volumes)
     u32 nFacets() const { return (u32)facetStart.size() - 1; }
     u32 nCells() const { return (u32)cellStart.size() - 1; }
     void load(const Grid& g);            // Mesh::LoadMesh
@@ -199,6 +200,7 @@ struct AmrForest {
     std::map<std::array<u32, 4>, u32> faceMid;
     std::map<std::array<u32, 4>, std::string> patchOf;    // boundary quads of every level -> patch name
     Vec3 dir{0, 0, 0};
+    bool spherical = false;                    // cubed sphere: the axis a 2-D refinement never splits is the radial one of each cell
     void init(const Grid& conforming_hex_grid, const Vec3& direction);
     Maps regrid(const std::vector<uint8_t>& refine, const std::vector<uint8_t>& coarsen);   // one flag per current cell
     Grid grid() const;                         // the current grid in the reference's format
@@ -217,7 +219,7 @@ struct EulerSolver;
 // Prepare::refineMesh's tagging (field.cpp:606-620, 696-824): normalised indicator sqrt(|field|) (cV^0.125 / max), element means against
 // field_max / field_min, buffer zone, limits, whole families only, 2:1 balance across faces.  `levels` = refinement level per cell.
 void amr_tag_cells(const EulerSolver& s, const RefineParams& rp, const std::vector<int>& levels, const std::vector<std::vector<u32>>& families,
-                   std::vector<uint8_t>& refine, std::vector<uint8_t>& coarsen);
+                   std::vector<uint8_t>& refine, std::vector<uint8_t>& coarsen, const std::vector<double>* node_volumes = nullptr);
 
 // ---- the solver app ------------------------------------------------------------------------------------------------
 struct EulerSolver {

@@ -1,5 +1,5 @@
-"""Golden fixture for an AMR RUN (BASELINE configs[4]): examples/atmo/srtb-amr as it ships, `amr_step 1`, `write_interval 50`, 100 steps,
-run by the UNMODIFIED reference binary (oracle/_ref/parity/{mesh,euler}).
+"""Golden fixtures for AMR RUNS by the UNMODIFIED reference binary (oracle/_ref/parity/{mesh,euler}): examples/atmo/srtb-amr as it ships
+(BASELINE configs[4]; `amr_step 1`, `write_interval 50`, 100 steps) and a reduced examples/atmo/acoustic-sphere-amr-dg (cubed sphere).
 
     python tests/golden/make_amr_run_golden.py          (build container: /root/reference + oracle/build_ref.sh)
 
@@ -21,20 +21,44 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from oracle import refio, run_ref  # noqa: E402
 from oracle.dg import Basis, Geometry  # noqa: E402
+from oracle.euler import Params  # noqa: E402
 from oracle.mesh import MeshTopo  # noqa: E402
 
-EX = "/root/reference/examples/atmo/srtb-amr"
-NSTEPS, INTERVAL = 100, 50
+EXAMPLES = "/root/reference/examples/atmo"
+
+
+def load_topo(grid, params):
+    topo = MeshTopo(grid)
+    topo.spherical, topo.sphere_radius, topo.sphere_height = params.is_spherical, params.sphere_radius, params.sphere_height
+    return topo.load()
 
 
 def main():
-    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "amr_run", "srtb-amr")
-    d = os.path.join(tempfile.mkdtemp(prefix="amr_run_"), "srtb-amr")
+    make("srtb-amr", 100, 50)
+    # a cubed-sphere AMR run: examples/atmo/acoustic-sphere-amr-dg at its 10 x 10 cells per panel, order 2, 10 steps per dump (the example:
+    # order 4, 240): regrid of the pressure pulse before step 1 (2-D refinement, the radial axis of every cell is never split) and after dump 1
+    make("acoustic-sphere-amr-dg", 20, 10, divisions=(10, 10, 1), nop=(2, 2, 0))
+
+
+def make(name, NSTEPS, INTERVAL, divisions=None, nop=None):
+    EX = os.path.join(EXAMPLES, name)
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "amr_run", name)
+    d = os.path.join(tempfile.mkdtemp(prefix="amr_run_"), name)
     shutil.copytree(EX, d)
+    for f in os.listdir(d):
+        os.chmod(os.path.join(d, f), 0o644)
     block = [f for f in os.listdir(d) if f != "controls" and not f.endswith((".txt", ".sh"))][0]
+    if divisions:
+        blk = open(os.path.join(d, block)).read()
+        blk, cnt = re.subn(r"(?m)^(8\{[^}]*\}\s+linear\s+)3\{\d+ \d+ \d+\}", r"\g<1>3{%d %d %d}" % divisions, blk)
+        assert cnt == 6
+        open(os.path.join(d, block), "w").write(blk)
     m = subprocess.run([run_ref.ref_bin("mesh"), block, "-o", "grid_0.bin"], cwd=d, capture_output=True, text=True, timeout=600)
     assert m.returncode == 0, m.stdout[-1000:] + m.stderr[-1000:]
     ctl = open(os.path.join(d, "controls")).read()
+    if nop:
+        for k, v in zip(("npx", "npy", "npz"), nop):
+            ctl = re.sub(rf"(?m)^(\s*){k}\s+\d+", rf"\g<1>{k} {v}", ctl)
     ctl = re.sub(r"(?m)^(\s*)end_step\s+\d+", rf"\g<1>end_step {NSTEPS}", ctl)
     ctl = re.sub(r"(?m)^(\s*)write_interval\s+\d+", rf"\g<1>write_interval {INTERVAL}", ctl)
     ctl = re.sub(r"(?m)^(\s*)write_format\s+\w+", r"\g<1>write_format BINARY", ctl)
@@ -47,9 +71,10 @@ def main():
     wall, log = run_ref.run_euler(d, variant="parity", timeout=1800)
     print("\n".join(l for l in log.splitlines() if "Refining" in l or "loss" in l)[-1500:])
     nop = [int(re.search(rf"(?m)^\s*{k}\s+(\d+)", ctl).group(1)) for k in ("npx", "npy", "npz")]
+    params = Params.from_controls(refio.read_controls(os.path.join(d, "controls")))
     keep = {}
     for k in (0, 1):
-        topo = MeshTopo(refio.read_grid(os.path.join(d, f"grid_{k}"), prefer_bin=True)).load()
+        topo = load_topo(refio.read_grid(os.path.join(d, f"grid_{k}"), prefer_bin=True), params)
         nb = topo.nBCS
         keep[f"grid{k}_CC"] = np.asarray(topo.CC)[:nb]
         keep[f"grid{k}_CV"] = np.asarray(topo.CV)[:nb]
@@ -65,7 +90,7 @@ def main():
     os.chmod(os.path.join(d50, "controls"), 0o644)
     open(os.path.join(d50, "controls"), "w").write(re.sub(r"(?m)^(\s*)end_step\s+\d+", rf"\g<1>end_step {INTERVAL}", ctl))
     run_ref.run_euler(d50, variant="parity", timeout=1800)
-    topo0 = MeshTopo(refio.read_grid(os.path.join(d50, "grid_0"), prefer_bin=True)).load()
+    topo0 = load_topo(refio.read_grid(os.path.join(d50, "grid_0"), prefer_bin=True), params)
     geo0 = Geometry(topo0, Basis(nop))
     n0 = geo0.gBCSfield
     half = run_ref.read_dump(d50, 1)

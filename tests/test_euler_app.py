@@ -166,8 +166,8 @@ def test_restart_reads_the_dump_start_step_names_and_the_newest_older_grid(tmp_p
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world", [1, 2])
-def test_amr_run_matches_the_reference_run(tmp_path, world):
+@pytest.mark.parametrize("case,world", [("srtb-amr", 1), ("srtb-amr", 2), ("acoustic-sphere-amr-dg", 1), ("acoustic-sphere-amr-dg", 2)])
+def test_amr_run_matches_the_reference_run(tmp_path, case, world):
     """BASELINE configs[4]: examples/atmo/srtb-amr exactly as it ships (amr_step 1), write_interval 50, 100 steps, through the drop-in
     `euler ./controls` on one GPU against the dump the UNMODIFIED reference binary wrote of the same run (tests/golden/amr_run/, made by
     make_amr_run_golden.py).  Both do what iteration.h:94-147 + euler.cpp:57-287 prescribe: start-branch set-up on the coarse grid, regrid
@@ -176,8 +176,10 @@ def test_amr_run_matches_the_reference_run(tmp_path, world):
     reference's facet splitting, so cells are matched by centroid and nodes by position; then rho, rho*theta <= 1e-11 and rho*U <= 1e-11 of
     ||rho|| c0 (north_star), on a mesh with non-conforming faces, after two regrids and their field transfers."""
     from nebulasem_b200 import host
-    src = os.path.join(ROOT, "tests", "golden", "amr_run", "srtb-amr")
-    a = str(tmp_path / "srtb-amr")
+    # acoustic-sphere-amr-dg: the same on a cubed sphere (examples/atmo/acoustic-sphere-amr-dg at order 2, 20 steps: 600 -> 672 -> 612 cells;
+    # 2-D refinement that never splits a cell's radial axis, tags weighed with the un-projected mesh's volumes as Prepare::refineMesh does)
+    src = os.path.join(ROOT, "tests", "golden", "amr_run", case)
+    a = str(tmp_path / case)
     shutil.copytree(src, a)
     exp = np.load(os.path.join(a, "expected.npz"))
     os.remove(os.path.join(a, "expected.npz"))

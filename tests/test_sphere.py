@@ -128,6 +128,30 @@ def test_partitions_of_the_shell_are_projected_like_the_whole_mesh(tmp_path):
     g.close()
 
 
+def test_regrid_of_the_shell_tags_and_splits_like_the_reference(tmp_path):
+    """The initial regrid of the reduced examples/atmo/acoustic-sphere-amr-dg (tests/golden/amr_run/, made by the reference's euler binary):
+    Prepare::refineMesh weighs the indicator with the node volumes of the UN-projected load of the mesh (field.cpp:606-645) and never
+    splits a cell's radial axis (uDir = unit(cell centre), mesh.cpp:1299); new vertices are placed on the cube shell and projected with
+    the rest.  Same 24 cells refined (600 -> 672), same centroids and curved-element volumes."""
+    from nebulasem_b200 import host
+    src = os.path.join(os.path.dirname(GOLD), "amr_run", "acoustic-sphere-amr-dg")
+    d = str(tmp_path / "case")
+    shutil.copytree(src, d)
+    exp = np.load(os.path.join(d, "expected.npz"))
+    s = host.Solver.open_case(d)
+    assert s.nBCS == 600
+    s.regrid()
+    assert s.nBCS == exp["grid0_CC"].shape[0] == 672
+    cc, cv = s.f64("gCC")[: 3 * s.nBCS].reshape(-1, 3), s.f64("gCV")[: s.nBCS]
+    s.close()
+    scale = np.abs(exp["grid0_CC"]).max()
+    key = lambda x: np.round(x / scale * 1e6).astype(np.int64)
+    oa, ob = np.lexsort(key(cc).T[::-1]), np.lexsort(key(exp["grid0_CC"]).T[::-1])
+    assert np.array_equal(key(cc)[oa], key(exp["grid0_CC"])[ob])
+    assert np.abs(cc[oa] - exp["grid0_CC"][ob]).max() <= 1e-12 * scale
+    assert np.abs(cv[oa] / exp["grid0_CV"][ob] - 1).max() <= 1e-11
+
+
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["hydro-sphere", "acoustic-sphere", "advection-sphere"])
