@@ -73,11 +73,10 @@ void AmrForest::init(const Grid& g, const Vec3& direction) {
             if (b == MAX_INT) throw Error("AmrForest: cell " + std::to_string(c) + " is not a hexahedron");
             n.v[k] = a; n.v[k + 4] = b;
         }
-        // right-handed frame: (c1-c0) x (c3-c0) must point towards c4
-        auto sub = [&](u32 a, u32 b) { return Vec3{V[a][0] - V[b][0], V[a][1] - V[b][1], V[a][2] - V[b][2]}; };
-        const Vec3 e1 = sub(n.v[1], n.v[0]), e2 = sub(n.v[3], n.v[0]), e3 = sub(n.v[4], n.v[0]);
-        const double trip = (e1[1] * e2[2] - e1[2] * e2[1]) * e3[0] + (e1[2] * e2[0] - e1[0] * e2[2]) * e3[1] + (e1[0] * e2[1] - e1[1] * e2[0]) * e3[2];
-        if (trip < 0) { std::swap(n.v[1], n.v[3]); std::swap(n.v[5], n.v[7]); }
+        // The frame stays as the grid file has it, left-handed cells included (three of the six panels of the reference's cubed-sphere block
+        // files are): cells a regrid does not touch must be re-emitted with the local axes they had, because fields are copied node by node
+        // (refineField, field.h:1877-1883) and, on the sphere, even the positions of an element's interior nodes depend on which of its
+        // axes is which (the radial rescale of the node placement, dg.cpp:257-285, is not symmetric in them)
         nodes.push_back(n);
         leaves.push_back((int)nodes.size() - 1);
     }

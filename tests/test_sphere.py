@@ -140,9 +140,23 @@ def test_regrid_of_the_shell_tags_and_splits_like_the_reference(tmp_path):
     exp = np.load(os.path.join(d, "expected.npz"))
     s = host.Solver.open_case(d)
     assert s.nBCS == 600
+    old_nodes = s.f64("cC").reshape(-1, 3)[: s.gBCSfield].reshape(s.nBCS, s.NP, 3).copy()
     s.regrid()
     assert s.nBCS == exp["grid0_CC"].shape[0] == 672
     cc, cv = s.f64("gCC")[: 3 * s.nBCS].reshape(-1, 3), s.f64("gCV")[: s.nBCS]
+    new_nodes = s.f64("cC").reshape(-1, 3)[: s.gBCSfield].reshape(s.nBCS, s.NP, 3)
+    # cells the regrid does not touch keep their local axes (three of the six panels are left-handed in the block file): refineField copies
+    # their values node by node, and on the sphere an element's interior nodes sit where they do because of which axis is which
+    cell_map = s.u32("cellMap")[:600]               # one entry per old cell first (the new cells' entries follow, mesh.cpp:2216-2748)
+    kept = np.nonzero(cell_map < s.nBCS)[0]
+    assert len(kept) == 600 - 24
+    assert np.abs(new_nodes[cell_map[kept]] - old_nodes[kept]).max() <= 1e-8
+    # and every node of the regridded mesh is where the reference's geometry of ITS regridded grid has it
+    from scipy.spatial import cKDTree
+    mine = np.concatenate([np.repeat(cc, s.NP, axis=0), new_nodes.reshape(-1, 3)], axis=1)
+    ref = np.concatenate([np.repeat(exp["grid0_CC"], int(exp["NP"]), axis=0), exp["half_node_xyz"]], axis=1)
+    dist, idx = cKDTree(ref).query(mine)
+    assert dist.max() <= 1e-7 and len(np.unique(idx)) == len(idx), dist.max()
     s.close()
     scale = np.abs(exp["grid0_CC"]).max()
     key = lambda x: np.round(x / scale * 1e6).astype(np.int64)
