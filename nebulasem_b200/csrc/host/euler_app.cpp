@@ -946,6 +946,7 @@ static void run_case_partitioned(std::unique_ptr<EulerSolver>& s) {
         if (verbose) std::printf("regrid[%d]: part of %zu cells, %zu neighbours\n", rank, n->cellGlobal.size(), n->peers.size());
         s = std::move(n);
         G = std::move(Gn);
+        if (std::getenv("NSEM_DEBUG_REGRID")) { s->write_fields(100 + (int)dump); s->merge_fields(100 + (int)dump); }
     };
     const long last = s->end_step;
     long dump = s->start_step;
@@ -970,6 +971,7 @@ void run_case(std::unique_ptr<EulerSolver>& s) {
         s = std::move(n);
         s->write_amr_grid(dump);
         std::printf("Regrid at dump %ld: %u -> %u cells\n", dump, before, s->geo.nBCS);
+        if (std::getenv("NSEM_DEBUG_REGRID")) { s->download(); s->write_fields(100 + (int)dump); }
     };
     const long last = s->end_step;
     long dump = s->start_step;

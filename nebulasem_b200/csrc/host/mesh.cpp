@@ -525,7 +525,11 @@ void MeshTopo::sphere_geometry() {
         CC[i] = mul(CC[i], (radiusb + radiust) / (2 * mag(CC[i])));
         FC[c[0]] = mul(FC[c[0]], radiusb / mag(FC[c[0]]));
         FC[c[1]] = mul(FC[c[1]], radiust / mag(FC[c[1]]));
-        for (int j = 2; j < 6; j++) {
+        const int nfac = (int)(cellStart[i + 1] - cellStart[i]);
+        for (int j = 2; j < nfac; j++) {
+            // The reference stops at entry 5 (mesh.cpp:529): a further sub-facet of a split side is corrected from the cell on its other
+            // side.  In a partition that cell can be on another rank; then, and only then, it is done from here (same radii: one layer)
+            if (j >= 6 && std::min(FOC[c[j]], FNC[c[j]]) < nBCS && std::max(FOC[c[j]], FNC[c[j]]) < nBCS) continue;
             FC[c[j]] = mul(FC[c[j]], (radiusb + radiust) / (2 * mag(FC[c[j]])));
             // area of a vertical face: half the geodesic length of its outline times the shell thickness
             double d = 0;

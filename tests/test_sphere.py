@@ -166,6 +166,43 @@ def test_regrid_of_the_shell_tags_and_splits_like_the_reference(tmp_path):
     assert np.abs(cv[oa] / exp["grid0_CV"][ob] - 1).max() <= 1e-11
 
 
+def test_partitions_of_a_regridded_shell_keep_the_face_geometry(tmp_path):
+    """The curved-element corrections visit entries 2..5 of a cell's facet list (mesh.cpp:529); a further sub-facet of a split side gets its
+    area and centre from the cell on its other side -- which a partition may not hold.  Then the cell that does hold it applies them, so the
+    faces of every part equal those of the whole mesh (this was 1e-6 in the solution of a two-partition AMR run before)."""
+    import re
+
+    from nebulasem_b200 import host
+    d = str(tmp_path / "case")
+    shutil.copytree(os.path.join(os.path.dirname(GOLD), "amr_run", "acoustic-sphere-amr-dg"), d)
+    s = host.Solver.open_case(d)
+    s.regrid()
+    s.write_amr_grid(0)                                  # grid_0.bin is now the regridded mesh (2:1 faces along the refined patch)
+    s.close()
+    os.remove(os.path.join(d, "grid_0.forest"))
+    ctl = re.sub(r"(?m)^\s*amr_step\s+\d+\s*\n", "", open(os.path.join(d, "controls")).read())
+    open(os.path.join(d, "controls"), "w").write(ctl)
+
+    def faces_of_cells(s):
+        fb, fe, af = s.u32("faceBegin"), s.u32("faceEnd"), s.u32("allFaces")
+        area = np.linalg.norm(s.f64("faceNormal").reshape(-1, 3), axis=1)
+        radius = np.linalg.norm(s.f64("faceCenter").reshape(-1, 3), axis=1)
+        return [np.array(sorted(zip(area[af[fb[c]:fe[c]]], radius[af[fb[c]:fe[c]]]))) for c in range(s.nBCS)]
+
+    g = host.Solver.open_case(d)
+    whole = faces_of_cells(g)
+    assert max(len(f) for f in whole) > 4                # cells with a split side are there (radial faces are deleted: 4 = conforming)
+    for nparts in (2, 3, 5):
+        for r in range(nparts):
+            p = host.Solver.open_case(d, 0, r, nparts)
+            mine = faces_of_cells(p)
+            for l, c in enumerate(p.u32("cellGlobal")):
+                assert mine[l].shape == whole[c].shape
+                assert np.abs(mine[l] / whole[c] - 1).max() <= 1e-12, (nparts, r, l, c)
+            p.close()
+    g.close()
+
+
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["hydro-sphere", "acoustic-sphere", "advection-sphere"])
