@@ -168,6 +168,10 @@ int nsem_upload_coords(nsem_ctx* ctx, const double* cC);
 /* Mesh::sphere_radius (src/mesh/mesh.cpp:32) of a cubed-sphere mesh (general{is_spherical YES}); read by problem_init 2 / 3 =
  * LAURITZEN_0 / LAURITZEN_1 (convection.cpp:55-72), the deformational winds on the sphere. */
 int nsem_set_sphere(nsem_ctx* ctx, double radius);
+/* Controls::time_scheme AB2..AB5 for the scalar (ddt + addTemporal, src/field/field.h:3789-3806, 3885-3905): order residuals are kept and
+ * combined with the Adams-Bashforth weights, the first steps use the lower orders as the reference does; order 1 (default) is the single
+ * forward-Euler stage.  Resets the history.  nsem_euler_step does not take it: no euler example asks for a multi-step scheme. */
+int nsem_set_ab_order(nsem_ctx* ctx, int order);
 int nsem_set_convection(nsem_ctx* ctx, int problem_init, double etime, long first_step);
 int nsem_convection_step(nsem_ctx* ctx, int nsteps);
 /* Pipelined variants for drivers that stream batches through the device: both only ENQUEUE and return.  The upload copies on a

@@ -91,8 +91,10 @@ void EulerSolver::read_controls(const std::string& case_dir) {
         throw Error("only convection_scheme RUSANOV is implemented on the GPU path");
     // BDF1, AB1 and RK1..RK4 are the same single forward-Euler stage on this path (SURVEY finding 1)
     const std::string& ts = time_scheme;
-    if (!(ts == "BDF1" || ts == "AB1" || ts == "RK1" || ts == "RK2" || ts == "RK3" || ts == "RK4"))
-        throw Error("time_scheme " + ts + " is not implemented on the GPU path (BDF1, AB1, RK1-RK4 are)");
+    const bool ab_multi = (ts == "AB2" || ts == "AB3" || ts == "AB4" || ts == "AB5");
+    // the scalar of the convection app also takes AB2..AB5 (examples/atmo/advection-leveque ships AB2): residual history on the device
+    if (!(ts == "BDF1" || ts == "AB1" || ts == "RK1" || ts == "RK2" || ts == "RK3" || ts == "RK4" || (convection && ab_multi)))
+        throw Error("time_scheme " + ts + " is not implemented on the GPU path (BDF1, AB1, RK1-RK4 are; AB2-AB5 for solver convection)");
     // cubed-sphere shells (field.cpp:516-519): the mesh loader projects the grid onto the sphere, set-up uses radial gravity
     topo.spherical = ctl.yes("general", "is_spherical", false);
     topo.sphere_radius = ctl.num("general", "sphere_radius", topo.sphere_radius);
@@ -665,6 +667,7 @@ void EulerSolver::attach_device(int device, int rank, int nranks, const void* ui
     if (convection) {
         ck(nsem_upload_coords(ctx, geo.cC.data()));
         if (geo.spherical) ck(nsem_set_sphere(ctx, geo.sphere_radius));
+        if (time_scheme.size() == 3 && time_scheme.compare(0, 2, "AB") == 0) ck(nsem_set_ab_order(ctx, time_scheme[2] - '0'));
         const int kind = conv_init == "LEVEQUE" ? 1 : (conv_init == "LAURITZEN_0" ? 2 : (conv_init == "LAURITZEN_1" ? 3 : 0));
         ck(nsem_set_convection(ctx, kind, (double)end_step * dt, write_interval * start_step + 1));
     }

@@ -146,6 +146,9 @@ struct nsem_ctx {
     int conv_init = 0;                 // 0 = the wind is the uploaded U, 1 = LEVEQUE (re-evaluated at every step)
     double conv_etime = 1.0;           // end_step * dt: the period of the analytic wind
     long conv_step = 0;                // steps taken (Iteration::get_step() - 1)
+    int ab_order = 1;                  // Adams-Bashforth order of the scalar's update (AB2..AB5 keep a residual history; 1 = one forward-Euler stage)
+    int ab_stored = 0, ab_head = 0;    // entries of the history in use (MeshField::nstored), ring position of PREV(0)
+    DevBuf<double> abHist[5];
     DevBuf<double> xyz[3];             // node coordinates (analytic wind only)
     bool speed_valid = false;  // S[cur] = |U| + c of the current state (kept by sweep B + the ghost update; recomputed after the state was set from outside)
     bool has_gh = false;
@@ -1813,6 +1816,16 @@ extern "C" int nsem_set_convection(nsem_ctx* c, int problem_init, double etime, 
     return 0;
 }
 
+// Controls::time_scheme AB1..AB5 for nsem_convection_step (order 1 = the one forward-Euler stage that BDF1, AB1 and RK1-RK4 all are on this
+// path); the residual history starts over (a new field after a regrid or a restart, field.h:3885-3895)
+extern "C" int nsem_set_ab_order(nsem_ctx* c, int order) {
+    if (order < 1 || order > 5) { c->err = "nsem_set_ab_order: order must be 1..5"; return 1; }
+    c->ab_order = order;
+    c->ab_stored = 0;
+    c->ab_head = 0;
+    return 0;
+}
+
 // Mesh::sphere_radius of a cubed-sphere mesh (mesh.cpp:32): only the Lauritzen winds read it, everything else of a spherical case is in
 // the uploaded geometry and the per-node gravity
 extern "C" int nsem_set_sphere(nsem_ctx* c, double radius) {
@@ -1858,6 +1871,28 @@ extern "C" int nsem_convection_step(nsem_ctx* c, int nsteps) {
         fill_kparams(c, P);
         P.visc = 0; P.buoyancy = 0;
         CUDA_TRY(c, launch_mortar(c, P, 0));
+        if (c->ab_order > 1) {
+            // AB2..AB5: the sweep leaves the residual, the update combines it with the stored ones (field.h:3789-3806, 3885-3905)
+            const bool v2 = c->use_v2;
+            if (!c->use_v4) c->use_v2 = false;         // the bulk-staged generation has no residual mode; the plain-load kernels do
+            P.op_mode = 1;
+            const cudaError_t e = launch_sweepA(c, P);
+            c->use_v2 = v2;
+            CUDA_TRY(c, e);
+            ABParams A;
+            std::memset(&A, 0, sizeof A);
+            const bool first = (c->ab_stored == 0);
+            for (int j = 0; j < c->ab_order; j++)
+                if (c->abHist[j].n < c->nNodes) { CUDA_TRY(c, c->abHist[j].alloc(c->nNodes)); }
+            if (!first) c->ab_head = (c->ab_head + c->ab_order - 1) % c->ab_order;      // updateStore: the oldest entry's buffer takes PREV(0)
+            c->ab_stored = first ? 1 : c->ab_stored + 1;
+            A.nB = c->nB; A.NP = c->NP; A.NPS = c->NPS; A.order = c->ab_order; A.use = std::min(c->ab_order, c->ab_stored); A.first = first ? 1 : 0;
+            A.dt = c->prm.dt; A.cV = c->cV.p; A.q_old = P.rho_old; A.r = P.rho_new;
+            for (int j = 0; j < c->ab_order; j++) A.prev[j] = c->abHist[(c->ab_head + j) % c->ab_order].p;
+            const uint64_t nn = (uint64_t)c->nB * c->NPS;
+            ab_update_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, c->stream>>>(A);
+            c->launches++;
+        } else
         CUDA_TRY(c, launch_sweepA(c, P));
         fill_bcparams(c, P, B, 0);
         CUDA_TRY(c, launch_bc(c, B));

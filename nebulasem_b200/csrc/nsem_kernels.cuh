@@ -227,6 +227,37 @@ __global__ void __launch_bounds__(256) wind_leveque_kernel(uint64_t n, double ti
     u2[q] = 0.0;
 }
 
+// Adams-Bashforth update of the transported scalar (ddt, field.h:3789-3806, with the history handling of addTemporal, :3885-3905): `r` holds
+// the residual of this step (the sweep ran in residual mode).  It becomes PREV(0); prev[j] = PREV(j) after the shift, prev[0] is the buffer
+// the oldest entry lived in.  `first`: the field's first step, every entry of the history is this residual (initStore).  `use` = the order
+// actually applied, min(scheme order, entries stored).  T_new = (T ap + combination) / ap with ap = -cV / dt; written over r.
+struct ABParams {
+    uint32_t nB;
+    int NP, NPS, order, use, first;
+    double dt;
+    const double* cV;
+    const double* q_old;
+    double* r;
+    double* prev[5];
+};
+__global__ void __launch_bounds__(256) ab_update_kernel(const __grid_constant__ ABParams A) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (uint64_t)A.nB * A.NPS || (int)(idx % A.NPS) >= A.NP) return;
+    const double r = A.r[idx];
+    if (A.first) for (int j = 1; j < A.order; j++) A.prev[j][idx] = r;
+    A.prev[0][idx] = r;
+    double comb;
+    switch (A.use) {
+        case 5: comb = (1901 * r - 2774 * A.prev[1][idx] + 2616 * A.prev[2][idx] - 1274 * A.prev[3][idx] + 251 * A.prev[4][idx]) / 720.0; break;
+        case 4: comb = (55 * r - 59 * A.prev[1][idx] + 37 * A.prev[2][idx] - 9 * A.prev[3][idx]) / 24.0; break;
+        case 3: comb = (23 * r - 16 * A.prev[1][idx] + 5 * A.prev[2][idx]) / 12.0; break;
+        case 2: comb = (3 * r - A.prev[1][idx]) / 2.0; break;
+        default: comb = r;
+    }
+    const double ap = (-1.0 / A.dt) * A.cV[idx];
+    A.r[idx] = __ddiv_rn(__dadd_rn(__dmul_rn(A.q_old[idx], ap), comb), ap);
+}
+
 // Lauritzen's deformational winds on the sphere (convection.cpp:55-72 with cart_to_sphere and wind_field, tensor.h:598-621): zonal and
 // meridional components from latitude/longitude of the node, turned into a Cartesian vector.  kind 0 = LAURITZEN_0, 1 = LAURITZEN_1.
 __global__ void __launch_bounds__(256) wind_lauritzen_kernel(uint64_t n, int kind, double time, double period, double radius, const double* __restrict__ x,

@@ -65,6 +65,28 @@ class ConvectionOracle(EulerOracle):
         fq = self.U * self.T[:, None]
         r = self.divf(fq, self.T, lam)
         ap0 = (-1.0 / P.dt) * self.g.cV
+        order = int(P.time_scheme[2]) if P.time_scheme.startswith("AB") else 1
+        if order > 1:
+            # AB2..AB5 (ddt, field.h:3789-3806; history of addTemporal, :3885-3905): the field's first step fills the whole history with its
+            # residual (initStore, nstored = 1), later ones shift it (updateStore); the order applied is min(scheme, nstored)
+            hist = getattr(self, "_ab_hist", None)
+            if hist is None:
+                self._ab_hist, self._ab_stored = [r.copy() for _ in range(order)], 1
+            else:
+                self._ab_hist = [r.copy()] + hist[:-1]
+                self._ab_stored += 1
+            h, use = self._ab_hist, min(order, self._ab_stored)
+            if use == 5:
+                comb = (1901 * h[0] - 2774 * h[1] + 2616 * h[2] - 1274 * h[3] + 251 * h[4]) / 720.0
+            elif use == 4:
+                comb = (55 * h[0] - 59 * h[1] + 37 * h[2] - 9 * h[3]) / 24.0
+            elif use == 3:
+                comb = (23 * h[0] - 16 * h[1] + 5 * h[2]) / 12.0
+            elif use == 2:
+                comb = (3 * h[0] - h[1]) / 2.0
+            else:
+                comb = h[0]
+            r = comb
         Su = (r + self.T * ap0) if P.time_scheme.startswith("BDF") else (self.T * ap0 + r)
         T = Su / ap0
         self.apply_bcs("T", T)

@@ -24,7 +24,13 @@ NSTEPS = 40
 
 
 def main():
-    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "convection", "advection-leveque")
+    make("advection-leveque", "AB1")
+    make("advection-leveque-ab2", "AB2")       # the scheme the example ships with: two residuals kept (field.h:3789-3806, 3885-3905)
+    make("advection-leveque-ab4", "AB4")       # the start-up sequence AB1, AB2, AB3, then AB4
+
+
+def make(name, scheme):
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "convection", name)
     d = os.path.join(tempfile.mkdtemp(prefix="conv_golden_"), "advection-leveque")
     shutil.copytree(EX, d)
     block = [f for f in os.listdir(d) if f != "controls" and not f.endswith((".txt", ".sh"))][0]
@@ -35,7 +41,7 @@ def main():
     ctl = re.sub(r"(?m)^(\s*)end_step\s+\d+", rf"\g<1>end_step {NSTEPS}", ctl)
     ctl = re.sub(r"(?m)^(\s*)write_interval\s+\d+", rf"\g<1>write_interval {NSTEPS}", ctl)
     ctl = re.sub(r"(?m)^(\s*)write_format\s+\w+", r"\g<1>write_format BINARY", ctl)
-    ctl = re.sub(r"(?m)^(\s*)time_scheme\s+\w+", r"\g<1>time_scheme AB1", ctl)
+    ctl = re.sub(r"(?m)^(\s*)time_scheme\s+\w+", rf"\g<1>time_scheme {scheme}", ctl)
     ctl = re.sub(r"(?m)^\s*amr_step\s+\d+\s*\n", "", ctl)
     open(os.path.join(d, "controls"), "w").write(ctl)
     shutil.rmtree(out, ignore_errors=True)
@@ -50,7 +56,7 @@ def main():
     T = refio.read_field_values(os.path.join(d, "T1"))[:, 0]
     U = refio.read_field_values(os.path.join(d, "U1"))
     np.savez_compressed(os.path.join(out, "expected.npz"), nsteps=NSTEPS, T=T, U=U)
-    print("advection-leveque", T.shape, U.shape, "T range", T.min(), T.max())
+    print(name, T.shape, U.shape, "T range", T.min(), T.max())
 
 
 if __name__ == "__main__":

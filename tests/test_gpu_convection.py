@@ -40,20 +40,32 @@ def device_from_convection_oracle(orc, device=0):
     ctx.upload_ref(zeros, zeros, None)
     ctx.upload_state(orc.T, orc.U, zeros, zeros)
     ctx.upload_coords(g.cC)
+    if p.time_scheme.startswith("AB"):
+        ctx.set_ab_order(int(p.time_scheme[2]))
     ctx.set_convection(orc.problem_init, orc.end_step * p.dt, 1)
     return ctx
 
 
-def test_oracle_convection_is_bit_identical_to_the_reference_binary():
+SCHEMES = {"AB1": GOLD, "AB2": GOLD + "-ab2", "AB4": GOLD + "-ab4"}        # AB2 is what the example ships; AB4 starts up through AB1, AB2, AB3
+
+
+@pytest.mark.parametrize("scheme", ["AB1", "AB2", "AB4"])
+def test_oracle_convection_is_bit_identical_to_the_reference_binary(scheme):
+    GOLD = SCHEMES[scheme]
     exp = np.load(os.path.join(GOLD, "expected.npz"))
     orc = ocase.load_convection_case(GOLD, exact_order=True)
+    assert orc.p.time_scheme == scheme
     orc.run(int(exp["nsteps"]))
     nb = orc.gB
     assert np.array_equal(orc.T[:nb], exp["T"]) and np.array_equal(orc.U[:nb], exp["U"])
 
 
 @pytest.mark.gpu
-def test_device_convection_matches_the_reference_binary():
+@pytest.mark.parametrize("scheme", ["AB1", "AB2", "AB4"])
+def test_device_convection_matches_the_reference_binary(scheme):
+    """AB2..AB5 (ddt + addTemporal, field.h:3789-3806, 3885-3905): the sweep leaves the residual, ab_update_kernel combines it with the ones
+    it keeps; the field's first steps run the lower orders."""
+    GOLD = SCHEMES[scheme]
     exp = np.load(os.path.join(GOLD, "expected.npz"))
     nsteps = int(exp["nsteps"])
     orc = ocase.load_convection_case(GOLD, exact_order=False)
@@ -104,7 +116,8 @@ def test_device_convection_3d_frozen_wind_matches_oracle(tmp_path):
 
 
 @pytest.mark.gpu
-def test_convection_binary_matches_the_reference_binary(tmp_path):
+@pytest.mark.parametrize("scheme", ["AB1", "AB2"])
+def test_convection_binary_matches_the_reference_binary(tmp_path, scheme):
     """The drop-in app: `convection ./controls` (nebulasem_b200/lib/convection, the same program as lib/euler, the solver chosen by the
     controls) on the reference's own example files writes the T/U dump the reference binary wrote."""
     import shutil
@@ -113,7 +126,7 @@ def test_convection_binary_matches_the_reference_binary(tmp_path):
     from nebulasem_b200 import build
     from oracle import refio
     d = str(tmp_path / "advection-leveque")
-    shutil.copytree(GOLD, d)
+    shutil.copytree(SCHEMES[scheme], d)
     exp = np.load(os.path.join(d, "expected.npz"))
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
     r = subprocess.run([os.path.join(os.path.dirname(build.EULER_BIN), "convection"), "./controls"], cwd=d, env=env, capture_output=True, text=True, timeout=600)
