@@ -478,7 +478,8 @@ void amr_tag_cells(const EulerSolver& s, const RefineParams& rp, const std::vect
     if (levels.size() != nB) throw Error("amr_tag_cells: one level per cell expected");
     const std::vector<double>* f = nullptr;
     int comps = 1;
-    if (rp.field == "T") f = &s.T; else if (rp.field == "p") f = &s.p; else if (rp.field == "rho") f = &s.rho;
+    if (rp.field == "T") f = s.convection ? &s.rho : &s.T;      // the convection app's scalar T lives in the rho slot
+    else if (rp.field == "p") f = &s.p; else if (rp.field == "rho") f = &s.rho;
     else if (rp.field == "U") { f = &s.U; comps = 3; }
     else throw Error("refinement{field " + rp.field + "}: rho, U, T or p expected");
     // qoi = sqrt(|f|) * (cV^(1/8) / max), normalised to max 1 (calcQOI, field.cpp:606-620)
@@ -670,6 +671,7 @@ void EulerSolver::copy_run_parameters(EulerSolver& n) const {
     n.mass0 = mass0; n.energy0 = energy0; n.volume0 = volume0;
     n.vtk_fields = vtk_fields; n.vtk_cell_value = vtk_cell_value; n.vtk_polyhedral = vtk_polyhedral; n.vtk_on_dump = vtk_on_dump;
     n.launch_nonce = launch_nonce;
+    n.convection = convection; n.conv_init = conv_init; n.scalar0 = scalar0; n.conv_end_step = conv_end_step;
     n.topo.spherical = topo.spherical; n.topo.sphere_radius = topo.sphere_radius; n.topo.sphere_height = topo.sphere_height;
 }
 
@@ -733,7 +735,7 @@ std::unique_ptr<EulerSolver> EulerSolver::regridded(const std::vector<uint8_t>& 
     n->set_fields(blank(1, file_bc_rho), blank(3, file_bc_U), blank(1, file_bc_T), blank(1, file_bc_p));
     lap("blank fields + BC tables");
     n->setup();                                         // reference state, gravity, BC tables on the new mesh (the fields are overwritten below)
-    n->mass0 = mass0; n->energy0 = energy0; n->volume0 = volume0;
+    n->mass0 = mass0; n->energy0 = energy0; n->volume0 = volume0; n->scalar0 = scalar0;
     lap("set-up (reference state)");
     if (ctx) {
         n->attach_device(device_id);

@@ -668,9 +668,16 @@ void EulerSolver::attach_device(int device, int rank, int nranks, const void* ui
         ck(nsem_upload_coords(ctx, geo.cC.data()));
         if (geo.spherical) ck(nsem_set_sphere(ctx, geo.sphere_radius));
         if (time_scheme.size() == 3 && time_scheme.compare(0, 2, "AB") == 0) ck(nsem_set_ab_order(ctx, time_scheme[2] - '0'));
-        const int kind = conv_init == "LEVEQUE" ? 1 : (conv_init == "LAURITZEN_0" ? 2 : (conv_init == "LAURITZEN_1" ? 3 : 0));
-        ck(nsem_set_convection(ctx, kind, (double)end_step * dt, write_interval * start_step + 1));
+        arm_wind(write_interval * start_step + 1);
     }
+}
+
+// the analytic wind is a function of the step number (convection.cpp:114-121): (re)set the step the next call starts with
+void EulerSolver::arm_wind(long first_step) {
+    if (!convection || !ctx) return;
+    const int kind = conv_init == "LEVEQUE" ? 1 : (conv_init == "LAURITZEN_0" ? 2 : (conv_init == "LAURITZEN_1" ? 3 : 0));
+    const long total = conv_end_step > 0 ? conv_end_step : end_step;       // the period is the WHOLE run's end_step * dt, also inside an AMR cycle
+    if (nsem_set_convection(ctx, kind, (double)total * dt, first_step)) throw Error(nsem_last_error(ctx));
 }
 
 void EulerSolver::exchange_setup_halos() {
@@ -779,9 +786,11 @@ void EulerSolver::merge_fields(int index) {
     if (nranks <= 1 || rank != 0) return;
     const std::string s = std::to_string(index);
     const int NP = Basis(nop).NP;
-    const char* names[4] = {"rho", "U", "T", "p"};
+    // the convection app dumps its scalar T (kept in the rho slot, conditions under bc_rho) and the wind
+    const char* names[4] = {convection ? "T" : "rho", "U", "T", "p"};
     const int comps[4] = {1, 3, 1, 1};
     const std::vector<BCond>* bcs[4] = {&bc_rho, &bc_U, &bc_T, &bc_p};
+    const int nfields = convection ? 2 : 4;
     std::vector<std::vector<u32>> maps(nranks);
     for (int r = 0; r < nranks; r++) {
         const std::string path = dir + "/grid" + std::to_string(r) + "/cells" + s;
@@ -804,7 +813,7 @@ void EulerSolver::merge_fields(int index) {
         std::fclose(f);
         if (got != nc) throw Error("merge: short read of " + path);
     }
-    for (int q = 0; q < 4; q++) {
+    for (int q = 0; q < nfields; q++) {
         const size_t per = (size_t)NP * comps[q];
         std::vector<double> all((size_t)nGlobalCells * per, 0.0);
         for (int r = 0; r < nranks; r++) {
@@ -822,6 +831,7 @@ void EulerSolver::merge_fields(int index) {
 void EulerSolver::run() {
     // Iteration (iteration.h:18-84): steps start_step*write_interval+1 .. end_step, dump when i % write_interval == 0
     long i = write_interval * start_step + 1;
+    arm_wind(i);
     const bool diag = !convection && (nranks == 1 || std::getenv("NSEM_DIAGNOSTICS"));
     double m0 = mass0, e0 = energy0, v0 = volume0;
     if (diag && nranks > 1 && i <= end_step) {          // the set-up's totals are those of this partition: take the global ones from the device
@@ -874,7 +884,6 @@ static void run_case_partitioned(std::unique_ptr<EulerSolver>& s) {
     const int rank = s->rank, nranks = s->nranks, device = s->device_id;
     const bool verbose = std::getenv("NSEM_VERBOSE") != nullptr;
     if (!s->ctx) throw Error("run_case: the partition is not attached to a device");
-    if (s->convection) throw Error("run_case: adaptive regridding of the convection app on several partitions is not built");
     const int NP = Basis(s->nop).NP;
     // the whole-domain solver: the case as one partition would set it up (no dumps, no prints)
     std::unique_ptr<EulerSolver> G(new EulerSolver());
@@ -952,12 +961,14 @@ static void run_case_partitioned(std::unique_ptr<EulerSolver>& s) {
         if (std::getenv("NSEM_DEBUG_REGRID")) { s->write_fields(100 + (int)dump); s->merge_fields(100 + (int)dump); }
     };
     const long last = s->end_step;
+    s->conv_end_step = last; G->conv_end_step = last;
     long dump = s->start_step;
     regrid(dump);
     while (dump * s->write_interval < last) {
         const long upto = std::min(last, (dump + s->amr_step) * s->write_interval);
         s->start_step = dump;
         s->end_step = upto;
+        s->conv_end_step = last;
         s->run();
         s->end_step = last;
         dump = upto / s->write_interval;
@@ -977,12 +988,14 @@ void run_case(std::unique_ptr<EulerSolver>& s) {
         if (std::getenv("NSEM_DEBUG_REGRID")) { s->download(); s->write_fields(100 + (int)dump); }
     };
     const long last = s->end_step;
+    s->conv_end_step = last;
     long dump = s->start_step;
     regrid(dump);
     while (dump * s->write_interval < last) {
         const long upto = std::min(last, (dump + s->amr_step) * s->write_interval);
         s->start_step = dump;
         s->end_step = upto;
+        s->conv_end_step = last;
         s->run();
         s->end_step = last;
         dump = upto / s->write_interval;
