@@ -28,6 +28,10 @@ def main():
     make("advection-leveque-ab2", "AB2")       # the scheme the example ships with: two residuals kept (field.h:3789-3806, 3885-3905)
     make("advection-leveque-ab4", "AB4")       # the start-up sequence AB1, AB2, AB3, then AB4
     make_amr()
+    # the same on the cubed sphere: examples/atmo/advection-sphere-amr (Lauritzen's wind, BDF1, 2-D refinement that never splits the radial
+    # axis) at 8 x 8 cells per panel, order 2, one 12-day period in 480 steps; dumps every 20 steps, regrids before step 1 and after dump 12
+    make_amr("advection-sphere-amr", 480, 20, example="/root/reference/examples/atmo/advection-sphere-amr", divisions=(8, 8, 1),
+             edits={"dt": 2160, "npx": 2, "npy": 2}, amr_step=12, scheme="BDF1")
 
 
 def make(name, scheme):
@@ -64,7 +68,7 @@ if __name__ == "__main__":
     main()
 
 
-def make_amr(name="advection-leveque-amr", nsteps=40, interval=20):
+def make_amr(name="advection-leveque-amr", nsteps=40, interval=20, example=EX, divisions=None, edits=None, amr_step=1, scheme="AB2"):
     """An AMR RUN of the convection app: the example exactly as it ships (AB2, amr_step 1, max_level 2, buffer_zone 2) for `nsteps` steps with
     a dump (and a regrid) every `interval`.  Kept: the case before the run, the cells of the grid of every regrid (centroid, volume), the
     scalar after the first `interval` steps (the same run stopped there) and at the end, with the node positions of their grids (oracle
@@ -72,19 +76,31 @@ def make_amr(name="advection-leveque-amr", nsteps=40, interval=20):
     from oracle.dg import Basis, Geometry
     from oracle.mesh import MeshTopo
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "convection", name)
-    d = os.path.join(tempfile.mkdtemp(prefix="conv_amr_"), "advection-leveque")
-    shutil.copytree(EX, d)
+    from oracle.euler import Params
+    d = os.path.join(tempfile.mkdtemp(prefix="conv_amr_"), "case")
+    shutil.copytree(example, d)
     for f in os.listdir(d):
         os.chmod(os.path.join(d, f), 0o644)
     block = [f for f in os.listdir(d) if f != "controls" and not f.endswith((".txt", ".sh"))][0]
+    if divisions:
+        blk = open(os.path.join(d, block)).read()
+        blk, cnt = re.subn(r"(?m)^(8\{[^}]*\}\s+linear\s+)3\{\d+ \d+ \d+\}", r"\g<1>3{%d %d %d}" % divisions, blk)
+        assert cnt == 6
+        open(os.path.join(d, block), "w").write(blk)
     m = subprocess.run([run_ref.ref_bin("mesh"), block, "-o", "grid_0.bin"], cwd=d, capture_output=True, text=True, timeout=600)
     assert m.returncode == 0, m.stdout[-1000:] + m.stderr[-1000:]
     ctl = open(os.path.join(d, "controls")).read()
     ctl = re.sub(r"(?m)^(\s*)end_step\s+\d+", rf"\g<1>end_step {nsteps}", ctl)
     ctl = re.sub(r"(?m)^(\s*)write_interval\s+\d+", rf"\g<1>write_interval {interval}", ctl)
-    ctl = re.sub(r"(?m)^(\s*)write_format\s+\w+", r"\g<1>write_format BINARY", ctl)
-    assert re.search(r"(?m)^\s*amr_step\s+1\s*$", ctl) and re.search(r"(?m)^\s*time_scheme\s+AB2\s*$", ctl)
+    if re.search(r"(?m)^\s*write_format", ctl):
+        ctl = re.sub(r"(?m)^(\s*)write_format\s+\w+", r"\g<1>write_format BINARY", ctl)
+    for k, v in (edits or {}).items():
+        assert re.search(rf"(?m)^(\s*){k}\s+\S+", ctl), k
+        ctl = re.sub(rf"(?m)^(\s*){k}\s+\S+", rf"\g<1>{k} {v}", ctl)
+    assert re.search(r"(?m)^\s*amr_step\s+1\s*$", ctl) and re.search(rf"(?m)^\s*time_scheme\s+{scheme}\s*$", ctl)
+    ctl = re.sub(r"(?m)^(\s*)amr_step\s+1", rf"\g<1>amr_step {amr_step}", ctl)
     open(os.path.join(d, "controls"), "w").write(ctl)
+    params = Params.from_controls(refio.read_controls(os.path.join(d, "controls")))
     shutil.rmtree(out, ignore_errors=True)
     os.makedirs(out)
     for f in ("controls", "grid_0.bin", "U0.txt", "T0.txt"):
@@ -94,19 +110,21 @@ def make_amr(name="advection-leveque-amr", nsteps=40, interval=20):
     # the wind's period is end_step * dt, so the run stopped at the first dump keeps end_step and gets a kill switch instead: run the
     # full case twice is not possible either (the second regrid overwrites dump 1) -- so the half-way state comes from a run whose second
     # regrid is switched off by amr_step 2
-    open(os.path.join(half, "controls"), "w").write(re.sub(r"(?m)^(\s*)amr_step\s+1", r"\g<1>amr_step 2", ctl))
+    open(os.path.join(half, "controls"), "w").write(re.sub(r"(?m)^(\s*)amr_step\s+\d+", rf"\g<1>amr_step {2 * amr_step}", ctl))
     nop = [int(re.search(rf"(?m)^\s*{k}\s+(\d+)", ctl).group(1)) for k in ("npx", "npy", "npz")]
     keep = {}
-    for tag, dd, gk, dump in (("half", half, 0, 1), ("end", d, 1, nsteps // interval)):
+    for tag, dd, gk, dump in (("half", half, 0, amr_step), ("end", d, amr_step, nsteps // interval)):
         r = subprocess.run([run_ref.ref_bin("convection"), "./controls"], cwd=dd, capture_output=True, text=True, timeout=1800)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         print(tag, [l for l in r.stdout.splitlines() if "Refining " in l])
-        topo = MeshTopo(refio.read_grid(os.path.join(dd, f"grid_{gk}"), prefer_bin=True)).load()
+        topo = MeshTopo(refio.read_grid(os.path.join(dd, f"grid_{gk}"), prefer_bin=True))
+        topo.spherical, topo.sphere_radius, topo.sphere_height = params.is_spherical, params.sphere_radius, params.sphere_height
+        topo.load()
         geo = Geometry(topo, Basis(nop))
         n = geo.gBCSfield
         keep[f"{tag}_CC"] = np.asarray(topo.CC)[: topo.nBCS]
         keep[f"{tag}_xyz"] = np.asarray(geo.cC)[:n]
         keep[f"{tag}_cV"] = np.asarray(geo.cV)[:n]
         keep[f"{tag}_T"] = refio.read_field_values(os.path.join(dd, f"T{dump}"))[:n, 0]
-    np.savez_compressed(os.path.join(out, "expected.npz"), nsteps=nsteps, interval=interval, NP=geo.gBCSfield // topo.nBCS, **keep)
+    np.savez_compressed(os.path.join(out, "expected.npz"), nsteps=nsteps, interval=interval, amr_step=amr_step, NP=geo.gBCSfield // topo.nBCS, **keep)
     print(name, {k: v.shape for k, v in keep.items()})
