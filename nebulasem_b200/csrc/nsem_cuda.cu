@@ -243,7 +243,8 @@ static int halo_check(nsem_ctx* c);       // halo over peer memory: did a neighb
 #define NSEM_ORDERS(X)                                                                            \
     X(2, 2, 2) X(3, 3, 3) X(4, 4, 4) X(5, 5, 5) X(6, 6, 6) X(7, 7, 7) X(8, 8, 8)                  \
     X(2, 1, 2) X(3, 1, 3) X(4, 1, 4) X(5, 1, 5) X(6, 1, 6) X(7, 1, 7) X(8, 1, 8)                  \
-    X(2, 2, 1) X(3, 3, 1) X(4, 4, 1) X(5, 5, 1) X(6, 6, 1) X(7, 7, 1) X(8, 8, 1)
+    X(2, 2, 1) X(3, 3, 1) X(4, 4, 1) X(5, 5, 1) X(6, 6, 1) X(7, 7, 1) X(8, 8, 1)                  \
+    X(2, 1, 1) X(3, 1, 1) X(4, 1, 1) X(5, 1, 1) X(6, 1, 1) X(7, 1, 1) X(8, 1, 1)
 #endif
 
 template <int NX, int NY, int NZ>

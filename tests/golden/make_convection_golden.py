@@ -27,6 +27,9 @@ def main():
     make("advection-leveque", "AB1")
     make("advection-leveque-ab2", "AB2")       # the scheme the example ships with: two residuals kept (field.h:3789-3806, 3885-3905)
     make("advection-leveque-ab4", "AB4")       # the start-up sequence AB1, AB2, AB3, then AB4
+    # examples/transport/scalar: a cosine bell carried round a periodic 1-D line of 20 elements (order 4 along x only: 5 x 1 x 1 nodes, CYCLIC
+    # inlet/outlet, frozen uniform wind, BDF1), 40 steps
+    make("transport-scalar", "BDF1", example="/root/reference/examples/transport/scalar")
     make_amr()
     # the same on the cubed sphere: examples/atmo/advection-sphere-amr (Lauritzen's wind, BDF1, 2-D refinement that never splits the radial
     # axis) at 8 x 8 cells per panel, order 2, one 12-day period in 480 steps; dumps every 20 steps, regrids before step 1 and after dump 12
@@ -34,10 +37,12 @@ def main():
              edits={"dt": 2160, "npx": 2, "npy": 2}, amr_step=12, scheme="BDF1")
 
 
-def make(name, scheme):
+def make(name, scheme, example=EX):
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "convection", name)
     d = os.path.join(tempfile.mkdtemp(prefix="conv_golden_"), "advection-leveque")
-    shutil.copytree(EX, d)
+    shutil.copytree(example, d)
+    for f in os.listdir(d):
+        os.chmod(os.path.join(d, f), 0o644)
     block = [f for f in os.listdir(d) if f != "controls" and not f.endswith((".txt", ".sh"))][0]
     m = subprocess.run([run_ref.ref_bin("mesh"), block, "-o", "grid_0.bin"], cwd=d, capture_output=True, text=True, timeout=600)
     assert m.returncode == 0, m.stdout[-1000:] + m.stderr[-1000:]
