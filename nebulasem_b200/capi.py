@@ -63,7 +63,7 @@ EXPORTS = ["nsem_create", "nsem_destroy", "nsem_last_error", "nsem_get_unique_id
            "nsem_upload_mesh", "nsem_set_bcs", "nsem_set_halo", "nsem_set_params", "nsem_set_schedule",
            "nsem_pin_host", "nsem_upload_state", "nsem_download_state", "nsem_upload_state_async", "nsem_download_state_async", "nsem_upload_ref", "nsem_upload_geopotential", "nsem_euler_step", "nsem_exchange_state_halos", "nsem_diagnostics",
            "nsem_sync", "nsem_time_steps", "nsem_launch_count", "nsem_kernel_info", "nsem_refine_state", "nsem_restart_state", "nsem_download_gradients",
-           "nsem_op_cds", "nsem_op_rusanov", "nsem_op_gradf_strong", "nsem_op_divf_weak", "nsem_op_apply_bcs", "nsem_op_halo", "nsem_halo_info", "nsem_halo_wait_ms", "nsem_upload_coords", "nsem_set_ab_order", "nsem_allreduce_host", "nsem_device", "nsem_set_sphere", "nsem_set_convection", "nsem_convection_step"]
+           "nsem_op_cds", "nsem_op_rusanov", "nsem_op_gradf_strong", "nsem_op_divf_weak", "nsem_op_apply_bcs", "nsem_op_halo", "nsem_halo_info", "nsem_halo_wait_ms", "nsem_upload_coords", "nsem_set_convection_scheme", "nsem_set_ab_order", "nsem_allreduce_host", "nsem_device", "nsem_set_sphere", "nsem_set_convection", "nsem_convection_step"]
 
 _lib = None
 
@@ -108,6 +108,7 @@ def load_library() -> C.CDLL:
     lib.nsem_set_convection.argtypes = [vp, C.c_int, C.c_double, C.c_long]
     lib.nsem_set_sphere.argtypes = [vp, C.c_double]
     lib.nsem_set_ab_order.argtypes = [vp, C.c_int]
+    lib.nsem_set_convection_scheme.argtypes = [vp, C.c_int, C.c_double]
     lib.nsem_allreduce_host.argtypes = [vp, C.c_void_p, C.c_uint64, C.c_int]
     lib.nsem_device.argtypes = [vp]
     lib.nsem_convection_step.argtypes = [vp, C.c_int]
@@ -284,6 +285,9 @@ class Context:
         a = _f64(cC)
         assert a.size == self.n_ref_nodes * 3
         self._ck(self.lib.nsem_upload_coords(self.h, _pd(a)))
+
+    def set_convection_scheme(self, scheme: str = "RUSANOV", blend_factor: float = 0.2):
+        self._ck(self.lib.nsem_set_convection_scheme(self.h, {"RUSANOV": 0, "CDS": 1, "UDS": 2, "BLENDED": 3}[scheme], float(blend_factor)))
 
     def set_ab_order(self, order: int):
         self._ck(self.lib.nsem_set_ab_order(self.h, int(order)))

@@ -87,8 +87,11 @@ void EulerSolver::read_controls(const std::string& case_dir) {
         const Vec3 n = ctl.vec("decomposition", "n", Vec3{1, 1, 1});
         for (int d = 0; d < 3; d++) decomp_n[d] = std::max(1, (int)n[d]);
     }
-    if (ctl.str("general", "convection_scheme", "RUSANOV") != "RUSANOV")
-        throw Error("only convection_scheme RUSANOV is implemented on the GPU path");
+    conv_scheme = ctl.str("general", "convection_scheme", "RUSANOV");
+    blend_factor = ctl.num("general", "blend_factor", blend_factor);
+    // the euler app hands divf its lambdaMax only under RUSANOV; the convection app's scalar also takes the plain face values
+    if (conv_scheme != "RUSANOV" && !(convection && (conv_scheme == "CDS" || conv_scheme == "UDS" || conv_scheme == "BLENDED")))
+        throw Error("convection_scheme " + conv_scheme + " is not implemented on the GPU path (RUSANOV; CDS, UDS, BLENDED for solver convection)");
     // BDF1, AB1 and RK1..RK4 are the same single forward-Euler stage on this path (SURVEY finding 1)
     const std::string& ts = time_scheme;
     const bool ab_multi = (ts == "AB2" || ts == "AB3" || ts == "AB4" || ts == "AB5");
@@ -668,6 +671,7 @@ void EulerSolver::attach_device(int device, int rank, int nranks, const void* ui
         ck(nsem_upload_coords(ctx, geo.cC.data()));
         if (geo.spherical) ck(nsem_set_sphere(ctx, geo.sphere_radius));
         if (time_scheme.size() == 3 && time_scheme.compare(0, 2, "AB") == 0) ck(nsem_set_ab_order(ctx, time_scheme[2] - '0'));
+        ck(nsem_set_convection_scheme(ctx, conv_scheme == "CDS" ? 1 : (conv_scheme == "UDS" ? 2 : (conv_scheme == "BLENDED" ? 3 : 0)), blend_factor));
         arm_wind(write_interval * start_step + 1);
     }
 }

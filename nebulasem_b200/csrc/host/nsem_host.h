@@ -309,6 +309,8 @@ struct EulerSolver {
     void run();                                           // Iteration loop: steps + dumps every write_interval
 
     void apply_bcs(std::vector<double>& f, int comps, std::vector<BCond>& bcs);   // applyExplicitBCs on the host
+    std::string conv_scheme = "RUSANOV";  // Controls::convection_scheme / blend_factor (field.cpp:56, 520-527)
+    double blend_factor = 0.2;
     long conv_end_step = 0;               // the whole run's end_step while run_case shortens end_step to the next regrid (the wind's period)
     void arm_wind(long first_step);       // convection: nsem_set_convection with the step the next call starts with
     void mark_unlisted_patches();         // patches rho has no condition for (NSEM_BC_UNLISTED)

@@ -146,6 +146,8 @@ struct nsem_ctx {
     int conv_init = 0;                 // 0 = the wind is the uploaded U, 1 = LEVEQUE (re-evaluated at every step)
     double conv_etime = 1.0;           // end_step * dt: the period of the analytic wind
     long conv_step = 0;                // steps taken (Iteration::get_step() - 1)
+    int conv_scheme = 0;               // 0 RUSANOV, 1 CDS, 2 UDS, 3 BLENDED (Controls::convection_scheme as the convection app's divf reads it)
+    double conv_blend = 0.2;
     int ab_order = 1;                  // Adams-Bashforth order of the scalar's update (AB2..AB5 keep a residual history; 1 = one forward-Euler stage)
     int ab_stored = 0, ab_head = 0;    // entries of the history in use (MeshField::nstored), ring position of PREV(0)
     DevBuf<double> abHist[5];
@@ -1817,6 +1819,15 @@ extern "C" int nsem_set_convection(nsem_ctx* c, int problem_init, double etime, 
     return 0;
 }
 
+// Controls::convection_scheme for the scalar's face value (divf, field.h:3427-3437): 0 RUSANOV (default), 1 CDS, 2 UDS, 3 BLENDED with
+// Controls::blend_factor.  examples/transport/wave2d runs BLENDED 0.6.
+extern "C" int nsem_set_convection_scheme(nsem_ctx* c, int scheme, double blend_factor) {
+    if (scheme < 0 || scheme > 3) { c->err = "nsem_set_convection_scheme: 0 RUSANOV, 1 CDS, 2 UDS or 3 BLENDED"; return 1; }
+    c->conv_scheme = scheme;
+    c->conv_blend = blend_factor;
+    return 0;
+}
+
 // Controls::time_scheme AB1..AB5 for nsem_convection_step (order 1 = the one forward-Euler stage that BDF1, AB1 and RK1-RK4 all are on this
 // path); the residual history starts over (a new field after a regrid or a restart, field.h:3885-3895)
 extern "C" int nsem_set_ab_order(nsem_ctx* c, int order) {
@@ -1871,6 +1882,12 @@ extern "C" int nsem_convection_step(nsem_ctx* c, int nsteps) {
         BCParams B;
         fill_kparams(c, P);
         P.visc = 0; P.buoyancy = 0;
+        P.conv_scheme = c->conv_scheme; P.blend = c->conv_blend;
+        const bool plain = (c->conv_scheme != 0);          // the other face values live in the plain-load sweep only
+        if (plain && c->nMortarGroups) { c->err = "nsem_convection_step: CDS / UDS / BLENDED face values are not built for non-conforming (2:1) faces"; return 1; }
+        const bool keep_v2 = c->use_v2, keep_v4 = c->use_v4;
+        if (plain) { c->use_v2 = false; c->use_v4 = false; }
+        struct Restore { nsem_ctx* c; bool v2, v4; ~Restore() { c->use_v2 = v2; c->use_v4 = v4; } } restore{c, keep_v2, keep_v4};
         CUDA_TRY(c, launch_mortar(c, P, 0));
         if (c->ab_order > 1) {
             // AB2..AB5: the sweep leaves the residual, the update combines it with the stored ones (field.h:3789-3806, 3885-3905)

@@ -71,6 +71,10 @@ struct KParams {
     // op_flux (plain-load sweep A only) = the rusanov mass flux . fN (field.h:2928-2943, 3093-3114) of every element face node,
     // [elem*6 + local face][NPF], in the owner's frame
     int op_mode;
+    // face value of the MASS flux in sweep A (divf, field.h:3427-3437): 0 = RUSANOV (the euler app and the default), 1 = CDS, 2 = UDS (upwind by
+    // the sign of flx(U) = cds(U).fN), 3 = BLENDED (blend * CDS + (1 - blend) * UDS).  Only the convection app sets it; plain-load sweeps only.
+    int conv_scheme;
+    double blend;
     double* op_flux;
     // halo fused into the v4 sweeps (null = the separate halo_push_kernel does it): table for this exchange, its epoch, per ghost cell
     // {neighbour index or 0xffffffff, first slot of the cell in the neighbour's window}, and the number of leading schedule positions
@@ -424,7 +428,13 @@ sweepA_kernel(const __grid_constant__ KParams P) {
         const double lam = ((mo * al + mn * (1 - al)) + (co * al + cn * (1 - al))) / 2;
         // mass flux
         const double fo = rho_o * (uo0 * N0 + uo1 * N1 + uo2 * N2), fn = rho_n * (un0 * N0 + un1 * N1 + un2 * N2);
-        const double flux = (fo * al + fn * (1 - al)) - lam * (rho_n - rho_o) * nN;
+        double flux = (fo * al + fn * (1 - al)) - lam * (rho_n - rho_o) * nN;
+        if (P.conv_scheme != 0) {
+            const double central = fo * al + fn * (1 - al);
+            const double F = (uo0 * al + un0 * (1 - al)) * N0 + ((uo1 * al + un1 * (1 - al)) * N1 + (uo2 * al + un2 * (1 - al)) * N2);
+            const double upwind = (F >= 0) ? fo : fn;
+            flux = (P.conv_scheme == 1) ? central : (P.conv_scheme == 2 ? upwind : P.blend * central + (1.0 - P.blend) * upwind);
+        }
         r_rho += own ? flux : -flux;
         if (P.op_flux) P.op_flux[((size_t)elem * 6 + s) * Dm::NPF + n] = flux;
         if (VISC) {

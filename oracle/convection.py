@@ -11,7 +11,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import libm
-from .euler import EulerOracle, vmag
+from .euler import EulerOracle, vdot, vmag
 
 PI = 3.14159265358979323846264          # Constants::PI
 
@@ -63,7 +63,13 @@ class ConvectionOracle(EulerOracle):
             self.U = self.wind(i * P.dt, self.end_step * P.dt)
         lam = self.cds(vmag(self.U)) / 2
         fq = self.U * self.T[:, None]
-        r = self.divf(fq, self.T, lam)
+        sch = P.convection_scheme
+        if sch == "RUSANOV":
+            r = self.divf(fq, self.T, lam)
+        else:
+            # F = flx(U) = dot(cds(U), fN) (field.h:3396-3399), the sign that picks the upwind side
+            F = vdot(self.cds(self.U), self.fNv)
+            r = self.divf(fq, self.T, lam, scheme=sch, flux=F, blend=P.blend_factor)
         ap0 = (-1.0 / P.dt) * self.g.cV
         order = int(P.time_scheme[2]) if P.time_scheme.startswith("AB") else 1
         if order > 1:

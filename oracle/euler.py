@@ -57,6 +57,8 @@ class Params:
     diffusion: bool = True
     time_scheme: str = "BDF1"                  # BDF1 | AB1 | RK1..RK4 (all one forward-Euler stage on this path)
     problem_init: str = "NONE"
+    convection_scheme: str = "RUSANOV"         # Controls::convection_scheme / blend_factor (field.cpp:520-527): read by the convection app's divf
+    blend_factor: float = 0.2
     is_spherical: bool = False                 # Mesh::is_spherical / sphere_radius / sphere_height, mesh.cpp:31-33
     sphere_radius: float = 6371220.0
     sphere_height: float = 10000.0
@@ -87,6 +89,9 @@ class Params:
             p.diffusion = yes(e["diffusion"][0])
         if "problem_init" in e:
             p.problem_init = e["problem_init"][0]
+        if "convection_scheme" in g:
+            p.convection_scheme = g["convection_scheme"][0]
+        p.blend_factor = f(g, "blend_factor", p.blend_factor)
         if "is_spherical" in g:
             p.is_spherical = yes(g["is_spherical"][0])
         p.sphere_radius = f(g, "sphere_radius", p.sphere_radius)
@@ -460,9 +465,25 @@ class EulerOracle:
         return r
 
     # ---- operators of the reference API -----------------------------------------------------------
-    def divf(self, F, q, lam):
-        """divf<weak>(F,false,&flux,&q,&lambdaMax) under RUSANOV (field.h:3417-3478)."""
-        fF = self.rusanov(F, q, lam)                               # on used slots
+    def uds(self, c, flux):
+        """upwind value by the sign of the facet flux (field.h:2904-2917)"""
+        fO, fN = self.scatter(c)
+        sel = (flux >= 0).reshape((-1,) + (1,) * (c.ndim - 1))
+        return np.where(sel, fO, fN)
+
+    def divf(self, F, q, lam, scheme="RUSANOV", flux=None, blend=0.0):
+        """divf<weak>(F,false,&flux,&q,&lambdaMax) (field.h:3417-3478): RUSANOV (what the euler app runs), or CDS / UDS / BLENDED of the
+        convection app's examples (flux = flx(U) on the used slots)."""
+        if scheme == "RUSANOV":
+            fF = self.rusanov(F, q, lam)                           # on used slots
+        elif scheme == "CDS":
+            fF = self.cds(F)
+        elif scheme == "BLENDED":
+            fF = blend * self.cds(F) + (1.0 - blend) * self.uds(F, flux)
+        elif scheme == "UDS":
+            fF = self.uds(F, flux)
+        else:
+            raise NotImplementedError(scheme)
         fFO, fFN = self.gather(fF)                                 # div_flux<weak>: gather_non_conforming first (field.h:3091)
         dotN = vdot if F.ndim == 2 else tdotv
         r = np.zeros(self.gA) if F.ndim == 2 else np.zeros((self.gA, 3))

@@ -30,6 +30,11 @@ def main():
     # examples/transport/scalar: a cosine bell carried round a periodic 1-D line of 20 elements (order 4 along x only: 5 x 1 x 1 nodes, CYCLIC
     # inlet/outlet, frozen uniform wind, BDF1), 40 steps
     make("transport-scalar", "BDF1", example="/root/reference/examples/transport/scalar")
+    # examples/transport/wave2d: a Gaussian carried across a 2-D box with the BLENDED face value (0.6 central + 0.4 upwind by the sign of
+    # the facet flux, field.h:3427-3437) instead of RUSANOV; also with UDS and CDS
+    make("transport-wave2d", "BDF1", example="/root/reference/examples/transport/wave2d", block="simple")
+    make("transport-wave2d-uds", "BDF1", example="/root/reference/examples/transport/wave2d", block="simple", edits={"convection_scheme": "UDS"})
+    make("transport-wave2d-cds", "BDF1", example="/root/reference/examples/transport/wave2d", block="simple", edits={"convection_scheme": "CDS"})
     make_amr()
     # the same on the cubed sphere: examples/atmo/advection-sphere-amr (Lauritzen's wind, BDF1, 2-D refinement that never splits the radial
     # axis) at 8 x 8 cells per panel, order 2, one 12-day period in 480 steps; dumps every 20 steps, regrids before step 1 and after dump 12
@@ -37,17 +42,20 @@ def main():
              edits={"dt": 2160, "npx": 2, "npy": 2}, amr_step=12, scheme="BDF1")
 
 
-def make(name, scheme, example=EX):
+def make(name, scheme, example=EX, block=None, edits=None):
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "convection", name)
     d = os.path.join(tempfile.mkdtemp(prefix="conv_golden_"), "advection-leveque")
     shutil.copytree(example, d)
     for f in os.listdir(d):
         os.chmod(os.path.join(d, f), 0o644)
-    block = [f for f in os.listdir(d) if f != "controls" and not f.endswith((".txt", ".sh"))][0]
+    block = block or [f for f in os.listdir(d) if f != "controls" and not f.endswith((".txt", ".sh"))][0]
     m = subprocess.run([run_ref.ref_bin("mesh"), block, "-o", "grid_0.bin"], cwd=d, capture_output=True, text=True, timeout=600)
     assert m.returncode == 0, m.stdout[-1000:] + m.stderr[-1000:]
     os.chmod(os.path.join(d, "controls"), 0o644)
     ctl = open(os.path.join(d, "controls")).read()
+    for k, v in (edits or {}).items():
+        assert re.search(rf"(?m)^(\s*){k}\s+\S+", ctl), k
+        ctl = re.sub(rf"(?m)^(\s*){k}\s+\S+", rf"\g<1>{k} {v}", ctl)
     ctl = re.sub(r"(?m)^(\s*)end_step\s+\d+", rf"\g<1>end_step {NSTEPS}", ctl)
     ctl = re.sub(r"(?m)^(\s*)write_interval\s+\d+", rf"\g<1>write_interval {NSTEPS}", ctl)
     ctl = re.sub(r"(?m)^(\s*)write_format\s+\w+", r"\g<1>write_format BINARY", ctl)

@@ -42,28 +42,32 @@ def device_from_convection_oracle(orc, device=0):
     ctx.upload_coords(g.cC)
     if p.time_scheme.startswith("AB"):
         ctx.set_ab_order(int(p.time_scheme[2]))
+    ctx.set_convection_scheme(p.convection_scheme, p.blend_factor)
     ctx.set_convection(orc.problem_init, orc.end_step * p.dt, 1)
     return ctx
 
 
 SCHEMES = {"AB1": GOLD, "AB2": GOLD + "-ab2", "AB4": GOLD + "-ab4",        # AB2 is what the example ships; AB4 starts up through AB1, AB2, AB3
            # examples/transport/scalar: 1-D (5 x 1 x 1 nodes per element), CYCLIC ends, frozen uniform wind
-           "BDF1": os.path.join(os.path.dirname(GOLD), "transport-scalar")}
+           "BDF1": os.path.join(os.path.dirname(GOLD), "transport-scalar"),
+           # examples/transport/wave2d: the face value of divf under convection_scheme BLENDED 0.6 (as shipped), UDS and CDS (field.h:3427-3437)
+           "BLENDED": os.path.join(os.path.dirname(GOLD), "transport-wave2d"), "UDS": os.path.join(os.path.dirname(GOLD), "transport-wave2d-uds"),
+           "CDS": os.path.join(os.path.dirname(GOLD), "transport-wave2d-cds")}
 
 
-@pytest.mark.parametrize("scheme", ["AB1", "AB2", "AB4", "BDF1"])
+@pytest.mark.parametrize("scheme", ["AB1", "AB2", "AB4", "BDF1", "BLENDED", "UDS", "CDS"])
 def test_oracle_convection_is_bit_identical_to_the_reference_binary(scheme):
     GOLD = SCHEMES[scheme]
     exp = np.load(os.path.join(GOLD, "expected.npz"))
     orc = ocase.load_convection_case(GOLD, exact_order=True)
-    assert orc.p.time_scheme == scheme
+    assert scheme in (orc.p.time_scheme, orc.p.convection_scheme)
     orc.run(int(exp["nsteps"]))
     nb = orc.gB
     assert np.array_equal(orc.T[:nb], exp["T"]) and np.array_equal(orc.U[:nb], exp["U"])
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("scheme", ["AB1", "AB2", "AB4", "BDF1"])
+@pytest.mark.parametrize("scheme", ["AB1", "AB2", "AB4", "BDF1", "BLENDED", "UDS", "CDS"])
 def test_device_convection_matches_the_reference_binary(scheme):
     """AB2..AB5 (ddt + addTemporal, field.h:3789-3806, 3885-3905): the sweep leaves the residual, ab_update_kernel combines it with the ones
     it keeps; the field's first steps run the lower orders."""
@@ -118,7 +122,7 @@ def test_device_convection_3d_frozen_wind_matches_oracle(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("scheme", ["AB1", "AB2", "BDF1"])
+@pytest.mark.parametrize("scheme", ["AB1", "AB2", "BDF1", "BLENDED"])
 def test_convection_binary_matches_the_reference_binary(tmp_path, scheme):
     """The drop-in app: `convection ./controls` (nebulasem_b200/lib/convection, the same program as lib/euler, the solver chosen by the
     controls) on the reference's own example files writes the T/U dump the reference binary wrote."""
