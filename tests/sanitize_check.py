@@ -2,7 +2,8 @@
     compute-sanitizer --tool memcheck python tests/sanitize_check.py
 Covers: v4 sweeps (conforming 3-D), v4 + mortar kernels (3-D non-conforming), v1 + mortar kernels (2-D non-conforming and 3-D with
 NSEM_MORTAR_V1=1), v1 2-D, the boundary/ghost-trace kernels, upload/download, the pipelined transfers and the AMR field-transfer kernels
-(copy / merge / split + restart pass), the run schedule of sweep A and the scalar-advection mode.  NSEM_SANITIZE_ONLY=amr runs the AMR group alone."""
+(copy / merge / split + restart pass), the run schedule of sweep A, the scalar-advection mode (winds, AB update, face-value schemes, 1-D)
+and the cubed-sphere cases.  NSEM_SANITIZE_ONLY=amr runs the AMR group alone."""
 import os
 import shutil
 import sys
@@ -74,6 +75,14 @@ def main():
         c = os.path.join(d, "leveque")
         shutil.copytree(os.path.join(ROOT, "tests", "golden", "convection", "advection-leveque"), c)
         ok &= run(host.Solver.open_case(c), 3, "convection advection-leveque")
+    # later in round 2: cubed-sphere cases (per-node gravity, the UNLISTED continuation of rho's boundary cells, the Lauritzen wind kernel),
+    # the Adams-Bashforth update, the 1-D instantiation and the upwind / blended face values of the plain-load sweep
+    with tempfile.TemporaryDirectory() as d:
+        for sub, name in (("sphere", "hydro-sphere"), ("sphere", "advection-sphere"), ("convection", "advection-leveque-ab4"),
+                          ("convection", "transport-scalar"), ("convection", "transport-wave2d")):
+            c = os.path.join(d, name)
+            shutil.copytree(os.path.join(ROOT, "tests", "golden", sub, name), c)
+            ok &= run(host.Solver.open_case(c), 5, f"{sub}/{name}")
     print("SANITIZE_DONE", "OK" if ok else "NOT FINITE", flush=True)
     sys.exit(0 if ok else 1)
 
