@@ -173,8 +173,8 @@ int nsem_set_sphere(nsem_ctx* ctx, double radius);
  * forward-Euler stage.  Resets the history.  nsem_euler_step does not take it: no euler example asks for a multi-step scheme. */
 int nsem_set_ab_order(nsem_ctx* ctx, int order);
 /* Controls::convection_scheme as the convection app's divf reads it (src/field/field.h:3427-3437): 0 RUSANOV (default), 1 CDS, 2 UDS (the
- * upwind side by the sign of flx(U)), 3 BLENDED (blend_factor * CDS + (1 - blend_factor) * UDS).  Conforming meshes; the euler step is
- * RUSANOV only. */
+ * upwind side by the sign of flx(U)), 3 BLENDED (blend_factor * CDS + (1 - blend_factor) * UDS), on conforming and on 2:1 faces; the
+ * euler step is RUSANOV only. */
 int nsem_set_convection_scheme(nsem_ctx* ctx, int scheme, double blend_factor);
 int nsem_set_convection(nsem_ctx* ctx, int problem_init, double etime, long first_step);
 int nsem_convection_step(nsem_ctx* ctx, int nsteps);

@@ -1473,6 +1473,7 @@ static cudaError_t launch_mortar(const nsem_ctx* c, const KParams& P, int phase)
     std::memset(&M, 0, sizeof M);
     M.nGroups = c->nMortarGroups;
     M.NX = c->NX; M.NY = c->NY; M.NZ = c->NZ; M.visc = P.visc;
+    M.conv_scheme = P.conv_scheme; M.blend = P.blend;
     M.T0 = P.T0; M.nu = P.nu; M.iPr = P.iPr; M.gammaR = P.gamma * P.R;
     std::memcpy(M.W, c->W, sizeof M.W);
     M.groups = c->mortarGroups.p; M.subs = c->mortarSubs.p;
@@ -1884,7 +1885,6 @@ extern "C" int nsem_convection_step(nsem_ctx* c, int nsteps) {
         P.visc = 0; P.buoyancy = 0;
         P.conv_scheme = c->conv_scheme; P.blend = c->conv_blend;
         const bool plain = (c->conv_scheme != 0);          // the other face values live in the plain-load sweep only
-        if (plain && c->nMortarGroups) { c->err = "nsem_convection_step: CDS / UDS / BLENDED face values are not built for non-conforming (2:1) faces"; return 1; }
         const bool keep_v2 = c->use_v2, keep_v4 = c->use_v4;
         if (plain) { c->use_v2 = false; c->use_v4 = false; }
         struct Restore { nsem_ctx* c; bool v2, v4; ~Restore() { c->use_v2 = v2; c->use_v4 = v4; } } restore{c, keep_v2, keep_v4};

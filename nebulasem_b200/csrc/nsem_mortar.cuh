@@ -43,6 +43,8 @@ struct MortarGroup {
 struct MortarParams {
     uint32_t nGroups;
     int NX, NY, NZ, visc;
+    int conv_scheme;          // face value of the mass flux: 0 RUSANOV, 1 CDS, 2 UDS, 3 BLENDED (KParams::conv_scheme; the convection app only)
+    double blend;
     double T0, nu, iPr, gammaR;
     double W[3][MAXN];
     const MortarGroup* groups;
@@ -139,6 +141,18 @@ __global__ void __launch_bounds__(MORTAR_MAXF) mortarA_kernel(const __grid_const
 #pragma unroll
             for (int f = 0; f < 3; f++) cq[f] = fu[f] * 0.5 + pc[5 + f] * 0.5;
             cq[3] = fth * 0.5 + pc[8] * 0.5;
+            if (M.conv_scheme != 0) {
+                // CDS / UDS / BLENDED (divf, field.h:3427-3437): the upwind side by the sign of flx(U) = cds(U).fN on the sub-facet, its two
+                // sides being the fine node and the projected coarse trace (uds over scatter_non_conforming, field.h:2904-2917)
+                const double F = cq[0] * N[0] + (cq[1] * N[1] + cq[2] * N[2]);
+                const bool ownerSide = (F >= 0);
+                const bool takeFine = (ownerSide == fineOwns);
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    const double central = fF[d] * 0.5 + pc[d] * 0.5, upwind = takeFine ? fF[d] : pc[d];
+                    flux[d] = (M.conv_scheme == 1) ? central : (M.conv_scheme == 2 ? upwind : M.blend * central + (1.0 - M.blend) * upwind);
+                }
+            }
             // fine side: the flux as it is
             double* o = M.outA + (size_t)sb.block * MORTAR_NA * MORTAR_MAXF + t;
             o[0] = sgF * (flux[0] * N[0] + flux[1] * N[1] + flux[2] * N[2]);

@@ -36,6 +36,8 @@ def main():
     make("transport-wave2d-uds", "BDF1", example="/root/reference/examples/transport/wave2d", block="simple", edits={"convection_scheme": "UDS"})
     make("transport-wave2d-cds", "BDF1", example="/root/reference/examples/transport/wave2d", block="simple", edits={"convection_scheme": "CDS"})
     make_amr()
+    # examples/transport/wave2d-amr-dg as shipped: UDS face values (also on the 2:1 faces), AB1, regrid every dump
+    make_amr("transport-wave2d-amr", 40, 20, example="/root/reference/examples/transport/wave2d-amr-dg", scheme="AB1", block="simple")
     # the same on the cubed sphere: examples/atmo/advection-sphere-amr (Lauritzen's wind, BDF1, 2-D refinement that never splits the radial
     # axis) at 8 x 8 cells per panel, order 2, one 12-day period in 480 steps; dumps every 20 steps, regrids before step 1 and after dump 12
     make_amr("advection-sphere-amr", 480, 20, example="/root/reference/examples/atmo/advection-sphere-amr", divisions=(8, 8, 1),
@@ -81,7 +83,7 @@ if __name__ == "__main__":
     main()
 
 
-def make_amr(name="advection-leveque-amr", nsteps=40, interval=20, example=EX, divisions=None, edits=None, amr_step=1, scheme="AB2"):
+def make_amr(name="advection-leveque-amr", nsteps=40, interval=20, example=EX, divisions=None, edits=None, amr_step=1, scheme="AB2", block=None):
     """An AMR RUN of the convection app: the example exactly as it ships (AB2, amr_step 1, max_level 2, buffer_zone 2) for `nsteps` steps with
     a dump (and a regrid) every `interval`.  Kept: the case before the run, the cells of the grid of every regrid (centroid, volume), the
     scalar after the first `interval` steps (the same run stopped there) and at the end, with the node positions of their grids (oracle
@@ -94,7 +96,7 @@ def make_amr(name="advection-leveque-amr", nsteps=40, interval=20, example=EX, d
     shutil.copytree(example, d)
     for f in os.listdir(d):
         os.chmod(os.path.join(d, f), 0o644)
-    block = [f for f in os.listdir(d) if f != "controls" and not f.endswith((".txt", ".sh"))][0]
+    block = block or [f for f in os.listdir(d) if f != "controls" and not f.endswith((".txt", ".sh"))][0]
     if divisions:
         blk = open(os.path.join(d, block)).read()
         blk, cnt = re.subn(r"(?m)^(8\{[^}]*\}\s+linear\s+)3\{\d+ \d+ \d+\}", r"\g<1>3{%d %d %d}" % divisions, blk)
@@ -118,6 +120,9 @@ def make_amr(name="advection-leveque-amr", nsteps=40, interval=20, example=EX, d
     os.makedirs(out)
     for f in ("controls", "grid_0.bin", "U0.txt", "T0.txt"):
         shutil.copy(os.path.join(d, f), os.path.join(out, f))
+    for f in os.listdir(d):          # only the case files travel into the runs (a second block file must not be picked up)
+        if f not in ("controls", "grid_0.bin", "U0.txt", "T0.txt"):
+            os.remove(os.path.join(d, f))
     half = d + "_half"
     shutil.copytree(out, half)
     # the wind's period is end_step * dt, so the run stopped at the first dump keeps end_step and gets a kill switch instead: run the

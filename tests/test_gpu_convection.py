@@ -147,14 +147,17 @@ def test_convection_binary_matches_the_reference_binary(tmp_path, scheme):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case,world", [("advection-leveque-amr", 1), ("advection-leveque-amr", 2), ("advection-sphere-amr", 1), ("advection-sphere-amr", 2)])
+@pytest.mark.parametrize("case,world", [("advection-leveque-amr", 1), ("advection-leveque-amr", 2), ("advection-sphere-amr", 1), ("advection-sphere-amr", 2),
+                                        ("transport-wave2d-amr", 1), ("transport-wave2d-amr", 2)])
 def test_convection_amr_run_matches_the_reference_run(tmp_path, case, world):
     """examples/atmo/advection-leveque exactly as it ships -- AB2, amr_step 1, max_level 2, buffer_zone 2, the wind re-evaluated every step --
     for 40 steps with a dump and a regrid every 20, through `convection ./controls` on one and on two partitions, against the same run of the
     UNMODIFIED reference binary (tests/golden/convection/advection-leveque-amr/, make_convection_golden.py: 256 -> 412 -> 568 cells).  The
     residual history starts over on every new mesh, as the reference's does with its new field objects; cells matched by centroid, nodes by
     position.  advection-sphere-amr: the same on the cubed sphere (examples/atmo/advection-sphere-amr at 8 x 8 cells per panel, order 2:
-    Lauritzen's wind over one period in 480 steps, regrids before step 1 and after dump 12: 384 -> 726 -> 384 cells)."""
+    Lauritzen's wind over one period in 480 steps, regrids before step 1 and after dump 12: 384 -> 726 -> 384 cells).  transport-wave2d-amr:
+    examples/transport/wave2d-amr-dg as shipped -- UDS face values, also on the 2:1 faces (the mortar kernel picks the upwind side between
+    the fine node and the projected coarse trace), AB1: 128 -> 212 -> 188 cells."""
     import shutil
     import subprocess
 
