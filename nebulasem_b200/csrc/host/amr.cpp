@@ -671,7 +671,7 @@ void EulerSolver::copy_run_parameters(EulerSolver& n) const {
     n.mass0 = mass0; n.energy0 = energy0; n.volume0 = volume0;
     n.vtk_fields = vtk_fields; n.vtk_cell_value = vtk_cell_value; n.vtk_polyhedral = vtk_polyhedral; n.vtk_on_dump = vtk_on_dump;
     n.launch_nonce = launch_nonce;
-    n.conv_scheme = conv_scheme; n.blend_factor = blend_factor;
+    n.conv_scheme = conv_scheme; n.blend_factor = blend_factor; n.cyclic_patches = cyclic_patches;
     n.convection = convection; n.conv_init = conv_init; n.scalar0 = scalar0; n.conv_end_step = conv_end_step;
     n.topo.spherical = topo.spherical; n.topo.sphere_radius = topo.sphere_radius; n.topo.sphere_height = topo.sphere_height;
 }

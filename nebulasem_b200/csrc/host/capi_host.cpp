@@ -146,6 +146,7 @@ nsemh_solver* nsemh_synthetic_part(const char* kind_, int nx, int ny, int nz, in
             s.nop[0] = s.nop[1] = order; s.nop[2] = 0;
             s.T0 = 1; s.P0 = 1; s.cp = 3.5; s.cv = 2.5; s.viscosity = 0; s.dt = 0.0005;
             s.gravity = Vec3{0, -9.80606, 0}; s.diffusion = false; s.buoyancy = false; s.problem_init = "ISENTROPIC_VORTEX";
+            s.cyclic_patches = {{"inx", "outx"}, {"iny", "outy"}};       // a decomposition keeps the owner cells of paired periodic faces together
             mesh(box_grid(n, lo, hi, {"inx", "outx", "iny", "outy", "delete", "delete"}));
             std::vector<BCond> cyc;
             const char* pr[4][2] = {{"inx", "outx"}, {"outx", "inx"}, {"iny", "outy"}, {"outy", "iny"}};

@@ -163,7 +163,15 @@ void EulerSolver::set_mesh_partition(const Grid& global, int rank_, int nranks_,
     const std::vector<u32> fmc = mortar_flags(global);
     lap("mortar flags of the global grid");
     const bool amr = std::any_of(fmc.begin(), fmc.end(), [](u32 v) { return v != 0; });
-    const std::vector<u32> part = partition_cells(global, nranks, type, nxyz, amr ? &fmc : nullptr);
+    // face j of a CYCLIC patch is paired with face j of its neighbor patch (field.h:2662-2664, 2683-2687): their owner cells stay together
+    std::vector<std::array<u32, 2>> together;
+    for (const auto& pr : cyclic_patches) {
+        auto a = global.boundaries.find(pr[0]), b = global.boundaries.find(pr[1]);
+        if (a == global.boundaries.end() || b == global.boundaries.end() || a->second.size() != b->second.size())
+            throw Error("CYCLIC patches " + pr[0] + "/" + pr[1] + " missing or of different size");
+        for (size_t j = 0; j < a->second.size(); j++) together.push_back({a->second[j], b->second[j]});
+    }
+    const std::vector<u32> part = partition_cells(global, nranks, type, nxyz, amr ? &fmc : nullptr, &together);
     lap("partition_cells");
     if (verbose && rank == 0) {
         // quality of the partition: cells and cut faces per part (the step time follows the largest of both)
@@ -210,8 +218,23 @@ void EulerSolver::load_mesh(int step_) {
     forest_file = dir + "/" + meshName + "_" + std::to_string(step) + ".forest";
     // one process per partition: every rank decomposes the same global grid the same way (Prepare::decomposeMesh does it
     // once on rank 0 and hands the parts over through grid<r>/ files, field.cpp:1086-1443) and keeps its own part
-    if (nranks > 1) set_mesh_partition(g, rank, nranks, decomp_type, decomp_n);
-    else { nGlobalCells = g.nCells(); set_mesh(g); }
+    if (nranks > 1) {
+        // the CYCLIC pairs are in the field files, which are read after the mesh: look at their boundary sections first
+        cyclic_patches.clear();
+        const std::string s = std::to_string(step_);
+        for (const char* f : {"U", "T", "p", "rho"}) {
+            struct stat st;
+            if (::stat((dir + "/" + f + s + ".txt").c_str(), &st) != 0 && ::stat((dir + "/" + f + s + ".bin").c_str(), &st) != 0) continue;
+            const FieldFile ff = read_field(dir + "/" + f + s, std::string(f) == "U" ? 3 : 1);
+            for (const BCond& b : ff.bcs) {
+                if (b.type != "CYCLIC") continue;
+                bool seen = false;
+                for (const auto& pr : cyclic_patches) seen |= (pr[0] == b.patch || pr[1] == b.patch);
+                if (!seen) cyclic_patches.push_back({b.patch, b.neighbor});
+            }
+        }
+        set_mesh_partition(g, rank, nranks, decomp_type, decomp_n);
+    } else { nGlobalCells = g.nCells(); set_mesh(g); }
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -82,7 +82,7 @@ Grid box_grid(const int n[3], const double lo[3], const double hi[3], const std:
 // face_mortar (gFMC in the grid's own face numbering, or nullptr): METIS edge weight 1000 on non-conforming faces so that
 // AMR families stay together (field.cpp:1037-1047); any method that still cuts one is refused (field.cpp:1215-1220)
 std::vector<u32> partition_cells(const Grid& g, int nparts, const std::string& method, const int nxyz[3],
-                                 const std::vector<u32>* face_mortar = nullptr);
+                                 const std::vector<u32>* face_mortar = nullptr, const std::vector<std::array<u32, 2>>* together = nullptr);
 // gFMC of a grid in its own face numbering (addBoundaryCells + fixHexCells only); all zero on a conforming grid
 std::vector<u32> mortar_flags(const Grid& g);
 struct Partition {
@@ -311,6 +311,8 @@ struct EulerSolver {
     void apply_bcs(std::vector<double>& f, int comps, std::vector<BCond>& bcs);   // applyExplicitBCs on the host
     std::string conv_scheme = "RUSANOV";  // Controls::convection_scheme / blend_factor (field.cpp:56, 520-527)
     double blend_factor = 0.2;
+    // (patch, neighbor) of the CYCLIC conditions of the case: a decomposition keeps the owner cells of paired faces in one part
+    std::vector<std::array<std::string, 2>> cyclic_patches;
     long conv_end_step = 0;               // the whole run's end_step while run_case shortens end_step to the next regrid (the wind's period)
     void arm_wind(long first_step);       // convection: nsem_set_convection with the step the next call starts with
     void mark_unlisted_patches();         // patches rho has no condition for (NSEM_BC_UNLISTED)

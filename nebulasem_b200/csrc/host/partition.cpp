@@ -42,29 +42,37 @@ static std::vector<u32> partition_cells_raw(const Grid& g, int nparts, const std
 
 // Cells joined by non-conforming faces form clusters that must stay in one part (both sides of a mortar are evaluated by one rank,
 // field.cpp:1215-1220): root[c] = the smallest cell index of c's cluster.
-static std::vector<u32> mortar_clusters(const Grid& g, const std::vector<u32>& face_mortar) {
+static std::vector<u32> mortar_clusters(const Grid& g, const std::vector<u32>* face_mortar, const std::vector<std::array<u32, 2>>* together) {
     std::vector<u32> foc, fnc, root(g.nCells());
     face_cells(g, foc, fnc);
     for (u32 c = 0; c < g.nCells(); c++) root[c] = c;
     auto find = [&](u32 c) { while (root[c] != c) { root[c] = root[root[c]]; c = root[c]; } return c; };
-    for (u32 f = 0; f < g.nFacets(); f++)
-        if (face_mortar[f] != 0 && fnc[f] != MAX_INT) {
-            const u32 a = find(foc[f]), b = find(fnc[f]);
-            if (a != b) root[std::max(a, b)] = std::min(a, b);
-        }
+    auto join = [&](u32 x, u32 y) {
+        const u32 a = find(x), b = find(y);
+        if (a != b) root[std::max(a, b)] = std::min(a, b);
+    };
+    if (face_mortar)
+        for (u32 f = 0; f < g.nFacets(); f++)
+            if ((*face_mortar)[f] != 0 && fnc[f] != MAX_INT) join(foc[f], fnc[f]);
+    // pairs of FACES whose owner cells must share a part: the two sides of a CYCLIC pair of patches (the ghost value of one is the owner
+    // value at the other, applyExplicitBCs field.h:2683-2687 -- a local read)
+    if (together)
+        for (const auto& pr : *together)
+            if (pr[0] < g.nFacets() && pr[1] < g.nFacets() && foc[pr[0]] != MAX_INT && foc[pr[1]] != MAX_INT) join(foc[pr[0]], foc[pr[1]]);
     for (u32 c = 0; c < g.nCells(); c++) root[c] = find(c);
     return root;
 }
 
 std::vector<u32> partition_cells(const Grid& g, int nparts, const std::string& method, const int nxyz[3],
-                                 const std::vector<u32>* face_mortar) {
+                                 const std::vector<u32>* face_mortar, const std::vector<std::array<u32, 2>>* together) {
     std::vector<u32> part;
-    if (face_mortar && nparts > 1) {
+    if (together && together->empty()) together = nullptr;
+    if ((face_mortar || together) && nparts > 1) {
         // the reference weighs mortar faces 1000 in the METIS graph (field.cpp:1037-1047), which makes cutting one unlikely but not
         // impossible (a tight balance on a few hundred cells does it).  Here the clusters are contracted first: METIS sees one vertex of
         // weight |cluster| per cluster (the edge weights count the faces between clusters), the other methods place a cluster where its
         // first cell goes -- a non-conforming face cannot be cut
-        const std::vector<u32> root = mortar_clusters(g, *face_mortar);
+        const std::vector<u32> root = mortar_clusters(g, face_mortar, together);
         if (method == "METIS") part = partition_cells_raw(g, nparts, method, nxyz, &root);
         else {
             part = partition_cells_raw(g, nparts, method, nxyz, nullptr);

@@ -30,6 +30,10 @@ def main():
     dist.broadcast(uid, 0)
     uid_bytes = bytes(uid.cpu().tolist())
     kind, n, order, nsteps = "bubble3d", (4, 4, 4), 3, 12
+    if os.environ.get("MP_CHECK_KIND"):        # e.g. "vortex": the doubly periodic isentropic vortex (CYCLIC pairs kept inside a part)
+        kind = os.environ["MP_CHECK_KIND"]
+        if kind == "vortex":
+            n, order, nsteps = (6, 6, 1), 4, 20
     if os.environ.get("MP_CHECK_MESH"):        # e.g. "16,8,8,4,20": elements per direction, order, steps
         v = [int(x) for x in os.environ["MP_CHECK_MESH"].split(",")]
         n, order, nsteps = tuple(v[:3]), v[3], v[4]

@@ -46,7 +46,7 @@ def make_case(tmp_path, name):
     return a
 
 
-@pytest.mark.parametrize("name,world", [("bubble3d", 2), ("bubble3d", 3), ("srtb3d_amr", 2)])
+@pytest.mark.parametrize("name,world", [("bubble3d", 2), ("bubble3d", 3), ("srtb3d_amr", 2), ("vortex", 2), ("vortex", 3)])
 def test_partitioned_setup_merges_to_the_single_process_fields(tmp_path, name, world):
     a = make_case(tmp_path, name)
     b = str(tmp_path / (name + "_n"))

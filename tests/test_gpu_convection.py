@@ -148,7 +148,7 @@ def test_convection_binary_matches_the_reference_binary(tmp_path, scheme):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("case,world", [("advection-leveque-amr", 1), ("advection-leveque-amr", 2), ("advection-sphere-amr", 1), ("advection-sphere-amr", 2),
-                                        ("transport-wave2d-amr", 1)])     # its CYCLIC in/out patches end up on different ranks: one partition
+                                        ("transport-wave2d-amr", 1), ("transport-wave2d-amr", 2)])
 def test_convection_amr_run_matches_the_reference_run(tmp_path, case, world):
     """examples/atmo/advection-leveque exactly as it ships -- AB2, amr_step 1, max_level 2, buffer_zone 2, the wind re-evaluated every step --
     for 40 steps with a dump and a regrid every 20, through `convection ./controls` on one and on two partitions, against the same run of the

@@ -216,9 +216,10 @@ def test_pipelined_transfers_match_blocking_ones():
     b.close()
 
 
-@pytest.mark.parametrize("decomp", ["METIS", "XYZ"])
+@pytest.mark.parametrize("decomp", ["METIS", "XYZ", "METIS-periodic"])
 def test_two_partitions_equal_one_partition(decomp):
-    """One METIS/XYZ partition per GPU with the NCCL face-trace halo == the single-partition run."""
+    """One METIS/XYZ partition per GPU with the NCCL face-trace halo == the single-partition run.  METIS-periodic: the doubly
+    periodic isentropic vortex -- the owner cells of paired CYCLIC faces are contracted before METIS, so the periodic copy stays a local read."""
     import subprocess
     import sys
 
@@ -228,7 +229,11 @@ def test_two_partitions_equal_one_partition(decomp):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29517", os.path.join(root, "tests", "mp_gpu_check.py"), decomp]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    env = dict(os.environ)
+    if decomp == "METIS-periodic":
+        cmd[-1] = "METIS"
+        env["MP_CHECK_KIND"] = "vortex"
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     print(out.stdout[-3000:], out.stderr[-3000:])
     assert out.returncode == 0 and "MP_CHECK_OK" in out.stdout
 
