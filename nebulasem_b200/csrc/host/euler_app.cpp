@@ -545,6 +545,7 @@ void EulerSolver::setup() {
         }
     }
     // ait.start() branch, euler.cpp:133-146
+#pragma omp parallel for schedule(static)
     for (uint64_t i = 0; i < gA; i++) p[i] += p_ref[i];
     bc_p_ref = scale_bcs(bc_p);
     apply_bcs(p_ref, 1, bc_p_ref);
@@ -554,16 +555,29 @@ void EulerSolver::setup() {
     apply_bcs(rho, 1, bc_rho);
     bc_rho_ref = scale_bcs(bc_rho);
     apply_bcs(rho_ref, 1, bc_rho_ref);
+#pragma omp parallel for schedule(static)
     for (uint64_t i = 0; i < gA; i++) p[i] -= p_ref[i];
     mark_unlisted_patches();
-    // totals (euler.cpp:164-176)
+    // totals (euler.cpp:164-176): one pow per node -- fixed chunks summed in parallel, the chunk sums added in order, so the result does not
+    // depend on the number of threads
     mass0 = energy0 = volume0 = 0;
-    for (uint64_t i = 0; i < gB; i++) {
-        const double sf = rho[i] * geo.cV[i];
-        mass0 += sf;
-        const double e = gh[i] + 0.5 * dot3(&U[i * 3], &U[i * 3]) + std::pow((p[i] + p_ref[i]) / P0, R / cp) * (T[i] + T0) * cv;
-        energy0 += rho[i] * geo.cV[i] * e;
-        volume0 += geo.cV[i];
+    {
+        const uint64_t chunk = 1u << 16, nchunks = (gB + chunk - 1) / chunk;
+        std::vector<double> part(nchunks * 3, 0.0);
+#pragma omp parallel for schedule(static)
+        for (int64_t q = 0; q < (int64_t)nchunks; q++) {
+            double m = 0, e_ = 0, v = 0;
+            const uint64_t i1 = std::min<uint64_t>(gB, (uint64_t)(q + 1) * chunk);
+            for (uint64_t i = (uint64_t)q * chunk; i < i1; i++) {
+                const double sf = rho[i] * geo.cV[i];
+                m += sf;
+                const double e = gh[i] + 0.5 * dot3(&U[i * 3], &U[i * 3]) + std::pow((p[i] + p_ref[i]) / P0, R / cp) * (T[i] + T0) * cv;
+                e_ += rho[i] * geo.cV[i] * e;
+                v += geo.cV[i];
+            }
+            part[q * 3] = m; part[q * 3 + 1] = e_; part[q * 3 + 2] = v;
+        }
+        for (uint64_t q = 0; q < nchunks; q++) { mass0 += part[q * 3]; energy0 += part[q * 3 + 1]; volume0 += part[q * 3 + 2]; }
     }
 }
 
