@@ -198,6 +198,8 @@ int nsem_upload_geopotential(nsem_ctx* ctx, const double* gh);
 /* nsteps iterations of the time-loop body apps/euler/euler.cpp:179-287 (steps 1-8 and 10 of SURVEY 3.2):
  * rho-, U- and T-equations with divf<weak>/gradf<strong>/rusanov/addTemporal<1>/Solve + BCs + halo. */
 int nsem_euler_step(nsem_ctx* ctx, int nsteps);
+/* On one partition of at most 32768 elements and nsteps >= 8 the call captures two steps into a CUDA graph, replays it and returns after
+ * the replays have finished (launch-bound meshes; NSEM_GRAPH=0 keeps plain launches); otherwise it only enqueues. */
 /* applyExplicitBCs(field, true) halos of the set-up phase (euler.cpp:105-146, field.h:2596-2599,2726): fills the
  * inter-partition ghost cells of rho, U, T, p, rho_ref and p_ref from the neighbouring ranks. Collective. */
 int nsem_exchange_state_halos(nsem_ctx* ctx);
