@@ -102,6 +102,41 @@ def main():
     make("acoustic-sphere", "euler", (4, 4, 1), (3, 3, 0), 30, 30)
     # the wind's period is end_step * dt (convection.cpp:48-50,103): the 12 days of the example in 4800 steps, compared after the first 48
     make("advection-sphere", "convection", (4, 4, 1), (3, 3, 0), 48, 216, edits={"time_scheme": "AB1"}, end_step=4800)
+    make_regridded()
+
+
+def make_regridded():
+    """The reference's own regridded cubed sphere: the initial regrid of tests/golden/amr_run/acoustic-sphere-amr-dg (24 cells refined, 2:1
+    faces along the patch) as the reference's euler wrote it, and the SHA-256 of every geometry array its LoadMesh builds on that grid
+    (geomdump) -- calcGeometry's spherical corrections on cells with more than six facets, node placement from merged sides, the mortar
+    flags.  The oracle and the C++ host must reproduce them bit for bit (tests/test_sphere.py)."""
+    import hashlib
+    import json
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "amr_run", "acoustic-sphere-amr-dg")
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "sphere", "acoustic-sphere-regridded")
+    d = os.path.join(tempfile.mkdtemp(prefix="sphere_nc_"), "case")
+    shutil.copytree(src, d)
+    os.remove(os.path.join(d, "expected.npz"))
+    ctl = open(os.path.join(d, "controls")).read()
+    open(os.path.join(d, "controls"), "w").write(re.sub(r"(?m)^(\s*)end_step\s+\d+", r"\g<1>end_step 10", ctl))
+    r = subprocess.run([run_ref.ref_bin("euler"), "./controls"], cwd=d, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "Refining 24 Coarsening 0" in r.stdout, r.stdout[-1500:] + r.stderr[-500:]
+    ctl = re.sub(r"(?m)^\s*amr_step\s+\d+\s*\n", "", ctl)                  # a fixed-mesh case on the regridded grid
+    open(os.path.join(d, "controls"), "w").write(ctl)
+    g = subprocess.run([run_ref.ref_bin("geomdump"), "./controls", "geom.bin", "euler"], cwd=d, capture_output=True, text=True, timeout=600)
+    assert g.returncode == 0, g.stdout[-1000:] + g.stderr[-1000:]
+    G = refio.read_geomdump(os.path.join(d, "geom.bin"))
+    shutil.rmtree(out, ignore_errors=True)
+    os.makedirs(out)
+    for f in ("controls", "grid_0.bin", "rho0.txt", "U0.txt", "T0.txt", "p0.txt"):
+        shutil.copy(os.path.join(src if f.endswith(".txt") else d, f), os.path.join(out, f))
+    sums = {"dims": [int(x) for x in G["dims"][:11]]}
+    for k in ("cC", "cV", "Jinv", "fN", "fC", "fI", "gFC", "gFN", "gCV", "gCC"):
+        sums[k] = hashlib.sha256(np.ascontiguousarray(G[k], dtype="<f8").tobytes()).hexdigest()
+    for k in ("FO", "FN", "gFMC", "gFOC", "gFNC"):
+        sums[k] = hashlib.sha256(np.ascontiguousarray(G[k], dtype="<i8").tobytes()).hexdigest()
+    json.dump(sums, open(os.path.join(out, "geom_sha256.json"), "w"), indent=1)
+    print("acoustic-sphere-regridded", sums["dims"])
 
 
 if __name__ == "__main__":

@@ -166,6 +166,36 @@ def test_regrid_of_the_shell_tags_and_splits_like_the_reference(tmp_path):
     assert np.abs(cv[oa] / exp["grid0_CV"][ob] - 1).max() <= 1e-11
 
 
+def test_regridded_shell_geometry_is_bit_identical_to_the_reference(tmp_path):
+    """The reference's OWN regridded cubed sphere (24 cells refined, 2:1 faces; tests/golden/sphere/acoustic-sphere-regridded, by
+    make_sphere_golden.make_regridded) and the SHA-256 of every geometry array its LoadMesh builds there: spherical corrections of calcGeometry
+    on cells with more than six facets, node placement from merged sides, mortar flags.  Oracle and C++ host reproduce all of them bit for bit."""
+    import hashlib
+    import json
+
+    from nebulasem_b200 import host
+    src = os.path.join(GOLD, "acoustic-sphere-regridded")
+    sums = json.load(open(os.path.join(src, "geom_sha256.json")))
+    sha = lambda a, dt: hashlib.sha256(np.ascontiguousarray(np.asarray(a).ravel(), dtype=dt).tobytes()).hexdigest()
+    orc = ocase.load_case(src, exact_order=False)
+    g = orc.g
+    assert [g.basis.NPX, g.basis.NPY, g.basis.NPZ, g.basis.NP, g.basis.NPF, g.nBCS] == sums["dims"][:6]
+    assert np.count_nonzero(np.asarray(g.topo.FMC)) > 0
+    for nm, arr in (("cC", g.cC), ("cV", g.cV), ("Jinv", g.Jinv), ("fN", g.fN), ("fC", g.fC), ("fI", g.fI), ("gFN", g.topo.FNv), ("gFC", g.topo.FC),
+                    ("gCV", g.topo.CV), ("gCC", g.topo.CC)):
+        assert sha(arr, "<f8") == sums[nm], "oracle " + nm
+    for nm, arr in (("FO", g.FO), ("FN", g.FN), ("gFMC", g.topo.FMC), ("gFOC", g.topo.FOC), ("gFNC", g.topo.FNC)):
+        assert sha(arr, "<i8") == sums[nm], "oracle " + nm
+    d = str(tmp_path / "case")
+    shutil.copytree(src, d)
+    s = host.Solver.open_case(d)
+    for nm, key in (("cC", "cC"), ("cV", "cV"), ("Jinv", "Jinv"), ("fN", "fN"), ("fC", "fC"), ("fI", "fI"), ("faceNormal", "gFN"), ("faceCenter", "gFC")):
+        assert sha(s.f64(nm), "<f8") == sums[key], "host " + nm
+    for nm, key in (("FO", "FO"), ("FN", "FN"), ("faceMortar", "gFMC"), ("faceOwner", "gFOC"), ("faceNeigh", "gFNC")):
+        assert sha(s.u32(nm).astype(np.int64), "<i8") == sums[key], "host " + nm
+    s.close()
+
+
 def test_partitions_of_a_regridded_shell_keep_the_face_geometry(tmp_path):
     """The curved-element corrections visit entries 2..5 of a cell's facet list (mesh.cpp:529); a further sub-facet of a split side gets its
     area and centre from the cell on its other side -- which a partition may not hold.  Then the cell that does hold it applies them, so the
