@@ -149,19 +149,20 @@ static std::vector<u32> partition_cells_raw(const Grid& g, int nparts, const std
         if ((int)nvx < nparts) throw Error("decomposition: " + std::to_string(nvx) + " clusters of cells joined by non-conforming faces cannot fill " + std::to_string(nparts) + " parts");
         // edges between different vertices, parallel faces merged into one weighted edge
         std::vector<std::pair<uint64_t, int64_t>> ed;
-        ed.reserve((size_t)g.nFacets() * 2);
-        for (u32 f = 0; f < g.nFacets(); f++)
-            if (fnc[f] != MAX_INT && vid[foc[f]] != vid[fnc[f]]) {
-                const u32 a = vid[foc[f]], b = vid[fnc[f]];
-                ed.push_back({((uint64_t)a << 32) | b, 1});
-                ed.push_back({((uint64_t)b << 32) | a, 1});
-            }
-        std::sort(ed.begin(), ed.end());
+        if (cluster_root) {
+            ed.reserve((size_t)g.nFacets() * 2);
+            for (u32 f = 0; f < g.nFacets(); f++)
+                if (fnc[f] != MAX_INT && vid[foc[f]] != vid[fnc[f]]) {
+                    const u32 a = vid[foc[f]], b = vid[fnc[f]];
+                    ed.push_back({((uint64_t)a << 32) | b, 1});
+                    ed.push_back({((uint64_t)b << 32) | a, 1});
+                }
+            std::sort(ed.begin(), ed.end());
+        }
         std::vector<int64_t> deg(nvx + 1, 0), adj, wgt;
         bool weighted = false;
         if (!cluster_root) {
             // conforming grid: the element graph with the neighbours in face order (one edge per face, field.cpp:1010-1047)
-            ed.clear();
             for (u32 f = 0; f < g.nFacets(); f++)
                 if (fnc[f] != MAX_INT) { deg[foc[f] + 1]++; deg[fnc[f] + 1]++; }
             for (u32 c = 0; c < nc; c++) deg[c + 1] += deg[c];
