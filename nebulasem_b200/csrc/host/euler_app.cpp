@@ -123,6 +123,10 @@ void EulerSolver::set_mesh(const Grid& g) {
         if (verbose) std::printf("set_mesh[%d]: %-32s %.3f s\n", rank, what, std::chrono::duration<double>(t1 - t0).count());
         t0 = t1;
     };
+    // Prepare::convertVTK loads with remove_empty = false (prepare.cpp:12): a 2-D cell keeps its two empty faces, the corners of its node
+    // placement are then taken from sides 0/1 instead of the first remaining pair -- the same nodes on a flat mesh, but on the sphere the
+    // radial rescale of the placement depends on that choice (the files of `prepare -vtk` differ from the solver's geometry by a metre)
+    topo.keep_empty = vtk_mode && topo.spherical;
     topo.load(g);
     lap("topology (MeshTopo::load)");
     Basis b(nop);
@@ -436,6 +440,7 @@ void EulerSolver::read_fields(int step) {
         // Only for the initial state: a dump that is not there stays an error
         frho.comps = 1;
         frho.inits.push_back({"uniform", std::vector<double>(1, 0.0)});
+        rho_file_missing = true;
     }
     FieldFile fU = read_field(dir + "/U" + s, 3), fT = read_field(dir + "/T" + s, 1), fp = read_field(dir + "/p" + s, 1);
     if (nranks > 1) {
@@ -814,7 +819,12 @@ void EulerSolver::write_vtk(int index) const {
     }
     std::vector<VtkField> fl;
     for (const auto& name : vtk_fields) {
-        if (name == "rho") fl.push_back({name, 1, rho.data()});
+        if (convection) {                                  // the scalar T lives in the rho slot; rho and p are not fields of that app
+            if (name == "T") fl.push_back({name, 1, rho.data()});
+            else if (name == "U") fl.push_back({name, 3, U.data()});
+            continue;
+        }
+        if (name == "rho") { if (!rho_file_missing) fl.push_back({name, 1, rho.data()}); }
         else if (name == "U") fl.push_back({name, 3, U.data()});
         else if (name == "T") fl.push_back({name, 1, T.data()});
         else if (name == "p") fl.push_back({name, 1, p.data()});

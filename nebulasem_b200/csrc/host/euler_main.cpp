@@ -158,6 +158,7 @@ int main(int argc, char* argv[]) {
         if (to_vtk) {
             if (rank != 0) return 0;                       // the merged dumps are global: one process converts them
             rank = 0; world = 1;
+            s.vtk_mode = true;
             s.read_controls(dir);
             std::printf("Converting result to VTK format.\n");
             for (int k = vtk_start; k < vtk_stop; k++) {

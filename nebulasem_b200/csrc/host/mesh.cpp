@@ -635,9 +635,11 @@ void MeshTopo::load(const Grid& g) {
     fix_hex_cells();
     if (spherical && !no_extrude) extrude();
     calc_geometry();
-    std::vector<u32> del = boundaries["delete"];
-    boundaries.erase("delete");
-    remove_boundary(del);
+    if (!keep_empty) {
+        std::vector<u32> del = boundaries["delete"];
+        boundaries.erase("delete");
+        remove_boundary(del);
+    }
     for (auto it = boundaries.begin(); it != boundaries.end();) {
         if (it->second.empty() || it->first.find("interior") != std::string::npos) it = boundaries.erase(it);
         else ++it;

@@ -108,6 +108,7 @@ struct MeshTopo {
     // the two cubes of the WHOLE grid (smallest and largest max|coordinate| over its vertices); when set (shell_h[1] > 0) extrude() uses
     // them instead of this mesh's own extremes, so that a partition that does not reach both shells is projected like the whole mesh
     double shell_h[2] = {0, 0};
+    bool keep_empty = false;             // LoadMesh(step, remove_empty = false), what Prepare::convertVTK loads: the `delete` patch stays
     bool no_extrude = false;             // LoadMesh(step, first, extrude = false): the cube shell as the grid file has it (the AMR tagging's volumes)
     u32 nFacets() const { return (u32)facetStart.size() - 1; }
     u32 nCells() const { return (u32)cellStart.size() - 1; }
@@ -313,6 +314,8 @@ struct EulerSolver {
     double blend_factor = 0.2;
     // (patch, neighbor) of the CYCLIC conditions of the case: a decomposition keeps the owner cells of paired faces in one part
     std::vector<std::array<std::string, 2>> cyclic_patches;
+    bool rho_file_missing = false;        // read_fields found no rho<step> file (a name without a file is not converted, field.cpp:556-590)
+    bool vtk_mode = false;                // `-vtk`: load meshes the way Prepare::convertVTK does (prepare.cpp:9-17)
     long conv_end_step = 0;               // the whole run's end_step while run_case shortens end_step to the next regrid (the wind's period)
     void arm_wind(long first_step);       // convection: nsem_set_convection with the step the next call starts with
     void mark_unlisted_patches();         // patches rho has no condition for (NSEM_BC_UNLISTED)
