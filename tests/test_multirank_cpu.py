@@ -20,6 +20,16 @@ def test_gloo_two_ranks_halo_ordering(decomp):
     assert out.returncode == 0 and "MP_CPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
+@pytest.mark.parametrize("case", ["sphere/hydro-sphere", "sphere/acoustic-sphere-regridded", "srtb3d_amr"])
+def test_gloo_two_ranks_halo_ordering_on_case_directories(case):
+    """The same world-size-2 check on case directories cut as their controls say: the cubed sphere (panel edges, curved elements: shared
+    nodes coincide to rounding), the reference's own regridded sphere (2:1 faces kept inside a part) and a flat regridded 3-D mesh."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29526", os.path.join(ROOT, "tests", "mp_cpu_check.py"), "METIS"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, MP_CPU_CASE=os.path.join(ROOT, "tests", "golden", case)))
+    assert out.returncode == 0 and "MP_CPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
 @pytest.mark.parametrize("decomp,nparts,pxyz", [("METIS", 4, (1, 1, 1)), ("XYZ", 4, (2, 2, 1)), ("CELLID", 3, (1, 1, 1))])
 def test_partitions_tile_the_mesh_and_keep_element_geometry(decomp, nparts, pxyz):
     g = host.Solver.synthetic("bubble3d", 4, 4, 4, 2)
