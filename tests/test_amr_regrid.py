@@ -412,3 +412,26 @@ def test_regrids_of_a_terrain_following_mesh_keep_its_volume():
         levels.update(s.cell_levels().tolist())
     assert 2 in levels and min(counts[1:]) < max(counts)          # deeper levels were reached, cells were removed again
     s.close()
+
+
+@pytest.mark.parametrize("case,n0,n1", [("advection-leveque-amr", 256, 412), ("advection-sphere-amr", 384, 726), ("transport-wave2d-amr", 128, 212)])
+def test_initial_regrid_of_the_convection_examples_is_the_references(tmp_path, case, n0, n1):
+    """The convection app's AMR cases (tests/golden/convection/*-amr, made by the reference's convection binary): the scalar is tagged from
+    the rho slot where this solver keeps it; flat (LeVeque, max_level 2 + buffer_zone 2; wave2d) and on the cubed sphere (tags weighed with the
+    un-projected load's volumes, radial axis never split).  Same cells as the reference's initial regrid, centroid by centroid."""
+    import shutil
+
+    from scipy.spatial import cKDTree
+
+    from nebulasem_b200 import host
+    d = str(tmp_path / case)
+    shutil.copytree(os.path.join(GOLD, "convection", case), d)
+    exp = np.load(os.path.join(d, "expected.npz"))
+    s = host.Solver.open_case(d)
+    assert s.nBCS == n0
+    s.regrid()
+    assert s.nBCS == n1 == exp["half_CC"].shape[0]
+    cc = s.f64("gCC")[: 3 * s.nBCS].reshape(-1, 3)
+    s.close()
+    dist, idx = cKDTree(exp["half_CC"]).query(cc)
+    assert dist.max() <= 1e-12 * max(1.0, np.abs(exp["half_CC"]).max()) and len(np.unique(idx)) == len(idx)
